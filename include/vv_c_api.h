@@ -1,0 +1,215 @@
+/*
+ * vv_c_api.h -- C ABI of libvv_b200.so, the B200-native 3D-LIC renderer.
+ *
+ * The reference (liaoyg/VectorVisualization, "VV/" below) has no plugin/FFI layer; its de-facto
+ * boundary is the public surface of `class Renderer` (VV/renderer.h:28-125) plus the loaders it is
+ * handed (VV/dataset.h:54-240, VV/reader.h, VV/parseArg.h, VV/transferEdit.h), all driven by the
+ * GLUT callbacks in VV/3DLIC.cpp.  Every entry point below names the reference interface it
+ * replaces.  Plain pointers and sizes only; the caller keeps ownership of every host buffer it
+ * passes in (the library copies to the device), output buffers are caller-allocated.
+ *
+ * Conventions
+ *   - all functions return VV_OK (0) or a negative VVStatus; vv_last_error() gives the message
+ *     (the reference prints to stderr and exit(1)s: VV/3DLIC.cpp:690,720 -- this library never exits).
+ *   - images are GL-ordered: row 0 is the BOTTOM row, premultiplied RGBA (what
+ *     Renderer::saveTexture(_imgBufferTex0) writes, VV/renderer.cpp:340-428,1500).
+ *   - volumes are [z][y][x] little-endian, x fastest (VV/reader.cpp:266-305).
+ *   - a handle is not re-entrant; use one handle per GPU / host thread.
+ *   - there is NO CPU fallback: every compute entry point fails with VV_ERR_CUDA without a device.
+ */
+#ifndef VV_C_API_H_
+#define VV_C_API_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VV_API __attribute__((visibility("default")))
+#else
+#define VV_API
+#endif
+
+typedef struct VVRenderer VVRenderer;
+
+typedef enum VVStatus {
+    VV_OK = 0,
+    VV_ERR_INVALID = -1,   /* bad argument / missing input */
+    VV_ERR_IO = -2,        /* file not found / parse error */
+    VV_ERR_CUDA = -3,      /* CUDA runtime error or no device */
+    VV_ERR_STATE = -4      /* call sequence error (e.g. render before data was set) */
+} VVStatus;
+
+/* RenderTechnique, VV/types.h:63-71 (same numeric values) */
+typedef enum VVTechnique {
+    VV_VOLIC_VOLUME = 0,     /* raw vector-field DVR (F1) -- out of scope, rejected */
+    VV_VOLIC_RAYCAST = 1,    /* F2: LIC ray-cast, lic3d_fragment.glsl */
+    VV_VOLIC_SLICING = 2,    /* F3: view-aligned slicing, lic3d_slicing_fragment.glsl */
+    VV_VOLIC_LICVOLUME = 3,  /* F4: ray-cast of the precomputed LIC volume, raycast_lic3d_fragment.glsl */
+    VV_VOLIC_VOLUMEANI = 4   /* F5: F4 with per-tick time interpolation + LIC-volume update */
+} VVTechnique;
+
+/* struct LICParams, VV/types.h:91-109 (same fields, same defaults via vv_default_lic_params) */
+typedef struct VVLicParams {
+    float stepSizeVol;     /* 1/128 */
+    float gradientScale;   /* 30 */
+    float illumScale;      /* 1 */
+    float freqScale;       /* 1 */
+    int   numIterations;   /* 255 */
+    int   stepsForward;    /* 32 */
+    int   stepsBackward;   /* 32 */
+    float stepSizeLIC;     /* 0.01 */
+} VVLicParams;
+
+/* data formats of DatFile, VV/reader.h (DATRAW_*) */
+typedef enum VVDataType { VV_UCHAR = 1, VV_USHORT = 2, VV_FLOAT = 3 } VVDataType;
+
+/* Shader-source choices the reference makes by editing/commenting GLSL. */
+typedef enum VVTfMode { VV_TF_B = 0, VV_TF_A = 1, VV_TF_R = 2, VV_TF_LENGTH = 3, VV_TF_SCALAR = 4 } VVTfMode;
+typedef enum VVGateMode { VV_GATE_ALWAYS = 0, VV_GATE_TF_ALPHA = 1 } VVGateMode;
+
+/* vv_set_option keys */
+typedef enum VVOption {
+    VV_OPT_TF_MODE = 1,            /* VVTfMode; lic3d_fragment.glsl:53-56 */
+    VV_OPT_GATE_MODE = 2,          /* VVGateMode; lic3d_fragment.glsl:59-61 */
+    VV_OPT_NOISE_GATE = 3,         /* 1 (default): scalar band (0.1,0.3) gates the noise, inc_lic.glsl:76-89 */
+    VV_OPT_QUIRK_SCALEVOLINV = 4,  /* 1 (default): reproduce VV/renderer.cpp:941-944 */
+    VV_OPT_QUIRK_LUMINANCE_ALPHA = 5, /* 0 (default): noise .a is the noise value; 1: GL_LUMINANCE .a == 1 (Q7) */
+    VV_OPT_LICVOL_FP16 = 6,        /* 1 (default): LIC volume rounded to fp16 like the RGBA16F target (Q14) */
+    VV_OPT_FIELD_LAYOUT = 7,       /* 0: float4 [z][y][x]; 1 (default): x-pair-packed fp16 (16 B/voxel) */
+    VV_OPT_COUNT_SAMPLES = 8,      /* 1 (default): count ray samples per frame */
+    VV_OPT_LICVOL_SIZE = 9,        /* LIC-volume edge length; 0 (default) = field resolution (reference: 512) */
+    VV_OPT_SPEC_EXP = 10,          /* gl_LightSource[0].spotExponent as int (default 40, VV/illumination.h:52) */
+    VV_OPT_SAMPLE_MAP = 11         /* 1: keep per-pixel ray-sample counts (vv_read_sample_map) */
+} VVOption;
+
+/* ---- lifecycle: Renderer() / init / resize / ~Renderer, VV/renderer.h:31-37 ------------------- */
+VV_API int  vv_create(VVRenderer **out, int cuda_device);
+VV_API void vv_destroy(VVRenderer *r);
+/* Renderer::init(char* defines) / loadGLSLShader(char* defines), VV/renderer.h:34,115: accepts the strings
+ * the keyboard handler passes (VV/3DLIC.cpp:416-436): "#define ILLUM_GRADIENT", "#define ILLUM_MALLO",
+ * "#define ILLUM_ZOECKLER", "#define SPEED_OF_FLOW", NULL/"" = plain illumLIC; selects kernel variants. */
+VV_API int  vv_init(VVRenderer *r, const char *defines);
+VV_API int  vv_load_glsl_shader(VVRenderer *r, const char *defines);
+VV_API int  vv_resize(VVRenderer *r, int width, int height);
+VV_API const char *vv_last_error(void);
+VV_API const char *vv_version(void);
+
+/* ---- technique: setTechnique / updateLICVolume / updateSlices, VV/renderer.h:44,119-123 ------- */
+VV_API int vv_set_technique(VVRenderer *r, int technique);
+VV_API int vv_update_lic_volume(VVRenderer *r);
+VV_API int vv_update_slices(VVRenderer *r);
+
+/* ---- inputs: setVolumeData/setDataTex (VectorDataSet), VV/renderer.h:48-60, VV/dataset.cpp:97-366 --- */
+/* FLOAT3 / UCHAR3 vector field; `next` may be NULL (single time step).  Packs to the RGBA16F texture
+ * contents of VectorDataSet::createTextureIterp (VV/dataset.cpp:290-366, 533-635) on the GPU. */
+VV_API int vv_set_vector_field(VVRenderer *r, const void *data, const void *next, int dtype,
+                               const int dims[3], const float slice_dist[3]);
+/* interpIndex / InterpSize of VectorDataSet (VV/dataset.cpp:202-210, VV/3DLIC.cpp:705): re-packs on the GPU */
+VV_API int vv_set_time_interp(VVRenderer *r, int interp_index, int interp_size);
+/* setScalarTex (VolumeDataSet, VV/dataset.cpp:840-1050); UCHAR or FLOAT scalar */
+VV_API int vv_set_scalar(VVRenderer *r, const void *data, int dtype, const int dims[3]);
+/* setNoiseTex (NoiseDataSet, VV/dataset.cpp:1124-1344): u8 noise; with_gradients = the `-g` flag:
+ * Sobel + 5^3 smoothing + quantise on the GPU (VV/gradient.cpp:190-532) and RGBA8 packing. */
+VV_API int vv_set_noise(VVRenderer *r, const uint8_t *data, const int dims[3], int with_gradients);
+/* NoiseDataSet::loadData fallback (VV/dataset.cpp:1142-1163): n^3 white noise, P(255) = p, mt19937(seed) */
+VV_API int vv_generate_white_noise(VVRenderer *r, int n, uint32_t seed, float p, int with_gradients);
+/* setLICFilter (LICFilter, VV/dataset.cpp:1405-1512): first row of a kernel image / box filter */
+VV_API int vv_set_filter(VVRenderer *r, const uint8_t *row, int width, int channels);
+VV_API int vv_set_box_filter(VVRenderer *r, int width);
+/* setTFrgbTex + setTFalphaOpacTex (TransferEdit, VV/transferEdit.cpp:61-98,480-543): 256 x (R,G,B,A,opacity) */
+VV_API int vv_set_tf(VVRenderer *r, const uint8_t *tf256x5);
+VV_API int vv_set_default_tf(VVRenderer *r);
+/* setLICParams, VV/renderer.h:103 */
+VV_API int vv_set_lic_params(VVRenderer *r, const VVLicParams *p);
+VV_API void vv_default_lic_params(VVLicParams *p);
+/* setCamera (Camera, VV/camera.cpp:42-68): quaternion (x,y,z,w), translation, distance, fovy (deg), near, far */
+VV_API int vv_set_camera(VVRenderer *r, const float quat[4], const float pos[3], float dist, float fovy,
+                         float near_clip, float far_clip);
+/* setLight + updateLightPos (Transform, VV/renderer.cpp:431-466) */
+VV_API int vv_set_light(VVRenderer *r, const float quat[4], float dist);
+VV_API int vv_update_light_pos(VVRenderer *r);
+/* enableLowRes / enableFBO, VV/renderer.h:76-83 */
+VV_API int vv_enable_lowres(VVRenderer *r, int enable);
+VV_API int vv_enable_float_target(VVRenderer *r, int enable);
+VV_API int vv_set_option(VVRenderer *r, int option, int value);
+/* setIllum*Tex (Illumination, VV/illumination.cpp:96-333): tables are generated inside (host, one-off) */
+
+/* ---- frame: Renderer::render(update), VV/renderer.cpp:126-312 -------------------------------- */
+VV_API int vv_render(VVRenderer *r, int update);
+/* stored frame (_imgBufferTex0): RGBA8 (default back-buffer path, Q18) or RGBA32F */
+VV_API int vv_read_rgba8(VVRenderer *r, uint8_t *out, size_t out_bytes);
+VV_API int vv_read_rgba32f(VVRenderer *r, float *out, size_t out_bytes);
+/* displayed frame: background_fragment.glsl:9-16 composited over white */
+VV_API int vv_read_display_rgba8(VVRenderer *r, uint8_t *out, size_t out_bytes);
+/* LIC volume contents (fp32 scalar [d][h][w]) */
+VV_API int vv_read_lic_volume(VVRenderer *r, float *out, size_t out_bytes, int dims_out[3]);
+/* texture read-back (glGetTexImage equivalents, used by the parity tests):
+ * vector texture as float RGBA [z][y][x][4] (the RGBA16F contents), noise texture as L8 or RGBA8 */
+VV_API int vv_read_field_texture(VVRenderer *r, float *out_rgba, size_t out_bytes);
+VV_API int vv_read_noise_texture(VVRenderer *r, uint8_t *out, size_t out_bytes, int *channels);
+/* per-pixel ray-sample counts of the last frame (needs VV_OPT_SAMPLE_MAP = 1 before vv_render) */
+VV_API int vv_read_sample_map(VVRenderer *r, uint32_t *out, size_t out_bytes);
+/* saveFrameBuffer / saveTexture, VV/renderer.h:39-42 */
+VV_API int vv_save_png(VVRenderer *r, const char *path, int displayed);
+VV_API int vv_save_raw(VVRenderer *r, const char *path);
+
+/* ---- measurement ------------------------------------------------------------------------------ */
+VV_API uint64_t vv_last_ray_samples(VVRenderer *r);   /* ray samples of the last vv_render */
+VV_API float    vv_last_kernel_ms(VVRenderer *r);     /* CUDA-event time of the dominant kernel, last frame */
+VV_API int      vv_last_launch_count(VVRenderer *r);  /* kernels launched by the last vv_render */
+VV_API int      vv_synchronize(VVRenderer *r);
+
+/* ---- device-side / multi-GPU hooks (pointers are CUDA device pointers on the handle's device) --- */
+/* sort-first partition: this handle renders only blocks b with b % world == rank (16x16-pixel blocks,
+ * row-major block index).  world = 1 restores the whole image. */
+VV_API int vv_set_partition(VVRenderer *r, int rank, int world);
+/* LIC-volume output slab [z0,z1) computed by vv_update_lic_volume on this handle (input field replicated) */
+VV_API int vv_set_licvol_slab(VVRenderer *r, int z0, int z1);
+/* compact block-major tile buffer of the last frame: n_blocks x 256 x float4 (device pointer) */
+VV_API int vv_get_tile_buffer(VVRenderer *r, void **dev_ptr, int *n_local_blocks, int *n_total_blocks);
+/* assemble a row-major frame on this handle from `world` gathered tile buffers laid out [rank][block][256][4] */
+VV_API int vv_assemble_tiles(VVRenderer *r, const void *gathered_dev, int world);
+VV_API int vv_get_lic_volume_ptr(VVRenderer *r, void **dev_ptr, int dims_out[3]);
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the handle's own stream */
+VV_API int vv_set_stream(VVRenderer *r, void *cuda_stream);
+
+/* ---- loaders: DatFile / NoiseDataSet / LICFilter / TransferEdit / ParseArguments ---------------- */
+typedef struct VVDatInfo {          /* DatFile, VV/reader.cpp:81-263 */
+    char raw_file[512];             /* resolved ObjectFileName (printf pattern for time-dependent sets) */
+    int  resolution[3];
+    float slice_thickness[3];
+    int  data_type;                 /* VVDataType */
+    int  data_dim;                  /* 1 scalar, 3 vector */
+    int  time_begin, time_end;      /* TimeDependent: b e */
+} VVDatInfo;
+VV_API int vv_parse_dat(const char *dat_path, VVDatInfo *out);
+/* DatFile::readRawData(timeStep), VV/reader.cpp:266-305: reads into caller buffer */
+VV_API int vv_read_raw(const VVDatInfo *info, int time_step, void *out, size_t out_bytes);
+VV_API int vv_load_dat(VVRenderer *r, const char *dat_path);          /* vector field (.dat, FLOAT3/UCHAR3) */
+VV_API int vv_load_scalar_dat(VVRenderer *r, const char *dat_path);   /* scalar volume (.dat, UCHAR/FLOAT) */
+VV_API int vv_load_noise(VVRenderer *r, const char *path, int with_gradients); /* 3 x int32 + u8, VV/dataset.cpp:1347-1389 */
+VV_API int vv_load_filter_png(VVRenderer *r, const char *path);       /* LICFilter::loadData, VV/dataset.cpp:1415-1467 */
+VV_API int vv_load_tf_png(VVRenderer *r, const char *name);           /* TransferEdit::loadTF, VV/transferEdit.cpp:224-337 */
+
+typedef struct VVArgs {             /* ParseArguments, VV/parseArg.h:43-51 */
+    char vol_file[512], noise_file[512], tf_file[512], filter_file[512], redirect_file[512], halton_file[512];
+    int  use_gradients, use_lambda2, show_help;
+} VVArgs;
+/* ParseArguments::parse, VV/parseArg.cpp:97-365: returns VV_OK or VV_ERR_INVALID (the reference prints usage
+ * and exit(1)s, VV/3DLIC.cpp:848-852); -h/--help sets show_help instead of exit(0). */
+VV_API int vv_parse_args(int argc, const char *const *argv, VVArgs *out);
+VV_API const char *vv_usage(void);
+
+/* standalone PNG helpers (imageUtils pngRead/pngWrite semantics: 8-bit gray/GA/RGB/RGBA, row 0 = top) */
+VV_API int vv_png_read(const char *path, uint8_t **data, int *w, int *h, int *channels);
+VV_API void vv_free(void *p);
+VV_API int vv_png_write(const char *path, const uint8_t *data, int w, int h, int channels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VV_C_API_H_ */

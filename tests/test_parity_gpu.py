@@ -1,0 +1,383 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances are the north star's: <= 2/255 max per-channel RGBA and PSNR >= 45 dB on the stored RGBA8 frame,
+ray-sample counts exactly equal, LIC volume <= 1e-4 relative, pre-processing bit-exact.
+"""
+import numpy as np
+import pytest
+
+from util import assert_image_parity, render_cuda, LICVOL_REL
+
+pytestmark = pytest.mark.gpu
+
+
+def _scenes():
+    from vectorvisualization_b200 import configs, fields as F
+    import vectorvisualization_b200 as vv
+    S = {}
+    S["cfg1_small"] = lambda: configs.cfg1(n=64, size=160)
+    S["cfg1_close"] = lambda: configs.cfg1(n=32, size=96, camera=F.CAMERA_CLOSE)
+    S["cfg2_small"] = lambda: configs.cfg2(n=64, size=128)
+    S["cfg3_small"] = lambda: configs.cfg3(n=64, size=128)
+    S["cfg3_close"] = lambda: configs.cfg3(n=48, size=96, camera=F.CAMERA_CLOSE)
+    S["cfg4_small"] = lambda: configs.cfg4(n=64, size=96, noise_n=32)
+
+    def lowcontrast():
+        s = configs.cfg1(n=48, size=128)
+        s.params.update(gradientScale=3.0)
+        return s
+    S["cfg1_gradscale3"] = lowcontrast
+
+    def lowcontrast3():
+        s = configs.cfg3(n=48, size=112)
+        s.params.update(gradientScale=4.0, illumScale=1.2)
+        return s
+    S["cfg3_gradscale4"] = lowcontrast3
+
+    def gate_tf():
+        s = configs.cfg2(n=48, size=96)
+        s.gate_mode = vv.GATE_TF_ALPHA
+        s.tf_mode = vv.TF_A
+        s.params.update(gradientScale=5.0)
+        return s
+    S["gate_tf_alpha_tf_a"] = gate_tf
+
+    def tf_r():
+        s = configs.cfg1(n=32, size=80)
+        s.tf_mode = vv.TF_R
+        s.params.update(gradientScale=6.0)
+        return s
+    S["tf_r"] = tf_r
+
+    def tf_scalar():
+        s = configs.cfg1(n=32, size=80)
+        s.tf_mode = vv.TF_SCALAR
+        rng = np.random.RandomState(5)
+        s.scalar = rng.randint(30, 90, size=(16, 16, 16)).astype(np.uint8)   # band (0.1,0.3) = 26..76: partly gated
+        s.params.update(gradientScale=6.0)
+        return s
+    S["tf_scalar_band_gate"] = tf_scalar
+
+    def lowres():
+        s = configs.cfg2(n=48, size=96)
+        s.lowres = 1
+        return s
+    S["lowres_preset"] = lowres
+
+    def sof():
+        s = configs.cfg2(n=48, size=96)
+        s.defines = "#define SPEED_OF_FLOW"
+        s.params.update(gradientScale=6.0)
+        return s
+    S["speed_of_flow"] = sof
+
+    def nogate():
+        s = configs.cfg1(n=32, size=80)
+        s.noise_gate = 0
+        s.scalar = None
+        return s
+    S["noise_gate_off"] = nogate
+
+    def lum():
+        s = configs.cfg1(n=32, size=80)
+        s.quirk_luminance_alpha = 1
+        s.params.update(gradientScale=1.0)
+        return s
+    S["quirk_luminance_alpha"] = lum
+
+    def aniso():
+        s = configs.cfg1(n=32, size=112, camera=F.CAMERA_CLOSE)
+        s.field = np.ascontiguousarray(F.abc_flow(64)[::2, :48, ::1][:24])   # 64 x 48 x 24 voxels (x,y,z)
+        s.slice_dist = (1.0, 1.0, 2.0)
+        s.params.update(gradientScale=6.0)
+        return s
+    S["anisotropic_noncubic"] = aniso
+
+    def aniso_grad():
+        s = configs.cfg3(n=32, size=96, camera=F.CAMERA_CLOSE)
+        s.field = np.ascontiguousarray(F.tornado(48)[:24, :40, :])          # 48 x 40 x 24
+        s.slice_dist = (1.0, 1.5, 2.0)
+        return s
+    S["anisotropic_gradient_q1"] = aniso_grad
+
+    def moved_cam():
+        cam = dict(quat=F.quat_from_axis_angle((0.3, -1.0, 0.2), 110.0), pos=(0.15, -0.1, 0.3), dist=3.0, fovy=35.0)
+        s = configs.cfg3(n=40, size=104, camera=cam)
+        s.light = dict(quat=F.quat_from_axis_angle((1, 0, 0), 40.0), dist=1.0)
+        return s
+    S["rotated_translated_camera_light"] = moved_cam
+
+    def steps():
+        s = configs.cfg2(n=40, size=96)
+        s.params.update(stepsForward=25, stepsBackward=40, stepSizeLIC=0.02, gradientScale=8.0)
+        return s
+    S["steps_25_40"] = steps
+
+    def onestep():
+        s = configs.cfg1(n=32, size=64)
+        s.params.update(stepsForward=1, stepsBackward=1)
+        return s
+    S["steps_1_1"] = onestep
+
+    def timeinterp():
+        s = configs.cfg1(n=32, size=80)
+        s.next_field = F.rankine_vortex(32)
+        s.interp = (3, 10)
+        return s
+    S["time_interpolation"] = timeinterp
+
+    def odd_size():
+        s = configs.cfg1(n=32, size=64, camera=F.CAMERA_CLOSE)
+        s.width, s.height = 75, 41
+        return s
+    S["odd_image_size"] = odd_size
+
+    def fine_step():
+        s = configs.cfg1(n=32, size=72)
+        s.params.update(stepSizeVol=1.0 / 256.0)
+        return s
+    S["raycast_step_256"] = fine_step
+    return S
+
+
+SCENES = list(_scenes().keys()) if True else []
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_raycast_parity(vv, oracle, name):
+    scene = _scenes()[name]()
+    o = oracle.OracleScene(scene)
+    ref, ref_cnt, ref_tot = o.raycast()
+    r, img, img8, cnt, tot = render_cuda(vv, scene)
+    # ray-sample counts must match exactly unless an early-termination decision (src.a > 0.95) flipped
+    mism = int((cnt != ref_cnt).sum())
+    assert mism <= max(1, cnt.size // 20000), "%s: %d pixels with different ray-sample counts" % (name, mism)
+    if mism == 0:
+        assert tot == ref_tot
+    md, ps, mf = assert_image_parity(oracle, img, ref, name)
+    assert np.array_equal(img8, oracle.quantize_rgba8(img))     # the library's RGBA8 store == GL conversion
+    assert ref_tot > 0 or "inside" in name
+    print("%s: samples %d, max8 %d, psnr %.1f dB, float max diff %.3g" % (name, tot, md, ps, mf))
+
+
+def test_layouts_bit_identical(vv):
+    """float4 and x-pair fp16 layouts hold the same RGBA16F values -> identical frames"""
+    from vectorvisualization_b200 import configs
+    s = configs.cfg3(n=48, size=96)
+    _, a, _, ca, ta = render_cuda(vv, s, layout=vv.LAYOUT_PAIR)
+    _, b, _, cb, tb = render_cuda(vv, s, layout=vv.LAYOUT_F4)
+    assert ta == tb and np.array_equal(ca, cb)
+    assert np.array_equal(a, b)
+
+
+def test_camera_inside_box_draws_nothing(vv, oracle):
+    from vectorvisualization_b200 import configs
+    s = configs.cfg1(n=32, size=64)
+    s.camera = dict(quat=(0, 0, 0, 1), pos=(0, 0, 0), dist=0.2, fovy=35.0)   # back faces are culled (VV/renderer.cpp:1099)
+    ref, _, ref_tot = oracle.OracleScene(s).raycast()
+    _, img, _, _, tot = render_cuda(vv, s)
+    assert ref_tot == 0 and tot == 0
+    assert not img.any() and not ref.any()
+
+
+def test_render_without_update_keeps_frame(vv):
+    from vectorvisualization_b200 import configs
+    s = configs.cfg1(n=32, size=64)
+    r, img, _, _, _ = render_cuda(vv, s)
+    r.render(False)    # Renderer::render(false) re-presents the stored frame (VV/renderer.cpp:150-152,228)
+    assert r.lastLaunchCount() > 0
+    assert np.array_equal(r.readRGBA32F(), img)
+    disp = r.readDisplayRGBA8()
+    assert disp.shape == (64, 64, 4)
+
+
+def test_display_background(vv, oracle):
+    from vectorvisualization_b200 import configs
+    s = configs.cfg1(n=32, size=64)
+    r, img, _, _, _ = render_cuda(vv, s)
+    want = oracle.quantize_rgba8(oracle.background(img))      # background_fragment.glsl:9-16
+    assert np.array_equal(r.readDisplayRGBA8(), want)
+
+
+def test_preprocess_bit_exact(vv, oracle):
+    """GPU packing / noise-gradient kernels reproduce the reference's host loops bit for bit"""
+    from vectorvisualization_b200 import fields as F
+    field = F.tornado(40)
+    nxt = F.abc_flow(40)
+    noise = F.white_noise(40, 11, F.SPARSE_P)
+    r = vv.Renderer(0)
+    r.setVectorField(field, nxt)
+    r.setTimeInterp(4, 10)
+    got = r.readFieldTexture((40, 40, 40))
+    want = oracle.pack_vector_field(field, nxt, (4, 10), fp16=True)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    r.setOption(vv.OPT_FIELD_LAYOUT, vv.LAYOUT_F4)
+    got = r.readFieldTexture((40, 40, 40))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # zero vectors -> rgb 0.5 (VV/dataset.cpp:596-602)
+    z = np.zeros((8, 8, 8, 3), np.float32)
+    z[1:] = field[:7, :8, :8]
+    r.setVectorField(z)
+    assert np.array_equal(r.readFieldTexture((8, 8, 8)).view(np.uint32), oracle.pack_vector_field(z).view(np.uint32))
+    # UCHAR3
+    u = np.random.RandomState(3).randint(0, 256, size=(12, 10, 14, 3)).astype(np.uint8)
+    r.setVectorField(u)
+    assert np.array_equal(r.readFieldTexture((12, 10, 14)).view(np.uint32), oracle.pack_vector_field(u).view(np.uint32))
+    # noise gradients (-g): RGBA8 = (quantised smoothed Sobel gradient, noise)
+    r.setNoise(noise, True)
+    got = r.readNoiseTexture((40, 40, 40), 4)
+    want = oracle.pack_noise_rgba(noise, oracle.noise_gradients(noise))
+    assert np.array_equal(got, want)
+    # ragged, non-cubic noise
+    n2 = np.random.RandomState(4).randint(0, 256, size=(9, 17, 12)).astype(np.uint8)
+    r.setNoise(n2, True)
+    assert np.array_equal(r.readNoiseTexture((9, 17, 12), 4), oracle.pack_noise_rgba(n2, oracle.noise_gradients(n2)))
+    # built-in white noise == mt19937 definition
+    r.generateWhiteNoise(24, seed=9, p=F.SPARSE_P)
+    assert np.array_equal(r.readNoiseTexture((24, 24, 24), 1), F.white_noise(24, 9, F.SPARSE_P))
+
+
+@pytest.mark.parametrize("grad", [False, True])
+def test_lic_volume_parity(vv, oracle, grad):
+    """LIC-volume mode vs the fp32 transcription of the shader integrator: <= 1e-4 relative"""
+    from vectorvisualization_b200 import configs
+    from vectorvisualization_b200.configs import apply_scene
+    s = configs.cfg3(n=32, size=64) if grad else configs.cfg2(n=32, size=64)
+    s.licvol_fp16 = 0
+    s.technique = vv.VOLIC_LICVOLUME
+    want = oracle.OracleScene(s).lic_volume()
+    r = vv.Renderer(0)
+    apply_scene(r, s)
+    r.updateLICVolume()
+    got = r.readLICVolume()
+    assert got.shape == want.shape
+    scale = np.maximum(np.abs(want), 1e-3 * np.abs(want).max())
+    rel = np.abs(got - want) / scale
+    print("LIC volume max rel err %.3g (grad=%s)" % (rel.max(), grad))
+    assert rel.max() <= LICVOL_REL
+    # fp16 target (Q14): identical after the same rounding, up to one fp16 ulp where the fp32 values straddle a tie
+    r.setOption(vv.OPT_LICVOL_FP16, 1)
+    r.updateLICVolume()
+    got16 = r.readLICVolume()
+    want16 = want.astype(np.float16).astype(np.float32)
+    assert np.abs(got16 - want16).max() <= np.abs(want).max() * 2.0 ** -10
+
+
+def test_lic_volume_resolution_and_slabs(vv, oracle):
+    """target resolution != field resolution, computed in two z-slabs == computed at once"""
+    from vectorvisualization_b200 import configs
+    from vectorvisualization_b200.configs import apply_scene
+    s = configs.cfg2(n=24, size=64)
+    s.licvol_fp16 = 0
+    s.licvol_size = 40
+    r = vv.Renderer(0)
+    apply_scene(r, s)
+    r.updateLICVolume()
+    full = r.readLICVolume().copy()
+    assert full.shape == (40, 40, 40)
+    want = oracle.OracleScene(s).lic_volume((40, 40, 40))
+    assert (np.abs(full - want) / np.maximum(np.abs(want), 1e-3 * want.max())).max() <= LICVOL_REL
+    r2 = vv.Renderer(0)
+    apply_scene(r2, s)
+    r2.setLICVolumeSlab(0, 17)
+    r2.updateLICVolume()
+    a = r2.readLICVolume().copy()
+    r2.setLICVolumeSlab(17, 40)
+    r2.updateLICVolume()
+    b = r2.readLICVolume()
+    assert np.array_equal(b[17:], full[17:]) and np.array_equal(a[:17], full[:17])
+
+
+def test_volume_raycast_parity(vv, oracle):
+    """raycast_lic3d_fragment.glsl: plain ray-cast over the precomputed LIC volume"""
+    from vectorvisualization_b200 import configs
+    from vectorvisualization_b200.configs import apply_scene
+    for mk in (lambda: configs.cfg2(n=32, size=128), lambda: configs.cfg1(n=32, size=96)):
+        s = mk()
+        s.technique = vv.VOLIC_LICVOLUME
+        s.params.update(gradientScale=4.0)
+        o = oracle.OracleScene(s)
+        lv = o.lic_volume()
+        r = vv.Renderer(0)
+        apply_scene(r, s)
+        r.setOption(vv.OPT_SAMPLE_MAP, 1)
+        r.render(True)
+        got_lv = r.readLICVolume()
+        # ray-cast the oracle against the CUDA LIC volume so that the comparison isolates the ray-cast stage
+        ref, ref_cnt, ref_tot = o.raycast_licvolume(got_lv)
+        img = r.readRGBA32F()
+        cnt = r.readSampleMap()
+        assert int((cnt != ref_cnt).sum()) <= 1
+        assert_image_parity(oracle, img, ref, "volume_raycast")
+        # and end to end (oracle LIC volume)
+        ref2, _, _ = o.raycast_licvolume(lv)
+        assert_image_parity(oracle, img, ref2, "volume_raycast_e2e")
+
+
+def test_partition_invariance_single_gpu(vv):
+    """sort-first block partition: 1 handle == 3 partitioned handles assembled (bit-identical)"""
+    import torch
+    from vectorvisualization_b200 import configs
+    from vectorvisualization_b200.configs import apply_scene
+    from vectorvisualization_b200.dist import device_tensor
+    s = configs.cfg1(n=32, size=64, camera=None)
+    s.width, s.height = 90, 70
+    _, full, _, _, tot = render_cuda(vv, s, sample_map=False)
+    world = 3
+    hs = []
+    total = 0
+    for rank in range(world):
+        r = vv.Renderer(0)
+        apply_scene(r, s)
+        r.setPartition(rank, world)
+        r.render(True)
+        r.synchronize()
+        total += r.lastRaySamples()
+        hs.append(r)
+    ptr, bpr, nb = hs[0].tileBuffer()
+    gathered = torch.empty((world, bpr, 256, 4), dtype=torch.float32, device="cuda")
+    for rank, r in enumerate(hs):
+        p, b, _ = r.tileBuffer()
+        gathered[rank].copy_(device_tensor(p, (b, 256, 4), torch.float32))
+    torch.cuda.synchronize()
+    hs[0].assembleTiles(gathered.data_ptr(), world)
+    img = hs[0].readRGBA32F()
+    assert total == tot
+    assert np.array_equal(img, full)
+
+
+def test_file_loaders_roundtrip(vv, oracle, tmp_path):
+    """DAT/RAW + noise file + PNG kernel + PNG TF through the reference's formats == in-memory path"""
+    from vectorvisualization_b200 import configs, fields as F
+    from vectorvisualization_b200.configs import apply_scene
+    s = configs.cfg2(n=32, size=64)
+    s.tf = F.tf_preset("tf-length")
+    _, want, _, _, _ = render_cuda(vv, s, sample_map=False)
+    dat = F.write_dat(str(tmp_path / "vol.dat"), s.field)
+    sdat = F.write_dat(str(tmp_path / "scalar.dat"), s.scalar)
+    nz = F.write_noise(str(tmp_path / "noise_32"), s.noise)
+    kpng = F.write_png(str(tmp_path / "kernel.png"), s.filter_row[None, :])
+    tfn = F.write_tf(str(tmp_path / "tf.png"), s.tf)
+    args = vv.parse_args(["volic", dat, "-n", nz, "-f", kpng, "--transfer=" + tfn])
+    r = vv.Renderer(0)
+    r.init(None)
+    r.loadDat(args.vol_file.decode())
+    r.loadNoise(args.noise_file.decode(), bool(args.use_gradients))
+    r.loadScalarDat(sdat)
+    r.loadFilterPNG(args.filter_file.decode())
+    r.loadTF(args.tf_file.decode())
+    r.setLICParams(s.lic_params())
+    r.setCamera(**s.camera)
+    r.resize(s.width, s.height)
+    r.render(True)
+    got = r.readRGBA32F()
+    # loadTF reads only <name>_rgba.png when it exists (VV/transferEdit.cpp:239 short-circuit): LIC opacity stays default
+    s2 = configs.cfg2(n=32, size=64)
+    s2.tf = F.default_tf()
+    s2.tf[:, :4] = s.tf[:, :4]
+    _, want2, _, _, _ = render_cuda(vv, s2, sample_map=False)
+    assert np.array_equal(got, want2)
+    out = str(tmp_path / "frame.png")
+    r.savePNG(out)
+    back = vv.png_read(out)
+    assert np.array_equal(back[::-1], r.readRGBA8())

@@ -1,0 +1,367 @@
+"""vectorvisualization_b200 -- B200-native 3D-LIC renderer (drop-in for liaoyg/VectorVisualization's LIC path).
+
+This module is only the Python mirror of the C ABI in include/vv_c_api.h (ctypes); all work happens in
+libvv_b200.so (hand-written CUDA for sm_100a).  There is no CPU fallback: if the library is missing or no CUDA
+device is present, construction raises.
+
+`Renderer` keeps the method names of the reference's `class Renderer` (VV/renderer.h:28-125) and of the objects
+it is handed (VectorDataSet / NoiseDataSet / LICFilter / TransferEdit / Camera / LICParams).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvv_b200.so")
+
+# RenderTechnique, VV/types.h:63-71
+VOLIC_VOLUME, VOLIC_RAYCAST, VOLIC_SLICING, VOLIC_LICVOLUME, VOLIC_VOLUMEANI = range(5)
+# VVDataType
+UCHAR, USHORT, FLOAT = 1, 2, 3
+# options
+TF_B, TF_A, TF_R, TF_LENGTH, TF_SCALAR = range(5)
+GATE_ALWAYS, GATE_TF_ALPHA = 0, 1
+(OPT_TF_MODE, OPT_GATE_MODE, OPT_NOISE_GATE, OPT_QUIRK_SCALEVOLINV, OPT_QUIRK_LUMINANCE_ALPHA, OPT_LICVOL_FP16,
+ OPT_FIELD_LAYOUT, OPT_COUNT_SAMPLES, OPT_LICVOL_SIZE, OPT_SPEC_EXP, OPT_SAMPLE_MAP) = range(1, 12)
+LAYOUT_F4, LAYOUT_PAIR = 0, 1
+BLOCK = 16  # pixels per image-block edge (sort-first partition unit)
+
+
+class LICParams(ctypes.Structure):
+    """struct LICParams, VV/types.h:91-109 (same defaults)"""
+    _fields_ = [("stepSizeVol", ctypes.c_float), ("gradientScale", ctypes.c_float), ("illumScale", ctypes.c_float),
+                ("freqScale", ctypes.c_float), ("numIterations", ctypes.c_int), ("stepsForward", ctypes.c_int),
+                ("stepsBackward", ctypes.c_int), ("stepSizeLIC", ctypes.c_float)]
+
+    def __init__(self, **kw):
+        super().__init__(1.0 / 128.0, 30.0, 1.0, 1.0, 255, 32, 32, 0.01)
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+class DatInfo(ctypes.Structure):
+    _fields_ = [("raw_file", ctypes.c_char * 512), ("resolution", ctypes.c_int * 3), ("slice_thickness", ctypes.c_float * 3),
+                ("data_type", ctypes.c_int), ("data_dim", ctypes.c_int), ("time_begin", ctypes.c_int), ("time_end", ctypes.c_int)]
+
+
+class Args(ctypes.Structure):
+    _fields_ = [("vol_file", ctypes.c_char * 512), ("noise_file", ctypes.c_char * 512), ("tf_file", ctypes.c_char * 512),
+                ("filter_file", ctypes.c_char * 512), ("redirect_file", ctypes.c_char * 512), ("halton_file", ctypes.c_char * 512),
+                ("use_gradients", ctypes.c_int), ("use_lambda2", ctypes.c_int), ("show_help", ctypes.c_int)]
+
+
+class VVError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("vv error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libvv_b200.so; raises if it has not been built (python vectorvisualization_b200/build.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libvv_b200.so is missing (%s): build it with `python vectorvisualization_b200/build.py`; "
+                           "there is no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    P, I, F, U64, CP = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_uint64, ctypes.c_char_p
+    sig = {
+        "vv_create": ([ctypes.POINTER(P), I], I), "vv_destroy": ([P], None), "vv_init": ([P, CP], I),
+        "vv_load_glsl_shader": ([P, CP], I), "vv_resize": ([P, I, I], I), "vv_last_error": ([], CP), "vv_version": ([], CP),
+        "vv_set_technique": ([P, I], I), "vv_update_lic_volume": ([P], I), "vv_update_slices": ([P], I),
+        "vv_set_vector_field": ([P, P, P, I, ctypes.POINTER(I), ctypes.POINTER(F)], I),
+        "vv_set_time_interp": ([P, I, I], I), "vv_set_scalar": ([P, P, I, ctypes.POINTER(I)], I),
+        "vv_set_noise": ([P, P, ctypes.POINTER(I), I], I), "vv_generate_white_noise": ([P, I, ctypes.c_uint32, F, I], I),
+        "vv_set_filter": ([P, P, I, I], I), "vv_set_box_filter": ([P, I], I), "vv_set_tf": ([P, P], I),
+        "vv_set_default_tf": ([P], I), "vv_set_lic_params": ([P, ctypes.POINTER(LICParams)], I),
+        "vv_default_lic_params": ([ctypes.POINTER(LICParams)], None),
+        "vv_set_camera": ([P, ctypes.POINTER(F), ctypes.POINTER(F), F, F, F, F], I),
+        "vv_set_light": ([P, ctypes.POINTER(F), F], I), "vv_update_light_pos": ([P], I),
+        "vv_enable_lowres": ([P, I], I), "vv_enable_float_target": ([P, I], I), "vv_set_option": ([P, I, I], I),
+        "vv_render": ([P, I], I), "vv_read_rgba8": ([P, P, ctypes.c_size_t], I), "vv_read_rgba32f": ([P, P, ctypes.c_size_t], I),
+        "vv_read_display_rgba8": ([P, P, ctypes.c_size_t], I),
+        "vv_read_lic_volume": ([P, P, ctypes.c_size_t, ctypes.POINTER(I)], I),
+        "vv_read_field_texture": ([P, P, ctypes.c_size_t], I),
+        "vv_read_noise_texture": ([P, P, ctypes.c_size_t, ctypes.POINTER(I)], I),
+        "vv_read_sample_map": ([P, P, ctypes.c_size_t], I),
+        "vv_save_png": ([P, CP, I], I), "vv_save_raw": ([P, CP], I),
+        "vv_last_ray_samples": ([P], U64), "vv_last_kernel_ms": ([P], F), "vv_last_launch_count": ([P], I),
+        "vv_synchronize": ([P], I), "vv_set_partition": ([P, I, I], I), "vv_set_licvol_slab": ([P, I, I], I),
+        "vv_get_tile_buffer": ([P, ctypes.POINTER(P), ctypes.POINTER(I), ctypes.POINTER(I)], I),
+        "vv_assemble_tiles": ([P, P, I], I), "vv_get_lic_volume_ptr": ([P, ctypes.POINTER(P), ctypes.POINTER(I)], I),
+        "vv_set_stream": ([P, P], I),
+        "vv_parse_dat": ([CP, ctypes.POINTER(DatInfo)], I), "vv_read_raw": ([ctypes.POINTER(DatInfo), I, P, ctypes.c_size_t], I),
+        "vv_load_dat": ([P, CP], I), "vv_load_scalar_dat": ([P, CP], I), "vv_load_noise": ([P, CP, I], I),
+        "vv_load_filter_png": ([P, CP], I), "vv_load_tf_png": ([P, CP], I),
+        "vv_parse_args": ([I, ctypes.POINTER(CP), ctypes.POINTER(Args)], I), "vv_usage": ([], CP),
+        "vv_png_read": ([CP, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)), ctypes.POINTER(I), ctypes.POINTER(I), ctypes.POINTER(I)], I),
+        "vv_free": ([P], None), "vv_png_write": ([CP, P, I, I, I], I),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(lib, name)   # AttributeError here == header/library mismatch
+        fn.argtypes = args
+        fn.restype = res
+    _lib = lib
+    return lib
+
+
+API_SYMBOLS = None  # filled lazily by tests from include/vv_c_api.h
+
+
+def _chk(rc):
+    if rc != 0:
+        raise VVError(rc, load_library().vv_last_error().decode(errors="replace"))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def parse_args(argv):
+    """ParseArguments::parse (VV/parseArg.cpp:97-365); argv includes the program name."""
+    lib = load_library()
+    arr = (ctypes.c_char_p * len(argv))(*[a.encode() for a in argv])
+    out = Args()
+    _chk(lib.vv_parse_args(len(argv), arr, ctypes.byref(out)))
+    return out
+
+
+def parse_dat(path):
+    lib = load_library()
+    info = DatInfo()
+    _chk(lib.vv_parse_dat(path.encode(), ctypes.byref(info)))
+    return info
+
+
+def png_read(path):
+    lib = load_library()
+    data = ctypes.POINTER(ctypes.c_uint8)()
+    w, h, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _chk(lib.vv_png_read(path.encode(), ctypes.byref(data), ctypes.byref(w), ctypes.byref(h), ctypes.byref(c)))
+    try:
+        return np.ctypeslib.as_array(data, shape=(h.value, w.value, c.value)).copy()
+    finally:
+        lib.vv_free(data)
+
+
+class Renderer:
+    """Headless counterpart of `class Renderer` (VV/renderer.h:28-125)."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        _chk(self._lib.vv_create(ctypes.byref(self._h), device))
+        self.width = self.height = 0
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.vv_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- lifecycle (VV/renderer.h:31-37,115)
+    def init(self, defines=None):
+        _chk(self._lib.vv_init(self._h, defines.encode() if defines else None))
+
+    def loadGLSLShader(self, defines=None):
+        _chk(self._lib.vv_load_glsl_shader(self._h, defines.encode() if defines else None))
+
+    def resize(self, w, h):
+        _chk(self._lib.vv_resize(self._h, w, h))
+        self.width, self.height = w, h
+
+    def setTechnique(self, t):
+        _chk(self._lib.vv_set_technique(self._h, t))
+
+    def updateLICVolume(self):
+        _chk(self._lib.vv_update_lic_volume(self._h))
+
+    def updateSlices(self):
+        _chk(self._lib.vv_update_slices(self._h))
+
+    # -- inputs
+    def setVectorField(self, field, next_field=None, slice_dist=(1.0, 1.0, 1.0)):
+        """field: [z][y][x][3] float32 (FLOAT3) or uint8 (UCHAR3)"""
+        field = np.ascontiguousarray(field)
+        assert field.ndim == 4 and field.shape[3] == 3
+        dtype = {np.dtype(np.float32): FLOAT, np.dtype(np.uint8): UCHAR}[field.dtype]
+        dims = (ctypes.c_int * 3)(field.shape[2], field.shape[1], field.shape[0])
+        sd = (ctypes.c_float * 3)(*slice_dist)
+        nxt = None
+        if next_field is not None:
+            next_field = np.ascontiguousarray(next_field, dtype=field.dtype)
+            nxt = _ptr(next_field)
+        _chk(self._lib.vv_set_vector_field(self._h, _ptr(field), nxt, dtype, dims, sd))
+
+    def setTimeInterp(self, index, size=10):
+        _chk(self._lib.vv_set_time_interp(self._h, index, size))
+
+    def setScalar(self, vol):
+        vol = np.ascontiguousarray(vol)
+        dtype = {np.dtype(np.float32): FLOAT, np.dtype(np.uint8): UCHAR}[vol.dtype]
+        dims = (ctypes.c_int * 3)(vol.shape[2], vol.shape[1], vol.shape[0])
+        _chk(self._lib.vv_set_scalar(self._h, _ptr(vol), dtype, dims))
+
+    def setNoise(self, noise, with_gradients=False):
+        noise = np.ascontiguousarray(noise, dtype=np.uint8)
+        dims = (ctypes.c_int * 3)(noise.shape[2], noise.shape[1], noise.shape[0])
+        _chk(self._lib.vv_set_noise(self._h, _ptr(noise), dims, int(with_gradients)))
+
+    def generateWhiteNoise(self, n=256, seed=0, p=1.0 / 6.0, with_gradients=False):
+        _chk(self._lib.vv_generate_white_noise(self._h, n, seed, p, int(with_gradients)))
+
+    def setLICFilter(self, row=None, channels=1):
+        if row is None:
+            _chk(self._lib.vv_set_box_filter(self._h, 256))
+        else:
+            row = np.ascontiguousarray(row, dtype=np.uint8)
+            _chk(self._lib.vv_set_filter(self._h, _ptr(row), row.size // channels, channels))
+
+    def setTF(self, tf=None):
+        if tf is None:
+            _chk(self._lib.vv_set_default_tf(self._h))
+        else:
+            tf = np.ascontiguousarray(tf, dtype=np.uint8)
+            assert tf.shape == (256, 5)
+            _chk(self._lib.vv_set_tf(self._h, _ptr(tf)))
+
+    def setLICParams(self, p):
+        _chk(self._lib.vv_set_lic_params(self._h, ctypes.byref(p)))
+
+    def setCamera(self, quat=(0, 0, 0, 1), pos=(0, 0, 0), dist=4.0, fovy=35.0, near=0.1, far=50.0):
+        _chk(self._lib.vv_set_camera(self._h, (ctypes.c_float * 4)(*quat), (ctypes.c_float * 3)(*pos), dist, fovy, near, far))
+
+    def setLight(self, quat=(0, 0, 0, 1), dist=1.0):
+        _chk(self._lib.vv_set_light(self._h, (ctypes.c_float * 4)(*quat), dist))
+
+    def updateLightPos(self):
+        _chk(self._lib.vv_update_light_pos(self._h))
+
+    def enableLowRes(self, enable):
+        _chk(self._lib.vv_enable_lowres(self._h, int(enable)))
+
+    def enableFBO(self, enable):
+        _chk(self._lib.vv_enable_float_target(self._h, int(enable)))
+
+    def setOption(self, option, value):
+        _chk(self._lib.vv_set_option(self._h, option, int(value)))
+
+    # -- loaders
+    def loadDat(self, path):
+        _chk(self._lib.vv_load_dat(self._h, path.encode()))
+
+    def loadScalarDat(self, path):
+        _chk(self._lib.vv_load_scalar_dat(self._h, path.encode()))
+
+    def loadNoise(self, path, with_gradients=False):
+        _chk(self._lib.vv_load_noise(self._h, path.encode(), int(with_gradients)))
+
+    def loadFilterPNG(self, path):
+        _chk(self._lib.vv_load_filter_png(self._h, path.encode()))
+
+    def loadTF(self, name):
+        _chk(self._lib.vv_load_tf_png(self._h, name.encode()))
+
+    # -- frame
+    def render(self, update=True):
+        _chk(self._lib.vv_render(self._h, int(update)))
+
+    def readRGBA8(self, out=None):
+        if out is None:
+            out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        _chk(self._lib.vv_read_rgba8(self._h, _ptr(out), out.nbytes))
+        return out
+
+    def readRGBA32F(self, out=None):
+        if out is None:
+            out = np.empty((self.height, self.width, 4), dtype=np.float32)
+        _chk(self._lib.vv_read_rgba32f(self._h, _ptr(out), out.nbytes))
+        return out
+
+    def readDisplayRGBA8(self):
+        out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        _chk(self._lib.vv_read_display_rgba8(self._h, _ptr(out), out.nbytes))
+        return out
+
+    def readLICVolume(self):
+        dims = (ctypes.c_int * 3)()
+        ptr = ctypes.c_void_p()
+        _chk(self._lib.vv_get_lic_volume_ptr(self._h, ctypes.byref(ptr), dims))
+        out = np.empty((dims[2], dims[1], dims[0]), dtype=np.float32)
+        _chk(self._lib.vv_read_lic_volume(self._h, _ptr(out), out.nbytes, dims))
+        return out
+
+    def readFieldTexture(self, shape):
+        """RGBA16F vector texture contents as float32 [z][y][x][4]"""
+        out = np.empty(tuple(shape) + (4,), dtype=np.float32)
+        _chk(self._lib.vv_read_field_texture(self._h, _ptr(out), out.nbytes))
+        return out
+
+    def readNoiseTexture(self, shape, channels):
+        out = np.empty(tuple(shape) + ((channels,) if channels > 1 else ()), dtype=np.uint8)
+        ch = ctypes.c_int()
+        _chk(self._lib.vv_read_noise_texture(self._h, _ptr(out), out.nbytes, ctypes.byref(ch)))
+        assert ch.value == channels
+        return out
+
+    def readSampleMap(self):
+        out = np.empty((self.height, self.width), dtype=np.uint32)
+        _chk(self._lib.vv_read_sample_map(self._h, _ptr(out), out.nbytes))
+        return out
+
+    def savePNG(self, path, displayed=False):
+        _chk(self._lib.vv_save_png(self._h, path.encode(), int(displayed)))
+
+    def saveRaw(self, path):
+        _chk(self._lib.vv_save_raw(self._h, path.encode()))
+
+    # -- measurement
+    def lastRaySamples(self):
+        return int(self._lib.vv_last_ray_samples(self._h))
+
+    def lastKernelMs(self):
+        return float(self._lib.vv_last_kernel_ms(self._h))
+
+    def lastLaunchCount(self):
+        return int(self._lib.vv_last_launch_count(self._h))
+
+    def synchronize(self):
+        _chk(self._lib.vv_synchronize(self._h))
+
+    # -- multi-GPU hooks
+    def setPartition(self, rank, world):
+        _chk(self._lib.vv_set_partition(self._h, rank, world))
+
+    def setLICVolumeSlab(self, z0, z1):
+        _chk(self._lib.vv_set_licvol_slab(self._h, z0, z1))
+
+    def tileBuffer(self):
+        """(device pointer, blocks per rank, total blocks) of the block-major tile buffer"""
+        ptr, nl, nt = ctypes.c_void_p(), ctypes.c_int(), ctypes.c_int()
+        _chk(self._lib.vv_get_tile_buffer(self._h, ctypes.byref(ptr), ctypes.byref(nl), ctypes.byref(nt)))
+        return ptr.value, nl.value, nt.value
+
+    def assembleTiles(self, gathered_dev_ptr, world):
+        _chk(self._lib.vv_assemble_tiles(self._h, ctypes.c_void_p(gathered_dev_ptr), world))
+
+    def licVolumePtr(self):
+        dims = (ctypes.c_int * 3)()
+        ptr = ctypes.c_void_p()
+        _chk(self._lib.vv_get_lic_volume_ptr(self._h, ctypes.byref(ptr), dims))
+        return ptr.value, (dims[0], dims[1], dims[2])
+
+    def setStream(self, cuda_stream):
+        _chk(self._lib.vv_set_stream(self._h, ctypes.c_void_p(cuda_stream) if cuda_stream else None))

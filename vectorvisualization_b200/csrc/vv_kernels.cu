@@ -1,0 +1,574 @@
+// vv_kernels.cu -- sm_100a kernels of the 3D-LIC hot path.
+//
+//   lic_raycast_kernel   K1  VV/shader/lic3d_fragment.glsl:5-99 + inc_lic.glsl:61-202 + inc_illum.glsl
+//   lic_volume_kernel    K2  VV/shader/lic3d_volume_fragment.glsl:2-21
+//   volume_raycast_kernel K3 VV/shader/raycast_lic3d_fragment.glsl:5-73
+//   unblock_kernel       K5  tile buffer -> row-major frame (+ RGBA8 store, + background_fragment.glsl:9-16)
+//
+// One thread per ray; a warp owns an 8x4-pixel ray tile and a 256-thread CTA a 16x16-pixel block, so the 32
+// rays of a warp sample neighbouring voxels at every march step and their 2x32 Heun streamline walks stay inside
+// the same few L1 lines.  CTAs are persistent and pull blocks from an atomic queue (only ~20-70 % of the
+// pixels hit the box and chord lengths vary 0..sqrt(3)).  Nothing here is a dense contraction: no tensor cores.
+#include "vv_device.cuh"
+#include "vv_kernels.h"
+
+namespace vvb200 {
+
+// ------------------------------------------------------------------------------------------------
+// ray set-up: VV/shader/lic3d_fragment.glsl:12-21; the fragment position is the entry point of the pixel
+// ray into [0,extent]^3 (front faces of the proxy cube, VV/renderer.cpp:682-736).  Evaluated with explicit
+// round-to-nearest double intrinsics (no FMA contraction) so the host oracle computes the same bits.
+__device__ __forceinline__ bool pixel_ray(const DevParams &P, int px, int py, float e[3])
+{
+    double ex = __dmul_rn(__dmul_rn(__dsub_rn(__ddiv_rn(__dmul_rn(2.0, (double)px + 0.5), (double)P.width), 1.0), P.tanHalf), P.aspect);
+    double ey = __dmul_rn(__dsub_rn(__ddiv_rn(__dmul_rn(2.0, (double)py + 0.5), (double)P.height), 1.0), P.tanHalf);
+    double ez = -1.0;
+    double d[3], o[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        d[i] = __dadd_rn(__dadd_rn(__dmul_rn(P.rot[i], ex), __dmul_rn(P.rot[3 + i], ey)), __dmul_rn(P.rot[6 + i], ez));
+        o[i] = P.camD[i];
+    }
+    double tn = -1e300, tf = 1e300, faceval = 0.0;
+    int face = -1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double lo = 0.0, hi = P.extent[i];
+        if (d[i] == 0.0) {
+            if (o[i] < lo || o[i] > hi) return false;
+            continue;
+        }
+        double t0 = __ddiv_rn(__dsub_rn(lo, o[i]), d[i]), t1 = __ddiv_rn(__dsub_rn(hi, o[i]), d[i]);
+        double fv = lo;
+        if (t0 > t1) { double t = t0; t0 = t1; t1 = t; fv = hi; }
+        if (t0 > tn) { tn = t0; face = i; faceval = fv; }
+        if (t1 < tf) tf = t1;
+    }
+    if (!(tn < tf) || tn <= 0.0 || face < 0) return false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double p = __dadd_rn(o[i], __dmul_rn(tn, d[i]));
+        if (i == face) p = faceval;
+        p = fmin(fmax(p, 0.0), P.extent[i]);
+        e[i] = (float)p;
+    }
+    return true;
+}
+
+// GLSL normalize() as v / sqrt(dot(v,v)), IEEE round-to-nearest, uncontracted
+__device__ __forceinline__ f3 normalize_rn(f3 v)
+{
+    float l = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z)));
+    return mk3(__fdiv_rn(v.x, l), __fdiv_rn(v.y, l), __fdiv_rn(v.z, l));
+}
+__device__ __forceinline__ f3 normalize3(f3 v)
+{
+    float l = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+    return mk3(v.x / l, v.y / l, v.z / l);
+}
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+
+// ------------------------------------------------------------------------------------------------
+// inc_lic.glsl
+
+// freqSampling, inc_lic.glsl:71-90 (scalar band gate + noise(pos * gradient.z).a)
+template <bool NGATE>
+__device__ __forceinline__ float noise_tap(const DevParams &P, f3 q)
+{
+    if (NGATE) {
+        float s = fetch_scalar(P, q.x, q.y, q.z);
+        if (!(s > 0.1f && s < 0.3f)) return 0.0f;
+    }
+    if (P.quirkLumAlpha) return 1.0f;   // Q7: GL_LUMINANCE noise read through .a
+    return fetch_noise_scalar(P, q.x * P.freq, q.y * P.freq, q.z * P.freq);
+}
+
+// one Heun step of singleLICstep (inc_lic.glsl:104-128); sh = dir * h
+template <int LAYOUT, bool SOF>
+__device__ __forceinline__ void heun_step(const DevParams &P, f3 &q, float4 &v, float sh)
+{
+    float s1 = SOF ? v.w * sh : sh;    // licdir *= step.a (SPEED_OF_FLOW) then *= h
+    f3 d1 = mk3(fmaf(2.0f, v.x, -1.0f) * s1, fmaf(2.0f, v.y, -1.0f) * s1, fmaf(2.0f, v.z, -1.0f) * s1);
+    float4 v2 = fetch_field<LAYOUT, false>(P, q.x + d1.x, q.y + d1.y, q.z + d1.z);
+    f3 d2 = mk3(fmaf(2.0f, v2.x, -1.0f) * s1, fmaf(2.0f, v2.y, -1.0f) * s1, fmaf(2.0f, v2.z, -1.0f) * s1);
+    q.x = fmaf(0.5f, d1.x + d2.x, q.x);
+    q.y = fmaf(0.5f, d1.y + d2.y, q.y);
+    q.z = fmaf(0.5f, d1.z + d2.z, q.z);
+    v = fetch_field<LAYOUT, SOF>(P, q.x, q.y, q.z);
+}
+
+// computeLIC, inc_lic.glsl:152-202, scalar build.  The backward and forward walks are independent; they are
+// advanced in the same loop iteration so that each thread keeps two dependent fetch chains in flight.
+template <int LAYOUT, bool NGATE, bool SOF>
+__device__ __forceinline__ float compute_lic_scalar(const DevParams &P, const float *s_kw, f3 pos, float4 centre)
+{
+    float acc0 = noise_tap<NGATE>(P, pos) * s_kw[0];
+    float accB = 0.0f, accF = 0.0f;
+    f3 qb = pos, qf = pos;
+    float4 vb = centre, vf = centre;
+    const float *kwB = s_kw + 1, *kwF = s_kw + 1 + P.nBwd;
+    const int nB = P.nBwd, nF = P.nFwd;
+    const int n = max(nB, nF);
+    for (int k = 0; k < n; ++k) {
+        if (k < nB) {
+            heun_step<LAYOUT, SOF>(P, qb, vb, -P.h);
+            accB = fmaf(noise_tap<NGATE>(P, qb), kwB[k], accB);
+        }
+        if (k < nF) {
+            heun_step<LAYOUT, SOF>(P, qf, vf, P.h);
+            accF = fmaf(noise_tap<NGATE>(P, qf), kwF[k], accF);
+        }
+    }
+    return (acc0 + accB) + accF;
+}
+
+// computeLIC, USE_NOISE_GRADIENTS build: vec4 accumulation of raw RGBA noise texels (Q8)
+template <int LAYOUT, bool SOF>
+__device__ __forceinline__ float4 compute_lic_grad(const DevParams &P, const float *s_kw, f3 pos, float4 centre)
+{
+    float4 c = fetch_noise_rgba(P, pos.x, pos.y, pos.z);
+    const float w0 = s_kw[0];
+    float4 accB = make_float4(0, 0, 0, 0), accF = make_float4(0, 0, 0, 0);
+    f3 qb = pos, qf = pos;
+    float4 vb = centre, vf = centre;
+    const float *kwB = s_kw + 1, *kwF = s_kw + 1 + P.nBwd;
+    const int nB = P.nBwd, nF = P.nFwd;
+    const int n = max(nB, nF);
+    for (int k = 0; k < n; ++k) {
+        if (k < nB) {
+            heun_step<LAYOUT, SOF>(P, qb, vb, -P.h);
+            float4 t = fetch_noise_rgba(P, qb.x, qb.y, qb.z);
+            float w = kwB[k];
+            accB.x = fmaf(t.x, w, accB.x); accB.y = fmaf(t.y, w, accB.y);
+            accB.z = fmaf(t.z, w, accB.z); accB.w = fmaf(t.w, w, accB.w);
+        }
+        if (k < nF) {
+            heun_step<LAYOUT, SOF>(P, qf, vf, P.h);
+            float4 t = fetch_noise_rgba(P, qf.x, qf.y, qf.z);
+            float w = kwF[k];
+            accF.x = fmaf(t.x, w, accF.x); accF.y = fmaf(t.y, w, accF.y);
+            accF.z = fmaf(t.z, w, accF.z); accF.w = fmaf(t.w, w, accF.w);
+        }
+    }
+    float4 r;
+    r.x = (c.x * w0 + accB.x) + accF.x;
+    r.y = (c.y * w0 + accB.y) + accF.y;
+    r.z = (c.z * w0 + accB.z) + accF.z;
+    r.w = (c.w * w0 + accB.w) + accF.w;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// inc_illum.glsl
+
+// color.a = 1 - pow(1 - color.a, alphaCorrection), inc_illum.glsl:38,169
+__device__ __forceinline__ float opacity_correct(const DevParams &P, float a) { return 1.0f - powf(1.0f - a, P.alphaCorr); }
+
+// illumLIC, inc_illum.glsl:158-172
+__device__ __forceinline__ float4 illum_lic(const DevParams &P, const float *s_opac, float illum, float4 tf)
+{
+    float4 c;
+    c.x = illum * tf.x * P.illumScale;
+    c.y = illum * tf.y * P.illumScale;
+    c.z = illum * tf.z * P.illumScale;
+    c.w = opacity_correct(P, opac_lookup(s_opac, illum * 1.3f) * tf.w);
+    return c;
+}
+
+// illumGradient, inc_illum.glsl:1-41 (LIGHT0: ambient 0, diffuse 1, specular 1; exponent VV/3DLIC.cpp:736)
+__device__ __forceinline__ float4 illum_gradient(const DevParams &P, const float *s_opac, float4 illum, float4 tf, f3 pos, f3 dir)
+{
+    f3 L = normalize3(mk3(P.lightPos[0] - pos.x * P.scaleVolInv[0], P.lightPos[1] - pos.y * P.scaleVolInv[1],
+                          P.lightPos[2] - pos.z * P.scaleVolInv[2]));
+    f3 V = normalize3(mk3(-dir.x, -dir.y, -dir.z));
+    f3 N = normalize3(mk3(-illum.x, -illum.y, -illum.z));
+    float ln = dot3(L, N);
+    f3 R = normalize3(mk3(2.0f * ln * N.x - L.x, 2.0f * ln * N.y - L.y, 2.0f * ln * N.z - L.z));
+    float spec = powf(clamp01(dot3(R, V)), P.specExp) * illum.w;
+    float diff = clamp01(ln) * P.illumScale;
+    float k = diff + 0.3f;
+    float4 c;
+    c.x = (tf.x * illum.w * k + spec) * P.illumScale;
+    c.y = (tf.y * illum.w * k + spec) * P.illumScale;
+    c.z = (tf.z * illum.w * k + spec) * P.illumScale;
+    c.w = opacity_correct(P, opac_lookup(s_opac, illum.w * 1.3f) * tf.w);
+    return c;
+}
+
+__device__ __forceinline__ void illum2d_lookup(const DevParams &P, int which, int ch, float sx, float sy, float *out)
+{
+    int x0, x1, y0, y1;
+    float fx, fy;
+    axis_clamp(sx, P.illum_w, x0, x1, fx);
+    axis_clamp(sy, P.illum_h, y0, y1, fy);
+    const float *T = P.illum2d[which];
+    for (int k = 0; k < ch; ++k) {
+        float a = lerpf(__ldg(T + (y0 * P.illum_w + x0) * ch + k), __ldg(T + (y0 * P.illum_w + x1) * ch + k), fx);
+        float b = lerpf(__ldg(T + (y1 * P.illum_w + x0) * ch + k), __ldg(T + (y1 * P.illum_w + x1) * ch + k), fx);
+        out[k] = lerpf(a, b, fy);
+    }
+}
+
+__device__ __forceinline__ f3 cross3(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+
+// illumMallo, inc_illum.glsl:46-112
+__device__ __forceinline__ float4 illum_mallo(const DevParams &P, const float *s_opac, float illum, float4 tf, f3 pos, f3 dir, f3 tangent)
+{
+    f3 L = normalize3(mk3(P.lightPos[0] - pos.x * P.scaleVolInv[0], P.lightPos[1] - pos.y * P.scaleVolInv[1],
+                          P.lightPos[2] - pos.z * P.scaleVolInv[2]));
+    f3 V = normalize3(mk3(-dir.x, -dir.y, -dir.z));
+    f3 T = normalize3(mk3(2.0f * tangent.x - 1.0f, 2.0f * tangent.y - 1.0f, 2.0f * tangent.z - 1.0f));
+    f3 B = normalize3(cross3(T, V));
+    f3 N = cross3(B, T);
+    f3 H = normalize3(mk3(V.x + L.x, V.y + L.y, V.z + L.z));
+    float ltx = dot3(L, N), lty = dot3(L, T), ltz = dot3(H, N), ltw = dot3(H, T);
+    float tmpx = 1.0f / sqrtf(1.0f - lty * lty);
+    float tmpy = 1.0f / sqrtf(1.0f - ltw * ltw);
+    float nz = ltx * tmpx, nw = ltz * tmpy;     // lt.zw = lt.xz * tmp
+    float cy = 0.5f * lty + 0.5f, cz = 0.5f * nz + 0.5f, cw = 0.5f * nw + 0.5f;
+    float d1, s1;
+    illum2d_lookup(P, 1, 1, cz, cy, &d1);
+    illum2d_lookup(P, 2, 1, cz, cw, &s1);
+    float specular = clamp01(s1 * powf(tmpy, -P.specExp));
+    float diffuse = d1 * P.illumScale;
+    float4 c;
+    c.x = tf.x * illum * diffuse + specular;
+    c.y = tf.y * illum * diffuse + specular;
+    c.z = tf.z * illum * diffuse + specular;
+    c.w = opacity_correct(P, opac_lookup(s_opac, illum * 1.3f) * tf.w);
+    return c;
+}
+
+// illumZoeckler, inc_illum.glsl:117-154 (Q17: .rg of a LUMINANCE_ALPHA texture = (L, L))
+__device__ __forceinline__ float4 illum_zoeckler(const DevParams &P, const float *s_opac, float illum, float4 tf, f3 pos, f3 dir, f3 tangent)
+{
+    f3 L = normalize3(mk3(P.lightPos[0] - pos.x * P.scaleVolInv[0], P.lightPos[1] - pos.y * P.scaleVolInv[1],
+                          P.lightPos[2] - pos.z * P.scaleVolInv[2]));
+    f3 V = normalize3(dir);
+    f3 T = normalize3(mk3(2.0f * tangent.x - 1.0f, 2.0f * tangent.y - 1.0f, 2.0f * tangent.z - 1.0f));
+    float la[2];
+    illum2d_lookup(P, 0, 2, 0.5f * dot3(L, T) + 0.5f, 0.5f * dot3(V, T) + 0.5f, la);
+    float sr = la[0] * P.illumScale, sg = la[0];
+    float4 c;
+    c.x = tf.x * illum * sr + 0.9f * sg;
+    c.y = tf.y * illum * sr + 0.9f * sg;
+    c.z = tf.z * illum * sr + 0.9f * sg;
+    c.w = opacity_correct(P, opac_lookup(s_opac, illum * 1.3f) * tf.w);
+    return c;
+}
+
+__device__ __forceinline__ float tf_index(const DevParams &P, float4 v, float scalar)
+{
+    switch (P.tfMode) {
+    case TF_A: return v.w;
+    case TF_R: return v.x;
+    case TF_LENGTH: return sqrtf(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+    case TF_SCALAR: return scalar;
+    default: return v.z;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct SharedTables {
+    float4 tf[256];
+    float opac[256];
+    float kw[2 * kMaxLicSteps + 1];
+    int block;
+};
+
+__device__ __forceinline__ void load_tables(const DevParams &P, SharedTables &S)
+{
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        S.tf[i] = P.tf_rgba[i];
+        S.opac[i] = P.tf_opac[i];
+    }
+    const int nk = 1 + P.nBwd + P.nFwd;
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) S.kw[i] = P.kw[i];
+    __syncthreads();
+}
+
+// K1 ------------------------------------------------------------------------------------------------
+template <int LAYOUT, int ILLUM, bool NGATE, bool SOF>
+__global__ void __launch_bounds__(256) lic_raycast_kernel(const __grid_constant__ DevParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SharedTables &S = *reinterpret_cast<SharedTables *>(smem_raw);
+    load_tables(P, S);
+    constexpr bool GRAD = (ILLUM == ILLUM_GRADIENT);   // ILLUM_GRADIENT => USE_NOISE_GRADIENTS, inc_header.glsl:17-19
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lx = (warp & 1) * 8 + (lane & 7);
+    const int ly = (warp >> 1) * 4 + (lane >> 3);
+
+    for (;;) {
+        if (threadIdx.x == 0) S.block = (int)atomicAdd(P.blockCounter, 1u);
+        __syncthreads();
+        const int lb = S.block;
+        __syncthreads();
+        if (lb >= P.nLocalBlocks) break;
+        const int b = P.rank + lb * P.world;
+        const int px = (b % P.nBlocksX) * kBlockDim + lx;
+        const int py = (b / P.nBlocksX) * kBlockDim + ly;
+
+        float4 dest = make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned int nsamples = 0;
+        float e[3];
+        if (px < P.width && py < P.height && pixel_ray(P, px, py, e)) {
+            // lic3d_fragment.glsl:12-21
+            f3 pos = mk3(__fmul_rn(e[0], P.scaleVol[0]), __fmul_rn(e[1], P.scaleVol[1]), __fmul_rn(e[2], P.scaleVol[2]));
+            f3 gd = normalize_rn(mk3(__fsub_rn(e[0], P.camera[0]), __fsub_rn(e[1], P.camera[1]), __fsub_rn(e[2], P.camera[2])));
+            f3 dir = mk3(__fmul_rn(gd.x, P.scaleVol[0]), __fmul_rn(gd.y, P.scaleVol[1]), __fmul_rn(gd.z, P.scaleVol[2]));
+            f3 dstep = mk3(__fmul_rn(dir.x, P.stepSize), __fmul_rn(dir.y, P.stepSize), __fmul_rn(dir.z, P.stepSize));
+            const unsigned int maxSamples = (unsigned int)P.numIter * (unsigned int)P.numIter;   // nested loops :38-40
+            float src_a = 0.0f;
+            for (;;) {
+                ++nsamples;
+                float4 vd = fetch_field<LAYOUT, true>(P, pos.x, pos.y, pos.z);                  // :44
+                float sc = 0.0f;
+                if (P.tfMode == TF_SCALAR) sc = fetch_scalar(P, pos.x, pos.y, pos.z);            // :52
+                float4 tf = tf_lookup(S.tf, tf_index(P, vd, sc));                               // :54
+                // gate :59-61 (scalarData.g > -0.0001 is always true for a LUMINANCE8 texture)
+                const bool gate = (P.gateMode == GATE_TF_ALPHA) ? (tf.w > 0.05f) : true;
+                if (gate) {
+                    float4 src;
+                    if (GRAD) {
+                        float4 il = compute_lic_grad<LAYOUT, SOF>(P, S.kw, pos, vd);            // :64
+                        il.w *= P.licScale;                                                     // :67
+                        src = illum_gradient(P, S.opac, il, tf, pos, dir);
+                    } else {
+                        float il = compute_lic_scalar<LAYOUT, NGATE, SOF>(P, S.kw, pos, vd) * P.licScale;
+                        if (ILLUM == ILLUM_MALLO) src = illum_mallo(P, S.opac, il, tf, pos, dir, mk3(vd.x, vd.y, vd.z));
+                        else if (ILLUM == ILLUM_ZOECKLER) src = illum_zoeckler(P, S.opac, il, tf, pos, dir, mk3(vd.x, vd.y, vd.z));
+                        else src = illum_lic(P, S.opac, il, tf);
+                    }
+                    // :83-84
+                    const float k = 1.0f - dest.w;
+                    dest.x = clamp01(fmaf(k, src.x * src.w, dest.x));
+                    dest.y = clamp01(fmaf(k, src.y * src.w, dest.y));
+                    dest.z = clamp01(fmaf(k, src.z * src.w, dest.z));
+                    dest.w = clamp01(fmaf(k, src.w, dest.w));
+                    src_a = src.w;
+                }
+                // :88-93
+                pos.x = __fadd_rn(pos.x, dstep.x);
+                pos.y = __fadd_rn(pos.y, dstep.y);
+                pos.z = __fadd_rn(pos.z, dstep.z);
+                const bool outside = pos.x < 0.0f || pos.x > P.texMax[0] || pos.y < 0.0f || pos.y > P.texMax[1] ||
+                                     pos.z < 0.0f || pos.z > P.texMax[2] || (src_a > 0.95f);   // Q4: src.a
+                if (outside || nsamples >= maxSamples) break;
+            }
+        }
+        const int o = lb * kBlockPixels + ly * kBlockDim + lx;
+        P.tiles[o] = dest;
+        if (P.samplesPerPixel) P.samplesPerPixel[o] = nsamples;
+        if (P.sampleCounter) {
+            unsigned int tot = __reduce_add_sync(0xffffffffu, nsamples);
+            if (lane == 0 && tot) atomicAdd(P.sampleCounter, (unsigned long long)tot);
+        }
+    }
+}
+
+// K3 ------------------------------------------------------------------------------------------------
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) volume_raycast_kernel(const __grid_constant__ DevParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SharedTables &S = *reinterpret_cast<SharedTables *>(smem_raw);
+    load_tables(P, S);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lx = (warp & 1) * 8 + (lane & 7);
+    const int ly = (warp >> 1) * 4 + (lane >> 3);
+    for (;;) {
+        if (threadIdx.x == 0) S.block = (int)atomicAdd(P.blockCounter, 1u);
+        __syncthreads();
+        const int lb = S.block;
+        __syncthreads();
+        if (lb >= P.nLocalBlocks) break;
+        const int b = P.rank + lb * P.world;
+        const int px = (b % P.nBlocksX) * kBlockDim + lx;
+        const int py = (b / P.nBlocksX) * kBlockDim + ly;
+        float4 dest = make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned int nsamples = 0;
+        float e[3];
+        if (px < P.width && py < P.height && pixel_ray(P, px, py, e)) {
+            f3 pos = mk3(__fmul_rn(e[0], P.scaleVol[0]), __fmul_rn(e[1], P.scaleVol[1]), __fmul_rn(e[2], P.scaleVol[2]));
+            f3 gd = normalize_rn(mk3(__fsub_rn(e[0], P.camera[0]), __fsub_rn(e[1], P.camera[1]), __fsub_rn(e[2], P.camera[2])));
+            f3 dstep = mk3(__fmul_rn(__fmul_rn(gd.x, P.scaleVol[0]), P.stepSize), __fmul_rn(__fmul_rn(gd.y, P.scaleVol[1]), P.stepSize),
+                           __fmul_rn(__fmul_rn(gd.z, P.scaleVol[2]), P.stepSize));
+            const unsigned int maxSamples = (unsigned int)P.numIter * (unsigned int)P.numIter;
+            for (;;) {
+                ++nsamples;
+                float4 vd = fetch_field<LAYOUT, false>(P, pos.x, pos.y, pos.z);                 // :40
+                float lic = fetch_licvol(P, pos.x, pos.y, pos.z);                               // :41
+                float4 tf = tf_lookup(S.tf, vd.z);                                              // :47
+                float4 src = illum_lic(P, S.opac, lic, tf);                                     // :51
+                const float k = 1.0f - dest.w;
+                dest.x = clamp01(fmaf(k, src.x * src.w, dest.x));
+                dest.y = clamp01(fmaf(k, src.y * src.w, dest.y));
+                dest.z = clamp01(fmaf(k, src.z * src.w, dest.z));
+                dest.w = clamp01(fmaf(k, src.w, dest.w));
+                pos.x = __fadd_rn(pos.x, dstep.x);
+                pos.y = __fadd_rn(pos.y, dstep.y);
+                pos.z = __fadd_rn(pos.z, dstep.z);
+                const bool outside = pos.x < 0.0f || pos.x > P.texMax[0] || pos.y < 0.0f || pos.y > P.texMax[1] ||
+                                     pos.z < 0.0f || pos.z > P.texMax[2] || (dest.w > 0.95f);   // :65 dest.a
+                if (outside || nsamples >= maxSamples) break;
+            }
+        }
+        const int o = lb * kBlockPixels + ly * kBlockDim + lx;
+        P.tiles[o] = dest;
+        if (P.samplesPerPixel) P.samplesPerPixel[o] = nsamples;
+        if (P.sampleCounter) {
+            unsigned int tot = __reduce_add_sync(0xffffffffu, nsamples);
+            if (lane == 0 && tot) atomicAdd(P.sampleCounter, (unsigned long long)tot);
+        }
+    }
+}
+
+// K2 ------------------------------------------------------------------------------------------------
+// one thread per voxel of the target; CTA = 8x8x4 voxels (warp = 8x4 voxels of one z-layer)
+template <int LAYOUT, bool GRAD, bool NGATE, bool SOF>
+__global__ void __launch_bounds__(256) lic_volume_kernel(const __grid_constant__ DevParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SharedTables &S = *reinterpret_cast<SharedTables *>(smem_raw);
+    load_tables(P, S);
+    const int bxn = (P.ow + 7) / 8, byn = (P.oh + 7) / 8, bzn = (P.oz1 - P.oz0 + 3) / 4;
+    const long long nblocks = (long long)bxn * byn * bzn;
+    const int t = threadIdx.x;
+    const int tx = t & 7, ty = (t >> 3) & 7, tz = t >> 6;
+    for (long long b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const int bx = (int)(b % bxn), by = (int)((b / bxn) % byn), bz = (int)(b / ((long long)bxn * byn));
+        const int x = bx * 8 + tx, y = by * 8 + ty, z = P.oz0 + bz * 4 + tz;
+        if (x >= P.ow || y >= P.oh || z >= P.oz1) continue;
+        // fragment of the full-screen quad of layer z: ((x+.5)/w, (y+.5)/h, (z+.5)/d), VV/renderer.cpp:1353-1358
+        f3 g = mk3(__fdiv_rn((float)x + 0.5f, (float)P.ow), __fdiv_rn((float)y + 0.5f, (float)P.oh), __fdiv_rn((float)z + 0.5f, (float)P.od));
+        f3 pos = mk3(__fmul_rn(g.x, P.scaleVol[0]), __fmul_rn(g.y, P.scaleVol[1]), __fmul_rn(g.z, P.scaleVol[2]));
+        float4 vd = fetch_field<LAYOUT, true>(P, pos.x, pos.y, pos.z);
+        float r;
+        if (GRAD) r = compute_lic_grad<LAYOUT, SOF>(P, S.kw, pos, vd).x;
+        else r = compute_lic_scalar<LAYOUT, NGATE, SOF>(P, S.kw, pos, vd);
+        r *= P.licScale;
+        if (P.licvolFp16) r = __half2float(__float2half_rn(r));
+        P.licvol_out[((size_t)z * P.oh + y) * P.ow + x] = r;
+    }
+}
+
+// K5 ------------------------------------------------------------------------------------------------
+// tiles laid out [world][nLocalBlocksMax][256] -> row-major float frame, RGBA8 frame, and displayed RGBA8
+__global__ void unblock_kernel(const float4 *__restrict__ tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY,
+                               int width, int height, float4 *__restrict__ frame, uchar4 *__restrict__ frame8,
+                               uchar4 *__restrict__ display8)
+{
+    const int px = blockIdx.x * blockDim.x + threadIdx.x;
+    const int py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= width || py >= height) return;
+    const int b = (py / kBlockDim) * nBlocksX + px / kBlockDim;
+    const int r = b % world, lb = b / world;
+    float4 c = tiles[((size_t)r * blocksPerRank + lb) * kBlockPixels + (py % kBlockDim) * kBlockDim + (px % kBlockDim)];
+    const size_t o = (size_t)py * width + px;
+    if (frame) frame[o] = c;
+    if (frame8) {
+        // GL float -> UNORM8 of the back buffer (VV/renderer.cpp:216-226)
+        frame8[o] = make_uchar4((unsigned char)floorf(clamp01(c.x) * 255.0f + 0.5f), (unsigned char)floorf(clamp01(c.y) * 255.0f + 0.5f),
+                                (unsigned char)floorf(clamp01(c.z) * 255.0f + 0.5f), (unsigned char)floorf(clamp01(c.w) * 255.0f + 0.5f));
+    }
+    if (display8) {
+        // background_fragment.glsl:9-16: clamp((1 - a) * white + dest)
+        const float k = 1.0f - c.w;
+        display8[o] = make_uchar4((unsigned char)floorf(clamp01(k + c.x) * 255.0f + 0.5f), (unsigned char)floorf(clamp01(k + c.y) * 255.0f + 0.5f),
+                                  (unsigned char)floorf(clamp01(k + c.z) * 255.0f + 0.5f), (unsigned char)floorf(clamp01(k + c.w) * 255.0f + 0.5f));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+
+template <int LAYOUT, int ILLUM, bool NGATE>
+static cudaError_t launch_raycast_sof(const DevParams &P, bool sof, int grid, size_t smem, cudaStream_t st)
+{
+    if (sof) {
+        cudaFuncSetAttribute(lic_raycast_kernel<LAYOUT, ILLUM, NGATE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lic_raycast_kernel<LAYOUT, ILLUM, NGATE, true><<<grid, 256, smem, st>>>(P);
+    } else {
+        cudaFuncSetAttribute(lic_raycast_kernel<LAYOUT, ILLUM, NGATE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lic_raycast_kernel<LAYOUT, ILLUM, NGATE, false><<<grid, 256, smem, st>>>(P);
+    }
+    return cudaGetLastError();
+}
+
+template <int LAYOUT>
+static cudaError_t launch_raycast_layout(const DevParams &P, int illum, bool ngate, bool sof, int grid, size_t smem, cudaStream_t st)
+{
+    switch (illum) {
+    case ILLUM_GRADIENT: return launch_raycast_sof<LAYOUT, ILLUM_GRADIENT, false>(P, sof, grid, smem, st);
+    case ILLUM_MALLO:
+        return ngate ? launch_raycast_sof<LAYOUT, ILLUM_MALLO, true>(P, sof, grid, smem, st)
+                     : launch_raycast_sof<LAYOUT, ILLUM_MALLO, false>(P, sof, grid, smem, st);
+    case ILLUM_ZOECKLER:
+        return ngate ? launch_raycast_sof<LAYOUT, ILLUM_ZOECKLER, true>(P, sof, grid, smem, st)
+                     : launch_raycast_sof<LAYOUT, ILLUM_ZOECKLER, false>(P, sof, grid, smem, st);
+    default:
+        return ngate ? launch_raycast_sof<LAYOUT, ILLUM_NONE, true>(P, sof, grid, smem, st)
+                     : launch_raycast_sof<LAYOUT, ILLUM_NONE, false>(P, sof, grid, smem, st);
+    }
+}
+
+size_t shared_table_bytes() { return sizeof(SharedTables); }
+
+cudaError_t launch_lic_raycast(const DevParams &P, int layout, int illum, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st)
+{
+    const size_t smem = sizeof(SharedTables);
+    if (layout == LAYOUT_PAIR) return launch_raycast_layout<LAYOUT_PAIR>(P, illum, noise_gate, speed_of_flow, grid, smem, st);
+    return launch_raycast_layout<LAYOUT_F4>(P, illum, noise_gate, speed_of_flow, grid, smem, st);
+}
+
+cudaError_t launch_volume_raycast(const DevParams &P, int layout, int grid, cudaStream_t st)
+{
+    const size_t smem = sizeof(SharedTables);
+    if (layout == LAYOUT_PAIR) {
+        cudaFuncSetAttribute(volume_raycast_kernel<LAYOUT_PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        volume_raycast_kernel<LAYOUT_PAIR><<<grid, 256, smem, st>>>(P);
+    } else {
+        cudaFuncSetAttribute(volume_raycast_kernel<LAYOUT_F4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        volume_raycast_kernel<LAYOUT_F4><<<grid, 256, smem, st>>>(P);
+    }
+    return cudaGetLastError();
+}
+
+template <int LAYOUT, bool GRAD, bool NGATE>
+static cudaError_t launch_licvol_sof(const DevParams &P, bool sof, int grid, size_t smem, cudaStream_t st)
+{
+    if (sof) {
+        cudaFuncSetAttribute(lic_volume_kernel<LAYOUT, GRAD, NGATE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lic_volume_kernel<LAYOUT, GRAD, NGATE, true><<<grid, 256, smem, st>>>(P);
+    } else {
+        cudaFuncSetAttribute(lic_volume_kernel<LAYOUT, GRAD, NGATE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lic_volume_kernel<LAYOUT, GRAD, NGATE, false><<<grid, 256, smem, st>>>(P);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lic_volume(const DevParams &P, int layout, bool grad, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st)
+{
+    const size_t smem = sizeof(SharedTables);
+    if (layout == LAYOUT_PAIR) {
+        if (grad) return launch_licvol_sof<LAYOUT_PAIR, true, false>(P, speed_of_flow, grid, smem, st);
+        return noise_gate ? launch_licvol_sof<LAYOUT_PAIR, false, true>(P, speed_of_flow, grid, smem, st)
+                          : launch_licvol_sof<LAYOUT_PAIR, false, false>(P, speed_of_flow, grid, smem, st);
+    }
+    if (grad) return launch_licvol_sof<LAYOUT_F4, true, false>(P, speed_of_flow, grid, smem, st);
+    return noise_gate ? launch_licvol_sof<LAYOUT_F4, false, true>(P, speed_of_flow, grid, smem, st)
+                      : launch_licvol_sof<LAYOUT_F4, false, false>(P, speed_of_flow, grid, smem, st);
+}
+
+cudaError_t launch_unblock(const float4 *tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY, int width, int height,
+                           float4 *frame, uchar4 *frame8, uchar4 *display8, cudaStream_t st)
+{
+    dim3 blk(16, 16), grd((width + 15) / 16, (height + 15) / 16);
+    unblock_kernel<<<grd, blk, 0, st>>>(tiles, world, blocksPerRank, nBlocksX, nBlocksY, width, height, frame, frame8, display8);
+    return cudaGetLastError();
+}
+
+} // namespace vvb200

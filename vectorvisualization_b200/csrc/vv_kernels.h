@@ -1,0 +1,34 @@
+// vv_kernels.h -- host-callable launchers of the sm_100a kernels (vv_kernels.cu, vv_preprocess.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vvb200 {
+
+struct DevParams;
+
+size_t shared_table_bytes();
+cudaError_t launch_lic_raycast(const DevParams &P, int layout, int illum, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st);
+cudaError_t launch_volume_raycast(const DevParams &P, int layout, int grid, cudaStream_t st);
+cudaError_t launch_lic_volume(const DevParams &P, int layout, bool grad, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st);
+cudaError_t launch_unblock(const float4 *tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY, int width, int height,
+                           float4 *frame, uchar4 *frame8, uchar4 *display8, cudaStream_t st);
+
+// ---- pre-processing (K6) ----
+// VectorDataSet::fillTexDataFloatInterp (VV/dataset.cpp:533-635): raw FLOAT3 / UCHAR3 time steps -> packed field.
+// tmp: float4 [n] scratch; maxbits: 1 uint scratch.  Writes the pair-packed fp16 layout and/or the float4 layout.
+cudaError_t launch_pack_field(const void *v0, const void *v1, int is_u8, int nx, int ny, int nz, float interp_frac,
+                              float4 *tmp, unsigned int *maxbits, uint4 *out_pair, float4 *out_f4, cudaStream_t st);
+// u8 volume -> cell8 layout (wrap: 0 = CLAMP_TO_EDGE, 1 = REPEAT); src_stride = bytes per voxel, src_offset = channel
+cudaError_t launch_build_cell8(const uint8_t *src, int src_stride, int src_offset, int nx, int ny, int nz, int repeat,
+                               uint2 *out, cudaStream_t st);
+// RGBA8 volume -> xy-quad layout with REPEAT
+cudaError_t launch_build_quad(const uchar4 *src, int nx, int ny, int nz, uint4 *out, cudaStream_t st);
+// float scalar volume -> u8 LUMINANCE (GL float->UNORM8 conversion on upload)
+cudaError_t launch_float_to_unorm8(const float *src, size_t n, uint8_t *out, cudaStream_t st);
+// noise gradients, VV/gradient.cpp:190-532: Sobel/one-sided -> 5^3 smoothing (Q16) -> normalise + quantise, and
+// NoiseDataSet::createTexture's RGBA8 packing (VV/dataset.cpp:1264-1282)
+cudaError_t launch_noise_gradients(const uint8_t *noise, int nx, int ny, int nz, const float slice_dist[3],
+                                   const float *filter125, float *grad_tmp, uchar4 *out_rgba, cudaStream_t st);
+
+} // namespace vvb200

@@ -1,0 +1,1186 @@
+// vv_renderer.cu -- host side of the hot path: the headless counterpart of `class Renderer`
+// (VV/renderer.h:28-299, VV/renderer.cpp) and of the dataset classes that feed it (VV/dataset.cpp), behind the
+// C ABI declared in include/vv_c_api.h.  Everything that touches voxels or pixels runs in the CUDA kernels of
+// vv_kernels.cu / vv_preprocess.cu; this file owns device memory, derives the parameter block the way
+// Renderer::setRenderVolParams does (VV/renderer.cpp:925-996) and sequences launches on one stream.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "vv_device.cuh"
+#include "vv_host.h"
+#include "vv_kernels.h"
+
+namespace vvb200 {
+const std::string &last_error_string();
+}
+
+using namespace vvb200;
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(VV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));               \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t ensure(size_t count)
+    {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+};
+
+struct VVRenderer {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int num_sms = 148;
+    bool inited = false;
+
+    // ---- volume geometry (VolumeData, VV/dataset.cpp:144-176) ----
+    int size[3] = {0, 0, 0};
+    float slice_dist[3] = {1, 1, 1};
+    float extent[3] = {1, 1, 1}, scale[3] = {1, 1, 1}, scale_inv[3] = {1, 1, 1}, center[3] = {.5f, .5f, .5f};
+
+    // ---- vector field ----
+    DevBuf<uint8_t> raw0, raw1;        // raw time steps (FLOAT3 or UCHAR3)
+    bool have_next = false, field_u8 = false, have_field = false;
+    int interp_index = 0, interp_size = 10;   // VV/3DLIC.cpp:705 setInterpolateSize(10)
+    DevBuf<float4> pack_tmp;
+    DevBuf<unsigned int> maxbits;
+    DevBuf<uint4> field_pair;
+    DevBuf<float4> field_f4;
+    int field_layout = LAYOUT_PAIR;
+    bool field_dirty = false;
+
+    // ---- scalar volume ----
+    DevBuf<uint2> scalar_cell;
+    int sdim[3] = {0, 0, 0};
+    bool have_scalar = false;
+
+    // ---- noise ----
+    DevBuf<uint8_t> noise_raw;
+    DevBuf<uint2> noise_cell;
+    DevBuf<uchar4> noise_rgba;
+    DevBuf<uint4> noise_quad;
+    DevBuf<float> grad_tmp, grad_filter;
+    int ndim[3] = {0, 0, 0};
+    bool have_noise = false, noise_has_grad = false;
+
+    // ---- filter kernel (LICFilter) / transfer function (TransferEdit) ----
+    std::vector<uint8_t> filter;
+    float inv_filter_area = 0.5f;
+    uint8_t tf[256 * 5];
+    DevBuf<float4> tf_rgba;
+    DevBuf<float> tf_opac, kw;
+    bool tables_dirty = true;
+
+    // ---- parameters ----
+    VVLicParams lp;
+    float cam_quat[4] = {0, 0, 0, 1}, cam_pos[3] = {0, 0, 0}, cam_dist = 4.0f, fovy = 35.0f, near_clip = 0.1f, far_clip = 50.0f;
+    float light_quat[4] = {0, 0, 0, 1}, light_dist = 1.0f;   // VV/3DLIC.cpp:681
+    float light_pos[3] = {0.5f, 0.5f, 1.5f};
+    int technique = VV_VOLIC_RAYCAST;
+    int illum_mode = ILLUM_NONE;
+    bool speed_of_flow = false, lowres = false, float_target = false;
+    int tf_mode = TF_B, gate_mode = GATE_ALWAYS, noise_gate = 1, quirk_scalevolinv = 1, quirk_lum_alpha = 0;
+    int licvol_fp16 = 1, count_samples = 1, licvol_size = 0, sample_map = 0;
+    DevBuf<unsigned int> sample_tiles;
+    float spec_exp = 40.0f;
+
+    // ---- frame ----
+    int width = 0, height = 0;
+    int rank = 0, world = 1;
+    int nbx = 0, nby = 0, n_local_blocks = 0, blocks_per_rank = 0;
+    DevBuf<float4> tiles, frame;
+    DevBuf<uchar4> frame8, display8;
+    DevBuf<unsigned long long> counters;   // [0] ray samples, [1] block queue (low 32 bits)
+    bool frame_valid = false;
+    int launches = 0;
+
+    // ---- LIC volume ----
+    DevBuf<float> licvol;
+    int ldim[3] = {0, 0, 0};
+    int slab_z0 = 0, slab_z1 = -1;
+    bool licvol_valid = false;
+
+    // ---- illumination tables (Illumination, VV/illumination.cpp) ----
+    DevBuf<float> illum_tab[3];
+    int illum_w = 0, illum_h = 0;
+};
+
+// ------------------------------------------------------------------------------------------------ helpers
+
+static void volume_geometry(VVRenderer *r)
+{
+    // VectorDataSet::loadData, VV/dataset.cpp:144-176
+    float volSize[3], maxVolSize = 0;
+    int maxTexSize = 0;
+    for (int i = 0; i < 3; ++i) {
+        volSize[i] = r->size[i] * r->slice_dist[i];
+        if (volSize[i] > maxVolSize) maxVolSize = volSize[i];
+        if (r->size[i] > maxTexSize) maxTexSize = r->size[i];
+    }
+    for (int i = 0; i < 3; ++i) {
+        r->scale[i] = maxTexSize / (r->size[i] * r->slice_dist[i]);
+        r->scale_inv[i] = r->size[i] * r->slice_dist[i] / maxTexSize;
+        r->extent[i] = r->size[i] * r->slice_dist[i] / maxVolSize;
+        r->center[i] = r->extent[i] / 2.0f;
+    }
+}
+
+// Quaternion_getAngleAxis, VV/mmath.cpp:213-232
+static void quat_angle_axis(const float q[4], float *angle, float axis[3])
+{
+    double d = std::sqrt((double)q[0] * q[0] + (double)q[1] * q[1] + (double)q[2] * q[2]);
+    if (d > 1e-6) {
+        d = 1.f / d;
+        axis[0] = (float)(q[0] * d); axis[1] = (float)(q[1] * d); axis[2] = (float)(q[2] * d);
+        *angle = (1.0 - std::fabs(q[3]) > 1e-6) ? 2.f * (float)std::acos(q[3]) : 0.0f;
+    } else {
+        axis[0] = 0.f; axis[1] = 0.f; axis[2] = 1.f; *angle = 0.f;
+    }
+}
+
+// glRotatef(angle, axis) as a row-major 3x3 (GL 2.1 spec 2.11.2)
+static void gl_rotation(float angle_rad, const float axis[3], float R[9])
+{
+    const double deg = (double)(float)(angle_rad * 180.0 / M_PI);   // VV/camera.cpp:67
+    const double a = deg * M_PI / 180.0;
+    double x = axis[0], y = axis[1], z = axis[2];
+    const double n = std::sqrt(x * x + y * y + z * z);
+    if (n > 0) { x /= n; y /= n; z /= n; }
+    const double c = std::cos(a), s = std::sin(a), t = 1.0 - c;
+    const double M[9] = {t * x * x + c,     t * x * y - s * z, t * x * z + s * y,
+                         t * x * y + s * z, t * y * y + c,     t * y * z - s * x,
+                         t * x * z - s * y, t * y * z + s * x, t * z * z + c};
+    for (int i = 0; i < 9; ++i) R[i] = (float)M[i];
+}
+
+// Renderer::updateLightPos, VV/renderer.cpp:431-466
+static void update_light(VVRenderer *r)
+{
+    // Transform::getPosition: q * (0,0,dist)
+    const double x = r->light_quat[0], y = r->light_quat[1], z = r->light_quat[2], w = r->light_quat[3];
+    const double v[3] = {0.0, 0.0, (double)r->light_dist};
+    const double tx = 2.0 * (y * v[2] - z * v[1]), ty = 2.0 * (z * v[0] - x * v[2]), tz = 2.0 * (x * v[1] - y * v[0]);
+    const float lp[3] = {(float)(v[0] + w * tx + (y * tz - z * ty)), (float)(v[1] + w * ty + (z * tx - x * tz)),
+                         (float)(v[2] + w * tz + (x * ty - y * tx))};
+    float angle, axis[3], Rm[9];
+    quat_angle_axis(r->cam_quat, &angle, axis);
+    gl_rotation(-angle, axis, Rm);
+    // M = T(center) R(-angle) T(cam_pos)   (no T(0,0,dist): the TODO at renderer.cpp:448)
+    const double l[3] = {(double)lp[0] + r->cam_pos[0], (double)lp[1] + r->cam_pos[1], (double)lp[2] + r->cam_pos[2]};
+    for (int i = 0; i < 3; ++i)
+        r->light_pos[i] = (float)(Rm[3 * i] * l[0] + Rm[3 * i + 1] * l[1] + Rm[3 * i + 2] * l[2] + r->center[i]);
+}
+
+static int ensure_frame(VVRenderer *r)
+{
+    r->nbx = (r->width + kBlockDim - 1) / kBlockDim;
+    r->nby = (r->height + kBlockDim - 1) / kBlockDim;
+    const int nb = r->nbx * r->nby;
+    r->blocks_per_rank = (nb + r->world - 1) / r->world;
+    r->n_local_blocks = (nb - r->rank + r->world - 1) / r->world;
+    if (r->n_local_blocks < 0) r->n_local_blocks = 0;
+    CU(r->tiles.ensure((size_t)r->blocks_per_rank * kBlockPixels));
+    const size_t npx = (size_t)r->width * r->height;
+    CU(r->frame.ensure(npx));
+    CU(r->frame8.ensure(npx));
+    CU(r->display8.ensure(npx));
+    CU(r->counters.ensure(2));
+    return VV_OK;
+}
+
+// LICFilter texture semantics: LUMINANCE8, LINEAR, GL_CLAMP with border 0 (VV/dataset.cpp:1489-1499)
+static float kernel_lookup(const VVRenderer *r, float s)
+{
+    const int n = (int)r->filter.size();
+    s = std::fmin(std::fmax(s, 0.0f), 1.0f);
+    const float u = s * (float)n - 0.5f;
+    const float fl = std::floor(u);
+    const float f = u - fl;
+    const int i0 = (int)fl, i1 = i0 + 1;
+    const float t0 = (i0 < 0 || i0 >= n) ? 0.0f : (float)r->filter[i0] / 255.0f;
+    const float t1 = (i1 < 0 || i1 >= n) ? 0.0f : (float)r->filter[i1] / 255.0f;
+    return (1.0f - f) * t0 + f * t1;
+}
+
+struct Uniforms {
+    float stepSize, gradient[3], licParams[3], licKernel[3], alphaCorrection;
+    int nFwd, nBwd;
+};
+
+// Renderer::setRenderVolParams, VV/renderer.cpp:947-995
+static Uniforms derive_uniforms(const VVRenderer *r)
+{
+    Uniforms u;
+    const VVLicParams &p = r->lp;
+    if (r->lowres) {
+        u.stepSize = 2.0f * p.stepSizeVol;
+        u.gradient[0] = p.gradientScale; u.gradient[1] = p.illumScale; u.gradient[2] = 0.7f * p.freqScale;
+        u.licParams[0] = 15.0f; u.licParams[1] = 15.0f; u.licParams[2] = 1.0f / 64.0f;
+        u.licKernel[0] = 0.5f / 15.0f; u.licKernel[1] = 0.5f / 15.0f; u.licKernel[2] = r->inv_filter_area / (30.0f);
+        u.alphaCorrection = 2.0f * p.stepSizeVol * 128.0f;
+    } else {
+        u.stepSize = p.stepSizeVol;
+        u.gradient[0] = p.gradientScale; u.gradient[1] = p.illumScale; u.gradient[2] = p.freqScale;
+        u.licParams[0] = (float)p.stepsForward; u.licParams[1] = (float)p.stepsBackward; u.licParams[2] = p.stepSizeLIC;
+        u.licKernel[0] = 0.5f / p.stepsForward; u.licKernel[1] = 0.5f / p.stepsBackward;
+        u.licKernel[2] = r->inv_filter_area / (p.stepsForward + p.stepsBackward);
+        u.alphaCorrection = p.stepSizeVol * 128.0f;
+    }
+    u.nFwd = (int)u.licParams[0];   // int(licParams.x), inc_lic.glsl:192
+    u.nBwd = (int)u.licParams[1];
+    return u;
+}
+
+static int upload_tables(VVRenderer *r, const Uniforms &u)
+{
+    if (r->filter.empty()) return fail(VV_ERR_STATE, "no LIC filter kernel set");
+    if (u.nFwd < 0 || u.nBwd < 0 || u.nFwd > kMaxLicSteps || u.nBwd > kMaxLicSteps)
+        return fail(VV_ERR_INVALID, "LIC steps out of range (0..1024 per direction)");
+    // per-step filter-kernel weights: texture1D(licKernelSampler, kernelOffset).r with the offsets of
+    // computeLIC (inc_lic.glsl:156,172,182,196)
+    std::vector<float> kw(1 + u.nBwd + u.nFwd);
+    kw[0] = kernel_lookup(r, 0.5f);
+    float off = 0.5f;
+    for (int i = 0; i < u.nBwd; ++i) { off -= u.licKernel[1]; kw[1 + i] = kernel_lookup(r, off); }
+    off = 0.5f;
+    for (int i = 0; i < u.nFwd; ++i) { off += u.licKernel[0]; kw[1 + u.nBwd + i] = kernel_lookup(r, off); }
+    CU(r->kw.ensure(2 * kMaxLicSteps + 1));
+    CU(cudaMemcpyAsync(r->kw.p, kw.data(), kw.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+    // TF textures: RGBA8 and LUMINANCE_ALPHA8 (.a = LIC opacity), VV/transferEdit.cpp:505-540
+    std::vector<float> rgba(256 * 4), opac(256);
+    for (int i = 0; i < 256; ++i) {
+        for (int k = 0; k < 4; ++k) rgba[4 * i + k] = (float)r->tf[5 * i + k] / 255.0f;
+        opac[i] = (float)r->tf[5 * i + 4] / 255.0f;
+    }
+    CU(r->tf_rgba.ensure(256));
+    CU(r->tf_opac.ensure(256));
+    CU(cudaMemcpyAsync(r->tf_rgba.p, rgba.data(), rgba.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+    CU(cudaMemcpyAsync(r->tf_opac.p, opac.data(), opac.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+    CU(cudaStreamSynchronize(r->stream));   // host vectors go out of scope
+    return VV_OK;
+}
+
+static int pack_field(VVRenderer *r)
+{
+    if (!r->have_field) return fail(VV_ERR_STATE, "no vector field set");
+    const size_t n = (size_t)r->size[0] * r->size[1] * r->size[2];
+    CU(r->pack_tmp.ensure(n));
+    CU(r->maxbits.ensure(1));
+    uint4 *pair = nullptr;
+    float4 *f4 = nullptr;
+    if (r->field_layout == LAYOUT_PAIR) { CU(r->field_pair.ensure(n)); pair = r->field_pair.p; }
+    else { CU(r->field_f4.ensure(n)); f4 = r->field_f4.p; }
+    const float frac = (float)r->interp_index / r->interp_size;   // VV/dataset.cpp:590
+    CU(launch_pack_field(r->raw0.p, r->have_next ? r->raw1.p : nullptr, r->field_u8 ? 1 : 0, r->size[0], r->size[1], r->size[2],
+                         frac, r->pack_tmp.p, r->maxbits.p, pair, f4, r->stream));
+    r->field_dirty = false;
+    return VV_OK;
+}
+
+static int fill_params(VVRenderer *r, DevParams &P, bool need_frame)
+{
+    if (!r->have_field) return fail(VV_ERR_STATE, "no vector field set (vv_set_vector_field / vv_load_dat)");
+    if (r->field_dirty || (r->field_layout == LAYOUT_PAIR ? !r->field_pair.p : !r->field_f4.p)) {
+        int rc = pack_field(r);
+        if (rc) return rc;
+    }
+    const bool grad = (r->illum_mode == ILLUM_GRADIENT);
+    if (!r->have_noise) return fail(VV_ERR_STATE, "no noise set (vv_set_noise / vv_load_noise / vv_generate_white_noise)");
+    if (grad && !r->noise_has_grad) return fail(VV_ERR_STATE, "ILLUM_GRADIENT needs noise gradients (-g)");
+    if (!grad && r->noise_gate && !r->have_scalar) return fail(VV_ERR_STATE, "no scalar volume set (vv_set_scalar); the noise gate needs it");
+    if (r->tf_mode == TF_SCALAR && !r->have_scalar) return fail(VV_ERR_STATE, "tf_mode scalar needs a scalar volume");
+    if (need_frame && (r->width <= 0 || r->height <= 0)) return fail(VV_ERR_STATE, "vv_resize not called");
+
+    const Uniforms u = derive_uniforms(r);
+    if (r->tables_dirty) {
+        int rc = upload_tables(r, u);
+        if (rc) return rc;
+        r->tables_dirty = false;
+    }
+    std::memset(&P, 0, sizeof(P));
+    P.field_pair = r->field_pair.p; P.field_f4 = r->field_f4.p;
+    P.fnx = r->size[0]; P.fny = r->size[1]; P.fnz = r->size[2];
+    P.scalar_cell = r->scalar_cell.p; P.snx = r->sdim[0]; P.sny = r->sdim[1]; P.snz = r->sdim[2];
+    P.noise_cell = r->noise_cell.p; P.noise_quad = r->noise_quad.p;
+    P.nnx = r->ndim[0]; P.nny = r->ndim[1]; P.nnz = r->ndim[2];
+    P.licvol = r->licvol.p; P.lnx = r->ldim[0]; P.lny = r->ldim[1]; P.lnz = r->ldim[2];
+    P.tf_rgba = r->tf_rgba.p; P.tf_opac = r->tf_opac.p; P.kw = r->kw.p;
+    for (int i = 0; i < 3; ++i) P.illum2d[i] = r->illum_tab[i].p;
+    P.illum_w = r->illum_w; P.illum_h = r->illum_h;
+    P.stepSize = u.stepSize; P.gradScale = u.gradient[0]; P.illumScale = u.gradient[1]; P.freq = u.gradient[2];
+    P.h = u.licParams[2] * (0.0f * 0.5f + 0.3f);          // logEyeDist = 0 (Q3), inc_lic.glsl:114
+    P.licScale = u.licKernel[2] * u.gradient[0];          // lic3d_fragment.glsl:67
+    P.alphaCorr = u.alphaCorrection; P.specExp = r->spec_exp;
+    P.numIter = r->lp.numIterations; P.nFwd = u.nFwd; P.nBwd = u.nBwd;
+    // VV/renderer.cpp:934-944 incl. Q1
+    const bool inv_active = (r->illum_mode != ILLUM_NONE);
+    for (int i = 0; i < 3; ++i) {
+        P.texMax[i] = r->extent[i] * r->scale[i];
+        if (inv_active && r->quirk_scalevolinv) { P.scaleVol[i] = r->scale_inv[i]; P.scaleVolInv[i] = 0.0f; }
+        else { P.scaleVol[i] = r->scale[i]; P.scaleVolInv[i] = r->scale_inv[i]; }
+        P.lightPos[i] = r->light_pos[i];
+        P.extent[i] = r->extent[i];
+    }
+    // view: Camera::setCamera (VV/camera.cpp:56-68) followed by glTranslatef(-center) (VV/renderer.cpp:146)
+    float angle, axis[3], R[9];
+    quat_angle_axis(r->cam_quat, &angle, axis);
+    gl_rotation(angle, axis, R);
+    const double t[3] = {-(double)r->cam_pos[0], -(double)r->cam_pos[1], (double)r->cam_dist - (double)r->cam_pos[2]};
+    for (int i = 0; i < 3; ++i) {
+        const double c = (double)r->center[i] + (double)R[i] * t[0] + (double)R[3 + i] * t[1] + (double)R[6 + i] * t[2];
+        P.camera[i] = (float)c;
+        P.camD[i] = (double)P.camera[i];
+    }
+    for (int i = 0; i < 9; ++i) P.rot[i] = (double)R[i];
+    P.tanHalf = (double)(float)std::tan((double)r->fovy * M_PI / 360.0);
+    P.aspect = (r->height > 0) ? (double)((float)r->width / (float)r->height) : 1.0;
+    P.width = r->width; P.height = r->height;
+    P.tfMode = r->tf_mode; P.gateMode = r->gate_mode; P.quirkLumAlpha = (r->quirk_lum_alpha && !r->noise_has_grad) ? 1 : 0;   // Q7 only bites GL_LUMINANCE noise
+    P.rank = r->rank; P.world = r->world; P.nBlocksX = r->nbx; P.nBlocksY = r->nby; P.nLocalBlocks = r->n_local_blocks;
+    P.tiles = r->tiles.p;
+    P.sampleCounter = r->count_samples ? r->counters.p : nullptr;
+    P.blockCounter = r->counters.p ? reinterpret_cast<unsigned int *>(r->counters.p + 1) : nullptr;
+    P.samplesPerPixel = nullptr;
+    if (r->sample_map && need_frame) {
+        CU(r->sample_tiles.ensure((size_t)r->blocks_per_rank * kBlockPixels));
+        P.samplesPerPixel = r->sample_tiles.p;
+    }
+    P.licvolFp16 = r->licvol_fp16;
+    return VV_OK;
+}
+
+static int persistent_grid(const VVRenderer *r, int work_items)
+{
+    int g = r->num_sms * 2;
+    if (work_items > 0 && g > work_items) g = work_items;
+    return g < 1 ? 1 : g;
+}
+
+static int run_unblock(VVRenderer *r, const float4 *tiles, int world, int blocks_per_rank)
+{
+    CU(launch_unblock(tiles, world, blocks_per_rank, r->nbx, r->nby, r->width, r->height, r->frame.p, r->frame8.p, r->display8.p, r->stream));
+    ++r->launches;
+    r->frame_valid = true;
+    return VV_OK;
+}
+
+static int compute_lic_volume(VVRenderer *r)
+{
+    int n = r->licvol_size > 0 ? r->licvol_size : 0;
+    int dims[3] = {n ? n : r->size[0], n ? n : r->size[1], n ? n : r->size[2]};
+    DevParams P;
+    int rc = fill_params(r, P, false);
+    if (rc) return rc;
+    const size_t cnt = (size_t)dims[0] * dims[1] * dims[2];
+    if (r->licvol.n < cnt || r->ldim[0] != dims[0] || r->ldim[1] != dims[1] || r->ldim[2] != dims[2]) {
+        CU(r->licvol.ensure(cnt));
+        CU(cudaMemsetAsync(r->licvol.p, 0, cnt * sizeof(float), r->stream));
+    }
+    r->ldim[0] = dims[0]; r->ldim[1] = dims[1]; r->ldim[2] = dims[2];
+    P.licvol_out = r->licvol.p;
+    P.ow = dims[0]; P.oh = dims[1]; P.od = dims[2];
+    P.oz0 = (r->slab_z1 >= 0) ? r->slab_z0 : 0;
+    P.oz1 = (r->slab_z1 >= 0) ? r->slab_z1 : dims[2];
+    if (P.oz0 < 0 || P.oz1 > dims[2] || P.oz0 > P.oz1) return fail(VV_ERR_INVALID, "LIC-volume slab out of range");
+    const long long nblocks = (long long)((dims[0] + 7) / 8) * ((dims[1] + 7) / 8) * ((P.oz1 - P.oz0 + 3) / 4);
+    if (nblocks > 0) {
+        const int grid = (int)std::min<long long>(nblocks, (long long)r->num_sms * 16);
+        const bool grad = (r->illum_mode == ILLUM_GRADIENT);
+        CU(cudaEventRecord(r->ev0, r->stream));
+        CU(launch_lic_volume(P, r->field_layout, grad, !grad && r->noise_gate, r->speed_of_flow, grid, r->stream));
+        CU(cudaEventRecord(r->ev1, r->stream));
+        ++r->launches;
+    }
+    r->licvol_valid = true;
+    return VV_OK;
+}
+
+#ifdef VV_HAVE_ILLUM_TABLES
+// CPU generation of the Zoeckler / Mallo tables is in vv_illum.cpp
+namespace vvb200 {
+void make_illum_tables(int w, int h, float spec_exp, std::vector<float> &zoeckler, std::vector<float> &mallo_diff, std::vector<float> &mallo_spec);
+}
+
+static int ensure_illum_tables(VVRenderer *r)
+{
+    if (r->illum_tab[0].p) return VV_OK;
+    std::vector<float> z, md, ms;
+    const int w = 256, h = 256;
+    make_illum_tables(w, h, r->spec_exp, z, md, ms);
+    CU(r->illum_tab[0].ensure(z.size()));
+    CU(r->illum_tab[1].ensure(md.size()));
+    CU(r->illum_tab[2].ensure(ms.size()));
+    CU(cudaMemcpy(r->illum_tab[0].p, z.data(), z.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(r->illum_tab[1].p, md.data(), md.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(r->illum_tab[2].p, ms.data(), ms.size() * sizeof(float), cudaMemcpyHostToDevice));
+    r->illum_w = w; r->illum_h = h;
+    return VV_OK;
+}
+#endif
+
+static int upload_noise(VVRenderer *r, const uint8_t *data, const int dims[3], int with_gradients)
+{
+    const size_t n = (size_t)dims[0] * dims[1] * dims[2];
+    if (n == 0 || n > ((size_t)1 << 31)) return fail(VV_ERR_INVALID, "noise dimensions out of range");
+    CU(r->noise_raw.ensure(n));
+    CU(cudaMemcpyAsync(r->noise_raw.p, data, n, cudaMemcpyHostToDevice, r->stream));
+    r->ndim[0] = dims[0]; r->ndim[1] = dims[1]; r->ndim[2] = dims[2];
+    CU(r->noise_cell.ensure(n));
+    CU(launch_build_cell8(r->noise_raw.p, 1, 0, dims[0], dims[1], dims[2], 1, r->noise_cell.p, r->stream));
+    r->noise_has_grad = false;
+    if (with_gradients) {
+        // filter table of filterGradients, VV/gradient.cpp:392-409 (only the k,j,i in -2..0 corner is ever written; Q16)
+        float filt[125];
+        std::memset(filt, 0, sizeof(filt));
+        const int fw = 2;
+        float sum = 0.0f;
+        for (int k = -fw; k < fw - 1; ++k)
+            for (int j = -fw; j < fw - 1; ++j)
+                for (int i = -fw; i < fw - 1; ++i)
+                    sum += filt[((fw + k) * 5 + fw + j) * 5 + fw + i] = std::exp(-(float)(i * i + j * j + k * k) / 5.0f);
+        for (int k = -fw; k < fw - 1; ++k)
+            for (int j = -fw; j < fw - 1; ++j)
+                for (int i = -fw; i < fw - 1; ++i) filt[((fw + k) * 5 + fw + j) * 5 + fw + i] /= sum;
+        CU(r->grad_filter.ensure(125));
+        CU(cudaMemcpyAsync(r->grad_filter.p, filt, sizeof(filt), cudaMemcpyHostToDevice, r->stream));
+        CU(r->grad_tmp.ensure(3 * n));
+        CU(r->noise_rgba.ensure(n));
+        CU(r->noise_quad.ensure(n));
+        // NoiseDataSet keeps sliceDist = 1 (never set for noise files, VV/dataset.cpp:1124-1173 / VolumeData ctor)
+        const float sd[3] = {1.0f, 1.0f, 1.0f};
+        CU(launch_noise_gradients(r->noise_raw.p, dims[0], dims[1], dims[2], sd, r->grad_filter.p, r->grad_tmp.p, r->noise_rgba.p, r->stream));
+        CU(launch_build_quad(r->noise_rgba.p, dims[0], dims[1], dims[2], r->noise_quad.p, r->stream));
+        r->noise_has_grad = true;
+    }
+    CU(cudaStreamSynchronize(r->stream));
+    r->grad_tmp.release();
+    r->have_noise = true;
+    r->frame_valid = false;
+    return VV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char *vv_version(void) { return "vectorvisualization_b200 0.1 (sm_100a)"; }
+
+void vv_default_lic_params(VVLicParams *p)
+{
+    // LICParams::LICParams, VV/types.h:93-98
+    p->stepSizeVol = 1.0f / 128.0f; p->gradientScale = 30.0f; p->illumScale = 1.0f; p->freqScale = 1.0f;
+    p->numIterations = 255; p->stepsForward = 32; p->stepsBackward = 32; p->stepSizeLIC = 0.01f;
+}
+
+int vv_create(VVRenderer **out, int cuda_device)
+{
+    if (!out) return fail(VV_ERR_INVALID, "vv_create: null out");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(VV_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                                     " (this library has no CPU fallback)");
+    if (cuda_device < 0 || cuda_device >= count) return fail(VV_ERR_INVALID, "vv_create: bad device index");
+    CU(cudaSetDevice(cuda_device));
+    VVRenderer *r = new VVRenderer();
+    r->device = cuda_device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cuda_device));
+    r->num_sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&r->own_stream, cudaStreamNonBlocking));
+    r->stream = r->own_stream;
+    CU(cudaEventCreate(&r->ev0));
+    CU(cudaEventCreate(&r->ev1));
+    vv_default_lic_params(&r->lp);
+    // TransferEdit ctor, VV/transferEdit.cpp:76-82
+    for (int i = 0; i < 256; ++i) {
+        for (int ch = 0; ch < 3; ++ch) r->tf[5 * i + ch] = (unsigned char)i;
+        for (int ch = 3; ch < 5; ++ch) r->tf[5 * i + ch] = (unsigned char)((i < 20) ? 0 : i - 20);
+    }
+    // LICFilter::createBoxFilter(256), VV/dataset.cpp:1405-1413 (3DLIC.cpp:729 fallback)
+    r->filter.assign(256, 255);
+    r->inv_filter_area = 0.5f;
+    *out = r;
+    return VV_OK;
+}
+
+void vv_destroy(VVRenderer *r)
+{
+    if (!r) return;
+    cudaSetDevice(r->device);
+    cudaDeviceSynchronize();
+    if (r->ev0) cudaEventDestroy(r->ev0);
+    if (r->ev1) cudaEventDestroy(r->ev1);
+    if (r->own_stream) cudaStreamDestroy(r->own_stream);
+    delete r;
+}
+
+// Renderer::loadGLSLShader(defines), VV/renderer.cpp:807-922; define strings from VV/3DLIC.cpp:416-436
+int vv_load_glsl_shader(VVRenderer *r, const char *defines)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    int illum = ILLUM_NONE;
+    bool sof = false;
+    if (defines) {
+        if (std::strstr(defines, "ILLUM_GRADIENT")) illum = ILLUM_GRADIENT;
+        else if (std::strstr(defines, "ILLUM_MALLO")) illum = ILLUM_MALLO;
+        else if (std::strstr(defines, "ILLUM_ZOECKLER")) illum = ILLUM_ZOECKLER;
+        if (std::strstr(defines, "SPEED_OF_FLOW")) sof = true;
+        if (std::strstr(defines, "TIME_DEPENDENT") || std::strstr(defines, "USE_MC_OFFSET"))
+            return fail(VV_ERR_INVALID, "TIME_DEPENDENT / USE_MC_OFFSET builds are not supported");
+    }
+    if (illum == ILLUM_MALLO || illum == ILLUM_ZOECKLER) {
+#ifdef VV_HAVE_ILLUM_TABLES
+        CU(cudaSetDevice(r->device));
+        int rc = ensure_illum_tables(r);
+        if (rc) return rc;
+#else
+        return fail(VV_ERR_INVALID, "ILLUM_MALLO / ILLUM_ZOECKLER are not built into this library yet");
+#endif
+    }
+    r->illum_mode = illum;
+    r->speed_of_flow = sof;
+    r->frame_valid = false;
+    r->licvol_valid = false;
+    return VV_OK;
+}
+
+int vv_init(VVRenderer *r, const char *defines)
+{
+    int rc = vv_load_glsl_shader(r, defines);
+    if (rc == VV_OK) r->inited = true;
+    return rc;
+}
+
+int vv_resize(VVRenderer *r, int width, int height)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    if (width <= 0 || height <= 0 || width > 32768 || height > 32768) return fail(VV_ERR_INVALID, "vv_resize: bad size");
+    CU(cudaSetDevice(r->device));
+    r->width = width; r->height = height;
+    r->frame_valid = false;
+    return ensure_frame(r);
+}
+
+int vv_set_technique(VVRenderer *r, int technique)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    if (technique == VV_VOLIC_VOLUME) return fail(VV_ERR_INVALID, "VOLIC_VOLUME (raw vector-field DVR, F1) is out of scope");
+    if (technique < VV_VOLIC_RAYCAST || technique > VV_VOLIC_VOLUMEANI) return fail(VV_ERR_INVALID, "unknown technique");
+    r->technique = technique;
+    r->frame_valid = false;
+    return VV_OK;
+}
+
+int vv_update_lic_volume(VVRenderer *r)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    CU(cudaSetDevice(r->device));
+    r->launches = 0;
+    return compute_lic_volume(r);
+}
+
+int vv_update_slices(VVRenderer *r)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    return VV_OK;   // slice set-up is derived per frame from the camera (VV/slicing.cpp:42-103)
+}
+
+int vv_set_vector_field(VVRenderer *r, const void *data, const void *next, int dtype, const int dims[3], const float slice_dist[3])
+{
+    if (!r || !data || !dims) return fail(VV_ERR_INVALID, "vv_set_vector_field: null argument");
+    if (dtype != VV_FLOAT && dtype != VV_UCHAR)
+        return fail(VV_ERR_INVALID, "VectorData:  Only 8bit integer and 32bit float vectors are supported.");   // dataset.cpp:136-141
+    const size_t n = (size_t)dims[0] * dims[1] * dims[2];
+    if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || n > ((size_t)1 << 31)) return fail(VV_ERR_INVALID, "bad field dimensions");
+    CU(cudaSetDevice(r->device));
+    const size_t bytes = n * 3 * (dtype == VV_FLOAT ? 4 : 1);
+    CU(r->raw0.ensure(bytes));
+    CU(cudaMemcpyAsync(r->raw0.p, data, bytes, cudaMemcpyHostToDevice, r->stream));
+    r->have_next = false;
+    if (next && dtype == VV_FLOAT) {
+        CU(r->raw1.ensure(bytes));
+        CU(cudaMemcpyAsync(r->raw1.p, next, bytes, cudaMemcpyHostToDevice, r->stream));
+        r->have_next = true;
+    }
+    CU(cudaStreamSynchronize(r->stream));
+    for (int i = 0; i < 3; ++i) { r->size[i] = dims[i]; r->slice_dist[i] = slice_dist ? slice_dist[i] : 1.0f; }
+    volume_geometry(r);
+    update_light(r);
+    r->field_u8 = (dtype == VV_UCHAR);
+    r->have_field = true;
+    r->interp_index = 0;
+    r->field_dirty = true;
+    r->frame_valid = false;
+    r->licvol_valid = false;
+    // re-pack now so the cost is not hidden in the first frame
+    return pack_field(r);
+}
+
+int vv_set_time_interp(VVRenderer *r, int interp_index, int interp_size)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    if (interp_size <= 0 || interp_index < 0) return fail(VV_ERR_INVALID, "bad interpolation index");
+    CU(cudaSetDevice(r->device));
+    r->interp_index = interp_index; r->interp_size = interp_size;
+    r->field_dirty = true;
+    r->frame_valid = false;
+    r->licvol_valid = false;
+    return r->have_field ? pack_field(r) : VV_OK;
+}
+
+int vv_set_scalar(VVRenderer *r, const void *data, int dtype, const int dims[3])
+{
+    if (!r || !data || !dims) return fail(VV_ERR_INVALID, "vv_set_scalar: null argument");
+    if (dtype != VV_UCHAR && dtype != VV_FLOAT)
+        return fail(VV_ERR_INVALID, "VolumeData:  Only 8bit integer and 32bit float scalar is supported.");   // dataset.cpp:873-878
+    const size_t n = (size_t)dims[0] * dims[1] * dims[2];
+    if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || n > ((size_t)1 << 31)) return fail(VV_ERR_INVALID, "bad scalar dimensions");
+    CU(cudaSetDevice(r->device));
+    DevBuf<uint8_t> raw;
+    CU(raw.ensure(n));
+    if (dtype == VV_FLOAT) {
+        // GL_LUMINANCE internal format with GL_FLOAT source data: clamped to [0,1] and stored as UNORM8
+        DevBuf<float> f;
+        CU(f.ensure(n));
+        CU(cudaMemcpyAsync(f.p, data, n * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+        CU(launch_float_to_unorm8(f.p, n, raw.p, r->stream));
+        CU(cudaStreamSynchronize(r->stream));
+    } else {
+        CU(cudaMemcpyAsync(raw.p, data, n, cudaMemcpyHostToDevice, r->stream));
+    }
+    CU(r->scalar_cell.ensure(n));
+    CU(launch_build_cell8(raw.p, 1, 0, dims[0], dims[1], dims[2], 0, r->scalar_cell.p, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    r->sdim[0] = dims[0]; r->sdim[1] = dims[1]; r->sdim[2] = dims[2];
+    r->have_scalar = true;
+    r->frame_valid = false;
+    r->licvol_valid = false;
+    return VV_OK;
+}
+
+int vv_set_noise(VVRenderer *r, const uint8_t *data, const int dims[3], int with_gradients)
+{
+    if (!r || !data || !dims) return fail(VV_ERR_INVALID, "vv_set_noise: null argument");
+    if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return fail(VV_ERR_INVALID, "bad noise dimensions");
+    CU(cudaSetDevice(r->device));
+    r->licvol_valid = false;
+    return upload_noise(r, data, dims, with_gradients);
+}
+
+int vv_generate_white_noise(VVRenderer *r, int n, uint32_t seed, float p, int with_gradients)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    if (n <= 0 || n > 1024) return fail(VV_ERR_INVALID, "noise size out of range");
+    // NoiseDataSet::loadData fallback, VV/dataset.cpp:1142-1163: floor(0.6 rand()/(RAND_MAX+1) + 0.5) * 255, i.e. 255 with
+    // probability 1/6.  rand() is unseeded there; here the stream is mt19937(seed), u = draw / 2^32, 255 iff u < p.
+    std::vector<uint8_t> v((size_t)n * n * n);
+    std::mt19937 gen(seed);
+    for (size_t i = 0; i < v.size(); ++i) v[i] = ((double)gen() / 4294967296.0 < (double)p) ? 255 : 0;
+    const int dims[3] = {n, n, n};
+    return vv_set_noise(r, v.data(), dims, with_gradients);
+}
+
+int vv_set_filter(VVRenderer *r, const uint8_t *row, int width, int channels)
+{
+    if (!r || !row || width <= 0 || channels <= 0) return fail(VV_ERR_INVALID, "vv_set_filter: bad argument");
+    // LICFilter::loadData, VV/dataset.cpp:1448-1461; calcFilterKernelInvArea :1503-1512
+    const int fw = next_pow2(width);
+    const int shift = (fw - width) / 2;
+    r->filter.assign(fw, 0);
+    for (int i = 0; i < width; ++i) r->filter[i + shift] = row[i * channels];
+    float area = 0.0f;
+    for (int i = 0; i < fw; ++i) area += r->filter[i];
+    r->inv_filter_area = 0.5f * fw * 255.0f / area;
+    r->tables_dirty = true;
+    r->frame_valid = false;
+    r->licvol_valid = false;
+    return VV_OK;
+}
+
+int vv_set_box_filter(VVRenderer *r, int width)
+{
+    if (!r || width <= 0) return fail(VV_ERR_INVALID, "vv_set_box_filter: bad argument");
+    r->filter.assign(next_pow2(width), 255);   // VV/dataset.cpp:1405-1413
+    r->inv_filter_area = 0.5f;
+    r->tables_dirty = true;
+    r->frame_valid = false;
+    r->licvol_valid = false;
+    return VV_OK;
+}
+
+int vv_set_tf(VVRenderer *r, const uint8_t *tf)
+{
+    if (!r || !tf) return fail(VV_ERR_INVALID, "vv_set_tf: null argument");
+    std::memcpy(r->tf, tf, 256 * 5);
+    r->tables_dirty = true;
+    r->frame_valid = false;
+    return VV_OK;
+}
+
+int vv_set_default_tf(VVRenderer *r)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    for (int i = 0; i < 256; ++i) {
+        for (int ch = 0; ch < 3; ++ch) r->tf[5 * i + ch] = (unsigned char)i;
+        for (int ch = 3; ch < 5; ++ch) r->tf[5 * i + ch] = (unsigned char)((i < 20) ? 0 : i - 20);
+    }
+    r->tables_dirty = true;
+    r->frame_valid = false;
+    return VV_OK;
+}
+
+int vv_set_lic_params(VVRenderer *r, const VVLicParams *p)
+{
+    if (!r || !p) return fail(VV_ERR_INVALID, "vv_set_lic_params: null argument");
+    if (p->stepsForward < 0 || p->stepsBackward < 0 || p->stepsForward > kMaxLicSteps || p->stepsBackward > kMaxLicSteps)
+        return fail(VV_ERR_INVALID, "LIC steps out of range (0..1024 per direction)");
+    if (!(p->stepSizeVol > 0.0f)) return fail(VV_ERR_INVALID, "stepSizeVol must be > 0");
+    if (p->numIterations <= 0) return fail(VV_ERR_INVALID, "numIterations must be > 0");
+    const bool steps_changed = p->stepsForward != r->lp.stepsForward || p->stepsBackward != r->lp.stepsBackward;
+    r->lp = *p;
+    if (steps_changed) r->tables_dirty = true;
+    r->frame_valid = false;
+    return VV_OK;
+}
+
+int vv_set_camera(VVRenderer *r, const float quat[4], const float pos[3], float dist, float fovy, float near_clip, float far_clip)
+{
+    if (!r || !quat || !pos) return fail(VV_ERR_INVALID, "vv_set_camera: null argument");
+    for (int i = 0; i < 4; ++i) r->cam_quat[i] = quat[i];
+    for (int i = 0; i < 3; ++i) r->cam_pos[i] = pos[i];
+    r->cam_dist = dist; r->fovy = fovy; r->near_clip = near_clip; r->far_clip = far_clip;
+    r->frame_valid = false;
+    return VV_OK;
+}
+
+int vv_set_light(VVRenderer *r, const float quat[4], float dist)
+{
+    if (!r || !quat) return fail(VV_ERR_INVALID, "vv_set_light: null argument");
+    for (int i = 0; i < 4; ++i) r->light_quat[i] = quat[i];
+    r->light_dist = dist;
+    r->frame_valid = false;
+    return VV_OK;
+}
+
+int vv_update_light_pos(VVRenderer *r)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    update_light(r);
+    r->frame_valid = false;
+    return VV_OK;
+}
+
+int vv_enable_lowres(VVRenderer *r, int enable)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    r->lowres = enable != 0;
+    r->tables_dirty = true;
+    r->frame_valid = false;
+    return VV_OK;
+}
+
+int vv_enable_float_target(VVRenderer *r, int enable)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    r->float_target = enable != 0;
+    return VV_OK;
+}
+
+int vv_set_option(VVRenderer *r, int option, int value)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    switch (option) {
+    case VV_OPT_TF_MODE:
+        if (value < TF_B || value > TF_SCALAR) return fail(VV_ERR_INVALID, "bad tf mode");
+        r->tf_mode = value; break;
+    case VV_OPT_GATE_MODE:
+        if (value != GATE_ALWAYS && value != GATE_TF_ALPHA) return fail(VV_ERR_INVALID, "bad gate mode");
+        r->gate_mode = value; break;
+    case VV_OPT_NOISE_GATE: r->noise_gate = value != 0; break;
+    case VV_OPT_QUIRK_SCALEVOLINV: r->quirk_scalevolinv = value != 0; break;
+    case VV_OPT_QUIRK_LUMINANCE_ALPHA: r->quirk_lum_alpha = value != 0; break;
+    case VV_OPT_LICVOL_FP16: r->licvol_fp16 = value != 0; break;
+    case VV_OPT_FIELD_LAYOUT:
+        if (value != LAYOUT_F4 && value != LAYOUT_PAIR) return fail(VV_ERR_INVALID, "bad field layout");
+        if (value != r->field_layout) {
+            r->field_layout = value;
+            r->field_pair.release();
+            r->field_f4.release();
+            r->field_dirty = true;
+        }
+        break;
+    case VV_OPT_COUNT_SAMPLES: r->count_samples = value != 0; break;
+    case VV_OPT_LICVOL_SIZE:
+        if (value < 0 || value > 2048) return fail(VV_ERR_INVALID, "bad LIC volume size");
+        r->licvol_size = value; break;
+    case VV_OPT_SPEC_EXP: r->spec_exp = (float)value; break;
+    case VV_OPT_SAMPLE_MAP: r->sample_map = value != 0; break;
+    default: return fail(VV_ERR_INVALID, "unknown option");
+    }
+    r->frame_valid = false;
+    r->licvol_valid = false;
+    return VV_OK;
+}
+
+// Renderer::render(update), VV/renderer.cpp:126-312: update == 0 re-presents the stored frame (:150-152, 228)
+int vv_render(VVRenderer *r, int update)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    CU(cudaSetDevice(r->device));
+    if (!update && r->frame_valid) return VV_OK;
+    r->launches = 0;
+    if (r->technique == VV_VOLIC_LICVOLUME || r->technique == VV_VOLIC_VOLUMEANI) {
+        if (!r->licvol_valid || r->technique == VV_VOLIC_VOLUMEANI) {
+            int rc = compute_lic_volume(r);
+            if (rc) return rc;
+        }
+    }
+    DevParams P;
+    int rc = fill_params(r, P, true);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(r->counters.p, 0, 2 * sizeof(unsigned long long), r->stream));
+    const int grid = persistent_grid(r, r->n_local_blocks);
+    CU(cudaEventRecord(r->ev0, r->stream));
+    switch (r->technique) {
+    case VV_VOLIC_RAYCAST:
+        CU(launch_lic_raycast(P, r->field_layout, r->illum_mode, r->illum_mode != ILLUM_GRADIENT && r->noise_gate, r->speed_of_flow, grid, r->stream));
+        break;
+    case VV_VOLIC_LICVOLUME:
+    case VV_VOLIC_VOLUMEANI:
+        CU(launch_volume_raycast(P, r->field_layout, grid, r->stream));
+        break;
+    default:
+        return fail(VV_ERR_INVALID, "technique not implemented");
+    }
+    CU(cudaEventRecord(r->ev1, r->stream));
+    ++r->launches;
+    if (r->world == 1) return run_unblock(r, r->tiles.p, 1, r->blocks_per_rank);
+    r->frame_valid = false;   // multi-GPU: the caller gathers tile buffers and calls vv_assemble_tiles
+    return VV_OK;
+}
+
+static int check_frame(VVRenderer *r, size_t out_bytes, size_t px_bytes)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    if (!r->frame_valid) return fail(VV_ERR_STATE, "no frame rendered");
+    if (out_bytes < (size_t)r->width * r->height * px_bytes) return fail(VV_ERR_INVALID, "output buffer too small");
+    return VV_OK;
+}
+
+int vv_read_rgba8(VVRenderer *r, uint8_t *out, size_t out_bytes)
+{
+    int rc = check_frame(r, out_bytes, 4);
+    if (rc) return rc;
+    CU(cudaSetDevice(r->device));
+    CU(cudaMemcpyAsync(out, r->frame8.p, (size_t)r->width * r->height * 4, cudaMemcpyDeviceToHost, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    return VV_OK;
+}
+
+int vv_read_rgba32f(VVRenderer *r, float *out, size_t out_bytes)
+{
+    int rc = check_frame(r, out_bytes, 16);
+    if (rc) return rc;
+    CU(cudaSetDevice(r->device));
+    CU(cudaMemcpyAsync(out, r->frame.p, (size_t)r->width * r->height * 16, cudaMemcpyDeviceToHost, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    return VV_OK;
+}
+
+int vv_read_display_rgba8(VVRenderer *r, uint8_t *out, size_t out_bytes)
+{
+    int rc = check_frame(r, out_bytes, 4);
+    if (rc) return rc;
+    CU(cudaSetDevice(r->device));
+    CU(cudaMemcpyAsync(out, r->display8.p, (size_t)r->width * r->height * 4, cudaMemcpyDeviceToHost, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    return VV_OK;
+}
+
+int vv_read_lic_volume(VVRenderer *r, float *out, size_t out_bytes, int dims_out[3])
+{
+    if (!r || !out) return fail(VV_ERR_INVALID, "vv_read_lic_volume: null argument");
+    if (!r->licvol_valid) return fail(VV_ERR_STATE, "LIC volume not computed (vv_update_lic_volume)");
+    const size_t n = (size_t)r->ldim[0] * r->ldim[1] * r->ldim[2];
+    if (out_bytes < n * sizeof(float)) return fail(VV_ERR_INVALID, "output buffer too small");
+    CU(cudaSetDevice(r->device));
+    CU(cudaMemcpyAsync(out, r->licvol.p, n * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    if (dims_out) { dims_out[0] = r->ldim[0]; dims_out[1] = r->ldim[1]; dims_out[2] = r->ldim[2]; }
+    return VV_OK;
+}
+
+static float half_bits_to_float(uint16_t h)
+{
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 0x1f, man = h & 0x3ffu, bits;
+    if (exp == 0) {
+        if (man == 0) bits = sign;
+        else {
+            exp = 127 - 15 + 1;
+            while (!(man & 0x400u)) { man <<= 1; --exp; }
+            bits = sign | (exp << 23) | ((man & 0x3ffu) << 13);
+        }
+    } else if (exp == 31) bits = sign | 0x7f800000u | (man << 13);
+    else bits = sign | ((exp + 127 - 15) << 23) | (man << 13);
+    float f;
+    std::memcpy(&f, &bits, 4);
+    return f;
+}
+
+int vv_read_field_texture(VVRenderer *r, float *out, size_t out_bytes)
+{
+    if (!r || !out) return fail(VV_ERR_INVALID, "vv_read_field_texture: null argument");
+    if (!r->have_field) return fail(VV_ERR_STATE, "no vector field set");
+    CU(cudaSetDevice(r->device));
+    if (r->field_dirty) { int rc = pack_field(r); if (rc) return rc; }
+    const size_t n = (size_t)r->size[0] * r->size[1] * r->size[2];
+    if (out_bytes < n * 16) return fail(VV_ERR_INVALID, "output buffer too small");
+    if (r->field_layout == LAYOUT_F4) {
+        CU(cudaMemcpyAsync(out, r->field_f4.p, n * 16, cudaMemcpyDeviceToHost, r->stream));
+        CU(cudaStreamSynchronize(r->stream));
+        return VV_OK;
+    }
+    std::vector<uint16_t> tmp(n * 8);
+    CU(cudaMemcpyAsync(tmp.data(), r->field_pair.p, n * 16, cudaMemcpyDeviceToHost, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    for (size_t i = 0; i < n; ++i)
+        for (int k = 0; k < 4; ++k) out[4 * i + k] = half_bits_to_float(tmp[8 * i + k]);
+    return VV_OK;
+}
+
+int vv_read_noise_texture(VVRenderer *r, uint8_t *out, size_t out_bytes, int *channels)
+{
+    if (!r || !out) return fail(VV_ERR_INVALID, "vv_read_noise_texture: null argument");
+    if (!r->have_noise) return fail(VV_ERR_STATE, "no noise set");
+    CU(cudaSetDevice(r->device));
+    const size_t n = (size_t)r->ndim[0] * r->ndim[1] * r->ndim[2];
+    const int ch = r->noise_has_grad ? 4 : 1;
+    if (out_bytes < n * ch) return fail(VV_ERR_INVALID, "output buffer too small");
+    CU(cudaMemcpyAsync(out, r->noise_has_grad ? (const void *)r->noise_rgba.p : (const void *)r->noise_raw.p, n * ch, cudaMemcpyDeviceToHost, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    if (channels) *channels = ch;
+    return VV_OK;
+}
+
+int vv_read_sample_map(VVRenderer *r, uint32_t *out, size_t out_bytes)
+{
+    if (!r || !out) return fail(VV_ERR_INVALID, "vv_read_sample_map: null argument");
+    if (!r->sample_map || !r->sample_tiles.p) return fail(VV_ERR_STATE, "VV_OPT_SAMPLE_MAP was not enabled before vv_render");
+    if (r->world != 1) return fail(VV_ERR_STATE, "sample map is only available on an unpartitioned handle");
+    const size_t npx = (size_t)r->width * r->height;
+    if (out_bytes < npx * 4) return fail(VV_ERR_INVALID, "output buffer too small");
+    CU(cudaSetDevice(r->device));
+    std::vector<uint32_t> t((size_t)r->blocks_per_rank * kBlockPixels);
+    CU(cudaMemcpyAsync(t.data(), r->sample_tiles.p, t.size() * 4, cudaMemcpyDeviceToHost, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    for (int y = 0; y < r->height; ++y)
+        for (int x = 0; x < r->width; ++x) {
+            const int b = (y / kBlockDim) * r->nbx + x / kBlockDim;
+            out[(size_t)y * r->width + x] = t[(size_t)b * kBlockPixels + (y % kBlockDim) * kBlockDim + (x % kBlockDim)];
+        }
+    return VV_OK;
+}
+
+// Renderer::saveTexture(_imgBufferTex0, 4, 15, 255) / saveFrameBuffer, VV/renderer.cpp:340-428, 1500: PNG rows top-down
+int vv_save_png(VVRenderer *r, const char *path, int displayed)
+{
+    if (!r || !path) return fail(VV_ERR_INVALID, "vv_save_png: null argument");
+    std::vector<uint8_t> img((size_t)r->width * r->height * 4), flip(img.size());
+    int rc = displayed ? vv_read_display_rgba8(r, img.data(), img.size()) : vv_read_rgba8(r, img.data(), img.size());
+    if (rc) return rc;
+    const size_t stride = (size_t)r->width * 4;
+    for (int y = 0; y < r->height; ++y) std::memcpy(&flip[stride * y], &img[stride * (r->height - 1 - y)], stride);
+    std::string err;
+    if (!png_write_file(path, flip.data(), r->width, r->height, 4, err)) return fail(VV_ERR_IO, err);
+    return VV_OK;
+}
+
+int vv_save_raw(VVRenderer *r, const char *path)
+{
+    if (!r || !path) return fail(VV_ERR_INVALID, "vv_save_raw: null argument");
+    std::vector<float> img((size_t)r->width * r->height * 4);
+    int rc = vv_read_rgba32f(r, img.data(), img.size() * sizeof(float));
+    if (rc) return rc;
+    FILE *fp = std::fopen(path, "wb");
+    if (!fp) return fail(VV_ERR_IO, std::string("cannot write ") + path);
+    const int32_t hdr[2] = {r->width, r->height};
+    std::fwrite(hdr, sizeof(hdr), 1, fp);
+    std::fwrite(img.data(), sizeof(float), img.size(), fp);
+    std::fclose(fp);
+    return VV_OK;
+}
+
+uint64_t vv_last_ray_samples(VVRenderer *r)
+{
+    if (!r || !r->counters.p) return 0;
+    cudaSetDevice(r->device);
+    unsigned long long v = 0;
+    cudaMemcpyAsync(&v, r->counters.p, sizeof(v), cudaMemcpyDeviceToHost, r->stream);
+    cudaStreamSynchronize(r->stream);
+    return (uint64_t)v;
+}
+
+float vv_last_kernel_ms(VVRenderer *r)
+{
+    if (!r) return -1.0f;
+    cudaSetDevice(r->device);
+    float ms = -1.0f;
+    if (cudaEventSynchronize(r->ev1) != cudaSuccess) return -1.0f;
+    if (cudaEventElapsedTime(&ms, r->ev0, r->ev1) != cudaSuccess) return -1.0f;
+    return ms;
+}
+
+int vv_last_launch_count(VVRenderer *r) { return r ? r->launches : 0; }
+
+int vv_synchronize(VVRenderer *r)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    CU(cudaSetDevice(r->device));
+    CU(cudaStreamSynchronize(r->stream));
+    return VV_OK;
+}
+
+int vv_set_partition(VVRenderer *r, int rank, int world)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    if (world < 1 || rank < 0 || rank >= world) return fail(VV_ERR_INVALID, "bad partition");
+    CU(cudaSetDevice(r->device));
+    r->rank = rank; r->world = world;
+    r->frame_valid = false;
+    return (r->width > 0) ? ensure_frame(r) : VV_OK;
+}
+
+int vv_set_licvol_slab(VVRenderer *r, int z0, int z1)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    r->slab_z0 = z0; r->slab_z1 = z1;
+    r->licvol_valid = false;
+    return VV_OK;
+}
+
+int vv_get_tile_buffer(VVRenderer *r, void **dev_ptr, int *n_local_blocks, int *n_total_blocks)
+{
+    if (!r || !dev_ptr) return fail(VV_ERR_INVALID, "vv_get_tile_buffer: null argument");
+    *dev_ptr = r->tiles.p;
+    if (n_local_blocks) *n_local_blocks = r->blocks_per_rank;
+    if (n_total_blocks) *n_total_blocks = r->nbx * r->nby;
+    return VV_OK;
+}
+
+int vv_assemble_tiles(VVRenderer *r, const void *gathered_dev, int world)
+{
+    if (!r || !gathered_dev) return fail(VV_ERR_INVALID, "vv_assemble_tiles: null argument");
+    if (world != r->world) return fail(VV_ERR_INVALID, "vv_assemble_tiles: world mismatch");
+    CU(cudaSetDevice(r->device));
+    return run_unblock(r, (const float4 *)gathered_dev, world, r->blocks_per_rank);
+}
+
+int vv_get_lic_volume_ptr(VVRenderer *r, void **dev_ptr, int dims_out[3])
+{
+    if (!r || !dev_ptr) return fail(VV_ERR_INVALID, "vv_get_lic_volume_ptr: null argument");
+    if (!r->licvol.p) return fail(VV_ERR_STATE, "LIC volume not allocated");
+    *dev_ptr = r->licvol.p;
+    if (dims_out) { dims_out[0] = r->ldim[0]; dims_out[1] = r->ldim[1]; dims_out[2] = r->ldim[2]; }
+    r->licvol_valid = true;   // the caller may have filled the other slabs (all-gather)
+    return VV_OK;
+}
+
+int vv_set_stream(VVRenderer *r, void *cuda_stream)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    r->stream = cuda_stream ? (cudaStream_t)cuda_stream : r->own_stream;
+    return VV_OK;
+}
+
+// ---- loaders ------------------------------------------------------------------------------------
+int vv_load_dat(VVRenderer *r, const char *dat_path)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    VVDatInfo info;
+    int rc = parse_dat(dat_path, &info);
+    if (rc) return rc;
+    if (info.data_dim != 3) return fail(VV_ERR_IO, std::string("VectorData:  DAT file \"") + dat_path + "\" refers not to a vector data set.");
+    if (info.data_type != VV_UCHAR && info.data_type != VV_FLOAT)
+        return fail(VV_ERR_IO, "VectorData:  Only 8bit integer and 32bit float vectors are supported.");
+    const size_t bytes = dat_bytes(&info);
+    std::vector<uint8_t> a(bytes), b;
+    rc = read_raw(&info, info.time_begin, a.data(), bytes);
+    if (rc) return rc;
+    const void *next = nullptr;
+    if (info.time_end > info.time_begin && info.data_type == VV_FLOAT) {
+        // VV/3DLIC.cpp:701-702: data = timestep cur, newData = the following one
+        b.resize(bytes);
+        rc = read_raw(&info, info.time_begin + 1, b.data(), bytes);
+        if (rc) return rc;
+        next = b.data();
+    }
+    return vv_set_vector_field(r, a.data(), next, info.data_type, info.resolution, info.slice_thickness);
+}
+
+int vv_load_scalar_dat(VVRenderer *r, const char *dat_path)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    VVDatInfo info;
+    int rc = parse_dat(dat_path, &info);
+    if (rc) return rc;
+    if (info.data_dim != 1) return fail(VV_ERR_IO, std::string("VolumeData:  DAT file \"") + dat_path + "\" refers not to a scalar data set.");
+    if (info.data_type != VV_UCHAR && info.data_type != VV_FLOAT)
+        return fail(VV_ERR_IO, "VolumeData:  Only 8bit integer and 32bit float scalar is supported.");
+    const size_t bytes = dat_bytes(&info);
+    std::vector<uint8_t> a(bytes);
+    rc = read_raw(&info, info.time_begin, a.data(), bytes);
+    if (rc) return rc;
+    return vv_set_scalar(r, a.data(), info.data_type, info.resolution);
+}
+
+int vv_load_noise(VVRenderer *r, const char *path, int with_gradients)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    std::vector<uint8_t> data;
+    int dims[3];
+    int rc = read_noise_file(path, data, dims);
+    if (rc) return rc;
+    return vv_set_noise(r, data.data(), dims, with_gradients);
+}
+
+int vv_load_filter_png(VVRenderer *r, const char *path)
+{
+    if (!r || !path) return fail(VV_ERR_INVALID, "FilterKernel:  No filename set.");
+    std::vector<uint8_t> img;
+    int w, h, ch;
+    std::string err;
+    if (!png_read_file(path, img, w, h, ch, err)) return fail(VV_ERR_IO, std::string("FilterKernel:  Could not load filter kernel (\"") + path + "\"): " + err);
+    return vv_set_filter(r, img.data(), w, ch);   // first row, first channel (VV/dataset.cpp:1439-1461)
+}
+
+int vv_load_tf_png(VVRenderer *r, const char *name)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    int rc = load_tf_png(name, r->tf);
+    if (rc) return rc;
+    r->tables_dirty = true;
+    r->frame_valid = false;
+    return VV_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,98 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink) for the gathers.
+
+Sort-first: the image is cut into 16x16-pixel blocks; block b belongs to rank b % world (interleaving balances the
+~20-70 % box coverage and the chord-length variation without a cost model); the vector field, noise, scalar volume
+and tables are replicated on every GPU.  Each rank renders its blocks into a compact block-major tile buffer; one
+all_gather of those buffers (a few MiB per frame) and one un-block kernel give every rank the frame.
+LIC-volume mode: output z-slabs per rank (input replicated, so no halo exchange is needed -- SURVEY 8(e)), one
+all_gather of the slabs.
+"""
+import numpy as np
+
+
+class _CAI:
+    """minimal __cuda_array_interface__ carrier so torch can view a raw device pointer without a copy"""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+def device_tensor(ptr, shape, dtype):
+    import torch
+    typestr = {torch.float32: "<f4", torch.uint8: "|u1", torch.int32: "<i4"}[dtype]
+    return torch.as_tensor(_CAI(ptr, shape, typestr), device="cuda")
+
+
+# ---- host-side partition bookkeeping (mirrors vv_renderer.cu: ensure_frame / unblock_kernel) ----
+
+def block_grid(width, height, block=16):
+    return (width + block - 1) // block, (height + block - 1) // block
+
+
+def blocks_per_rank(width, height, world, block=16):
+    nbx, nby = block_grid(width, height, block)
+    return (nbx * nby + world - 1) // world
+
+
+def local_blocks(width, height, rank, world, block=16):
+    nbx, nby = block_grid(width, height, block)
+    return list(range(rank, nbx * nby, world))
+
+
+def assemble_host(gathered, width, height, world, block=16):
+    """numpy reference of unblock_kernel: gathered [world][blocks_per_rank][block*block][C] -> [h][w][C]"""
+    nbx, nby = block_grid(width, height, block)
+    out = np.zeros((height, width, gathered.shape[-1]), dtype=gathered.dtype)
+    for b in range(nbx * nby):
+        r, lb = b % world, b // world
+        bx, by = b % nbx, b // nbx
+        tile = gathered[r, lb].reshape(block, block, -1)
+        y0, x0 = by * block, bx * block
+        h, w = min(block, height - y0), min(block, width - x0)
+        out[y0:y0 + h, x0:x0 + w] = tile[:h, :w]
+    return out
+
+
+def slab_range(depth, rank, world):
+    """z-slab [z0,z1) of the LIC volume owned by `rank`: equal slabs, remainder to the first ranks"""
+    base, rem = divmod(depth, world)
+    z0 = rank * base + min(rank, rem)
+    return z0, z0 + base + (1 if rank < rem else 0)
+
+
+def render_distributed(renderer, group=None):
+    """render this rank's blocks, all-gather the tile buffers over NCCL, assemble the frame on every rank.
+    Returns the gathered tensor (kept alive by the caller until the frame has been read)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    renderer.setStream(torch.cuda.current_stream().cuda_stream)   # kernels and NCCL on one stream: no cross-stream race
+    renderer.render(True)
+    ptr, bpr, _ = renderer.tileBuffer()
+    local = device_tensor(ptr, (bpr * 256 * 4,), torch.float32)
+    gathered = torch.empty((world * bpr * 256 * 4,), dtype=torch.float32, device=local.device)
+    dist.all_gather_into_tensor(gathered, local, group=group)
+    renderer.assembleTiles(gathered.data_ptr(), world)
+    return gathered
+
+
+def update_lic_volume_distributed(renderer, depth, group=None):
+    """each rank computes its z-slab of the LIC volume, then the slabs are all-gathered in place"""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    z0, z1 = slab_range(depth, rank, world)
+    renderer.setStream(torch.cuda.current_stream().cuda_stream)
+    renderer.setLICVolumeSlab(z0, z1)
+    renderer.updateLICVolume()
+    ptr, dims = renderer.licVolumePtr()
+    vol = device_tensor(ptr, (dims[2], dims[1] * dims[0]), torch.float32)
+    if depth % world == 0:
+        dist.all_gather_into_tensor(vol.view(-1), vol[z0:z1].reshape(-1).clone(), group=group)
+    else:
+        for r in range(world):
+            a, b = slab_range(depth, r, world)
+            dist.broadcast(vol[a:b], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+    return vol
