@@ -178,7 +178,8 @@ def run_cuda(args):
     scene = make_scene(args.config)
     r = vv.Renderer(local_rank)
     configs.apply_scene(r, scene)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-legacy) stream: the library, NCCL and the timing events share it
+    torch.cuda.set_stream(stream)
     r.setStream(stream.cuda_stream)
     if world > 1:
         r.setPartition(rank, world)

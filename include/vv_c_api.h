@@ -83,7 +83,9 @@ typedef enum VVOption {
     VV_OPT_COUNT_SAMPLES = 8,      /* 1 (default): count ray samples per frame */
     VV_OPT_LICVOL_SIZE = 9,        /* LIC-volume edge length; 0 (default) = field resolution (reference: 512) */
     VV_OPT_SPEC_EXP = 10,          /* gl_LightSource[0].spotExponent as int (default 40, VV/illumination.h:52) */
-    VV_OPT_SAMPLE_MAP = 11         /* 1: keep per-pixel ray-sample counts (vv_read_sample_map) */
+    VV_OPT_SAMPLE_MAP = 11,        /* 1: keep per-pixel ray-sample counts (vv_read_sample_map) */
+    VV_OPT_RAYCAST_MODE = 12,      /* 1 (default): sample-parallel pipeline; 0: one thread per ray (cross-check) */
+    VV_OPT_LIC_CTAS_PER_SM = 13    /* persistent CTAs per SM of the lic_sample kernel (0 = default: all resident) */
 } VVOption;
 
 /* ---- lifecycle: Renderer() / init / resize / ~Renderer, VV/renderer.h:31-37 ------------------- */

@@ -170,6 +170,24 @@ def test_layouts_bit_identical(vv):
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("name", ["cfg1_small", "cfg3_small", "gate_tf_alpha_tf_a", "odd_image_size"])
+def test_raycast_modes_bit_identical(vv, name):
+    """sample-parallel pipeline (default) == one-thread-per-ray kernel, bit for bit, incl. early termination"""
+    from vectorvisualization_b200.configs import apply_scene
+    scene = _scenes()[name]()
+    out = []
+    for mode in (1, 0):
+        r = vv.Renderer(0)
+        r.setOption(vv.OPT_RAYCAST_MODE, mode)
+        apply_scene(r, scene)
+        r.setOption(vv.OPT_SAMPLE_MAP, 1)
+        r.render(True)
+        out.append((r.readRGBA32F(), r.readSampleMap(), r.lastRaySamples()))
+    assert out[0][2] == out[1][2] and out[0][2] > 0
+    assert np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][0], out[1][0])
+
+
 def test_camera_inside_box_draws_nothing(vv, oracle):
     from vectorvisualization_b200 import configs
     s = configs.cfg1(n=32, size=64)

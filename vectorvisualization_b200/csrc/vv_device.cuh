@@ -61,6 +61,13 @@ struct DevParams {
     unsigned long long *sampleCounter;
     unsigned int *blockCounter;
     unsigned int *samplesPerPixel;   // optional, block-major like tiles
+    // ---- sample-parallel pipeline ----
+    float4 *rayA, *rayB;             // [tile*32 + lane]: (pos0.xyz, n) and (dir.xyz, state)
+    uint2  *tileRec;                 // [tile]: (first src row, max samples of the tile)
+    float4 *src;                     // [(row + k) * 32 + lane]: shaded ray samples, w < 0 = gated off
+    uint2  *items, *itemsNext;       // work items (tile, k) of the current / next depth window
+    unsigned int *itemCount, *itemCountNext, *itemHead, *slotAlloc, *nMaxGlobal;
+    int win0, win1, win2;            // current window [win0, win1), next window ends at win2
     // ---- LIC volume target ----
     float *licvol_out;
     int ow, oh, od, oz0, oz1, licvolFp16;

@@ -288,14 +288,64 @@ __device__ __forceinline__ void load_tables(const DevParams &P, SharedTables &S)
     __syncthreads();
 }
 
-// K1 ------------------------------------------------------------------------------------------------
+// one ray sample of lic3d_fragment.glsl:44-81: vector fetch, TF, gate, computeLIC, illumination.
+// Returns false when the LIC gate skips the sample (src keeps its previous value in the shader).
+template <int LAYOUT, int ILLUM, bool NGATE, bool SOF>
+__device__ __forceinline__ bool shade_sample(const DevParams &P, const SharedTables &S, f3 pos, f3 dir, float4 &src)
+{
+    constexpr bool GRAD = (ILLUM == ILLUM_GRADIENT);   // ILLUM_GRADIENT => USE_NOISE_GRADIENTS, inc_header.glsl:17-19
+    float4 vd = fetch_field<LAYOUT, true>(P, pos.x, pos.y, pos.z);                  // :44
+    float sc = 0.0f;
+    if (P.tfMode == TF_SCALAR) sc = fetch_scalar(P, pos.x, pos.y, pos.z);            // :52
+    float4 tf = tf_lookup(S.tf, tf_index(P, vd, sc));                               // :54
+    // gate :59-61 (scalarData.g > -0.0001 is always true for a LUMINANCE8 texture)
+    if (P.gateMode == GATE_TF_ALPHA && !(tf.w > 0.05f)) return false;
+    if (GRAD) {
+        float4 il = compute_lic_grad<LAYOUT, SOF>(P, S.kw, pos, vd);                // :64
+        il.w *= P.licScale;                                                         // :67
+        src = illum_gradient(P, S.opac, il, tf, pos, dir);
+    } else {
+        float il = compute_lic_scalar<LAYOUT, NGATE, SOF>(P, S.kw, pos, vd) * P.licScale;
+        if (ILLUM == ILLUM_MALLO) src = illum_mallo(P, S.opac, il, tf, pos, dir, mk3(vd.x, vd.y, vd.z));
+        else if (ILLUM == ILLUM_ZOECKLER) src = illum_zoeckler(P, S.opac, il, tf, pos, dir, mk3(vd.x, vd.y, vd.z));
+        else src = illum_lic(P, S.opac, il, tf);
+    }
+    return true;
+}
+
+// lic3d_fragment.glsl:83-84: src.rgb *= src.a; dest = clamp((1 - dest.a) src + dest, 0, 1)
+__device__ __forceinline__ void composite(float4 &dest, float4 src)
+{
+    const float k = 1.0f - dest.w;
+    dest.x = clamp01(fmaf(k, src.x * src.w, dest.x));
+    dest.y = clamp01(fmaf(k, src.y * src.w, dest.y));
+    dest.z = clamp01(fmaf(k, src.z * src.w, dest.z));
+    dest.w = clamp01(fmaf(k, src.w, dest.w));
+}
+
+// ray set-up in texture space (lic3d_fragment.glsl:12-21), uncontracted fp32
+__device__ __forceinline__ void ray_setup(const DevParams &P, const float e[3], f3 &pos, f3 &dir, f3 &dstep)
+{
+    pos = mk3(__fmul_rn(e[0], P.scaleVol[0]), __fmul_rn(e[1], P.scaleVol[1]), __fmul_rn(e[2], P.scaleVol[2]));
+    f3 gd = normalize_rn(mk3(__fsub_rn(e[0], P.camera[0]), __fsub_rn(e[1], P.camera[1]), __fsub_rn(e[2], P.camera[2])));
+    dir = mk3(__fmul_rn(gd.x, P.scaleVol[0]), __fmul_rn(gd.y, P.scaleVol[1]), __fmul_rn(gd.z, P.scaleVol[2]));
+    dstep = mk3(__fmul_rn(dir.x, P.stepSize), __fmul_rn(dir.y, P.stepSize), __fmul_rn(dir.z, P.stepSize));
+}
+__device__ __forceinline__ bool outside_box(const DevParams &P, f3 pos)
+{
+    // any(clamp(pos, 0, texMax) - pos), lic3d_fragment.glsl:91
+    return pos.x < 0.0f || pos.x > P.texMax[0] || pos.y < 0.0f || pos.y > P.texMax[1] || pos.z < 0.0f || pos.z > P.texMax[2];
+}
+
+// K1 (per-ray variant) ------------------------------------------------------------------------------------
+// One thread marches one ray front to back.  Kept as the literal form of the fragment shader and as a cross-check
+// of the sample-parallel pipeline below (VV_OPT_RAYCAST_MODE = 0); it under-fills the GPU for small images.
 template <int LAYOUT, int ILLUM, bool NGATE, bool SOF>
 __global__ void __launch_bounds__(256) lic_raycast_kernel(const __grid_constant__ DevParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SharedTables &S = *reinterpret_cast<SharedTables *>(smem_raw);
     load_tables(P, S);
-    constexpr bool GRAD = (ILLUM == ILLUM_GRADIENT);   // ILLUM_GRADIENT => USE_NOISE_GRADIENTS, inc_header.glsl:17-19
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lx = (warp & 1) * 8 + (lane & 7);
@@ -315,48 +365,22 @@ __global__ void __launch_bounds__(256) lic_raycast_kernel(const __grid_constant_
         unsigned int nsamples = 0;
         float e[3];
         if (px < P.width && py < P.height && pixel_ray(P, px, py, e)) {
-            // lic3d_fragment.glsl:12-21
-            f3 pos = mk3(__fmul_rn(e[0], P.scaleVol[0]), __fmul_rn(e[1], P.scaleVol[1]), __fmul_rn(e[2], P.scaleVol[2]));
-            f3 gd = normalize_rn(mk3(__fsub_rn(e[0], P.camera[0]), __fsub_rn(e[1], P.camera[1]), __fsub_rn(e[2], P.camera[2])));
-            f3 dir = mk3(__fmul_rn(gd.x, P.scaleVol[0]), __fmul_rn(gd.y, P.scaleVol[1]), __fmul_rn(gd.z, P.scaleVol[2]));
-            f3 dstep = mk3(__fmul_rn(dir.x, P.stepSize), __fmul_rn(dir.y, P.stepSize), __fmul_rn(dir.z, P.stepSize));
+            f3 pos, dir, dstep;
+            ray_setup(P, e, pos, dir, dstep);
             const unsigned int maxSamples = (unsigned int)P.numIter * (unsigned int)P.numIter;   // nested loops :38-40
             float src_a = 0.0f;
             for (;;) {
                 ++nsamples;
-                float4 vd = fetch_field<LAYOUT, true>(P, pos.x, pos.y, pos.z);                  // :44
-                float sc = 0.0f;
-                if (P.tfMode == TF_SCALAR) sc = fetch_scalar(P, pos.x, pos.y, pos.z);            // :52
-                float4 tf = tf_lookup(S.tf, tf_index(P, vd, sc));                               // :54
-                // gate :59-61 (scalarData.g > -0.0001 is always true for a LUMINANCE8 texture)
-                const bool gate = (P.gateMode == GATE_TF_ALPHA) ? (tf.w > 0.05f) : true;
-                if (gate) {
-                    float4 src;
-                    if (GRAD) {
-                        float4 il = compute_lic_grad<LAYOUT, SOF>(P, S.kw, pos, vd);            // :64
-                        il.w *= P.licScale;                                                     // :67
-                        src = illum_gradient(P, S.opac, il, tf, pos, dir);
-                    } else {
-                        float il = compute_lic_scalar<LAYOUT, NGATE, SOF>(P, S.kw, pos, vd) * P.licScale;
-                        if (ILLUM == ILLUM_MALLO) src = illum_mallo(P, S.opac, il, tf, pos, dir, mk3(vd.x, vd.y, vd.z));
-                        else if (ILLUM == ILLUM_ZOECKLER) src = illum_zoeckler(P, S.opac, il, tf, pos, dir, mk3(vd.x, vd.y, vd.z));
-                        else src = illum_lic(P, S.opac, il, tf);
-                    }
-                    // :83-84
-                    const float k = 1.0f - dest.w;
-                    dest.x = clamp01(fmaf(k, src.x * src.w, dest.x));
-                    dest.y = clamp01(fmaf(k, src.y * src.w, dest.y));
-                    dest.z = clamp01(fmaf(k, src.z * src.w, dest.z));
-                    dest.w = clamp01(fmaf(k, src.w, dest.w));
+                float4 src;
+                if (shade_sample<LAYOUT, ILLUM, NGATE, SOF>(P, S, pos, dir, src)) {
+                    composite(dest, src);
                     src_a = src.w;
                 }
                 // :88-93
                 pos.x = __fadd_rn(pos.x, dstep.x);
                 pos.y = __fadd_rn(pos.y, dstep.y);
                 pos.z = __fadd_rn(pos.z, dstep.z);
-                const bool outside = pos.x < 0.0f || pos.x > P.texMax[0] || pos.y < 0.0f || pos.y > P.texMax[1] ||
-                                     pos.z < 0.0f || pos.z > P.texMax[2] || (src_a > 0.95f);   // Q4: src.a
-                if (outside || nsamples >= maxSamples) break;
+                if (outside_box(P, pos) || (src_a > 0.95f) || nsamples >= maxSamples) break;   // Q4: src.a
             }
         }
         const int o = lb * kBlockPixels + ly * kBlockDim + lx;
@@ -365,6 +389,154 @@ __global__ void __launch_bounds__(256) lic_raycast_kernel(const __grid_constant_
         if (P.sampleCounter) {
             unsigned int tot = __reduce_add_sync(0xffffffffu, nsamples);
             if (lane == 0 && tot) atomicAdd(P.sampleCounter, (unsigned long long)tot);
+        }
+    }
+}
+
+// K1 (sample-parallel pipeline) ----------------------------------------------------------------------------
+// The LIC integral of a ray sample does not depend on any other sample; only the compositing and the
+// `src.a > 0.95` termination are sequential along a ray.  So the frame is computed in three kernels:
+//   ray_setup_kernel     one warp per 8x4 ray tile: entry point, direction, sample count n (march without shading),
+//                        slot allocation in the src buffer, work items (tile, k) of the first depth window
+//   lic_sample_kernel    persistent warps pull items (tile, k) from a queue; the 32 lanes shade sample k of the 32
+//                        rays of the tile (the dominant kernel: perfectly balanced, full occupancy at any image size)
+//   composite_kernel     one thread per ray: front-to-back over-operator in sample order with the shader's clamp and
+//                        early termination; emits the next window's items for rays still alive
+// Depth windows bound the speculative work past an early termination (4, 8, 16, ... samples); when the transfer
+// function cannot produce src.a > 0.95 a single window covers the whole ray.
+
+__device__ __forceinline__ int tile_pixel(const DevParams &P, int lt, int lane, int &px, int &py)
+{
+    // local tile lt = local block * 8 + sub-tile; sub-tiles 8x4 pixels arranged 2 x 4 inside the 16x16 block
+    const int lb = lt >> 3, sub = lt & 7;
+    const int b = P.rank + lb * P.world;
+    const int lx = (sub & 1) * 8 + (lane & 7), ly = (sub >> 1) * 4 + (lane >> 3);
+    px = (b % P.nBlocksX) * kBlockDim + lx;
+    py = (b / P.nBlocksX) * kBlockDim + ly;
+    return lb * kBlockPixels + ly * kBlockDim + lx;
+}
+
+__global__ void __launch_bounds__(256) ray_setup_kernel(const __grid_constant__ DevParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const int nTiles = P.nLocalBlocks * 8;
+    for (int lt = blockIdx.x * 8 + (threadIdx.x >> 5); lt < nTiles; lt += gridDim.x * 8) {
+        int px, py;
+        const int o = tile_pixel(P, lt, lane, px, py);
+        int n = 0;
+        f3 pos = mk3(0, 0, 0), dir = mk3(0, 0, 0), dstep;
+        float e[3];
+        if (px < P.width && py < P.height && pixel_ray(P, px, py, e)) {
+            ray_setup(P, e, pos, dir, dstep);
+            const int maxSamples = P.numIter * P.numIter;
+            f3 q = pos;
+            for (;;) {                                  // the march of lic3d_fragment.glsl:38-95 without the shading
+                ++n;
+                q.x = __fadd_rn(q.x, dstep.x); q.y = __fadd_rn(q.y, dstep.y); q.z = __fadd_rn(q.z, dstep.z);
+                if (outside_box(P, q) || n >= maxSamples) break;
+            }
+        }
+        const int nmax = __reduce_max_sync(0xffffffffu, n);
+        unsigned int base = 0;
+        if (lane == 0 && nmax > 0) base = atomicAdd(P.slotAlloc, (unsigned int)nmax);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const int ray = lt * 32 + lane;
+        P.rayA[ray] = make_float4(pos.x, pos.y, pos.z, __int_as_float(n));
+        P.rayB[ray] = make_float4(dir.x, dir.y, dir.z, __int_as_float(n > 0 ? 0 : -1));   // state: consumed samples, < 0 = finished
+        if (lane == 0) {
+            P.tileRec[lt] = make_uint2(base, (unsigned int)nmax);
+            if (nmax > 0) atomicMax(P.nMaxGlobal, (unsigned int)nmax);
+        }
+        P.tiles[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (P.samplesPerPixel) P.samplesPerPixel[o] = 0;
+        // the first window's work items are emitted by composite_kernel run on the empty window [0,0), after the
+        // host has sized the src / item buffers from slotAlloc
+    }
+}
+
+template <int LAYOUT, int ILLUM, bool NGATE, bool SOF>
+__global__ void __launch_bounds__(256) lic_sample_kernel(const __grid_constant__ DevParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SharedTables &S = *reinterpret_cast<SharedTables *>(smem_raw);
+    const unsigned int nItems = *P.itemCount;
+    if (nItems == 0) return;
+    load_tables(P, S);
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned int i = 0;
+        if (lane == 0) i = atomicAdd(P.itemHead, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= nItems) break;
+        const uint2 it = P.items[i];
+        const int ray = (int)it.x * 32 + lane;
+        const int k = (int)it.y;
+        const float4 A = P.rayA[ray];
+        const int n = __float_as_int(A.w);
+        if (k >= n) continue;
+        const float4 B = P.rayB[ray];
+        if (__float_as_int(B.w) < 0) continue;            // ray finished in an earlier window
+        const f3 dir = mk3(B.x, B.y, B.z);
+        const f3 dstep = mk3(__fmul_rn(dir.x, P.stepSize), __fmul_rn(dir.y, P.stepSize), __fmul_rn(dir.z, P.stepSize));
+        f3 pos = mk3(A.x, A.y, A.z);
+        for (int j = 0; j < k; ++j) {                      // pos += dir * stepSize, k times, as the shader accumulates it
+            pos.x = __fadd_rn(pos.x, dstep.x); pos.y = __fadd_rn(pos.y, dstep.y); pos.z = __fadd_rn(pos.z, dstep.z);
+        }
+        float4 src;
+        if (!shade_sample<LAYOUT, ILLUM, NGATE, SOF>(P, S, pos, dir, src)) src = make_float4(0.f, 0.f, 0.f, -1.0f);   // gated
+        const uint2 tr = P.tileRec[it.x];
+        P.src[((size_t)tr.x + k) * 32 + lane] = src;
+    }
+}
+
+__global__ void __launch_bounds__(256) composite_kernel(const __grid_constant__ DevParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const int nTiles = P.nLocalBlocks * 8;
+    for (int lt = blockIdx.x * 8 + (threadIdx.x >> 5); lt < nTiles; lt += gridDim.x * 8) {
+        const uint2 tr = P.tileRec[lt];
+        const int nmax = (int)tr.y;
+        if (nmax <= P.win0) continue;                      // warp-uniform: nothing of this tile in the window
+        const int ray = lt * 32 + lane;
+        const float4 A = P.rayA[ray];
+        float4 B = P.rayB[ray];
+        const int n = __float_as_int(A.w);
+        int state = __float_as_int(B.w);
+        int px, py;
+        const int o = tile_pixel(P, lt, lane, px, py);
+        unsigned int consumed = 0;
+        if (state >= 0) {
+            float4 dest = P.tiles[o];
+            const int kend = min(n, P.win1);
+            bool done = false;
+            for (int k = P.win0; k < kend; ++k) {
+                const float4 s = P.src[((size_t)tr.x + k) * 32 + lane];
+                ++consumed;
+                if (s.w >= 0.0f) {
+                    composite(dest, s);
+                    if (s.w > 0.95f) { done = true; break; }          // early ray termination on src.a (Q4)
+                }
+            }
+            if (kend >= n) done = true;
+            state += (int)consumed;
+            P.tiles[o] = dest;
+            if (P.samplesPerPixel) P.samplesPerPixel[o] = (unsigned int)state;
+            if (done) state = -1 - state;
+            B.w = __int_as_float(state);
+            P.rayB[ray] = B;
+        }
+        if (P.sampleCounter) {
+            unsigned int tot = __reduce_add_sync(0xffffffffu, consumed);
+            if (lane == 0 && tot) atomicAdd(P.sampleCounter, (unsigned long long)tot);
+        }
+        // items of the next window for rays still alive
+        const int live = __reduce_max_sync(0xffffffffu, state >= 0 ? n : 0);
+        const int cnt = min(live, P.win2) - P.win1;
+        if (cnt > 0) {
+            unsigned int ib = 0;
+            if (lane == 0) ib = atomicAdd(P.itemCountNext, (unsigned int)cnt);
+            ib = __shfl_sync(0xffffffffu, ib, 0);
+            for (int k = lane; k < cnt; k += 32) P.itemsNext[ib + k] = make_uint2((unsigned int)lt, (unsigned int)(P.win1 + k));
         }
     }
 }
@@ -516,6 +688,68 @@ static cudaError_t launch_raycast_layout(const DevParams &P, int illum, bool nga
 }
 
 size_t shared_table_bytes() { return sizeof(SharedTables); }
+
+cudaError_t launch_ray_setup(const DevParams &P, int grid, cudaStream_t st)
+{
+    ray_setup_kernel<<<grid, 256, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_composite(const DevParams &P, int grid, cudaStream_t st)
+{
+    composite_kernel<<<grid, 256, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+// persistent grid: (resident CTAs per SM of this instantiation) x (SM count), capped by ctas_per_sm
+template <class K>
+static int persistent_ctas(K kernel, size_t smem, int num_sms_times_cap)
+{
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem) != cudaSuccess || occ < 1) occ = 1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int cap = num_sms_times_cap > 0 ? num_sms_times_cap / sms : occ;
+    return sms * (cap > 0 && cap < occ ? cap : occ);
+}
+
+template <int LAYOUT, int ILLUM, bool NGATE>
+static cudaError_t launch_sample_sof(const DevParams &P, bool sof, int grid, size_t smem, cudaStream_t st)
+{
+    if (sof) {
+        static int g = persistent_ctas(lic_sample_kernel<LAYOUT, ILLUM, NGATE, true>, smem, 0);
+        lic_sample_kernel<LAYOUT, ILLUM, NGATE, true><<<grid > 0 ? grid : g, 256, smem, st>>>(P);
+    } else {
+        static int g = persistent_ctas(lic_sample_kernel<LAYOUT, ILLUM, NGATE, false>, smem, 0);
+        lic_sample_kernel<LAYOUT, ILLUM, NGATE, false><<<grid > 0 ? grid : g, 256, smem, st>>>(P);
+    }
+    return cudaGetLastError();
+}
+
+template <int LAYOUT>
+static cudaError_t launch_sample_layout(const DevParams &P, int illum, bool ngate, bool sof, int grid, size_t smem, cudaStream_t st)
+{
+    switch (illum) {
+    case ILLUM_GRADIENT: return launch_sample_sof<LAYOUT, ILLUM_GRADIENT, false>(P, sof, grid, smem, st);
+    case ILLUM_MALLO:
+        return ngate ? launch_sample_sof<LAYOUT, ILLUM_MALLO, true>(P, sof, grid, smem, st)
+                     : launch_sample_sof<LAYOUT, ILLUM_MALLO, false>(P, sof, grid, smem, st);
+    case ILLUM_ZOECKLER:
+        return ngate ? launch_sample_sof<LAYOUT, ILLUM_ZOECKLER, true>(P, sof, grid, smem, st)
+                     : launch_sample_sof<LAYOUT, ILLUM_ZOECKLER, false>(P, sof, grid, smem, st);
+    default:
+        return ngate ? launch_sample_sof<LAYOUT, ILLUM_NONE, true>(P, sof, grid, smem, st)
+                     : launch_sample_sof<LAYOUT, ILLUM_NONE, false>(P, sof, grid, smem, st);
+    }
+}
+
+cudaError_t launch_lic_sample(const DevParams &P, int layout, int illum, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st)
+{
+    const size_t smem = sizeof(SharedTables);
+    if (layout == LAYOUT_PAIR) return launch_sample_layout<LAYOUT_PAIR>(P, illum, noise_gate, speed_of_flow, grid, smem, st);
+    return launch_sample_layout<LAYOUT_F4>(P, illum, noise_gate, speed_of_flow, grid, smem, st);
+}
 
 cudaError_t launch_lic_raycast(const DevParams &P, int layout, int illum, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st)
 {

@@ -9,6 +9,10 @@ struct DevParams;
 
 size_t shared_table_bytes();
 cudaError_t launch_lic_raycast(const DevParams &P, int layout, int illum, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st);
+// sample-parallel pipeline (ray_setup -> [lic_sample -> composite] per depth window)
+cudaError_t launch_ray_setup(const DevParams &P, int grid, cudaStream_t st);
+cudaError_t launch_lic_sample(const DevParams &P, int layout, int illum, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st);
+cudaError_t launch_composite(const DevParams &P, int grid, cudaStream_t st);
 cudaError_t launch_volume_raycast(const DevParams &P, int layout, int grid, cudaStream_t st);
 cudaError_t launch_lic_volume(const DevParams &P, int layout, bool grad, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st);
 cudaError_t launch_unblock(const float4 *tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY, int width, int height,

@@ -28,6 +28,8 @@ using namespace vvb200;
             return fail(VV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));               \
     } while (0)
 
+static const int kNumCounters = 16;
+
 template <class T>
 struct DevBuf {
     T *p = nullptr;
@@ -108,7 +110,14 @@ struct VVRenderer {
     int nbx = 0, nby = 0, n_local_blocks = 0, blocks_per_rank = 0;
     DevBuf<float4> tiles, frame;
     DevBuf<uchar4> frame8, display8;
-    DevBuf<unsigned long long> counters;   // [0] ray samples, [1] block queue (low 32 bits)
+    DevBuf<unsigned long long> counters;   // as unsigned int[16]: [0,1] ray samples (u64), [2] block queue, [3] src rows,
+                                           // [4],[5] item counts (ping-pong), [6] item queue head, [7] max samples per ray
+    unsigned int *host_counters = nullptr; // pinned
+    // sample-parallel pipeline state
+    DevBuf<float4> rayA, rayB, src;
+    DevBuf<uint2> tileRec, items[2];
+    int raycast_mode = 1;                  // 1: sample-parallel pipeline (default), 0: one thread per ray
+    int lic_ctas_per_sm = 0;               // 0: as many as are resident (occupancy query)
     bool frame_valid = false;
     int launches = 0;
 
@@ -202,7 +211,7 @@ static int ensure_frame(VVRenderer *r)
     CU(r->frame.ensure(npx));
     CU(r->frame8.ensure(npx));
     CU(r->display8.ensure(npx));
-    CU(r->counters.ensure(2));
+    CU(r->counters.ensure(kNumCounters / 2));
     return VV_OK;
 }
 
@@ -477,6 +486,78 @@ static int upload_noise(VVRenderer *r, const uint8_t *data, const int dims[3], i
     return VV_OK;
 }
 
+// Can a ray sample ever reach src.a > 0.95 (the shader's early-termination test, lic3d_fragment.glsl:91)?  src.a =
+// 1 - (1 - opac * tf.a)^alphaCorrection with both factors linearly interpolated table entries, so the table maxima
+// bound it.  If not, one depth window covers the whole ray and nothing is computed speculatively.
+static bool termination_possible(const VVRenderer *r, const Uniforms &u)
+{
+    int amax = 0, omax = 0;
+    for (int i = 0; i < 256; ++i) { amax = std::max<int>(amax, r->tf[5 * i + 3]); omax = std::max<int>(omax, r->tf[5 * i + 4]); }
+    const double a = (amax / 255.0) * (omax / 255.0);
+    const double corrected = 1.0 - std::pow(1.0 - a, (double)u.alphaCorrection);
+    return corrected > 0.94;   // margin for fp32 rounding
+}
+
+// K1 as three kernels: ray_setup -> [lic_sample -> composite] per depth window (see vv_kernels.cu)
+static int render_sample_parallel(VVRenderer *r, DevParams &P)
+{
+    const int nTiles = r->n_local_blocks * 8;
+    if (nTiles == 0) return VV_OK;
+    CU(r->rayA.ensure((size_t)nTiles * 32));
+    CU(r->rayB.ensure((size_t)nTiles * 32));
+    CU(r->tileRec.ensure((size_t)nTiles));
+    unsigned int *cnt = reinterpret_cast<unsigned int *>(r->counters.p);
+    P.rayA = r->rayA.p; P.rayB = r->rayB.p; P.tileRec = r->tileRec.p;
+    P.slotAlloc = cnt + 3; P.nMaxGlobal = cnt + 7; P.itemHead = cnt + 6;
+    const int setup_grid = std::max(1, std::min((nTiles + 7) / 8, r->num_sms * 8));
+    CU(launch_ray_setup(P, setup_grid, r->stream));
+    ++r->launches;
+    // size the src / item buffers from the allocation the set-up made (one small read-back per frame)
+    if (!r->host_counters) CU(cudaMallocHost((void **)&r->host_counters, kNumCounters * sizeof(unsigned int)));
+    CU(cudaMemcpyAsync(r->host_counters, cnt, kNumCounters * sizeof(unsigned int), cudaMemcpyDeviceToHost, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    const size_t rows = r->host_counters[3];
+    const int nmax = (int)r->host_counters[7];
+    if (rows == 0 || nmax == 0) return VV_OK;
+    CU(r->src.ensure(rows * 32));
+    CU(r->items[0].ensure(rows));
+    CU(r->items[1].ensure(rows));
+    P.src = r->src.p;
+    // depth windows: whole ray at once when no sample can trigger the early termination, else 4, 8, 16, ... samples
+    std::vector<int> w;
+    w.push_back(0);
+    if (!termination_possible(r, derive_uniforms(r))) w.push_back(nmax);
+    else for (int len = 4; w.back() < nmax; len *= 2) w.push_back(std::min(nmax, w.back() + len));
+    w.push_back(w.back());   // sentinel: nothing after the last window
+    const int comp_grid = setup_grid;
+    const int lic_grid = r->num_sms * r->lic_ctas_per_sm;   // 0: launcher uses the occupancy of the instantiation
+    const bool ngate = r->illum_mode != ILLUM_GRADIENT && r->noise_gate;
+    // empty window [0,0): emits the work items of the first real window
+    int cur = 0;
+    P.win0 = 0; P.win1 = 0; P.win2 = w[1];
+    P.itemsNext = r->items[cur].p; P.itemCountNext = cnt + 4 + cur;
+    P.sampleCounter = nullptr;
+    CU(launch_composite(P, comp_grid, r->stream));
+    ++r->launches;
+    P.sampleCounter = r->count_samples ? r->counters.p : nullptr;
+    CU(cudaEventRecord(r->ev0, r->stream));
+    for (size_t p = 0; p + 2 < w.size(); ++p) {
+        P.win0 = w[p]; P.win1 = w[p + 1]; P.win2 = w[p + 2];
+        P.items = r->items[cur].p; P.itemCount = cnt + 4 + cur;
+        P.itemsNext = r->items[cur ^ 1].p; P.itemCountNext = cnt + 4 + (cur ^ 1);
+        if (p > 0) {
+            CU(cudaMemsetAsync(cnt + 6, 0, sizeof(unsigned int), r->stream));          // queue head
+        }
+        CU(cudaMemsetAsync(cnt + 4 + (cur ^ 1), 0, sizeof(unsigned int), r->stream));  // next window's item count
+        CU(launch_lic_sample(P, r->field_layout, r->illum_mode, ngate, r->speed_of_flow, lic_grid, r->stream));
+        if (p == 0) CU(cudaEventRecord(r->ev1, r->stream));   // first window = the bulk of the work (all of it in single-window mode)
+        CU(launch_composite(P, comp_grid, r->stream));
+        r->launches += 2;
+        cur ^= 1;
+    }
+    return VV_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ C ABI
 extern "C" {
 
@@ -530,6 +611,7 @@ void vv_destroy(VVRenderer *r)
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
     if (r->own_stream) cudaStreamDestroy(r->own_stream);
+    if (r->host_counters) cudaFreeHost(r->host_counters);
     delete r;
 }
 
@@ -834,6 +916,12 @@ int vv_set_option(VVRenderer *r, int option, int value)
         r->licvol_size = value; break;
     case VV_OPT_SPEC_EXP: r->spec_exp = (float)value; break;
     case VV_OPT_SAMPLE_MAP: r->sample_map = value != 0; break;
+    case VV_OPT_RAYCAST_MODE:
+        if (value != 0 && value != 1) return fail(VV_ERR_INVALID, "bad raycast mode");
+        r->raycast_mode = value; break;
+    case VV_OPT_LIC_CTAS_PER_SM:
+        if (value < 0 || value > 8) return fail(VV_ERR_INVALID, "bad CTAs per SM");
+        r->lic_ctas_per_sm = value; break;
     default: return fail(VV_ERR_INVALID, "unknown option");
     }
     r->frame_valid = false;
@@ -857,22 +945,30 @@ int vv_render(VVRenderer *r, int update)
     DevParams P;
     int rc = fill_params(r, P, true);
     if (rc) return rc;
-    CU(cudaMemsetAsync(r->counters.p, 0, 2 * sizeof(unsigned long long), r->stream));
+    CU(cudaMemsetAsync(r->counters.p, 0, kNumCounters * sizeof(unsigned int), r->stream));
     const int grid = persistent_grid(r, r->n_local_blocks);
-    CU(cudaEventRecord(r->ev0, r->stream));
     switch (r->technique) {
     case VV_VOLIC_RAYCAST:
-        CU(launch_lic_raycast(P, r->field_layout, r->illum_mode, r->illum_mode != ILLUM_GRADIENT && r->noise_gate, r->speed_of_flow, grid, r->stream));
+        if (r->raycast_mode == 0) {
+            CU(cudaEventRecord(r->ev0, r->stream));
+            CU(launch_lic_raycast(P, r->field_layout, r->illum_mode, r->illum_mode != ILLUM_GRADIENT && r->noise_gate, r->speed_of_flow, grid, r->stream));
+            CU(cudaEventRecord(r->ev1, r->stream));
+            ++r->launches;
+        } else {
+            rc = render_sample_parallel(r, P);
+            if (rc) return rc;
+        }
         break;
     case VV_VOLIC_LICVOLUME:
     case VV_VOLIC_VOLUMEANI:
+        CU(cudaEventRecord(r->ev0, r->stream));
         CU(launch_volume_raycast(P, r->field_layout, grid, r->stream));
+        CU(cudaEventRecord(r->ev1, r->stream));
+        ++r->launches;
         break;
     default:
         return fail(VV_ERR_INVALID, "technique not implemented");
     }
-    CU(cudaEventRecord(r->ev1, r->stream));
-    ++r->launches;
     if (r->world == 1) return run_unblock(r, r->tiles.p, 1, r->blocks_per_rank);
     r->frame_valid = false;   // multi-GPU: the caller gathers tile buffers and calls vv_assemble_tiles
     return VV_OK;

@@ -67,7 +67,10 @@ def render_distributed(renderer, group=None):
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    renderer.setStream(torch.cuda.current_stream().cuda_stream)   # kernels and NCCL on one stream: no cross-stream race
+    st = torch.cuda.current_stream().cuda_stream   # kernels and NCCL on one stream: no cross-stream race
+    if st == 0:
+        raise RuntimeError("render_distributed needs a non-default torch stream (torch.cuda.set_stream(torch.cuda.Stream()))")
+    renderer.setStream(st)
     renderer.render(True)
     ptr, bpr, _ = renderer.tileBuffer()
     local = device_tensor(ptr, (bpr * 256 * 4,), torch.float32)
@@ -84,7 +87,10 @@ def update_lic_volume_distributed(renderer, depth, group=None):
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     z0, z1 = slab_range(depth, rank, world)
-    renderer.setStream(torch.cuda.current_stream().cuda_stream)
+    st = torch.cuda.current_stream().cuda_stream
+    if st == 0:
+        raise RuntimeError("update_lic_volume_distributed needs a non-default torch stream")
+    renderer.setStream(st)
     renderer.setLICVolumeSlab(z0, z1)
     renderer.updateLICVolume()
     ptr, dims = renderer.licVolumePtr()

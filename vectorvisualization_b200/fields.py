@@ -190,7 +190,10 @@ def tf_preset(name):
         tf[:, 0] = np.floor(255 * r + 0.5)
         tf[:, 1] = np.floor(255 * g + 0.5)
         tf[:, 2] = np.floor(255 * b + 0.5)
-        tf[:, 3] = np.floor(255 * np.clip((i - 20) / 235.0, 0, 1) + 0.5)
+        # semi-transparent (alpha <= 0.1): no ray sample can reach src.a > 0.95, so the shader's early termination
+        # (Q4) never fires and every ray is marched over its full chord -- the ray-sample count of a frame is then the
+        # analytic one (~21.7 M for cfg3 at the default view)
+        tf[:, 3] = np.floor(255 * 0.1 * np.clip((i - 20) / 235.0, 0, 1) + 0.5)
         tf[:, 4] = i
         return tf
     if name == "op-high":
