@@ -1,0 +1,36 @@
+/* ref_api.h -- TEST INFRASTRUCTURE ONLY: C interface of oracle/_ref/libvv_ref.so (see build_ref.py) */
+#pragma once
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct RefTex {
+    const void *data;
+    int dim[3];
+    int fmt;    /* glsl::Fmt  */
+    int wrap;   /* glsl::Wrap */
+} RefTex;
+
+typedef struct RefUniforms {
+    RefTex volume, scalar, noise, kernel, tf_rgba, tf_alphaopac, licvol, zoeckler, mallo_diff, mallo_spec;
+    float texMax[4], scaleVol[4], scaleVolInv[4];
+    float stepSize;
+    float gradient[3];
+    int numIterations;
+    float alphaCorrection;
+    float licParams[3];
+    float licKernel[3];
+    float camera[4];              /* gl_ModelViewMatrixInverse[3] */
+    float light_position[4];      /* gl_LightSource[0].position */
+    float light_ambient[4], light_diffuse[4], light_specular[4];
+    float spot_exponent;
+} RefUniforms;
+
+/* sets the gl_* state shared by all programs */
+void vvref_set_gl_state(const RefUniforms *u);
+
+#ifdef __cplusplus
+}
+#endif

@@ -792,6 +792,30 @@ int vvo_pixel_ray(const VVOScene *s, int x, int y, float entry[3], float dir[3])
     return 1;
 }
 
+/* entry points of all pixel rays of [x0,x1) x [y0,y1): out[(y-y0)*(x1-x0) + (x-x0)][4] = (entry.xyz, hit ? 1 : 0) */
+void vvo_pixel_rays(const VVOScene *s, int x0, int y0, int x1, int y1, float *out)
+{
+    Ctx c;
+    make_ctx(s, c);
+    for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+            float *o = out + 4 * ((size_t)(y - y0) * (x1 - x0) + (x - x0));
+            V3 e;
+            if (pixel_ray(c, x, y, e)) { o[0] = e.x; o[1] = e.y; o[2] = e.z; o[3] = 1.0f; }
+            else { o[0] = o[1] = o[2] = o[3] = 0.0f; }
+        }
+}
+
+/* effective scaleVol / scaleVolInv / texMax uniforms of the ray-cast program (incl. Q1): out[9] */
+void vvo_scale_uniforms(const VVOScene *s, float *out)
+{
+    Ctx c;
+    make_ctx(s, c);
+    out[0] = c.scaleVol.x; out[1] = c.scaleVol.y; out[2] = c.scaleVol.z;
+    out[3] = c.scaleVolInv.x; out[4] = c.scaleVolInv.y; out[5] = c.scaleVolInv.z;
+    out[6] = c.texMax.x; out[7] = c.texMax.y; out[8] = c.texMax.z;
+}
+
 /* VectorDataSet::loadData, dataset.cpp:144-176 */
 void vvo_volume_geometry(const int size[3], const float slice_dist[3], float extent[3], float scale[3], float scale_inv[3], float center[3])
 {

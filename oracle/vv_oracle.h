@@ -106,6 +106,8 @@ void vvo_view(const VVOScene *s, float cam_obj[3], float rot[9]);
 void vvo_light_position(const VVOScene *s, float out[4]);
 /* per-pixel ray: returns 1 on hit; entry[3] = gl_TexCoord[0], dir[3] = normalize(entry - camera) */
 int vvo_pixel_ray(const VVOScene *s, int x, int y, float entry[3], float dir[3]);
+void vvo_pixel_rays(const VVOScene *s, int x0, int y0, int x1, int y1, float *out_xyzh);
+void vvo_scale_uniforms(const VVOScene *s, float *out9);
 /* dataset.cpp:144-176 */
 void vvo_volume_geometry(const int size[3], const float slice_dist[3],
                          float extent[3], float scale[3], float scale_inv[3], float center[3]);

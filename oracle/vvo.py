@@ -68,6 +68,8 @@ def lib():
         L.vvo_light_position.argtypes = [S, P]
         L.vvo_pixel_ray.argtypes = [S, I, I, P, P]; L.vvo_pixel_ray.restype = I
         L.vvo_volume_geometry.argtypes = [P, P, P, P, P, P]
+        L.vvo_pixel_rays.argtypes = [S, I, I, I, I, P]
+        L.vvo_scale_uniforms.argtypes = [S, P]
         L.vvo_pack_vector_field.argtypes = [P, P, P, I, I, I, P]
         L.vvo_pack_vector_field_u8.argtypes = [P, P, I, P]
         L.vvo_noise_gradients.argtypes = [P, P, P, P]

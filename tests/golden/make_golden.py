@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz from the REFERENCE'S OWN SHADER CODE (oracle/_ref/libvv_ref.so, built by
+oracle/build_ref.py from /root/reference/VectorVisualization/shader/*.glsl).  Run in the build container (where the
+reference is mounted); the vectors are committed so the GPU box can check both the oracle and the CUDA path against
+outputs of the reference without the reference being present.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from oracle import refshim  # noqa: E402
+from scenes import golden_scenes  # noqa: E402
+
+
+def main():
+    if not refshim.available():
+        raise SystemExit("oracle/_ref/libvv_ref.so missing: run python oracle/build_ref.py (needs /root/reference)")
+    for name, mk in golden_scenes().items():
+        s = mk()
+        r = refshim.RefScene(s)
+        img, cnt, tot = r.raycast()
+        s.licvol_fp16 = 0
+        lv = r.lic_volume((12, 12, 12))
+        nz, ny, nx = s.field.shape[:3]
+        lv_full = r.lic_volume((nx, ny, nz))
+        vimg, vcnt, vtot = r.raycast_licvolume(lv_full)
+        out = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(out, raycast=img, raycast_samples=cnt.astype(np.uint16), total=np.int64(tot),
+                            licvol12=lv, volraycast=vimg, volraycast_samples=vcnt.astype(np.uint16))
+        print("%-32s ray samples %7d  -> %s (%d bytes)" % (name, tot, os.path.basename(out), os.path.getsize(out)))
+
+
+if __name__ == "__main__":
+    main()

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvv_b200.so")
+LIB_PATH = os.environ.get("VV_B200_LIB") or os.path.join(_HERE, "libvv_b200.so")   # override only for A/B experiments
 
 # RenderTechnique, VV/types.h:63-71
 VOLIC_VOLUME, VOLIC_RAYCAST, VOLIC_SLICING, VOLIC_LICVOLUME, VOLIC_VOLUMEANI = range(5)

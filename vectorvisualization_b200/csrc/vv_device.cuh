@@ -50,6 +50,7 @@ struct DevParams {
     float licScale;               // licKernel.b * gradient.r
     float alphaCorr, specExp;
     int   numIter, nFwd, nBwd;
+    int   nFwdEff, nBwdEff;       // steps up to the last non-zero filter-kernel weight
     float texMax[3], scaleVol[3], scaleVolInv[3], lightPos[3], camera[3];
     // ---- view (double: bit-identical ray set-up on host oracle and device) ----
     double camD[3], rot[9], tanHalf, aspect, extent[3];
@@ -85,9 +86,8 @@ __device__ __forceinline__ void axis_clamp(float s, int n, int &i0, int &i1, flo
 {
     float u = fmaf(s, (float)n, -0.5f);
     u = fminf(fmaxf(u, 0.0f), (float)(n - 1));
-    float fl = floorf(u);
-    f = u - fl;
-    i0 = (int)fl;
+    i0 = __float2int_rd(u);             // one conversion-pipe op; the float floor comes back through I2FP
+    f = u - __int2float_rn(i0);
     i1 = min(i0 + 1, n - 1);
 }
 
@@ -96,9 +96,8 @@ __device__ __forceinline__ void axis_repeat(float s, int n, int &i0, float &f)
 {
     s = s - floorf(s);
     float u = fmaf(s, (float)n, -0.5f);
-    float fl = floorf(u);
-    f = u - fl;
-    i0 = (int)fl;
+    i0 = __float2int_rd(u);
+    f = u - __int2float_rn(i0);
     if (i0 < 0) i0 += n;
     if (i0 >= n) i0 -= n;
 }
@@ -113,79 +112,108 @@ __device__ __forceinline__ float2 h2f(unsigned int w)
     return __half22float2(h);
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2): two IEEE binary32 lanes per issue slot ----
+// The hot kernel is issue-bound (profiles/README.md), and ~half of its instructions are the sub + fma of the
+// trilinear lerps, so two lerps per instruction is the main lever.  Each lane is exactly the scalar operation.
+typedef unsigned long long pk2_t;
+__device__ __forceinline__ pk2_t pk2(float lo, float hi) { pk2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void up2(pk2_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ float lo2(pk2_t v) { float a, b; up2(v, a, b); return a; }
+__device__ __forceinline__ float hi2(pk2_t v) { float a, b; up2(v, a, b); return b; }
+__device__ __forceinline__ pk2_t fma2(pk2_t a, pk2_t b, pk2_t c) { pk2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ pk2_t add2(pk2_t a, pk2_t b) { pk2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ pk2_t sub2(pk2_t a, pk2_t b) { pk2_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ pk2_t mul2(pk2_t a, pk2_t b) { pk2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ pk2_t bc2(float f) { return pk2(f, f); }
+// a + f (b - a) in both lanes: the same sub + fma as lerpf()
+__device__ __forceinline__ pk2_t lerp2(pk2_t a, pk2_t b, pk2_t f) { return fma2(f, sub2(b, a), a); }
+__device__ __forceinline__ pk2_t h2pk(unsigned int w) { float2 t = h2f(w); return pk2(t.x, t.y); }
+__device__ __forceinline__ float hlo(unsigned int w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
+
+struct FieldVal { pk2_t rg; float b, a; };
+
 // ---- vector field: trilinear RGBA16F fetch, CLAMP_TO_EDGE (volumeSampler, VV/dataset.cpp:350-357) ----
 template <int LAYOUT, bool ALPHA>
-__device__ __forceinline__ float4 fetch_field(const DevParams &P, float px, float py, float pz)
+__device__ __forceinline__ FieldVal fetch_field_pk(const DevParams &P, float px, float py, float pz)
 {
     int x0, x1, y0, y1, z0, z1;
     float fx, fy, fz;
     axis_clamp(px, P.fnx, x0, x1, fx);
     axis_clamp(py, P.fny, y0, y1, fy);
     axis_clamp(pz, P.fnz, z0, z1, fz);
+    // 32-bit element indices (volumes up to 2^31 voxels), one zero-extended pointer add per load
     const unsigned int row = (unsigned int)P.fnx;
-    const unsigned int slab = row * (unsigned int)P.fny;
-    const unsigned int b00 = (unsigned int)z0 * slab + (unsigned int)y0 * row;
-    const unsigned int b10 = (unsigned int)z0 * slab + (unsigned int)y1 * row;
-    const unsigned int b01 = (unsigned int)z1 * slab + (unsigned int)y0 * row;
-    const unsigned int b11 = (unsigned int)z1 * slab + (unsigned int)y1 * row;
-    float4 r;
+    const unsigned int b00 = ((unsigned int)z0 * (unsigned int)P.fny + (unsigned int)y0) * row + (unsigned int)x0;
+    const unsigned int dy = (unsigned int)(y1 - y0) * row;                       // 0 at the clamped edge
+    const unsigned int dz = (unsigned int)(z1 - z0) * row * (unsigned int)P.fny;
+    const unsigned int b10 = b00 + dy, b01 = b00 + dz, b11 = b01 + dy;
+    const pk2_t fx2 = bc2(fx), fy2 = bc2(fy), fz2 = bc2(fz);
+    FieldVal r;
     if (LAYOUT == LAYOUT_PAIR) {
         const uint4 *F = P.field_pair;
-        uint4 a = ld_u4(F + b00 + x0), b = ld_u4(F + b10 + x0), c = ld_u4(F + b01 + x0), d = ld_u4(F + b11 + x0);
-        float2 a0 = h2f(a.x), a2 = h2f(a.z), b0 = h2f(b.x), b2 = h2f(b.z);
-        float2 c0 = h2f(c.x), c2 = h2f(c.z), d0 = h2f(d.x), d2 = h2f(d.z);
-        float2 a1 = h2f(a.y), a3 = h2f(a.w), b1 = h2f(b.y), b3 = h2f(b.w);
-        float2 c1 = h2f(c.y), c3 = h2f(c.w), d1 = h2f(d.y), d3 = h2f(d.w);
-        // x-lerp inside each pair
-        float ar = lerpf(a0.x, a2.x, fx), ag = lerpf(a0.y, a2.y, fx), ab = lerpf(a1.x, a3.x, fx);
-        float br = lerpf(b0.x, b2.x, fx), bg = lerpf(b0.y, b2.y, fx), bb = lerpf(b1.x, b3.x, fx);
-        float cr = lerpf(c0.x, c2.x, fx), cg = lerpf(c0.y, c2.y, fx), cb = lerpf(c1.x, c3.x, fx);
-        float dr = lerpf(d0.x, d2.x, fx), dg = lerpf(d0.y, d2.y, fx), db = lerpf(d1.x, d3.x, fx);
-        r.x = lerpf(lerpf(ar, br, fy), lerpf(cr, dr, fy), fz);
-        r.y = lerpf(lerpf(ag, bg, fy), lerpf(cg, dg, fy), fz);
-        r.z = lerpf(lerpf(ab, bb, fy), lerpf(cb, db, fy), fz);
+        // corner loads A = (y0,z0), B = (y1,z0), C = (y0,z1), D = (y1,z1); each holds texels x0 (.x,.y) and x0+1 (.z,.w)
+        const uint4 A = ld_u4(F + b00), B = ld_u4(F + b10), C = ld_u4(F + b01), D = ld_u4(F + b11);
+        const pk2_t rgA = lerp2(h2pk(A.x), h2pk(A.z), fx2), rgB = lerp2(h2pk(B.x), h2pk(B.z), fx2);
+        const pk2_t rgC = lerp2(h2pk(C.x), h2pk(C.z), fx2), rgD = lerp2(h2pk(D.x), h2pk(D.z), fx2);
+        r.rg = lerp2(lerp2(rgA, rgB, fy2), lerp2(rgC, rgD, fy2), fz2);
         if (ALPHA) {
-            float aa = lerpf(a1.y, a3.y, fx), ba = lerpf(b1.y, b3.y, fx);
-            float ca = lerpf(c1.y, c3.y, fx), da = lerpf(d1.y, d3.y, fx);
-            r.w = lerpf(lerpf(aa, ba, fy), lerpf(ca, da, fy), fz);
+            const pk2_t baA = lerp2(h2pk(A.y), h2pk(A.w), fx2), baB = lerp2(h2pk(B.y), h2pk(B.w), fx2);
+            const pk2_t baC = lerp2(h2pk(C.y), h2pk(C.w), fx2), baD = lerp2(h2pk(D.y), h2pk(D.w), fx2);
+            const pk2_t ba = lerp2(lerp2(baA, baB, fy2), lerp2(baC, baD, fy2), fz2);
+            up2(ba, r.b, r.a);
         } else {
-            r.w = 0.0f;
+            // blue only: pack the two z planes into one register pair for the x and y lerps
+            const pk2_t bAC = lerp2(pk2(hlo(A.y), hlo(C.y)), pk2(hlo(A.w), hlo(C.w)), fx2);
+            const pk2_t bBD = lerp2(pk2(hlo(B.y), hlo(D.y)), pk2(hlo(B.w), hlo(D.w)), fx2);
+            const pk2_t by = lerp2(bAC, bBD, fy2);
+            r.b = lerpf(lo2(by), hi2(by), fz);
+            r.a = 0.0f;
         }
     } else {
         const float4 *F = P.field_f4;
-        float4 t000 = ld_f4(F + b00 + x0), t100 = ld_f4(F + b00 + x1);
-        float4 t010 = ld_f4(F + b10 + x0), t110 = ld_f4(F + b10 + x1);
-        float4 t001 = ld_f4(F + b01 + x0), t101 = ld_f4(F + b01 + x1);
-        float4 t011 = ld_f4(F + b11 + x0), t111 = ld_f4(F + b11 + x1);
-        r.x = lerpf(lerpf(lerpf(t000.x, t100.x, fx), lerpf(t010.x, t110.x, fx), fy),
-                    lerpf(lerpf(t001.x, t101.x, fx), lerpf(t011.x, t111.x, fx), fy), fz);
-        r.y = lerpf(lerpf(lerpf(t000.y, t100.y, fx), lerpf(t010.y, t110.y, fx), fy),
-                    lerpf(lerpf(t001.y, t101.y, fx), lerpf(t011.y, t111.y, fx), fy), fz);
-        r.z = lerpf(lerpf(lerpf(t000.z, t100.z, fx), lerpf(t010.z, t110.z, fx), fy),
-                    lerpf(lerpf(t001.z, t101.z, fx), lerpf(t011.z, t111.z, fx), fy), fz);
-        if (ALPHA)
-            r.w = lerpf(lerpf(lerpf(t000.w, t100.w, fx), lerpf(t010.w, t110.w, fx), fy),
-                        lerpf(lerpf(t001.w, t101.w, fx), lerpf(t011.w, t111.w, fx), fy), fz);
-        else
-            r.w = 0.0f;
+        const unsigned int dx = (unsigned int)(x1 - x0);
+        const float4 t000 = ld_f4(F + b00), t100 = ld_f4(F + b00 + dx);
+        const float4 t010 = ld_f4(F + b10), t110 = ld_f4(F + b10 + dx);
+        const float4 t001 = ld_f4(F + b01), t101 = ld_f4(F + b01 + dx);
+        const float4 t011 = ld_f4(F + b11), t111 = ld_f4(F + b11 + dx);
+        const pk2_t rgA = lerp2(pk2(t000.x, t000.y), pk2(t100.x, t100.y), fx2), rgB = lerp2(pk2(t010.x, t010.y), pk2(t110.x, t110.y), fx2);
+        const pk2_t rgC = lerp2(pk2(t001.x, t001.y), pk2(t101.x, t101.y), fx2), rgD = lerp2(pk2(t011.x, t011.y), pk2(t111.x, t111.y), fx2);
+        r.rg = lerp2(lerp2(rgA, rgB, fy2), lerp2(rgC, rgD, fy2), fz2);
+        const pk2_t baA = lerp2(pk2(t000.z, t000.w), pk2(t100.z, t100.w), fx2), baB = lerp2(pk2(t010.z, t010.w), pk2(t110.z, t110.w), fx2);
+        const pk2_t baC = lerp2(pk2(t001.z, t001.w), pk2(t101.z, t101.w), fx2), baD = lerp2(pk2(t011.z, t011.w), pk2(t111.z, t111.w), fx2);
+        const pk2_t ba = lerp2(lerp2(baA, baB, fy2), lerp2(baC, baD, fy2), fz2);
+        up2(ba, r.b, r.a);
     }
     return r;
 }
 
-// byte k of w -> float, exactly, without I2F: bits 0x4B0000bb = 8388608 + bb
-__device__ __forceinline__ float byte_f(unsigned int w, int k)
+template <int LAYOUT, bool ALPHA>
+__device__ __forceinline__ float4 fetch_field(const DevParams &P, float px, float py, float pz)
 {
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + k)) - 8388608.0f;
+    const FieldVal v = fetch_field_pk<LAYOUT, ALPHA>(P, px, py, pz);
+    float4 r;
+    up2(v.rg, r.x, r.y);
+    r.z = v.b;
+    r.w = v.a;
+    return r;
 }
+
+// byte k of w as the float 8388608 + byte (bits 0x4B0000bb): no I2F; the bias cancels in differences
+constexpr float kByteBias = 8388608.0f;
+__device__ __forceinline__ float byte_biased(unsigned int w, int k) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + k)); }
+__device__ __forceinline__ float byte_f(unsigned int w, int k) { return byte_biased(w, k) - kByteBias; }
+// x-lerp of two biased byte pairs: (a - bias) + f (b - a); b - a is exact on the biased values
+__device__ __forceinline__ pk2_t lerp2_biased(pk2_t a, pk2_t b, pk2_t f) { return fma2(f, sub2(b, a), sub2(a, bc2(kByteBias))); }
 
 // trilinear blend of the 8 corner bytes of one cell8 entry, result in [0,1]
 __device__ __forceinline__ float cell8_blend(uint2 c, float fx, float fy, float fz)
 {
-    float x00 = lerpf(byte_f(c.x, 0), byte_f(c.x, 1), fx);
-    float x10 = lerpf(byte_f(c.x, 2), byte_f(c.x, 3), fx);
-    float x01 = lerpf(byte_f(c.y, 0), byte_f(c.y, 1), fx);
-    float x11 = lerpf(byte_f(c.y, 2), byte_f(c.y, 3), fx);
-    return lerpf(lerpf(x00, x10, fy), lerpf(x01, x11, fy), fz) * (1.0f / 255.0f);
+    // register pairs hold the two z planes: (z0, z1)
+    const pk2_t fx2 = bc2(fx);
+    const pk2_t xa = lerp2_biased(pk2(byte_biased(c.x, 0), byte_biased(c.y, 0)), pk2(byte_biased(c.x, 1), byte_biased(c.y, 1)), fx2);   // y0
+    const pk2_t xb = lerp2_biased(pk2(byte_biased(c.x, 2), byte_biased(c.y, 2)), pk2(byte_biased(c.x, 3), byte_biased(c.y, 3)), fx2);   // y1
+    const pk2_t y = lerp2(xa, xb, bc2(fy));
+    return lerpf(lo2(y), hi2(y), fz) * (1.0f / 255.0f);
 }
 
 // scalarSampler: LUMINANCE8, CLAMP_TO_EDGE (VV/dataset.cpp:1025-1038) -> .r
@@ -196,7 +224,7 @@ __device__ __forceinline__ float fetch_scalar(const DevParams &P, float px, floa
     axis_clamp(px, P.snx, x0, x1, fx);
     axis_clamp(py, P.sny, y0, y1, fy);
     axis_clamp(pz, P.snz, z0, z1, fz);
-    uint2 c = ld_u2(P.scalar_cell + ((unsigned int)z0 * P.sny + y0) * P.snx + x0);
+    uint2 c = ld_u2(P.scalar_cell + (((unsigned int)z0 * (unsigned int)P.sny + (unsigned int)y0) * (unsigned int)P.snx + (unsigned int)x0));
     return cell8_blend(c, fx, fy, fz);
 }
 
@@ -208,23 +236,27 @@ __device__ __forceinline__ float fetch_noise_scalar(const DevParams &P, float px
     axis_repeat(px, P.nnx, x0, fx);
     axis_repeat(py, P.nny, y0, fy);
     axis_repeat(pz, P.nnz, z0, fz);
-    uint2 c = ld_u2(P.noise_cell + ((unsigned int)z0 * P.nny + y0) * P.nnx + x0);
+    uint2 c = ld_u2(P.noise_cell + (((unsigned int)z0 * (unsigned int)P.nny + (unsigned int)y0) * (unsigned int)P.nnx + (unsigned int)x0));
     return cell8_blend(c, fx, fy, fz);
 }
 
-__device__ __forceinline__ float4 rgba8_lerp4(unsigned int t00, unsigned int t10, unsigned int t01, unsigned int t11,
-                                              float fx, float fy)
+struct Rgba2 { pk2_t rg, ba; };
+
+// bilinear blend inside one plane of the quad layout: texels (x0y0, x1y0, x0y1, x1y1), channels as (r,g) and (b,a) pairs
+__device__ __forceinline__ Rgba2 quad_blend(uint4 q, pk2_t fx2, pk2_t fy2)
 {
-    float4 r;
-    r.x = lerpf(lerpf(byte_f(t00, 0), byte_f(t10, 0), fx), lerpf(byte_f(t01, 0), byte_f(t11, 0), fx), fy);
-    r.y = lerpf(lerpf(byte_f(t00, 1), byte_f(t10, 1), fx), lerpf(byte_f(t01, 1), byte_f(t11, 1), fx), fy);
-    r.z = lerpf(lerpf(byte_f(t00, 2), byte_f(t10, 2), fx), lerpf(byte_f(t01, 2), byte_f(t11, 2), fx), fy);
-    r.w = lerpf(lerpf(byte_f(t00, 3), byte_f(t10, 3), fx), lerpf(byte_f(t01, 3), byte_f(t11, 3), fx), fy);
+    Rgba2 r;
+    const pk2_t rg0 = lerp2_biased(pk2(byte_biased(q.x, 0), byte_biased(q.x, 1)), pk2(byte_biased(q.y, 0), byte_biased(q.y, 1)), fx2);
+    const pk2_t rg1 = lerp2_biased(pk2(byte_biased(q.z, 0), byte_biased(q.z, 1)), pk2(byte_biased(q.w, 0), byte_biased(q.w, 1)), fx2);
+    const pk2_t ba0 = lerp2_biased(pk2(byte_biased(q.x, 2), byte_biased(q.x, 3)), pk2(byte_biased(q.y, 2), byte_biased(q.y, 3)), fx2);
+    const pk2_t ba1 = lerp2_biased(pk2(byte_biased(q.z, 2), byte_biased(q.z, 3)), pk2(byte_biased(q.w, 2), byte_biased(q.w, 3)), fx2);
+    r.rg = lerp2(rg0, rg1, fy2);
+    r.ba = lerp2(ba0, ba1, fy2);
     return r;
 }
 
 // noiseSampler, RGBA8 (gradient.xyz, noise), REPEAT -> raw texel (freqSamplingGrad, inc_lic.glsl:61-68)
-__device__ __forceinline__ float4 fetch_noise_rgba(const DevParams &P, float px, float py, float pz)
+__device__ __forceinline__ Rgba2 fetch_noise_rgba_pk(const DevParams &P, float px, float py, float pz)
 {
     int x0, y0, z0;
     float fx, fy, fz;
@@ -233,16 +265,24 @@ __device__ __forceinline__ float4 fetch_noise_rgba(const DevParams &P, float px,
     axis_repeat(pz, P.nnz, z0, fz);
     int z1 = z0 + 1;
     if (z1 >= P.nnz) z1 = 0;
-    uint4 a = ld_u4(P.noise_quad + ((unsigned int)z0 * P.nny + y0) * P.nnx + x0);
-    uint4 b = ld_u4(P.noise_quad + ((unsigned int)z1 * P.nny + y0) * P.nnx + x0);
-    float4 p0 = rgba8_lerp4(a.x, a.y, a.z, a.w, fx, fy);
-    float4 p1 = rgba8_lerp4(b.x, b.y, b.z, b.w, fx, fy);
-    const float k = 1.0f / 255.0f;
+    const unsigned int plane = (unsigned int)P.nny * (unsigned int)P.nnx;
+    const unsigned int i0 = (unsigned int)y0 * (unsigned int)P.nnx + (unsigned int)x0;
+    const uint4 a = ld_u4(P.noise_quad + ((unsigned int)z0 * plane + i0));
+    const uint4 b = ld_u4(P.noise_quad + ((unsigned int)z1 * plane + i0));
+    const pk2_t fx2 = bc2(fx), fy2 = bc2(fy), fz2 = bc2(fz), k2 = bc2(1.0f / 255.0f);
+    const Rgba2 p0 = quad_blend(a, fx2, fy2), p1 = quad_blend(b, fx2, fy2);
+    Rgba2 r;
+    r.rg = mul2(lerp2(p0.rg, p1.rg, fz2), k2);
+    r.ba = mul2(lerp2(p0.ba, p1.ba, fz2), k2);
+    return r;
+}
+
+__device__ __forceinline__ float4 fetch_noise_rgba(const DevParams &P, float px, float py, float pz)
+{
+    const Rgba2 v = fetch_noise_rgba_pk(P, px, py, pz);
     float4 r;
-    r.x = lerpf(p0.x, p1.x, fz) * k;
-    r.y = lerpf(p0.y, p1.y, fz) * k;
-    r.z = lerpf(p0.z, p1.z, fz) * k;
-    r.w = lerpf(p0.w, p1.w, fz) * k;
+    up2(v.rg, r.x, r.y);
+    up2(v.ba, r.z, r.w);
     return r;
 }
 

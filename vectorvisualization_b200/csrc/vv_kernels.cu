@@ -12,6 +12,10 @@
 #include "vv_device.cuh"
 #include "vv_kernels.h"
 
+#ifndef LIC_MIN_CTAS
+#define LIC_MIN_CTAS 3   // resident CTAs per SM the sample kernel is compiled for (<= 80 registers per thread, no spills)
+#endif
+
 namespace vvb200 {
 
 // ------------------------------------------------------------------------------------------------
@@ -84,40 +88,56 @@ __device__ __forceinline__ float noise_tap(const DevParams &P, f3 q)
     return fetch_noise_scalar(P, q.x * P.freq, q.y * P.freq, q.z * P.freq);
 }
 
+// streamline walker: position (x,y packed, z) and the field sample at it (r,g packed, b, a)
+struct Walker { pk2_t qxy; float qz; pk2_t vrg; float vb, va; };
+
+__device__ __forceinline__ Walker make_walker(f3 pos, float4 centre)
+{
+    Walker w;
+    w.qxy = pk2(pos.x, pos.y); w.qz = pos.z;
+    w.vrg = pk2(centre.x, centre.y); w.vb = centre.z; w.va = centre.w;
+    return w;
+}
+
 // one Heun step of singleLICstep (inc_lic.glsl:104-128); sh = dir * h
 template <int LAYOUT, bool SOF>
-__device__ __forceinline__ void heun_step(const DevParams &P, f3 &q, float4 &v, float sh)
+__device__ __forceinline__ void heun_step(const DevParams &P, Walker &w, float sh)
 {
-    float s1 = SOF ? v.w * sh : sh;    // licdir *= step.a (SPEED_OF_FLOW) then *= h
-    f3 d1 = mk3(fmaf(2.0f, v.x, -1.0f) * s1, fmaf(2.0f, v.y, -1.0f) * s1, fmaf(2.0f, v.z, -1.0f) * s1);
-    float4 v2 = fetch_field<LAYOUT, false>(P, q.x + d1.x, q.y + d1.y, q.z + d1.z);
-    f3 d2 = mk3(fmaf(2.0f, v2.x, -1.0f) * s1, fmaf(2.0f, v2.y, -1.0f) * s1, fmaf(2.0f, v2.z, -1.0f) * s1);
-    q.x = fmaf(0.5f, d1.x + d2.x, q.x);
-    q.y = fmaf(0.5f, d1.y + d2.y, q.y);
-    q.z = fmaf(0.5f, d1.z + d2.z, q.z);
-    v = fetch_field<LAYOUT, SOF>(P, q.x, q.y, q.z);
+    const float s1 = SOF ? w.va * sh : sh;    // licdir *= step.a (SPEED_OF_FLOW) then *= h
+    const pk2_t s2 = bc2(s1), two = bc2(2.0f), mone = bc2(-1.0f);
+    const pk2_t d1 = mul2(fma2(two, w.vrg, mone), s2);                    // licdir = (2 v - 1) * dir * h
+    const float d1z = fmaf(2.0f, w.vb, -1.0f) * s1;
+    const pk2_t p2 = add2(w.qxy, d1);                                      // Pos2 = newPos + licdir
+    const FieldVal v2 = fetch_field_pk<LAYOUT, false>(P, lo2(p2), hi2(p2), w.qz + d1z);
+    const pk2_t d2 = mul2(fma2(two, v2.rg, mone), s2);
+    const float d2z = fmaf(2.0f, v2.b, -1.0f) * s1;
+    w.qxy = fma2(bc2(0.5f), add2(d1, d2), w.qxy);                          // newPos += 0.5 (licdir + licdir2)
+    w.qz = fmaf(0.5f, d1z + d2z, w.qz);
+    const FieldVal v = fetch_field_pk<LAYOUT, SOF>(P, lo2(w.qxy), hi2(w.qxy), w.qz);
+    w.vrg = v.rg; w.vb = v.b; w.va = v.a;
 }
 
 // computeLIC, inc_lic.glsl:152-202, scalar build.  The backward and forward walks are independent; they are
 // advanced in the same loop iteration so that each thread keeps two dependent fetch chains in flight.
+// nBwdEff / nFwdEff: the walk stops after the last step whose filter-kernel weight is non-zero (trailing zero
+// weights contribute exactly 0 to the sum).
 template <int LAYOUT, bool NGATE, bool SOF>
 __device__ __forceinline__ float compute_lic_scalar(const DevParams &P, const float *s_kw, f3 pos, float4 centre)
 {
     float acc0 = noise_tap<NGATE>(P, pos) * s_kw[0];
     float accB = 0.0f, accF = 0.0f;
-    f3 qb = pos, qf = pos;
-    float4 vb = centre, vf = centre;
+    Walker wb = make_walker(pos, centre), wf = wb;
     const float *kwB = s_kw + 1, *kwF = s_kw + 1 + P.nBwd;
-    const int nB = P.nBwd, nF = P.nFwd;
+    const int nB = P.nBwdEff, nF = P.nFwdEff;
     const int n = max(nB, nF);
     for (int k = 0; k < n; ++k) {
         if (k < nB) {
-            heun_step<LAYOUT, SOF>(P, qb, vb, -P.h);
-            accB = fmaf(noise_tap<NGATE>(P, qb), kwB[k], accB);
+            heun_step<LAYOUT, SOF>(P, wb, -P.h);
+            accB = fmaf(noise_tap<NGATE>(P, mk3(lo2(wb.qxy), hi2(wb.qxy), wb.qz)), kwB[k], accB);
         }
         if (k < nF) {
-            heun_step<LAYOUT, SOF>(P, qf, vf, P.h);
-            accF = fmaf(noise_tap<NGATE>(P, qf), kwF[k], accF);
+            heun_step<LAYOUT, SOF>(P, wf, P.h);
+            accF = fmaf(noise_tap<NGATE>(P, mk3(lo2(wf.qxy), hi2(wf.qxy), wf.qz)), kwF[k], accF);
         }
     }
     return (acc0 + accB) + accF;
@@ -127,35 +147,34 @@ __device__ __forceinline__ float compute_lic_scalar(const DevParams &P, const fl
 template <int LAYOUT, bool SOF>
 __device__ __forceinline__ float4 compute_lic_grad(const DevParams &P, const float *s_kw, f3 pos, float4 centre)
 {
-    float4 c = fetch_noise_rgba(P, pos.x, pos.y, pos.z);
-    const float w0 = s_kw[0];
-    float4 accB = make_float4(0, 0, 0, 0), accF = make_float4(0, 0, 0, 0);
-    f3 qb = pos, qf = pos;
-    float4 vb = centre, vf = centre;
+    const Rgba2 c = fetch_noise_rgba_pk(P, pos.x, pos.y, pos.z);
+    const pk2_t w0 = bc2(s_kw[0]);
+    pk2_t accBrg = pk2(0.f, 0.f), accBba = accBrg, accFrg = accBrg, accFba = accBrg;
+    Walker wb = make_walker(pos, centre), wf = wb;
     const float *kwB = s_kw + 1, *kwF = s_kw + 1 + P.nBwd;
-    const int nB = P.nBwd, nF = P.nFwd;
+    const int nB = P.nBwdEff, nF = P.nFwdEff;
     const int n = max(nB, nF);
     for (int k = 0; k < n; ++k) {
         if (k < nB) {
-            heun_step<LAYOUT, SOF>(P, qb, vb, -P.h);
-            float4 t = fetch_noise_rgba(P, qb.x, qb.y, qb.z);
-            float w = kwB[k];
-            accB.x = fmaf(t.x, w, accB.x); accB.y = fmaf(t.y, w, accB.y);
-            accB.z = fmaf(t.z, w, accB.z); accB.w = fmaf(t.w, w, accB.w);
+            heun_step<LAYOUT, SOF>(P, wb, -P.h);
+            const Rgba2 t = fetch_noise_rgba_pk(P, lo2(wb.qxy), hi2(wb.qxy), wb.qz);
+            const pk2_t w = bc2(kwB[k]);
+            accBrg = fma2(t.rg, w, accBrg);
+            accBba = fma2(t.ba, w, accBba);
         }
         if (k < nF) {
-            heun_step<LAYOUT, SOF>(P, qf, vf, P.h);
-            float4 t = fetch_noise_rgba(P, qf.x, qf.y, qf.z);
-            float w = kwF[k];
-            accF.x = fmaf(t.x, w, accF.x); accF.y = fmaf(t.y, w, accF.y);
-            accF.z = fmaf(t.z, w, accF.z); accF.w = fmaf(t.w, w, accF.w);
+            heun_step<LAYOUT, SOF>(P, wf, P.h);
+            const Rgba2 t = fetch_noise_rgba_pk(P, lo2(wf.qxy), hi2(wf.qxy), wf.qz);
+            const pk2_t w = bc2(kwF[k]);
+            accFrg = fma2(t.rg, w, accFrg);
+            accFba = fma2(t.ba, w, accFba);
         }
     }
+    const pk2_t rg = add2(fma2(c.rg, w0, accBrg), accFrg);
+    const pk2_t ba = add2(fma2(c.ba, w0, accBba), accFba);
     float4 r;
-    r.x = (c.x * w0 + accB.x) + accF.x;
-    r.y = (c.y * w0 + accB.y) + accF.y;
-    r.z = (c.z * w0 + accB.z) + accF.z;
-    r.w = (c.w * w0 + accB.w) + accF.w;
+    up2(rg, r.x, r.y);
+    up2(ba, r.z, r.w);
     return r;
 }
 
@@ -455,7 +474,7 @@ __global__ void __launch_bounds__(256) ray_setup_kernel(const __grid_constant__ 
 }
 
 template <int LAYOUT, int ILLUM, bool NGATE, bool SOF>
-__global__ void __launch_bounds__(256) lic_sample_kernel(const __grid_constant__ DevParams P)
+__global__ void __launch_bounds__(256, LIC_MIN_CTAS) lic_sample_kernel(const __grid_constant__ DevParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SharedTables &S = *reinterpret_cast<SharedTables *>(smem_raw);

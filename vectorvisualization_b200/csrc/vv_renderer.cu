@@ -90,6 +90,7 @@ struct VVRenderer {
     DevBuf<float4> tf_rgba;
     DevBuf<float> tf_opac, kw;
     bool tables_dirty = true;
+    int n_bwd_eff = 0, n_fwd_eff = 0;      // LIC steps up to the last non-zero kernel weight
 
     // ---- parameters ----
     VVLicParams lp;
@@ -271,6 +272,10 @@ static int upload_tables(VVRenderer *r, const Uniforms &u)
     for (int i = 0; i < u.nBwd; ++i) { off -= u.licKernel[1]; kw[1 + i] = kernel_lookup(r, off); }
     off = 0.5f;
     for (int i = 0; i < u.nFwd; ++i) { off += u.licKernel[0]; kw[1 + u.nBwd + i] = kernel_lookup(r, off); }
+    r->n_bwd_eff = u.nBwd;
+    while (r->n_bwd_eff > 0 && kw[r->n_bwd_eff] == 0.0f) --r->n_bwd_eff;
+    r->n_fwd_eff = u.nFwd;
+    while (r->n_fwd_eff > 0 && kw[u.nBwd + r->n_fwd_eff] == 0.0f) --r->n_fwd_eff;
     CU(r->kw.ensure(2 * kMaxLicSteps + 1));
     CU(cudaMemcpyAsync(r->kw.p, kw.data(), kw.size() * sizeof(float), cudaMemcpyHostToDevice, r->stream));
     // TF textures: RGBA8 and LUMINANCE_ALPHA8 (.a = LIC opacity), VV/transferEdit.cpp:505-540
@@ -339,6 +344,7 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame)
     P.licScale = u.licKernel[2] * u.gradient[0];          // lic3d_fragment.glsl:67
     P.alphaCorr = u.alphaCorrection; P.specExp = r->spec_exp;
     P.numIter = r->lp.numIterations; P.nFwd = u.nFwd; P.nBwd = u.nBwd;
+    P.nFwdEff = r->n_fwd_eff; P.nBwdEff = r->n_bwd_eff;
     // VV/renderer.cpp:934-944 incl. Q1
     const bool inv_active = (r->illum_mode != ILLUM_NONE);
     for (int i = 0; i < 3; ++i) {
