@@ -1,0 +1,273 @@
+/* ref_host_driver.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Drives the reference's OWN host code (VV/reader.cpp, parseArg.cpp, gradient.cpp, dataset.cpp, transferEdit.cpp,
+ * mmath.cpp, texture.cpp -- compiled unmodified from /root/reference by oracle/build_ref.py against the capturing
+ * GL stub in oracle/ref_shim/) and hands back what it would have uploaded to OpenGL:
+ *   the packed RGBA16F vector texture (VectorDataSet::createTextureIterp), the noise texture with or without
+ *   gradients (NoiseDataSet::createTexture), the LIC filter kernel + inverse area (LICFilter), the two transfer
+ *   function textures (TransferEdit::updateTextures), DatFile / ParseArguments results and the mmath quaternion helpers.
+ * Only the PNG codec (the reference links libpng, which is not in this image) and the GL entry points are ours.
+ */
+#include <zlib.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "GL/glew.h"
+#include "dataset.h"
+#include "gradient.h"
+#include "imageUtils.h"
+#include "mmath.h"
+#include "parseArg.h"
+#include "reader.h"
+#include "transferEdit.h"
+
+/* ------------------------------------------------------------------------------------------------ GL capture */
+static std::map<GLuint, VVStubTex> g_tex;
+static GLuint g_next_id = 1, g_bound = 0, g_last = 0;
+
+static VVStubTex &cur()
+{
+    VVStubTex &t = g_tex[g_bound];
+    return t;
+}
+
+extern "C" {
+VVStubTex *vv_stub_texture(GLuint id) { auto it = g_tex.find(id); return it == g_tex.end() ? nullptr : &it->second; }
+GLuint vv_stub_last_texture(void) { return g_last; }
+void vv_stub_reset(void)
+{
+    for (auto &kv : g_tex) std::free(kv.second.data);
+    g_tex.clear();
+    g_bound = g_last = 0;
+}
+void glGenTextures(GLsizei n, GLuint *ids) { for (int i = 0; i < n; ++i) { ids[i] = g_next_id++; g_tex[ids[i]] = VVStubTex(); } }
+void glDeleteTextures(GLsizei n, const GLuint *ids)
+{
+    for (int i = 0; i < n; ++i) { auto it = g_tex.find(ids[i]); if (it != g_tex.end()) { std::free(it->second.data); g_tex.erase(it); } }
+}
+void glBindTexture(GLenum target, GLuint id) { g_bound = id; g_tex[id].target = target; }
+void glTexParameteri(GLenum, GLenum pname, GLint v)
+{
+    VVStubTex &t = cur();
+    switch (pname) {
+    case GL_TEXTURE_MIN_FILTER: t.min_filter = v; break;
+    case GL_TEXTURE_MAG_FILTER: t.mag_filter = v; break;
+    case GL_TEXTURE_WRAP_S: t.wrap_s = v; break;
+    case GL_TEXTURE_WRAP_T: t.wrap_t = v; break;
+    case GL_TEXTURE_WRAP_R: t.wrap_r = v; break;
+    default: break;
+    }
+}
+static void upload(GLint ifmt, int w, int h, int d, GLenum fmt, GLenum type, const void *data)
+{
+    VVStubTex &t = cur();
+    int ch = (fmt == GL_RGBA) ? 4 : (fmt == GL_RGB ? 3 : (fmt == GL_LUMINANCE_ALPHA ? 2 : 1));
+    int bs = (type == GL_FLOAT) ? 4 : (type == GL_UNSIGNED_SHORT ? 2 : 1);
+    t.internal_format = ifmt; t.format = fmt; t.type = type;
+    t.dim[0] = w; t.dim[1] = h; t.dim[2] = d;
+    t.bytes = (size_t)w * h * d * ch * bs;
+    std::free(t.data);
+    t.data = std::malloc(t.bytes ? t.bytes : 1);
+    if (data) std::memcpy(t.data, data, t.bytes);
+    g_last = g_bound;
+}
+void glTexImage1D(GLenum, GLint, GLint ifmt, GLsizei w, GLint, GLenum fmt, GLenum type, const void *data) { upload(ifmt, w, 1, 1, fmt, type, data); }
+void glTexImage2D(GLenum, GLint, GLint ifmt, GLsizei w, GLsizei h, GLint, GLenum fmt, GLenum type, const void *data) { upload(ifmt, w, h, 1, fmt, type, data); }
+void glTexImage3D(GLenum, GLint, GLint ifmt, GLsizei w, GLsizei h, GLsizei d, GLint, GLenum fmt, GLenum type, const void *data) { upload(ifmt, w, h, d, fmt, type, data); }
+}
+
+/* ------------------------------------------------------------------------------------------------ PNG codec (ours) */
+static unsigned be32(const unsigned char *p) { return (p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]; }
+
+bool pngRead(const char *fileName, Image *img)
+{
+    FILE *fp = std::fopen(fileName, "rb");
+    if (!fp) { std::fprintf(stderr, "Could not open PNG file %s.\n", fileName); return false; }
+    std::vector<unsigned char> buf;
+    unsigned char tmp[65536];
+    size_t n;
+    while ((n = std::fread(tmp, 1, sizeof(tmp), fp)) > 0) buf.insert(buf.end(), tmp, tmp + n);
+    std::fclose(fp);
+    if (buf.size() < 8) return false;
+    size_t pos = 8;
+    int w = 0, h = 0, depth = 0, ctype = -1;
+    std::vector<unsigned char> idat;
+    while (pos + 12 <= buf.size()) {
+        unsigned len = be32(&buf[pos]);
+        const char *type = (const char *)&buf[pos + 4];
+        const unsigned char *d = &buf[pos + 8];
+        if (!std::memcmp(type, "IHDR", 4)) { w = be32(d); h = be32(d + 4); depth = d[8]; ctype = d[9]; }
+        else if (!std::memcmp(type, "IDAT", 4)) idat.insert(idat.end(), d, d + len);
+        else if (!std::memcmp(type, "IEND", 4)) break;
+        pos += 12 + len;
+    }
+    if (depth != 8) return false;
+    int ch = ctype == 0 ? 1 : ctype == 4 ? 2 : ctype == 2 ? 3 : ctype == 6 ? 4 : 0;
+    if (!ch) return false;
+    size_t stride = (size_t)w * ch;
+    std::vector<unsigned char> raw((stride + 1) * h);
+    uLongf rl = raw.size();
+    if (uncompress(raw.data(), &rl, idat.data(), idat.size()) != Z_OK) return false;
+    img->imgData = new unsigned char[stride * h];
+    for (int y = 0; y < h; ++y) {
+        const unsigned char *src = &raw[(stride + 1) * y];
+        unsigned char *dst = img->imgData + stride * y, *up = y ? img->imgData + stride * (y - 1) : nullptr;
+        for (size_t i = 0; i < stride; ++i) {
+            int a = i >= (size_t)ch ? dst[i - ch] : 0, b = up ? up[i] : 0, c = (up && i >= (size_t)ch) ? up[i - ch] : 0, x = src[1 + i];
+            switch (src[0]) {
+            case 1: x += a; break;
+            case 2: x += b; break;
+            case 3: x += (a + b) >> 1; break;
+            case 4: { int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c); x += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
+            default: break;
+            }
+            dst[i] = (unsigned char)x;
+        }
+    }
+    img->width = w; img->height = h; img->channel = ch; img->gamma = 1.0;
+    return true;
+}
+bool pngWrite(const char *, const Image *, bool) { return false; }
+bool ppmRead(const char *, Image *) { return false; }
+bool ppmWrite(const char *, const Image *) { return false; }
+
+/* ------------------------------------------------------------------------------------------------ exported drivers */
+static int copy_tex(GLuint id, void *out, size_t cap, int dims[3], int *ifmt, int *wrap)
+{
+    VVStubTex *t = vv_stub_texture(id);
+    if (!t || !t->data) return -1;
+    if (out) { if (cap < t->bytes) return -2; std::memcpy(out, t->data, t->bytes); }
+    if (dims) { dims[0] = t->dim[0]; dims[1] = t->dim[1]; dims[2] = t->dim[2]; }
+    if (ifmt) *ifmt = t->internal_format;
+    if (wrap) *wrap = t->wrap_s;
+    return (int)(t->bytes > 0x7fffffff ? 0x7fffffff : t->bytes);
+}
+
+extern "C" {
+
+/* VectorDataSet: loadData(.dat) + loadTimeStep x2 + setInterpolateSize + createTextureIterp (VV/3DLIC.cpp:686-707),
+ * repeated `interp_index + 1` times so the captured upload is the one made with that interpIndex */
+int vvref_vector_texture(const char *dat, int interp_index, int interp_size, float *out, size_t cap, int dims[3], float geom[17],
+                         int *ifmt, int *wrap)
+{
+    VectorDataSet vd;
+    if (!vd.loadData(dat)) return -10;
+    vd.getVolumeData()->data = vd.loadTimeStep(vd.getCurTimeStep());
+    vd.getVolumeData()->newData = vd.loadTimeStep(vd.NextTimeStep());
+    vd.setInterpolateSize(interp_size);
+    for (int i = 0; i <= interp_index; ++i) vd.createTextureIterp("VectorData_Tex", GL_TEXTURE2_ARB, true);
+    VolumeData *v = vd.getVolumeData();
+    if (geom) {
+        for (int i = 0; i < 3; ++i) { geom[i] = v->extent[i]; geom[3 + i] = v->center[i]; geom[14 + i] = v->sliceDist[i]; }
+        for (int i = 0; i < 4; ++i) { geom[6 + i] = v->scale[i]; geom[10 + i] = v->scaleInv[i]; }
+    }
+    return copy_tex(vd.getTextureRef()->id, out, cap, dims, ifmt, wrap);
+}
+
+/* NoiseDataSet: loadData(file) + enableGradient + createTexture (VV/3DLIC.cpp:711-713) */
+int vvref_noise_texture(const char *file, int use_gradient, unsigned char *out, size_t cap, int dims[3], int *ifmt, int *wrap)
+{
+    NoiseDataSet nd;
+    if (!nd.loadData(file)) return -10;
+    if (!nd.getFileName()) return -11;          /* fell back to rand() white noise: not reproducible */
+    nd.enableGradient(use_gradient != 0);
+    nd.createTexture("Noise_Tex", GL_TEXTURE3_ARB);
+    /* the gradient cache file <noise>.grd is written next to the input: remove it so runs stay independent */
+    std::string grd = std::string(file) + ".grd";
+    std::remove(grd.c_str());
+    return copy_tex(nd.getTextureRef()->id, out, cap, dims, ifmt, wrap);
+}
+
+/* LICFilter: loadData(png) or createBoxFilter + createTexture (VV/3DLIC.cpp:725-731) */
+int vvref_filter_texture(const char *png, unsigned char *out, size_t cap, int *width, float *inv_area, int *wrap)
+{
+    LICFilter f;
+    if (!png || !f.loadData(png)) f.createBoxFilter();
+    f.createTexture("LIC_kernel_Tex", GL_TEXTURE5_ARB);
+    int dims[3];
+    int rc = copy_tex(f.getTextureRef()->id, out, cap, dims, nullptr, wrap);
+    if (width) *width = f.getFilterWidth();
+    if (inv_area) *inv_area = f.getInverseFilterArea();
+    return rc;
+}
+
+/* TransferEdit: ctor (+ loadTF(name)) + updateTextures (VV/3DLIC.cpp:739-747): RGBA8 256 + LUMINANCE_ALPHA8 256 */
+int vvref_tf_textures(const char *name, unsigned char *rgba, unsigned char *la, int *loaded)
+{
+    TransferEdit te;
+    int ok = 0;
+    if (name) ok = te.loadTF(name) ? 1 : 0;
+    if (loaded) *loaded = ok;
+    te.updateTextures();
+    if (copy_tex(te.getTextureRGB()->id, rgba, 1024, nullptr, nullptr, nullptr) < 0) return -1;
+    if (copy_tex(te.getTextureAlphaOpac()->id, la, 512, nullptr, nullptr, nullptr) < 0) return -2;
+    return 0;
+}
+
+/* gradient.cpp entry points on a caller-provided u8 volume */
+int vvref_noise_gradients(const unsigned char *noise, const int dims[3], const float sd[3], float *grad_f, float *filtered_f, unsigned char *quant)
+{
+    VolumeData vd;
+    size_t n = (size_t)dims[0] * dims[1] * dims[2];
+    vd.data = new unsigned char[n];
+    std::memcpy(vd.data, noise, n);
+    vd.dataType = DATRAW_UCHAR;
+    for (int i = 0; i < 3; ++i) { vd.size[i] = dims[i]; vd.sliceDist[i] = sd[i]; }
+    float *g = computeGradients(&vd);
+    if (grad_f) std::memcpy(grad_f, g, 3 * n * sizeof(float));
+    filterGradients(&vd, g);
+    if (filtered_f) std::memcpy(filtered_f, g, 3 * n * sizeof(float));
+    unsigned char *q = (unsigned char *)quantizeGradients(&vd, g, DATRAW_UCHAR);
+    if (quant) std::memcpy(quant, q, 3 * n);
+    delete[] g;
+    delete[] q;
+    return 0;
+}
+
+/* DatFile::parseDatFile */
+int vvref_parse_dat(const char *dat, int res[3], float dist[3], int *dtype, int *ddim, int *tb, int *te)
+{
+    DatFile d;
+    if (!d.parseDatFile((char *)dat)) return -1;
+    for (int i = 0; i < 3; ++i) { res[i] = d.getDataSizes()[i]; dist[i] = d.getDataDists()[i]; }
+    *dtype = (int)d.getDataType(); *ddim = d.getDataDimension(); *tb = d.getTimeStepBegin(); *te = d.getTimeStepEnd();
+    return 0;
+}
+
+/* ParseArguments::parse; strings copied into out[6][512]: vol, noise, tf, filter, redirect, halton; flags[2]: gradients, lambda2 */
+int vvref_parse_args(int argc, char **argv, char *out, int *flags)
+{
+    ParseArguments pa;
+    pa.setArguments(argc, argv);
+    bool ok = pa.parse();
+    const char *s[6] = {pa.getVolFileName(), pa.getNoiseFileName(), pa.getTfFileName(), pa.getLicFilterFileName(),
+                        pa.getRedirectFileName(), pa.getHaltonFileName()};
+    for (int i = 0; i < 6; ++i) { std::memset(out + 512 * i, 0, 512); if (s[i]) std::strncpy(out + 512 * i, s[i], 511); }
+    flags[0] = pa.getGradientsFlag(); flags[1] = pa.getLambda2Flag();
+    return ok ? 0 : -1;
+}
+
+/* mmath.cpp */
+void vvref_quat_angle_axis(const float q[4], float *angle, float axis[3])
+{
+    Quaternion qq; qq.x = q[0]; qq.y = q[1]; qq.z = q[2]; qq.w = q[3];
+    Vector3 a;
+    Quaternion_getAngleAxis(qq, angle, &a);
+    axis[0] = a.x; axis[1] = a.y; axis[2] = a.z;
+}
+void vvref_quat_mult_vec(const float q[4], const float v[3], float out[3])
+{
+    Quaternion qq; qq.x = q[0]; qq.y = q[1]; qq.z = q[2]; qq.w = q[3];
+    Vector3 a = Vector3_new(v[0], v[1], v[2]);
+    Vector3 r = Quaternion_multVector3(qq, a);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+int vvref_next_pow2(int v) { return nextPowerTwo(v); }
+int vvref_has_host(void) { return 1; }
+
+} /* extern "C" */

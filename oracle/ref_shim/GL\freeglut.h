@@ -1,0 +1,1 @@
+#include "vv_gl_stub.h"

@@ -1,0 +1,123 @@
+"""ctypes wrapper of the reference HOST code inside oracle/_ref/libvv_ref.so -- TEST INFRASTRUCTURE ONLY.
+(VV/dataset.cpp, gradient.cpp, reader.cpp, parseArg.cpp, transferEdit.cpp, mmath.cpp compiled unmodified against the
+capturing GL stub of oracle/ref_shim/; see oracle/ref_host_driver.cpp.)"""
+import ctypes
+
+import numpy as np
+
+from . import refshim
+
+GL_CLAMP, GL_REPEAT, GL_CLAMP_TO_EDGE = 0x2900, 0x2901, 0x812F
+GL_RGBA, GL_LUMINANCE, GL_RGBA16F_ARB = 0x1908, 0x1909, 0x881A
+
+
+def available():
+    if not refshim.available():
+        return False
+    try:
+        return bool(refshim.lib().vvref_has_host())
+    except AttributeError:
+        return False
+
+
+def _L():
+    L = refshim.lib()
+    L.vvref_vector_texture.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.vvref_noise_texture.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.vvref_filter_texture.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.vvref_tf_textures.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.vvref_noise_gradients.argtypes = [ctypes.c_void_p] * 6
+    L.vvref_parse_dat.argtypes = [ctypes.c_char_p] + [ctypes.c_void_p] * 6
+    L.vvref_parse_args.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_void_p, ctypes.c_void_p]
+    L.vvref_quat_angle_axis.argtypes = [ctypes.c_void_p] * 3
+    L.vvref_quat_mult_vec.argtypes = [ctypes.c_void_p] * 3
+    return L
+
+
+def vector_texture(dat_path, shape, interp=(0, 10)):
+    """returns (float RGBA [z][y][x][4] as handed to glTexImage3D, geometry dict, internal format, wrap)"""
+    out = np.zeros(tuple(shape) + (4,), np.float32)
+    dims = (ctypes.c_int * 3)()
+    geom = np.zeros(17, np.float32)
+    ifmt, wrap = ctypes.c_int(), ctypes.c_int()
+    rc = _L().vvref_vector_texture(dat_path.encode(), interp[0], interp[1], out.ctypes.data, out.nbytes, dims, geom.ctypes.data,
+                                   ctypes.byref(ifmt), ctypes.byref(wrap))
+    assert rc > 0, rc
+    assert tuple(dims) == tuple(shape[::-1])
+    g = dict(extent=geom[0:3], center=geom[3:6], scale=geom[6:10], scale_inv=geom[10:14], slice_dist=geom[14:17])
+    return out, g, ifmt.value, wrap.value
+
+
+def noise_texture(path, shape, use_gradient):
+    ch = 4 if use_gradient else 1
+    out = np.zeros(tuple(shape) + ((4,) if use_gradient else ()), np.uint8)
+    dims = (ctypes.c_int * 3)()
+    ifmt, wrap = ctypes.c_int(), ctypes.c_int()
+    rc = _L().vvref_noise_texture(path.encode(), int(use_gradient), out.ctypes.data, out.nbytes, dims, ctypes.byref(ifmt), ctypes.byref(wrap))
+    assert rc == out.nbytes, rc
+    return out, ifmt.value, wrap.value
+
+
+def filter_texture(png_path=None):
+    out = np.zeros(4096, np.uint8)
+    width, inv, wrap = ctypes.c_int(), ctypes.c_float(), ctypes.c_int()
+    rc = _L().vvref_filter_texture(png_path.encode() if png_path else None, out.ctypes.data, out.nbytes, ctypes.byref(width),
+                                   ctypes.byref(inv), ctypes.byref(wrap))
+    assert rc == width.value, rc
+    return out[:width.value].copy(), inv.value, wrap.value
+
+
+def tf_textures(name=None):
+    rgba = np.zeros((256, 4), np.uint8)
+    la = np.zeros((256, 2), np.uint8)
+    loaded = ctypes.c_int()
+    rc = _L().vvref_tf_textures(name.encode() if name else None, rgba.ctypes.data, la.ctypes.data, ctypes.byref(loaded))
+    assert rc == 0
+    return rgba, la, bool(loaded.value)
+
+
+def noise_gradients(noise, slice_dist=(1.0, 1.0, 1.0)):
+    noise = np.ascontiguousarray(noise, np.uint8)
+    nz, ny, nx = noise.shape
+    g = np.zeros((nz, ny, nx, 3), np.float32)
+    f = np.zeros_like(g)
+    q = np.zeros((nz, ny, nx, 3), np.uint8)
+    dims = (ctypes.c_int * 3)(nx, ny, nz)
+    sd = (ctypes.c_float * 3)(*slice_dist)
+    _L().vvref_noise_gradients(noise.ctypes.data, dims, sd, g.ctypes.data, f.ctypes.data, q.ctypes.data)
+    return g, f, q
+
+
+def parse_dat(path):
+    res, dist = (ctypes.c_int * 3)(), (ctypes.c_float * 3)()
+    dt, dd, tb, te = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = _L().vvref_parse_dat(path.encode(), res, dist, ctypes.byref(dt), ctypes.byref(dd), ctypes.byref(tb), ctypes.byref(te))
+    if rc:
+        return None
+    return dict(resolution=tuple(res), slice_thickness=tuple(dist), data_type=dt.value, data_dim=dd.value, time=(tb.value, te.value))
+
+
+def parse_args(argv):
+    arr = (ctypes.c_char_p * len(argv))(*[a.encode() for a in argv])
+    out = ctypes.create_string_buffer(6 * 512)
+    flags = (ctypes.c_int * 2)()
+    rc = _L().vvref_parse_args(len(argv), arr, out, flags)
+    names = [out.raw[512 * i:512 * (i + 1)].split(b"\0")[0].decode() for i in range(6)]
+    return rc == 0, dict(vol=names[0], noise=names[1], tf=names[2], filter=names[3], redirect=names[4], halton=names[5],
+                         gradients=bool(flags[0]), lambda2=bool(flags[1]))
+
+
+def quat_angle_axis(q):
+    q = np.asarray(q, np.float32)
+    ang = ctypes.c_float()
+    ax = np.zeros(3, np.float32)
+    _L().vvref_quat_angle_axis(q.ctypes.data, ctypes.byref(ang), ax.ctypes.data)
+    return ang.value, ax
+
+
+def quat_mult_vec(q, v):
+    q = np.asarray(q, np.float32); v = np.asarray(v, np.float32)
+    out = np.zeros(3, np.float32)
+    _L().vvref_quat_mult_vec(q.ctypes.data, v.ctypes.data, out.ctypes.data)
+    return out

@@ -142,7 +142,9 @@ class RefScene:
             tfm = {0: "", 1: "_tfa", 2: "_tfr", 3: "_tflength", 4: "_tfscalar"}[self.s.tf_mode]
             return base + tfm
         if kind == "licvol":
-            return "licvol_gradient" if "ILLUM_GRADIENT" in d else "licvol_none"
+            if "ILLUM_GRADIENT" in d:
+                return "licvol_gradient"
+            return "licvol_sof" if "SPEED_OF_FLOW" in d else "licvol_none"
         return "volraycast"
 
     def _run(self, prog, tc):

@@ -1,0 +1,89 @@
+"""world_size-2 gloo test of the N > 1 host logic (sort-first block partition, tile gather layout, LIC-volume slabs).
+The device kernels are not involved: each rank builds its block-major tile buffer from a known image with the same
+bookkeeping the renderer uses, the buffers are all-gathered over gloo and assembled with the numpy mirror of the
+un-block kernel."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, w, h, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from vectorvisualization_b200 import dist as vd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.RandomState(7)
+    full = rng.rand(h, w, 4).astype(np.float32)                      # the frame every rank would agree on
+    nbx, nby = vd.block_grid(w, h)
+    bpr = vd.blocks_per_rank(w, h, world)
+    mine = np.zeros((bpr, 256, 4), np.float32)
+    for lb, b in enumerate(vd.local_blocks(w, h, rank, world)):      # this rank "renders" only its own blocks
+        bx, by = b % nbx, b // nbx
+        tile = np.zeros((16, 16, 4), np.float32)
+        y0, x0 = by * 16, bx * 16
+        hh, ww = min(16, h - y0), min(16, w - x0)
+        tile[:hh, :ww] = full[y0:y0 + hh, x0:x0 + ww]
+        mine[lb] = tile.reshape(256, 4)
+    gathered = torch.empty((world * bpr * 256 * 4,), dtype=torch.float32)
+    dist.all_gather_into_tensor(gathered, torch.from_numpy(mine).reshape(-1))
+    img = vd.assemble_host(gathered.numpy().reshape(world, bpr, 256, 4), w, h, world)
+    ok = bool(np.array_equal(img, full))
+    # LIC-volume slabs: every rank fills its z range, slabs are exchanged, result is complete
+    depth = 13
+    vol = torch.zeros((depth, 5))
+    z0, z1 = vd.slab_range(depth, rank, world)
+    vol[z0:z1] = torch.arange(z0, z1, dtype=torch.float32)[:, None]
+    for r in range(world):
+        a, b = vd.slab_range(depth, r, world)
+        dist.broadcast(vol[a:b], src=r)
+    ok = ok and bool(torch.equal(vol[:, 0], torch.arange(depth, dtype=torch.float32)))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("size", [(90, 70), (64, 64), (33, 17)])
+def test_partition_gather_assemble_gloo(size):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, size[0], size[1], q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_partition_bookkeeping():
+    from vectorvisualization_b200 import dist as vd
+    for (w, h) in ((1024, 1024), (90, 70), (16, 16), (1, 1)):
+        nbx, nby = vd.block_grid(w, h)
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(world):
+                lb = vd.local_blocks(w, h, r, world)
+                assert len(lb) <= vd.blocks_per_rank(w, h, world)
+                seen += lb
+            assert sorted(seen) == list(range(nbx * nby))
+    for depth in (1024, 13, 7):
+        for world in (1, 2, 4, 8):
+            z = [vd.slab_range(depth, r, world) for r in range(world)]
+            assert z[0][0] == 0 and z[-1][1] == depth and all(z[i][1] == z[i + 1][0] for i in range(world - 1))

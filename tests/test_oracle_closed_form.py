@@ -1,0 +1,202 @@
+"""Known-answer tests of the oracle against closed forms: GL sampling rules, the Heun integrator on
+analytic fields, computeLIC on a uniform field, opacity correction / compositing, uniform derivation, ray counts."""
+import ctypes
+
+import numpy as np
+import pytest
+
+
+def _scene(oracle, **kw):
+    from vectorvisualization_b200 import configs
+    s = configs.cfg1(n=kw.pop("n", 16), size=kw.pop("size", 32))
+    for k, v in kw.items():
+        setattr(s, k, v)
+    return s
+
+
+def _sample(oracle, o, which, p):
+    out = np.zeros(4, np.float32)
+    getattr(oracle.lib(), "vvo_sample_" + which)(ctypes.byref(o.c), oracle._p(np.asarray(p, np.float32)), oracle._p(out))
+    return out
+
+
+def test_linear_sampling_texel_centres(oracle):
+    """LINEAR: u = s N - 0.5 -> texel centres at (i + 0.5)/N reproduce the texel, midpoints average neighbours"""
+    from vectorvisualization_b200 import fields as F
+    s = _scene(oracle, n=8)
+    s.field = F.abc_flow(8)
+    o = oracle.OracleScene(s)
+    T = o.vec
+    for (x, y, z) in [(0, 0, 0), (3, 4, 5), (7, 7, 7), (1, 6, 2)]:
+        got = _sample(oracle, o, "vec", ((x + .5) / 8, (y + .5) / 8, (z + .5) / 8))
+        assert np.allclose(got, T[z, y, x], atol=1e-7)
+    got = _sample(oracle, o, "vec", (4 / 8, 4.5 / 8, 5.5 / 8))          # halfway between x = 3 and x = 4
+    assert np.allclose(got, 0.5 * (T[5, 4, 3] + T[5, 4, 4]), atol=1e-6)
+    # CLAMP_TO_EDGE: outside [0,1] the edge texel is returned
+    assert np.allclose(_sample(oracle, o, "vec", (-0.3, 0.5 / 8, 0.5 / 8)), T[0, 0, 0], atol=1e-7)
+    assert np.allclose(_sample(oracle, o, "vec", (1.7, 7.5 / 8, 7.5 / 8)), T[7, 7, 7], atol=1e-7)
+
+
+def test_noise_repeat_wrap(oracle):
+    s = _scene(oracle, n=8)
+    s.noise = np.random.RandomState(1).randint(0, 256, size=(8, 8, 8)).astype(np.uint8)
+    o = oracle.OracleScene(s)
+    p = np.array([0.3, 0.6, 0.9], np.float32)
+    a = _sample(oracle, o, "noise", p)
+    for shift in ((1, 0, 0), (0, -2, 0), (3, 1, -1)):
+        b = _sample(oracle, o, "noise", p + np.array(shift, np.float32))
+        assert np.allclose(a, b, atol=2e-6)                              # REPEAT: integer part ignored
+    # wrap across the seam: halfway between texel 7 and texel 0
+    got = _sample(oracle, o, "noise", (0.0, 0.5 / 8, 0.5 / 8))
+    want = 0.5 * (s.noise[0, 0, 7] + s.noise[0, 0, 0]) / 255.0
+    assert np.allclose(got[3], want, atol=1e-6)
+
+
+def test_kernel_gl_clamp_border(oracle):
+    """GL_CLAMP + LINEAR: s = 0 and s = 1 blend 50 % border colour 0 (Q10)"""
+    s = _scene(oracle)
+    o = oracle.OracleScene(s)          # box filter: 256 x 255
+    k = lambda x: oracle.lib().vvo_sample_kernel(ctypes.byref(o.c), ctypes.c_float(x))
+    assert k(0.5) == pytest.approx(1.0)
+    assert k(0.0) == pytest.approx(0.5) and k(1.0) == pytest.approx(0.5)
+    assert k(-3.0) == pytest.approx(0.5)                                  # s is clamped to [0,1] first
+    assert k(0.5 / 256) == pytest.approx(1.0)
+
+
+def test_tf_default_table(oracle):
+    s = _scene(oracle)
+    o = oracle.OracleScene(s)
+    rgba, la = np.zeros(4, np.float32), np.zeros(2, np.float32)
+    for i in (0, 19, 20, 21, 128, 255):
+        oracle.lib().vvo_sample_tf(ctypes.byref(o.c), ctypes.c_float((i + 0.5) / 256), oracle._p(rgba), oracle._p(la))
+        assert np.allclose(rgba[:3], i / 255.0, atol=1e-7)
+        assert np.allclose(rgba[3], max(0, i - 20) / 255.0, atol=1e-7) and np.allclose(la[1], max(0, i - 20) / 255.0, atol=1e-7)
+
+
+def test_uniform_derivation(oracle):
+    """Renderer::setRenderVolParams (VV/renderer.cpp:947-995) incl. the low-res preset"""
+    s = _scene(oracle)
+    s.params.update(stepSizeVol=1 / 128, stepsForward=25, stepsBackward=40, stepSizeLIC=0.02, gradientScale=7.0, illumScale=1.5, freqScale=2.2)
+    u = oracle.OracleScene(s).uniforms()
+    assert u[0] == np.float32(1 / 128) and tuple(u[1:4]) == (np.float32(7.0), np.float32(1.5), np.float32(2.2))
+    assert tuple(u[4:7]) == (25.0, 40.0, np.float32(0.02))
+    assert u[7] == np.float32(0.5) / np.float32(25) and u[8] == np.float32(0.5) / np.float32(40)
+    assert u[9] == np.float32(0.5) / np.float32(65)                     # box filter: invFilterArea 0.5 / (fwd + bwd)
+    assert u[10] == np.float32(1.0) and u[11] == 255
+    assert u[12] == np.float32(0.02) * np.float32(0.3)                  # Q3: logEyeDist = 0 -> h = 0.3 * stepSizeLIC
+    s.lowres = 1
+    u = oracle.OracleScene(s).uniforms()
+    assert u[0] == np.float32(2 / 128) and u[3] == np.float32(0.7) * np.float32(2.2)
+    assert tuple(u[4:7]) == (15.0, 15.0, np.float32(1 / 64)) and u[9] == np.float32(0.5) / np.float32(30.0) and u[10] == np.float32(2.0)
+
+
+def test_lic_uniform_field_closed_form(oracle):
+    """uniform field along +x, constant noise c: streamline = straight line, LIC = c * sum_k K(offset_k)"""
+    from vectorvisualization_b200 import fields as F
+    s = _scene(oracle, n=16)
+    s.field = F.uniform_field(16, (1.0, 0.0, 0.0))
+    s.noise = np.full((16, 16, 16), 102, np.uint8)                       # 0.4
+    s.filter_row = F.filter_kernel("triangle")
+    s.params.update(stepsForward=8, stepsBackward=8)
+    o = oracle.OracleScene(s)
+    got = o.compute_lic((0.5, 0.5, 0.5))[3]
+    k = lambda x: oracle.lib().vvo_sample_kernel(ctypes.byref(o.c), ctypes.c_float(x))
+    want = 0.4 * (k(0.5) + sum(k(0.5 - i / 16.0) for i in range(1, 9)) + sum(k(0.5 + i / 16.0) for i in range(1, 9)))
+    assert got == pytest.approx(want, rel=2e-6)
+
+
+def test_lic_streamline_positions_uniform_field(oracle):
+    """noise = x ramp: each tap reads the x coordinate of the streamline -> positions advance by exactly h = 0.3 * stepSizeLIC"""
+    from vectorvisualization_b200 import fields as F
+    n = 64
+    s = _scene(oracle, n=16)
+    s.field = F.uniform_field(16, (1.0, 0.0, 0.0))
+    ramp = np.broadcast_to((np.arange(n) * 255 // (n - 1)).astype(np.uint8), (n, n, n)).copy()
+    s.noise = ramp
+    s.params.update(stepsForward=4, stepsBackward=0, stepSizeLIC=0.05)
+    o = oracle.OracleScene(s)
+    h = np.float32(0.05) * np.float32(0.3)
+    lic = o.compute_lic((0.25, 0.5, 0.5))[3]
+    samp = lambda x: _sample(oracle, o, "noise", (x, 0.5, 0.5))[3]
+    want = sum(samp(np.float32(0.25) + np.float32(i) * h) for i in range(0, 5))    # box kernel weight 1 (last tap at offset 1.0 -> 0.5)
+    want -= 0.5 * samp(np.float32(0.25) + np.float32(4) * h)
+    assert lic == pytest.approx(want, rel=1e-5)
+
+
+def test_heun_on_rigid_rotation(oracle):
+    """Heun (RK2) on a rigid rotation keeps the radius to O(h^3) per step and turns by ~h/r per step"""
+    n = 64
+    c = -1.0 + (2.0 * np.arange(n) + 1.0) / n
+    z, y, x = np.meshgrid(c, c, c, indexing="ij")
+    field = np.stack([-y, x, np.zeros_like(x)], axis=-1).astype(np.float32)
+    s = _scene(oracle, n=16)
+    s.field = field
+    # noise = y ramp: a tap reads y of the streamline position
+    s.noise = np.broadcast_to((np.arange(256) * 255 // 255).astype(np.uint8)[None, :, None], (4, 256, 4)).copy()
+    s.params.update(stepsForward=1, stepsBackward=0, stepSizeLIC=0.1)
+    o = oracle.OracleScene(s)
+    p0 = np.array([0.75, 0.5, 0.5], np.float32)                             # radius 0.25 in tex space, direction +y
+    lic = o.compute_lic(p0)[3]
+    tap0 = _sample(oracle, o, "noise", p0)[3]
+    y1 = (lic - tap0) / 0.5          # last (only) forward tap is weighted by K(1.0) = 0.5
+    h = 0.1 * 0.3
+    # exact circle: y advances by r sin(h / r); Heun: h (1 - (h/r)^2/2)-ish -> agree to O(h^3)
+    yy = y1 * 256 / 255.0 + 0.5 / 256 * 0    # ramp decode (approx.)
+    assert abs((y1 * 255.0 / 255.0) - (0.5 + 0.25 * np.sin(h / 0.25))) < 3e-3
+
+
+def test_opacity_correction_and_compositing(oracle):
+    """constant LIC intensity volume: dest after n samples = closed form of the over operator with clamp"""
+    from vectorvisualization_b200 import configs, fields as F
+    s = configs.cfg2(n=16, size=24)
+    s.field = F.uniform_field(16, (0.0, 0.0, 1.0))
+    s.tf = F.default_tf()
+    s.params.update(stepSizeVol=1 / 64)          # alphaCorrection = 2
+    o = oracle.OracleScene(s)
+    lic = np.full((16, 16, 16), 0.5, np.float32)
+    img, cnt, tot = o.raycast_licvolume(lic)
+    y, x = 12, 12
+    n = int(cnt[y, x])
+    assert n > 0
+    # field direction (0,0,1): rgb = (.5,.5,1), TF index = .b = 1 -> tf = (1,1,1, 235/255); illum 0.5 -> opacity table at 0.65
+    tfa = 235 / 255.0
+    oi = 0.65 * 256 - 0.5
+    op = ((1 - (oi % 1)) * max(0, int(oi) - 20) + (oi % 1) * max(0, int(oi) + 1 - 20)) / 255.0
+    a = 1 - (1 - op * tfa) ** 2
+    rgb = 0.5 * 1.0 * 1.0 * a
+    d = np.zeros(4)
+    for _ in range(n):
+        d = np.clip((1 - d[3]) * np.array([rgb, rgb, rgb, a]) + d, 0, 1)
+        if d[3] > 0.95:
+            break
+    assert np.allclose(img[y, x], d, atol=2e-5)
+
+
+def test_ray_sample_count_analytic(oracle):
+    """axis-aligned view: a central ray crosses the unit cube over length 1 -> floor(1/step) + 1 samples (no early stop)"""
+    from vectorvisualization_b200 import configs, fields as F
+    s = configs.cfg3(n=8, size=33)
+    for step, want in ((1 / 64, 65), (1 / 128, 129), (1 / 256, 257)):
+        s.params.update(stepSizeVol=step)
+        _, cnt, _ = oracle.OracleScene(s).raycast(rect=(16, 16, 17, 17))
+        assert abs(int(cnt[16, 16]) - want) <= 1
+
+
+def test_white_noise_definition(oracle):
+    from vectorvisualization_b200 import fields as F
+    for seed, p in ((1, F.SPARSE_P), (2, F.DENSE_P)):
+        assert np.array_equal(oracle.white_noise(12, seed, p), F.white_noise(12, seed, p))
+    assert abs(F.white_noise(32, 1, F.SPARSE_P).mean() / 255 - 1 / 6) < 0.01
+
+
+def test_half_round(oracle):
+    for v in (0.1, 0.3333, 1.0, 0.5004883, 6.1e-5, 0.99951172):
+        assert oracle.lib().vvo_half_round(ctypes.c_float(v)) == float(np.float32(v).astype(np.float16))
+
+
+def test_background_and_rgba8_store(oracle):
+    rgba = np.array([[0.2, 0.1, 0.0, 0.5], [1.0, 1.0, 1.0, 1.0], [0.0, 0.0, 0.0, 0.0], [0.5019, 0.4981, 1.2, -0.1]], np.float32)
+    bg = oracle.background(rgba)
+    assert np.allclose(bg[0], [0.7, 0.6, 0.5, 1.0]) and np.allclose(bg[2], 1.0)
+    q = oracle.quantize_rgba8(rgba)
+    assert list(q[3]) == [128, 127, 255, 0]

@@ -1,0 +1,63 @@
+"""The oracle (fp32 C++ restatement) against the REFERENCE'S OWN SHADER SOURCE compiled as C++ (oracle/_ref, built by
+oracle/build_ref.py from /root/reference/VectorVisualization/shader/*.glsl).  Runs wherever oracle/_ref/libvv_ref.so
+exists (the build container; the .so also travels to the GPU box).  Expectation: bit-identical frames and ray-sample
+counts -- both sides are single-operation IEEE fp32 in the order the shader source writes the arithmetic."""
+import numpy as np
+import pytest
+
+from oracle import refshim
+
+pytestmark = pytest.mark.skipif(not refshim.available(), reason="oracle/_ref/libvv_ref.so not built (needs /root/reference)")
+
+
+def _scenes():
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from scenes import golden_scenes
+    import vectorvisualization_b200 as vv
+    from vectorvisualization_b200 import configs, fields as F
+    S = dict(golden_scenes())
+
+    def lum():
+        s = configs.cfg1(n=16, size=32)
+        s.quirk_luminance_alpha = 1          # GL_LUMINANCE noise: .a == 1 (Q7)
+        s.params.update(gradientScale=1.0)
+        return s
+    S["quirk_luminance_alpha"] = lum
+
+    def lowres():
+        s = configs.cfg2(n=20, size=32)
+        s.lowres = 1
+        return s
+    S["lowres"] = lowres
+
+    def q1():
+        s = configs.cfg3(n=16, size=32, camera=F.CAMERA_CLOSE)
+        s.field = np.ascontiguousarray(F.tornado(24)[:12, :20, :])
+        s.slice_dist = (1.0, 1.5, 2.0)        # anisotropic: scale != scaleInv, Q1 visible
+        s.tf_mode = vv.TF_B
+        return s
+    S["q1_anisotropic_gradient"] = q1
+    return S
+
+
+@pytest.mark.parametrize("name", sorted(_scenes().keys()))
+def test_raycast_bit_exact(oracle, name):
+    s = _scenes()[name]()
+    a, ca, ta = oracle.OracleScene(s).raycast()
+    b, cb, tb = refshim.RefScene(s).raycast()
+    assert ta == tb and np.array_equal(ca, cb)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "max abs diff %g" % np.abs(a - b).max()
+
+
+@pytest.mark.parametrize("name", ["cfg2_close_gs6", "cfg3_gradient_length", "anisotropic_tf_scalar_band"])
+def test_lic_volume_and_volume_raycast_bit_exact(oracle, name):
+    s = _scenes()[name]()
+    s.licvol_fp16 = 0
+    o, r = oracle.OracleScene(s), refshim.RefScene(s)
+    lo, lr = o.lic_volume((10, 12, 14)), r.lic_volume((10, 12, 14))
+    assert np.array_equal(lo.view(np.uint32), lr.view(np.uint32))
+    a, ca, ta = o.raycast_licvolume(lo)
+    b, cb, tb = r.raycast_licvolume(lo)
+    assert ta == tb and np.array_equal(ca, cb)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))

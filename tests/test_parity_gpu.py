@@ -399,3 +399,40 @@ def test_file_loaders_roundtrip(vv, oracle, tmp_path):
     r.savePNG(out)
     back = vv.png_read(out)
     assert np.array_equal(back[::-1], r.readRGBA8())
+
+
+def _golden_names():
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from scenes import golden_scenes
+    return sorted(golden_scenes().keys())
+
+
+@pytest.mark.parametrize("name", _golden_names())
+def test_cuda_matches_golden_vectors(vv, oracle, name):
+    """CUDA path against tests/golden/*.npz -- outputs of the reference's own shader code (tests/golden/make_golden.py)"""
+    import os
+    from scenes import golden_scenes
+    from vectorvisualization_b200.configs import apply_scene
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    s = golden_scenes()[name]()
+    r, img, _, cnt, tot = render_cuda(vv, s)
+    assert tot == int(g["total"]) and np.array_equal(cnt, g["raycast_samples"].astype(np.uint32))
+    assert_image_parity(oracle, img, g["raycast"], name)
+    # LIC volume (12^3 target) and the volume ray-cast over the full-resolution LIC volume
+    s.licvol_fp16 = 0
+    s.licvol_size = 12
+    s.technique = vv.VOLIC_LICVOLUME
+    r2 = vv.Renderer(0)
+    apply_scene(r2, s)
+    r2.updateLICVolume()
+    lv = r2.readLICVolume()
+    want = g["licvol12"]
+    assert (np.abs(lv - want) / np.maximum(np.abs(want), 1e-3 * np.abs(want).max())).max() <= LICVOL_REL
+    s.licvol_size = 0
+    r3 = vv.Renderer(0)
+    apply_scene(r3, s)
+    r3.setOption(vv.OPT_SAMPLE_MAP, 1)
+    r3.render(True)
+    assert int((r3.readSampleMap() != g["volraycast_samples"].astype(np.uint32)).sum()) <= 1
+    assert_image_parity(oracle, r3.readRGBA32F(), g["volraycast"], name + " volume ray-cast")
