@@ -273,14 +273,14 @@ def run_cuda(args):
     n = scene.field.shape
     compulsory = n[0] * n[1] * n[2] * 16 + scene.noise.size * (16 if scene.with_gradients else 8) + scene.width * scene.height * 16
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes_per_ray_sample": B, "kernel": "lic_raycast_kernel",
+                "peak_source": peak_src, "algorithmic_bytes_per_ray_sample": B, "kernel": "lic_sample_kernel",
                 "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
                 "note": "requested gather bytes (L1/L2-served, reuse makes frac > 1 legitimate); compulsory HBM bytes/frame = %d" % compulsory,
                 "compulsory_hbm_frac": compulsory / (k_ms * 1e-3) / 1e9 / peak}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get(scene.name)
+            roofline["traffic"] = (json.load(open(prof)).get(scene.name) or {}).get("bytes_per_launch")
         except Exception:
             pass
 

@@ -280,7 +280,9 @@ inline V3 quat_rotate(const float q[4], V3 v)
             (float)(v.z + w * tz + (x * ty - y * tx))};
 }
 
-void make_ctx(const VVOScene *s, Ctx &c)
+/* raycast_program: the LIC ray-cast / slicing programs, where scaleVolInv can be an active uniform (Q1);
+ * the LIC-volume and volume-ray-cast programs never reference it (VV/renderer.cpp:807-922) */
+void make_ctx(const VVOScene *s, Ctx &c, bool raycast_program = true)
 {
     c.s = s;
     /* renderer.cpp:947-995 */
@@ -303,7 +305,7 @@ void make_ctx(const VVOScene *s, Ctx &c)
     /* renderer.cpp:934-944, incl. Q1: scaleVolInv is written into scaleVol's slot in programs
      * where scaleVolInv is an active uniform (the ILLUM_* builds); scaleVolInv itself stays 0. */
     c.texMax = {s->extent[0] * s->scale[0], s->extent[1] * s->scale[1], s->extent[2] * s->scale[2]};
-    bool inv_active = (s->illum_mode != VVO_ILLUM_NONE);
+    bool inv_active = raycast_program && (s->illum_mode != VVO_ILLUM_NONE);
     if (inv_active && s->quirk_scalevolinv) {
         c.scaleVol = {s->scale_inv[0], s->scale_inv[1], s->scale_inv[2]};
         c.scaleVolInv = {0.0f, 0.0f, 0.0f};
@@ -628,10 +630,10 @@ V4 frag_raycast_licvolume(const Ctx &c, V3 geomPos, uint32_t &nsamples)
 }
 
 template <class F>
-uint64_t for_pixels(const VVOScene *s, int x0, int y0, int x1, int y1, float *out_rgba, uint32_t *out_samples, F frag)
+uint64_t for_pixels(const VVOScene *s, int x0, int y0, int x1, int y1, float *out_rgba, uint32_t *out_samples, F frag, bool raycast_program = true)
 {
     Ctx c;
-    make_ctx(s, c);
+    make_ctx(s, c, raycast_program);
     uint64_t total = 0;
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
     for (int y = y0; y < y1; ++y) {
@@ -671,7 +673,7 @@ uint64_t vvo_raycast_lic(const VVOScene *s, float *out_rgba, uint32_t *out_sampl
 uint64_t vvo_raycast_licvolume(const VVOScene *s, float *out_rgba, uint32_t *out_samples)
 {
     return for_pixels(s, 0, 0, s->width, s->height, out_rgba, out_samples,
-                      [](const Ctx &c, V3 e, uint32_t &n) { return frag_raycast_licvolume(c, e, n); });
+                      [](const Ctx &c, V3 e, uint32_t &n) { return frag_raycast_licvolume(c, e, n); }, false);
 }
 
 /* lic3d_volume_fragment.glsl:2-21, one fragment per voxel centre of a w x h x d target
@@ -680,7 +682,7 @@ uint64_t vvo_raycast_licvolume(const VVOScene *s, float *out_rgba, uint32_t *out
 void vvo_lic_volume(const VVOScene *s, int w, int h, int d, int z0, int z1, float *out)
 {
     Ctx c;
-    make_ctx(s, c);
+    make_ctx(s, c, false);
     bool grad = (s->illum_mode == VVO_ILLUM_GRADIENT);
 #pragma omp parallel for schedule(dynamic, 1) collapse(2)
     for (int z = z0; z < z1; ++z)

@@ -50,7 +50,7 @@ def test_raycast_bit_exact(oracle, name):
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "max abs diff %g" % np.abs(a - b).max()
 
 
-@pytest.mark.parametrize("name", ["cfg2_close_gs6", "cfg3_gradient_length", "anisotropic_tf_scalar_band"])
+@pytest.mark.parametrize("name", ["cfg2_close_gs6", "cfg3_gradient_length", "anisotropic_tf_scalar_band", "q1_anisotropic_gradient"])
 def test_lic_volume_and_volume_raycast_bit_exact(oracle, name):
     s = _scenes()[name]()
     s.licvol_fp16 = 0

@@ -309,7 +309,8 @@ static int pack_field(VVRenderer *r)
     return VV_OK;
 }
 
-static int fill_params(VVRenderer *r, DevParams &P, bool need_frame)
+// raycast_program: the LIC ray-cast program, the only one where scaleVolInv can be an active uniform (Q1)
+static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycast_program = true)
 {
     if (!r->have_field) return fail(VV_ERR_STATE, "no vector field set (vv_set_vector_field / vv_load_dat)");
     if (r->field_dirty || (r->field_layout == LAYOUT_PAIR ? !r->field_pair.p : !r->field_f4.p)) {
@@ -346,7 +347,7 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame)
     P.numIter = r->lp.numIterations; P.nFwd = u.nFwd; P.nBwd = u.nBwd;
     P.nFwdEff = r->n_fwd_eff; P.nBwdEff = r->n_bwd_eff;
     // VV/renderer.cpp:934-944 incl. Q1
-    const bool inv_active = (r->illum_mode != ILLUM_NONE);
+    const bool inv_active = raycast_program && (r->illum_mode != ILLUM_NONE);
     for (int i = 0; i < 3; ++i) {
         P.texMax[i] = r->extent[i] * r->scale[i];
         if (inv_active && r->quirk_scalevolinv) { P.scaleVol[i] = r->scale_inv[i]; P.scaleVolInv[i] = 0.0f; }
@@ -402,7 +403,7 @@ static int compute_lic_volume(VVRenderer *r)
     int n = r->licvol_size > 0 ? r->licvol_size : 0;
     int dims[3] = {n ? n : r->size[0], n ? n : r->size[1], n ? n : r->size[2]};
     DevParams P;
-    int rc = fill_params(r, P, false);
+    int rc = fill_params(r, P, false, false);
     if (rc) return rc;
     const size_t cnt = (size_t)dims[0] * dims[1] * dims[2];
     if (r->licvol.n < cnt || r->ldim[0] != dims[0] || r->ldim[1] != dims[1] || r->ldim[2] != dims[2]) {
@@ -949,7 +950,7 @@ int vv_render(VVRenderer *r, int update)
         }
     }
     DevParams P;
-    int rc = fill_params(r, P, true);
+    int rc = fill_params(r, P, true, r->technique == VV_VOLIC_RAYCAST || r->technique == VV_VOLIC_SLICING);
     if (rc) return rc;
     CU(cudaMemsetAsync(r->counters.p, 0, kNumCounters * sizeof(unsigned int), r->stream));
     const int grid = persistent_grid(r, r->n_local_blocks);
