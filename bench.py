@@ -94,42 +94,44 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
 
-def cpu_rate(scene, budget_s, use_ref=True):
-    """ray samples/s of the CPU implementation on a centred pixel rectangle sized for ~budget_s seconds.
-    Returns dict(value, cores, kind, sample, seconds, samples)."""
+def make_cpu_runner(scene, use_ref=True):
+    """the CPU implementation of the path: the reference's shader code compiled as C++ (oracle/_ref, kind "reference")
+    when it was built from /root/reference, else the oracle port (kind "port")"""
     from oracle import vvo
-    kind = "port"
-    runner = None
     if use_ref:
         try:
             from oracle import refshim
             if refshim.available():
-                runner = refshim.RefScene(scene)
-                kind = "reference"
+                return refshim.RefScene(scene), "reference", vvo.lib().vvo_num_threads()
         except Exception:
-            runner = None
-    if runner is None:
-        runner = vvo.OracleScene(scene)
-    cores = vvo.lib().vvo_num_threads()
+            pass
+    return vvo.OracleScene(scene), "port", vvo.lib().vvo_num_threads()
+
+
+def centred_rect(scene, side):
     w, h = scene.width, scene.height
-    # probe on a small centred rectangle, then scale the rectangle to the budget
-    def rect(side):
-        side = max(8, min(side, min(w, h)))
-        x0, y0 = (w - side) // 2, (h - side) // 2
-        return (x0, y0, x0 + side, y0 + side)
-    t = time.perf_counter()
-    _, _, n = runner.raycast(rect(24))
-    dt = time.perf_counter() - t
-    rate = max(n, 1) / max(dt, 1e-6)
-    per_px = max(n, 1) / (24.0 * 24.0)
-    side = int((budget_s * rate / per_px) ** 0.5)
-    rc = rect(side)
+    side = max(8, min(int(side), min(w, h)))
+    x0, y0 = (w - side) // 2, (h - side) // 2
+    return (x0, y0, x0 + side, y0 + side)
+
+
+def cpu_rate(scene, runner, kind, cores, budget_s, side=None):
+    """ray samples/s of the CPU implementation on a centred pixel rectangle sized for ~budget_s seconds"""
+    if side is None:
+        t = time.perf_counter()
+        _, _, n = runner.raycast(centred_rect(scene, 24))
+        dt = time.perf_counter() - t
+        rate = max(n, 1) / max(dt, 1e-6)
+        per_px = max(n, 1) / (24.0 * 24.0)
+        side = (budget_s * rate / per_px) ** 0.5
+    rc = centred_rect(scene, side)
     t = time.perf_counter()
     _, _, n = runner.raycast(rc)
     dt = time.perf_counter() - t
-    return dict(value=n / dt, cores=cores, kind=kind, seconds=dt, samples=int(n),
-                sample="%s, centred %dx%d-pixel rectangle of the %dx%d frame (%d ray samples, %.1f s)" % (
-                    scene.name, rc[2] - rc[0], rc[3] - rc[1], w, h, n, dt))
+    return dict(value=n / dt, cores=cores, kind=kind, seconds=dt, samples=int(n), side=rc[2] - rc[0],
+                sample="%s, centred %dx%d-pixel rectangle of the %dx%d frame (%d ray samples, %.1f s, %s)" % (
+                    scene.name, rc[2] - rc[0], rc[3] - rc[1], scene.width, scene.height, n, dt,
+                    "reference shader code compiled as C++ (oracle/_ref)" if kind == "reference" else "fp32 C++ port (oracle/)"))
 
 
 def run_reference(args):
@@ -137,14 +139,17 @@ def run_reference(args):
     if rank != 0:
         return 0
     scene = make_scene(args.config)
+    runner, kind, cores = make_cpu_runner(scene)
     total_budget = 150.0
     per_step = max(1.0, min(12.0, total_budget / max(1, args.steps + args.warmup)))
-    for _ in range(args.warmup):
-        cpu_rate(scene, per_step)
-    vals, secs, samples, info = [], 0.0, 0, None
+    info = cpu_rate(scene, runner, kind, cores, per_step)          # sizes the rectangle (counts as the first warm-up)
+    side = info["side"]
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_rate(scene, runner, kind, cores, per_step, side)
+    secs, samples = 0.0, 0
     for _ in range(args.steps):
-        info = cpu_rate(scene, per_step)
-        vals.append(info["value"]); secs += info["seconds"]; samples += info["samples"]
+        info = cpu_rate(scene, runner, kind, cores, per_step, side)
+        secs += info["seconds"]; samples += info["samples"]
     value = samples / secs
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -287,7 +292,8 @@ def run_cuda(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         try:
-            c = cpu_rate(scene, 15.0)
+            runner, kind, cores = make_cpu_runner(scene)
+            c = cpu_rate(scene, runner, kind, cores, 15.0)
             cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"], "sample": c["sample"]}
         except Exception as ex:   # the baseline is reported, never required for the GPU number
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}

@@ -138,7 +138,10 @@ VV_API int vv_update_light_pos(VVRenderer *r);
 VV_API int vv_enable_lowres(VVRenderer *r, int enable);
 VV_API int vv_enable_float_target(VVRenderer *r, int enable);
 VV_API int vv_set_option(VVRenderer *r, int option, int value);
-/* setIllum*Tex (Illumination, VV/illumination.cpp:96-333): tables are generated inside (host, one-off) */
+/* setIllum*Tex (Illumination, VV/illumination.cpp:96-390): the Zoeckler / Mallo look-up tables are generated inside the
+ * library when an ILLUM_MALLO / ILLUM_ZOECKLER build is selected; this host-only entry point returns the same tables
+ * (decoded UNORM8 values): zoeckler [h][w][2] (luminance, alpha), mallo [h][w] each */
+VV_API int vv_make_illum_tables(float spec_exp, int width, int height, float *zoeckler_la, float *mallo_diffuse, float *mallo_specular);
 
 /* ---- frame: Renderer::render(update), VV/renderer.cpp:126-312 -------------------------------- */
 VV_API int vv_render(VVRenderer *r, int update);

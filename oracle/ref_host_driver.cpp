@@ -20,6 +20,7 @@
 #include "GL/glew.h"
 #include "dataset.h"
 #include "gradient.h"
+#include "illumination.h"
 #include "imageUtils.h"
 #include "mmath.h"
 #include "parseArg.h"
@@ -266,6 +267,20 @@ void vvref_quat_mult_vec(const float q[4], const float v[3], float out[3])
     Vector3 a = Vector3_new(v[0], v[1], v[2]);
     Vector3 r = Quaternion_multVector3(qq, a);
     out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+/* Illumination::createIllumTextures(true, true, true) as VV/3DLIC.cpp:735 calls it; returns the three uploads:
+ * zoeckler float LA [h][w][2], mallo diffuse / specular float RGBA [h][w][4], and their internal formats */
+int vvref_illum_tables(float *zoeckler, float *mdiff, float *mspec, int dims[2], int ifmt[3], float *spec_exp)
+{
+    Illumination il;
+    il.createIllumTextures(true, true, true);
+    int d[3];
+    if (copy_tex(il.getTexZoeckler()->id, zoeckler, (size_t)256 * 256 * 2 * 4, d, &ifmt[0], nullptr) < 0) return -1;
+    if (copy_tex(il.getTexMalloDiffuse()->id, mdiff, (size_t)256 * 256 * 4 * 4, d, &ifmt[1], nullptr) < 0) return -2;
+    if (copy_tex(il.getTexMalloSpecular()->id, mspec, (size_t)256 * 256 * 4 * 4, d, &ifmt[2], nullptr) < 0) return -3;
+    dims[0] = d[0]; dims[1] = d[1];
+    *spec_exp = il.getSpecularExp();
+    return 0;
 }
 int vvref_next_pow2(int v) { return nextPowerTwo(v); }
 int vvref_has_host(void) { return 1; }

@@ -121,3 +121,15 @@ def quat_mult_vec(q, v):
     out = np.zeros(3, np.float32)
     _L().vvref_quat_mult_vec(q.ctypes.data, v.ctypes.data, out.ctypes.data)
     return out
+
+
+def illum_tables():
+    """(zoeckler float [256][256][2], mallo diffuse [256][256][4], mallo specular [256][256][4], internal formats, specExp)
+    exactly as Illumination::createIllumTextures hands them to glTexImage2D"""
+    L = _L()
+    L.vvref_illum_tables.argtypes = [ctypes.c_void_p] * 6
+    z = np.zeros((256, 256, 2), np.float32); d = np.zeros((256, 256, 4), np.float32); s = np.zeros((256, 256, 4), np.float32)
+    dims = (ctypes.c_int * 2)(); ifmt = (ctypes.c_int * 3)(); se = ctypes.c_float()
+    rc = L.vvref_illum_tables(z.ctypes.data, d.ctypes.data, s.ctypes.data, dims, ifmt, ctypes.byref(se))
+    assert rc == 0 and tuple(dims) == (256, 256)
+    return z, d, s, tuple(ifmt), se.value

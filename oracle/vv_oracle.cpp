@@ -1040,6 +1040,72 @@ void vvo_default_tf(uint8_t *tf)
     }
 }
 
+/* GL float -> UNORM8 -> float of an 8-bit texture upload */
+static float unorm8_roundtrip(float v) { return std::floor(clampf(v, 0.0f, 1.0f) * 255.0f + 0.5f) / 255.0f; }
+
+/* Illumination::createIllumTexZoeckler / createIllumTexMallo / computeSpecTermMallo, illumination.cpp:96-390, with the
+ * LineMat defaults of illumination.h:40-62.  createIllumTextures does not forward floatTex (illumination.cpp:59-91), so
+ * the textures are 8-bit: out arrays hold the decoded UNORM8 values.  zoeckler [h][w][2], mallo_* [h][w] (4 equal channels). */
+void vvo_illum_tables(float spec_exp, int w, int h, float *zoeckler, float *mallo_diff, float *mallo_spec)
+{
+    const float lightColor = 1.0f, ambient = 0.1f, diffuseM = 0.5f, specularM = 0.8f, diffExp = 2.0f;
+    auto integrand = [](double beta, double n, double theta) {
+        double y = std::cos(theta - beta);
+        if (y < 0.0) y = 0.0;
+        return (std::pow(y, n) * (std::cos(theta) / 2.0));
+    };
+    auto specTerm = [&](double alpha, double beta, double n) {
+        double a = alpha - M_PI / 2.0, b = M_PI / 2.0;
+        int m = 10;
+        double hh = (b - a) / (2.0 * m), integral = 0.0;
+        for (int i = 0; i < 2 * m; i += 2) {
+            double xi = a + i * hh;
+            integral += 2.0 * integrand(beta, n, xi);
+            xi = a + (i + 1) * hh;
+            integral += 4.0 * integrand(beta, n, xi);
+        }
+        integral += integrand(beta, n, b);
+        integral -= integrand(beta, n, a);
+        integral *= hh / 3.0;
+        return integral;
+    };
+    int idx = 0;
+    double invResX = 1.0 / (double)(w - 1), invResY = 1.0 / (double)(h - 1);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            double t1 = (double)x * invResX, t2 = (double)y * invResY;
+            double lt = 2.0 * t1 - 1.0, vt = 2.0 * t2 - 1.0;
+            double diffuse = std::sqrt(1.0 - lt * lt);
+            diffuse = std::pow(diffuse, (double)diffExp);
+            double dotproduct = lt * vt - std::sqrt(1.0 - lt * lt) * std::sqrt(1.0 - vt * vt);
+            dotproduct = (dotproduct < -1.0) ? -1.0 : ((dotproduct > 1.0) ? 1.0 : dotproduct);
+            double traditionalDiff = ambient * lightColor + diffuse * diffuseM * lightColor;
+            double traditionalSpec = std::pow(std::fabs(dotproduct), static_cast<double>(spec_exp)) * specularM * lightColor;
+            traditionalDiff *= 0.5;
+            traditionalDiff = (traditionalDiff < 0.0) ? 0.0 : ((traditionalDiff > 1.0) ? 1.0 : traditionalDiff);
+            traditionalSpec *= 0.5;
+            traditionalSpec = (traditionalSpec < 0.0) ? 0.0 : ((traditionalSpec > 1.0) ? 1.0 : traditionalSpec);
+            zoeckler[idx++] = unorm8_roundtrip(static_cast<float>(traditionalDiff));
+            zoeckler[idx++] = unorm8_roundtrip(static_cast<float>(traditionalSpec) * 0.9f);
+        }
+    idx = 0;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            double s = ((double)x + 0.5) / w, t = ((double)y + 0.5) / h;
+            double alpha = std::acos(2.0 * s - 1.0), beta = std::acos(2.0 * t - 1.0);
+            double lt = 2.0 * t - 1.0;
+            double diffuse = std::sqrt(1.0 - lt * lt) * (std::sin(alpha) + (M_PI - alpha) * std::cos(alpha)) * 0.25;
+            double specular = 3.5 * specTerm(alpha, beta, spec_exp);
+            double color = diffuse * diffuseM * lightColor;
+            color = (color < 0.0) ? 0.0 : ((color > 1.0) ? 1.0 : color);
+            mallo_diff[idx] = unorm8_roundtrip((float)color);
+            color = specular * specularM * lightColor;
+            color = (color < 0.0) ? 0.0 : ((color > 1.0) ? 1.0 : color);
+            mallo_spec[idx] = unorm8_roundtrip((float)color);
+            idx++;
+        }
+}
+
 float vvo_half_round(float x) { return half_round(x); }
 
 int vvo_num_threads(void)

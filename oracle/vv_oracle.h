@@ -131,6 +131,8 @@ int vvo_filter_from_row(const uint8_t *row, int width, int channels, uint8_t *ou
 int vvo_box_filter(int width, uint8_t *out, float *inv_area);
 /* transferEdit.cpp:61-98 */
 void vvo_default_tf(uint8_t *tf5);
+/* illumination.cpp:96-390: zoeckler [h][w][2], mallo diffuse / specular [h][w]; decoded 8-bit values */
+void vvo_illum_tables(float spec_exp, int w, int h, float *zoeckler, float *mallo_diff, float *mallo_spec);
 /* fp16 round trip */
 float vvo_half_round(float x);
 

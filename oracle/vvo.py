@@ -81,6 +81,7 @@ def lib():
         L.vvo_box_filter.argtypes = [I, P, P]; L.vvo_box_filter.restype = I
         L.vvo_default_tf.argtypes = [P]
         L.vvo_half_round.argtypes = [F]; L.vvo_half_round.restype = F
+        L.vvo_illum_tables.argtypes = [F, I, I, P, P, P]
         L.vvo_num_threads.restype = I
         _lib = L
     return _lib
@@ -141,6 +142,12 @@ def box_filter(width=256):
     inv = ctypes.c_float()
     fw = lib().vvo_box_filter(width, _p(out), ctypes.byref(inv))
     return out[:fw].copy(), inv.value
+
+
+def illum_tables(spec_exp=40.0, w=256, h=256):
+    z = np.zeros((h, w, 2), np.float32); d = np.zeros((h, w), np.float32); s = np.zeros((h, w), np.float32)
+    lib().vvo_illum_tables(spec_exp, w, h, _p(z), _p(d), _p(s))
+    return z, d, s
 
 
 def default_tf():

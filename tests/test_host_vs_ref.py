@@ -173,3 +173,17 @@ def test_quaternion_helpers(oracle):
         if ang:
             assert np.allclose(a, np.deg2rad(ang), atol=1e-5)
             assert np.allclose(ax, np.asarray(axis, np.float32) / np.linalg.norm(axis), atol=1e-6)
+
+
+def test_illumination_tables(vv, oracle):
+    """Zoeckler / Mallo look-up tables: reference generator (captured glTexImage2D data, 8-bit internal formats) ==
+    oracle restatement == the tables the product library builds"""
+    z, d, s, ifmt, spec_exp = refhost.illum_tables()
+    assert ifmt == (0x190A, 0x1908, 0x1908) and spec_exp == 40.0      # GL_LUMINANCE_ALPHA, GL_RGBA: floatTex is not forwarded
+    q = lambda a: np.floor(np.clip(a, 0, 1).astype(np.float32) * np.float32(255) + np.float32(0.5)) / np.float32(255)
+    oz, od, os_ = oracle.illum_tables(spec_exp)
+    assert np.array_equal(oz, q(z)) and np.array_equal(od, q(d[..., 0])) and np.array_equal(os_, q(s[..., 0]))
+    for c in (1, 2, 3):
+        assert np.array_equal(d[..., 0], d[..., c]) and np.array_equal(s[..., 0], s[..., c])
+    pz, pd, ps = vv.make_illum_tables(spec_exp)
+    assert np.array_equal(pz, oz) and np.array_equal(pd, od) and np.array_equal(ps, os_)

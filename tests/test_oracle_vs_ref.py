@@ -50,6 +50,23 @@ def test_raycast_bit_exact(oracle, name):
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "max abs diff %g" % np.abs(a - b).max()
 
 
+@pytest.mark.parametrize("define", ["ILLUM_MALLO", "ILLUM_ZOECKLER"])
+def test_illuminated_streamlines_bit_exact(oracle, define):
+    """Mallo / Zoeckler builds (keys 8 / 7, VV/3DLIC.cpp:416-427) with the tables of VV/illumination.cpp"""
+    import vectorvisualization_b200 as vv
+    from vectorvisualization_b200 import configs, fields as F
+    tables = oracle.illum_tables(40.0)
+    for mk in (lambda: configs.cfg2(n=20, size=36, camera=F.CAMERA_CLOSE), lambda: configs.cfg1(n=16, size=32)):
+        s = mk()
+        s.defines = "#define " + define
+        s.params.update(gradientScale=4.0, illumScale=1.3)
+        s.light = dict(quat=F.quat_from_axis_angle((0.2, 1, 0), 70.0), dist=1.0)
+        a, ca, ta = oracle.OracleScene(s, illum_tables=tables).raycast()
+        b, cb, tb = refshim.RefScene(s, illum_tables=tables).raycast()
+        assert ta == tb and ta > 0 and np.array_equal(ca, cb)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "max abs diff %g" % np.abs(a - b).max()
+
+
 @pytest.mark.parametrize("name", ["cfg2_close_gs6", "cfg3_gradient_length", "anisotropic_tf_scalar_band", "q1_anisotropic_gradient"])
 def test_lic_volume_and_volume_raycast_bit_exact(oracle, name):
     s = _scenes()[name]()

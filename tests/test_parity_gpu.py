@@ -160,6 +160,22 @@ def test_raycast_parity(vv, oracle, name):
     print("%s: samples %d, max8 %d, psnr %.1f dB, float max diff %.3g" % (name, tot, md, ps, mf))
 
 
+@pytest.mark.parametrize("define", ["ILLUM_MALLO", "ILLUM_ZOECKLER"])
+def test_illuminated_streamlines_parity(vv, oracle, define):
+    """Mallo / Zoeckler illuminated-streamline builds"""
+    from vectorvisualization_b200 import configs, fields as F
+    tables = oracle.illum_tables(40.0)
+    for mk in (lambda: configs.cfg2(n=48, size=112, camera=F.CAMERA_CLOSE), lambda: configs.cfg1(n=32, size=80)):
+        s = mk()
+        s.defines = "#define " + define
+        s.params.update(gradientScale=4.0, illumScale=1.3)
+        s.light = dict(quat=F.quat_from_axis_angle((0.2, 1, 0), 70.0), dist=1.0)
+        ref, ref_cnt, ref_tot = oracle.OracleScene(s, illum_tables=tables).raycast()
+        _, img, _, cnt, tot = render_cuda(vv, s)
+        assert int((cnt != ref_cnt).sum()) <= 1
+        assert_image_parity(oracle, img, ref, define)
+
+
 def test_layouts_bit_identical(vv):
     """float4 and x-pair fp16 layouts hold the same RGBA16F values -> identical frames"""
     from vectorvisualization_b200 import configs

@@ -90,6 +90,7 @@ def load_library():
         "vv_read_field_texture": ([P, P, ctypes.c_size_t], I),
         "vv_read_noise_texture": ([P, P, ctypes.c_size_t, ctypes.POINTER(I)], I),
         "vv_read_sample_map": ([P, P, ctypes.c_size_t], I),
+        "vv_make_illum_tables": ([F, I, I, P, P, P], I),
         "vv_save_png": ([P, CP, I], I), "vv_save_raw": ([P, CP], I),
         "vv_last_ray_samples": ([P], U64), "vv_last_kernel_ms": ([P], F), "vv_last_launch_count": ([P], I),
         "vv_synchronize": ([P], I), "vv_set_partition": ([P, I, I], I), "vv_set_licvol_slab": ([P, I, I], I),
@@ -137,6 +138,16 @@ def parse_dat(path):
     info = DatInfo()
     _chk(lib.vv_parse_dat(path.encode(), ctypes.byref(info)))
     return info
+
+
+def make_illum_tables(spec_exp=40.0, width=256, height=256):
+    """Zoeckler (LA) and Mallo (diffuse, specular) tables as the library builds them (VV/illumination.cpp:96-390)"""
+    lib = load_library()
+    z = np.zeros((height, width, 2), np.float32)
+    d = np.zeros((height, width), np.float32)
+    s = np.zeros((height, width), np.float32)
+    _chk(lib.vv_make_illum_tables(spec_exp, width, height, _ptr(z), _ptr(d), _ptr(s)))
+    return z, d, s
 
 
 def png_read(path):
