@@ -34,6 +34,7 @@ LIB = os.path.join(OUT, "libvv_ref.so")
 RAYCAST = ["inc_header.glsl", "inc_lic.glsl", "inc_illum.glsl", "lic3d_fragment.glsl"]
 LICVOL = ["inc_header.glsl", "inc_lic.glsl", "lic3d_volume_fragment.glsl"]
 VOLRAY = ["inc_header.glsl", "inc_illum.glsl", "raycast_lic3d_fragment.glsl"]
+SLICING = ["inc_header.glsl", "inc_lic.glsl", "inc_illum.glsl", "lic3d_slicing_fragment.glsl"]
 PROGRAMS = {
     "raycast_none": (RAYCAST, [], []),
     "raycast_gradient": (RAYCAST, ["ILLUM_GRADIENT"], []),
@@ -44,6 +45,10 @@ PROGRAMS = {
     "licvol_gradient": (LICVOL, ["ILLUM_GRADIENT"], []),
     "licvol_sof": (LICVOL, ["SPEED_OF_FLOW"], []),
     "volraycast": (VOLRAY, [], ["REF_HAS_LICVOL"]),
+    "slicing_none": (SLICING, [], ["REF_SLICING"]),
+    "slicing_gradient": (SLICING, ["ILLUM_GRADIENT"], ["REF_SLICING"]),
+    "slicing_mallo": (SLICING, ["ILLUM_MALLO"], ["REF_SLICING"]),
+    "slicing_zoeckler": (SLICING, ["ILLUM_ZOECKLER"], ["REF_SLICING"]),
 }
 # Source-edit variants: the reference switches the TF index and the LIC gate by (un)commenting lines of
 # lic3d_fragment.glsl:53-61.  Each variant swaps the live expression for one of the alternatives the file itself lists.
@@ -92,6 +97,9 @@ def generate():
         text += ["namespace glsl { namespace %s {" % name, rewrite(body), '#include "ref_frag_driver.inc"', "} }",
                  'extern "C" void vvref_run_%s(const RefUniforms *u, const float *tc, int n, float *out, uint32_t *cnt)' % name,
                  "{ glsl::%s::run(*u, tc, n, out, cnt); }" % name]
+        if "REF_SLICING" in cxxdefs:
+            text += ['extern "C" void vvref_slice_%s(const RefUniforms *u, const float *fr, const int *st, int np, float *out, uint32_t *cnt)' % name,
+                     "{ glsl::%s::run_slicing(*u, fr, st, np, out, cnt); }" % name]
         path = os.path.join(GEN, "prog_%s.cpp" % name)
         with open(path, "w") as f:
             f.write("\n".join(text) + "\n")

@@ -175,7 +175,7 @@ inline float abs(float a) { return std::fabs(a); }
 
 // ---- textures ------------------------------------------------------------------------------------------------
 enum Wrap { W_CLAMP_TO_EDGE = 0, W_REPEAT = 1, W_CLAMP = 2 /* border colour (0,0,0,0) */ };
-enum Fmt { F_L8 = 0, F_LA8 = 1, F_RGBA8 = 2, F_RGBA32F = 3, F_L32F = 4, F_LA32F = 5 };
+enum Fmt { F_L8 = 0, F_LA8 = 1, F_RGBA8 = 2, F_RGBA32F = 3, F_L32F = 4, F_LA32F = 5, F_FBO = 6 /* the frame buffer under the fragment */ };
 
 struct Texture {
     const void *data = nullptr;
@@ -190,6 +190,7 @@ typedef const Texture *sampler3D;
 typedef const Texture *sampler2DRect;
 
 extern thread_local uint32_t g_fetch_count[16];
+extern thread_local float g_fbo_dest[4];   /* imageFBOSampler content at gl_FragCoord (slicing ping-pong target) */
 
 struct AxisL { int i0, i1; float f; bool b0, b1; };
 
@@ -256,6 +257,7 @@ inline vec4 texture3D(sampler3D t, const vec3 &p) { return sample_linear(t, p.d[
 /* rectangle textures use unnormalised coordinates; only reached by the slicing / background / MC-offset paths */
 inline vec4 texture2DRect(sampler2DRect t, const vec2 &p)
 {
+    if (t->fmt == F_FBO) return vec4(g_fbo_dest[0], g_fbo_dest[1], g_fbo_dest[2], g_fbo_dest[3]);
     int x = (int)std::floor(p.d[0]), y = (int)std::floor(p.d[1]);
     x = x < 0 ? 0 : (x > t->dim[0] - 1 ? t->dim[0] - 1 : x);
     y = y < 0 ? 0 : (y > t->dim[1] - 1 ? t->dim[1] - 1 : y);

@@ -4,6 +4,7 @@
 
 namespace glsl {
 thread_local uint32_t g_fetch_count[16];
+thread_local float g_fbo_dest[4];
 thread_local vec4 gl_TexCoord[8];
 thread_local vec4 gl_FragColor;
 thread_local vec4 gl_FragCoord;

@@ -177,6 +177,37 @@ class RefScene:
         cm[y0:y1, x0:x1] = cnt.reshape(y1 - y0, x1 - x0)
         return img, cm, int(cnt.sum())
 
+    def slicing(self):
+        """lic3d_slicing_fragment.glsl over the oracle's slice geometry; the shader hard-codes TF index .a and the
+        tfData.a > 0.05 gate, so the scene must use tf_mode A / gate TF_ALPHA"""
+        s = self.s
+        assert s.tf_mode == 1 and s.gate_mode == 1
+        d = s.defines or ""
+        prog = "slicing_none"
+        for k, v in (("ILLUM_GRADIENT", "gradient"), ("ILLUM_MALLO", "mallo"), ("ILLUM_ZOECKLER", "zoeckler")):
+            if k in d:
+                prog = "slicing_" + v
+        self._set_scale(raycast=True)
+        L = lib()
+        _, _, nslices = self.o.slicing_setup()
+        frags, starts = [], [0]
+        buf = np.zeros((nslices, 4), np.float32)
+        for y in range(s.height):
+            for x in range(s.width):
+                n = vvo.lib().vvo_slice_fragments(ctypes.byref(self.o.c), x, y, vvo._p(buf), nslices)
+                frags.append(buf[:n].copy())
+                starts.append(starts[-1] + n)
+        fr = np.ascontiguousarray(np.concatenate(frags, axis=0) if frags else np.zeros((0, 4), np.float32))
+        st = np.asarray(starts, np.int32)
+        npix = s.width * s.height
+        out = np.zeros((npix, 4), np.float32)
+        cnt = np.zeros(npix, np.uint32)
+        fn = getattr(L, "vvref_slice_" + prog)
+        fn.argtypes = [ctypes.POINTER(RefUniforms), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.vvref_set_gl_state(ctypes.byref(self.u))
+        fn(ctypes.byref(self.u), vvo._p(fr), vvo._p(st), npix, vvo._p(out), vvo._p(cnt))
+        return out.reshape(s.height, s.width, 4), cnt.reshape(s.height, s.width), int(cnt.sum())
+
     def lic_volume(self, dims=None):
         nz, ny, nx = self.s.field.shape[:3]
         w, h, d = dims or (nx, ny, nz)

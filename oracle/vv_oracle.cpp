@@ -375,6 +375,78 @@ bool pixel_ray(const Ctx &c, int px, int py, V3 &entry)
     return true;
 }
 
+/* ---- view-aligned slicing geometry: ViewSlicing::setupSlicing / drawSlice, slicing.cpp:42-114 ------------- */
+struct Slicing {
+    float v[3];       /* unit view vector in object space (slicing.cpp:71-81) */
+    float d;          /* depth range covered by the slices, 2 * max projection (slicing.cpp:87-99) */
+    int numSlices;    /* (int)(d / sampDist) + 1 (slicing.cpp:101) */
+};
+
+/* Renderer::updateSlices (renderer.cpp:1270-1292): model-view of the frame, sampDist = stepSizeVol (x2 in low-res) */
+Slicing setup_slicing(const Ctx &c)
+{
+    const VVOScene *s = c.s;
+    Slicing sl;
+    /* m[2], m[6], m[10] = third row of R; m[3] = m[7] = m[11] = 0; m[14] = z translation; m[15] = 1 */
+    double tz = ((double)s->cam_pos[2] - (double)s->cam_dist) -
+                ((double)c.rot[6] * s->center[0] + (double)c.rot[7] * s->center[1] + (double)c.rot[8] * s->center[2]);
+    float m14 = (float)tz;
+    float invNorm = 1.0f / (m14 - 1.0f);
+    sl.v[0] = (c.rot[6] - 0.0f) * invNorm;
+    sl.v[1] = (c.rot[7] - 0.0f) * invNorm;
+    sl.v[2] = (c.rot[8] - 0.0f) * invNorm;
+    invNorm = 1.0f / std::sqrt(sl.v[0] * sl.v[0] + sl.v[1] * sl.v[1] + sl.v[2] * sl.v[2]);
+    sl.v[0] *= invNorm; sl.v[1] *= invNorm; sl.v[2] *= invNorm;
+    float xMax = 0.5f * s->extent[0], yMax = 0.5f * s->extent[1], zMax = 0.5f * s->extent[2];
+    float v[3] = {std::fabs(sl.v[0]), std::fabs(sl.v[1]), std::fabs(sl.v[2])};
+    float dv[7] = {v[0] * xMax, v[1] * yMax, v[2] * zMax, v[0] * xMax + v[1] * yMax, v[0] * xMax + v[2] * zMax,
+                   v[1] * yMax + v[2] * zMax, v[0] * xMax + v[1] * yMax + v[2] * zMax};
+    sl.d = dv[6];
+    for (int i = 0; i < 6; ++i)
+        if (sl.d < dv[i]) sl.d = dv[i];
+    sl.d *= 2.0;
+    sl.numSlices = (int)(sl.d / c.stepSize) + 1;
+    return sl;
+}
+
+/* plane offset of slice i from the volume centre along v (slicing.cpp:114) */
+inline float slice_offset(const Slicing &sl, int slice) { return -0.5f * sl.d + (slice + 0.5f) * sl.d / sl.numSlices; }
+
+struct PixelRay { double o[3], d[3]; };
+
+inline PixelRay pixel_dir(const Ctx &c, int px, int py)
+{
+    const VVOScene *s = c.s;
+    PixelRay r;
+    double ex = (2.0 * (px + 0.5) / s->width - 1.0) * (double)c.tanHalf * (double)c.aspect;
+    double ey = (2.0 * (py + 0.5) / s->height - 1.0) * (double)c.tanHalf;
+    double ez = -1.0;
+    for (int i = 0; i < 3; ++i)
+        r.d[i] = (double)c.rot[0 * 3 + i] * ex + (double)c.rot[1 * 3 + i] * ey + (double)c.rot[2 * 3 + i] * ez;
+    r.o[0] = c.camera.x; r.o[1] = c.camera.y; r.o[2] = c.camera.z;
+    return r;
+}
+
+/* The fragment of slice i under a pixel: intersection of the pixel ray with the plane v.(p - center) = d_i, if it lies
+ * in the box [0,extent]^3 (the slice polygon is that plane clipped to the box; texcoord0 = vertex, slicing.cpp:246-261). */
+inline bool slice_fragment(const Ctx &c, const Slicing &sl, const PixelRay &r, int slice, V3 &geomPos)
+{
+    const VVOScene *s = c.s;
+    double a = (r.o[0] - (double)s->center[0]) * (double)sl.v[0] + (r.o[1] - (double)s->center[1]) * (double)sl.v[1] +
+               (r.o[2] - (double)s->center[2]) * (double)sl.v[2];
+    double b = r.d[0] * (double)sl.v[0] + r.d[1] * (double)sl.v[1] + r.d[2] * (double)sl.v[2];
+    if (b == 0.0) return false;
+    double t = ((double)slice_offset(sl, slice) - a) / b;
+    if (!(t > 0.0)) return false;
+    double p[3];
+    for (int i = 0; i < 3; ++i) {
+        p[i] = r.o[i] + t * r.d[i];
+        if (p[i] < 0.0 || p[i] > (double)s->extent[i]) return false;
+    }
+    geomPos = {(float)p[0], (float)p[1], (float)p[2]};
+    return true;
+}
+
 /* ---- inc_lic.glsl -------------------------------------------------------- */
 
 /* freqSamplingGrad, inc_lic.glsl:61-68: raw RGBA noise texel at pos (no frequency scale, no gate; Q8) */
@@ -629,6 +701,41 @@ V4 frag_raycast_licvolume(const Ctx &c, V3 geomPos, uint32_t &nsamples)
     return dest;
 }
 
+/* main() of lic3d_slicing_fragment.glsl:5-74 for one fragment; dest = the frame buffer under the fragment
+ * (imageFBOSampler, :11).  The shader hard-codes TF index .a and gate tfData.a > 0.05; tf_mode / gate_mode select them here. */
+template <bool GRAD>
+V4 frag_slicing(const Ctx &c, V3 geomPos, V4 dest, bool &shaded)
+{
+    V4 src = {0, 0, 0, 0};
+    shaded = false;
+    if (dest.w < 0.95f) {                                                  /* :14 */
+        shaded = true;
+        V3 pos = geomPos * c.scaleVol;                                     /* :18 */
+        V3 geomDir = normalize(geomPos - c.camera);                        /* :24 */
+        V3 dir = geomDir * c.scaleVol;                                     /* :25 */
+        V4 vectorData = texVolume(c, pos);                                 /* :36 */
+        V4 scalarData = {0, 0, 0, 1};
+        if (c.s->tf_mode == VVO_TF_SCALAR) scalarData = texScalar(c, pos);
+        V4 tfData = texTF(c, tf_index(c, vectorData, scalarData));         /* :43 */
+        bool gate = (c.s->gate_mode == VVO_GATE_TF_ALPHA) ? (tfData.w > 0.05f) : true;   /* :46 */
+        if (gate) {
+            V4 illum = computeLIC<GRAD>(c, pos, vectorData);               /* :49 */
+            illum.w *= c.licKernel[2] * c.gradient[0];                     /* :52 */
+            switch (c.s->illum_mode) {                                     /* :56-65 */
+            case VVO_ILLUM_GRADIENT: src = illumGradient(c, illum, tfData, pos, dir); break;
+            case VVO_ILLUM_MALLO: src = illumMallo(c, illum.w, tfData, pos, dir, rgb(vectorData)); break;
+            case VVO_ILLUM_ZOECKLER: src = illumZoeckler(c, illum.w, tfData, pos, dir, rgb(vectorData)); break;
+            default: src = illumLIC(c, illum.w, tfData); break;
+            }
+            src.x *= src.w; src.y *= src.w; src.z *= src.w;                /* :68 */
+            float k = 1.0f - dest.w;
+            dest = {clampf(k * src.x + dest.x, 0.0f, 1.0f), clampf(k * src.y + dest.y, 0.0f, 1.0f),
+                    clampf(k * src.z + dest.z, 0.0f, 1.0f), clampf(k * src.w + dest.w, 0.0f, 1.0f)};   /* :69 */
+        }
+    }
+    return dest;
+}
+
 template <class F>
 uint64_t for_pixels(const VVOScene *s, int x0, int y0, int x1, int y1, float *out_rgba, uint32_t *out_samples, F frag, bool raycast_program = true)
 {
@@ -674,6 +781,63 @@ uint64_t vvo_raycast_licvolume(const VVOScene *s, float *out_rgba, uint32_t *out
 {
     return for_pixels(s, 0, 0, s->width, s->height, out_rgba, out_samples,
                       [](const Ctx &c, V3 e, uint32_t &n) { return frag_raycast_licvolume(c, e, n); }, false);
+}
+
+/* Renderer::sliceVolume (renderer.cpp:1123-1267): numSlices view-aligned polygons drawn front to back, each fragment
+ * runs lic3d_slicing_fragment.glsl on the frame buffer content left by the previous slices (FBO ping-pong variant).
+ * out_samples counts the fragments that did any work (dest.a < 0.95). */
+uint64_t vvo_slicing_lic(const VVOScene *s, float *out_rgba, uint32_t *out_samples)
+{
+    Ctx c;
+    make_ctx(s, c);
+    const Slicing sl = setup_slicing(c);
+    const bool grad = (s->illum_mode == VVO_ILLUM_GRADIENT);
+    uint64_t total = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
+    for (int y = 0; y < s->height; ++y)
+        for (int x = 0; x < s->width; ++x) {
+            PixelRay r = pixel_dir(c, x, y);
+            V4 dest = {0, 0, 0, 0};
+            uint32_t n = 0;
+            for (int i = 0; i < sl.numSlices; ++i) {
+                V3 g;
+                if (!slice_fragment(c, sl, r, i, g)) continue;
+                bool shaded;
+                dest = grad ? frag_slicing<true>(c, g, dest, shaded) : frag_slicing<false>(c, g, dest, shaded);
+                if (shaded) ++n;
+            }
+            float *o = out_rgba + 4 * ((size_t)y * s->width + x);
+            o[0] = dest.x; o[1] = dest.y; o[2] = dest.z; o[3] = dest.w;
+            if (out_samples) out_samples[(size_t)y * s->width + x] = n;
+            total += n;
+        }
+    return total;
+}
+
+/* slicing set-up read-back for tests: out[5] = v.xyz, d, numSlices */
+void vvo_slicing_setup(const VVOScene *s, float *out)
+{
+    Ctx c;
+    make_ctx(s, c);
+    Slicing sl = setup_slicing(c);
+    out[0] = sl.v[0]; out[1] = sl.v[1]; out[2] = sl.v[2]; out[3] = sl.d; out[4] = (float)sl.numSlices;
+}
+
+/* fragments of one pixel column for the reference-shader driver: out[numSlices][4] = (geomPos.xyz, valid) */
+int vvo_slice_fragments(const VVOScene *s, int x, int y, float *out, int cap)
+{
+    Ctx c;
+    make_ctx(s, c);
+    Slicing sl = setup_slicing(c);
+    PixelRay r = pixel_dir(c, x, y);
+    int n = 0;
+    for (int i = 0; i < sl.numSlices && n < cap; ++i) {
+        V3 g;
+        if (!slice_fragment(c, sl, r, i, g)) continue;
+        out[4 * n] = g.x; out[4 * n + 1] = g.y; out[4 * n + 2] = g.z; out[4 * n + 3] = 1.0f;
+        ++n;
+    }
+    return n;
 }
 
 /* lic3d_volume_fragment.glsl:2-21, one fragment per voxel centre of a w x h x d target

@@ -83,6 +83,10 @@ uint64_t vvo_raycast_lic_rect(const VVOScene *s, int x0, int y0, int x1, int y1,
 void vvo_lic_volume(const VVOScene *s, int w, int h, int d, int z0, int z1, float *out);
 /* raycast_lic3d_fragment.glsl:5-73 */
 uint64_t vvo_raycast_licvolume(const VVOScene *s, float *out_rgba, uint32_t *out_samples);
+/* lic3d_slicing_fragment.glsl:5-74 over the view-aligned slices of slicing.cpp:42-114 / renderer.cpp:1123-1267 */
+uint64_t vvo_slicing_lic(const VVOScene *s, float *out_rgba, uint32_t *out_samples);
+void vvo_slicing_setup(const VVOScene *s, float *out5);
+int vvo_slice_fragments(const VVOScene *s, int x, int y, float *out_xyzv, int cap);
 /* one computeLIC (inc_lic.glsl:152-202) at pos; out[4] */
 void vvo_compute_lic(const VVOScene *s, const float pos[3], float out[4]);
 /* background_fragment.glsl:7-20 and the RGBA8 store (renderer.cpp:216-226) */

@@ -58,6 +58,9 @@ def lib():
         L.vvo_lic_volume.argtypes = [S, I, I, I, I, I, P]; L.vvo_lic_volume.restype = None
         L.vvo_raycast_licvolume.argtypes = [S, P, P]; L.vvo_raycast_licvolume.restype = U64
         L.vvo_compute_lic.argtypes = [S, P, P]; L.vvo_compute_lic.restype = None
+        L.vvo_slicing_lic.argtypes = [S, P, P]; L.vvo_slicing_lic.restype = U64
+        L.vvo_slicing_setup.argtypes = [S, P]
+        L.vvo_slice_fragments.argtypes = [S, I, I, P, I]; L.vvo_slice_fragments.restype = I
         L.vvo_background.argtypes = [P, I, P]; L.vvo_quantize_rgba8.argtypes = [P, I, P]
         for n in ("vvo_sample_vec", "vvo_sample_noise", "vvo_sample_scalar"):
             getattr(L, n).argtypes = [S, P, P]
@@ -230,6 +233,19 @@ class OracleScene:
         else:
             tot = lib().vvo_raycast_lic_rect(ctypes.byref(self.c), rect[0], rect[1], rect[2], rect[3], _p(out), _p(cnt))
         return out, cnt, int(tot)
+
+    def slicing(self):
+        """returns (rgba float [h][w][4], shaded fragments per pixel, total)"""
+        s = self.s
+        out = np.zeros((s.height, s.width, 4), dtype=np.float32)
+        cnt = np.zeros((s.height, s.width), dtype=np.uint32)
+        tot = lib().vvo_slicing_lic(ctypes.byref(self.c), _p(out), _p(cnt))
+        return out, cnt, int(tot)
+
+    def slicing_setup(self):
+        o = np.zeros(5, np.float32)
+        lib().vvo_slicing_setup(ctypes.byref(self.c), _p(o))
+        return o[:3].copy(), float(o[3]), int(o[4])
 
     def lic_volume(self, dims=None, z0=0, z1=None):
         nz, ny, nx = self.s.field.shape[:3]

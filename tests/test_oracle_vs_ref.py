@@ -50,6 +50,26 @@ def test_raycast_bit_exact(oracle, name):
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "max abs diff %g" % np.abs(a - b).max()
 
 
+@pytest.mark.parametrize("define", ["", "ILLUM_GRADIENT", "ILLUM_MALLO"])
+def test_slicing_bit_exact(oracle, define):
+    """VOLIC_SLICING: lic3d_slicing_fragment.glsl run slice by slice on the frame buffer (VV/renderer.cpp:1123-1267)"""
+    import vectorvisualization_b200 as vv
+    from vectorvisualization_b200 import configs, fields as F
+    tables = oracle.illum_tables(40.0)
+    for mk in (lambda: configs.cfg3(n=20, size=32, camera=F.CAMERA_CLOSE), lambda: configs.cfg2(n=20, size=36)):
+        s = mk()
+        s.defines = ("#define " + define) if define else ""
+        s.with_gradients = True
+        s.technique = vv.VOLIC_SLICING
+        s.tf_mode, s.gate_mode = vv.TF_A, vv.GATE_TF_ALPHA         # what the slicing shader hard-codes
+        s.tf = F.default_tf()
+        s.params.update(gradientScale=4.0)
+        a, ca, ta = oracle.OracleScene(s, illum_tables=tables).slicing()
+        b, cb, tb = refshim.RefScene(s, illum_tables=tables).slicing()
+        assert ta == tb and ta > 0 and np.array_equal(ca, cb)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "max abs diff %g" % np.abs(a - b).max()
+
+
 @pytest.mark.parametrize("define", ["ILLUM_MALLO", "ILLUM_ZOECKLER"])
 def test_illuminated_streamlines_bit_exact(oracle, define):
     """Mallo / Zoeckler builds (keys 8 / 7, VV/3DLIC.cpp:416-427) with the tables of VV/illumination.cpp"""

@@ -176,6 +176,44 @@ def test_illuminated_streamlines_parity(vv, oracle, define):
         assert_image_parity(oracle, img, ref, define)
 
 
+@pytest.mark.parametrize("define", ["", "ILLUM_GRADIENT"])
+def test_slicing_parity(vv, oracle, define):
+    """VOLIC_SLICING (F3): view-aligned slices, TF index .a, gate tfData.a > 0.05, stop on dest.a >= 0.95"""
+    from vectorvisualization_b200 import configs, fields as F
+    for mk in (lambda: configs.cfg3(n=48, size=112, camera=F.CAMERA_CLOSE), lambda: configs.cfg2(n=40, size=96),
+               lambda: configs.cfg1(n=32, size=75, camera=dict(quat=F.quat_from_axis_angle((0.3, -1.0, 0.2), 110.0), pos=(0.1, 0, 0.2), dist=3.0, fovy=35.0))):
+        s = mk()
+        s.defines = ("#define " + define) if define else ""
+        s.with_gradients = True
+        s.technique = vv.VOLIC_SLICING
+        s.tf_mode, s.gate_mode = vv.TF_A, vv.GATE_TF_ALPHA
+        s.tf = F.default_tf()
+        s.params.update(gradientScale=4.0)
+        ref, ref_cnt, ref_tot = oracle.OracleScene(s).slicing()
+        _, img, _, cnt, tot = render_cuda(vv, s)
+        assert ref_tot > 0
+        assert int((cnt != ref_cnt).sum()) <= max(1, cnt.size // 20000), "%d pixels differ in fragment count" % int((cnt != ref_cnt).sum())
+        assert_image_parity(oracle, img, ref, "slicing " + define)
+
+
+def test_slicing_default_modes(vv):
+    """selecting VOLIC_SLICING switches to the slicing program's own TF index / gate (Q5, Q6) without touching the ray-cast ones"""
+    from vectorvisualization_b200 import configs
+    from vectorvisualization_b200.configs import apply_scene
+    s = configs.cfg2(n=24, size=48)
+    s.params.update(gradientScale=4.0)
+    r = vv.Renderer(0)
+    apply_scene(r, s)                      # sets ray-cast options (B, always)
+    r.render(True)
+    a = r.readRGBA32F().copy()
+    r.setTechnique(vv.VOLIC_SLICING)       # slicing defaults: TF .a, gate tf.a > 0.05
+    r.render(True)
+    b = r.readRGBA32F().copy()
+    r.setTechnique(vv.VOLIC_RAYCAST)
+    r.render(True)
+    assert np.array_equal(r.readRGBA32F(), a) and not np.array_equal(a, b) and b.any()
+
+
 def test_layouts_bit_identical(vv):
     """float4 and x-pair fp16 layouts hold the same RGBA16F values -> identical frames"""
     from vectorvisualization_b200 import configs

@@ -90,6 +90,7 @@ def apply_scene(r: Renderer, s: Scene):
         r.setScalar(s.scalar)
     r.setLICFilter(s.filter_row)
     r.setTF(s.tf)
+    r.setTechnique(s.technique)          # TF-index / gate options are kept per shader program (ray-cast vs slicing)
     r.setOption(OPT_TF_MODE, s.tf_mode)
     r.setOption(OPT_GATE_MODE, s.gate_mode)
     r.setOption(OPT_NOISE_GATE, s.noise_gate)

@@ -69,6 +69,11 @@ struct DevParams {
     uint2  *items, *itemsNext;       // work items (tile, k) of the current / next depth window
     unsigned int *itemCount, *itemCountNext, *itemHead, *slotAlloc, *nMaxGlobal;
     int win0, win1, win2;            // current window [win0, win1), next window ends at win2
+    // ---- view-aligned slicing (VV/slicing.cpp:42-114): unit view vector, covered depth, slice count ----
+    int slicing;
+    float slV[3], slD;
+    int slNum;
+    double slCenter[3];
     // ---- LIC volume target ----
     float *licvol_out;
     int ow, oh, od, oz0, oz1, licvolFp16;

@@ -473,6 +473,84 @@ __global__ void __launch_bounds__(256) ray_setup_kernel(const __grid_constant__ 
     }
 }
 
+// ---- view-aligned slicing (VOLIC_SLICING): VV/slicing.cpp:42-114, VV/renderer.cpp:1123-1267 ---------------------
+// The slice polygons are planes v.(p - center) = d_i clipped to the box; under a pixel the fragment of slice i is the
+// intersection of the pixel ray with that plane.  Same double arithmetic, same order as the oracle.
+struct PixelDir { double o[3], d[3]; };
+
+__device__ __forceinline__ PixelDir pixel_dir(const DevParams &P, int px, int py)
+{
+    PixelDir r;
+    const double ex = __dmul_rn(__dmul_rn(__dsub_rn(__ddiv_rn(__dmul_rn(2.0, (double)px + 0.5), (double)P.width), 1.0), P.tanHalf), P.aspect);
+    const double ey = __dmul_rn(__dsub_rn(__ddiv_rn(__dmul_rn(2.0, (double)py + 0.5), (double)P.height), 1.0), P.tanHalf);
+    const double ez = -1.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        r.d[i] = __dadd_rn(__dadd_rn(__dmul_rn(P.rot[i], ex), __dmul_rn(P.rot[3 + i], ey)), __dmul_rn(P.rot[6 + i], ez));
+        r.o[i] = P.camD[i];
+    }
+    return r;
+}
+
+// plane offset of slice i: -0.5 d + (i + 0.5) d / numSlices in float (VV/slicing.cpp:114)
+__device__ __forceinline__ float slice_offset(const DevParams &P, int slice)
+{
+    return __fadd_rn(__fmul_rn(-0.5f, P.slD), __fdiv_rn(__fmul_rn(__fadd_rn((float)slice, 0.5f), P.slD), (float)P.slNum));
+}
+
+__device__ __forceinline__ bool slice_fragment(const DevParams &P, const PixelDir &r, int slice, float g[3])
+{
+    const double v0 = (double)P.slV[0], v1 = (double)P.slV[1], v2 = (double)P.slV[2];
+    const double a = __dadd_rn(__dadd_rn(__dmul_rn(__dsub_rn(r.o[0], P.slCenter[0]), v0), __dmul_rn(__dsub_rn(r.o[1], P.slCenter[1]), v1)),
+                               __dmul_rn(__dsub_rn(r.o[2], P.slCenter[2]), v2));
+    const double b = __dadd_rn(__dadd_rn(__dmul_rn(r.d[0], v0), __dmul_rn(r.d[1], v1)), __dmul_rn(r.d[2], v2));
+    if (b == 0.0) return false;
+    const double t = __ddiv_rn(__dsub_rn((double)slice_offset(P, slice), a), b);
+    if (!(t > 0.0)) return false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double p = __dadd_rn(r.o[i], __dmul_rn(t, r.d[i]));
+        if (p < 0.0 || p > P.extent[i]) return false;
+        g[i] = (float)p;
+    }
+    return true;
+}
+
+// set-up for slicing: per pixel the first slice with a fragment and the span up to the last one
+__global__ void __launch_bounds__(256) slice_setup_kernel(const __grid_constant__ DevParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const int nTiles = P.nLocalBlocks * 8;
+    for (int lt = blockIdx.x * 8 + (threadIdx.x >> 5); lt < nTiles; lt += gridDim.x * 8) {
+        int px, py;
+        const int o = tile_pixel(P, lt, lane, px, py);
+        int first = -1, last = -1;
+        if (px < P.width && py < P.height) {
+            const PixelDir r = pixel_dir(P, px, py);
+            float g[3];
+            for (int i = 0; i < P.slNum; ++i)
+                if (slice_fragment(P, r, i, g)) { if (first < 0) first = i; last = i; }
+        }
+        // a tile's items address slices first_tile + k, so that the 32 lanes of an item shade the same slice
+        const int tfirst = __reduce_min_sync(0xffffffffu, first < 0 ? 0x7fffffff : first);
+        const int tlast = __reduce_max_sync(0xffffffffu, last);
+        const int nmax = (tlast >= 0) ? tlast - tfirst + 1 : 0;
+        const int n = (last >= 0) ? last - tfirst + 1 : 0;       // per ray: samples up to its last fragment
+        unsigned int base = 0;
+        if (lane == 0 && nmax > 0) base = atomicAdd(P.slotAlloc, (unsigned int)nmax);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const int ray = lt * 32 + lane;
+        P.rayA[ray] = make_float4(__int_as_float(tfirst), 0.f, 0.f, __int_as_float(n));
+        P.rayB[ray] = make_float4(0.f, 0.f, 0.f, __int_as_float(n > 0 ? 0 : -1));
+        if (lane == 0) {
+            P.tileRec[lt] = make_uint2(base, (unsigned int)nmax);
+            if (nmax > 0) atomicMax(P.nMaxGlobal, (unsigned int)nmax);
+        }
+        P.tiles[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (P.samplesPerPixel) P.samplesPerPixel[o] = 0;
+    }
+}
+
 template <int LAYOUT, int ILLUM, bool NGATE, bool SOF>
 __global__ void __launch_bounds__(256, LIC_MIN_CTAS) lic_sample_kernel(const __grid_constant__ DevParams P)
 {
@@ -495,14 +573,30 @@ __global__ void __launch_bounds__(256, LIC_MIN_CTAS) lic_sample_kernel(const __g
         if (k >= n) continue;
         const float4 B = P.rayB[ray];
         if (__float_as_int(B.w) < 0) continue;            // ray finished in an earlier window
-        const f3 dir = mk3(B.x, B.y, B.z);
-        const f3 dstep = mk3(__fmul_rn(dir.x, P.stepSize), __fmul_rn(dir.y, P.stepSize), __fmul_rn(dir.z, P.stepSize));
-        f3 pos = mk3(A.x, A.y, A.z);
-        for (int j = 0; j < k; ++j) {                      // pos += dir * stepSize, k times, as the shader accumulates it
-            pos.x = __fadd_rn(pos.x, dstep.x); pos.y = __fadd_rn(pos.y, dstep.y); pos.z = __fadd_rn(pos.z, dstep.z);
-        }
+        f3 dir, pos;
         float4 src;
-        if (!shade_sample<LAYOUT, ILLUM, NGATE, SOF>(P, S, pos, dir, src)) src = make_float4(0.f, 0.f, 0.f, -1.0f);   // gated
+        bool have = true;
+        if (P.slicing) {
+            // fragment of slice (first slice of the tile + k) under this pixel: lic3d_slicing_fragment.glsl:17-25
+            int px, py;
+            tile_pixel(P, (int)it.x, lane, px, py);
+            const PixelDir r = pixel_dir(P, px, py);
+            float g[3];
+            have = slice_fragment(P, r, __float_as_int(A.x) + k, g);
+            if (have) {
+                f3 dstep;
+                ray_setup(P, g, pos, dir, dstep);
+            }
+        } else {
+            dir = mk3(B.x, B.y, B.z);
+            const f3 dstep = mk3(__fmul_rn(dir.x, P.stepSize), __fmul_rn(dir.y, P.stepSize), __fmul_rn(dir.z, P.stepSize));
+            pos = mk3(A.x, A.y, A.z);
+            for (int j = 0; j < k; ++j) {                  // pos += dir * stepSize, k times, as the shader accumulates it
+                pos.x = __fadd_rn(pos.x, dstep.x); pos.y = __fadd_rn(pos.y, dstep.y); pos.z = __fadd_rn(pos.z, dstep.z);
+            }
+        }
+        if (!have) src = make_float4(0.f, 0.f, 0.f, -2.0f);                                                               // no fragment
+        else if (!shade_sample<LAYOUT, ILLUM, NGATE, SOF>(P, S, pos, dir, src)) src = make_float4(0.f, 0.f, 0.f, -1.0f);   // gated
         const uint2 tr = P.tileRec[it.x];
         P.src[((size_t)tr.x + k) * 32 + lane] = src;
     }
@@ -530,6 +624,14 @@ __global__ void __launch_bounds__(256) composite_kernel(const __grid_constant__ 
             bool done = false;
             for (int k = P.win0; k < kend; ++k) {
                 const float4 s = P.src[((size_t)tr.x + k) * 32 + lane];
+                if (P.slicing) {
+                    // lic3d_slicing_fragment.glsl:14: a fragment only works while the frame buffer has dest.a < 0.95
+                    if (s.w == -2.0f) continue;                       // no fragment of this slice under the pixel
+                    if (!(dest.w < 0.95f)) { done = true; break; }
+                    ++consumed;
+                    if (s.w >= 0.0f) composite(dest, s);
+                    continue;
+                }
                 ++consumed;
                 if (s.w >= 0.0f) {
                     composite(dest, s);
@@ -710,7 +812,8 @@ size_t shared_table_bytes() { return sizeof(SharedTables); }
 
 cudaError_t launch_ray_setup(const DevParams &P, int grid, cudaStream_t st)
 {
-    ray_setup_kernel<<<grid, 256, 0, st>>>(P);
+    if (P.slicing) slice_setup_kernel<<<grid, 256, 0, st>>>(P);
+    else ray_setup_kernel<<<grid, 256, 0, st>>>(P);
     return cudaGetLastError();
 }
 

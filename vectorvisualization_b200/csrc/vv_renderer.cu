@@ -100,7 +100,10 @@ struct VVRenderer {
     int technique = VV_VOLIC_RAYCAST;
     int illum_mode = ILLUM_NONE;
     bool speed_of_flow = false, lowres = false, float_target = false;
-    int tf_mode = TF_B, gate_mode = GATE_ALWAYS, noise_gate = 1, quirk_scalevolinv = 1, quirk_lum_alpha = 0;
+    // TF index / LIC gate are hard-coded per shader in the reference (Q5, Q6): [0] ray-cast program (.b, always),
+    // [1] slicing program (.a, tfData.a > 0.05); vv_set_option changes the entry of the current technique
+    int tf_modes[2] = {TF_B, TF_A}, gate_modes[2] = {GATE_ALWAYS, GATE_TF_ALPHA};
+    int noise_gate = 1, quirk_scalevolinv = 1, quirk_lum_alpha = 0;
     int licvol_fp16 = 1, count_samples = 1, licvol_size = 0, sample_map = 0;
     DevBuf<unsigned int> sample_tiles;
     float spec_exp = 40.0f;
@@ -321,7 +324,8 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycas
     if (!r->have_noise) return fail(VV_ERR_STATE, "no noise set (vv_set_noise / vv_load_noise / vv_generate_white_noise)");
     if (grad && !r->noise_has_grad) return fail(VV_ERR_STATE, "ILLUM_GRADIENT needs noise gradients (-g)");
     if (!grad && r->noise_gate && !r->have_scalar) return fail(VV_ERR_STATE, "no scalar volume set (vv_set_scalar); the noise gate needs it");
-    if (r->tf_mode == TF_SCALAR && !r->have_scalar) return fail(VV_ERR_STATE, "tf_mode scalar needs a scalar volume");
+    const int prog = (r->technique == VV_VOLIC_SLICING) ? 1 : 0;
+    if (r->tf_modes[prog] == TF_SCALAR && !r->have_scalar) return fail(VV_ERR_STATE, "tf_mode scalar needs a scalar volume");
     if (need_frame && (r->width <= 0 || r->height <= 0)) return fail(VV_ERR_STATE, "vv_resize not called");
 
     const Uniforms u = derive_uniforms(r);
@@ -369,7 +373,31 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycas
     P.tanHalf = (double)(float)std::tan((double)r->fovy * M_PI / 360.0);
     P.aspect = (r->height > 0) ? (double)((float)r->width / (float)r->height) : 1.0;
     P.width = r->width; P.height = r->height;
-    P.tfMode = r->tf_mode; P.gateMode = r->gate_mode; P.quirkLumAlpha = (r->quirk_lum_alpha && !r->noise_has_grad) ? 1 : 0;   // Q7 only bites GL_LUMINANCE noise
+    P.slicing = 0;
+    if (r->technique == VV_VOLIC_SLICING && need_frame) {
+        // ViewSlicing::setupSlicing (VV/slicing.cpp:42-103) on the model-view of Renderer::updateSlices
+        // (VV/renderer.cpp:1270-1292): m[2],m[6],m[10] = third row of R, m[14] = z translation, m[15] = 1
+        const double tz = ((double)r->cam_pos[2] - (double)r->cam_dist) -
+                          ((double)R[6] * r->center[0] + (double)R[7] * r->center[1] + (double)R[8] * r->center[2]);
+        const float m14 = (float)tz;
+        float inv = 1.0f / (m14 - 1.0f);
+        float v[3] = {(R[6] - 0.0f) * inv, (R[7] - 0.0f) * inv, (R[8] - 0.0f) * inv};
+        inv = 1.0f / std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        v[0] *= inv; v[1] *= inv; v[2] *= inv;
+        const float xMax = 0.5f * r->extent[0], yMax = 0.5f * r->extent[1], zMax = 0.5f * r->extent[2];
+        const float av[3] = {std::fabs(v[0]), std::fabs(v[1]), std::fabs(v[2])};
+        const float dv[7] = {av[0] * xMax, av[1] * yMax, av[2] * zMax, av[0] * xMax + av[1] * yMax, av[0] * xMax + av[2] * zMax,
+                             av[1] * yMax + av[2] * zMax, av[0] * xMax + av[1] * yMax + av[2] * zMax};
+        float d = dv[6];
+        for (int i = 0; i < 6; ++i) if (d < dv[i]) d = dv[i];
+        d *= 2.0;
+        P.slicing = 1;
+        P.slV[0] = v[0]; P.slV[1] = v[1]; P.slV[2] = v[2];
+        P.slD = d;
+        P.slNum = (int)(d / u.stepSize) + 1;
+        for (int i = 0; i < 3; ++i) P.slCenter[i] = (double)r->center[i];
+    }
+    P.tfMode = r->tf_modes[prog]; P.gateMode = r->gate_modes[prog]; P.quirkLumAlpha = (r->quirk_lum_alpha && !r->noise_has_grad) ? 1 : 0;   // Q7 only bites GL_LUMINANCE noise
     P.rank = r->rank; P.world = r->world; P.nBlocksX = r->nbx; P.nBlocksY = r->nby; P.nLocalBlocks = r->n_local_blocks;
     P.tiles = r->tiles.p;
     P.sampleCounter = r->count_samples ? r->counters.p : nullptr;
@@ -533,7 +561,8 @@ static int render_sample_parallel(VVRenderer *r, DevParams &P)
     // depth windows: whole ray at once when no sample can trigger the early termination, else 4, 8, 16, ... samples
     std::vector<int> w;
     w.push_back(0);
-    if (!termination_possible(r, derive_uniforms(r))) w.push_back(nmax);
+    // (slicing stops on the accumulated dest.a, which any TF can drive past 0.95: always windowed)
+    if (!P.slicing && !termination_possible(r, derive_uniforms(r))) w.push_back(nmax);
     else for (int len = 4; w.back() < nmax; len *= 2) w.push_back(std::min(nmax, w.back() + len));
     w.push_back(w.back());   // sentinel: nothing after the last window
     const int comp_grid = setup_grid;
@@ -900,10 +929,10 @@ int vv_set_option(VVRenderer *r, int option, int value)
     switch (option) {
     case VV_OPT_TF_MODE:
         if (value < TF_B || value > TF_SCALAR) return fail(VV_ERR_INVALID, "bad tf mode");
-        r->tf_mode = value; break;
+        r->tf_modes[r->technique == VV_VOLIC_SLICING ? 1 : 0] = value; break;
     case VV_OPT_GATE_MODE:
         if (value != GATE_ALWAYS && value != GATE_TF_ALPHA) return fail(VV_ERR_INVALID, "bad gate mode");
-        r->gate_mode = value; break;
+        r->gate_modes[r->technique == VV_VOLIC_SLICING ? 1 : 0] = value; break;
     case VV_OPT_NOISE_GATE: r->noise_gate = value != 0; break;
     case VV_OPT_QUIRK_SCALEVOLINV: r->quirk_scalevolinv = value != 0; break;
     case VV_OPT_QUIRK_LUMINANCE_ALPHA: r->quirk_lum_alpha = value != 0; break;
@@ -955,6 +984,10 @@ int vv_render(VVRenderer *r, int update)
     CU(cudaMemsetAsync(r->counters.p, 0, kNumCounters * sizeof(unsigned int), r->stream));
     const int grid = persistent_grid(r, r->n_local_blocks);
     switch (r->technique) {
+    case VV_VOLIC_SLICING:
+        rc = render_sample_parallel(r, P);
+        if (rc) return rc;
+        break;
     case VV_VOLIC_RAYCAST:
         if (r->raycast_mode == 0) {
             CU(cudaEventRecord(r->ev0, r->stream));

@@ -94,6 +94,13 @@ def curl_noise(n, seed, octaves=3, base_freq=4.0, slab=16):
     Psi(p) = sum_o 2^-o G_o(2^o * base_freq * p), G_o a periodic (64) tri-linear lattice of U[-1,1]^3 values from
     mt19937(seed + o); v = curl Psi by central differences with spacing 1/n in the [-1,1] coordinate.
     Evaluated slab by slab in z to bound memory."""
+    if n >= 256:
+        try:   # large fields: the same arithmetic (float64) on the GPU; 512^3 takes minutes in numpy
+            import torch
+            if torch.cuda.is_available():
+                return _curl_noise_torch(n, seed, octaves, base_freq, slab)
+        except ImportError:
+            pass
     lats = [_lattice(seed + o) for o in range(octaves)]
     c = _centres(n)
     eps = 1.0 / n
@@ -115,6 +122,43 @@ def curl_noise(n, seed, octaves=3, base_freq=4.0, slab=16):
         out[z0:z0 + slab, ..., 0] = dpy[..., 2] - dpz[..., 1]
         out[z0:z0 + slab, ..., 1] = dpz[..., 0] - dpx[..., 2]
         out[z0:z0 + slab, ..., 2] = dpx[..., 1] - dpy[..., 0]
+    return out
+
+
+def _curl_noise_torch(n, seed, octaves, base_freq, slab, device="cuda"):
+    """torch mirror of curl_noise (same float64 operations, evaluated on `device`); synthetic-input plumbing only"""
+    import torch
+    lats = [torch.from_numpy(_lattice(seed + o)).to(device) for o in range(octaves)]
+    c = torch.from_numpy(_centres(n)).to(device)
+    eps = 1.0 / n
+    out = np.empty((n, n, n, 3), dtype=np.float32)
+
+    def sample(lat, px, py, pz):
+        P = lat.shape[0]
+        fx, fy, fz = torch.floor(px), torch.floor(py), torch.floor(pz)
+        tx, ty, tz = (px - fx)[..., None], (py - fy)[..., None], (pz - fz)[..., None]
+        x0, y0, z0 = fx.long() % P, fy.long() % P, fz.long() % P
+        x1, y1, z1 = (x0 + 1) % P, (y0 + 1) % P, (z0 + 1) % P
+        c00 = lat[z0, y0, x0] * (1 - tx) + lat[z0, y0, x1] * tx
+        c10 = lat[z0, y1, x0] * (1 - tx) + lat[z0, y1, x1] * tx
+        c01 = lat[z1, y0, x0] * (1 - tx) + lat[z1, y0, x1] * tx
+        c11 = lat[z1, y1, x0] * (1 - tx) + lat[z1, y1, x1] * tx
+        return (c00 * (1 - ty) + c10 * ty) * (1 - tz) + (c01 * (1 - ty) + c11 * ty) * tz
+
+    def psi(x, y, z):
+        acc = 0.0
+        for o, lat in enumerate(lats):
+            f = (2.0 ** o) * base_freq
+            acc = acc + (2.0 ** -o) * sample(lat, x * f, y * f, z * f)
+        return acc
+
+    for z0 in range(0, n, slab):
+        zz, yy, xx = torch.meshgrid(c[z0:z0 + slab], c, c, indexing="ij")
+        dpx = (psi(xx + eps, yy, zz) - psi(xx - eps, yy, zz)) / (2 * eps)
+        dpy = (psi(xx, yy + eps, zz) - psi(xx, yy - eps, zz)) / (2 * eps)
+        dpz = (psi(xx, yy, zz + eps) - psi(xx, yy, zz - eps)) / (2 * eps)
+        v = torch.stack([dpy[..., 2] - dpz[..., 1], dpz[..., 0] - dpx[..., 2], dpx[..., 1] - dpy[..., 0]], dim=-1)
+        out[z0:z0 + slab] = v.to(torch.float32).cpu().numpy()
     return out
 
 
