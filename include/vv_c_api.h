@@ -85,7 +85,11 @@ typedef enum VVOption {
     VV_OPT_SPEC_EXP = 10,          /* gl_LightSource[0].spotExponent as int (default 40, VV/illumination.h:52) */
     VV_OPT_SAMPLE_MAP = 11,        /* 1: keep per-pixel ray-sample counts (vv_read_sample_map) */
     VV_OPT_RAYCAST_MODE = 12,      /* 1 (default): sample-parallel pipeline; 0: one thread per ray (cross-check) */
-    VV_OPT_LIC_CTAS_PER_SM = 13    /* persistent CTAs per SM of the lic_sample kernel (0 = default: all resident) */
+    VV_OPT_LIC_CTAS_PER_SM = 13,   /* persistent CTAs per SM of the lic_sample kernel (0 = default: all resident) */
+    VV_OPT_ITEM_CHUNK = 14,        /* experiment knob (unused) */
+    VV_OPT_DEPTH_MAJOR = 15,       /* 1 (default): work items ordered band-major / depth-major for L2 locality; 0: tile-major */
+    VV_OPT_BAND_ROWS = 16,         /* 16-pixel block rows per band of the depth-major order (default 4) */
+    VV_OPT_NOISE_LAYOUT = 17       /* RGBA (-g) noise: 1 (default) fp16 x-pair, 0 u8 xy-quad; same values, same frames */
 } VVOption;
 
 /* ---- lifecycle: Renderer() / init / resize / ~Renderer, VV/renderer.h:31-37 ------------------- */

@@ -23,6 +23,14 @@ if "mode" in opts:
     r.setOption(vv.OPT_RAYCAST_MODE, int(opts["mode"]))
 if "layout" in opts:
     r.setOption(vv.OPT_FIELD_LAYOUT, int(opts["layout"]))
+if "chunk" in opts:
+    r.setOption(vv.OPT_ITEM_CHUNK, int(opts["chunk"]))
+if "depthmajor" in opts:
+    r.setOption(vv.OPT_DEPTH_MAJOR, int(opts["depthmajor"]))
+if "band" in opts:
+    r.setOption(vv.OPT_BAND_ROWS, int(opts["band"]))
+if "noiselayout" in opts:
+    r.setOption(vv.OPT_NOISE_LAYOUT, int(opts["noiselayout"]))
 if "ctas" in opts:
     r.setOption(vv.OPT_LIC_CTAS_PER_SM, int(opts["ctas"]))
 configs.apply_scene(r, s)

@@ -490,3 +490,36 @@ def test_cuda_matches_golden_vectors(vv, oracle, name):
     r3.render(True)
     assert int((r3.readSampleMap() != g["volraycast_samples"].astype(np.uint32)).sum()) <= 1
     assert_image_parity(oracle, r3.readRGBA32F(), g["volraycast"], name + " volume ray-cast")
+
+
+def test_item_order_does_not_change_the_frame(vv):
+    """depth-major (band, depth-chunk) work-item order vs tile-major order: bit-identical frames and counts"""
+    from vectorvisualization_b200 import configs
+    from vectorvisualization_b200.configs import apply_scene
+    for mk in (lambda: configs.cfg3(n=48, size=200), lambda: configs.cfg1(n=32, size=150)):
+        s = mk()
+        out = []
+        for dm, band in ((1, 4), (0, 4), (1, 1), (1, 64)):
+            r = vv.Renderer(0)
+            r.setOption(vv.OPT_DEPTH_MAJOR, dm)
+            r.setOption(vv.OPT_BAND_ROWS, band)
+            apply_scene(r, s)
+            r.render(True)
+            out.append((r.readRGBA32F(), r.lastRaySamples()))
+        for img, n in out[1:]:
+            assert n == out[0][1] and np.array_equal(img, out[0][0])
+
+
+def test_noise_layouts_bit_identical(vv):
+    """RGBA (-g) noise as fp16 x-pairs (FHADD lerps) vs u8 xy-quads (PRMT decode): same values, same frames"""
+    from vectorvisualization_b200 import configs
+    from vectorvisualization_b200.configs import apply_scene
+    s = configs.cfg3(n=48, size=128)
+    out = []
+    for layout in (1, 0):
+        r = vv.Renderer(0)
+        r.setOption(vv.OPT_NOISE_LAYOUT, layout)
+        apply_scene(r, s)
+        r.render(True)
+        out.append(r.readRGBA32F())
+    assert np.array_equal(out[0], out[1])

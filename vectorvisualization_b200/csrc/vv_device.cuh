@@ -35,7 +35,8 @@ struct DevParams {
     const uint2  *scalar_cell;
     int snx, sny, snz;
     const uint2  *noise_cell;     // scalar noise (LUMINANCE / .a channel)
-    const uint4  *noise_quad;     // RGBA noise (gradient build)
+    const uint4  *noise_quad;     // RGBA noise (gradient build), u8 xy-quad layout
+    const uint4  *noise_pair;     // RGBA noise as fp16 x-pairs {half4 T[x], half4 T[x+1 mod nx]} (used when non-null)
     int nnx, nny, nnz;
     const float  *licvol;         // fp32 scalar LIC volume, sampled REPEAT
     int lnx, lny, lnz;
@@ -69,6 +70,10 @@ struct DevParams {
     uint2  *items, *itemsNext;       // work items (tile, k) of the current / next depth window
     unsigned int *itemCount, *itemCountNext, *itemHead, *slotAlloc, *nMaxGlobal;
     int win0, win1, win2;            // current window [win0, win1), next window ends at win2
+    int itemChunk;                   // (experiment knob, unused by the shipped kernel)
+    // depth-major item order: buckets = (band of block rows) x (chunk of 8 depths)
+    unsigned int *bucketCount, *bucketBase, *bucketFill;
+    int bandRows, nDepthChunks;
     // ---- view-aligned slicing (VV/slicing.cpp:42-114): unit view vector, covered depth, slice count ----
     int slicing;
     float slV[3], slD;
@@ -135,6 +140,22 @@ __device__ __forceinline__ pk2_t lerp2(pk2_t a, pk2_t b, pk2_t f) { return fma2(
 __device__ __forceinline__ pk2_t h2pk(unsigned int w) { float2 t = h2f(w); return pk2(t.x, t.y); }
 __device__ __forceinline__ float hlo(unsigned int w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
 
+// Blackwell mixed-precision add (FHADD: f32 = f16 + f32) runs at the full FMA-pipe rate, whereas the fp16 -> fp32
+// conversion HADD2.F32 runs at half rate (scripts/microbench/pipes.cu: 3.6 vs 1.9 warp-instr/clk/SM).  So a texel is
+// converted with "h + 0" and the lerp's difference is formed as "h1 - t0" directly from the fp16 neighbour: one
+// full-rate instruction each, no separate conversion.  Both are exact conversions followed by one fp32 rounding, i.e. the
+// same bits as cvt + sub.
+__device__ __forceinline__ unsigned short h_lo(unsigned int w) { return (unsigned short)(w & 0xffffu); }
+__device__ __forceinline__ unsigned short h_hi(unsigned int w) { return (unsigned short)(w >> 16); }
+__device__ __forceinline__ float fh_cvt(unsigned short h) { float d; asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(h), "f"(0.0f)); return d; }
+__device__ __forceinline__ float fh_sub(unsigned short h, float c) { float d; asm("sub.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(h), "f"(c)); return d; }
+// x-lerp of two channels held as half2 words w0 (texel x0) and w1 (texel x0+1)
+__device__ __forceinline__ pk2_t xlerp_h2(unsigned int w0, unsigned int w1, pk2_t fx2)
+{
+    const float a0 = fh_cvt(h_lo(w0)), a1 = fh_cvt(h_hi(w0));
+    return fma2(fx2, pk2(fh_sub(h_lo(w1), a0), fh_sub(h_hi(w1), a1)), pk2(a0, a1));
+}
+
 struct FieldVal { pk2_t rg; float b, a; };
 
 // ---- vector field: trilinear RGBA16F fetch, CLAMP_TO_EDGE (volumeSampler, VV/dataset.cpp:350-357) ----
@@ -158,18 +179,20 @@ __device__ __forceinline__ FieldVal fetch_field_pk(const DevParams &P, float px,
         const uint4 *F = P.field_pair;
         // corner loads A = (y0,z0), B = (y1,z0), C = (y0,z1), D = (y1,z1); each holds texels x0 (.x,.y) and x0+1 (.z,.w)
         const uint4 A = ld_u4(F + b00), B = ld_u4(F + b10), C = ld_u4(F + b01), D = ld_u4(F + b11);
-        const pk2_t rgA = lerp2(h2pk(A.x), h2pk(A.z), fx2), rgB = lerp2(h2pk(B.x), h2pk(B.z), fx2);
-        const pk2_t rgC = lerp2(h2pk(C.x), h2pk(C.z), fx2), rgD = lerp2(h2pk(D.x), h2pk(D.z), fx2);
+        // x-lerp straight from the fp16 pair: t0 + fx (t1 - t0) with t0 = FHADD(h0, 0), t1 - t0 = FHADD(h1, -t0)
+        const pk2_t rgA = xlerp_h2(A.x, A.z, fx2), rgB = xlerp_h2(B.x, B.z, fx2);
+        const pk2_t rgC = xlerp_h2(C.x, C.z, fx2), rgD = xlerp_h2(D.x, D.z, fx2);
         r.rg = lerp2(lerp2(rgA, rgB, fy2), lerp2(rgC, rgD, fy2), fz2);
         if (ALPHA) {
-            const pk2_t baA = lerp2(h2pk(A.y), h2pk(A.w), fx2), baB = lerp2(h2pk(B.y), h2pk(B.w), fx2);
-            const pk2_t baC = lerp2(h2pk(C.y), h2pk(C.w), fx2), baD = lerp2(h2pk(D.y), h2pk(D.w), fx2);
+            const pk2_t baA = xlerp_h2(A.y, A.w, fx2), baB = xlerp_h2(B.y, B.w, fx2);
+            const pk2_t baC = xlerp_h2(C.y, C.w, fx2), baD = xlerp_h2(D.y, D.w, fx2);
             const pk2_t ba = lerp2(lerp2(baA, baB, fy2), lerp2(baC, baD, fy2), fz2);
             up2(ba, r.b, r.a);
         } else {
             // blue only: pack the two z planes into one register pair for the x and y lerps
-            const pk2_t bAC = lerp2(pk2(hlo(A.y), hlo(C.y)), pk2(hlo(A.w), hlo(C.w)), fx2);
-            const pk2_t bBD = lerp2(pk2(hlo(B.y), hlo(D.y)), pk2(hlo(B.w), hlo(D.w)), fx2);
+            const float bA0 = fh_cvt(h_lo(A.y)), bC0 = fh_cvt(h_lo(C.y)), bB0 = fh_cvt(h_lo(B.y)), bD0 = fh_cvt(h_lo(D.y));
+            const pk2_t bAC = fma2(fx2, pk2(fh_sub(h_lo(A.w), bA0), fh_sub(h_lo(C.w), bC0)), pk2(bA0, bC0));
+            const pk2_t bBD = fma2(fx2, pk2(fh_sub(h_lo(B.w), bB0), fh_sub(h_lo(D.w), bD0)), pk2(bB0, bD0));
             const pk2_t by = lerp2(bAC, bBD, fy2);
             r.b = lerpf(lo2(by), hi2(by), fz);
             r.a = 0.0f;
@@ -272,6 +295,21 @@ __device__ __forceinline__ Rgba2 fetch_noise_rgba_pk(const DevParams &P, float p
     if (z1 >= P.nnz) z1 = 0;
     const unsigned int plane = (unsigned int)P.nny * (unsigned int)P.nnx;
     const unsigned int i0 = (unsigned int)y0 * (unsigned int)P.nnx + (unsigned int)x0;
+    if (P.noise_pair) {
+        // fp16 x-pair layout (byte values 0..255 are exact in fp16): the same FHADD lerp as the vector field, no byte decode
+        int y1 = y0 + 1;
+        if (y1 >= P.nny) y1 = 0;
+        const unsigned int i1 = (unsigned int)y1 * (unsigned int)P.nnx + (unsigned int)x0;
+        const uint4 A = ld_u4(P.noise_pair + ((unsigned int)z0 * plane + i0)), B = ld_u4(P.noise_pair + ((unsigned int)z0 * plane + i1));
+        const uint4 C = ld_u4(P.noise_pair + ((unsigned int)z1 * plane + i0)), D = ld_u4(P.noise_pair + ((unsigned int)z1 * plane + i1));
+        const pk2_t fx2 = bc2(fx), fy2 = bc2(fy), fz2 = bc2(fz), k2 = bc2(1.0f / 255.0f);
+        Rgba2 r;
+        r.rg = mul2(lerp2(lerp2(xlerp_h2(A.x, A.z, fx2), xlerp_h2(B.x, B.z, fx2), fy2),
+                          lerp2(xlerp_h2(C.x, C.z, fx2), xlerp_h2(D.x, D.z, fx2), fy2), fz2), k2);
+        r.ba = mul2(lerp2(lerp2(xlerp_h2(A.y, A.w, fx2), xlerp_h2(B.y, B.w, fx2), fy2),
+                          lerp2(xlerp_h2(C.y, C.w, fx2), xlerp_h2(D.y, D.w, fx2), fy2), fz2), k2);
+        return r;
+    }
     const uint4 a = ld_u4(P.noise_quad + ((unsigned int)z0 * plane + i0));
     const uint4 b = ld_u4(P.noise_quad + ((unsigned int)z1 * plane + i0));
     const pk2_t fx2 = bc2(fx), fy2 = bc2(fy), fz2 = bc2(fz), k2 = bc2(1.0f / 255.0f);

@@ -292,9 +292,12 @@ __device__ __forceinline__ float tf_index(const DevParams &P, float4 v, float sc
 struct SharedTables {
     float4 tf[256];
     float opac[256];
-    float kw[2 * kMaxLicSteps + 1];
     int block;
+    float kw[1];      // 1 + nBwd + nFwd weights; the dynamic shared-memory size is table_bytes(P)
 };
+
+// shared memory actually needed: the smaller it is, the more of the 256 KB L1/shared array is left to the L1 cache
+static size_t table_bytes(const DevParams &P) { return offsetof(SharedTables, kw) + sizeof(float) * (size_t)(1 + P.nBwd + P.nFwd); }
 
 __device__ __forceinline__ void load_tables(const DevParams &P, SharedTables &S)
 {
@@ -560,7 +563,11 @@ __global__ void __launch_bounds__(256, LIC_MIN_CTAS) lic_sample_kernel(const __g
     if (nItems == 0) return;
     load_tables(P, S);
     const int lane = threadIdx.x & 31;
+    // Items are ordered tile-major, depth-minor; every warp pops single items.  (Measured alternative: a CTA pops a chunk
+    // of 8..64 consecutive items and its warps walk it together behind a barrier -- L1 hit rate unchanged at 89 %, issue
+    // utilisation 72 % -> 64 % from the barrier; profiles/README.md.)
     for (;;) {
+      {
         unsigned int i = 0;
         if (lane == 0) i = atomicAdd(P.itemHead, 1u);
         i = __shfl_sync(0xffffffffu, i, 0);
@@ -599,6 +606,7 @@ __global__ void __launch_bounds__(256, LIC_MIN_CTAS) lic_sample_kernel(const __g
         else if (!shade_sample<LAYOUT, ILLUM, NGATE, SOF>(P, S, pos, dir, src)) src = make_float4(0.f, 0.f, 0.f, -1.0f);   // gated
         const uint2 tr = P.tileRec[it.x];
         P.src[((size_t)tr.x + k) * 32 + lane] = src;
+      }
     }
 }
 
@@ -660,6 +668,61 @@ __global__ void __launch_bounds__(256) composite_kernel(const __grid_constant__ 
             for (int k = lane; k < cnt; k += 32) P.itemsNext[ib + k] = make_uint2((unsigned int)lt, (unsigned int)(P.win1 + k));
         }
     }
+}
+
+// ---- depth-major work-item order --------------------------------------------------------------------------------
+// The item list decides which voxels are live in L2 at any time.  Tile-major order (all depths of a tile, then the
+// next tile) re-reads every voxel from DRAM once per row of tiles whose streamlines reach it (measured 6.9 GB per cfg3
+// frame against 0.55 GB of compulsory bytes).  Here items are bucketed by (band of block rows, chunk of 8 depths) and the
+// list is bucket-major: the frame is swept band by band, front to back, so the live set is a slab of the band a few
+// streamline lengths thick and each voxel comes from DRAM about once per band.
+// pass 0 counts the items of every bucket, bucket_scan_kernel turns counts into offsets, pass 1 writes the items.
+__global__ void __launch_bounds__(256) item_bucket_kernel(const __grid_constant__ DevParams P, int pass)
+{
+    const int lane = threadIdx.x & 31;
+    const int nTiles = P.nLocalBlocks * 8;
+    for (int lt = blockIdx.x * 8 + (threadIdx.x >> 5); lt < nTiles; lt += gridDim.x * 8) {
+        const uint2 tr = P.tileRec[lt];
+        const int nmax = min((int)tr.y, P.win2);
+        if (nmax <= 0) continue;
+        const int b = P.rank + (lt >> 3) * P.world;
+        const int band = (b / P.nBlocksX) / P.bandRows;
+        const int nchunks = (nmax + 7) >> 3;
+        for (int c = lane; c < nchunks; c += 32) {
+            const int cnt = min(8, nmax - 8 * c);
+            const int bucket = band * P.nDepthChunks + c;
+            if (pass == 0) {
+                atomicAdd(P.bucketCount + bucket, (unsigned int)cnt);
+            } else {
+                const unsigned int at = P.bucketBase[bucket] + atomicAdd(P.bucketFill + bucket, (unsigned int)cnt);
+                for (int j = 0; j < cnt; ++j) P.itemsNext[at + j] = make_uint2((unsigned int)lt, (unsigned int)(8 * c + j));
+            }
+        }
+    }
+}
+
+// exclusive scan of the bucket counts (a few thousand entries: one CTA), total -> item count of the window
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(const __grid_constant__ DevParams P, int nBuckets)
+{
+    __shared__ unsigned int s_part[1024];
+    const int t = threadIdx.x;
+    const int per = (nBuckets + 1023) / 1024;
+    unsigned int sum = 0;
+    for (int i = t * per; i < min(nBuckets, (t + 1) * per); ++i) sum += P.bucketCount[i];
+    s_part[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        unsigned int v = (t >= off) ? s_part[t - off] : 0u;
+        __syncthreads();
+        s_part[t] += v;
+        __syncthreads();
+    }
+    unsigned int run = s_part[t] - sum;   // exclusive prefix of this thread's segment
+    for (int i = t * per; i < min(nBuckets, (t + 1) * per); ++i) {
+        P.bucketBase[i] = run;
+        run += P.bucketCount[i];
+    }
+    if (t == 1023) *P.itemCountNext = s_part[1023];
 }
 
 // K3 ------------------------------------------------------------------------------------------------
@@ -817,6 +880,14 @@ cudaError_t launch_ray_setup(const DevParams &P, int grid, cudaStream_t st)
     return cudaGetLastError();
 }
 
+cudaError_t launch_item_buckets(const DevParams &P, int nBuckets, int grid, cudaStream_t st)
+{
+    item_bucket_kernel<<<grid, 256, 0, st>>>(P, 0);
+    bucket_scan_kernel<<<1, 1024, 0, st>>>(P, nBuckets);
+    item_bucket_kernel<<<grid, 256, 0, st>>>(P, 1);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_composite(const DevParams &P, int grid, cudaStream_t st)
 {
     composite_kernel<<<grid, 256, 0, st>>>(P);
@@ -836,14 +907,32 @@ static int persistent_ctas(K kernel, size_t smem, int num_sms_times_cap)
     return sms * (cap > 0 && cap < occ ? cap : occ);
 }
 
+// Ask for the smallest shared-memory carve-out that still holds the resident CTAs' tables, so the rest of the unified
+// 256 KB array serves as L1 (the driver's default picked 102 KB of shared memory for 3 x 14 KB; ncu
+// launch__shared_mem_config_size).  The gathers of this kernel live on L1 hits.
+template <class K>
+static int prefer_l1(K kernel, size_t smem)
+{
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem) != cudaSuccess || occ < 1) occ = 1;
+    const size_t need = (size_t)occ * (smem + 1024);                 // + 1 KB per CTA reserved by the driver
+    int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    return occ;
+}
+
 template <int LAYOUT, int ILLUM, bool NGATE>
 static cudaError_t launch_sample_sof(const DevParams &P, bool sof, int grid, size_t smem, cudaStream_t st)
 {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sof) {
-        static int g = persistent_ctas(lic_sample_kernel<LAYOUT, ILLUM, NGATE, true>, smem, 0);
+        const int g = sms * prefer_l1(lic_sample_kernel<LAYOUT, ILLUM, NGATE, true>, smem);
         lic_sample_kernel<LAYOUT, ILLUM, NGATE, true><<<grid > 0 ? grid : g, 256, smem, st>>>(P);
     } else {
-        static int g = persistent_ctas(lic_sample_kernel<LAYOUT, ILLUM, NGATE, false>, smem, 0);
+        const int g = sms * prefer_l1(lic_sample_kernel<LAYOUT, ILLUM, NGATE, false>, smem);
         lic_sample_kernel<LAYOUT, ILLUM, NGATE, false><<<grid > 0 ? grid : g, 256, smem, st>>>(P);
     }
     return cudaGetLastError();
@@ -868,21 +957,21 @@ static cudaError_t launch_sample_layout(const DevParams &P, int illum, bool ngat
 
 cudaError_t launch_lic_sample(const DevParams &P, int layout, int illum, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st)
 {
-    const size_t smem = sizeof(SharedTables);
+    const size_t smem = table_bytes(P);
     if (layout == LAYOUT_PAIR) return launch_sample_layout<LAYOUT_PAIR>(P, illum, noise_gate, speed_of_flow, grid, smem, st);
     return launch_sample_layout<LAYOUT_F4>(P, illum, noise_gate, speed_of_flow, grid, smem, st);
 }
 
 cudaError_t launch_lic_raycast(const DevParams &P, int layout, int illum, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st)
 {
-    const size_t smem = sizeof(SharedTables);
+    const size_t smem = table_bytes(P);
     if (layout == LAYOUT_PAIR) return launch_raycast_layout<LAYOUT_PAIR>(P, illum, noise_gate, speed_of_flow, grid, smem, st);
     return launch_raycast_layout<LAYOUT_F4>(P, illum, noise_gate, speed_of_flow, grid, smem, st);
 }
 
 cudaError_t launch_volume_raycast(const DevParams &P, int layout, int grid, cudaStream_t st)
 {
-    const size_t smem = sizeof(SharedTables);
+    const size_t smem = table_bytes(P);
     if (layout == LAYOUT_PAIR) {
         cudaFuncSetAttribute(volume_raycast_kernel<LAYOUT_PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         volume_raycast_kernel<LAYOUT_PAIR><<<grid, 256, smem, st>>>(P);
@@ -897,10 +986,10 @@ template <int LAYOUT, bool GRAD, bool NGATE>
 static cudaError_t launch_licvol_sof(const DevParams &P, bool sof, int grid, size_t smem, cudaStream_t st)
 {
     if (sof) {
-        cudaFuncSetAttribute(lic_volume_kernel<LAYOUT, GRAD, NGATE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        prefer_l1(lic_volume_kernel<LAYOUT, GRAD, NGATE, true>, smem);
         lic_volume_kernel<LAYOUT, GRAD, NGATE, true><<<grid, 256, smem, st>>>(P);
     } else {
-        cudaFuncSetAttribute(lic_volume_kernel<LAYOUT, GRAD, NGATE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        prefer_l1(lic_volume_kernel<LAYOUT, GRAD, NGATE, false>, smem);
         lic_volume_kernel<LAYOUT, GRAD, NGATE, false><<<grid, 256, smem, st>>>(P);
     }
     return cudaGetLastError();
@@ -908,7 +997,7 @@ static cudaError_t launch_licvol_sof(const DevParams &P, bool sof, int grid, siz
 
 cudaError_t launch_lic_volume(const DevParams &P, int layout, bool grad, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st)
 {
-    const size_t smem = sizeof(SharedTables);
+    const size_t smem = table_bytes(P);
     if (layout == LAYOUT_PAIR) {
         if (grad) return launch_licvol_sof<LAYOUT_PAIR, true, false>(P, speed_of_flow, grid, smem, st);
         return noise_gate ? launch_licvol_sof<LAYOUT_PAIR, false, true>(P, speed_of_flow, grid, smem, st)

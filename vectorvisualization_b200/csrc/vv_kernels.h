@@ -13,6 +13,7 @@ cudaError_t launch_lic_raycast(const DevParams &P, int layout, int illum, bool n
 cudaError_t launch_ray_setup(const DevParams &P, int grid, cudaStream_t st);
 cudaError_t launch_lic_sample(const DevParams &P, int layout, int illum, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st);
 cudaError_t launch_composite(const DevParams &P, int grid, cudaStream_t st);
+cudaError_t launch_item_buckets(const DevParams &P, int nBuckets, int grid, cudaStream_t st);
 cudaError_t launch_volume_raycast(const DevParams &P, int layout, int grid, cudaStream_t st);
 cudaError_t launch_lic_volume(const DevParams &P, int layout, bool grad, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st);
 cudaError_t launch_unblock(const float4 *tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY, int width, int height,
@@ -28,6 +29,8 @@ cudaError_t launch_build_cell8(const uint8_t *src, int src_stride, int src_offse
                                uint2 *out, cudaStream_t st);
 // RGBA8 volume -> xy-quad layout with REPEAT
 cudaError_t launch_build_quad(const uchar4 *src, int nx, int ny, int nz, uint4 *out, cudaStream_t st);
+// RGBA8 volume -> fp16 x-pair layout with REPEAT in x
+cudaError_t launch_build_noise_pair(const uchar4 *src, int nx, int ny, int nz, uint4 *out, cudaStream_t st);
 // float scalar volume -> u8 LUMINANCE (GL float->UNORM8 conversion on upload)
 cudaError_t launch_float_to_unorm8(const float *src, size_t n, uint8_t *out, cudaStream_t st);
 // noise gradients, VV/gradient.cpp:190-532: Sobel/one-sided -> 5^3 smoothing (Q16) -> normalise + quantise, and

@@ -141,6 +141,26 @@ cudaError_t launch_build_quad(const uchar4 *src, int nx, int ny, int nz, uint4 *
     return cudaGetLastError();
 }
 
+// RGBA8 volume -> fp16 x-pair layout {half4 T[x], half4 T[(x+1) mod nx]}; byte values are exact in fp16
+__global__ void build_noise_pair_kernel(const uchar4 *__restrict__ src, int nx, int ny, int nz, uint4 *__restrict__ out)
+{
+    const size_t n = (size_t)nx * ny * nz;
+    for (size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(a % nx);
+        const uchar4 t0 = src[a], t1 = src[(x + 1 < nx) ? a + 1 : a - x];
+        __half2 p0 = __floats2half2_rn((float)t0.x, (float)t0.y), p1 = __floats2half2_rn((float)t0.z, (float)t0.w);
+        __half2 q0 = __floats2half2_rn((float)t1.x, (float)t1.y), q1 = __floats2half2_rn((float)t1.z, (float)t1.w);
+        out[a] = make_uint4(*reinterpret_cast<unsigned int *>(&p0), *reinterpret_cast<unsigned int *>(&p1),
+                            *reinterpret_cast<unsigned int *>(&q0), *reinterpret_cast<unsigned int *>(&q1));
+    }
+}
+
+cudaError_t launch_build_noise_pair(const uchar4 *src, int nx, int ny, int nz, uint4 *out, cudaStream_t st)
+{
+    build_noise_pair_kernel<<<148 * 8, 256, 0, st>>>(src, nx, ny, nz, out);
+    return cudaGetLastError();
+}
+
 __global__ void float_to_unorm8_kernel(const float *__restrict__ src, size_t n, uint8_t *__restrict__ out)
 {
     for (size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += (size_t)gridDim.x * blockDim.x)

@@ -78,7 +78,8 @@ struct VVRenderer {
     DevBuf<uint8_t> noise_raw;
     DevBuf<uint2> noise_cell;
     DevBuf<uchar4> noise_rgba;
-    DevBuf<uint4> noise_quad;
+    DevBuf<uint4> noise_quad, noise_pair;
+    int noise_layout = 1;                  // RGBA noise: 1 = fp16 x-pair (default), 0 = u8 xy-quad
     DevBuf<float> grad_tmp, grad_filter;
     int ndim[3] = {0, 0, 0};
     bool have_noise = false, noise_has_grad = false;
@@ -122,6 +123,10 @@ struct VVRenderer {
     DevBuf<uint2> tileRec, items[2];
     int raycast_mode = 1;                  // 1: sample-parallel pipeline (default), 0: one thread per ray
     int lic_ctas_per_sm = 0;               // 0: as many as are resident (occupancy query)
+    int item_chunk = 8;                    // (experiment knob)
+    int depth_major = 1;                   // 1: bucket work items by (band, depth chunk) for L2 locality; 0: tile-major
+    int band_rows = 4;                     // block rows per band (4 x 16 = 64 pixel rows)
+    DevBuf<unsigned int> buckets;
     bool frame_valid = false;
     int launches = 0;
 
@@ -339,6 +344,7 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycas
     P.fnx = r->size[0]; P.fny = r->size[1]; P.fnz = r->size[2];
     P.scalar_cell = r->scalar_cell.p; P.snx = r->sdim[0]; P.sny = r->sdim[1]; P.snz = r->sdim[2];
     P.noise_cell = r->noise_cell.p; P.noise_quad = r->noise_quad.p;
+    P.noise_pair = (r->noise_layout == 1) ? r->noise_pair.p : nullptr;
     P.nnx = r->ndim[0]; P.nny = r->ndim[1]; P.nnz = r->ndim[2];
     P.licvol = r->licvol.p; P.lnx = r->ldim[0]; P.lny = r->ldim[1]; P.lnz = r->ldim[2];
     P.tf_rgba = r->tf_rgba.p; P.tf_opac = r->tf_opac.p; P.kw = r->kw.p;
@@ -512,6 +518,8 @@ static int upload_noise(VVRenderer *r, const uint8_t *data, const int dims[3], i
         const float sd[3] = {1.0f, 1.0f, 1.0f};
         CU(launch_noise_gradients(r->noise_raw.p, dims[0], dims[1], dims[2], sd, r->grad_filter.p, r->grad_tmp.p, r->noise_rgba.p, r->stream));
         CU(launch_build_quad(r->noise_rgba.p, dims[0], dims[1], dims[2], r->noise_quad.p, r->stream));
+        CU(r->noise_pair.ensure(n));
+        CU(launch_build_noise_pair(r->noise_rgba.p, dims[0], dims[1], dims[2], r->noise_pair.p, r->stream));
         r->noise_has_grad = true;
     }
     CU(cudaStreamSynchronize(r->stream));
@@ -558,6 +566,7 @@ static int render_sample_parallel(VVRenderer *r, DevParams &P)
     CU(r->items[0].ensure(rows));
     CU(r->items[1].ensure(rows));
     P.src = r->src.p;
+    P.itemChunk = r->item_chunk;
     // depth windows: whole ray at once when no sample can trigger the early termination, else 4, 8, 16, ... samples
     std::vector<int> w;
     w.push_back(0);
@@ -568,13 +577,26 @@ static int render_sample_parallel(VVRenderer *r, DevParams &P)
     const int comp_grid = setup_grid;
     const int lic_grid = r->num_sms * r->lic_ctas_per_sm;   // 0: launcher uses the occupancy of the instantiation
     const bool ngate = r->illum_mode != ILLUM_GRADIENT && r->noise_gate;
-    // empty window [0,0): emits the work items of the first real window
     int cur = 0;
     P.win0 = 0; P.win1 = 0; P.win2 = w[1];
     P.itemsNext = r->items[cur].p; P.itemCountNext = cnt + 4 + cur;
-    P.sampleCounter = nullptr;
-    CU(launch_composite(P, comp_grid, r->stream));
-    ++r->launches;
+    if (r->depth_major) {
+        // work items of the first window in (band, depth chunk)-major order (see item_bucket_kernel)
+        P.bandRows = r->band_rows;
+        P.nDepthChunks = (std::min(nmax, w[1]) + 7) / 8;
+        const int nBands = (r->nby + r->band_rows - 1) / r->band_rows;
+        const int nBuckets = nBands * P.nDepthChunks;
+        CU(r->buckets.ensure((size_t)3 * nBuckets));
+        CU(cudaMemsetAsync(r->buckets.p, 0, (size_t)3 * nBuckets * sizeof(unsigned int), r->stream));
+        P.bucketCount = r->buckets.p; P.bucketBase = r->buckets.p + nBuckets; P.bucketFill = r->buckets.p + 2 * nBuckets;
+        CU(launch_item_buckets(P, nBuckets, comp_grid, r->stream));
+        r->launches += 3;
+    } else {
+        // empty window [0,0): composite_kernel emits the work items of the first real window, tile-major
+        P.sampleCounter = nullptr;
+        CU(launch_composite(P, comp_grid, r->stream));
+        ++r->launches;
+    }
     P.sampleCounter = r->count_samples ? r->counters.p : nullptr;
     CU(cudaEventRecord(r->ev0, r->stream));
     for (size_t p = 0; p + 2 < w.size(); ++p) {
@@ -955,6 +977,16 @@ int vv_set_option(VVRenderer *r, int option, int value)
     case VV_OPT_RAYCAST_MODE:
         if (value != 0 && value != 1) return fail(VV_ERR_INVALID, "bad raycast mode");
         r->raycast_mode = value; break;
+    case VV_OPT_NOISE_LAYOUT:
+        if (value != 0 && value != 1) return fail(VV_ERR_INVALID, "bad noise layout");
+        r->noise_layout = value; break;
+    case VV_OPT_DEPTH_MAJOR: r->depth_major = value != 0; break;
+    case VV_OPT_BAND_ROWS:
+        if (value < 1 || value > 1024) return fail(VV_ERR_INVALID, "bad band rows");
+        r->band_rows = value; break;
+    case VV_OPT_ITEM_CHUNK:
+        if (value < 8 || value > 256 || (value % 8)) return fail(VV_ERR_INVALID, "item chunk must be a multiple of 8 in 8..256");
+        r->item_chunk = value; break;
     case VV_OPT_LIC_CTAS_PER_SM:
         if (value < 0 || value > 8) return fail(VV_ERR_INVALID, "bad CTAs per SM");
         r->lic_ctas_per_sm = value; break;
