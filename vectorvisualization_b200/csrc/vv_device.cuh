@@ -8,7 +8,11 @@
 //   u8 volumes     cell8 : uint2 [z][y][x] = the 8 corner bytes of the trilinear cell whose low corner is
 //                  (x,y,z), wrap mode (REPEAT for noise, CLAMP_TO_EDGE for the scalar volume) baked in;
 //                  byte order x fastest: (x0y0z0, x1y0z0, x0y1z0, x1y1z0, x0y0z1, ...).
-//   RGBA8 noise    quad : uint4 [z][y][x] = RGBA8 texels (x0y0, x1y0, x0y1, x1y1) of plane z, REPEAT baked in.
+//   RGBA8 noise    pair : uint4 = { half4 N[x], half4 N[x+1] }, bytes 0..255 as fp16 integers (hot layout)
+//                  quad : uint4 [z][y][x] = RGBA8 texels (x0y0, x1y0, x0y1, x1y1) of plane z, REPEAT baked in (check).
+//   padding        hot layouts carry their wrap mode as border rows / planes (edge replicated for CLAMP_TO_EDGE, wrapped
+//                  for REPEAT, where the cell index floor(u) lies in [-1, n-1]), so the sampler never clamps or wraps
+//                  an index: neighbours are +row / +plane.
 //   tables         TF RGBA as float4[256], LIC-opacity as float[256], per-step filter-kernel weights as float[]
 //                  (staged into shared memory by every CTA).
 #pragma once
@@ -29,15 +33,22 @@ constexpr int kMaxLicSteps = 1024;   // per direction (weights live in shared me
 
 struct DevParams {
     // ---- textures ----
-    const uint4  *field_pair;
+    const uint4  *field_pair;     // padded [nz+1][ny+1][nx] (edge replicated): neighbours are +fRow / +fPlane, no index clamp
     const float4 *field_f4;
     int fnx, fny, fnz;
+    float fnf[3], fnm1f[3];       // (float)n and (float)(n-1) per axis: no I2FP of loop invariants in the walk
+    unsigned int fRow, fPlane;    // element strides of field_pair
     const uint2  *scalar_cell;
     int snx, sny, snz;
-    const uint2  *noise_cell;     // scalar noise (LUMINANCE / .a channel)
-    const uint4  *noise_quad;     // RGBA noise (gradient build), u8 xy-quad layout
-    const uint4  *noise_pair;     // RGBA noise as fp16 x-pairs {half4 T[x], half4 T[x+1 mod nx]} (used when non-null)
+    float snf[3], snm1f[3];
+    // REPEAT textures are stored with a wrapped border so that the cell index floor(u) in [-1, n-1] addresses memory
+    // directly: the pointers below already point at cell (0,0,0) of the padded arrays (signed element offsets).
+    const uint2  *noise_cell;     // scalar noise (LUMINANCE / .a channel), cell8, padded [nz+1][ny+1][nx+1]
+    const uint4  *noise_quad;     // RGBA noise (gradient build), u8 xy-quad layout (unpadded check layout)
+    const uint4  *noise_pair;     // RGBA noise as fp16 x-pairs {half4 T[x], half4 T[x+1]} padded [nz+2][ny+2][nx+1] (used when non-null)
     int nnx, nny, nnz;
+    float nnf[3];
+    int ncRow, ncPlane, npRow, npPlane;   // element strides of noise_cell / noise_pair
     const float  *licvol;         // fp32 scalar LIC volume, sampled REPEAT
     int lnx, lny, lnz;
     const float4 *tf_rgba;        // [256]
@@ -112,6 +123,24 @@ __device__ __forceinline__ void axis_repeat(float s, int n, int &i0, float &f)
     if (i0 >= n) i0 -= n;
 }
 
+// The same two rules with the axis size passed as floats (loop-invariant conversions hoisted to the host) and
+// without the neighbour index: the padded layouts make it i0 + 1 unconditionally.
+__device__ __forceinline__ void axis_clamp_f(float s, float nf, float nm1f, int &i0, float &f)
+{
+    float u = fmaf(s, nf, -0.5f);
+    u = fminf(fmaxf(u, 0.0f), nm1f);
+    i0 = __float2int_rd(u);
+    f = u - __int2float_rn(i0);
+}
+// i0 is left unwrapped in [-1, n-1]
+__device__ __forceinline__ void axis_repeat_f(float s, float nf, int &i0, float &f)
+{
+    s = s - floorf(s);
+    float u = fmaf(s, nf, -0.5f);
+    i0 = __float2int_rd(u);
+    f = u - __int2float_rn(i0);
+}
+
 __device__ __forceinline__ float4 ld_f4(const float4 *p) { return __ldg(p); }
 __device__ __forceinline__ uint4 ld_u4(const uint4 *p) { return __ldg(p); }
 __device__ __forceinline__ uint2 ld_u2(const uint2 *p) { return __ldg(p); }
@@ -162,20 +191,18 @@ struct FieldVal { pk2_t rg; float b, a; };
 template <int LAYOUT, bool ALPHA>
 __device__ __forceinline__ FieldVal fetch_field_pk(const DevParams &P, float px, float py, float pz)
 {
-    int x0, x1, y0, y1, z0, z1;
-    float fx, fy, fz;
-    axis_clamp(px, P.fnx, x0, x1, fx);
-    axis_clamp(py, P.fny, y0, y1, fy);
-    axis_clamp(pz, P.fnz, z0, z1, fz);
-    // 32-bit element indices (volumes up to 2^31 voxels), one zero-extended pointer add per load
-    const unsigned int row = (unsigned int)P.fnx;
-    const unsigned int b00 = ((unsigned int)z0 * (unsigned int)P.fny + (unsigned int)y0) * row + (unsigned int)x0;
-    const unsigned int dy = (unsigned int)(y1 - y0) * row;                       // 0 at the clamped edge
-    const unsigned int dz = (unsigned int)(z1 - z0) * row * (unsigned int)P.fny;
-    const unsigned int b10 = b00 + dy, b01 = b00 + dz, b11 = b01 + dy;
-    const pk2_t fx2 = bc2(fx), fy2 = bc2(fy), fz2 = bc2(fz);
     FieldVal r;
     if (LAYOUT == LAYOUT_PAIR) {
+        int x0, y0, z0;
+        float fx, fy, fz;
+        axis_clamp_f(px, P.fnf[0], P.fnm1f[0], x0, fx);
+        axis_clamp_f(py, P.fnf[1], P.fnm1f[1], y0, fy);
+        axis_clamp_f(pz, P.fnf[2], P.fnm1f[2], z0, fz);
+        // 32-bit element indices (volumes up to 2^31 voxels), one zero-extended pointer add per load; the y / z
+        // neighbours are one padded row / plane further (at the clamped edge the replicated texel, weight 0)
+        const unsigned int b00 = (unsigned int)z0 * P.fPlane + (unsigned int)y0 * P.fRow + (unsigned int)x0;
+        const unsigned int b10 = b00 + P.fRow, b01 = b00 + P.fPlane, b11 = b01 + P.fRow;
+        const pk2_t fx2 = bc2(fx), fy2 = bc2(fy), fz2 = bc2(fz);
         const uint4 *F = P.field_pair;
         // corner loads A = (y0,z0), B = (y1,z0), C = (y0,z1), D = (y1,z1); each holds texels x0 (.x,.y) and x0+1 (.z,.w)
         const uint4 A = ld_u4(F + b00), B = ld_u4(F + b10), C = ld_u4(F + b01), D = ld_u4(F + b11);
@@ -198,6 +225,17 @@ __device__ __forceinline__ FieldVal fetch_field_pk(const DevParams &P, float px,
             r.a = 0.0f;
         }
     } else {
+        int x0, x1, y0, y1, z0, z1;
+        float fx, fy, fz;
+        axis_clamp(px, P.fnx, x0, x1, fx);
+        axis_clamp(py, P.fny, y0, y1, fy);
+        axis_clamp(pz, P.fnz, z0, z1, fz);
+        const unsigned int row = (unsigned int)P.fnx;
+        const unsigned int b00 = ((unsigned int)z0 * (unsigned int)P.fny + (unsigned int)y0) * row + (unsigned int)x0;
+        const unsigned int dy = (unsigned int)(y1 - y0) * row;                       // 0 at the clamped edge
+        const unsigned int dz = (unsigned int)(z1 - z0) * row * (unsigned int)P.fny;
+        const unsigned int b10 = b00 + dy, b01 = b00 + dz, b11 = b01 + dy;
+        const pk2_t fx2 = bc2(fx), fy2 = bc2(fy), fz2 = bc2(fz);
         const float4 *F = P.field_f4;
         const unsigned int dx = (unsigned int)(x1 - x0);
         const float4 t000 = ld_f4(F + b00), t100 = ld_f4(F + b00 + dx);
@@ -247,11 +285,11 @@ __device__ __forceinline__ float cell8_blend(uint2 c, float fx, float fy, float 
 // scalarSampler: LUMINANCE8, CLAMP_TO_EDGE (VV/dataset.cpp:1025-1038) -> .r
 __device__ __forceinline__ float fetch_scalar(const DevParams &P, float px, float py, float pz)
 {
-    int x0, x1, y0, y1, z0, z1;
+    int x0, y0, z0;
     float fx, fy, fz;
-    axis_clamp(px, P.snx, x0, x1, fx);
-    axis_clamp(py, P.sny, y0, y1, fy);
-    axis_clamp(pz, P.snz, z0, z1, fz);
+    axis_clamp_f(px, P.snf[0], P.snm1f[0], x0, fx);
+    axis_clamp_f(py, P.snf[1], P.snm1f[1], y0, fy);
+    axis_clamp_f(pz, P.snf[2], P.snm1f[2], z0, fz);
     uint2 c = ld_u2(P.scalar_cell + (((unsigned int)z0 * (unsigned int)P.sny + (unsigned int)y0) * (unsigned int)P.snx + (unsigned int)x0));
     return cell8_blend(c, fx, fy, fz);
 }
@@ -261,10 +299,10 @@ __device__ __forceinline__ float fetch_noise_scalar(const DevParams &P, float px
 {
     int x0, y0, z0;
     float fx, fy, fz;
-    axis_repeat(px, P.nnx, x0, fx);
-    axis_repeat(py, P.nny, y0, fy);
-    axis_repeat(pz, P.nnz, z0, fz);
-    uint2 c = ld_u2(P.noise_cell + (((unsigned int)z0 * (unsigned int)P.nny + (unsigned int)y0) * (unsigned int)P.nnx + (unsigned int)x0));
+    axis_repeat_f(px, P.nnf[0], x0, fx);
+    axis_repeat_f(py, P.nnf[1], y0, fy);
+    axis_repeat_f(pz, P.nnf[2], z0, fz);
+    uint2 c = ld_u2(P.noise_cell + (z0 * P.ncPlane + y0 * P.ncRow + x0));   // signed: cell -1 is the wrapped border
     return cell8_blend(c, fx, fy, fz);
 }
 
@@ -288,20 +326,15 @@ __device__ __forceinline__ Rgba2 fetch_noise_rgba_pk(const DevParams &P, float p
 {
     int x0, y0, z0;
     float fx, fy, fz;
-    axis_repeat(px, P.nnx, x0, fx);
-    axis_repeat(py, P.nny, y0, fy);
-    axis_repeat(pz, P.nnz, z0, fz);
-    int z1 = z0 + 1;
-    if (z1 >= P.nnz) z1 = 0;
-    const unsigned int plane = (unsigned int)P.nny * (unsigned int)P.nnx;
-    const unsigned int i0 = (unsigned int)y0 * (unsigned int)P.nnx + (unsigned int)x0;
+    axis_repeat_f(px, P.nnf[0], x0, fx);
+    axis_repeat_f(py, P.nnf[1], y0, fy);
+    axis_repeat_f(pz, P.nnf[2], z0, fz);
     if (P.noise_pair) {
-        // fp16 x-pair layout (byte values 0..255 are exact in fp16): the same FHADD lerp as the vector field, no byte decode
-        int y1 = y0 + 1;
-        if (y1 >= P.nny) y1 = 0;
-        const unsigned int i1 = (unsigned int)y1 * (unsigned int)P.nnx + (unsigned int)x0;
-        const uint4 A = ld_u4(P.noise_pair + ((unsigned int)z0 * plane + i0)), B = ld_u4(P.noise_pair + ((unsigned int)z0 * plane + i1));
-        const uint4 C = ld_u4(P.noise_pair + ((unsigned int)z1 * plane + i0)), D = ld_u4(P.noise_pair + ((unsigned int)z1 * plane + i1));
+        // fp16 x-pair layout (byte values 0..255 are exact in fp16): the same FHADD lerp as the vector field, no byte
+        // decode; wrapped border rows / planes, so the neighbours are +npRow / +npPlane for every cell index in [-1, n-1]
+        const uint4 *N = P.noise_pair + (z0 * P.npPlane + y0 * P.npRow + x0);
+        const uint4 A = ld_u4(N), B = ld_u4(N + P.npRow);
+        const uint4 C = ld_u4(N + P.npPlane), D = ld_u4(N + P.npPlane + P.npRow);
         const pk2_t fx2 = bc2(fx), fy2 = bc2(fy), fz2 = bc2(fz), k2 = bc2(1.0f / 255.0f);
         Rgba2 r;
         r.rg = mul2(lerp2(lerp2(xlerp_h2(A.x, A.z, fx2), xlerp_h2(B.x, B.z, fx2), fy2),
@@ -310,6 +343,13 @@ __device__ __forceinline__ Rgba2 fetch_noise_rgba_pk(const DevParams &P, float p
                           lerp2(xlerp_h2(C.y, C.w, fx2), xlerp_h2(D.y, D.w, fx2), fy2), fz2), k2);
         return r;
     }
+    if (x0 < 0) x0 += P.nnx;
+    if (y0 < 0) y0 += P.nny;
+    if (z0 < 0) z0 += P.nnz;
+    int z1 = z0 + 1;
+    if (z1 >= P.nnz) z1 = 0;
+    const unsigned int plane = (unsigned int)P.nny * (unsigned int)P.nnx;
+    const unsigned int i0 = (unsigned int)y0 * (unsigned int)P.nnx + (unsigned int)x0;
     const uint4 a = ld_u4(P.noise_quad + ((unsigned int)z0 * plane + i0));
     const uint4 b = ld_u4(P.noise_quad + ((unsigned int)z1 * plane + i0));
     const pk2_t fx2 = bc2(fx), fy2 = bc2(fy), fz2 = bc2(fz), k2 = bc2(1.0f / 255.0f);

@@ -21,15 +21,17 @@ cudaError_t launch_unblock(const float4 *tiles, int world, int blocksPerRank, in
 
 // ---- pre-processing (K6) ----
 // VectorDataSet::fillTexDataFloatInterp (VV/dataset.cpp:533-635): raw FLOAT3 / UCHAR3 time steps -> packed field.
-// tmp: float4 [n] scratch; maxbits: 1 uint scratch.  Writes the pair-packed fp16 layout and/or the float4 layout.
+// tmp: float4 [n] scratch; maxbits: 1 uint scratch.  Writes the pair-packed fp16 layout (padded [nz+1][ny+1][nx], edge
+// replicated) and/or the float4 layout.
 cudaError_t launch_pack_field(const void *v0, const void *v1, int is_u8, int nx, int ny, int nz, float interp_frac,
                               float4 *tmp, unsigned int *maxbits, uint4 *out_pair, float4 *out_f4, cudaStream_t st);
-// u8 volume -> cell8 layout (wrap: 0 = CLAMP_TO_EDGE, 1 = REPEAT); src_stride = bytes per voxel, src_offset = channel
-cudaError_t launch_build_cell8(const uint8_t *src, int src_stride, int src_offset, int nx, int ny, int nz, int repeat,
+// u8 volume -> cell8 layout (wrap: 0 = CLAMP_TO_EDGE, 1 = REPEAT); src_stride = bytes per voxel, src_offset = channel;
+// pad = 1 adds the wrapped cell -1 on every axis: out is [nz+1][ny+1][nx+1]
+cudaError_t launch_build_cell8(const uint8_t *src, int src_stride, int src_offset, int nx, int ny, int nz, int repeat, int pad,
                                uint2 *out, cudaStream_t st);
 // RGBA8 volume -> xy-quad layout with REPEAT
 cudaError_t launch_build_quad(const uchar4 *src, int nx, int ny, int nz, uint4 *out, cudaStream_t st);
-// RGBA8 volume -> fp16 x-pair layout with REPEAT in x
+// RGBA8 volume -> fp16 x-pair layout with wrapped borders: out is [nz+2][ny+2][nx+1]
 cudaError_t launch_build_noise_pair(const uchar4 *src, int nx, int ny, int nz, uint4 *out, cudaStream_t st);
 // float scalar volume -> u8 LUMINANCE (GL float->UNORM8 conversion on upload)
 cudaError_t launch_float_to_unorm8(const float *src, size_t n, uint8_t *out, cudaStream_t st);

@@ -65,20 +65,28 @@ __device__ __forceinline__ uint2 to_half4(float4 v, float maxLen)
 }
 
 // pass 2: scale |v| by 1/max, round to fp16, write the x-pair layout and/or float4
-__global__ void pack_field_pass2(const float4 *__restrict__ tmp, const unsigned int *__restrict__ maxbits, int nx, size_t n,
+// The x-pair layout is padded to [nz+1][ny+1][nx] with the last row / plane replicated (CLAMP_TO_EDGE), so the
+// sampler's y / z neighbours are always one row / plane further.
+__global__ void pack_field_pass2(const float4 *__restrict__ tmp, const unsigned int *__restrict__ maxbits, int nx, int ny, int nz,
                                  uint4 *__restrict__ out_pair, float4 *__restrict__ out_f4)
 {
     const float maxLen = __uint_as_float(*maxbits);
-    for (size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(a % nx);
-        uint2 t0 = to_half4(tmp[a], maxLen);
-        if (out_pair) {
-            uint2 t1 = (x + 1 < nx) ? to_half4(tmp[a + 1], maxLen) : t0;
-            out_pair[a] = make_uint4(t0.x, t0.y, t1.x, t1.y);
-        }
-        if (out_f4) {
+    const size_t n = (size_t)nx * ny * nz;
+    if (out_f4) {
+        for (size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += (size_t)gridDim.x * blockDim.x) {
+            uint2 t0 = to_half4(tmp[a], maxLen);
             float2 rg = h2f(t0.x), ba = h2f(t0.y);
             out_f4[a] = make_float4(rg.x, rg.y, ba.x, ba.y);
+        }
+    }
+    if (out_pair) {
+        const size_t np = (size_t)nx * (ny + 1) * (nz + 1);
+        for (size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x; a < np; a += (size_t)gridDim.x * blockDim.x) {
+            const int x = (int)(a % nx), y = (int)((a / nx) % (ny + 1)), z = (int)(a / ((size_t)nx * (ny + 1)));
+            const size_t s = ((size_t)min(z, nz - 1) * ny + min(y, ny - 1)) * nx + x;
+            uint2 t0 = to_half4(tmp[s], maxLen);
+            uint2 t1 = (x + 1 < nx) ? to_half4(tmp[s + 1], maxLen) : t0;
+            out_pair[a] = make_uint4(t0.x, t0.y, t1.x, t1.y);
         }
     }
 }
@@ -92,17 +100,23 @@ cudaError_t launch_pack_field(const void *v0, const void *v1, int is_u8, int nx,
     const int grid = 148 * 8;
     if (is_u8) pack_field_pass1<true><<<grid, 256, 0, st>>>(v0, v1, n, interp_frac, tmp, maxbits);
     else pack_field_pass1<false><<<grid, 256, 0, st>>>(v0, v1, n, interp_frac, tmp, maxbits);
-    pack_field_pass2<<<grid, 256, 0, st>>>(tmp, maxbits, nx, n, out_pair, out_f4);
+    pack_field_pass2<<<grid, 256, 0, st>>>(tmp, maxbits, nx, ny, nz, out_pair, out_f4);
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void build_cell8_kernel(const uint8_t *__restrict__ src, int stride, int off, int nx, int ny, int nz, int repeat,
+// pad = 1 (REPEAT volumes): the output is [nz+1][ny+1][nx+1] and entry (jx,jy,jz) is the cell whose low corner is
+// texel (jx-1, jy-1, jz-1) mod n, so the sampler's cell index floor(u) in [-1, n-1] needs no wrap.
+__global__ void build_cell8_kernel(const uint8_t *__restrict__ src, int stride, int off, int nx, int ny, int nz, int repeat, int pad,
                                    uint2 *__restrict__ out)
 {
-    const size_t n = (size_t)nx * ny * nz;
+    const int px = nx + pad, py = ny + pad, pz = nz + pad;
+    const size_t n = (size_t)px * py * pz;
     for (size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(a % nx), y = (int)((a / nx) % ny), z = (int)(a / ((size_t)nx * ny));
+        int x = (int)(a % px) - pad, y = (int)((a / px) % py) - pad, z = (int)(a / ((size_t)px * py)) - pad;
+        if (x < 0) x += nx;
+        if (y < 0) y += ny;
+        if (z < 0) z += nz;
         const int x1 = (x + 1 < nx) ? x + 1 : (repeat ? 0 : x);
         const int y1 = (y + 1 < ny) ? y + 1 : (repeat ? 0 : y);
         const int z1 = (z + 1 < nz) ? z + 1 : (repeat ? 0 : z);
@@ -116,10 +130,10 @@ __global__ void build_cell8_kernel(const uint8_t *__restrict__ src, int stride, 
     }
 }
 
-cudaError_t launch_build_cell8(const uint8_t *src, int src_stride, int src_offset, int nx, int ny, int nz, int repeat,
+cudaError_t launch_build_cell8(const uint8_t *src, int src_stride, int src_offset, int nx, int ny, int nz, int repeat, int pad,
                                uint2 *out, cudaStream_t st)
 {
-    build_cell8_kernel<<<148 * 8, 256, 0, st>>>(src, src_stride, src_offset, nx, ny, nz, repeat, out);
+    build_cell8_kernel<<<148 * 8, 256, 0, st>>>(src, src_stride, src_offset, nx, ny, nz, repeat, pad, out);
     return cudaGetLastError();
 }
 
@@ -144,10 +158,15 @@ cudaError_t launch_build_quad(const uchar4 *src, int nx, int ny, int nz, uint4 *
 // RGBA8 volume -> fp16 x-pair layout {half4 T[x], half4 T[(x+1) mod nx]}; byte values are exact in fp16
 __global__ void build_noise_pair_kernel(const uchar4 *__restrict__ src, int nx, int ny, int nz, uint4 *__restrict__ out)
 {
-    const size_t n = (size_t)nx * ny * nz;
+    // padded [nz+2][ny+2][nx+1]: entry (jx,jy,jz) = texels ((jx-1) mod nx, jx mod nx) of row (jy-1) mod ny, plane (jz-1) mod nz
+    const int px = nx + 1, py = ny + 2;
+    const size_t n = (size_t)px * py * (nz + 2);
     for (size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(a % nx);
-        const uchar4 t0 = src[a], t1 = src[(x + 1 < nx) ? a + 1 : a - x];
+        const int jx = (int)(a % px), jy = (int)((a / px) % py), jz = (int)(a / ((size_t)px * py));
+        const int x0 = (jx == 0) ? nx - 1 : jx - 1, x1 = (jx == nx) ? 0 : jx;
+        const int y = (jy == 0) ? ny - 1 : (jy == ny + 1 ? 0 : jy - 1), z = (jz == 0) ? nz - 1 : (jz == nz + 1 ? 0 : jz - 1);
+        const size_t r = ((size_t)z * ny + y) * nx;
+        const uchar4 t0 = src[r + x0], t1 = src[r + x1];
         __half2 p0 = __floats2half2_rn((float)t0.x, (float)t0.y), p1 = __floats2half2_rn((float)t0.z, (float)t0.w);
         __half2 q0 = __floats2half2_rn((float)t1.x, (float)t1.y), q1 = __floats2half2_rn((float)t1.z, (float)t1.w);
         out[a] = make_uint4(*reinterpret_cast<unsigned int *>(&p0), *reinterpret_cast<unsigned int *>(&p1),

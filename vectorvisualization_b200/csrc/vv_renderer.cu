@@ -308,7 +308,10 @@ static int pack_field(VVRenderer *r)
     CU(r->maxbits.ensure(1));
     uint4 *pair = nullptr;
     float4 *f4 = nullptr;
-    if (r->field_layout == LAYOUT_PAIR) { CU(r->field_pair.ensure(n)); pair = r->field_pair.p; }
+    if (r->field_layout == LAYOUT_PAIR) {   // padded [nz+1][ny+1][nx]
+        CU(r->field_pair.ensure((size_t)r->size[0] * (r->size[1] + 1) * (r->size[2] + 1)));
+        pair = r->field_pair.p;
+    }
     else { CU(r->field_f4.ensure(n)); f4 = r->field_f4.p; }
     const float frac = (float)r->interp_index / r->interp_size;   // VV/dataset.cpp:590
     CU(launch_pack_field(r->raw0.p, r->have_next ? r->raw1.p : nullptr, r->field_u8 ? 1 : 0, r->size[0], r->size[1], r->size[2],
@@ -342,10 +345,20 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycas
     std::memset(&P, 0, sizeof(P));
     P.field_pair = r->field_pair.p; P.field_f4 = r->field_f4.p;
     P.fnx = r->size[0]; P.fny = r->size[1]; P.fnz = r->size[2];
+    P.fRow = (unsigned int)r->size[0]; P.fPlane = (unsigned int)r->size[0] * (unsigned int)(r->size[1] + 1);
     P.scalar_cell = r->scalar_cell.p; P.snx = r->sdim[0]; P.sny = r->sdim[1]; P.snz = r->sdim[2];
-    P.noise_cell = r->noise_cell.p; P.noise_quad = r->noise_quad.p;
-    P.noise_pair = (r->noise_layout == 1) ? r->noise_pair.p : nullptr;
     P.nnx = r->ndim[0]; P.nny = r->ndim[1]; P.nnz = r->ndim[2];
+    for (int k = 0; k < 3; ++k) {
+        P.fnf[k] = (float)r->size[k]; P.fnm1f[k] = (float)(r->size[k] - 1);
+        P.snf[k] = (float)r->sdim[k]; P.snm1f[k] = (float)(r->sdim[k] - 1);
+        P.nnf[k] = (float)r->ndim[k];
+    }
+    // wrapped-border layouts: point at cell (0,0,0), i.e. one padded plane + row + element in
+    P.ncRow = r->ndim[0] + 1; P.ncPlane = P.ncRow * (r->ndim[1] + 1);
+    P.npRow = r->ndim[0] + 1; P.npPlane = P.npRow * (r->ndim[1] + 2);
+    P.noise_cell = r->noise_cell.p ? r->noise_cell.p + (P.ncPlane + P.ncRow + 1) : nullptr;
+    P.noise_quad = r->noise_quad.p;
+    P.noise_pair = (r->noise_layout == 1 && r->noise_pair.p) ? r->noise_pair.p + (P.npPlane + P.npRow + 1) : nullptr;
     P.licvol = r->licvol.p; P.lnx = r->ldim[0]; P.lny = r->ldim[1]; P.lnz = r->ldim[2];
     P.tf_rgba = r->tf_rgba.p; P.tf_opac = r->tf_opac.p; P.kw = r->kw.p;
     for (int i = 0; i < 3; ++i) P.illum2d[i] = r->illum_tab[i].p;
@@ -489,12 +502,14 @@ static int ensure_illum_tables(VVRenderer *r)
 static int upload_noise(VVRenderer *r, const uint8_t *data, const int dims[3], int with_gradients)
 {
     const size_t n = (size_t)dims[0] * dims[1] * dims[2];
-    if (n == 0 || n > ((size_t)1 << 31)) return fail(VV_ERR_INVALID, "noise dimensions out of range");
+    // the padded layouts are addressed with signed 32-bit element offsets
+    if (n == 0 || (size_t)(dims[0] + 1) * (dims[1] + 2) * (dims[2] + 2) >= ((size_t)1 << 31)) return fail(VV_ERR_INVALID, "noise dimensions out of range");
     CU(r->noise_raw.ensure(n));
     CU(cudaMemcpyAsync(r->noise_raw.p, data, n, cudaMemcpyHostToDevice, r->stream));
     r->ndim[0] = dims[0]; r->ndim[1] = dims[1]; r->ndim[2] = dims[2];
-    CU(r->noise_cell.ensure(n));
-    CU(launch_build_cell8(r->noise_raw.p, 1, 0, dims[0], dims[1], dims[2], 1, r->noise_cell.p, r->stream));
+    // REPEAT layouts carry a wrapped border (cell -1 on every axis), see vv_device.cuh
+    CU(r->noise_cell.ensure((size_t)(dims[0] + 1) * (dims[1] + 1) * (dims[2] + 1)));
+    CU(launch_build_cell8(r->noise_raw.p, 1, 0, dims[0], dims[1], dims[2], 1, 1, r->noise_cell.p, r->stream));
     r->noise_has_grad = false;
     if (with_gradients) {
         // filter table of filterGradients, VV/gradient.cpp:392-409 (only the k,j,i in -2..0 corner is ever written; Q16)
@@ -518,7 +533,7 @@ static int upload_noise(VVRenderer *r, const uint8_t *data, const int dims[3], i
         const float sd[3] = {1.0f, 1.0f, 1.0f};
         CU(launch_noise_gradients(r->noise_raw.p, dims[0], dims[1], dims[2], sd, r->grad_filter.p, r->grad_tmp.p, r->noise_rgba.p, r->stream));
         CU(launch_build_quad(r->noise_rgba.p, dims[0], dims[1], dims[2], r->noise_quad.p, r->stream));
-        CU(r->noise_pair.ensure(n));
+        CU(r->noise_pair.ensure((size_t)(dims[0] + 1) * (dims[1] + 2) * (dims[2] + 2)));
         CU(launch_build_noise_pair(r->noise_rgba.p, dims[0], dims[1], dims[2], r->noise_pair.p, r->stream));
         r->noise_has_grad = true;
     }
@@ -808,7 +823,7 @@ int vv_set_scalar(VVRenderer *r, const void *data, int dtype, const int dims[3])
         CU(cudaMemcpyAsync(raw.p, data, n, cudaMemcpyHostToDevice, r->stream));
     }
     CU(r->scalar_cell.ensure(n));
-    CU(launch_build_cell8(raw.p, 1, 0, dims[0], dims[1], dims[2], 0, r->scalar_cell.p, r->stream));
+    CU(launch_build_cell8(raw.p, 1, 0, dims[0], dims[1], dims[2], 0, 0, r->scalar_cell.p, r->stream));
     CU(cudaStreamSynchronize(r->stream));
     r->sdim[0] = dims[0]; r->sdim[1] = dims[1]; r->sdim[2] = dims[2];
     r->have_scalar = true;
@@ -1128,11 +1143,17 @@ int vv_read_field_texture(VVRenderer *r, float *out, size_t out_bytes)
         CU(cudaStreamSynchronize(r->stream));
         return VV_OK;
     }
-    std::vector<uint16_t> tmp(n * 8);
-    CU(cudaMemcpyAsync(tmp.data(), r->field_pair.p, n * 16, cudaMemcpyDeviceToHost, r->stream));
+    // gather the unpadded [nz][ny][nx] texels out of the padded x-pair layout
+    const size_t nx = r->size[0], ny = r->size[1], nz = r->size[2], np = nx * (ny + 1) * (nz + 1);
+    std::vector<uint16_t> tmp(np * 8);
+    CU(cudaMemcpyAsync(tmp.data(), r->field_pair.p, np * 16, cudaMemcpyDeviceToHost, r->stream));
     CU(cudaStreamSynchronize(r->stream));
-    for (size_t i = 0; i < n; ++i)
-        for (int k = 0; k < 4; ++k) out[4 * i + k] = half_bits_to_float(tmp[8 * i + k]);
+    for (size_t z = 0; z < nz; ++z)
+        for (size_t y = 0; y < ny; ++y)
+            for (size_t x = 0; x < nx; ++x) {
+                const size_t i = (z * ny + y) * nx + x, j = (z * (ny + 1) + y) * nx + x;
+                for (int k = 0; k < 4; ++k) out[4 * i + k] = half_bits_to_float(tmp[8 * j + k]);
+            }
     return VV_OK;
 }
 
