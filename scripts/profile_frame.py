@@ -34,6 +34,19 @@ if "noiselayout" in opts:
 if "ctas" in opts:
     r.setOption(vv.OPT_LIC_CTAS_PER_SM, int(opts["ctas"]))
 configs.apply_scene(r, s)
+if "part" in opts:   # one rank's share of a sort-first partition, e.g. part=0/8
+    pr, pw = (int(v) for v in opts["part"].split("/"))
+    r.setPartition(pr, pw)
+if "loop" in opts:   # back-to-back frames, one synchronize at the end (the bench.py `value` loop without NCCL)
+    r.render(True)
+    r.synchronize()
+    k = int(opts["loop"])
+    t = time.perf_counter()
+    for i in range(k):
+        r.render(True)
+    r.synchronize()
+    dt = (time.perf_counter() - t) / k
+    print("%s loop of %d frames: %.3f ms/frame wall, last kernel %.3f ms, %d ray samples" % (name, k, dt * 1e3, r.lastKernelMs(), r.lastRaySamples()), flush=True)
 for i in range(frames):
     t = time.perf_counter()
     r.render(True)

@@ -34,7 +34,7 @@ def _worker(rank, world, port, w, h, q):
     bpr = vd.blocks_per_rank(w, h, world)
     mine = np.zeros((bpr, 256, 4), np.float32)
     for lb, b in enumerate(vd.local_blocks(w, h, rank, world)):      # this rank "renders" only its own blocks
-        bx, by = b % nbx, b // nbx
+        bx, by = vd.block_xy(nbx, vd.block_skew(world), b)
         tile = np.zeros((16, 16, 4), np.float32)
         y0, x0 = by * 16, bx * 16
         hh, ww = min(16, h - y0), min(16, w - x0)
@@ -83,6 +83,17 @@ def test_partition_bookkeeping():
                 assert len(lb) <= vd.blocks_per_rank(w, h, world)
                 seen += lb
             assert sorted(seen) == list(range(nbx * nby))
+            # id <-> (bx, by) is a bijection (what unblock_kernel and ray_setup_kernel rely on)
+            sk = vd.block_skew(world)
+            pos = [vd.block_xy(nbx, sk, b) for b in range(nbx * nby)]
+            assert sorted(pos) == sorted((x, y) for y in range(nby) for x in range(nbx))
+            assert all(vd.block_id(nbx, sk, x, y) == b for b, (x, y) in enumerate(pos))
+    # the rotation scatters a rank's blocks over columns as well as rows even when nbx % world == 0
+    nbx, nby = vd.block_grid(1024, 1024)
+    for world in (2, 4, 8):
+        for r in range(world):
+            cols = {vd.block_xy(nbx, vd.block_skew(world), b)[0] for b in vd.local_blocks(1024, 1024, r, world)}
+            assert len(cols) == nbx
     for depth in (1024, 13, 7):
         for world in (1, 2, 4, 8):
             z = [vd.slab_range(depth, r, world) for r in range(world)]

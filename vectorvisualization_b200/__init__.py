@@ -174,9 +174,13 @@ class Renderer:
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             self._lib.vv_destroy(self._h)
-            self._h = ctypes.c_void_p()
+            self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # interpreter shutdown: module globals may already be gone
+            pass
 
     def __enter__(self):
         return self

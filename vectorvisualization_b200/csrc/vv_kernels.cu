@@ -381,8 +381,10 @@ __global__ void __launch_bounds__(256) lic_raycast_kernel(const __grid_constant_
         __syncthreads();
         if (lb >= P.nLocalBlocks) break;
         const int b = P.rank + lb * P.world;
-        const int px = (b % P.nBlocksX) * kBlockDim + lx;
-        const int py = (b / P.nBlocksX) * kBlockDim + ly;
+        int bx, by;
+        block_xy(P, b, bx, by);
+        const int px = bx * kBlockDim + lx;
+        const int py = by * kBlockDim + ly;
 
         float4 dest = make_float4(0.f, 0.f, 0.f, 0.f);
         unsigned int nsamples = 0;
@@ -434,8 +436,10 @@ __device__ __forceinline__ int tile_pixel(const DevParams &P, int lt, int lane, 
     const int lb = lt >> 3, sub = lt & 7;
     const int b = P.rank + lb * P.world;
     const int lx = (sub & 1) * 8 + (lane & 7), ly = (sub >> 1) * 4 + (lane >> 3);
-    px = (b % P.nBlocksX) * kBlockDim + lx;
-    py = (b / P.nBlocksX) * kBlockDim + ly;
+    int bx, by;
+    block_xy(P, b, bx, by);
+    px = bx * kBlockDim + lx;
+    py = by * kBlockDim + ly;
     return lb * kBlockPixels + ly * kBlockDim + lx;
 }
 
@@ -631,20 +635,30 @@ __global__ void __launch_bounds__(256) composite_kernel(const __grid_constant__ 
             float4 dest = P.tiles[o];
             const int kend = min(n, P.win1);
             bool done = false;
-            for (int k = P.win0; k < kend; ++k) {
-                const float4 s = P.src[((size_t)tr.x + k) * 32 + lane];
-                if (P.slicing) {
-                    // lic3d_slicing_fragment.glsl:14: a fragment only works while the frame buffer has dest.a < 0.95
-                    if (s.w == -2.0f) continue;                       // no fragment of this slice under the pixel
-                    if (!(dest.w < 0.95f)) { done = true; break; }
+            // The blend is a serial chain but the loads are not: fetch 8 samples ahead so that one ray keeps 8 requests in
+            // flight (the kernel is latency-bound: a 222-sample ray is 222 dependent round trips otherwise).
+            constexpr int kAhead = 8;
+            for (int k0 = P.win0; k0 < kend && !done; k0 += kAhead) {
+                float4 buf[kAhead];
+#pragma unroll
+                for (int j = 0; j < kAhead; ++j) buf[j] = P.src[((size_t)tr.x + min(k0 + j, kend - 1)) * 32 + lane];
+#pragma unroll
+                for (int j = 0; j < kAhead; ++j) {
+                    if (done || k0 + j >= kend) continue;
+                    const float4 s = buf[j];
+                    if (P.slicing) {
+                        // lic3d_slicing_fragment.glsl:14: a fragment only works while the frame buffer has dest.a < 0.95
+                        if (s.w == -2.0f) continue;                       // no fragment of this slice under the pixel
+                        if (!(dest.w < 0.95f)) { done = true; continue; }
+                        ++consumed;
+                        if (s.w >= 0.0f) composite(dest, s);
+                        continue;
+                    }
                     ++consumed;
-                    if (s.w >= 0.0f) composite(dest, s);
-                    continue;
-                }
-                ++consumed;
-                if (s.w >= 0.0f) {
-                    composite(dest, s);
-                    if (s.w > 0.95f) { done = true; break; }          // early ray termination on src.a (Q4)
+                    if (s.w >= 0.0f) {
+                        composite(dest, s);
+                        if (s.w > 0.95f) done = true;                     // early ray termination on src.a (Q4)
+                    }
                 }
             }
             if (kend >= n) done = true;
@@ -743,8 +757,10 @@ __global__ void __launch_bounds__(256) volume_raycast_kernel(const __grid_consta
         __syncthreads();
         if (lb >= P.nLocalBlocks) break;
         const int b = P.rank + lb * P.world;
-        const int px = (b % P.nBlocksX) * kBlockDim + lx;
-        const int py = (b / P.nBlocksX) * kBlockDim + ly;
+        int bx, by;
+        block_xy(P, b, bx, by);
+        const int px = bx * kBlockDim + lx;
+        const int py = by * kBlockDim + ly;
         float4 dest = make_float4(0.f, 0.f, 0.f, 0.f);
         unsigned int nsamples = 0;
         float e[3];
@@ -814,14 +830,14 @@ __global__ void __launch_bounds__(256) lic_volume_kernel(const __grid_constant__
 
 // K5 ------------------------------------------------------------------------------------------------
 // tiles laid out [world][nLocalBlocksMax][256] -> row-major float frame, RGBA8 frame, and displayed RGBA8
-__global__ void unblock_kernel(const float4 *__restrict__ tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY,
+__global__ void unblock_kernel(const float4 *__restrict__ tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY, int skew,
                                int width, int height, float4 *__restrict__ frame, uchar4 *__restrict__ frame8,
                                uchar4 *__restrict__ display8)
 {
     const int px = blockIdx.x * blockDim.x + threadIdx.x;
     const int py = blockIdx.y * blockDim.y + threadIdx.y;
     if (px >= width || py >= height) return;
-    const int b = (py / kBlockDim) * nBlocksX + px / kBlockDim;
+    const int b = block_id(nBlocksX, skew, px / kBlockDim, py / kBlockDim);
     const int r = b % world, lb = b / world;
     float4 c = tiles[((size_t)r * blocksPerRank + lb) * kBlockPixels + (py % kBlockDim) * kBlockDim + (px % kBlockDim)];
     const size_t o = (size_t)py * width + px;
@@ -1009,11 +1025,11 @@ cudaError_t launch_lic_volume(const DevParams &P, int layout, bool grad, bool no
                       : launch_licvol_sof<LAYOUT_F4, false, false>(P, speed_of_flow, grid, smem, st);
 }
 
-cudaError_t launch_unblock(const float4 *tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY, int width, int height,
+cudaError_t launch_unblock(const float4 *tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY, int skew, int width, int height,
                            float4 *frame, uchar4 *frame8, uchar4 *display8, cudaStream_t st)
 {
     dim3 blk(16, 16), grd((width + 15) / 16, (height + 15) / 16);
-    unblock_kernel<<<grd, blk, 0, st>>>(tiles, world, blocksPerRank, nBlocksX, nBlocksY, width, height, frame, frame8, display8);
+    unblock_kernel<<<grd, blk, 0, st>>>(tiles, world, blocksPerRank, nBlocksX, nBlocksY, skew, width, height, frame, frame8, display8);
     return cudaGetLastError();
 }
 

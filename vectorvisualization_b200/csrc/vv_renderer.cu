@@ -418,6 +418,7 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycas
     }
     P.tfMode = r->tf_modes[prog]; P.gateMode = r->gate_modes[prog]; P.quirkLumAlpha = (r->quirk_lum_alpha && !r->noise_has_grad) ? 1 : 0;   // Q7 only bites GL_LUMINANCE noise
     P.rank = r->rank; P.world = r->world; P.nBlocksX = r->nbx; P.nBlocksY = r->nby; P.nLocalBlocks = r->n_local_blocks;
+    P.blockSkew = block_skew_for(r->world);
     P.tiles = r->tiles.p;
     P.sampleCounter = r->count_samples ? r->counters.p : nullptr;
     P.blockCounter = r->counters.p ? reinterpret_cast<unsigned int *>(r->counters.p + 1) : nullptr;
@@ -439,7 +440,7 @@ static int persistent_grid(const VVRenderer *r, int work_items)
 
 static int run_unblock(VVRenderer *r, const float4 *tiles, int world, int blocks_per_rank)
 {
-    CU(launch_unblock(tiles, world, blocks_per_rank, r->nbx, r->nby, r->width, r->height, r->frame.p, r->frame8.p, r->display8.p, r->stream));
+    CU(launch_unblock(tiles, world, blocks_per_rank, r->nbx, r->nby, block_skew_for(world), r->width, r->height, r->frame.p, r->frame8.p, r->display8.p, r->stream));
     ++r->launches;
     r->frame_valid = true;
     return VV_OK;

@@ -1,8 +1,10 @@
 """Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink) for the gathers.
 
-Sort-first: the image is cut into 16x16-pixel blocks; block b belongs to rank b % world (interleaving balances the
-~20-70 % box coverage and the chord-length variation without a cost model); the vector field, noise, scalar volume
-and tables are replicated on every GPU.  Each rank renders its blocks into a compact block-major tile buffer; one
+Sort-first: the image is cut into 16x16-pixel blocks; block (bx, by) has the id by*nbx + (bx + skew*by) % nbx and
+belongs to rank id % world.  The per-row rotation scatters one rank's blocks over x and y, which balances the ~20-70 %
+box coverage and the chord-length variation without a cost model (plain row-major ids gave whole block columns to a
+rank whenever nbx % world == 0: 9 % imbalance at 8 GPUs on cfg3, 0.2 % with the rotation); the vector field, noise,
+scalar volume and tables are replicated on every GPU.  Each rank renders its blocks into a compact block-major tile buffer; one
 all_gather of those buffers (a few MiB per frame) and one un-block kernel give every rank the frame.
 LIC-volume mode: output z-slabs per rank (input replicated, so no halo exchange is needed -- SURVEY 8(e)), one
 all_gather of the slabs.
@@ -30,12 +32,27 @@ def block_grid(width, height, block=16):
     return (width + block - 1) // block, (height + block - 1) // block
 
 
+def block_skew(world):
+    """per-row rotation of the block ids (vv_device.cuh: block_skew_for)"""
+    return 0 if world <= 1 else 2 * ((382 * world // 1000) // 2) + 1
+
+
+def block_id(nbx, skew, bx, by):
+    return by * nbx + (bx + skew * by) % nbx
+
+
+def block_xy(nbx, skew, b):
+    by = b // nbx
+    return (b % nbx - skew * by) % nbx, by
+
+
 def blocks_per_rank(width, height, world, block=16):
     nbx, nby = block_grid(width, height, block)
     return (nbx * nby + world - 1) // world
 
 
 def local_blocks(width, height, rank, world, block=16):
+    """block ids owned by `rank`, in local order; block_xy() gives their position"""
     nbx, nby = block_grid(width, height, block)
     return list(range(rank, nbx * nby, world))
 
@@ -46,7 +63,7 @@ def assemble_host(gathered, width, height, world, block=16):
     out = np.zeros((height, width, gathered.shape[-1]), dtype=gathered.dtype)
     for b in range(nbx * nby):
         r, lb = b % world, b // world
-        bx, by = b % nbx, b // nbx
+        bx, by = block_xy(nbx, block_skew(world), b)
         tile = gathered[r, lb].reshape(block, block, -1)
         y0, x0 = by * block, bx * block
         h, w = min(block, height - y0), min(block, width - x0)
