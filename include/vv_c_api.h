@@ -142,6 +142,21 @@ VV_API int vv_update_light_pos(VVRenderer *r);
 VV_API int vv_enable_lowres(VVRenderer *r, int enable);
 VV_API int vv_enable_float_target(VVRenderer *r, int enable);
 VV_API int vv_set_option(VVRenderer *r, int option, int value);
+/* Monte-Carlo ray-start offsets.  Renderer::updateMCOffsetTex (VV/renderer.cpp:636-679) fills a width x height
+ * GL_LUMINANCE16F rectangle texture with rand()/RAND_MAX; programs built with "#define USE_MC_OFFSET" (passed to vv_init /
+ * vv_load_glsl_shader) start each ray / slice fragment at pos + dir * stepSize * offset[pixel]
+ * (lic3d_fragment.glsl:31-33, lic3d_slicing_fragment.glsl:31-33).  vv_set_mc_offsets takes the values (row 0 = bottom
+ * row, rounded to fp16 like the upload; NULL removes the texture); vv_update_mc_offset_tex draws them from
+ * mt19937(seed).  The size must equal the frame size at vv_render. */
+VV_API int vv_set_mc_offsets(VVRenderer *r, const float *offsets, int width, int height);
+VV_API int vv_update_mc_offset_tex(VVRenderer *r, int width, int height, uint32_t seed);
+/* User clip planes: ClipPlane::setNormal(x, y, z, d) + activation (VV/transform.cpp:296-315, 446-483), index 0..2 =
+ * GL_CLIP_PLANE0 + index (VV/3DLIC.cpp:763-781).  equation = (n.xyz, d) in volume-centred object coordinates, the
+ * half-space n.q + d >= 0 is kept; NULL keeps the stored equation.  Semantics as drawn by Renderer::render
+ * (VV/renderer.cpp:156-163, 1294-1309): the front faces of the proxy cube and the slice polygons are clipped, and for
+ * the two ray-cast techniques each active plane adds the box cross-section n^.q = -(d - 0.0001) as a ray-entry polygon
+ * (culled when it faces away); rays still leave through the box, as in the reference. */
+VV_API int vv_set_clip_plane(VVRenderer *r, int index, const double equation[4], int active);
 /* setIllum*Tex (Illumination, VV/illumination.cpp:96-390): the Zoeckler / Mallo look-up tables are generated inside the
  * library when an ILLUM_MALLO / ILLUM_ZOECKLER build is selected; this host-only entry point returns the same tables
  * (decoded UNORM8 values): zoeckler [h][w][2] (luminance, alpha), mallo [h][w] each */
@@ -200,7 +215,18 @@ VV_API int vv_parse_dat(const char *dat_path, VVDatInfo *out);
 VV_API int vv_read_raw(const VVDatInfo *info, int time_step, void *out, size_t out_bytes);
 VV_API int vv_load_dat(VVRenderer *r, const char *dat_path);          /* vector field (.dat, FLOAT3/UCHAR3) */
 VV_API int vv_load_scalar_dat(VVRenderer *r, const char *dat_path);   /* scalar volume (.dat, UCHAR/FLOAT) */
-VV_API int vv_load_noise(VVRenderer *r, const char *path, int with_gradients); /* 3 x int32 + u8, VV/dataset.cpp:1347-1389 */
+/* 3 x int32 + u8, VV/dataset.cpp:1347-1389.  With gradients the quantised gradients are cached next to the noise file as
+ * NoiseDataSet::createTexture does (VV/dataset.cpp:1238-1267): "<path>.grd" is used when it exists and has the right
+ * size, otherwise the gradients are computed (on the GPU) and written there; a failed write is not an error. */
+VV_API int vv_load_noise(VVRenderer *r, const char *path, int with_gradients);
+/* the gradient cache itself: loadGradients / saveGradients(DATRAW_UCHAR), VV/gradient.cpp:93-187 -- "<file_name>.grd" holds
+ * 3 * nx*ny*nz bytes, [z][y][x][3].  vv_grd_read returns VV_ERR_IO when the file is missing or short.  Host-only. */
+VV_API int vv_grd_read(const char *file_name, const int dims[3], uint8_t *gradients3);
+VV_API int vv_grd_write(const char *file_name, const int dims[3], const uint8_t *gradients3);
+/* noise volume + already quantised gradients -> the RGBA8 noise texture (VV/dataset.cpp:1269-1282) */
+VV_API int vv_set_noise_with_gradients(VVRenderer *r, const uint8_t *noise, const uint8_t *gradients3, const int dims[3]);
+/* read back the quantised gradients of the current noise ([z][y][x][3]) */
+VV_API int vv_read_noise_gradients(VVRenderer *r, uint8_t *out, size_t out_bytes);
 VV_API int vv_load_filter_png(VVRenderer *r, const char *path);       /* LICFilter::loadData, VV/dataset.cpp:1415-1467 */
 VV_API int vv_load_tf_png(VVRenderer *r, const char *name);           /* TransferEdit::loadTF, VV/transferEdit.cpp:224-337 */
 

@@ -49,6 +49,10 @@ PROGRAMS = {
     "slicing_gradient": (SLICING, ["ILLUM_GRADIENT"], ["REF_SLICING"]),
     "slicing_mallo": (SLICING, ["ILLUM_MALLO"], ["REF_SLICING"]),
     "slicing_zoeckler": (SLICING, ["ILLUM_ZOECKLER"], ["REF_SLICING"]),
+    # "// TODO: MC offset" builds (inc_header.glsl:14, lic3d_fragment.glsl:31-33, lic3d_slicing_fragment.glsl:31-33)
+    "raycast_none_mc": (RAYCAST, ["USE_MC_OFFSET"], []),
+    "raycast_gradient_mc": (RAYCAST, ["ILLUM_GRADIENT", "USE_MC_OFFSET"], []),
+    "slicing_none_mc": (SLICING, ["USE_MC_OFFSET"], ["REF_SLICING"]),
 }
 # Source-edit variants: the reference switches the TF index and the LIC gate by (un)commenting lines of
 # lic3d_fragment.glsl:53-61.  Each variant swaps the live expression for one of the alternatives the file itself lists.

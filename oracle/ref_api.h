@@ -26,6 +26,8 @@ typedef struct RefUniforms {
     float light_position[4];      /* gl_LightSource[0].position */
     float light_ambient[4], light_diffuse[4], light_specular[4];
     float spot_exponent;
+    RefTex mc_offset;             /* mcOffsetSampler: F_L32F [frame height][frame width] (USE_MC_OFFSET programs) */
+    int frag_x0, frag_y0, frag_w; /* fragment i of a run is pixel (frag_x0 + i % frag_w, frag_y0 + i / frag_w); frag_w = 0: unset */
 } RefUniforms;
 
 /* sets the gl_* state shared by all programs */

@@ -184,6 +184,18 @@ int vvref_noise_texture(const char *file, int use_gradient, unsigned char *out, 
     return copy_tex(nd.getTextureRef()->id, out, cap, dims, ifmt, wrap);
 }
 
+/* the same with the gradient cache left alone: an existing <noise>.grd is used (loadGradients, VV/gradient.cpp:112-149),
+ * otherwise the reference writes one (saveGradients, :152-187) and it stays on disk */
+int vvref_noise_texture_cached(const char *file, unsigned char *out, size_t cap, int dims[3], int *ifmt, int *wrap)
+{
+    NoiseDataSet nd;
+    if (!nd.loadData(file)) return -10;
+    if (!nd.getFileName()) return -11;
+    nd.enableGradient(true);
+    nd.createTexture("Noise_Tex", GL_TEXTURE3_ARB);
+    return copy_tex(nd.getTextureRef()->id, out, cap, dims, ifmt, wrap);
+}
+
 /* LICFilter: loadData(png) or createBoxFilter + createTexture (VV/3DLIC.cpp:725-731) */
 int vvref_filter_texture(const char *png, unsigned char *out, size_t cap, int *width, float *inv_area, int *wrap)
 {

@@ -25,6 +25,7 @@ def _L():
     L.vvref_vector_texture.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.vvref_noise_texture.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.vvref_noise_texture_cached.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.vvref_filter_texture.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.vvref_tf_textures.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.vvref_noise_gradients.argtypes = [ctypes.c_void_p] * 6
@@ -57,6 +58,16 @@ def noise_texture(path, shape, use_gradient):
     rc = _L().vvref_noise_texture(path.encode(), int(use_gradient), out.ctypes.data, out.nbytes, dims, ctypes.byref(ifmt), ctypes.byref(wrap))
     assert rc == out.nbytes, rc
     return out, ifmt.value, wrap.value
+
+
+def noise_texture_cached(path, shape):
+    """NoiseDataSet::createTexture with gradients, leaving / using the <path>.grd cache"""
+    out = np.zeros(tuple(shape) + (4,), np.uint8)
+    dims = (ctypes.c_int * 3)()
+    ifmt, wrap = ctypes.c_int(), ctypes.c_int()
+    rc = _L().vvref_noise_texture_cached(path.encode(), out.ctypes.data, out.nbytes, dims, ctypes.byref(ifmt), ctypes.byref(wrap))
+    assert rc == out.nbytes, rc
+    return out
 
 
 def filter_texture(png_path=None):

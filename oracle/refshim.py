@@ -29,7 +29,8 @@ class RefUniforms(ctypes.Structure):
         ("stepSize", ctypes.c_float), ("gradient", ctypes.c_float * 3), ("numIterations", ctypes.c_int),
         ("alphaCorrection", ctypes.c_float), ("licParams", ctypes.c_float * 3), ("licKernel", ctypes.c_float * 3),
         ("camera", ctypes.c_float * 4), ("light_position", ctypes.c_float * 4), ("light_ambient", ctypes.c_float * 4),
-        ("light_diffuse", ctypes.c_float * 4), ("light_specular", ctypes.c_float * 4), ("spot_exponent", ctypes.c_float)]
+        ("light_diffuse", ctypes.c_float * 4), ("light_specular", ctypes.c_float * 4), ("spot_exponent", ctypes.c_float),
+        ("mc_offset", RefTex), ("frag_x0", ctypes.c_int), ("frag_y0", ctypes.c_int), ("frag_w", ctypes.c_int)]
 
 
 _lib = None
@@ -113,6 +114,10 @@ class RefScene:
         u.light_diffuse = (ctypes.c_float * 4)(1, 1, 1, 1)
         u.light_specular = (ctypes.c_float * 4)(1, 1, 1, 1)
         u.spot_exponent = 40.0                                   # VV/3DLIC.cpp:736, VV/illumination.h:52
+        if getattr(s, "mc_offsets", None) is not None:
+            # mcOffsetSampler: GL_LUMINANCE16F_ARB rectangle texture, NEAREST (VV/renderer.cpp:636-679)
+            self.mc = vvo.half_round(np.ascontiguousarray(s.mc_offsets, dtype=np.float32).reshape(s.height, s.width))
+            u.mc_offset = _tex(self.mc, (s.width, s.height, 1), F_L32F, W_CLAMP_TO_EDGE)
         self.u = u
         self._set_scale(raycast=True)
 
@@ -140,6 +145,9 @@ class RefScene:
             if self.s.gate_mode == 1:
                 base += "_gatetf"
             tfm = {0: "", 1: "_tfa", 2: "_tfr", 3: "_tflength", 4: "_tfscalar"}[self.s.tf_mode]
+            if getattr(self.s, "mc_offsets", None) is not None:
+                assert base + tfm in ("raycast_none", "raycast_gradient"), "MC-offset variants are built for the .b / always-gate programs"
+                return base + "_mc"
             return base + tfm
         if kind == "licvol":
             if "ILLUM_GRADIENT" in d:
@@ -170,6 +178,7 @@ class RefScene:
         rect = rect or (0, 0, s.width, s.height)
         x0, y0, x1, y1 = rect
         self._set_scale(raycast=True)
+        self.u.frag_x0, self.u.frag_y0, self.u.frag_w = x0, y0, x1 - x0
         out, cnt = self._run(self.program("raycast"), self._rays(rect))
         img = np.zeros((s.height, s.width, 4), np.float32)
         cm = np.zeros((s.height, s.width), np.uint32)
@@ -187,7 +196,11 @@ class RefScene:
         for k, v in (("ILLUM_GRADIENT", "gradient"), ("ILLUM_MALLO", "mallo"), ("ILLUM_ZOECKLER", "zoeckler")):
             if k in d:
                 prog = "slicing_" + v
+        if getattr(s, "mc_offsets", None) is not None:
+            assert prog == "slicing_none"
+            prog = "slicing_none_mc"
         self._set_scale(raycast=True)
+        self.u.frag_x0, self.u.frag_y0, self.u.frag_w = 0, 0, s.width
         L = lib()
         _, _, nslices = self.o.slicing_setup()
         frags, starts = [], [0]

@@ -366,11 +366,58 @@ bool pixel_ray(const Ctx &c, int px, int py, V3 &entry)
         if (t1 < tf) tf = t1;
     }
     /* front faces only (back faces culled, renderer.cpp:1099): camera must be outside the box */
-    if (!(tn < tf) || tn <= 0.0 || face < 0) return false;
-    double p[3] = {o[0] + tn * d[0], o[1] + tn * d[1], o[2] + tn * d[2]};
-    p[face] = faceval;
-    for (int i = 0; i < 3; ++i)
-        p[i] = std::min(std::max(p[i], 0.0), (double)s->extent[i]);
+    bool have = (tn < tf) && tn > 0.0 && face >= 0;
+    double p[3] = {0.0, 0.0, 0.0};
+    if (have) {
+        for (int i = 0; i < 3; ++i) p[i] = o[i] + tn * d[i];
+        p[face] = faceval;
+        for (int i = 0; i < 3; ++i)
+            p[i] = std::min(std::max(p[i], 0.0), (double)s->extent[i]);
+    }
+    const int nc = s->num_clip_planes;
+    if (nc > 0) {
+        /* User clip planes.  Renderer::render enables them around the whole draw (renderer.cpp:156-163, 199): GL discards
+         * the part of the cube's front faces with n.q + d < 0 (q = position relative to the volume centre).
+         * drawClippedPolygon (renderer.cpp:1294-1309) then draws, per active plane in order, the box's cross-section
+         * n^.q = -(d - 0.0001) (ClipPlane / ViewSlicing::drawSingleSlice, slicing.cpp:368-560) with texcoord = position;
+         * it is wound to face viewers looking along +n and back faces are culled; the other planes clip it too.  No depth
+         * test and no blending in the FBO (renderer.cpp:1097-1101): the last fragment drawn under a pixel is the one the
+         * shader's result is kept for. */
+        double ctr[3] = {s->center[0], s->center[1], s->center[2]};
+        auto kept = [&](const double q[3], int skip) {
+            for (int j = 0; j < nc; ++j) {
+                if (j == skip) continue;
+                const double *e = s->clip_planes[j];
+                if (e[0] * q[0] + e[1] * q[1] + e[2] * q[2] + e[3] < 0.0) return false;
+            }
+            return true;
+        };
+        if (have) {
+            double q[3] = {p[0] - ctr[0], p[1] - ctr[1], p[2] - ctr[2]};
+            have = kept(q, -1);
+        }
+        double oc[3] = {o[0] - ctr[0], o[1] - ctr[1], o[2] - ctr[2]};
+        for (int i = 0; i < nc; ++i) {
+            const double *e = s->clip_planes[i];
+            double len = std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+            if (!(len > 1e-8)) continue;                                   /* VS_EPS, slicing.h */
+            double n[3] = {e[0] / len, e[1] / len, e[2] / len};
+            double dist = -(e[3] - 0.0001);
+            double dn = n[0] * d[0] + n[1] * d[1] + n[2] * d[2];
+            if (!(dn > 0.0)) continue;                                     /* cap faces away from the viewer: culled */
+            double t = (dist - (n[0] * oc[0] + n[1] * oc[1] + n[2] * oc[2])) / dn;
+            if (!(t > 0.0)) continue;
+            double q[3] = {oc[0] + t * d[0], oc[1] + t * d[1], oc[2] + t * d[2]};
+            bool inside = true;
+            for (int k = 0; k < 3; ++k)
+                if (std::fabs(q[k]) > 0.5 * (double)s->extent[k]) inside = false;
+            if (!inside || !kept(q, i)) continue;
+            have = true;
+            for (int k = 0; k < 3; ++k)
+                p[k] = std::min(std::max(q[k] + 0.5 * (double)s->extent[k], 0.0), (double)s->extent[k]);
+        }
+    }
+    if (!have) return false;
     entry = {(float)p[0], (float)p[1], (float)p[2]};
     return true;
 }
@@ -442,6 +489,12 @@ inline bool slice_fragment(const Ctx &c, const Slicing &sl, const PixelRay &r, i
     for (int i = 0; i < 3; ++i) {
         p[i] = r.o[i] + t * r.d[i];
         if (p[i] < 0.0 || p[i] > (double)s->extent[i]) return false;
+    }
+    /* user clip planes are enabled around sliceVolume too (renderer.cpp:156-163): the slice polygons are clipped */
+    for (int j = 0; j < s->num_clip_planes; ++j) {
+        const double *e = s->clip_planes[j];
+        double q[3] = {p[0] - (double)s->center[0], p[1] - (double)s->center[1], p[2] - (double)s->center[2]};
+        if (e[0] * q[0] + e[1] * q[1] + e[2] * q[2] + e[3] < 0.0) return false;
     }
     geomPos = {(float)p[0], (float)p[1], (float)p[2]};
     return true;
@@ -635,7 +688,7 @@ inline bool outside_box(const Ctx &c, V3 pos)
 
 /* main() of lic3d_fragment.glsl:5-99 for one fragment */
 template <bool GRAD>
-V4 frag_raycast_lic(const Ctx &c, V3 geomPos, uint32_t &nsamples)
+V4 frag_raycast_lic(const Ctx &c, V3 geomPos, uint32_t &nsamples, float mc)
 {
     bool outside = false;
     V3 pos = geomPos * c.scaleVol;                                         /* :14 */
@@ -643,6 +696,7 @@ V4 frag_raycast_lic(const Ctx &c, V3 geomPos, uint32_t &nsamples)
     V3 dir = geomDir * c.scaleVol;                                         /* :21 */
     V4 dest = {0, 0, 0, 0}, src = {0, 0, 0, 0};
     nsamples = 0;
+    if (mc >= 0.0f) pos = pos + dir * c.stepSize * mc;                     /* :31-33 USE_MC_OFFSET */
     for (int j = 0; !outside && j < c.numIterations; ++j) {                /* :38 */
         for (int i = 0; i < c.numIterations; ++i) {                        /* :40 */
             ++nsamples;
@@ -704,7 +758,7 @@ V4 frag_raycast_licvolume(const Ctx &c, V3 geomPos, uint32_t &nsamples)
 /* main() of lic3d_slicing_fragment.glsl:5-74 for one fragment; dest = the frame buffer under the fragment
  * (imageFBOSampler, :11).  The shader hard-codes TF index .a and gate tfData.a > 0.05; tf_mode / gate_mode select them here. */
 template <bool GRAD>
-V4 frag_slicing(const Ctx &c, V3 geomPos, V4 dest, bool &shaded)
+V4 frag_slicing(const Ctx &c, V3 geomPos, V4 dest, bool &shaded, float mc)
 {
     V4 src = {0, 0, 0, 0};
     shaded = false;
@@ -713,6 +767,7 @@ V4 frag_slicing(const Ctx &c, V3 geomPos, V4 dest, bool &shaded)
         V3 pos = geomPos * c.scaleVol;                                     /* :18 */
         V3 geomDir = normalize(geomPos - c.camera);                        /* :24 */
         V3 dir = geomDir * c.scaleVol;                                     /* :25 */
+        if (mc >= 0.0f) pos = pos + dir * c.stepSize * mc;                 /* :31-33 USE_MC_OFFSET */
         V4 vectorData = texVolume(c, pos);                                 /* :36 */
         V4 scalarData = {0, 0, 0, 1};
         if (c.s->tf_mode == VVO_TF_SCALAR) scalarData = texScalar(c, pos);
@@ -748,7 +803,8 @@ uint64_t for_pixels(const VVOScene *s, int x0, int y0, int x1, int y1, float *ou
             V3 entry;
             V4 col = {0, 0, 0, 0};
             uint32_t n = 0;
-            if (pixel_ray(c, x, y, entry)) col = frag(c, entry, n);
+            const float mc = s->mc_offsets ? s->mc_offsets[(size_t)y * s->width + x] : -1.0f;
+            if (pixel_ray(c, x, y, entry)) col = frag(c, entry, n, mc);
             float *o = out_rgba + 4 * ((size_t)y * s->width + x);
             o[0] = col.x; o[1] = col.y; o[2] = col.z; o[3] = col.w;
             if (out_samples) out_samples[(size_t)y * s->width + x] = n;
@@ -767,9 +823,9 @@ uint64_t vvo_raycast_lic_rect(const VVOScene *s, int x0, int y0, int x1, int y1,
     bool grad = (s->illum_mode == VVO_ILLUM_GRADIENT);   /* ILLUM_GRADIENT => USE_NOISE_GRADIENTS (inc_header.glsl:17-19) */
     if (grad)
         return for_pixels(s, x0, y0, x1, y1, out_rgba, out_samples,
-                          [](const Ctx &c, V3 e, uint32_t &n) { return frag_raycast_lic<true>(c, e, n); });
+                          [](const Ctx &c, V3 e, uint32_t &n, float mc) { return frag_raycast_lic<true>(c, e, n, mc); });
     return for_pixels(s, x0, y0, x1, y1, out_rgba, out_samples,
-                      [](const Ctx &c, V3 e, uint32_t &n) { return frag_raycast_lic<false>(c, e, n); });
+                      [](const Ctx &c, V3 e, uint32_t &n, float mc) { return frag_raycast_lic<false>(c, e, n, mc); });
 }
 
 uint64_t vvo_raycast_lic(const VVOScene *s, float *out_rgba, uint32_t *out_samples)
@@ -780,7 +836,7 @@ uint64_t vvo_raycast_lic(const VVOScene *s, float *out_rgba, uint32_t *out_sampl
 uint64_t vvo_raycast_licvolume(const VVOScene *s, float *out_rgba, uint32_t *out_samples)
 {
     return for_pixels(s, 0, 0, s->width, s->height, out_rgba, out_samples,
-                      [](const Ctx &c, V3 e, uint32_t &n) { return frag_raycast_licvolume(c, e, n); }, false);
+                      [](const Ctx &c, V3 e, uint32_t &n, float) { return frag_raycast_licvolume(c, e, n); }, false);
 }
 
 /* Renderer::sliceVolume (renderer.cpp:1123-1267): numSlices view-aligned polygons drawn front to back, each fragment
@@ -799,11 +855,12 @@ uint64_t vvo_slicing_lic(const VVOScene *s, float *out_rgba, uint32_t *out_sampl
             PixelRay r = pixel_dir(c, x, y);
             V4 dest = {0, 0, 0, 0};
             uint32_t n = 0;
+            const float mc = s->mc_offsets ? s->mc_offsets[(size_t)y * s->width + x] : -1.0f;
             for (int i = 0; i < sl.numSlices; ++i) {
                 V3 g;
                 if (!slice_fragment(c, sl, r, i, g)) continue;
                 bool shaded;
-                dest = grad ? frag_slicing<true>(c, g, dest, shaded) : frag_slicing<false>(c, g, dest, shaded);
+                dest = grad ? frag_slicing<true>(c, g, dest, shaded, mc) : frag_slicing<false>(c, g, dest, shaded, mc);
                 if (shaded) ++n;
             }
             float *o = out_rgba + 4 * ((size_t)y * s->width + x);

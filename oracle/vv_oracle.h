@@ -70,6 +70,11 @@ typedef struct VVOScene {
     int speed_of_flow;         /* inc_lic.glsl:108-110,120-122 */
     int licvol_fp16;           /* Q14: LIC volume stored as RGBA16F */
     int weight_bits;           /* 0: exact fp32 lerp weights; 8: quantise f to 8 fractional bits (B.6) */
+    /* SURVEY 8(f) N4 */
+    const float *mc_offsets;   /* USE_MC_OFFSET (lic3d_fragment.glsl:31-33, renderer.cpp:636-679): [height][width] ray-start
+                                  offsets in [0,1], already fp16-rounded (GL_LUMINANCE16F rectangle texture); NULL = off */
+    int    num_clip_planes;    /* active user clip planes (transform.cpp:424-449, renderer.cpp:156-163,1294-1309) */
+    double clip_planes[3][4];  /* glClipPlane equations (n.xyz, d) in volume-centred object space: n.q + d >= 0 is kept */
 } VVOScene;
 
 /* ---- hot path ------------------------------------------------------- */

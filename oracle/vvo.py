@@ -40,6 +40,7 @@ class Scene(ctypes.Structure):
         ("illum_mode", ctypes.c_int), ("tf_mode", ctypes.c_int), ("gate_mode", ctypes.c_int), ("noise_gate", ctypes.c_int),
         ("lowres", ctypes.c_int), ("quirk_scalevolinv", ctypes.c_int), ("quirk_luminance_alpha", ctypes.c_int),
         ("speed_of_flow", ctypes.c_int), ("licvol_fp16", ctypes.c_int), ("weight_bits", ctypes.c_int),
+        ("mc_offsets", ctypes.c_void_p), ("num_clip_planes", ctypes.c_int), ("clip_planes", (ctypes.c_double * 4) * 3),
     ]
 
 
@@ -153,6 +154,11 @@ def illum_tables(spec_exp=40.0, w=256, h=256):
     return z, d, s
 
 
+def half_round(a):
+    """float32 -> fp16 -> float32 (round to nearest even), the GL_*16F upload rounding"""
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32).astype(np.float16).astype(np.float32))
+
+
 def default_tf():
     out = np.empty((256, 5), dtype=np.uint8)
     lib().vvo_default_tf(_p(out))
@@ -216,6 +222,15 @@ class OracleScene:
         c.quirk_luminance_alpha = 0 if s.with_gradients else s.quirk_luminance_alpha   # Q7 only bites GL_LUMINANCE noise
         c.speed_of_flow = 1 if "SPEED_OF_FLOW" in (s.defines or "") else 0
         c.licvol_fp16 = s.licvol_fp16; c.weight_bits = weight_bits
+        if getattr(s, "mc_offsets", None) is not None:
+            assert "USE_MC_OFFSET" in (s.defines or ""), "mc_offsets need #define USE_MC_OFFSET"
+            self.mc = half_round(np.ascontiguousarray(s.mc_offsets, dtype=np.float32).reshape(s.height, s.width))
+            c.mc_offsets = self.mc.ctypes.data
+        planes = list(getattr(s, "clip_planes", ()) or ())
+        c.num_clip_planes = len(planes)
+        for i, e in enumerate(planes):
+            for k in range(4):
+                c.clip_planes[i][k] = float(e[k])
         if illum_tables is not None:
             self.illum_tables = [np.ascontiguousarray(t, dtype=np.float32) for t in illum_tables]
             for i, t in enumerate(self.illum_tables):

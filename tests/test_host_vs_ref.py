@@ -3,6 +3,7 @@ DAT reader, argument parser, quaternion helpers) against that host code itself, 
 /root/reference against a capturing GL stub (oracle/_ref, oracle/ref_host_driver.cpp).  Also checks the product's
 host-only loaders (vv_parse_dat / vv_parse_args / vv_png_read) against the reference's."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -65,6 +66,32 @@ def test_noise_gradients(oracle, tmp_path, shape):
     oracle.lib().vvo_filter_gradients_f(dims, oracle._p(og))
     assert np.array_equal(og.view(np.uint32), f.view(np.uint32))
     assert np.array_equal(oracle.noise_gradients(noise), q)
+
+
+def test_gradient_cache_file(oracle, tmp_path):
+    """.grd cache (VV/gradient.cpp:93-187, VV/dataset.cpp:1238-1267): the product reads what the reference's saveGradients
+    writes, and the reference's loadGradients reads what the product writes"""
+    import vectorvisualization_b200 as vv
+    from vectorvisualization_b200 import fields as F
+    shape = (9, 14, 11)
+    noise = np.random.RandomState(5).randint(0, 256, size=shape).astype(np.uint8)
+    path = F.write_noise(str(tmp_path / "noise"), noise)
+    dims = shape[::-1]
+    with pytest.raises(RuntimeError):
+        vv.grd_read(path, dims)                                   # no cache yet
+    ref = refhost.noise_texture_cached(path, shape)               # the reference computes and saves <path>.grd
+    assert os.path.getsize(path + ".grd") == 3 * noise.size
+    got = vv.grd_read(path, dims)
+    assert np.array_equal(got, oracle.noise_gradients(noise)) and np.array_equal(got, ref[..., :3])
+    # the other direction: a cache written by the product is what the reference loads (sentinel values prove it is used)
+    sentinel = np.random.RandomState(6).randint(0, 256, size=shape + (3,)).astype(np.uint8)
+    vv.grd_write(path, sentinel)
+    ref2 = refhost.noise_texture_cached(path, shape)
+    assert np.array_equal(ref2[..., :3], sentinel) and np.array_equal(ref2[..., 3], noise)
+    with open(path + ".grd", "r+b") as f:
+        f.truncate(10)
+    with pytest.raises(RuntimeError):
+        vv.grd_read(path, dims)                                   # short file: "Reading gradients ... failed"
 
 
 def test_filter_kernels(oracle, tmp_path):

@@ -200,3 +200,68 @@ def test_background_and_rgba8_store(oracle):
     assert np.allclose(bg[0], [0.7, 0.6, 0.5, 1.0]) and np.allclose(bg[2], 1.0)
     q = oracle.quantize_rgba8(rgba)
     assert list(q[3]) == [128, 127, 255, 0]
+
+
+def _entries(oracle, s):
+    o = oracle.OracleScene(s)
+    out = np.zeros((s.height, s.width, 4), np.float32)
+    oracle.lib().vvo_pixel_rays(ctypes.byref(o.c), 0, 0, s.width, s.height, oracle._p(out))
+    return o, out
+
+
+def test_clip_planes_entry_points(oracle):
+    """user clip planes (VV/renderer.cpp:156-163, 1294-1309): clipped front faces, cap polygon n.q = -(d - 1e-4) as the new
+    entry when it faces the viewer, nothing when it faces away"""
+    from vectorvisualization_b200 import configs
+    s = configs.cfg1(n=8, size=48)
+    o0, e0 = _entries(oracle, s)
+    ext = np.array(list(o0.c.extent), np.float64)
+    ctr = np.array(list(o0.c.center), np.float64)
+    hit0 = e0[..., 3] > 0
+    assert hit0.sum() > 200
+    # the default camera looks down -z of the volume: rays travel in -z, i.e. along n = (0,0,-1)
+    # a plane that keeps everything changes nothing
+    s.clip_planes = ((0.0, 0.0, -1.0, 10.0),)
+    _, e = _entries(oracle, s)
+    assert np.array_equal(e, e0)
+    # keep z' <= 0.1 (q relative to the centre): the near part is cut away, rays now start on the cap 1e-4 inside the plane
+    s.clip_planes = ((0.0, 0.0, -1.0, 0.1),)
+    _, e = _entries(oracle, s)
+    hit = e[..., 3] > 0
+    q = e[..., :3].astype(np.float64) - ctr
+    on_cap = hit & (np.abs(-q[..., 2] + 0.1 - 1e-4) < 1e-6)
+    assert on_cap.sum() > 200 and on_cap.sum() == hit.sum()        # every visible ray enters through the cap
+    assert (np.abs(q[hit][:, 0]) <= ext[0] / 2 + 1e-6).all() and (np.abs(q[hit][:, 1]) <= ext[1] / 2 + 1e-6).all()
+    assert not (hit & ~hit0).any()                                 # the cap lies inside the box silhouette
+    # the opposite half-space: the front faces survive only where they are kept, the cap faces away and is culled
+    s.clip_planes = ((0.0, 0.0, 1.0, 0.1),)
+    _, e = _entries(oracle, s)
+    hit = e[..., 3] > 0
+    q = e[..., :3].astype(np.float64) - ctr
+    assert hit.sum() > 0 and (q[hit][:, 2] + 0.1 >= -1e-6).all()
+    assert np.array_equal(e[hit], e0[hit])                         # surviving fragments are the unclipped front-face fragments
+    # two planes: the cap of plane 0 is itself clipped by plane 1
+    s.clip_planes = ((0.0, 0.0, -1.0, 0.1), (1.0, 0.0, 0.0, 0.0))
+    _, e = _entries(oracle, s)
+    hit = e[..., 3] > 0
+    q = e[..., :3].astype(np.float64) - ctr
+    assert hit.sum() > 50 and (q[hit][:, 0] >= -1e-6).all()
+
+
+def test_clip_planes_shorten_rays_and_clip_slices(oracle):
+    import vectorvisualization_b200 as vv
+    from vectorvisualization_b200 import configs
+    s = configs.cfg1(n=8, size=33)
+    s.params.update(stepSizeVol=1 / 64)
+    _, cnt0, _ = oracle.OracleScene(s).raycast(rect=(16, 16, 17, 17))
+    s.clip_planes = ((0.0, 0.0, -1.0, 0.0),)                        # keep the far half: the central ray is half as long
+    _, cnt1, _ = oracle.OracleScene(s).raycast(rect=(16, 16, 17, 17))
+    assert abs(int(cnt1[16, 16]) - (int(cnt0[16, 16]) + 1) // 2) <= 1
+    # slicing: the slices in the clipped half-space produce no fragments
+    s.technique = vv.VOLIC_SLICING
+    s.tf_mode, s.gate_mode = vv.TF_A, vv.GATE_ALWAYS
+    s.clip_planes = ()
+    _, c0, t0 = oracle.OracleScene(s).slicing()
+    s.clip_planes = ((0.0, 0.0, -1.0, 0.0),)
+    _, c1, t1 = oracle.OracleScene(s).slicing()
+    assert 0 < t1 < t0 and abs(int(c1[16, 16]) - int(c0[16, 16]) / 2) <= 1.5

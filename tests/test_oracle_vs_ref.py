@@ -98,3 +98,33 @@ def test_lic_volume_and_volume_raycast_bit_exact(oracle, name):
     b, cb, tb = r.raycast_licvolume(lo)
     assert ta == tb and np.array_equal(ca, cb)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_mc_offset_builds_bit_exact(oracle):
+    """USE_MC_OFFSET programs (inc_header.glsl:14; lic3d_fragment.glsl:31-33, lic3d_slicing_fragment.glsl:31-33): the ray /
+    fragment start is jittered by dir * stepSize * mcOffset[pixel]"""
+    import vectorvisualization_b200 as vv
+    from vectorvisualization_b200 import configs
+    def plain():
+        return configs.cfg1(n=24, size=48)
+    def grad():
+        s = configs.cfg3(n=24, size=40)
+        s.tf_mode = vv.TF_B
+        return s
+    def slicing():
+        s = configs.cfg1(n=24, size=40)
+        s.technique = vv.VOLIC_SLICING
+        s.tf_mode, s.gate_mode = vv.TF_A, vv.GATE_TF_ALPHA
+        return s
+    for i, mk in enumerate((plain, grad, slicing)):
+        s = mk()
+        base = oracle.OracleScene(s)
+        base = base.slicing() if s.technique == vv.VOLIC_SLICING else base.raycast()
+        s.defines = (s.defines or "") + "\n#define USE_MC_OFFSET"
+        s.mc_offsets = np.random.RandomState(3 + i).rand(s.height, s.width).astype(np.float32)
+        o, r = oracle.OracleScene(s), refshim.RefScene(s)
+        a, ca, ta = o.slicing() if s.technique == vv.VOLIC_SLICING else o.raycast()
+        b, cb, tb = r.slicing() if s.technique == vv.VOLIC_SLICING else r.raycast()
+        assert ta == tb and ta > 0 and np.array_equal(ca, cb)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "max abs diff %g" % np.abs(a - b).max()
+        assert not np.array_equal(a, base[0])                      # the offsets do move the samples

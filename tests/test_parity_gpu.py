@@ -196,6 +196,106 @@ def test_slicing_parity(vv, oracle, define):
         assert_image_parity(oracle, img, ref, "slicing " + define)
 
 
+def test_mc_offset_parity(vv, oracle):
+    """USE_MC_OFFSET builds: jittered ray starts for the ray-cast programs and the slicing program"""
+    from vectorvisualization_b200 import configs, fields as F
+    def plain():
+        return configs.cfg1(n=32, size=80)
+    def grad():
+        return configs.cfg3(n=40, size=96, camera=F.CAMERA_CLOSE)
+    def slicing():
+        s = configs.cfg2(n=40, size=75)
+        s.technique = vv.VOLIC_SLICING
+        s.tf_mode, s.gate_mode = vv.TF_A, vv.GATE_TF_ALPHA
+        s.tf = F.default_tf()
+        return s
+    for i, mk in enumerate((plain, grad, slicing)):
+        s = mk()
+        _, base, _, _, _ = render_cuda(vv, s)
+        s.defines = (s.defines or "") + "\n#define USE_MC_OFFSET"
+        s.mc_offsets = np.random.RandomState(11 + i).rand(s.height, s.width).astype(np.float32)
+        o = oracle.OracleScene(s)
+        ref, ref_cnt, ref_tot = o.slicing() if s.technique == vv.VOLIC_SLICING else o.raycast()
+        r, img, _, cnt, tot = render_cuda(vv, s)
+        assert int((cnt != ref_cnt).sum()) <= max(1, cnt.size // 20000)
+        assert_image_parity(oracle, img, ref, "mc offset %d" % i)
+        assert not np.array_equal(img, base)
+        # per-ray kernel (VV_OPT_RAYCAST_MODE 0) applies the same offsets
+        if s.technique != vv.VOLIC_SLICING:
+            r.setOption(vv.OPT_RAYCAST_MODE, 0)
+            r.render(True)
+            # (the two kernels inline the shading code separately: fused-multiply-add contraction may differ by an ulp)
+            assert np.abs(r.readRGBA32F() - img).max() <= 2e-5
+        # a define without a texture is the plain program (an unbound sampler reads 0)
+        r.setMCOffsets(None)
+        r.setOption(vv.OPT_RAYCAST_MODE, 1)
+        r.render(True)
+        assert np.array_equal(r.readRGBA32F(), base)
+    # the generator fills a frame-sized texture with values in [0,1]; a wrong size is refused at render time
+    r = vv.Renderer(0)
+    s = plain()
+    s.defines = "#define USE_MC_OFFSET"
+    configs.apply_scene(r, s)
+    r.updateMCOffsetTex(s.width, s.height, 5)
+    r.render(True)
+    assert not np.array_equal(r.readRGBA32F(), render_cuda(vv, plain())[1])
+    r.updateMCOffsetTex(s.width + 1, s.height, 5)
+    with pytest.raises(vv.VVError):
+        r.render(True)
+
+
+@pytest.mark.parametrize("planes", [((0.0, 0.0, -1.0, 0.1),), ((0.0, 0.0, 1.0, 0.1),), ((0.3, 0.5, -0.8, 0.05), (1.0, 0.0, 0.0, 0.12)),
+                                    ((0.0, 0.0, -1.0, 0.2), (0.6, -0.8, 0.0, 0.1), (0.0, 1.0, 0.0, 0.3))])
+def test_clip_planes_parity(vv, oracle, planes):
+    """user clip planes: clipped front faces + cap polygons for the ray-cast techniques, clipped slices"""
+    from vectorvisualization_b200 import configs, fields as F
+    from vectorvisualization_b200.configs import apply_scene
+    cam = dict(quat=F.quat_from_axis_angle((0.3, -1.0, 0.2), 40.0), pos=(0.05, 0.0, 0.1), dist=3.0, fovy=35.0)
+    for mk in (lambda: configs.cfg1(n=32, size=96), lambda: configs.cfg3(n=40, size=88, camera=cam)):
+        s = mk()
+        _, base, _, base_cnt, _ = render_cuda(vv, s)
+        s.clip_planes = planes
+        ref, ref_cnt, ref_tot = oracle.OracleScene(s).raycast()
+        r, img, _, cnt, tot = render_cuda(vv, s)
+        assert np.array_equal(cnt > 0, ref_cnt > 0)                          # same set of covered pixels
+        assert int((cnt != ref_cnt).sum()) <= max(1, cnt.size // 20000)
+        assert_image_parity(oracle, img, ref, "clip raycast")
+        # (a plane whose kept side contains the whole front of the box changes nothing: rays still leave through the box)
+        assert planes[0][2] > 0 or not np.array_equal(cnt, base_cnt)
+        r.setOption(vv.OPT_RAYCAST_MODE, 0)
+        r.render(True)
+        assert np.abs(r.readRGBA32F() - img).max() <= 2e-5
+        # deactivating the planes restores the unclipped frame
+        for i in range(3):
+            r.setClipPlane(i, None, False)
+        r.setOption(vv.OPT_RAYCAST_MODE, 1)
+        r.render(True)
+        assert np.array_equal(r.readRGBA32F(), base)
+    # slicing: the slice polygons are clipped
+    s = configs.cfg2(n=40, size=75)
+    s.technique = vv.VOLIC_SLICING
+    s.tf_mode, s.gate_mode = vv.TF_A, vv.GATE_TF_ALPHA
+    s.tf = F.default_tf()
+    s.clip_planes = planes
+    ref, ref_cnt, ref_tot = oracle.OracleScene(s).slicing()
+    _, img, _, cnt, tot = render_cuda(vv, s)
+    assert int((cnt != ref_cnt).sum()) <= max(1, cnt.size // 20000)
+    assert_image_parity(oracle, img, ref, "clip slicing")
+    # LIC-volume technique: the plain ray-cast over the precomputed volume starts at the same entry points
+    s = configs.cfg1(n=32, size=96)
+    s.technique = vv.VOLIC_LICVOLUME
+    s.params.update(gradientScale=4.0)
+    s.clip_planes = planes
+    o = oracle.OracleScene(s)
+    r = vv.Renderer(0)
+    apply_scene(r, s)
+    r.setOption(vv.OPT_SAMPLE_MAP, 1)
+    r.render(True)
+    ref, ref_cnt, _ = o.raycast_licvolume(r.readLICVolume())
+    assert int((r.readSampleMap() != ref_cnt).sum()) <= 1
+    assert_image_parity(oracle, r.readRGBA32F(), ref, "clip volume raycast")
+
+
 def test_slicing_default_modes(vv):
     """selecting VOLIC_SLICING switches to the slicing program's own TF index / gate (Q5, Q6) without touching the ray-cast ones"""
     from vectorvisualization_b200 import configs
@@ -453,6 +553,32 @@ def test_file_loaders_roundtrip(vv, oracle, tmp_path):
     r.savePNG(out)
     back = vv.png_read(out)
     assert np.array_equal(back[::-1], r.readRGBA8())
+
+
+def test_noise_gradient_cache(vv, oracle, tmp_path):
+    """vv_load_noise(-g): computes the gradients on the GPU and stores <noise>.grd like NoiseDataSet::createTexture
+    (VV/dataset.cpp:1238-1267); a second load uses the stored file (sentinel values prove it)"""
+    import os
+    from vectorvisualization_b200 import fields as F
+    shape = (12, 10, 14)
+    noise = np.random.RandomState(8).randint(0, 256, size=shape).astype(np.uint8)
+    path = F.write_noise(str(tmp_path / "noise"), noise)
+    r = vv.Renderer(0)
+    r.loadNoise(path, True)
+    want = oracle.noise_gradients(noise)
+    assert os.path.getsize(path + ".grd") == 3 * noise.size
+    assert np.array_equal(vv.grd_read(path, shape[::-1]), want)
+    assert np.array_equal(r.readNoiseTexture(shape, 4), oracle.pack_noise_rgba(noise, want))
+    sentinel = np.random.RandomState(9).randint(0, 256, size=shape + (3,)).astype(np.uint8)
+    vv.grd_write(path, sentinel)
+    r.loadNoise(path, True)
+    tex = r.readNoiseTexture(shape, 4)
+    assert np.array_equal(tex[..., :3], sentinel) and np.array_equal(tex[..., 3], noise)
+    assert np.array_equal(r.readNoiseGradients(shape), sentinel)
+    # the in-memory entry point gives the same texture
+    r2 = vv.Renderer(0)
+    r2.setNoiseWithGradients(noise, sentinel)
+    assert np.array_equal(r2.readNoiseTexture(shape, 4), tex)
 
 
 def _golden_names():

@@ -84,6 +84,8 @@ def load_library():
         "vv_set_camera": ([P, ctypes.POINTER(F), ctypes.POINTER(F), F, F, F, F], I),
         "vv_set_light": ([P, ctypes.POINTER(F), F], I), "vv_update_light_pos": ([P], I),
         "vv_enable_lowres": ([P, I], I), "vv_enable_float_target": ([P, I], I), "vv_set_option": ([P, I, I], I),
+        "vv_set_mc_offsets": ([P, P, I, I], I), "vv_update_mc_offset_tex": ([P, I, I, ctypes.c_uint32], I),
+        "vv_set_clip_plane": ([P, I, P, I], I),
         "vv_render": ([P, I], I), "vv_read_rgba8": ([P, P, ctypes.c_size_t], I), "vv_read_rgba32f": ([P, P, ctypes.c_size_t], I),
         "vv_read_display_rgba8": ([P, P, ctypes.c_size_t], I),
         "vv_read_lic_volume": ([P, P, ctypes.c_size_t, ctypes.POINTER(I)], I),
@@ -100,6 +102,8 @@ def load_library():
         "vv_parse_dat": ([CP, ctypes.POINTER(DatInfo)], I), "vv_read_raw": ([ctypes.POINTER(DatInfo), I, P, ctypes.c_size_t], I),
         "vv_load_dat": ([P, CP], I), "vv_load_scalar_dat": ([P, CP], I), "vv_load_noise": ([P, CP, I], I),
         "vv_load_filter_png": ([P, CP], I), "vv_load_tf_png": ([P, CP], I),
+        "vv_grd_read": ([CP, P, P], I), "vv_grd_write": ([CP, P, P], I),
+        "vv_set_noise_with_gradients": ([P, P, P, P], I), "vv_read_noise_gradients": ([P, P, ctypes.c_size_t], I),
         "vv_parse_args": ([I, ctypes.POINTER(CP), ctypes.POINTER(Args)], I), "vv_usage": ([], CP),
         "vv_png_read": ([CP, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)), ctypes.POINTER(I), ctypes.POINTER(I), ctypes.POINTER(I)], I),
         "vv_free": ([P], None), "vv_png_write": ([CP, P, I, I, I], I),
@@ -148,6 +152,22 @@ def make_illum_tables(spec_exp=40.0, width=256, height=256):
     s = np.zeros((height, width), np.float32)
     _chk(lib.vv_make_illum_tables(spec_exp, width, height, _ptr(z), _ptr(d), _ptr(s)))
     return z, d, s
+
+
+def grd_read(file_name, dims):
+    """loadGradients(DATRAW_UCHAR), VV/gradient.cpp:112-149: "<file_name>.grd" -> uint8 [nz][ny][nx][3]; dims = (nx, ny, nz)"""
+    lib = load_library()
+    out = np.empty((dims[2], dims[1], dims[0], 3), np.uint8)
+    _chk(lib.vv_grd_read(file_name.encode(), (ctypes.c_int * 3)(*dims), _ptr(out)))
+    return out
+
+
+def grd_write(file_name, gradients):
+    """saveGradients(DATRAW_UCHAR), VV/gradient.cpp:152-187; gradients uint8 [nz][ny][nx][3]"""
+    lib = load_library()
+    g = np.ascontiguousarray(gradients, dtype=np.uint8)
+    nz, ny, nx = g.shape[:3]
+    _chk(lib.vv_grd_write(file_name.encode(), (ctypes.c_int * 3)(nx, ny, nz), _ptr(g)))
 
 
 def png_read(path):
@@ -269,6 +289,22 @@ class Renderer:
     def enableLowRes(self, enable):
         _chk(self._lib.vv_enable_lowres(self._h, int(enable)))
 
+    def setMCOffsets(self, offsets):
+        """Renderer::updateMCOffsetTex with explicit values: float32 [height][width] in [0,1] (None removes the texture)"""
+        if offsets is None:
+            _chk(self._lib.vv_set_mc_offsets(self._h, None, 0, 0))
+            return
+        a = np.ascontiguousarray(offsets, dtype=np.float32)
+        _chk(self._lib.vv_set_mc_offsets(self._h, _ptr(a), a.shape[1], a.shape[0]))
+
+    def updateMCOffsetTex(self, width, height, seed=0):
+        _chk(self._lib.vv_update_mc_offset_tex(self._h, width, height, seed))
+
+    def setClipPlane(self, index, equation, active=True):
+        """ClipPlane::setNormal(x, y, z, d) + activation; n.q + d >= 0 is kept (q relative to the volume centre)"""
+        eq = (ctypes.c_double * 4)(*equation) if equation is not None else None
+        _chk(self._lib.vv_set_clip_plane(self._h, index, eq, int(active)))
+
     def enableFBO(self, enable):
         _chk(self._lib.vv_enable_float_target(self._h, int(enable)))
 
@@ -284,6 +320,19 @@ class Renderer:
 
     def loadNoise(self, path, with_gradients=False):
         _chk(self._lib.vv_load_noise(self._h, path.encode(), int(with_gradients)))
+
+    def setNoiseWithGradients(self, noise, gradients):
+        """noise uint8 [nz][ny][nx] + quantised gradients uint8 [nz][ny][nx][3] (the .grd contents)"""
+        a = np.ascontiguousarray(noise, dtype=np.uint8)
+        g = np.ascontiguousarray(gradients, dtype=np.uint8)
+        nz, ny, nx = a.shape
+        assert g.shape == (nz, ny, nx, 3)
+        _chk(self._lib.vv_set_noise_with_gradients(self._h, _ptr(a), _ptr(g), (ctypes.c_int * 3)(nx, ny, nz)))
+
+    def readNoiseGradients(self, shape):
+        out = np.empty(tuple(shape) + (3,), dtype=np.uint8)
+        _chk(self._lib.vv_read_noise_gradients(self._h, _ptr(out), out.nbytes))
+        return out
 
     def loadFilterPNG(self, path):
         _chk(self._lib.vv_load_filter_png(self._h, path.encode()))

@@ -38,6 +38,8 @@ class Scene:
     next_field: Optional[np.ndarray] = None
     interp: tuple = (0, 10)
     slice_dist: tuple = (1.0, 1.0, 1.0)
+    mc_offsets: Optional[np.ndarray] = None   # [height][width] float32 in [0,1]; needs "#define USE_MC_OFFSET" in defines
+    clip_planes: tuple = ()                # up to 3 active planes (nx, ny, nz, d): n.q + d >= 0 kept, q relative to the centre
 
     def lic_params(self):
         return LICParams(**self.params)
@@ -105,4 +107,11 @@ def apply_scene(r: Renderer, s: Scene):
     r.updateLightPos()
     r.setTechnique(s.technique)
     r.resize(s.width, s.height)
+    if s.mc_offsets is not None:
+        r.setMCOffsets(s.mc_offsets)
+    for i in range(3):
+        if i < len(s.clip_planes):
+            r.setClipPlane(i, s.clip_planes[i], True)
+        else:
+            r.setClipPlane(i, (0.0, 0.0, -1.0, 0.0), False)
     return r

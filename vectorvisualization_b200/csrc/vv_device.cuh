@@ -68,6 +68,12 @@ struct DevParams {
     double camD[3], rot[9], tanHalf, aspect, extent[3];
     int width, height;
     int tfMode, gateMode, quirkLumAlpha;
+    // ---- Monte-Carlo ray-start offsets (USE_MC_OFFSET) and user clip planes ----
+    const float *mcOffsets;          // [height][width], fp16-rounded values in [0,1]; null = off
+    int nClip;                       // active clip planes
+    double clipEq[3][4];             // glClipPlane equations, n.q + d >= 0 kept, q = position - centerD
+    double clipN[3][3], clipDist[3]; // unit normal and distance of the cap polygon, n^.q = -(d - 0.0001); clipDist NaN = no cap
+    double centerD[3];
     // ---- partition / outputs ----
     int rank, world, nBlocksX, nBlocksY, nLocalBlocks;
     int blockSkew;                   // per-row rotation of the block ids, see block_id()

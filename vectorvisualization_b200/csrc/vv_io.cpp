@@ -319,6 +319,33 @@ const char *vv_last_error(void)
     return vvb200::last_error_string().c_str();
 }
 
+// loadGradients / saveGradients with DATRAW_UCHAR, VV/gradient.cpp:93-187
+int vv_grd_read(const char *file_name, const int dims[3], uint8_t *gradients3)
+{
+    if (!file_name || !dims || !gradients3) return fail(VV_ERR_INVALID, "vv_grd_read: null argument");
+    const std::string p = std::string(file_name) + ".grd";
+    FILE *fp = std::fopen(p.c_str(), "rb");
+    if (!fp) return fail(VV_ERR_IO, "loadGradients: No pre-computed gradients found.");
+    const size_t n = (size_t)3 * dims[0] * dims[1] * dims[2];
+    const size_t got = std::fread(gradients3, 1, n, fp);
+    std::fclose(fp);
+    if (got != n) return fail(VV_ERR_IO, "loadGradients: Reading gradients from \"" + p + "\" failed.");
+    return VV_OK;
+}
+
+int vv_grd_write(const char *file_name, const int dims[3], const uint8_t *gradients3)
+{
+    if (!file_name || !dims || !gradients3) return fail(VV_ERR_INVALID, "vv_grd_write: null argument");
+    const std::string p = std::string(file_name) + ".grd";
+    FILE *fp = std::fopen(p.c_str(), "wb");
+    if (!fp) return fail(VV_ERR_IO, "saveGradients: Could not open file \"" + p + "\".");
+    const size_t n = (size_t)3 * dims[0] * dims[1] * dims[2];
+    const size_t put = std::fwrite(gradients3, 1, n, fp);
+    const int rc = std::fclose(fp);
+    if (put != n || rc != 0) return fail(VV_ERR_IO, "saveGradients: Writing gradients to \"" + p + "\" failed.");
+    return VV_OK;
+}
+
 int vv_parse_dat(const char *dat_path, VVDatInfo *out) { return parse_dat(dat_path, out); }
 int vv_read_raw(const VVDatInfo *info, int time_step, void *out, size_t out_bytes) { return read_raw(info, time_step, out, out_bytes); }
 

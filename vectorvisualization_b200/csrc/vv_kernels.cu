@@ -49,15 +49,68 @@ __device__ __forceinline__ bool pixel_ray(const DevParams &P, int px, int py, fl
         if (t0 > tn) { tn = t0; face = i; faceval = fv; }
         if (t1 < tf) tf = t1;
     }
-    if (!(tn < tf) || tn <= 0.0 || face < 0) return false;
+    bool have = (tn < tf) && tn > 0.0 && face >= 0;
+    double p[3] = {0.0, 0.0, 0.0};
+    if (have) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        double p = __dadd_rn(o[i], __dmul_rn(tn, d[i]));
-        if (i == face) p = faceval;
-        p = fmin(fmax(p, 0.0), P.extent[i]);
-        e[i] = (float)p;
+        for (int i = 0; i < 3; ++i) {
+            p[i] = __dadd_rn(o[i], __dmul_rn(tn, d[i]));
+            if (i == face) p[i] = faceval;
+            p[i] = fmin(fmax(p[i], 0.0), P.extent[i]);
+        }
     }
+    if (P.nClip > 0) {
+        // User clip planes (Renderer::enableClipPlanes / drawClippedPolygon, VV/renderer.cpp:156-163, 1294-1309): GL clips
+        // the cube's front faces; the cap polygons n^.q = -(d - 0.0001) are drawn afterwards in plane order, culled when
+        // they face away, clipped by the other planes; without depth test or blending the last fragment under the pixel
+        // wins.  Same double arithmetic, same order as the oracle.
+        auto kept = [&](const double q[3], int skip) {
+            for (int j = 0; j < P.nClip; ++j) {
+                if (j == skip) continue;
+                const double *c = P.clipEq[j];
+                if (__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(c[0], q[0]), __dmul_rn(c[1], q[1])), __dmul_rn(c[2], q[2])), c[3]) < 0.0) return false;
+            }
+            return true;
+        };
+        if (have) {
+            const double q[3] = {__dsub_rn(p[0], P.centerD[0]), __dsub_rn(p[1], P.centerD[1]), __dsub_rn(p[2], P.centerD[2])};
+            have = kept(q, -1);
+        }
+        const double oc[3] = {__dsub_rn(o[0], P.centerD[0]), __dsub_rn(o[1], P.centerD[1]), __dsub_rn(o[2], P.centerD[2])};
+        for (int i = 0; i < P.nClip; ++i) {
+            const double *n = P.clipN[i];
+            const double dist = P.clipDist[i];
+            if (!(dist == dist)) continue;                                    // degenerate normal: no cap
+            const double dn = __dadd_rn(__dadd_rn(__dmul_rn(n[0], d[0]), __dmul_rn(n[1], d[1])), __dmul_rn(n[2], d[2]));
+            if (!(dn > 0.0)) continue;                                        // cap faces away from the viewer: culled
+            const double on = __dadd_rn(__dadd_rn(__dmul_rn(n[0], oc[0]), __dmul_rn(n[1], oc[1])), __dmul_rn(n[2], oc[2]));
+            const double t = __ddiv_rn(__dsub_rn(dist, on), dn);
+            if (!(t > 0.0)) continue;
+            const double q[3] = {__dadd_rn(oc[0], __dmul_rn(t, d[0])), __dadd_rn(oc[1], __dmul_rn(t, d[1])), __dadd_rn(oc[2], __dmul_rn(t, d[2]))};
+            bool inside = true;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (fabs(q[k]) > __dmul_rn(0.5, P.extent[k])) inside = false;
+            if (!inside || !kept(q, i)) continue;
+            have = true;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) p[k] = fmin(fmax(__dadd_rn(q[k], __dmul_rn(0.5, P.extent[k])), 0.0), P.extent[k]);
+        }
+    }
+    if (!have) return false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) e[i] = (float)p[i];
     return true;
+}
+
+// pos += dir * stepSize * texture2DRect(mcOffsetSampler, gl_FragCoord.xy).r  (lic3d_fragment.glsl:31-33, USE_MC_OFFSET)
+__device__ __forceinline__ void mc_offset(const DevParams &P, int px, int py, f3 &pos, f3 dstep)
+{
+    if (!P.mcOffsets) return;
+    const float r = P.mcOffsets[(size_t)py * P.width + px];
+    pos.x = __fadd_rn(pos.x, __fmul_rn(dstep.x, r));
+    pos.y = __fadd_rn(pos.y, __fmul_rn(dstep.y, r));
+    pos.z = __fadd_rn(pos.z, __fmul_rn(dstep.z, r));
 }
 
 // GLSL normalize() as v / sqrt(dot(v,v)), IEEE round-to-nearest, uncontracted
@@ -392,6 +445,7 @@ __global__ void __launch_bounds__(256) lic_raycast_kernel(const __grid_constant_
         if (px < P.width && py < P.height && pixel_ray(P, px, py, e)) {
             f3 pos, dir, dstep;
             ray_setup(P, e, pos, dir, dstep);
+            mc_offset(P, px, py, pos, dstep);
             const unsigned int maxSamples = (unsigned int)P.numIter * (unsigned int)P.numIter;   // nested loops :38-40
             float src_a = 0.0f;
             for (;;) {
@@ -455,6 +509,7 @@ __global__ void __launch_bounds__(256) ray_setup_kernel(const __grid_constant__ 
         float e[3];
         if (px < P.width && py < P.height && pixel_ray(P, px, py, e)) {
             ray_setup(P, e, pos, dir, dstep);
+            mc_offset(P, px, py, pos, dstep);
             const int maxSamples = P.numIter * P.numIter;
             f3 q = pos;
             for (;;) {                                  // the march of lic3d_fragment.glsl:38-95 without the shading
@@ -515,11 +570,19 @@ __device__ __forceinline__ bool slice_fragment(const DevParams &P, const PixelDi
     if (b == 0.0) return false;
     const double t = __ddiv_rn(__dsub_rn((double)slice_offset(P, slice), a), b);
     if (!(t > 0.0)) return false;
+    double pd[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const double p = __dadd_rn(r.o[i], __dmul_rn(t, r.d[i]));
         if (p < 0.0 || p > P.extent[i]) return false;
+        pd[i] = p;
         g[i] = (float)p;
+    }
+    // user clip planes clip the slice polygons (VV/renderer.cpp:156-163)
+    for (int j = 0; j < P.nClip; ++j) {
+        const double *c = P.clipEq[j];
+        const double q0 = __dsub_rn(pd[0], P.slCenter[0]), q1 = __dsub_rn(pd[1], P.slCenter[1]), q2 = __dsub_rn(pd[2], P.slCenter[2]);
+        if (__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(c[0], q0), __dmul_rn(c[1], q1)), __dmul_rn(c[2], q2)), c[3]) < 0.0) return false;
     }
     return true;
 }
@@ -598,6 +661,7 @@ __global__ void __launch_bounds__(256, LIC_MIN_CTAS) lic_sample_kernel(const __g
             if (have) {
                 f3 dstep;
                 ray_setup(P, g, pos, dir, dstep);
+                mc_offset(P, px, py, pos, dstep);     // lic3d_slicing_fragment.glsl:31-33
             }
         } else {
             dir = mk3(B.x, B.y, B.z);

@@ -108,6 +108,12 @@ struct VVRenderer {
     int licvol_fp16 = 1, count_samples = 1, licvol_size = 0, sample_map = 0;
     DevBuf<unsigned int> sample_tiles;
     float spec_exp = 40.0f;
+    // MC ray-start offsets (USE_MC_OFFSET + Renderer::updateMCOffsetTex) and user clip planes
+    bool use_mc = false;
+    DevBuf<float> mc_offsets;
+    int mc_w = 0, mc_h = 0;
+    bool clip_active[3] = {false, false, false};
+    double clip_eq[3][4] = {{0, 0, -1, 0}, {0, 0, -1, 0}, {0, 0, -1, 0}};   // ClipPlane ctor, VV/transform.cpp:240-254
 
     // ---- frame ----
     int width = 0, height = 0;
@@ -417,6 +423,25 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycas
         for (int i = 0; i < 3; ++i) P.slCenter[i] = (double)r->center[i];
     }
     P.tfMode = r->tf_modes[prog]; P.gateMode = r->gate_modes[prog]; P.quirkLumAlpha = (r->quirk_lum_alpha && !r->noise_has_grad) ? 1 : 0;   // Q7 only bites GL_LUMINANCE noise
+    if (r->use_mc && r->mc_offsets.p && need_frame) {
+        if (r->mc_w != r->width || r->mc_h != r->height) return fail(VV_ERR_STATE, "MC offset texture size differs from the frame (vv_set_mc_offsets after vv_resize)");
+        P.mcOffsets = r->mc_offsets.p;
+    }
+    for (int k = 0; k < 3; ++k) P.centerD[k] = (double)r->center[k];
+    P.nClip = 0;
+    for (int i = 0; i < 3; ++i) {
+        if (!r->clip_active[i]) continue;
+        const double *e = r->clip_eq[i];
+        const int j = P.nClip++;
+        for (int k = 0; k < 4; ++k) P.clipEq[j][k] = e[k];
+        const double len = std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+        if (len > 1e-8) {                                   // ViewSlicing::setupSingleSlice normalises, VV/slicing.cpp:337-348
+            for (int k = 0; k < 3; ++k) P.clipN[j][k] = e[k] / len;
+            P.clipDist[j] = -(e[3] - 0.0001);               // ClipPlane::drawSlice, VV/transform.cpp:432-444
+        } else {
+            P.clipDist[j] = std::nan("");
+        }
+    }
     P.rank = r->rank; P.world = r->world; P.nBlocksX = r->nbx; P.nBlocksY = r->nby; P.nLocalBlocks = r->n_local_blocks;
     P.blockSkew = block_skew_for(r->world);
     P.tiles = r->tiles.p;
@@ -500,7 +525,8 @@ static int ensure_illum_tables(VVRenderer *r)
 }
 #endif
 
-static int upload_noise(VVRenderer *r, const uint8_t *data, const int dims[3], int with_gradients)
+// grad3: already quantised gradients [z][y][x][3] (the .grd cache), or null to compute them on the GPU
+static int upload_noise(VVRenderer *r, const uint8_t *data, const int dims[3], int with_gradients, const uint8_t *grad3 = nullptr)
 {
     const size_t n = (size_t)dims[0] * dims[1] * dims[2];
     // the padded layouts are addressed with signed 32-bit element offsets
@@ -512,7 +538,18 @@ static int upload_noise(VVRenderer *r, const uint8_t *data, const int dims[3], i
     CU(r->noise_cell.ensure((size_t)(dims[0] + 1) * (dims[1] + 1) * (dims[2] + 1)));
     CU(launch_build_cell8(r->noise_raw.p, 1, 0, dims[0], dims[1], dims[2], 1, 1, r->noise_cell.p, r->stream));
     r->noise_has_grad = false;
-    if (with_gradients) {
+    if (with_gradients && grad3) {
+        // NoiseDataSet::createTexture with stored gradients: pack (gradient.xyz, noise), VV/dataset.cpp:1269-1282
+        std::vector<uint8_t> rgba(4 * n);
+        for (size_t i = 0; i < n; ++i) {
+            rgba[4 * i] = grad3[3 * i]; rgba[4 * i + 1] = grad3[3 * i + 1]; rgba[4 * i + 2] = grad3[3 * i + 2];
+            rgba[4 * i + 3] = data[i];
+        }
+        CU(r->noise_rgba.ensure(n));
+        CU(r->noise_quad.ensure(n));
+        CU(cudaMemcpyAsync(r->noise_rgba.p, rgba.data(), 4 * n, cudaMemcpyHostToDevice, r->stream));
+        CU(cudaStreamSynchronize(r->stream));   // rgba goes out of scope
+    } else if (with_gradients) {
         // filter table of filterGradients, VV/gradient.cpp:392-409 (only the k,j,i in -2..0 corner is ever written; Q16)
         float filt[125];
         std::memset(filt, 0, sizeof(filt));
@@ -533,6 +570,8 @@ static int upload_noise(VVRenderer *r, const uint8_t *data, const int dims[3], i
         // NoiseDataSet keeps sliceDist = 1 (never set for noise files, VV/dataset.cpp:1124-1173 / VolumeData ctor)
         const float sd[3] = {1.0f, 1.0f, 1.0f};
         CU(launch_noise_gradients(r->noise_raw.p, dims[0], dims[1], dims[2], sd, r->grad_filter.p, r->grad_tmp.p, r->noise_rgba.p, r->stream));
+    }
+    if (with_gradients) {
         CU(launch_build_quad(r->noise_rgba.p, dims[0], dims[1], dims[2], r->noise_quad.p, r->stream));
         CU(r->noise_pair.ensure((size_t)(dims[0] + 1) * (dims[1] + 2) * (dims[2] + 2)));
         CU(launch_build_noise_pair(r->noise_rgba.p, dims[0], dims[1], dims[2], r->noise_pair.p, r->stream));
@@ -694,14 +733,14 @@ int vv_load_glsl_shader(VVRenderer *r, const char *defines)
 {
     if (!r) return fail(VV_ERR_INVALID, "null renderer");
     int illum = ILLUM_NONE;
-    bool sof = false;
+    bool sof = false, mc = false;
     if (defines) {
         if (std::strstr(defines, "ILLUM_GRADIENT")) illum = ILLUM_GRADIENT;
         else if (std::strstr(defines, "ILLUM_MALLO")) illum = ILLUM_MALLO;
         else if (std::strstr(defines, "ILLUM_ZOECKLER")) illum = ILLUM_ZOECKLER;
         if (std::strstr(defines, "SPEED_OF_FLOW")) sof = true;
-        if (std::strstr(defines, "TIME_DEPENDENT") || std::strstr(defines, "USE_MC_OFFSET"))
-            return fail(VV_ERR_INVALID, "TIME_DEPENDENT / USE_MC_OFFSET builds are not supported");
+        if (std::strstr(defines, "USE_MC_OFFSET")) mc = true;
+        if (std::strstr(defines, "TIME_DEPENDENT")) return fail(VV_ERR_INVALID, "TIME_DEPENDENT builds are not supported");
     }
     if (illum == ILLUM_MALLO || illum == ILLUM_ZOECKLER) {
 #ifdef VV_HAVE_ILLUM_TABLES
@@ -714,8 +753,50 @@ int vv_load_glsl_shader(VVRenderer *r, const char *defines)
     }
     r->illum_mode = illum;
     r->speed_of_flow = sof;
+    r->use_mc = mc;
     r->frame_valid = false;
     r->licvol_valid = false;
+    return VV_OK;
+}
+
+// Renderer::updateMCOffsetTex, VV/renderer.cpp:636-679: one offset in [0,1] per pixel, GL_LUMINANCE16F rectangle texture,
+// NEAREST.  Used by the ray-cast and slicing programs when they were built with USE_MC_OFFSET.
+int vv_set_mc_offsets(VVRenderer *r, const float *offsets, int width, int height)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    CU(cudaSetDevice(r->device));
+    r->frame_valid = false;
+    if (!offsets) { r->mc_offsets.release(); r->mc_w = r->mc_h = 0; return VV_OK; }
+    if (width < 1 || height < 1) return fail(VV_ERR_INVALID, "vv_set_mc_offsets: bad size");
+    const size_t n = (size_t)width * height;
+    std::vector<float> h(n);
+    for (size_t i = 0; i < n; ++i) h[i] = __half2float(__float2half_rn(offsets[i]));   // the 16F upload rounding
+    CU(r->mc_offsets.ensure(n));
+    CU(cudaMemcpyAsync(r->mc_offsets.p, h.data(), n * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    r->mc_w = width; r->mc_h = height;
+    return VV_OK;
+}
+
+int vv_update_mc_offset_tex(VVRenderer *r, int width, int height, uint32_t seed)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    if (width < 1 || height < 1) return fail(VV_ERR_INVALID, "vv_update_mc_offset_tex: bad size");
+    // noise[i] = rand() / RAND_MAX there (unseeded); here mt19937(seed), u = draw / (2^32 - 1) in [0,1]
+    std::vector<float> v((size_t)width * height);
+    std::mt19937 gen(seed);
+    for (size_t i = 0; i < v.size(); ++i) v[i] = (float)((double)gen() / 4294967295.0);
+    return vv_set_mc_offsets(r, v.data(), width, height);
+}
+
+// ClipPlane::setNormal + setActive (VV/transform.cpp:296-315) for plane index 0..2 (GL_CLIP_PLANE0 + index, VV/3DLIC.cpp:763-781)
+int vv_set_clip_plane(VVRenderer *r, int index, const double equation[4], int active)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    if (index < 0 || index > 2) return fail(VV_ERR_INVALID, "vv_set_clip_plane: index must be 0..2");
+    if (equation) for (int k = 0; k < 4; ++k) r->clip_eq[index][k] = equation[k];
+    r->clip_active[index] = active != 0;
+    r->frame_valid = false;
     return VV_OK;
 }
 
@@ -840,6 +921,29 @@ int vv_set_noise(VVRenderer *r, const uint8_t *data, const int dims[3], int with
     CU(cudaSetDevice(r->device));
     r->licvol_valid = false;
     return upload_noise(r, data, dims, with_gradients);
+}
+
+int vv_set_noise_with_gradients(VVRenderer *r, const uint8_t *noise, const uint8_t *gradients3, const int dims[3])
+{
+    if (!r || !noise || !gradients3 || !dims) return fail(VV_ERR_INVALID, "vv_set_noise_with_gradients: null argument");
+    if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return fail(VV_ERR_INVALID, "bad noise dimensions");
+    CU(cudaSetDevice(r->device));
+    r->licvol_valid = false;
+    return upload_noise(r, noise, dims, 1, gradients3);
+}
+
+int vv_read_noise_gradients(VVRenderer *r, uint8_t *out, size_t out_bytes)
+{
+    if (!r || !out) return fail(VV_ERR_INVALID, "vv_read_noise_gradients: null argument");
+    if (!r->have_noise || !r->noise_has_grad) return fail(VV_ERR_STATE, "the current noise has no gradients");
+    const size_t n = (size_t)r->ndim[0] * r->ndim[1] * r->ndim[2];
+    if (out_bytes < 3 * n) return fail(VV_ERR_INVALID, "output buffer too small");
+    CU(cudaSetDevice(r->device));
+    std::vector<uint8_t> rgba(4 * n);
+    CU(cudaMemcpyAsync(rgba.data(), r->noise_rgba.p, 4 * n, cudaMemcpyDeviceToHost, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    for (size_t i = 0; i < n; ++i) { out[3 * i] = rgba[4 * i]; out[3 * i + 1] = rgba[4 * i + 1]; out[3 * i + 2] = rgba[4 * i + 2]; }
+    return VV_OK;
 }
 
 int vv_generate_white_noise(VVRenderer *r, int n, uint32_t seed, float p, int with_gradients)
@@ -1350,7 +1454,17 @@ int vv_load_noise(VVRenderer *r, const char *path, int with_gradients)
     int dims[3];
     int rc = read_noise_file(path, data, dims);
     if (rc) return rc;
-    return vv_set_noise(r, data.data(), dims, with_gradients);
+    if (!with_gradients) return vv_set_noise(r, data.data(), dims, 0);
+    // NoiseDataSet::createTexture, VV/dataset.cpp:1238-1267: stored gradients if there are any, else compute and store
+    std::vector<uint8_t> grd((size_t)3 * dims[0] * dims[1] * dims[2]);
+    if (vv_grd_read(path, dims, grd.data()) == VV_OK) return vv_set_noise_with_gradients(r, data.data(), grd.data(), dims);
+    set_error("");
+    rc = vv_set_noise(r, data.data(), dims, 1);
+    if (rc) return rc;
+    rc = vv_read_noise_gradients(r, grd.data(), grd.size());
+    if (rc) return rc;
+    if (vv_grd_write(path, dims, grd.data()) != VV_OK) set_error("");   // "Saving gradients was not sucessful" is only a warning there
+    return VV_OK;
 }
 
 int vv_load_filter_png(VVRenderer *r, const char *path)
