@@ -142,6 +142,15 @@ VV_API int vv_update_light_pos(VVRenderer *r);
 VV_API int vv_enable_lowres(VVRenderer *r, int enable);
 VV_API int vv_enable_float_target(VVRenderer *r, int enable);
 VV_API int vv_set_option(VVRenderer *r, int option, int value);
+/* Screenshot / recording: Renderer::screenshot / switchRecording (VV/renderer.h:99-101, keys 'p' / 'P' VV/3DLIC.cpp:262-270)
+ * and the tail of Renderer::renderFBO (VV/renderer.cpp:1478-1513): after a screenshot request, and for every vv_render
+ * while recording, the stored RGBA8 frame is written as PNG to "<dir>/<frames>_<file_name>" (recording or animation on;
+ * frames counts the recorded frames) or "<dir>/<dd-mm-YYYY HH-MM-SS> <file_name>".  Defaults: dir "snapshotOut",
+ * file_name "snapshot.png".  vv_switch_recording returns the new state (1 = recording). */
+VV_API int vv_set_snapshot(VVRenderer *r, const char *dir, const char *file_name, int animation_on);
+VV_API int vv_screenshot(VVRenderer *r);
+VV_API int vv_switch_recording(VVRenderer *r);
+VV_API const char *vv_last_snapshot_path(VVRenderer *r);
 /* Monte-Carlo ray-start offsets.  Renderer::updateMCOffsetTex (VV/renderer.cpp:636-679) fills a width x height
  * GL_LUMINANCE16F rectangle texture with rand()/RAND_MAX; programs built with "#define USE_MC_OFFSET" (passed to vv_init /
  * vv_load_glsl_shader) start each ray / slice fragment at pos + dir * stepSize * offset[pixel]

@@ -581,6 +581,35 @@ def test_noise_gradient_cache(vv, oracle, tmp_path):
     assert np.array_equal(r2.readNoiseTexture(shape, 4), tex)
 
 
+def test_screenshot_and_recording(vv, tmp_path):
+    """Renderer::screenshot / switchRecording + the file naming of renderFBO (VV/renderer.cpp:1478-1513)"""
+    import os, re
+    from vectorvisualization_b200 import configs
+    s = configs.cfg1(n=16, size=40)
+    r = vv.Renderer(0)
+    configs.apply_scene(r, s)
+    out = str(tmp_path / "snapshotOut")
+    os.makedirs(out)
+    r.setSnapshot(out, "shot.png")
+    r.render(True)
+    assert os.listdir(out) == []                                   # nothing is written unless asked
+    r.screenshot()
+    r.render(False)                                                # a redisplay of the stored frame is enough
+    files = os.listdir(out)
+    assert len(files) == 1 and re.fullmatch(r"\d\d-\d\d-\d{4} \d\d-\d\d-\d\d shot\.png", files[0])
+    assert r.lastSnapshotPath() == os.path.join(out, files[0])
+    assert np.array_equal(vv.png_read(r.lastSnapshotPath())[::-1], r.readRGBA8())
+    r.render(False)
+    assert len(os.listdir(out)) == 1                               # one-shot
+    assert r.switchRecording() is True
+    for i in range(3):
+        r.render(i % 2 == 0)
+        assert r.lastSnapshotPath() == os.path.join(out, "%d_shot.png" % i)
+    assert r.switchRecording() is False
+    r.render(True)
+    assert sorted(f for f in os.listdir(out) if f[0].isdigit() and "_" in f) == ["0_shot.png", "1_shot.png", "2_shot.png"]
+
+
 def _golden_names():
     import os, sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))

@@ -86,6 +86,8 @@ def load_library():
         "vv_enable_lowres": ([P, I], I), "vv_enable_float_target": ([P, I], I), "vv_set_option": ([P, I, I], I),
         "vv_set_mc_offsets": ([P, P, I, I], I), "vv_update_mc_offset_tex": ([P, I, I, ctypes.c_uint32], I),
         "vv_set_clip_plane": ([P, I, P, I], I),
+        "vv_set_snapshot": ([P, CP, CP, I], I), "vv_screenshot": ([P], I), "vv_switch_recording": ([P], I),
+        "vv_last_snapshot_path": ([P], CP),
         "vv_render": ([P, I], I), "vv_read_rgba8": ([P, P, ctypes.c_size_t], I), "vv_read_rgba32f": ([P, P, ctypes.c_size_t], I),
         "vv_read_display_rgba8": ([P, P, ctypes.c_size_t], I),
         "vv_read_lic_volume": ([P, P, ctypes.c_size_t, ctypes.POINTER(I)], I),
@@ -288,6 +290,22 @@ class Renderer:
 
     def enableLowRes(self, enable):
         _chk(self._lib.vv_enable_lowres(self._h, int(enable)))
+
+    def setSnapshot(self, directory=None, file_name=None, animation_on=False):
+        _chk(self._lib.vv_set_snapshot(self._h, directory.encode() if directory is not None else None,
+                                       file_name.encode() if file_name is not None else None, int(animation_on)))
+
+    def screenshot(self):
+        _chk(self._lib.vv_screenshot(self._h))
+
+    def switchRecording(self):
+        rc = self._lib.vv_switch_recording(self._h)
+        if rc < 0:
+            _chk(rc)
+        return bool(rc)
+
+    def lastSnapshotPath(self):
+        return self._lib.vv_last_snapshot_path(self._h).decode()
 
     def setMCOffsets(self, offsets):
         """Renderer::updateMCOffsetTex with explicit values: float32 [height][width] in [0,1] (None removes the texture)"""

@@ -4,6 +4,7 @@
 // vv_kernels.cu / vv_preprocess.cu; this file owns device memory, derives the parameter block the way
 // Renderer::setRenderVolParams does (VV/renderer.cpp:925-996) and sequences launches on one stream.
 #include <cmath>
+#include <ctime>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -112,6 +113,10 @@ struct VVRenderer {
     bool use_mc = false;
     DevBuf<float> mc_offsets;
     int mc_w = 0, mc_h = 0;
+    // screenshot / recording (Renderer::renderFBO tail, VV/renderer.cpp:1478-1513; keys VV/3DLIC.cpp:262-270)
+    bool screenshot = false, recording = false, animation_on = false;
+    int frames = 0;
+    std::string snapshot_dir = "snapshotOut", snapshot_name = "snapshot.png", last_snapshot;
     bool clip_active[3] = {false, false, false};
     double clip_eq[3][4] = {{0, 0, -1, 0}, {0, 0, -1, 0}, {0, 0, -1, 0}};   // ClipPlane ctor, VV/transform.cpp:240-254
 
@@ -1118,7 +1123,64 @@ int vv_set_option(VVRenderer *r, int option, int value)
 }
 
 // Renderer::render(update), VV/renderer.cpp:126-312: update == 0 re-presents the stored frame (:150-152, 228)
+static int render_frame(VVRenderer *r, int update);
+
+// the tail of Renderer::renderFBO, VV/renderer.cpp:1478-1513: while recording (or after a screenshot request) every
+// displayed frame is written as "<dir>/<frames>_<name>" (animation / recording) or "<dir>/<dd-mm-YYYY HH-MM-SS> <name>"
+static int save_snapshot(VVRenderer *r)
+{
+    char stamp[64];
+    std::string path = r->snapshot_dir.empty() ? std::string() : r->snapshot_dir + "/";
+    if (r->animation_on || r->recording) {
+        std::snprintf(stamp, sizeof(stamp), "%d_", r->frames);
+    } else {
+        std::time_t t = std::time(nullptr);
+        std::tm tmv;
+        localtime_r(&t, &tmv);
+        std::strftime(stamp, sizeof(stamp), "%d-%m-%Y %H-%M-%S ", &tmv);
+    }
+    path += stamp + r->snapshot_name;
+    int rc = vv_save_png(r, path.c_str(), 0);   // saveTexture(_imgBufferTex0, 4, 15, 255.0): the stored RGBA8 frame
+    if (rc) return rc;
+    r->last_snapshot = path;
+    if (r->screenshot) r->screenshot = false;
+    if (r->recording) ++r->frames;
+    return VV_OK;
+}
+
 int vv_render(VVRenderer *r, int update)
+{
+    int rc = render_frame(r, update);
+    if (rc == VV_OK && r->world == 1 && (r->screenshot || r->recording)) rc = save_snapshot(r);
+    return rc;
+}
+
+int vv_set_snapshot(VVRenderer *r, const char *dir, const char *file_name, int animation_on)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    if (dir) r->snapshot_dir = dir;
+    if (file_name) r->snapshot_name = file_name;
+    r->animation_on = animation_on != 0;
+    return VV_OK;
+}
+
+int vv_screenshot(VVRenderer *r)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    r->screenshot = true;
+    return VV_OK;
+}
+
+int vv_switch_recording(VVRenderer *r)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    r->recording = !r->recording;
+    return r->recording ? 1 : 0;
+}
+
+const char *vv_last_snapshot_path(VVRenderer *r) { return r ? r->last_snapshot.c_str() : ""; }
+
+static int render_frame(VVRenderer *r, int update)
 {
     if (!r) return fail(VV_ERR_INVALID, "null renderer");
     CU(cudaSetDevice(r->device));
