@@ -175,7 +175,9 @@ __device__ __forceinline__ void heun_step(const DevParams &P, Walker &w, float s
 // advanced in the same loop iteration so that each thread keeps two dependent fetch chains in flight.
 // nBwdEff / nFwdEff: the walk stops after the last step whose filter-kernel weight is non-zero (trailing zero
 // weights contribute exactly 0 to the sum).
-template <int LAYOUT, bool NGATE, bool SOF>
+// STRAIGHT: the common part of the two walks as straight-line code (measured: 3 % faster in lic_sample_kernel on the
+// scalar builds, neutral on the gradient build, 8 % slower in lic_volume_kernel, which therefore keeps the guarded loop)
+template <int LAYOUT, bool NGATE, bool SOF, bool STRAIGHT = true>
 __device__ __forceinline__ float compute_lic_scalar(const DevParams &P, const float *s_kw, f3 pos, float4 centre)
 {
     float acc0 = noise_tap<NGATE>(P, pos) * s_kw[0];
@@ -183,22 +185,42 @@ __device__ __forceinline__ float compute_lic_scalar(const DevParams &P, const fl
     Walker wb = make_walker(pos, centre), wf = wb;
     const float *kwB = s_kw + 1, *kwF = s_kw + 1 + P.nBwd;
     const int nB = P.nBwdEff, nF = P.nFwdEff;
-    const int n = max(nB, nF);
-    for (int k = 0; k < n; ++k) {
-        if (k < nB) {
+    if (STRAIGHT) {
+        // common part of the two walks without per-direction guards, then the tail of the longer walk
+        const int nMin = min(nB, nF);
+        int k = 0;
+        for (; k < nMin; ++k) {
+            heun_step<LAYOUT, SOF>(P, wb, -P.h);
+            heun_step<LAYOUT, SOF>(P, wf, P.h);
+            accB = fmaf(noise_tap<NGATE>(P, mk3(lo2(wb.qxy), hi2(wb.qxy), wb.qz)), kwB[k], accB);
+            accF = fmaf(noise_tap<NGATE>(P, mk3(lo2(wf.qxy), hi2(wf.qxy), wf.qz)), kwF[k], accF);
+        }
+        for (; k < nB; ++k) {
             heun_step<LAYOUT, SOF>(P, wb, -P.h);
             accB = fmaf(noise_tap<NGATE>(P, mk3(lo2(wb.qxy), hi2(wb.qxy), wb.qz)), kwB[k], accB);
         }
-        if (k < nF) {
+        for (; k < nF; ++k) {
             heun_step<LAYOUT, SOF>(P, wf, P.h);
             accF = fmaf(noise_tap<NGATE>(P, mk3(lo2(wf.qxy), hi2(wf.qxy), wf.qz)), kwF[k], accF);
+        }
+    } else {
+        const int n = max(nB, nF);
+        for (int k = 0; k < n; ++k) {
+            if (k < nB) {
+                heun_step<LAYOUT, SOF>(P, wb, -P.h);
+                accB = fmaf(noise_tap<NGATE>(P, mk3(lo2(wb.qxy), hi2(wb.qxy), wb.qz)), kwB[k], accB);
+            }
+            if (k < nF) {
+                heun_step<LAYOUT, SOF>(P, wf, P.h);
+                accF = fmaf(noise_tap<NGATE>(P, mk3(lo2(wf.qxy), hi2(wf.qxy), wf.qz)), kwF[k], accF);
+            }
         }
     }
     return (acc0 + accB) + accF;
 }
 
 // computeLIC, USE_NOISE_GRADIENTS build: vec4 accumulation of raw RGBA noise texels (Q8)
-template <int LAYOUT, bool SOF>
+template <int LAYOUT, bool SOF, bool STRAIGHT = true>
 __device__ __forceinline__ float4 compute_lic_grad(const DevParams &P, const float *s_kw, f3 pos, float4 centre)
 {
     const Rgba2 c = fetch_noise_rgba_pk(P, pos.x, pos.y, pos.z);
@@ -207,21 +229,51 @@ __device__ __forceinline__ float4 compute_lic_grad(const DevParams &P, const flo
     Walker wb = make_walker(pos, centre), wf = wb;
     const float *kwB = s_kw + 1, *kwF = s_kw + 1 + P.nBwd;
     const int nB = P.nBwdEff, nF = P.nFwdEff;
-    const int n = max(nB, nF);
-    for (int k = 0; k < n; ++k) {
-        if (k < nB) {
+    if (STRAIGHT) {
+        const int nMin = min(nB, nF);
+        int k = 0;
+        for (; k < nMin; ++k) {
+            heun_step<LAYOUT, SOF>(P, wb, -P.h);
+            heun_step<LAYOUT, SOF>(P, wf, P.h);
+            const Rgba2 tb = fetch_noise_rgba_pk(P, lo2(wb.qxy), hi2(wb.qxy), wb.qz);
+            const Rgba2 tf = fetch_noise_rgba_pk(P, lo2(wf.qxy), hi2(wf.qxy), wf.qz);
+            const pk2_t wB = bc2(kwB[k]), wF = bc2(kwF[k]);
+            accBrg = fma2(tb.rg, wB, accBrg);
+            accBba = fma2(tb.ba, wB, accBba);
+            accFrg = fma2(tf.rg, wF, accFrg);
+            accFba = fma2(tf.ba, wF, accFba);
+        }
+        for (; k < nB; ++k) {
             heun_step<LAYOUT, SOF>(P, wb, -P.h);
             const Rgba2 t = fetch_noise_rgba_pk(P, lo2(wb.qxy), hi2(wb.qxy), wb.qz);
             const pk2_t w = bc2(kwB[k]);
             accBrg = fma2(t.rg, w, accBrg);
             accBba = fma2(t.ba, w, accBba);
         }
-        if (k < nF) {
+        for (; k < nF; ++k) {
             heun_step<LAYOUT, SOF>(P, wf, P.h);
             const Rgba2 t = fetch_noise_rgba_pk(P, lo2(wf.qxy), hi2(wf.qxy), wf.qz);
             const pk2_t w = bc2(kwF[k]);
             accFrg = fma2(t.rg, w, accFrg);
             accFba = fma2(t.ba, w, accFba);
+        }
+    } else {
+        const int n = max(nB, nF);
+        for (int k = 0; k < n; ++k) {
+            if (k < nB) {
+                heun_step<LAYOUT, SOF>(P, wb, -P.h);
+                const Rgba2 t = fetch_noise_rgba_pk(P, lo2(wb.qxy), hi2(wb.qxy), wb.qz);
+                const pk2_t w = bc2(kwB[k]);
+                accBrg = fma2(t.rg, w, accBrg);
+                accBba = fma2(t.ba, w, accBba);
+            }
+            if (k < nF) {
+                heun_step<LAYOUT, SOF>(P, wf, P.h);
+                const Rgba2 t = fetch_noise_rgba_pk(P, lo2(wf.qxy), hi2(wf.qxy), wf.qz);
+                const pk2_t w = bc2(kwF[k]);
+                accFrg = fma2(t.rg, w, accFrg);
+                accFba = fma2(t.ba, w, accFba);
+            }
         }
     }
     const pk2_t rg = add2(fma2(c.rg, w0, accBrg), accFrg);
@@ -884,8 +936,8 @@ __global__ void __launch_bounds__(256) lic_volume_kernel(const __grid_constant__
         f3 pos = mk3(__fmul_rn(g.x, P.scaleVol[0]), __fmul_rn(g.y, P.scaleVol[1]), __fmul_rn(g.z, P.scaleVol[2]));
         float4 vd = fetch_field<LAYOUT, true>(P, pos.x, pos.y, pos.z);
         float r;
-        if (GRAD) r = compute_lic_grad<LAYOUT, SOF>(P, S.kw, pos, vd).x;
-        else r = compute_lic_scalar<LAYOUT, NGATE, SOF>(P, S.kw, pos, vd);
+        if (GRAD) r = compute_lic_grad<LAYOUT, SOF, false>(P, S.kw, pos, vd).x;
+        else r = compute_lic_scalar<LAYOUT, NGATE, SOF, false>(P, S.kw, pos, vd);
         r *= P.licScale;
         if (P.licvolFp16) r = __half2float(__float2half_rn(r));
         P.licvol_out[((size_t)z * P.oh + y) * P.ow + x] = r;
