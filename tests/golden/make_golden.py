@@ -17,7 +17,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
 from oracle import refshim  # noqa: E402
-from scenes import golden_scenes  # noqa: E402
+from oracle import vvo  # noqa: E402
+from scenes import golden_scenes, golden_extra_scenes  # noqa: E402
 
 
 def main():
@@ -36,6 +37,15 @@ def main():
         np.savez_compressed(out, raycast=img, raycast_samples=cnt.astype(np.uint16), total=np.int64(tot),
                             licvol12=lv, volraycast=vimg, volraycast_samples=vcnt.astype(np.uint16))
         print("%-32s ray samples %7d  -> %s (%d bytes)" % (name, tot, os.path.basename(out), os.path.getsize(out)))
+    tables = vvo.illum_tables(40.0)      # bit-identical to VV/illumination.cpp (tests/test_host_vs_ref.py)
+    for name, (mk, kind) in golden_extra_scenes().items():
+        s = mk()
+        need_tables = "MALLO" in (s.defines or "") or "ZOECKLER" in (s.defines or "")
+        r = refshim.RefScene(s, illum_tables=tables if need_tables else None)
+        img, cnt, tot = r.slicing() if kind == "slicing" else r.raycast()
+        out = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(out, frame=img, samples=cnt.astype(np.uint16), total=np.int64(tot))
+        print("%-32s %-8s samples %7d  -> %s (%d bytes)" % (name, kind, tot, os.path.basename(out), os.path.getsize(out)))
 
 
 if __name__ == "__main__":

@@ -60,3 +60,63 @@ def golden_scenes():
         return s
     S["anisotropic_tf_scalar_band"] = g8
     return S
+
+
+def golden_extra_scenes():
+    """second family: the slicing program, the illuminated-streamline builds and the USE_MC_OFFSET builds.
+    name -> (maker, kind) with kind "raycast" or "slicing"; scenes with ILLUM_MALLO / ILLUM_ZOECKLER need the
+    illumination tables (oracle.illum_tables(40.0))"""
+    import vectorvisualization_b200 as vv
+    from vectorvisualization_b200 import configs, fields as F
+    S = {}
+
+    def slicing(s):
+        s.technique = vv.VOLIC_SLICING
+        s.tf_mode, s.gate_mode = vv.TF_A, vv.GATE_TF_ALPHA          # what lic3d_slicing_fragment.glsl hard-codes
+        s.tf = F.default_tf()
+        s.params.update(gradientScale=4.0)
+        return s
+
+    def e1():
+        s = configs.cfg3(n=20, size=32, camera=F.CAMERA_CLOSE)
+        return slicing(s)
+    S["x_slicing_gradient"] = (e1, "slicing")
+
+    def e2():
+        s = configs.cfg2(n=20, size=36)
+        s.with_gradients = True
+        return slicing(s)
+    S["x_slicing_plain"] = (e2, "slicing")
+
+    def e3():
+        s = configs.cfg2(n=24, size=40, camera=F.CAMERA_CLOSE)
+        s.defines = "#define ILLUM_MALLO"
+        s.params.update(gradientScale=4.0, illumScale=1.3)
+        s.light = dict(quat=F.quat_from_axis_angle((0.2, 1, 0), 70.0), dist=1.0)
+        return s
+    S["x_mallo_raycast"] = (e3, "raycast")
+
+    def e4():
+        s = configs.cfg1(n=20, size=36)
+        s.defines = "#define ILLUM_ZOECKLER"
+        s.params.update(gradientScale=4.0)
+        s.light = dict(quat=F.quat_from_axis_angle((1, 0.2, 0), 40.0), dist=1.0)
+        return s
+    S["x_zoeckler_raycast"] = (e4, "raycast")
+
+    def e5():
+        s = configs.cfg3(n=24, size=40)
+        s.tf_mode = vv.TF_B
+        s.defines += "\n#define USE_MC_OFFSET"
+        s.mc_offsets = np.random.RandomState(21).rand(s.height, s.width).astype(np.float32)
+        return s
+    S["x_mc_raycast_gradient"] = (e5, "raycast")
+
+    def e6():
+        s = configs.cfg1(n=24, size=40)
+        s = slicing(s)
+        s.defines = "#define USE_MC_OFFSET"
+        s.mc_offsets = np.random.RandomState(22).rand(s.height, s.width).astype(np.float32)
+        return s
+    S["x_mc_slicing"] = (e6, "slicing")
+    return S

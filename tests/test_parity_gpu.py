@@ -730,6 +730,25 @@ def test_cuda_matches_golden_vectors(vv, oracle, name):
     assert_image_parity(oracle, r3.readRGBA32F(), g["volraycast"], name + " volume ray-cast")
 
 
+def _golden_extra_names():
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from scenes import golden_extra_scenes
+    return sorted(golden_extra_scenes().keys())
+
+
+@pytest.mark.parametrize("name", _golden_extra_names())
+def test_cuda_matches_golden_extra(vv, oracle, name):
+    """CUDA path against the second golden family (slicing, Mallo / Zoeckler, USE_MC_OFFSET): reference shader outputs"""
+    import os
+    from scenes import golden_extra_scenes
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    s = golden_extra_scenes()[name][0]()
+    r, img, _, cnt, tot = render_cuda(vv, s)
+    assert int((cnt != g["samples"].astype(np.uint32)).sum()) <= 1
+    assert_image_parity(oracle, img, g["frame"], name)
+
+
 def test_item_order_does_not_change_the_frame(vv):
     """depth-major (band, depth-chunk) work-item order vs tile-major order: bit-identical frames and counts"""
     from vectorvisualization_b200 import configs
