@@ -138,7 +138,9 @@ VV_API int vv_set_camera(VVRenderer *r, const float quat[4], const float pos[3],
 /* setLight + updateLightPos (Transform, VV/renderer.cpp:431-466) */
 VV_API int vv_set_light(VVRenderer *r, const float quat[4], float dist);
 VV_API int vv_update_light_pos(VVRenderer *r);
-/* enableLowRes / enableFBO, VV/renderer.h:76-83 */
+/* enableLowRes / enableFBO, VV/renderer.h:76-83.  Low-res = the interaction preset of VV/renderer.cpp:947-966 (step x2,
+ * 15+15 LIC steps of 1/64, frequency x0.7, alpha correction for the doubled step).  The reference additionally renders
+ * into half the window in that mode (VV/renderer.cpp:111-119): call vv_resize(w / 2, h / 2) for that. */
 VV_API int vv_enable_lowres(VVRenderer *r, int enable);
 VV_API int vv_enable_float_target(VVRenderer *r, int enable);
 VV_API int vv_set_option(VVRenderer *r, int option, int value);
