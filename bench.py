@@ -170,7 +170,7 @@ def run_cuda(args):
     import torch.distributed as dist
     import vectorvisualization_b200 as vv
     from vectorvisualization_b200 import configs
-    from vectorvisualization_b200.dist import render_distributed
+    from vectorvisualization_b200.dist import render_distributed, connect_p2p, render_distributed_p2p, disconnect_p2p
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -186,10 +186,26 @@ def run_cuda(args):
     stream = torch.cuda.Stream()          # a real (non-legacy) stream: the library, NCCL and the timing events share it
     torch.cuda.set_stream(stream)
     r.setStream(stream.cuda_stream)
+    exchange = "none"
     if world > 1:
         r.setPartition(rank, world)
+        # tile exchange: peer-to-peer stores over NVLink (vv_p2p_*), or one NCCL all_gather per frame.  Every rank must
+        # take the same path, so the outcome of the IPC set-up is agreed on first.
+        ok = 0
+        if args.exchange == "p2p":
+            try:
+                connect_p2p(r)
+                ok = 1
+            except Exception as ex:
+                print("bench.py: rank %d: peer-to-peer set-up failed (%r), falling back to the NCCL gather" % (rank, ex), file=sys.stderr)
+        t = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        exchange = "p2p" if int(t.item()) == 1 else "nccl"
 
     def frame():
+        if exchange == "p2p":
+            render_distributed_p2p(r)
+            return None
         if world > 1:
             return render_distributed(r)
         r.render(True)
@@ -264,6 +280,8 @@ def run_cuda(args):
     h2d = 1024          # sizeof(DevParams) kernel-argument block (< 1 KiB) per frame
     d2h = scene.width * scene.height * 4
 
+    if exchange == "p2p":
+        disconnect_p2p(r)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -306,6 +324,8 @@ def run_cuda(args):
                    "l2": "inputs larger than L2 (field %.0f MB + noise %.0f MB vs 126 MB)" % (
                        n[0] * n[1] * n[2] * 16 / 1e6, scene.noise.size * (16 if scene.with_gradients else 8) / 1e6),
                    "parallelism": "sort-first 16x16 blocks over %d GPU(s), volume replicated" % world,
+                   "exchange": {"none": "single GPU", "p2p": "peer-to-peer tile stores over NVLink + arrival counters (vv_p2p_render)",
+                                "nccl": "NCCL all_gather_into_tensor of the tile buffers"}[exchange],
                    "field_layout": "x-pair fp16 (16 B/voxel)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "fps": args.steps / e2e_s, "what": "vv_set_camera + vv_set_lic_params + vv_render + vv_read_rgba8 into pinned host memory, per frame"},
@@ -326,6 +346,7 @@ def main():
     ap.add_argument("--config", default=None)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU tile exchange (N > 1)")
     args = ap.parse_args()
     if args.config is None:
         args.config = "cfg3"

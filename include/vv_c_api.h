@@ -209,6 +209,20 @@ VV_API int vv_get_tile_buffer(VVRenderer *r, void **dev_ptr, int *n_local_blocks
 /* assemble a row-major frame on this handle from `world` gathered tile buffers laid out [rank][block][256][4] */
 VV_API int vv_assemble_tiles(VVRenderer *r, const void *gathered_dev, int world);
 VV_API int vv_get_lic_volume_ptr(VVRenderer *r, void **dev_ptr, int dims_out[3]);
+/* Peer-to-peer frame exchange for one process per GPU on one NVLink / NVSwitch node (no reference counterpart: the
+ * reference is single-GPU).  Instead of gathering tile buffers with a collective, vv_p2p_render stores this rank's
+ * finished tiles straight into every rank's gather buffer over NVLink, signals arrival with system-scope atomics, waits
+ * for the other ranks' arrivals and un-blocks the frame, all on the handle's stream.  Protocol, after vv_resize and
+ * vv_set_partition on every rank: vv_p2p_export (allocates the gather buffer, returns its 64-byte cudaIpcMemHandle_t
+ * and/or base pointer) -> exchange the handles between the ranks (any host channel) -> vv_p2p_connect with the `world`
+ * handles concatenated in rank order (or base pointers for handles living in the same process) -> vv_p2p_render once
+ * per frame on EVERY rank (it is collective).  A rank that never arrives makes the others give up after about 4 s;
+ * vv_p2p_status then reports VV_ERR_STATE. */
+VV_API int vv_p2p_export(VVRenderer *r, void *ipc_handle_out64, void **base_out);
+VV_API int vv_p2p_connect(VVRenderer *r, const void *ipc_handles, void *const *local_bases, int world);
+VV_API int vv_p2p_render(VVRenderer *r);
+VV_API int vv_p2p_status(VVRenderer *r);
+VV_API int vv_p2p_disconnect(VVRenderer *r);
 /* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the handle's own stream */
 VV_API int vv_set_stream(VVRenderer *r, void *cuda_stream);
 

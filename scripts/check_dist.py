@@ -10,7 +10,8 @@ import torch.distributed as dist
 
 import vectorvisualization_b200 as vv
 from vectorvisualization_b200 import configs
-from vectorvisualization_b200.dist import render_distributed, update_lic_volume_distributed
+from vectorvisualization_b200.dist import (render_distributed, update_lic_volume_distributed, connect_p2p, render_distributed_p2p,
+                                           disconnect_p2p)
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -36,6 +37,16 @@ for mk in (lambda: configs.cfg3(n=64, size=200), lambda: configs.cfg1(n=64, size
     same = bool(np.array_equal(got, want)) and int(n.item()) == total
     print("rank %d %s: frame identical %s, ray samples %d / %d" % (rank, s.name, same, int(n.item()), total), flush=True)
     ok = ok and same
+    # the same frame through the peer-to-peer exchange (CUDA IPC + NVLink stores), three frames for both buffer parities
+    connect_p2p(r)
+    for it in range(3):
+        render_distributed_p2p(r)
+        torch.cuda.synchronize()
+        r.p2pStatus()
+        same = bool(np.array_equal(r.readRGBA32F(), want))
+        print("rank %d %s: p2p frame %d identical %s" % (rank, s.name, it, same), flush=True)
+        ok = ok and same
+    disconnect_p2p(r)
 # LIC volume slabs
 s = configs.cfg2(n=48, size=64)
 s.licvol_fp16 = 0

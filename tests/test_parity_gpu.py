@@ -518,6 +518,46 @@ def test_partition_invariance_single_gpu(vv):
     assert np.array_equal(img, full)
 
 
+def test_p2p_exchange_single_process(vv):
+    """vv_p2p_*: three partitioned handles in one process exchange their tiles through peer stores + arrival counters
+    (the multi-GPU path without IPC): every handle ends up with the unpartitioned frame, over several frames (buffer
+    parity / arrival targets) and a camera change"""
+    from vectorvisualization_b200 import configs, fields as F
+    from vectorvisualization_b200.configs import apply_scene
+    s = configs.cfg3(n=32, size=64)
+    s.width, s.height = 90, 70
+    world = 3
+    hs = []
+    for rank in range(world):
+        r = vv.Renderer(0)
+        apply_scene(r, s)
+        r.setPartition(rank, world)
+        # warm-up with both views: every buffer reaches its final size.  (Ranks normally live in separate processes; here
+        # they share one, where a cudaFree / cudaMalloc of one handle would wait for the other handle's spinning stream.)
+        for cam in (dict(F.CAMERA_CLOSE), s.camera):
+            r.setCamera(**cam)
+            r.render(True)
+            r.synchronize()
+        hs.append(r)
+    bases = [r.p2pExport()[1] for r in hs]
+    for r in hs:
+        r.p2pConnect(local_bases=bases)
+    cams = [s.camera, dict(F.CAMERA_CLOSE), s.camera, dict(F.CAMERA_CLOSE), s.camera]
+    for cam in cams:
+        s.camera = cam
+        _, want, _, _, _ = render_cuda(vv, s, sample_map=False)
+        for r in hs:
+            r.setCamera(**cam)
+            r.updateLightPos()             # the light is placed relative to the camera (VV/renderer.cpp:431-466)
+        for r in hs:
+            r.p2pRender()                  # asynchronous: rank 0 waits on the device for ranks 1 and 2
+        for r in hs:
+            r.p2pStatus()
+            assert np.array_equal(r.readRGBA32F(), want)
+    for r in hs:
+        r.p2pDisconnect()
+
+
 def test_full_size_cfg3(vv, oracle):
     """BASELINE.json configs[1] at full size (256^3 field, 256^3 noise + gradients, 1024^2): the oracle shades sampled pixel
     patches of the full frame (direct parity), and the whole frame is checked through size-independent properties:

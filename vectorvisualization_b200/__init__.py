@@ -101,6 +101,8 @@ def load_library():
         "vv_get_tile_buffer": ([P, ctypes.POINTER(P), ctypes.POINTER(I), ctypes.POINTER(I)], I),
         "vv_assemble_tiles": ([P, P, I], I), "vv_get_lic_volume_ptr": ([P, ctypes.POINTER(P), ctypes.POINTER(I)], I),
         "vv_set_stream": ([P, P], I),
+        "vv_p2p_export": ([P, P, ctypes.POINTER(P)], I), "vv_p2p_connect": ([P, P, ctypes.POINTER(P), I], I),
+        "vv_p2p_render": ([P], I), "vv_p2p_status": ([P], I), "vv_p2p_disconnect": ([P], I),
         "vv_parse_dat": ([CP, ctypes.POINTER(DatInfo)], I), "vv_read_raw": ([ctypes.POINTER(DatInfo), I, P, ctypes.c_size_t], I),
         "vv_load_dat": ([P, CP], I), "vv_load_scalar_dat": ([P, CP], I), "vv_load_noise": ([P, CP, I], I),
         "vv_load_filter_png": ([P, CP], I), "vv_load_tf_png": ([P, CP], I),
@@ -439,6 +441,30 @@ class Renderer:
 
     def assembleTiles(self, gathered_dev_ptr, world):
         _chk(self._lib.vv_assemble_tiles(self._h, ctypes.c_void_p(gathered_dev_ptr), world))
+
+    # ---- peer-to-peer frame exchange (see include/vv_c_api.h: vv_p2p_*) ----
+    def p2pExport(self):
+        """allocates the gather buffer; returns (64-byte cudaIpcMemHandle_t, base device pointer)"""
+        h = (ctypes.c_ubyte * 64)()
+        base = ctypes.c_void_p()
+        _chk(self._lib.vv_p2p_export(self._h, h, ctypes.byref(base)))
+        return bytes(h), base.value
+
+    def p2pConnect(self, handles=None, local_bases=None):
+        """handles: list of `world` 64-byte IPC handles in rank order; local_bases: base pointers of ranks in this process"""
+        world = len(handles) if handles is not None else len(local_bases)
+        hb = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles)) if handles is not None else None
+        lb = (ctypes.c_void_p * world)(*[ctypes.c_void_p(b) for b in local_bases]) if local_bases is not None else None
+        _chk(self._lib.vv_p2p_connect(self._h, hb, lb, world))
+
+    def p2pRender(self):
+        _chk(self._lib.vv_p2p_render(self._h))
+
+    def p2pStatus(self):
+        _chk(self._lib.vv_p2p_status(self._h))
+
+    def p2pDisconnect(self):
+        _chk(self._lib.vv_p2p_disconnect(self._h))
 
     def licVolumePtr(self):
         dims = (ctypes.c_int * 3)()

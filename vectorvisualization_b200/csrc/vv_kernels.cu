@@ -1141,6 +1141,55 @@ cudaError_t launch_lic_volume(const DevParams &P, int layout, bool grad, bool no
                       : launch_licvol_sof<LAYOUT_F4, false, false>(P, speed_of_flow, grid, smem, st);
 }
 
+// ---- peer-to-peer tile exchange (multi-GPU, one process per GPU on one NVLink / NVSwitch node) ----------------------
+// Replaces "all_gather of the tile buffers" by stores into the peers' memory: every rank writes its finished tiles
+// into slot `rank` of every rank's gather buffer (P2P stores over NVLink), fences, and bumps an arrival counter in each
+// peer; the consumer waits until `world` arrivals of the frame are in before it un-blocks.  Two gather buffers
+// alternate by frame parity: a rank can only be one frame ahead of the slowest peer (its own wait needs that peer's
+// arrival, which is stream-ordered after the peer's previous un-block), so the buffer it overwrites is no longer read.
+__global__ void __launch_bounds__(256) scatter_tiles_kernel(P2PArgs a)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        const float4 v = a.tiles[i];
+        for (int j = 0; j < a.world; ++j) a.peerTiles[j][(size_t)a.rank * a.n + i] = v;
+    }
+    __threadfence_system();                       // this thread's stores are visible system-wide before the counter moves
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(a.doneCounter, 1u);
+        if (t == gridDim.x - 1) {                 // last CTA: all tiles of this rank have landed
+            *a.doneCounter = 0;
+            __threadfence_system();
+            for (int j = 0; j < a.world; ++j) atomicAdd_system(a.peerFlags[j], 1u);
+        }
+    }
+}
+
+// one thread spins until `target` arrivals are in (wrap-safe compare); gives up after ~4 s and raises *err instead of
+// hanging the stream when a peer never arrives
+__global__ void wait_arrivals_kernel(volatile unsigned int *flag, unsigned int target, unsigned int *err)
+{
+    const long long t0 = clock64();
+    while ((int)(*flag - target) < 0) {
+        if (clock64() - t0 > (1LL << 33)) { *err = 1u; break; }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+
+cudaError_t launch_scatter_tiles(const P2PArgs &a, int grid, cudaStream_t st)
+{
+    scatter_tiles_kernel<<<grid, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wait_arrivals(unsigned int *flag, unsigned int target, unsigned int *err, cudaStream_t st)
+{
+    wait_arrivals_kernel<<<1, 1, 0, st>>>(flag, target, err);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_unblock(const float4 *tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY, int skew, int width, int height,
                            float4 *frame, uchar4 *frame8, uchar4 *display8, cudaStream_t st)
 {

@@ -19,6 +19,19 @@ cudaError_t launch_lic_volume(const DevParams &P, int layout, bool grad, bool no
 cudaError_t launch_unblock(const float4 *tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY, int skew, int width, int height,
                            float4 *frame, uchar4 *frame8, uchar4 *display8, cudaStream_t st);
 
+// ---- peer-to-peer tile exchange (multi-GPU) ----
+constexpr int kMaxPeers = 16;
+struct P2PArgs {
+    const float4 *tiles;               // this rank's tile buffer, n float4
+    float4 *peerTiles[kMaxPeers];      // gather buffer (current parity) of every rank, own included: [world][n]
+    unsigned int *peerFlags[kMaxPeers];// arrival counter (current parity) in every rank's buffer
+    unsigned int *doneCounter;         // local scratch, zero between launches
+    int rank, world;
+    size_t n;                          // blocksPerRank * 256
+};
+cudaError_t launch_scatter_tiles(const P2PArgs &a, int grid, cudaStream_t st);
+cudaError_t launch_wait_arrivals(unsigned int *flag, unsigned int target, unsigned int *err, cudaStream_t st);
+
 // ---- pre-processing (K6) ----
 // VectorDataSet::fillTexDataFloatInterp (VV/dataset.cpp:533-635): raw FLOAT3 / UCHAR3 time steps -> packed field.
 // tmp: float4 [n] scratch; maxbits: 1 uint scratch.  Writes the pair-packed fp16 layout (padded [nz+1][ny+1][nx], edge

@@ -113,6 +113,14 @@ struct VVRenderer {
     bool use_mc = false;
     DevBuf<float> mc_offsets;
     int mc_w = 0, mc_h = 0;
+    // peer-to-peer frame exchange (vv_p2p_*): [256 B header: arrival counters of the two parities][tiles parity 0][tiles parity 1]
+    unsigned char *p2p_base = nullptr;
+    size_t p2p_tile_bytes = 0;
+    int p2p_world = 0;
+    void *p2p_peer[kMaxPeers] = {};
+    bool p2p_opened[kMaxPeers] = {};
+    unsigned int p2p_epoch = 0;
+    DevBuf<unsigned int> p2p_scratch;      // [0] done counter of the scatter kernel, [1] time-out flag of the wait kernel
     // screenshot / recording (Renderer::renderFBO tail, VV/renderer.cpp:1478-1513; keys VV/3DLIC.cpp:262-270)
     bool screenshot = false, recording = false, animation_on = false;
     int frames = 0;
@@ -721,6 +729,8 @@ int vv_create(VVRenderer **out, int cuda_device)
     return VV_OK;
 }
 
+static void p2p_close(VVRenderer *r);
+
 void vv_destroy(VVRenderer *r)
 {
     if (!r) return;
@@ -730,6 +740,8 @@ void vv_destroy(VVRenderer *r)
     if (r->ev1) cudaEventDestroy(r->ev1);
     if (r->own_stream) cudaStreamDestroy(r->own_stream);
     if (r->host_counters) cudaFreeHost(r->host_counters);
+    p2p_close(r);
+    if (r->p2p_base) cudaFree(r->p2p_base);
     delete r;
 }
 
@@ -1449,6 +1461,113 @@ int vv_assemble_tiles(VVRenderer *r, const void *gathered_dev, int world)
     if (world != r->world) return fail(VV_ERR_INVALID, "vv_assemble_tiles: world mismatch");
     CU(cudaSetDevice(r->device));
     return run_unblock(r, (const float4 *)gathered_dev, world, r->blocks_per_rank);
+}
+
+// ---- peer-to-peer frame exchange ---------------------------------------------------------------------------------
+static void p2p_close(VVRenderer *r)
+{
+    for (int j = 0; j < kMaxPeers; ++j) {
+        if (r->p2p_opened[j] && r->p2p_peer[j]) cudaIpcCloseMemHandle(r->p2p_peer[j]);
+        r->p2p_peer[j] = nullptr;
+        r->p2p_opened[j] = false;
+    }
+}
+
+int vv_p2p_export(VVRenderer *r, void *ipc_handle_out, void **base_out)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    if (r->width <= 0 || r->height <= 0) return fail(VV_ERR_STATE, "vv_p2p_export: vv_resize / vv_set_partition first");
+    if (r->world > kMaxPeers) return fail(VV_ERR_INVALID, "vv_p2p_export: more than 16 ranks");
+    CU(cudaSetDevice(r->device));
+    CU(cudaStreamSynchronize(r->stream));
+    p2p_close(r);
+    if (r->p2p_base) { CU(cudaFree(r->p2p_base)); r->p2p_base = nullptr; }
+    r->p2p_tile_bytes = (size_t)r->world * r->blocks_per_rank * kBlockPixels * sizeof(float4);
+    r->p2p_world = r->world;
+    r->p2p_epoch = 0;
+    CU(cudaMalloc((void **)&r->p2p_base, 256 + 2 * r->p2p_tile_bytes));   // plain cudaMalloc: IPC-exportable
+    CU(cudaMemset(r->p2p_base, 0, 256 + 2 * r->p2p_tile_bytes));
+    CU(r->p2p_scratch.ensure(2));
+    CU(cudaMemset(r->p2p_scratch.p, 0, 2 * sizeof(unsigned int)));
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, r->p2p_base));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        std::memcpy(ipc_handle_out, &h, sizeof(h));
+    }
+    if (base_out) *base_out = r->p2p_base;
+    return VV_OK;
+}
+
+int vv_p2p_connect(VVRenderer *r, const void *ipc_handles, void *const *local_bases, int world)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    if (!r->p2p_base || world != r->p2p_world || world != r->world) return fail(VV_ERR_STATE, "vv_p2p_connect: vv_p2p_export first (same partition)");
+    if (!ipc_handles && !local_bases) return fail(VV_ERR_INVALID, "vv_p2p_connect: no peer handles");
+    CU(cudaSetDevice(r->device));
+    p2p_close(r);
+    for (int j = 0; j < world; ++j) {
+        if (j == r->rank) { r->p2p_peer[j] = r->p2p_base; continue; }
+        if (local_bases && local_bases[j]) { r->p2p_peer[j] = local_bases[j]; continue; }   // peers of the same process
+        if (!ipc_handles) return fail(VV_ERR_INVALID, "vv_p2p_connect: missing handle");
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const unsigned char *)ipc_handles + 64 * (size_t)j, sizeof(h));
+        void *ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        r->p2p_peer[j] = ptr;
+        r->p2p_opened[j] = true;
+    }
+    return VV_OK;
+}
+
+int vv_p2p_render(VVRenderer *r)
+{
+    int rc = render_frame(r, 1);
+    if (rc) return rc;
+    if (r->world == 1) return VV_OK;
+    if (!r->p2p_base || !r->p2p_peer[r->world - 1] || !r->p2p_peer[0]) return fail(VV_ERR_STATE, "vv_p2p_render: not connected (vv_p2p_export / vv_p2p_connect)");
+    const unsigned int parity = r->p2p_epoch & 1u;
+    P2PArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.tiles = r->tiles.p;
+    a.rank = r->rank; a.world = r->world;
+    a.n = (size_t)r->blocks_per_rank * kBlockPixels;
+    a.doneCounter = r->p2p_scratch.p;
+    for (int j = 0; j < r->world; ++j) {
+        unsigned char *b = (unsigned char *)r->p2p_peer[j];
+        a.peerFlags[j] = (unsigned int *)(b + 128 * parity);
+        a.peerTiles[j] = (float4 *)(b + 256 + parity * r->p2p_tile_bytes);
+    }
+    const int grid = (int)std::min<size_t>((a.n + 255) / 256, (size_t)r->num_sms * 4);
+    CU(launch_scatter_tiles(a, std::max(grid, 1), r->stream));
+    const unsigned int target = (unsigned int)r->world * (r->p2p_epoch / 2 + 1);
+    CU(launch_wait_arrivals((unsigned int *)(r->p2p_base + 128 * parity), target, r->p2p_scratch.p + 1, r->stream));
+    r->launches += 2;
+    ++r->p2p_epoch;
+    return run_unblock(r, (const float4 *)(r->p2p_base + 256 + parity * r->p2p_tile_bytes), r->world, r->blocks_per_rank);
+}
+
+// VV_ERR_STATE if a wait timed out (a peer never delivered its tiles); synchronises the stream
+int vv_p2p_status(VVRenderer *r)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    if (!r->p2p_scratch.p) return VV_OK;
+    CU(cudaSetDevice(r->device));
+    unsigned int e[2] = {0, 0};
+    CU(cudaMemcpyAsync(e, r->p2p_scratch.p, sizeof(e), cudaMemcpyDeviceToHost, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
+    return e[1] ? fail(VV_ERR_STATE, "peer-to-peer exchange timed out: a rank did not deliver its tiles") : VV_OK;
+}
+
+int vv_p2p_disconnect(VVRenderer *r)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    CU(cudaSetDevice(r->device));
+    CU(cudaStreamSynchronize(r->stream));
+    p2p_close(r);
+    if (r->p2p_base) { CU(cudaFree(r->p2p_base)); r->p2p_base = nullptr; }
+    r->p2p_world = 0;
+    return VV_OK;
 }
 
 int vv_get_lic_volume_ptr(VVRenderer *r, void **dev_ptr, int dims_out[3])

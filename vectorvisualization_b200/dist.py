@@ -97,6 +97,38 @@ def render_distributed(renderer, group=None):
     return gathered
 
 
+def connect_p2p(renderer, group=None):
+    """peer-to-peer exchange instead of the NCCL gather: every rank allocates its gather buffer, the CUDA IPC handles go
+    round once over the host channel, every rank maps every buffer.  Call after resize / setPartition; collective."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    st = torch.cuda.current_stream().cuda_stream
+    if st == 0:
+        raise RuntimeError("connect_p2p needs a non-default torch stream (torch.cuda.set_stream(torch.cuda.Stream()))")
+    renderer.setStream(st)
+    handle, _ = renderer.p2pExport()
+    handles = [None] * world
+    dist.all_gather_object(handles, handle, group=group)
+    renderer.p2pConnect(handles=handles)
+    dist.barrier(group)          # every buffer is mapped everywhere before the first store
+
+
+def render_distributed_p2p(renderer):
+    """render this rank's blocks, store them into every rank's gather buffer over NVLink, wait for the peers' blocks,
+    assemble the frame -- one call per frame on every rank, nothing but kernels on the stream"""
+    renderer.p2pRender()
+
+
+def disconnect_p2p(renderer, group=None):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    renderer.p2pStatus()
+    dist.barrier(group)          # nobody still writes into a buffer that is about to be freed
+    renderer.p2pDisconnect()
+
+
 def update_lic_volume_distributed(renderer, depth, group=None):
     """each rank computes its z-slab of the LIC volume, then the slabs are all-gathered in place"""
     import torch
