@@ -220,6 +220,24 @@ def run_cuda(args):
     for _ in range(max(args.warmup, 3)):
         keep = frame()
     barrier()
+    if exchange == "p2p":
+        # the warm-up frames went through the peer-to-peer exchange: if any rank saw a time-out, every rank drops to NCCL
+        ok = 1
+        try:
+            r.p2pStatus()
+        except Exception as ex:
+            ok = 0
+            print("bench.py: rank %d: %r, falling back to the NCCL gather" % (rank, ex), file=sys.stderr)
+        t = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t.item()) == 0:
+            torch.cuda.synchronize()
+            dist.barrier()
+            r.p2pDisconnect()
+            exchange = "nccl"
+            for _ in range(3):
+                keep = frame()
+            barrier()
     samples_per_frame = r.lastRaySamples()
     launches_per_frame = r.lastLaunchCount()
     if world > 1:

@@ -216,7 +216,7 @@ VV_API int vv_get_lic_volume_ptr(VVRenderer *r, void **dev_ptr, int dims_out[3])
  * vv_set_partition on every rank: vv_p2p_export (allocates the gather buffer, returns its 64-byte cudaIpcMemHandle_t
  * and/or base pointer) -> exchange the handles between the ranks (any host channel) -> vv_p2p_connect with the `world`
  * handles concatenated in rank order (or base pointers for handles living in the same process) -> vv_p2p_render once
- * per frame on EVERY rank (it is collective).  A rank that never arrives makes the others give up after about 4 s;
+ * per frame on EVERY rank (it is collective).  A rank that never arrives makes the others give up after about 17 s;
  * vv_p2p_status then reports VV_ERR_STATE. */
 VV_API int vv_p2p_export(VVRenderer *r, void *ipc_handle_out64, void **base_out);
 VV_API int vv_p2p_connect(VVRenderer *r, const void *ipc_handles, void *const *local_bases, int world);

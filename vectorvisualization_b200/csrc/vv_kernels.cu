@@ -1149,30 +1149,36 @@ cudaError_t launch_lic_volume(const DevParams &P, int layout, bool grad, bool no
 // arrival, which is stream-ordered after the peer's previous un-block), so the buffer it overwrites is no longer read.
 __global__ void __launch_bounds__(256) scatter_tiles_kernel(P2PArgs a)
 {
+    // blockIdx.y = destination rank: a CTA streams contiguous 16-byte stores to ONE peer (the local re-reads of the tiles
+    // hit L2), so that many independent NVLink write streams are in flight per SM
+    const int j = blockIdx.y;
+    float4 *dst = a.peerTiles[j] + (size_t)a.rank * a.n;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-        const float4 v = a.tiles[i];
-        for (int j = 0; j < a.world; ++j) a.peerTiles[j][(size_t)a.rank * a.n + i] = v;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < a.n; i += 4 * stride) {
+        const float4 v0 = a.tiles[i], v1 = a.tiles[i + stride], v2 = a.tiles[i + 2 * stride], v3 = a.tiles[i + 3 * stride];
+        dst[i] = v0; dst[i + stride] = v1; dst[i + 2 * stride] = v2; dst[i + 3 * stride] = v3;
     }
+    for (; i < a.n; i += stride) dst[i] = a.tiles[i];
     __threadfence_system();                       // this thread's stores are visible system-wide before the counter moves
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int t = atomicAdd(a.doneCounter, 1u);
-        if (t == gridDim.x - 1) {                 // last CTA: all tiles of this rank have landed
+        if (t == gridDim.x * gridDim.y - 1) {     // last CTA: all tiles of this rank have landed everywhere
             *a.doneCounter = 0;
             __threadfence_system();
-            for (int j = 0; j < a.world; ++j) atomicAdd_system(a.peerFlags[j], 1u);
+            for (int k = 0; k < a.world; ++k) atomicAdd_system(a.peerFlags[k], 1u);
         }
     }
 }
 
-// one thread spins until `target` arrivals are in (wrap-safe compare); gives up after ~4 s and raises *err instead of
-// hanging the stream when a peer never arrives
+// one thread spins until `target` arrivals are in (wrap-safe compare); gives up after ~17 s (2^35 cycles) and raises
+// *err instead of hanging the stream when a peer never arrives
 __global__ void wait_arrivals_kernel(volatile unsigned int *flag, unsigned int target, unsigned int *err)
 {
     const long long t0 = clock64();
     while ((int)(*flag - target) < 0) {
-        if (clock64() - t0 > (1LL << 33)) { *err = 1u; break; }
+        if (clock64() - t0 > (1LL << 35)) { *err = 1u; break; }
         __nanosleep(100);
     }
     __threadfence_system();
@@ -1180,7 +1186,7 @@ __global__ void wait_arrivals_kernel(volatile unsigned int *flag, unsigned int t
 
 cudaError_t launch_scatter_tiles(const P2PArgs &a, int grid, cudaStream_t st)
 {
-    scatter_tiles_kernel<<<grid, 256, 0, st>>>(a);
+    scatter_tiles_kernel<<<dim3(grid, a.world), 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -1538,7 +1538,8 @@ int vv_p2p_render(VVRenderer *r)
         a.peerFlags[j] = (unsigned int *)(b + 128 * parity);
         a.peerTiles[j] = (float4 *)(b + 256 + parity * r->p2p_tile_bytes);
     }
-    const int grid = (int)std::min<size_t>((a.n + 255) / 256, (size_t)r->num_sms * 4);
+    // grid.x CTAs per destination rank (grid.y = world): about 4 CTAs per SM in total
+    const int grid = (int)std::min<size_t>((a.n + 1023) / 1024, (size_t)std::max(1, r->num_sms * 4 / r->world));
     CU(launch_scatter_tiles(a, std::max(grid, 1), r->stream));
     const unsigned int target = (unsigned int)r->world * (r->p2p_epoch / 2 + 1);
     CU(launch_wait_arrivals((unsigned int *)(r->p2p_base + 128 * parity), target, r->p2p_scratch.p + 1, r->stream));
