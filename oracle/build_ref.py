@@ -137,7 +137,7 @@ def build_host_objects(verbose=False):
     """reference C++ translation units, unmodified, against the capturing GL stub in oracle/ref_shim/"""
     shim = os.path.join(HERE, "ref_shim")
     objs = []
-    units = ["mmath.cpp", "reader.cpp", "parseArg.cpp", "gradient.cpp", "dataset.cpp", "transferEdit.cpp", "texture.cpp", "illumination.cpp"]
+    units = ["mmath.cpp", "reader.cpp", "parseArg.cpp", "gradient.cpp", "dataset.cpp", "transferEdit.cpp", "texture.cpp", "illumination.cpp", "slicing.cpp"]
     flags = ["-O1", "-std=c++14", "-fPIC", "-w", "-fpermissive", "-ffp-contract=off", "-DGLEW_NO_GLU", "-D_USE_MATH_DEFINES",
              "-include", "climits", "-include", "cstring", "-include", "cstdlib", "-include", os.path.join(shim, "ref_prelude.h"),
              "-I", shim, "-I", REF]

@@ -26,6 +26,12 @@
 #include "parseArg.h"
 #include "reader.h"
 #include "transferEdit.h"
+/* ViewSlicing keeps its set-up results (_v, _d) private; the driver only READS them */
+#define private public
+#define protected public
+#include "slicing.h"
+#undef private
+#undef protected
 
 /* ------------------------------------------------------------------------------------------------ GL capture */
 static std::map<GLuint, VVStubTex> g_tex;
@@ -294,6 +300,57 @@ int vvref_illum_tables(float *zoeckler, float *mdiff, float *mspec, int dims[2],
     *spec_exp = il.getSpecularExp();
     return 0;
 }
+/* ---- VV/slicing.cpp: view-aligned slices (ViewSlicing::setupSlicing / drawSlice) and the clip-plane cap polygon
+ * (ClipPlane::drawSlice, VV/transform.cpp:432-444 = setupSingleSlice(normal, extent) + drawSingleSlice(-(d - 0.0001))).
+ * The polygons are captured from the glMultiTexCoord3fvARB / glVertex3fv calls the reference makes. */
+static std::vector<float> g_poly_vert, g_poly_tex;
+void glVertex3fv(const GLfloat *v) { g_poly_vert.insert(g_poly_vert.end(), v, v + 3); }
+void glMultiTexCoord3fvARB(GLenum, const GLfloat *v) { g_poly_tex.insert(g_poly_tex.end(), v, v + 3); }
+
+static int copy_poly(float *verts, float *tex, int cap)
+{
+    int n = (int)(g_poly_vert.size() / 3);
+    if (n > cap) return -1;
+    if (verts) std::memcpy(verts, g_poly_vert.data(), g_poly_vert.size() * sizeof(float));
+    if (tex) std::memcpy(tex, g_poly_tex.data(), g_poly_tex.size() * sizeof(float));
+    return n;
+}
+
+/* out5 = view vector (3), covered depth d, number of slices */
+int vvref_slicing_setup(const float mv[16], float samp_dist, const float ext[3], float out5[5])
+{
+    ViewSlicing vs;
+    float m[16], e[3] = {ext[0], ext[1], ext[2]};
+    std::memcpy(m, mv, sizeof(m));
+    int n = vs.setupSlicing(m, samp_dist, e);
+    out5[0] = vs._v[0]; out5[1] = vs._v[1]; out5[2] = vs._v[2]; out5[3] = vs._d; out5[4] = (float)n;
+    return n;
+}
+
+/* polygon of slice `slice` (front to back as Renderer::sliceVolume draws them): returns the vertex count */
+int vvref_slice_polygon(const float mv[16], float samp_dist, const float ext[3], int slice, float *verts, float *tex, int cap)
+{
+    ViewSlicing vs;
+    float m[16], e[3] = {ext[0], ext[1], ext[2]};
+    std::memcpy(m, mv, sizeof(m));
+    vs.setupSlicing(m, samp_dist, e);
+    g_poly_vert.clear(); g_poly_tex.clear();
+    vs.drawSlice(slice);
+    return copy_poly(verts, tex, cap);
+}
+
+/* cap polygon of a user clip plane (n.xyz, d) */
+int vvref_clip_cap_polygon(const double plane[4], const float ext[3], float *verts, float *tex, int cap)
+{
+    ViewSlicing vs;
+    double n[4] = {plane[0], plane[1], plane[2], plane[3]};
+    float e[3] = {ext[0], ext[1], ext[2]};
+    vs.setupSingleSlice(n, e);
+    g_poly_vert.clear(); g_poly_tex.clear();
+    vs.drawSingleSlice((float)-(n[3] - 0.0001));
+    return copy_poly(verts, tex, cap);
+}
+
 int vvref_next_pow2(int v) { return nextPowerTwo(v); }
 int vvref_has_host(void) { return 1; }
 

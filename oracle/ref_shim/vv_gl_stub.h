@@ -85,6 +85,9 @@ static inline void glEnd(void) {}
 static inline void glVertex2i(GLint, GLint) {}
 static inline void glVertex2f(GLfloat, GLfloat) {}
 static inline void glVertex3f(GLfloat, GLfloat, GLfloat) {}
+/* captured (ref_host_driver.cpp): the slice / cap polygons of VV/slicing.cpp */
+void glVertex3fv(const GLfloat *v);
+void glMultiTexCoord3fvARB(GLenum unit, const GLfloat *v);
 static inline void glTexCoord1f(GLfloat) {}
 static inline void glTexCoord2f(GLfloat, GLfloat) {}
 static inline void glColor3f(GLfloat, GLfloat, GLfloat) {}

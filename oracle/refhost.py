@@ -31,6 +31,9 @@ def _L():
     L.vvref_noise_gradients.argtypes = [ctypes.c_void_p] * 6
     L.vvref_parse_dat.argtypes = [ctypes.c_char_p] + [ctypes.c_void_p] * 6
     L.vvref_parse_args.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_void_p, ctypes.c_void_p]
+    L.vvref_slicing_setup.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
+    L.vvref_slice_polygon.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    L.vvref_clip_cap_polygon.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     L.vvref_quat_angle_axis.argtypes = [ctypes.c_void_p] * 3
     L.vvref_quat_mult_vec.argtypes = [ctypes.c_void_p] * 3
     return L
@@ -144,3 +147,32 @@ def illum_tables():
     rc = L.vvref_illum_tables(z.ctypes.data, d.ctypes.data, s.ctypes.data, dims, ifmt, ctypes.byref(se))
     assert rc == 0 and tuple(dims) == (256, 256)
     return z, d, s, tuple(ifmt), se.value
+
+
+def slicing_setup(mv, samp_dist, extent):
+    """ViewSlicing::setupSlicing (VV/slicing.cpp:42-114): returns (v[3], d, numSlices)"""
+    m = np.ascontiguousarray(mv, np.float32).reshape(16)
+    e = np.ascontiguousarray(extent, np.float32)
+    out = np.zeros(5, np.float32)
+    n = _L().vvref_slicing_setup(m.ctypes.data, float(samp_dist), e.ctypes.data, out.ctypes.data)
+    return out[:3].copy(), float(out[3]), n
+
+
+def slice_polygon(mv, samp_dist, extent, slice_index):
+    """the vertices ViewSlicing::drawSlice(slice) emits: (verts [n][3], texcoords [n][3]) in volume coordinates"""
+    m = np.ascontiguousarray(mv, np.float32).reshape(16)
+    e = np.ascontiguousarray(extent, np.float32)
+    v = np.zeros((8, 3), np.float32); t = np.zeros((8, 3), np.float32)
+    n = _L().vvref_slice_polygon(m.ctypes.data, float(samp_dist), e.ctypes.data, int(slice_index), v.ctypes.data, t.ctypes.data, 8)
+    assert n >= 0
+    return v[:n].copy(), t[:n].copy()
+
+
+def clip_cap_polygon(plane, extent):
+    """ClipPlane::drawSlice (VV/transform.cpp:432-444) for the plane (n.xyz, d): (verts, texcoords)"""
+    pl = np.ascontiguousarray(plane, np.float64)
+    e = np.ascontiguousarray(extent, np.float32)
+    v = np.zeros((8, 3), np.float32); t = np.zeros((8, 3), np.float32)
+    n = _L().vvref_clip_cap_polygon(pl.ctypes.data, e.ctypes.data, v.ctypes.data, t.ctypes.data, 8)
+    assert n >= 0
+    return v[:n].copy(), t[:n].copy()

@@ -214,3 +214,155 @@ def test_illumination_tables(vv, oracle):
         assert np.array_equal(d[..., 0], d[..., c]) and np.array_equal(s[..., 0], s[..., c])
     pz, pd, ps = vv.make_illum_tables(spec_exp)
     assert np.array_equal(pz, oz) and np.array_equal(pd, od) and np.array_equal(ps, os_)
+
+
+# ---- slicing geometry and clip-plane caps: VV/slicing.cpp compiled unmodified, polygons captured from its gl* calls ----
+
+def _view(oracle, o):
+    cam = np.zeros(3, np.float32); rot = np.zeros(9, np.float32)
+    oracle.lib().vvo_view(ctypes.byref(o.c), oracle._p(cam), oracle._p(rot))
+    return cam.astype(np.float64), rot
+
+
+def _modelview(o, rot):
+    """column-major GL_MODELVIEW as Renderer::updateSlices reads it back (VV/renderer.cpp:1270-1292): rows of R, and the
+    z translation (cam_pos.z - dist) - R3 . center; setupSlicing only uses m[2], m[6], m[10], m[3], m[7], m[11], m[14], m[15]"""
+    c = o.c
+    m = np.zeros(16, np.float32)
+    for col in range(3):
+        for row in range(3):
+            m[4 * col + row] = rot[3 * row + col]
+    tz = (float(c.cam_pos[2]) - float(c.cam_dist)) - sum(float(rot[6 + k]) * float(c.center[k]) for k in range(3))
+    m[14] = np.float32(tz)
+    m[15] = 1.0
+    return m
+
+
+def _inside_convex(poly, p, n, eps=1e-5):
+    """p (on the polygon's plane) inside the convex polygon (any winding)"""
+    sgn = 0
+    for i in range(len(poly)):
+        a, b = poly[i], poly[(i + 1) % len(poly)]
+        s = float(np.dot(np.cross(b - a, p - a), n))
+        if abs(s) <= eps:
+            continue
+        if sgn == 0:
+            sgn = 1 if s > 0 else -1
+        elif (s > 0) != (sgn > 0):
+            return False
+    return True
+
+
+def _scenes_for_geometry():
+    import vectorvisualization_b200 as vv
+    from vectorvisualization_b200 import configs, fields as F
+    out = []
+    for cam, slice_dist, step in ((None, (1, 1, 1), 1 / 64), (F.CAMERA_CLOSE, (1, 1, 1), 1 / 128),
+                                  (dict(quat=F.quat_from_axis_angle((0.3, -1.0, 0.2), 110.0), pos=(0.1, 0.0, 0.2), dist=3.0, fovy=35.0), (1.0, 1.5, 2.0), 1 / 32)):
+        s = configs.cfg1(n=12, size=41, camera=cam)
+        s.slice_dist = slice_dist
+        s.params.update(stepSizeVol=step)
+        s.technique = vv.VOLIC_SLICING
+        s.tf_mode, s.gate_mode = vv.TF_A, vv.GATE_TF_ALPHA
+        out.append(s)
+    return out
+
+
+def test_slicing_setup_and_polygons(oracle):
+    """ViewSlicing::setupSlicing / drawSlice (VV/slicing.cpp:42-263) against the oracle's slicing geometry: view vector, depth
+    range and slice count bit for bit; the oracle's fragments are exactly the pixel-ray hits inside the reference's polygons"""
+    for s in _scenes_for_geometry():
+        o = oracle.OracleScene(s)
+        cam, rot = _view(oracle, o)
+        ext = np.array(list(o.c.extent), np.float32)
+        mv = _modelview(o, rot)
+        step = s.lic_params().stepSizeVol
+        v_ref, d_ref, n_ref = refhost.slicing_setup(mv, step, ext)
+        v, d, n = o.slicing_setup()
+        assert n == n_ref and np.float32(d) == np.float32(d_ref)
+        assert np.array_equal(np.asarray(v, np.float32).view(np.uint32), v_ref.view(np.uint32))
+        polys = [refhost.slice_polygon(mv, step, ext, i) for i in range(n_ref)]
+        for verts, tex in polys:
+            assert np.array_equal(verts, tex)                      # texcoord0 = vertex position (volume coordinates)
+        buf = np.zeros((n_ref, 4), np.float32)
+        ent = (ctypes.c_float * 3)(); dr = (ctypes.c_float * 3)()
+        rng = np.random.RandomState(2)
+        checked = 0
+        for _ in range(400):
+            if checked >= 25:
+                break
+            x, y = int(rng.randint(0, s.width)), int(rng.randint(0, s.height))
+            k = oracle.lib().vvo_slice_fragments(ctypes.byref(o.c), x, y, oracle._p(buf), n_ref)
+            got = buf[:k, :3].astype(np.float64)
+            # pixel ray: through the camera and any fragment / entry point of that pixel
+            if k == 0:
+                continue
+            d_ray = got[0] - cam
+            d_ray /= np.linalg.norm(d_ray)
+            want = []
+            vn = np.asarray(v_ref, np.float64)
+            for verts, _ in polys:
+                if len(verts) < 3:
+                    continue
+                P = verts.astype(np.float64)
+                dist = float(np.dot(vn, P[0] - ext / 2))
+                den = float(np.dot(vn, d_ray))
+                t = (dist - float(np.dot(vn, cam - ext / 2))) / den
+                hit = cam + t * d_ray
+                if t > 0 and _inside_convex(P, hit, vn, eps=1e-6):
+                    want.append(hit)
+            # polygons touching the ray at their very edge may go either way: compare the interior hits
+            assert abs(len(want) - k) <= 2, (x, y, len(want), k)
+            for g in got:
+                assert min(np.abs(np.asarray(want) - g).max(axis=1)) < 2e-5
+            checked += 1
+        assert checked >= 10
+
+
+@pytest.mark.parametrize("plane", [(0.0, 0.0, -1.0, 0.1), (0.3, 0.5, -0.8, 0.05), (0.6, -0.8, 0.0, 0.1), (-1.0, 0.0, 0.0, -0.2)])
+def test_clip_cap_polygon(oracle, plane):
+    """ClipPlane::drawSlice (VV/transform.cpp:432-444 -> VV/slicing.cpp:313-560): the cap polygon lies in n^.q = -(d - 0.0001),
+    is wound to face viewers looking along +n, and contains exactly the oracle's cap entry points"""
+    from vectorvisualization_b200 import configs, fields as F
+    n = np.asarray(plane[:3], np.float64)
+    n /= np.linalg.norm(n)
+    cams = (None, F.CAMERA_CLOSE, dict(quat=F.quat_from_axis_angle((0.3, -1.0, 0.2), 110.0), pos=(0.1, 0.0, 0.2), dist=3.0, fovy=35.0),
+            dict(quat=F.quat_from_axis_angle((0.0, 1.0, 0.0), 180.0), pos=(0.0, 0.0, 0.0), dist=3.0, fovy=35.0))
+    seen_caps = 0
+    for cam_cfg in cams:
+        s = configs.cfg1(n=8, size=48, camera=cam_cfg)
+        o = oracle.OracleScene(s)
+        ext = np.array(list(o.c.extent), np.float64)
+        verts, tex = refhost.clip_cap_polygon(plane, ext.astype(np.float32))
+        assert len(verts) >= 3 and np.array_equal(verts, tex)
+        P = verts.astype(np.float64)
+        assert np.abs((P - ext / 2) @ n + (plane[3] - 1e-4)).max() < 1e-6            # on the offset plane
+        newell = sum(np.cross(P[i] - ext / 2, P[(i + 1) % len(P)] - ext / 2) for i in range(len(P)))
+        assert np.dot(newell, n) < 0          # counter-clockwise seen from the -n side: front-facing for rays along +n
+        cam, _ = _view(oracle, o)
+        base = np.zeros((s.height, s.width, 4), np.float32)
+        oracle.lib().vvo_pixel_rays(ctypes.byref(o.c), 0, 0, s.width, s.height, oracle._p(base))
+        s.clip_planes = (plane,)
+        o2 = oracle.OracleScene(s)
+        e = np.zeros((s.height, s.width, 4), np.float32)
+        oracle.lib().vvo_pixel_rays(ctypes.byref(o2.c), 0, 0, s.width, s.height, oracle._p(e))
+        for y in range(0, s.height, 3):
+            for x in range(0, s.width, 3):
+                # the pixel ray, from the unclipped frame (any pixel that hits the box) -- else skip
+                if base[y, x, 3] == 0:
+                    continue
+                d_ray = base[y, x, :3].astype(np.float64) - cam
+                d_ray /= np.linalg.norm(d_ray)
+                dn = float(np.dot(n, d_ray))
+                t = (-(plane[3] - 1e-4) - float(np.dot(n, cam - ext / 2))) / dn if dn != 0 else -1
+                hit = cam + t * d_ray
+                expect_cap = dn > 0 and t > 0 and _inside_convex(P, hit, n, eps=1e-7) and \
+                    np.all(hit > 1e-6) and np.all(hit < ext - 1e-6)
+                on_cap = e[y, x, 3] > 0 and abs(float(np.dot(n, e[y, x, :3].astype(np.float64) - ext / 2)) + plane[3] - 1e-4) < 2e-6
+                if expect_cap:
+                    assert on_cap and np.abs(e[y, x, :3] - hit).max() < 2e-6, (x, y)
+                    seen_caps += 1
+                elif on_cap:
+                    # only possible at the polygon's very edge
+                    assert _inside_convex(P, e[y, x, :3].astype(np.float64), n, eps=1e-4)
+    assert seen_caps > 20
