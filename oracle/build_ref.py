@@ -137,7 +137,8 @@ def build_host_objects(verbose=False):
     """reference C++ translation units, unmodified, against the capturing GL stub in oracle/ref_shim/"""
     shim = os.path.join(HERE, "ref_shim")
     objs = []
-    units = ["mmath.cpp", "reader.cpp", "parseArg.cpp", "gradient.cpp", "dataset.cpp", "transferEdit.cpp", "texture.cpp", "illumination.cpp", "slicing.cpp"]
+    units = ["mmath.cpp", "reader.cpp", "parseArg.cpp", "gradient.cpp", "dataset.cpp", "transferEdit.cpp", "texture.cpp", "illumination.cpp", "slicing.cpp",
+             "transform.cpp", "trackball.cpp", "camera.cpp", "VolumeBuffer.cpp", "renderer.cpp", "GLSLShader.cpp"]
     flags = ["-O1", "-std=c++14", "-fPIC", "-w", "-fpermissive", "-ffp-contract=off", "-DGLEW_NO_GLU", "-D_USE_MATH_DEFINES",
              "-include", "climits", "-include", "cstring", "-include", "cstdlib", "-include", os.path.join(shim, "ref_prelude.h"),
              "-I", shim, "-I", REF]
@@ -147,6 +148,8 @@ def build_host_objects(verbose=False):
             continue
         o = os.path.join(GEN, "host_" + u + ".o")
         cmd = ["g++"] + flags + ["-c", src, "-o", o]
+        if u == "GLSLShader.cpp":      # `return false;` from a char* function (VV/GLSLShader.cpp): valid only before C++11
+            cmd = ["g++"] + [("-std=gnu++98" if f == "-std=c++14" else f) for f in flags] + ["-c", src, "-o", o]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

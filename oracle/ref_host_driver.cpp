@@ -26,12 +26,21 @@
 #include "parseArg.h"
 #include "reader.h"
 #include "transferEdit.h"
-/* ViewSlicing keeps its set-up results (_v, _d) private; the driver only READS them */
+/* ViewSlicing / Renderer keep their state private; the driver only READS it (and calls the protected
+ * Renderer::setRenderVolParams).  The standard headers those files pull in are included first, untouched. */
+#include <cmath>
+#include <ctime>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
 #define private public
 #define protected public
 #include "slicing.h"
+#include "renderer.h"
 #undef private
 #undef protected
+#include <cmath>
 
 /* ------------------------------------------------------------------------------------------------ GL capture */
 static std::map<GLuint, VVStubTex> g_tex;
@@ -349,6 +358,151 @@ int vvref_clip_cap_polygon(const double plane[4], const float ext[3], float *ver
     g_poly_vert.clear(); g_poly_tex.clear();
     vs.drawSingleSlice((float)-(n[3] - 0.0001));
     return copy_poly(verts, tex, cap);
+}
+
+/* ---- GL matrix stack / uniform / light capture for VV/renderer.cpp, camera.cpp, transform.cpp -------------------
+ * The matrix arithmetic is the OpenGL 2.1 specification's (section 2.11.2: Translate, Rotate; gluPerspective per the
+ * GLU reference), in double; what the reference contributes is the sequence of calls and their arguments. */
+struct Mat4 { double m[16]; };
+static Mat4 mat_identity() { Mat4 r; for (int i = 0; i < 16; ++i) r.m[i] = (i % 5 == 0) ? 1.0 : 0.0; return r; }
+static Mat4 mat_mul(const Mat4 &a, const Mat4 &b)      /* column-major a * b */
+{
+    Mat4 r;
+    for (int c = 0; c < 4; ++c)
+        for (int rr = 0; rr < 4; ++rr) {
+            double s = 0.0;
+            for (int k = 0; k < 4; ++k) s += a.m[4 * k + rr] * b.m[4 * c + k];
+            r.m[4 * c + rr] = s;
+        }
+    return r;
+}
+static std::vector<Mat4> g_mv(1, mat_identity()), g_proj(1, mat_identity());
+static GLenum g_mode = GL_MODELVIEW;
+static std::vector<Mat4> &stack() { return g_mode == GL_PROJECTION ? g_proj : g_mv; }
+static std::map<int, std::vector<float>> g_uniform;
+static float g_light_pos[4];
+static double g_clip[6][4];
+static int g_viewport[4];
+
+void glMatrixMode(GLenum mode) { g_mode = mode; }
+void glLoadIdentity(void) { stack().back() = mat_identity(); }
+void glPushMatrix(void) { stack().push_back(stack().back()); }
+void glPopMatrix(void) { if (stack().size() > 1) stack().pop_back(); }
+void glTranslated(GLdouble x, GLdouble y, GLdouble z)
+{
+    Mat4 t = mat_identity();
+    t.m[12] = x; t.m[13] = y; t.m[14] = z;
+    stack().back() = mat_mul(stack().back(), t);
+}
+void glTranslatef(GLfloat x, GLfloat y, GLfloat z) { glTranslated(x, y, z); }
+void glRotatef(GLfloat angle, GLfloat x, GLfloat y, GLfloat z)
+{
+    double len = std::sqrt((double)x * x + (double)y * y + (double)z * z);
+    if (len == 0.0) return;                               /* degenerate axis: implementations leave the matrix alone */
+    double ux = x / len, uy = y / len, uz = z / len, a = (double)angle * M_PI / 180.0, c = std::cos(a), s = std::sin(a), t = 1.0 - c;
+    Mat4 r = mat_identity();
+    r.m[0] = ux * ux * t + c;      r.m[4] = ux * uy * t - uz * s; r.m[8] = ux * uz * t + uy * s;
+    r.m[1] = uy * ux * t + uz * s; r.m[5] = uy * uy * t + c;      r.m[9] = uy * uz * t - ux * s;
+    r.m[2] = uz * ux * t - uy * s; r.m[6] = uz * uy * t + ux * s; r.m[10] = uz * uz * t + c;
+    stack().back() = mat_mul(stack().back(), r);
+}
+void gluPerspective(GLdouble fovy, GLdouble aspect, GLdouble zn, GLdouble zf)
+{
+    double f = 1.0 / std::tan(fovy * M_PI / 360.0);
+    Mat4 p;
+    for (int i = 0; i < 16; ++i) p.m[i] = 0.0;
+    p.m[0] = f / aspect; p.m[5] = f; p.m[10] = (zf + zn) / (zn - zf); p.m[11] = -1.0; p.m[14] = 2.0 * zf * zn / (zn - zf);
+    stack().back() = mat_mul(stack().back(), p);
+}
+void glGetDoublev(GLenum pname, GLdouble *out)
+{
+    const Mat4 &m = (pname == GL_PROJECTION_MATRIX) ? g_proj.back() : g_mv.back();
+    for (int i = 0; i < 16; ++i) out[i] = m.m[i];
+}
+void glGetFloatv(GLenum pname, GLfloat *out)
+{
+    if (pname != GL_MODELVIEW_MATRIX && pname != GL_PROJECTION_MATRIX) { for (int i = 0; i < 4; ++i) out[i] = 0.0f; return; }
+    double d[16];
+    glGetDoublev(pname, d);
+    for (int i = 0; i < 16; ++i) out[i] = (float)d[i];
+}
+void glGetIntegerv(GLenum pname, GLint *out) { for (int i = 0; i < 4; ++i) out[i] = (pname == GL_VIEWPORT) ? g_viewport[i] : 0; }
+void glViewport(GLint x, GLint y, GLsizei w, GLsizei h) { g_viewport[0] = x; g_viewport[1] = y; g_viewport[2] = w; g_viewport[3] = h; }
+void glLightfv(GLenum, GLenum pname, const GLfloat *v)
+{
+    if (pname != GL_POSITION) return;
+    const Mat4 &m = g_mv.back();                          /* positions are transformed by the current model-view */
+    for (int r = 0; r < 4; ++r)
+        g_light_pos[r] = (float)(m.m[r] * v[0] + m.m[4 + r] * v[1] + m.m[8 + r] * v[2] + m.m[12 + r] * v[3]);
+}
+void glClipPlane(GLenum plane, const GLdouble *eq) { int i = (int)plane - GL_CLIP_PLANE0; if (i >= 0 && i < 6) for (int k = 0; k < 4; ++k) g_clip[i][k] = eq[k]; }
+void glUniform1iARB(GLint loc, GLint v) { g_uniform[loc] = {(float)v}; }
+void glUniform1fARB(GLint loc, GLfloat v) { g_uniform[loc] = {v}; }
+void glUniform3fARB(GLint loc, GLfloat a, GLfloat b, GLfloat c) { g_uniform[loc] = {a, b, c}; }
+void glUniform4fARB(GLint loc, GLfloat a, GLfloat b, GLfloat c, GLfloat d) { g_uniform[loc] = {a, b, c, d}; }
+void glUniform4fvARB(GLint loc, GLsizei, const GLfloat *v) { g_uniform[loc] = {v[0], v[1], v[2], v[3]}; }
+void glUniform4iARB(GLint loc, GLint a, GLint b, GLint c, GLint d) { g_uniform[loc] = {(float)a, (float)b, (float)c, (float)d}; }
+
+/* Renderer + Camera + Transform driven as VV/3DLIC.cpp does (init :733-760, display :93-126, keyboard F3 / 'l'):
+ *   out[0..15]   GL_MODELVIEW of the frame: Camera::setCamera() + glTranslatef(-center)      (VV/renderer.cpp:134-146)
+ *   out[16..19]  gl_LightSource[0].position after Renderer::updateLightPos()                  (VV/renderer.cpp:431-466)
+ *   out[20..24]  ViewSlicing state after Renderer::updateSlices(): v[3], d, numSlices          (VV/renderer.cpp:1270-1292)
+ *   out[25..]    uniforms of Renderer::setRenderVolParams, 4 floats per slot in the order
+ *                texMax, scaleVol, scaleVolInv(-> what ended up in slot scaleVol when has_scalevolinv), stepSize, gradient,
+ *                licParams, licKernel, numIterations, alphaCorrection, viewport                (VV/renderer.cpp:925-996)
+ * has_scalevolinv: whether the program has an active scaleVolInv uniform (ILLUM_* builds of the ray-cast program, Q1). */
+int vvref_renderer_state(const char *dat, const char *filter_png, const float cam_quat[4], const float cam_pos[3], float cam_dist,
+                         const float light_quat[4], float light_dist, const float lic[8], int lowres, int has_scalevolinv,
+                         int width, int height, float *out)
+{
+    VectorDataSet vd;
+    if (!vd.loadData(dat)) return -10;
+    LICFilter filt;
+    if (!filter_png || !filt.loadData(filter_png)) filt.createBoxFilter();
+    LICParams lp;
+    lp.stepSizeVol = lic[0]; lp.gradientScale = lic[1]; lp.illumScale = lic[2]; lp.freqScale = lic[3];
+    lp.numIterations = (int)lic[4]; lp.stepsForward = (int)lic[5]; lp.stepsBackward = (int)lic[6]; lp.stepSizeLIC = lic[7];
+    Camera cam;
+    Quaternion q; q.x = cam_quat[0]; q.y = cam_quat[1]; q.z = cam_quat[2]; q.w = cam_quat[3];
+    cam.rotate(q);                                          /* (Transform::setQuaternion only ever writes .x) */
+    cam.setPosition(Vector3_new(cam_pos[0], cam_pos[1], cam_pos[2]));
+    cam.setDistance(cam_dist);
+    cam.setWindow(width, height);
+    Transform light;
+    Quaternion ql; ql.x = light_quat[0]; ql.y = light_quat[1]; ql.z = light_quat[2]; ql.w = light_quat[3];
+    light.rotate(ql);
+    light.setDistance(light_dist);
+    Renderer r;
+    r.setVolumeData(vd.getVolumeData());
+    r._licFilter = &filt;
+    r.setLICParams(&lp);
+    r.setCamera(&cam);
+    r.setLight(&light);
+    r._winWidth = width; r._winHeight = height;
+    r.enableLowRes(lowres != 0);
+    g_mv.assign(1, mat_identity()); g_proj.assign(1, mat_identity()); g_mode = GL_MODELVIEW;
+    g_uniform.clear();
+    /* frame model-view, Renderer::render :134-146 */
+    cam.setCamera();
+    VolumeData *v = vd.getVolumeData();
+    glTranslatef(-v->center[0], -v->center[1], -v->center[2]);
+    glGetFloatv(GL_MODELVIEW_MATRIX, out);
+    r.updateLightPos();
+    for (int i = 0; i < 4; ++i) out[16 + i] = g_light_pos[i];
+    r.updateSlices();
+    out[20] = r._slices._v[0]; out[21] = r._slices._v[1]; out[22] = r._slices._v[2]; out[23] = r._slices._d; out[24] = (float)r._slices._numSlices;
+    GLSLParamsLIC p;
+    p.texMax = 1; p.scaleVol = 2; p.scaleVolInv = has_scalevolinv ? 3 : -1; p.stepSize = 4; p.gradient = 5; p.licParams = 6;
+    p.licKernel = 7; p.numIterations = 8; p.alphaCorrection = 9; p.viewport = 10;
+    r.setRenderVolParams(&p);
+    for (int slot = 1; slot <= 10; ++slot) {
+        float *o = out + 25 + 4 * (slot - 1);
+        o[0] = o[1] = o[2] = o[3] = 0.0f;
+        auto it = g_uniform.find(slot);
+        if (it != g_uniform.end()) for (size_t k = 0; k < it->second.size() && k < 4; ++k) o[k] = it->second[k];
+    }
+    r._licFilter = NULL;                                    /* stack objects: nothing for ~Renderer to touch */
+    return 0;
 }
 
 int vvref_next_pow2(int v) { return nextPowerTwo(v); }

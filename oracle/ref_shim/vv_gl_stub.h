@@ -73,12 +73,12 @@ static inline void glActiveTextureARB(GLenum) {}
 static inline GLenum glGetError(void) { return GL_NO_ERROR; }
 static inline const GLubyte *gluErrorString(GLenum) { return (const GLubyte *)"stub"; }
 static inline GLenum glCheckFramebufferStatusEXT(GLenum) { return GL_FRAMEBUFFER_COMPLETE_EXT; }
-static inline void glMatrixMode(GLenum) {}
-static inline void glPushMatrix(void) {}
-static inline void glPopMatrix(void) {}
-static inline void glLoadIdentity(void) {}
+void glMatrixMode(GLenum mode);
+void glPushMatrix(void);
+void glPopMatrix(void);
+void glLoadIdentity(void);
 static inline void glOrtho(GLdouble, GLdouble, GLdouble, GLdouble, GLdouble, GLdouble) {}
-static inline void glTranslatef(GLfloat, GLfloat, GLfloat) {}
+void glTranslatef(GLfloat x, GLfloat y, GLfloat z);
 static inline void glScalef(GLfloat, GLfloat, GLfloat) {}
 static inline void glBegin(GLenum) {}
 static inline void glEnd(void) {}
@@ -109,4 +109,5 @@ static inline void glutPostRedisplay(void) {}
 #ifdef __cplusplus
 }
 #endif
+#include "vv_gl_stub_renderer.h"
 #endif

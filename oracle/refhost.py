@@ -34,6 +34,8 @@ def _L():
     L.vvref_slicing_setup.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
     L.vvref_slice_polygon.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     L.vvref_clip_cap_polygon.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    L.vvref_renderer_state.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p,
+                                       ctypes.c_float, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     L.vvref_quat_angle_axis.argtypes = [ctypes.c_void_p] * 3
     L.vvref_quat_mult_vec.argtypes = [ctypes.c_void_p] * 3
     return L
@@ -176,3 +178,21 @@ def clip_cap_polygon(plane, extent):
     n = _L().vvref_clip_cap_polygon(pl.ctypes.data, e.ctypes.data, v.ctypes.data, t.ctypes.data, 8)
     assert n >= 0
     return v[:n].copy(), t[:n].copy()
+
+
+def renderer_state(dat_path, filter_png, camera, light, lic_params, lowres, has_scalevolinv, width, height):
+    """Renderer / Camera / Transform driven as VV/3DLIC.cpp does, GL calls captured (oracle/ref_host_driver.cpp):
+    returns dict(modelview[16], light_position[4], slicing=(v[3], d, n), uniforms={name: 4 floats})"""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    q, pos = f32(camera["quat"]), f32(camera["pos"])
+    lq = f32(light["quat"])
+    lp = f32([lic_params.stepSizeVol, lic_params.gradientScale, lic_params.illumScale, lic_params.freqScale, lic_params.numIterations,
+              lic_params.stepsForward, lic_params.stepsBackward, lic_params.stepSizeLIC])
+    out = np.zeros(25 + 40, np.float32)
+    rc = _L().vvref_renderer_state(dat_path.encode(), filter_png.encode() if filter_png else None, q.ctypes.data, pos.ctypes.data,
+                                   float(camera["dist"]), lq.ctypes.data, float(light["dist"]), lp.ctypes.data, int(lowres),
+                                   int(has_scalevolinv), int(width), int(height), out.ctypes.data)
+    assert rc == 0, rc
+    names = ["texMax", "scaleVol", "scaleVolInv", "stepSize", "gradient", "licParams", "licKernel", "numIterations", "alphaCorrection", "viewport"]
+    return dict(modelview=out[:16].copy(), light_position=out[16:20].copy(), slicing=(out[20:23].copy(), float(out[23]), int(out[24])),
+                uniforms={n: out[25 + 4 * i: 29 + 4 * i].copy() for i, n in enumerate(names)})

@@ -366,3 +366,60 @@ def test_clip_cap_polygon(oracle, plane):
                     # only possible at the polygon's very edge
                     assert _inside_convex(P, e[y, x, :3].astype(np.float64), n, eps=1e-4)
     assert seen_caps > 20
+
+
+@pytest.mark.parametrize("case", ["default", "moved_lowres", "anisotropic_illum"])
+def test_renderer_camera_light_uniforms(oracle, tmp_path, case):
+    """VV/renderer.cpp (setRenderVolParams, updateLightPos, updateSlices), camera.cpp and transform.cpp compiled unmodified; their
+    GL matrix / uniform / light calls captured.  Checks the oracle's view (camera position, rotation), light position,
+    slicing set-up and every uniform of the parameter block, including the low-res preset and Q1 (scaleVolInv -> scaleVol)."""
+    import vectorvisualization_b200 as vv
+    from vectorvisualization_b200 import configs, fields as F
+    s = configs.cfg1(n=12, size=48)
+    if case == "moved_lowres":
+        s = configs.cfg2(n=12, size=50, camera=dict(quat=F.quat_from_axis_angle((0.3, -1.0, 0.2), 110.0), pos=(0.15, -0.1, 0.3), dist=3.0, fovy=35.0))
+        s.height = 40
+        s.lowres = 1
+        s.light = dict(quat=F.quat_from_axis_angle((1, 0.2, 0), 40.0), dist=1.5)
+        s.params.update(stepsForward=25, stepsBackward=40, stepSizeLIC=0.02, gradientScale=8.0, freqScale=3.0)
+    if case == "anisotropic_illum":
+        s = configs.cfg3(n=12, size=44, camera=F.CAMERA_CLOSE)
+        s.field = np.ascontiguousarray(F.abc_flow(24)[::2, :16, :])        # 24 x 16 x 12
+        s.slice_dist = (1.0, 1.5, 2.0)
+        s.light = dict(quat=F.quat_from_axis_angle((0.2, 1, 0), 70.0), dist=1.0)
+    dat = F.write_dat(str(tmp_path / "vol.dat"), s.field, slice_thickness=s.slice_dist)
+    with open(dat, "a") as f:
+        f.write("TimeDependent: 0 0\n")
+    kpng = F.write_png(str(tmp_path / "kernel.png"), s.filter_row[None, :]) if s.filter_row is not None else None
+    illum = "ILLUM_" in (s.defines or "")
+    ref = refhost.renderer_state(dat, kpng, s.camera, s.light, s.lic_params(), s.lowres, illum, s.width, s.height)
+    o = oracle.OracleScene(s)
+    cam, rot = _view(oracle, o)
+    # view: rotation block and camera position (= gl_ModelViewMatrixInverse[3]) of the frame's model-view
+    mv = ref["modelview"].astype(np.float64).reshape(4, 4).T            # column-major -> [row][col]
+    assert np.abs(mv[:3, :3] - rot.reshape(3, 3)).max() < 2e-6
+    cam_ref = -mv[:3, :3].T @ mv[:3, 3]
+    assert np.abs(cam_ref - cam).max() < 5e-6
+    # light position
+    lp = np.zeros(4, np.float32)
+    oracle.lib().vvo_light_position(ctypes.byref(o.c), oracle._p(lp))
+    assert np.abs(ref["light_position"][:3] - lp[:3]).max() < 5e-6 and ref["light_position"][3] == 1.0
+    # slicing set-up through Renderer::updateSlices (model-view built by the reference's own GL calls)
+    v_ref, d_ref, n_ref = ref["slicing"]
+    v, d, n = o.slicing_setup()
+    assert n == n_ref and abs(d - d_ref) < 1e-6 and np.abs(np.asarray(v) - v_ref).max() < 2e-6
+    # parameter block
+    un = o.uniforms()
+    u = ref["uniforms"]
+    assert u["stepSize"][0] == np.float32(un[0])
+    assert np.array_equal(u["gradient"][:3], np.asarray(un[1:4], np.float32))
+    assert np.array_equal(u["licParams"][:3], np.asarray(un[4:7], np.float32))
+    assert np.array_equal(u["licKernel"][:3], np.asarray(un[7:10], np.float32))
+    assert u["alphaCorrection"][0] == np.float32(un[10]) and int(u["numIterations"][0]) == int(un[11])
+    sc = np.zeros(9, np.float32)
+    oracle.lib().vvo_scale_uniforms(ctypes.byref(o.c), oracle._p(sc))
+    assert np.array_equal(u["scaleVol"][:3], sc[0:3])                    # Q1: holds scaleInv in ILLUM_* builds
+    assert np.array_equal(u["texMax"][:3], sc[6:9])
+    assert not u["scaleVolInv"].any()                                    # the scaleVolInv slot itself is never written (Q1)
+    rw, rh = (max(s.width // 2, 1), max(s.height // 2, 1)) if s.lowres else (s.width, s.height)
+    assert list(u["viewport"]) == [0, 0, rw, rh]
