@@ -315,6 +315,13 @@ int vvref_illum_tables(float *zoeckler, float *mdiff, float *mspec, int dims[2],
 static std::vector<float> g_poly_vert, g_poly_tex;
 void glVertex3fv(const GLfloat *v) { g_poly_vert.insert(g_poly_vert.end(), v, v + 3); }
 void glMultiTexCoord3fvARB(GLenum, const GLfloat *v) { g_poly_tex.insert(g_poly_tex.end(), v, v + 3); }
+void glVertex3f(GLfloat x, GLfloat y, GLfloat z) { const float v[3] = {x, y, z}; g_poly_vert.insert(g_poly_vert.end(), v, v + 3); }
+void glMultiTexCoord3fARB(GLenum unit, GLfloat x, GLfloat y, GLfloat z)
+{
+    if (unit != GL_TEXTURE0_ARB) return;
+    const float v[3] = {x, y, z};
+    g_poly_tex.insert(g_poly_tex.end(), v, v + 3);
+}
 
 static int copy_poly(float *verts, float *tex, int cap)
 {
@@ -503,6 +510,18 @@ int vvref_renderer_state(const char *dat, const char *filter_png, const float ca
     }
     r._licFilter = NULL;                                    /* stack objects: nothing for ~Renderer to touch */
     return 0;
+}
+
+/* the proxy cube of Renderer::drawCubeFaces (VV/renderer.cpp:682-736): 6 quads, texcoord0 + position per vertex */
+int vvref_cube_faces(const char *dat, float *verts, float *tex, int cap)
+{
+    VectorDataSet vd;
+    if (!vd.loadData(dat)) return -10;
+    Renderer r;
+    r.setVolumeData(vd.getVolumeData());
+    g_poly_vert.clear(); g_poly_tex.clear();
+    r.drawCubeFaces();
+    return copy_poly(verts, tex, cap);
 }
 
 int vvref_next_pow2(int v) { return nextPowerTwo(v); }

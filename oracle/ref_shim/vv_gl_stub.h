@@ -84,7 +84,7 @@ static inline void glBegin(GLenum) {}
 static inline void glEnd(void) {}
 static inline void glVertex2i(GLint, GLint) {}
 static inline void glVertex2f(GLfloat, GLfloat) {}
-static inline void glVertex3f(GLfloat, GLfloat, GLfloat) {}
+void glVertex3f(GLfloat x, GLfloat y, GLfloat z);      /* captured: cube faces of Renderer::drawCubeFaces */
 /* captured (ref_host_driver.cpp): the slice / cap polygons of VV/slicing.cpp */
 void glVertex3fv(const GLfloat *v);
 void glMultiTexCoord3fvARB(GLenum unit, const GLfloat *v);

@@ -50,6 +50,7 @@ void glUniform4fARB(GLint loc, GLfloat a, GLfloat b, GLfloat c, GLfloat d);
 void glUniform4fvARB(GLint loc, GLsizei n, const GLfloat *v);
 void glUniform4iARB(GLint loc, GLint a, GLint b, GLint c, GLint d);
 void glViewport(GLint x, GLint y, GLsizei w, GLsizei h);
+void glMultiTexCoord3fARB(GLenum unit, GLfloat x, GLfloat y, GLfloat z);
 /* ---- no-ops ---- */
 static inline void *wglGetProcAddress(const char *) { return (void *)0; }
 static inline void glNormal3f(GLfloat, GLfloat, GLfloat) {}
@@ -96,7 +97,6 @@ static inline void glMaterialfv(GLenum, GLenum, const GLfloat *) {}
 static inline void glVertex3d(GLdouble, GLdouble, GLdouble) {}
 static inline void glVertex3dv(const GLdouble *) {}
 static inline void glMultiTexCoord4fARB(GLenum, GLfloat, GLfloat, GLfloat, GLfloat) {}
-static inline void glMultiTexCoord3fARB(GLenum, GLfloat, GLfloat, GLfloat) {}
 static inline void glMultiTexCoord3dARB(GLenum, GLdouble, GLdouble, GLdouble) {}
 static inline void glMultiTexCoord3dvARB(GLenum, const GLdouble *) {}
 static inline void gluOrtho2D(GLdouble, GLdouble, GLdouble, GLdouble) {}

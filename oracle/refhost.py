@@ -36,6 +36,7 @@ def _L():
     L.vvref_clip_cap_polygon.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     L.vvref_renderer_state.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p,
                                        ctypes.c_float, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.vvref_cube_faces.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     L.vvref_quat_angle_axis.argtypes = [ctypes.c_void_p] * 3
     L.vvref_quat_mult_vec.argtypes = [ctypes.c_void_p] * 3
     return L
@@ -196,3 +197,11 @@ def renderer_state(dat_path, filter_png, camera, light, lic_params, lowres, has_
     names = ["texMax", "scaleVol", "scaleVolInv", "stepSize", "gradient", "licParams", "licKernel", "numIterations", "alphaCorrection", "viewport"]
     return dict(modelview=out[:16].copy(), light_position=out[16:20].copy(), slicing=(out[20:23].copy(), float(out[23]), int(out[24])),
                 uniforms={n: out[25 + 4 * i: 29 + 4 * i].copy() for i, n in enumerate(names)})
+
+
+def cube_faces(dat_path):
+    """Renderer::drawCubeFaces: (verts [24][3], texcoords [24][3]), four vertices per quad"""
+    v = np.zeros((24, 3), np.float32); t = np.zeros((24, 3), np.float32)
+    n = _L().vvref_cube_faces(dat_path.encode(), v.ctypes.data, t.ctypes.data, 24)
+    assert n == 24, n
+    return v, t

@@ -423,3 +423,30 @@ def test_renderer_camera_light_uniforms(oracle, tmp_path, case):
     assert not u["scaleVolInv"].any()                                    # the scaleVolInv slot itself is never written (Q1)
     rw, rh = (max(s.width // 2, 1), max(s.height // 2, 1)) if s.lowres else (s.width, s.height)
     assert list(u["viewport"]) == [0, 0, rw, rh]
+
+
+def test_proxy_cube_faces(oracle, tmp_path):
+    """Renderer::drawCubeFaces (VV/renderer.cpp:682-736): the proxy geometry is the box [0, extent]^3, every vertex carries its
+    own position as texcoord0 (so a fragment's gl_TexCoord[0] is the point where the pixel ray enters the box -- the oracle's
+    pixel_ray), and every quad is wound counter-clockwise seen from outside (front faces survive glEnable(GL_CULL_FACE))"""
+    from vectorvisualization_b200 import configs, fields as F
+    s = configs.cfg1(n=12, size=16)
+    s.field = np.ascontiguousarray(F.abc_flow(24)[::2, :16, :])            # 24 x 16 x 12, anisotropic spacing
+    s.slice_dist = (1.0, 1.5, 2.0)
+    dat = F.write_dat(str(tmp_path / "vol.dat"), s.field, slice_thickness=s.slice_dist)
+    with open(dat, "a") as f:
+        f.write("TimeDependent: 0 0\n")
+    verts, tex = refhost.cube_faces(dat)
+    assert np.array_equal(verts, tex)
+    o = oracle.OracleScene(s)
+    ext = np.array(list(o.c.extent), np.float32)
+    assert set(np.unique(verts[:, 0])) == {0.0, ext[0]} and set(np.unique(verts[:, 1])) == {0.0, ext[1]} and set(np.unique(verts[:, 2])) == {0.0, ext[2]}
+    centre = ext.astype(np.float64) / 2
+    for q in range(6):
+        P = verts[4 * q: 4 * q + 4].astype(np.float64)
+        newell = sum(np.cross(P[i], P[(i + 1) % 4]) for i in range(4))
+        outward = P.mean(axis=0) - centre
+        assert np.dot(newell, outward) > 0
+        # planar, on a face of the box
+        axis = int(np.argmax(np.abs(outward)))
+        assert len(set(P[:, axis])) == 1
