@@ -284,6 +284,11 @@ def test_slicing_setup_and_polygons(oracle):
         polys = [refhost.slice_polygon(mv, step, ext, i) for i in range(n_ref)]
         for verts, tex in polys:
             assert np.array_equal(verts, tex)                      # texcoord0 = vertex position (volume coordinates)
+        # Renderer::sliceVolume draws drawSlice(0), drawSlice(1), ... (VV/renderer.cpp:1176-1225): increasing index must be
+        # increasing depth along the view vector, which points away from the camera -> front to back
+        depth = [float(np.dot(np.asarray(v_ref, np.float64), vt[0].astype(np.float64) - ext / 2)) for vt, _ in polys if len(vt) >= 3]
+        assert all(b > a for a, b in zip(depth, depth[1:]))
+        assert float(np.dot(np.asarray(v_ref, np.float64), ext / 2 - cam)) > 0
         buf = np.zeros((n_ref, 4), np.float32)
         ent = (ctypes.c_float * 3)(); dr = (ctypes.c_float * 3)()
         rng = np.random.RandomState(2)
