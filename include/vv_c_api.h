@@ -132,7 +132,9 @@ VV_API int vv_set_default_tf(VVRenderer *r);
 /* setLICParams, VV/renderer.h:103 */
 VV_API int vv_set_lic_params(VVRenderer *r, const VVLicParams *p);
 VV_API void vv_default_lic_params(VVLicParams *p);
-/* setCamera (Camera, VV/camera.cpp:42-68): quaternion (x,y,z,w), translation, distance, fovy (deg), near, far */
+/* setCamera (Camera, VV/camera.cpp:42-68): quaternion (x,y,z,w), translation, distance, fovy (deg), near, far (the
+ * reference's defaults: 0.1, 50).  near / far bound the view volume the GL clips the proxy geometry to: a pixel whose ray enters
+ * the box (or a slice / cap polygon) at an eye-space depth outside [near, far] has no fragment, as in the reference. */
 VV_API int vv_set_camera(VVRenderer *r, const float quat[4], const float pos[3], float dist, float fovy,
                          float near_clip, float far_clip);
 /* setLight + updateLightPos (Transform, VV/renderer.cpp:431-466) */
@@ -166,7 +168,10 @@ VV_API int vv_update_mc_offset_tex(VVRenderer *r, int width, int height, uint32_
  * half-space n.q + d >= 0 is kept; NULL keeps the stored equation.  Semantics as drawn by Renderer::render
  * (VV/renderer.cpp:156-163, 1294-1309): the front faces of the proxy cube and the slice polygons are clipped, and for
  * the two ray-cast techniques each active plane adds the box cross-section n^.q = -(d - 0.0001) as a ray-entry polygon
- * (culled when it faces away); rays still leave through the box, as in the reference. */
+ * (culled when it faces away); rays still leave through the box, as in the reference.  The plane is evaluated as
+ * (n / |n|, d): the reference normalises the normal in place the first time it draws the plane's cap (VV/renderer.cpp:1301
+ * hands ClipPlane::getNormal() to ViewSlicing::setupSingleSlice, VV/slicing.cpp:337-348), d untouched, so that is the plane
+ * every frame but the first is clipped with (the reference's own callers only ever pass unit normals). */
 VV_API int vv_set_clip_plane(VVRenderer *r, int index, const double equation[4], int active);
 /* setIllum*Tex (Illumination, VV/illumination.cpp:96-390): the Zoeckler / Mallo look-up tables are generated inside the
  * library when an ILLUM_MALLO / ILLUM_ZOECKLER build is selected; this host-only entry point returns the same tables

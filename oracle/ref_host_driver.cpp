@@ -313,14 +313,39 @@ int vvref_illum_tables(float *zoeckler, float *mdiff, float *mspec, int dims[2],
  * (ClipPlane::drawSlice, VV/transform.cpp:432-444 = setupSingleSlice(normal, extent) + drawSingleSlice(-(d - 0.0001))).
  * The polygons are captured from the glMultiTexCoord3fvARB / glVertex3fv calls the reference makes. */
 static std::vector<float> g_poly_vert, g_poly_tex;
-void glVertex3fv(const GLfloat *v) { g_poly_vert.insert(g_poly_vert.end(), v, v + 3); }
-void glMultiTexCoord3fvARB(GLenum, const GLfloat *v) { g_poly_tex.insert(g_poly_tex.end(), v, v + 3); }
-void glVertex3f(GLfloat x, GLfloat y, GLfloat z) { const float v[3] = {x, y, z}; g_poly_vert.insert(g_poly_vert.end(), v, v + 3); }
+/* draw list: every glBegin/glEnd primitive with the state it was issued under; vertices = position + the texcoord0
+ * current at glVertex time (GL 2.1 spec 2.6: current values are latched per vertex) */
+struct Mat4 { double m[16]; };
+struct DrawRec {
+    unsigned program, mode;
+    int cull, clip_mask, viewport[4];
+    Mat4 mv, proj;
+    double clip_eye[6][4];
+    std::vector<double> v;          /* x y z s t r per vertex */
+};
+static std::vector<DrawRec> g_draws;
+static bool g_record_draws = false, g_in_prim = false;
+static float g_cur_tc[3] = {0.0f, 0.0f, 0.0f};
+static void draw_vertex(const float *v)
+{
+    if (!g_record_draws || !g_in_prim || g_draws.empty()) return;
+    std::vector<double> &d = g_draws.back().v;
+    for (int k = 0; k < 3; ++k) d.push_back((double)v[k]);
+    for (int k = 0; k < 3; ++k) d.push_back((double)g_cur_tc[k]);
+}
+void glVertex3fv(const GLfloat *v) { g_poly_vert.insert(g_poly_vert.end(), v, v + 3); draw_vertex(v); }
+void glMultiTexCoord3fvARB(GLenum unit, const GLfloat *v)
+{
+    g_poly_tex.insert(g_poly_tex.end(), v, v + 3);
+    if (unit == GL_TEXTURE0_ARB) for (int k = 0; k < 3; ++k) g_cur_tc[k] = v[k];
+}
+void glVertex3f(GLfloat x, GLfloat y, GLfloat z) { const float v[3] = {x, y, z}; g_poly_vert.insert(g_poly_vert.end(), v, v + 3); draw_vertex(v); }
 void glMultiTexCoord3fARB(GLenum unit, GLfloat x, GLfloat y, GLfloat z)
 {
     if (unit != GL_TEXTURE0_ARB) return;
     const float v[3] = {x, y, z};
     g_poly_tex.insert(g_poly_tex.end(), v, v + 3);
+    for (int k = 0; k < 3; ++k) g_cur_tc[k] = v[k];
 }
 
 static int copy_poly(float *verts, float *tex, int cap)
@@ -370,7 +395,6 @@ int vvref_clip_cap_polygon(const double plane[4], const float ext[3], float *ver
 /* ---- GL matrix stack / uniform / light capture for VV/renderer.cpp, camera.cpp, transform.cpp -------------------
  * The matrix arithmetic is the OpenGL 2.1 specification's (section 2.11.2: Translate, Rotate; gluPerspective per the
  * GLU reference), in double; what the reference contributes is the sequence of calls and their arguments. */
-struct Mat4 { double m[16]; };
 static Mat4 mat_identity() { Mat4 r; for (int i = 0; i < 16; ++i) r.m[i] = (i % 5 == 0) ? 1.0 : 0.0; return r; }
 static Mat4 mat_mul(const Mat4 &a, const Mat4 &b)      /* column-major a * b */
 {
@@ -442,7 +466,70 @@ void glLightfv(GLenum, GLenum pname, const GLfloat *v)
     for (int r = 0; r < 4; ++r)
         g_light_pos[r] = (float)(m.m[r] * v[0] + m.m[4 + r] * v[1] + m.m[8 + r] * v[2] + m.m[12 + r] * v[3]);
 }
-void glClipPlane(GLenum plane, const GLdouble *eq) { int i = (int)plane - GL_CLIP_PLANE0; if (i >= 0 && i < 6) for (int k = 0; k < 4; ++k) g_clip[i][k] = eq[k]; }
+/* inverse of a general 4x4 (cofactors), column-major */
+static bool mat_inverse(const Mat4 &a, Mat4 &out)
+{
+    const double *m = a.m;
+    double inv[16];
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const double det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    if (det == 0.0) return false;
+    for (int i = 0; i < 16; ++i) out.m[i] = inv[i] / det;
+    return true;
+}
+static double g_clip_eye[6][4];
+static int g_clip_mask = 0, g_cull = 0;
+static GLhandleARB g_program = 0;
+/* GL 2.1 spec 2.12: the plane is stored in eye coordinates, (p1' p2' p3' p4') = (p1 p2 p3 p4) M^-1 with the model-view
+ * of the time of the call */
+void glClipPlane(GLenum plane, const GLdouble *eq)
+{
+    int i = (int)plane - GL_CLIP_PLANE0;
+    if (i < 0 || i >= 6) return;
+    for (int k = 0; k < 4; ++k) g_clip[i][k] = eq[k];
+    Mat4 inv;
+    if (!mat_inverse(g_mv.back(), inv)) inv = mat_identity();
+    for (int c = 0; c < 4; ++c)
+        g_clip_eye[i][c] = eq[0] * inv.m[4 * c + 0] + eq[1] * inv.m[4 * c + 1] + eq[2] * inv.m[4 * c + 2] + eq[3] * inv.m[4 * c + 3];
+}
+void glEnable(GLenum cap)
+{
+    if (cap == GL_CULL_FACE) g_cull = 1;
+    else if (cap >= GL_CLIP_PLANE0 && cap < GL_CLIP_PLANE0 + 6) g_clip_mask |= 1 << (cap - GL_CLIP_PLANE0);
+}
+void glDisable(GLenum cap)
+{
+    if (cap == GL_CULL_FACE) g_cull = 0;
+    else if (cap >= GL_CLIP_PLANE0 && cap < GL_CLIP_PLANE0 + 6) g_clip_mask &= ~(1 << (cap - GL_CLIP_PLANE0));
+}
+void glUseProgramObjectARB(GLhandleARB program) { g_program = program; }
+void glBegin(GLenum mode)
+{
+    g_in_prim = true;
+    if (!g_record_draws) return;
+    DrawRec d;
+    d.program = g_program; d.mode = mode; d.cull = g_cull; d.clip_mask = g_clip_mask;
+    for (int k = 0; k < 4; ++k) d.viewport[k] = g_viewport[k];
+    d.mv = g_mv.back(); d.proj = g_proj.back();
+    std::memcpy(d.clip_eye, g_clip_eye, sizeof(d.clip_eye));
+    g_draws.push_back(d);
+}
+void glEnd(void) { g_in_prim = false; }
 void glUniform1iARB(GLint loc, GLint v) { g_uniform[loc] = {(float)v}; }
 void glUniform1fARB(GLint loc, GLfloat v) { g_uniform[loc] = {v}; }
 void glUniform3fARB(GLint loc, GLfloat a, GLfloat b, GLfloat c) { g_uniform[loc] = {a, b, c}; }
@@ -522,6 +609,96 @@ int vvref_cube_faces(const char *dat, float *verts, float *tex, int cap)
     g_poly_vert.clear(); g_poly_tex.clear();
     r.drawCubeFaces();
     return copy_poly(verts, tex, cap);
+}
+
+/* One frame of Renderer::render(true) in ray-cast mode (VV/renderer.cpp:126-312), run unmodified; every glBegin/glEnd primitive is
+ * recorded with the program, matrices, viewport, cull / clip state it was issued under.  Serialised as doubles:
+ *   out[0] = number of primitives, then per primitive
+ *   program, mode, cull, clip_mask, viewport[4], modelview[16], projection[16], clip planes in eye space [6][4], nverts,
+ *   nverts x (x y z s t r)
+ * The ray-cast program has the handle 77, the slicing program 79 (set below; no GLSL is compiled in the shim); slicing != 0
+ * renders with VOLIC_SLICING (after Renderer::updateSlices) instead of VOLIC_RAYCAST; step_size_vol > 0 overrides LICParams.  planes: up to 3 user clip planes
+ * (n.xyz, d) as ClipPlane::setNormal takes them, active[i] != 0 to enable; frames >= 1: how many frames to render, the last one
+ * is the one returned.  Returns the number of doubles written, < 0 on error. */
+int vvref_raycast_draws(const char *dat, const float cam_quat[4], const float cam_pos[3], float cam_dist, int width, int height,
+                        int lowres, const double planes[3][4], const int active[3], int frames, int slicing, float step_size_vol,
+                        double *out, int cap)
+{
+    VectorDataSet vd;
+    if (!vd.loadData(dat)) return -10;
+    LICFilter filt;
+    filt.createBoxFilter();
+    LICParams lp;
+    if (step_size_vol > 0.0f) lp.stepSizeVol = step_size_vol;
+    Camera cam;
+    Quaternion q; q.x = cam_quat[0]; q.y = cam_quat[1]; q.z = cam_quat[2]; q.w = cam_quat[3];
+    cam.rotate(q);
+    cam.setPosition(Vector3_new(cam_pos[0], cam_pos[1], cam_pos[2]));
+    cam.setDistance(cam_dist);
+    cam.setWindow(width, height);
+    Transform light;
+    ClipPlane cp[3];
+    VolumeData *v = vd.getVolumeData();
+    for (int i = 0; i < 3; ++i) {
+        cp[i].setPlaneId(GL_CLIP_PLANE0 + i);                          /* VV/3DLIC.cpp:768-781 */
+        cp[i].setBoundingBox(-v->extent[0] / 2.0f, -v->extent[1] / 2.0f, -v->extent[2] / 2.0f, v->extent[0] / 2.0f, v->extent[1] / 2.0f, v->extent[2] / 2.0f);
+        cp[i].setNormal(planes[i][0], planes[i][1], planes[i][2], planes[i][3]);
+        cp[i].setActive(active[i] != 0);
+    }
+    Texture dummy[8];
+    Renderer r;
+    r.setVolumeData(v);
+    r._licFilter = &filt;
+    r.setLICParams(&lp);
+    r.setCamera(&cam);
+    r.setLight(&light);
+    r.setClipPlanes(cp, 3);
+    r._dataTex = &dummy[0]; r._tfRGBTex = &dummy[1]; r._tfAlphaOpacTex = &dummy[2]; r._noiseTex = &dummy[3];
+    r._scalarTex = &dummy[4]; r._licKernelTex = &dummy[5];
+    r._raycastShader._programObj = 77;
+    r._bgShader._programObj = 78;
+    std::memset(&r._paramRaycast, 0xff, sizeof(r._paramRaycast));      /* every uniform location -1: no GLSL program in the shim */
+    std::memset(&r._paramBackground, 0xff, sizeof(r._paramBackground));
+    r._sliceShader._programObj = 79;
+    std::memset(&r._paramSlice, 0xff, sizeof(r._paramSlice));
+    r._paramSlice.imageFBOSampler = 20;                                 /* sliceVolume returns early without it (:1127) */
+    r.enableLowRes(lowres != 0);
+    r.resize(width, height);                                            /* VV/3DLIC.cpp:174-200 */
+    if (slicing) {
+        r._useFBO = true;                                               /* the FBO ping-pong branch of sliceVolume (keys F3, VV/3DLIC.cpp:457-475) */
+        r.setTechnique(VOLIC_SLICING);
+    } else {
+        r.setTechnique(VOLIC_RAYCAST);
+    }
+    g_mv.assign(1, mat_identity()); g_proj.assign(1, mat_identity()); g_mode = GL_MODELVIEW;
+    g_clip_mask = 0; g_cull = 0; g_program = 0;
+    glViewport(0, 0, width, height);                                    /* resize callback, VV/3DLIC.cpp:176 */
+    /* `frames` calls of render(true); the LAST one is recorded.  (The first frame differs for non-unit plane normals:
+     * drawClippedPolygon normalises ClipPlane::_normal in place, VV/renderer.cpp:1301 -> VV/slicing.cpp:337-348.) */
+    if (slicing) r.updateSlices();                                      /* VV/3DLIC.cpp:168, 469 */
+    for (int f = 0; f < frames; ++f) {
+        g_draws.clear();
+        g_record_draws = true;
+        r.render(true);
+        g_record_draws = false;
+    }
+    r._licFilter = NULL;
+    size_t need = 1;
+    for (const DrawRec &d : g_draws) need += 4 + 4 + 16 + 16 + 24 + 1 + d.v.size();
+    if ((size_t)cap < need) { g_draws.clear(); return -2; }
+    size_t k = 0;
+    out[k++] = (double)g_draws.size();
+    for (const DrawRec &d : g_draws) {
+        out[k++] = d.program; out[k++] = d.mode; out[k++] = d.cull; out[k++] = d.clip_mask;
+        for (int i = 0; i < 4; ++i) out[k++] = d.viewport[i];
+        for (int i = 0; i < 16; ++i) out[k++] = d.mv.m[i];
+        for (int i = 0; i < 16; ++i) out[k++] = d.proj.m[i];
+        for (int i = 0; i < 6; ++i) for (int j = 0; j < 4; ++j) out[k++] = d.clip_eye[i][j];
+        out[k++] = (double)(d.v.size() / 6);
+        for (double x : d.v) out[k++] = x;
+    }
+    g_draws.clear();
+    return (int)k;
 }
 
 int vvref_next_pow2(int v) { return nextPowerTwo(v); }

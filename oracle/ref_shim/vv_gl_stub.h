@@ -80,8 +80,8 @@ void glLoadIdentity(void);
 static inline void glOrtho(GLdouble, GLdouble, GLdouble, GLdouble, GLdouble, GLdouble) {}
 void glTranslatef(GLfloat x, GLfloat y, GLfloat z);
 static inline void glScalef(GLfloat, GLfloat, GLfloat) {}
-static inline void glBegin(GLenum) {}
-static inline void glEnd(void) {}
+void glBegin(GLenum mode);                              /* captured: draw list (oracle/softgl.py rasterises it) */
+void glEnd(void);
 static inline void glVertex2i(GLint, GLint) {}
 static inline void glVertex2f(GLfloat, GLfloat) {}
 void glVertex3f(GLfloat x, GLfloat y, GLfloat z);      /* captured: cube faces of Renderer::drawCubeFaces */
@@ -94,8 +94,8 @@ static inline void glColor3f(GLfloat, GLfloat, GLfloat) {}
 static inline void glColor4f(GLfloat, GLfloat, GLfloat, GLfloat) {}
 static inline void glColor4fv(const GLfloat *) {}
 static inline void glColor3fv(const GLfloat *) {}
-static inline void glEnable(GLenum) {}
-static inline void glDisable(GLenum) {}
+void glEnable(GLenum cap);                              /* captured: GL_CULL_FACE, GL_CLIP_PLANEi */
+void glDisable(GLenum cap);
 static inline void glBlendFunc(GLenum, GLenum) {}
 static inline void glPushAttrib(GLbitfield) {}
 static inline void glPopAttrib(void) {}

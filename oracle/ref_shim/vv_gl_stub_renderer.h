@@ -51,6 +51,7 @@ void glUniform4fvARB(GLint loc, GLsizei n, const GLfloat *v);
 void glUniform4iARB(GLint loc, GLint a, GLint b, GLint c, GLint d);
 void glViewport(GLint x, GLint y, GLsizei w, GLsizei h);
 void glMultiTexCoord3fARB(GLenum unit, GLfloat x, GLfloat y, GLfloat z);
+void glUseProgramObjectARB(GLhandleARB program);       /* the program bound when a primitive is drawn */
 /* ---- no-ops ---- */
 static inline void *wglGetProcAddress(const char *) { return (void *)0; }
 static inline void glNormal3f(GLfloat, GLfloat, GLfloat) {}
@@ -72,7 +73,6 @@ static inline void glTexCoord3f(GLfloat, GLfloat, GLfloat) {}
 static inline void glCopyTexSubImage3D(GLenum, GLint, GLint, GLint, GLint, GLint, GLint, GLsizei, GLsizei) {}
 static inline void glCopyTexImage2D(GLenum, GLint, GLenum, GLint, GLint, GLsizei, GLsizei, GLint) {}
 static inline void glGetObjectParameterivARB(GLhandleARB, GLenum, GLint *v) { if (v) *v = 0; }
-static inline void glUseProgramObjectARB(GLhandleARB) {}
 static inline void glShaderSourceARB(GLhandleARB, GLsizei, const GLcharARB **, const GLint *) {}
 static inline void glGetInfoLogARB(GLhandleARB, GLsizei, GLsizei *len, GLcharARB *log) { if (len) *len = 0; if (log) log[0] = 0; }
 static inline void glGetActiveUniformARB(GLhandleARB, GLuint, GLsizei, GLsizei *len, GLint *size, GLenum *type, GLcharARB *name)

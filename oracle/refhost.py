@@ -205,3 +205,43 @@ def cube_faces(dat_path):
     n = _L().vvref_cube_faces(dat_path.encode(), v.ctypes.data, t.ctypes.data, 24)
     assert n == 24, n
     return v, t
+
+
+def raycast_draws(dat_path, camera, width, height, lowres=0, planes=(), frames=2, slicing=False, step_size_vol=0.0):
+    """Renderer::render(true) in ray-cast mode, run unmodified with the GL calls captured: the list of glBegin/glEnd primitives,
+    each a dict(program, mode, cull, clip_mask, viewport[4], modelview[4][4], projection[4][4], clip_eye[6][4],
+    verts[n][3], tex[n][3]).  program 77 = the LIC ray-cast program, 79 = the slicing program, 78 = the background program, 0 = fixed function.
+    frames: render(true) is called that many times and the last frame is returned (2 = the steady state, see the driver)."""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    q, pos = f32(camera["quat"]), f32(camera["pos"])
+    pl = np.zeros((3, 4), np.float64)
+    pl[:, 2] = -1.0
+    act = (ctypes.c_int * 3)(0, 0, 0)
+    for i, p in enumerate(planes):
+        pl[i] = p
+        act[i] = 1
+    cap = 1 << 20
+    out = np.zeros(cap, np.float64)
+    L = _L()
+    L.vvref_raycast_draws.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                      ctypes.c_void_p, ctypes.c_int]
+    n = L.vvref_raycast_draws(dat_path.encode(), q.ctypes.data, pos.ctypes.data, float(camera["dist"]), int(width), int(height),
+                              int(lowres), pl.ctypes.data, act, int(frames), int(bool(slicing)), float(step_size_vol),
+                              out.ctypes.data, cap)
+    assert n > 0, n
+    k = 1
+    draws = []
+    for _ in range(int(out[0])):
+        d = dict(program=int(out[k]), mode=int(out[k + 1]), cull=int(out[k + 2]), clip_mask=int(out[k + 3]),
+                 viewport=[int(x) for x in out[k + 4:k + 8]])
+        k += 8
+        d["modelview"] = out[k:k + 16].reshape(4, 4).T.copy(); k += 16          # column-major -> [row][col]
+        d["projection"] = out[k:k + 16].reshape(4, 4).T.copy(); k += 16
+        d["clip_eye"] = out[k:k + 24].reshape(6, 4).copy(); k += 24
+        nv = int(out[k]); k += 1
+        v = out[k:k + 6 * nv].reshape(nv, 6); k += 6 * nv
+        d["verts"], d["tex"] = v[:, :3].copy(), v[:, 3:].copy()
+        draws.append(d)
+    assert k == n
+    return draws

@@ -173,22 +173,27 @@ class RefScene:
         vvo.lib().vvo_pixel_rays(ctypes.byref(self.o.c), x0, y0, x1, y1, vvo._p(tc))
         return tc
 
-    def raycast(self, rect=None):
+    def raycast(self, rect=None, texcoords=None):
+        """texcoords: optional [h][w][4] fragment texcoord0 (w = 1 where the pixel has a fragment) to shade instead of the
+        oracle's analytic ray entry points -- e.g. the fragments oracle/softgl.py rasterises from the reference's own draw calls"""
         s = self.s
         rect = rect or (0, 0, s.width, s.height)
         x0, y0, x1, y1 = rect
         self._set_scale(raycast=True)
         self.u.frag_x0, self.u.frag_y0, self.u.frag_w = x0, y0, x1 - x0
-        out, cnt = self._run(self.program("raycast"), self._rays(rect))
+        tc = self._rays(rect) if texcoords is None else np.ascontiguousarray(np.asarray(texcoords, np.float32)[y0:y1, x0:x1].reshape(-1, 4))
+        out, cnt = self._run(self.program("raycast"), tc)
         img = np.zeros((s.height, s.width, 4), np.float32)
         cm = np.zeros((s.height, s.width), np.uint32)
         img[y0:y1, x0:x1] = out.reshape(y1 - y0, x1 - x0, 4)
         cm[y0:y1, x0:x1] = cnt.reshape(y1 - y0, x1 - x0)
         return img, cm, int(cnt.sum())
 
-    def slicing(self):
+    def slicing(self, fragments=None):
         """lic3d_slicing_fragment.glsl over the oracle's slice geometry; the shader hard-codes TF index .a and the
-        tfData.a > 0.05 gate, so the scene must use tf_mode A / gate TF_ALPHA"""
+        tfData.a > 0.05 gate, so the scene must use tf_mode A / gate TF_ALPHA.
+        fragments: optional (starts int32 [h*w + 1], frags [n][3]) per-pixel fragment lists in draw order to shade instead
+        (oracle/softgl.py fragment_lists of the reference's own slice polygons)"""
         s = self.s
         assert s.tf_mode == 1 and s.gate_mode == 1
         d = s.defines or ""
@@ -202,16 +207,22 @@ class RefScene:
         self._set_scale(raycast=True)
         self.u.frag_x0, self.u.frag_y0, self.u.frag_w = 0, 0, s.width
         L = lib()
-        _, _, nslices = self.o.slicing_setup()
-        frags, starts = [], [0]
-        buf = np.zeros((nslices, 4), np.float32)
-        for y in range(s.height):
-            for x in range(s.width):
-                n = vvo.lib().vvo_slice_fragments(ctypes.byref(self.o.c), x, y, vvo._p(buf), nslices)
-                frags.append(buf[:n].copy())
-                starts.append(starts[-1] + n)
-        fr = np.ascontiguousarray(np.concatenate(frags, axis=0) if frags else np.zeros((0, 4), np.float32))
-        st = np.asarray(starts, np.int32)
+        if fragments is not None:
+            st = np.ascontiguousarray(fragments[0], np.int32)
+            fr = np.zeros((len(fragments[1]), 4), np.float32)
+            fr[:, :3] = fragments[1]
+            fr[:, 3] = 1.0
+        else:
+            _, _, nslices = self.o.slicing_setup()
+            frags, starts = [], [0]
+            buf = np.zeros((nslices, 4), np.float32)
+            for y in range(s.height):
+                for x in range(s.width):
+                    n = vvo.lib().vvo_slice_fragments(ctypes.byref(self.o.c), x, y, vvo._p(buf), nslices)
+                    frags.append(buf[:n].copy())
+                    starts.append(starts[-1] + n)
+            fr = np.ascontiguousarray(np.concatenate(frags, axis=0) if frags else np.zeros((0, 4), np.float32))
+            st = np.asarray(starts, np.int32)
         npix = s.width * s.height
         out = np.zeros((npix, 4), np.float32)
         cnt = np.zeros(npix, np.uint32)

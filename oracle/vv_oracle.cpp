@@ -340,6 +340,19 @@ void make_ctx(const VVOScene *s, Ctx &c, bool raycast_program = true)
  * renderer.h:168-172): the fragment's gl_TexCoord[0] is the point where the pixel ray enters the box
  * [0,extent]^3.  Analytic slab test in double, rounded once to float; the coordinate of the entry
  * face is exact (it is constant over the rasterised quad). */
+/* Plane j as the GL holds it from the second frame on: (n / |n|, d); |n| <= VS_EPS zeroes the normal (slicing.cpp:337-348) */
+inline void clip_equation(const VVOScene *s, int j, double out[4])
+{
+    const double *e = s->clip_planes[j];
+    const double len = std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+    for (int k = 0; k < 3; ++k) out[k] = (len > 1e-8) ? e[k] / len : 0.0;
+    out[3] = e[3];
+}
+
+/* view-volume clipping of the proxy geometry (GL 2.1 spec 2.12): the pixel ray's parameter t is the eye-space depth of
+ * o + t d because d = R^T (ex, ey, -1) */
+inline bool in_depth_range(const VVOScene *s, double t) { return t >= (double)s->near_clip && t <= (double)s->far_clip; }
+
 bool pixel_ray(const Ctx &c, int px, int py, V3 &entry)
 {
     const VVOScene *s = c.s;
@@ -365,8 +378,9 @@ bool pixel_ray(const Ctx &c, int px, int py, V3 &entry)
         if (t0 > tn) { tn = t0; face = i; faceval = fv; }
         if (t1 < tf) tf = t1;
     }
-    /* front faces only (back faces culled, renderer.cpp:1099): camera must be outside the box */
-    bool have = (tn < tf) && tn > 0.0 && face >= 0;
+    /* front faces only (back faces culled, renderer.cpp:1099): camera outside the box; the part of a face nearer than the
+     * near plane is clipped away, and the fragment with it */
+    bool have = (tn < tf) && in_depth_range(s, tn) && face >= 0;
     double p[3] = {0.0, 0.0, 0.0};
     if (have) {
         for (int i = 0; i < 3; ++i) p[i] = o[i] + tn * d[i];
@@ -384,10 +398,12 @@ bool pixel_ray(const Ctx &c, int px, int py, V3 &entry)
          * test and no blending in the FBO (renderer.cpp:1097-1101): the last fragment drawn under a pixel is the one the
          * shader's result is kept for. */
         double ctr[3] = {s->center[0], s->center[1], s->center[2]};
+        double eq[3][4];
+        for (int j = 0; j < nc; ++j) clip_equation(s, j, eq[j]);
         auto kept = [&](const double q[3], int skip) {
             for (int j = 0; j < nc; ++j) {
                 if (j == skip) continue;
-                const double *e = s->clip_planes[j];
+                const double *e = eq[j];
                 if (e[0] * q[0] + e[1] * q[1] + e[2] * q[2] + e[3] < 0.0) return false;
             }
             return true;
@@ -406,7 +422,7 @@ bool pixel_ray(const Ctx &c, int px, int py, V3 &entry)
             double dn = n[0] * d[0] + n[1] * d[1] + n[2] * d[2];
             if (!(dn > 0.0)) continue;                                     /* cap faces away from the viewer: culled */
             double t = (dist - (n[0] * oc[0] + n[1] * oc[1] + n[2] * oc[2])) / dn;
-            if (!(t > 0.0)) continue;
+            if (!in_depth_range(s, t)) continue;
             double q[3] = {oc[0] + t * d[0], oc[1] + t * d[1], oc[2] + t * d[2]};
             bool inside = true;
             for (int k = 0; k < 3; ++k)
@@ -484,7 +500,7 @@ inline bool slice_fragment(const Ctx &c, const Slicing &sl, const PixelRay &r, i
     double b = r.d[0] * (double)sl.v[0] + r.d[1] * (double)sl.v[1] + r.d[2] * (double)sl.v[2];
     if (b == 0.0) return false;
     double t = ((double)slice_offset(sl, slice) - a) / b;
-    if (!(t > 0.0)) return false;
+    if (!in_depth_range(s, t)) return false;
     double p[3];
     for (int i = 0; i < 3; ++i) {
         p[i] = r.o[i] + t * r.d[i];
@@ -492,7 +508,8 @@ inline bool slice_fragment(const Ctx &c, const Slicing &sl, const PixelRay &r, i
     }
     /* user clip planes are enabled around sliceVolume too (renderer.cpp:156-163): the slice polygons are clipped */
     for (int j = 0; j < s->num_clip_planes; ++j) {
-        const double *e = s->clip_planes[j];
+        double e[4];
+        clip_equation(s, j, e);
         double q[3] = {p[0] - (double)s->center[0], p[1] - (double)s->center[1], p[2] - (double)s->center[2]};
         if (e[0] * q[0] + e[1] * q[1] + e[2] * q[2] + e[3] < 0.0) return false;
     }

@@ -74,7 +74,12 @@ typedef struct VVOScene {
     const float *mc_offsets;   /* USE_MC_OFFSET (lic3d_fragment.glsl:31-33, renderer.cpp:636-679): [height][width] ray-start
                                   offsets in [0,1], already fp16-rounded (GL_LUMINANCE16F rectangle texture); NULL = off */
     int    num_clip_planes;    /* active user clip planes (transform.cpp:424-449, renderer.cpp:156-163,1294-1309) */
-    double clip_planes[3][4];  /* glClipPlane equations (n.xyz, d) in volume-centred object space: n.q + d >= 0 is kept */
+    double clip_planes[3][4];  /* ClipPlane::setNormal arguments (n.xyz, d) in volume-centred object space.  The reference normalises
+                                  n IN PLACE the first time the plane's cap is drawn (drawClippedPolygon hands getNormal() to
+                                  ViewSlicing::setupSingleSlice, renderer.cpp:1301, slicing.cpp:337-348), d untouched: from then
+                                  on the GL plane is n^.q + d >= 0.  The oracle evaluates that steady state. */
+    float  near_clip, far_clip; /* gluPerspective near / far (camera.cpp:42-47: 0.1, 50): GL clips the proxy geometry to the view
+                                  volume, so a fragment exists only where its eye-space depth lies in [near, far] */
 } VVOScene;
 
 /* ---- hot path ------------------------------------------------------- */

@@ -820,3 +820,39 @@ def test_noise_layouts_bit_identical(vv):
         r.render(True)
         out.append(r.readRGBA32F())
     assert np.array_equal(out[0], out[1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("technique", ["raycast", "slicing"])
+def test_near_plane_clips_the_proxy_geometry(vv, oracle, technique):
+    """GL clips the cube faces / slice polygons to the view volume: where the entry point lies nearer than gluPerspective's
+    near plane (0.1, VV/camera.cpp:42-47) the reference has no fragment -- a hole in the frame -- and slices nearer than it are
+    dropped (tests/test_softgl_vs_ref.py pins this against the reference's own draw calls)"""
+    from vectorvisualization_b200 import configs, fields as F
+    cams = (dict(quat=F.quat_from_axis_angle((0.2, 1.0, 0.1), 50.0), pos=(0.0, 0.0, 0.0), dist=0.75, fovy=35.0),      # near plane cuts the front face
+            dict(quat=F.quat_from_axis_angle((0.2, 1.0, 0.1), 30.0), pos=(0.0, 0.0, 0.0), dist=0.62, fovy=35.0))      # everything visible is nearer than 0.1
+    for i, cam in enumerate(cams):
+        s = configs.cfg1(n=32, size=96, camera=cam)
+        if technique == "slicing":
+            s.technique = vv.VOLIC_SLICING
+            s.tf_mode, s.gate_mode = vv.TF_A, vv.GATE_TF_ALPHA
+            ref, ref_cnt, ref_tot = oracle.OracleScene(s).slicing()
+        else:
+            ref, ref_cnt, ref_tot = oracle.OracleScene(s).raycast()
+        _, img, _, cnt, tot = render_cuda(vv, s)
+        if technique == "raycast":
+            assert tot == ref_tot and np.array_equal(cnt, ref_cnt)
+            if i == 0:
+                hit = ref_cnt > 0
+                assert 0.02 < hit.mean() < 0.9
+            else:
+                assert ref_tot == 0 and not img.any()
+        else:
+            assert ref_tot > 0
+            assert int((cnt != ref_cnt).sum()) <= max(1, cnt.size // 20000)
+        assert_image_parity(oracle, img, ref, "near plane %s %d" % (technique, i))
+        # a wider view volume brings the clipped part back
+        s.camera = dict(cam, near=0.001)
+        full_tot = oracle.OracleScene(s).raycast()[2] if technique == "raycast" else oracle.OracleScene(s).slicing()[2]
+        _, _, _, _, tot2 = render_cuda(vv, s)
+        assert tot2 == full_tot and full_tot > ref_tot

@@ -1,0 +1,208 @@
+"""The step the reference leaves to the GL implementation -- clipping, culling, rasterisation of its proxy geometry -- restated
+from the OpenGL 2.1 specification (oracle/softgl.py) and applied to the primitives that Renderer::render(true) itself emits
+(VV/renderer.cpp compiled unmodified, GL calls captured: oracle/ref_host_driver.cpp vvref_raycast_draws).
+
+Checked here:
+  * the oracle's analytic ray entry points (pixel_ray) are the gl_TexCoord[0] of the rasterised fragments: same coverage, same
+    coordinates, for plain, moved, anisotropic, near-plane-clipped and user-clipped views (cube faces + cap polygons);
+  * the oracle's slice fragments are the rasterised fragments of the reference's slice polygons, pixel by pixel and in order;
+  * the reference's shader run on the rasterised fragments gives the oracle's frame;
+  * the low-res preset renders into a (w/2, h/2) viewport with the window's aspect ratio;
+  * the clip-plane normal is normalised in place by the first cap draw (first frame != steady state for non-unit normals).
+Runs wherever oracle/_ref/libvv_ref.so exists (built from /root/reference; travels to the GPU box)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import refhost, refshim, softgl
+
+pytestmark = pytest.mark.skipif(not (refshim.available() and refhost.available()), reason="oracle/_ref/libvv_ref.so not built (needs /root/reference)")
+
+EDGE_EPS = 1e-6      # pixels: a fragment centre this close to an edge line may go either way (implementation-defined)
+TC_EPS = 3e-6        # texcoord units: fp32 rounding of the oracle's entry point + conditioning of the interpolation
+
+
+def _cams():
+    from vectorvisualization_b200 import fields as F
+    return dict(
+        default=None,
+        close=F.CAMERA_CLOSE,
+        rot=dict(quat=F.quat_from_axis_angle((0.3, -1.0, 0.2), 110.0), pos=(0.1, 0.0, 0.2), dist=3.0, fovy=35.0),
+        back=dict(quat=F.quat_from_axis_angle((0.0, 1.0, 0.0), 180.0), pos=(0.0, 0.0, 0.0), dist=3.0, fovy=35.0),
+        # 0.037 outside the front face: all of what the frustum sees of that face lies nearer than the near plane (0.1)
+        near=dict(quat=F.quat_from_axis_angle((0.2, 1.0, 0.1), 30.0), pos=(0.0, 0.0, 0.0), dist=0.62, fovy=35.0),
+        # the near plane cuts the front face: a hole in the middle of the frame
+        near_partial=dict(quat=F.quat_from_axis_angle((0.2, 1.0, 0.1), 50.0), pos=(0.0, 0.0, 0.0), dist=0.75, fovy=35.0),
+        inside=dict(quat=F.quat_from_axis_angle((0.2, 1.0, 0.1), 30.0), pos=(0.0, 0.0, 0.0), dist=0.3, fovy=35.0))
+
+
+PLANES = dict(
+    none=(),
+    front=((0.0, 0.0, -1.0, 0.1),),
+    back=((0.0, 0.0, 1.0, 0.1),),
+    two_nonunit=((0.3, 0.5, -0.8, 0.05), (1.0, 0.0, 0.0, 0.12)),                        # |n| = 0.99: steady state = (n / |n|, d)
+    three=((0.6, -0.8, 0.0, 0.1), (-1.0, 0.0, 0.0, -0.2), (0.0, 0.3, 1.0, 0.2)))
+
+
+def _scene(cam, size=72, aniso=False):
+    from vectorvisualization_b200 import configs, fields as F
+    s = configs.cfg1(n=12, size=size, camera=_cams()[cam])
+    if aniso:
+        s.height = size - 22
+        s.field = np.ascontiguousarray(F.abc_flow(24)[::2, :16, :])            # 24 x 16 x 12, anisotropic spacing
+        s.slice_dist = (1.0, 1.5, 2.0)
+    return s
+
+
+def _dat(tmp_path, s):
+    from vectorvisualization_b200 import fields as F
+    dat = F.write_dat(str(tmp_path / "vol.dat"), s.field, slice_thickness=s.slice_dist)
+    with open(dat, "a") as f:
+        f.write("TimeDependent: 0 0\n")
+    return dat
+
+
+def _oracle_rays(oracle, s):
+    o = oracle.OracleScene(s)
+    e = np.zeros((s.height, s.width, 4), np.float32)
+    oracle.lib().vvo_pixel_rays(ctypes.byref(o.c), 0, 0, s.width, s.height, oracle._p(e))
+    return e
+
+
+@pytest.mark.parametrize("cam,planes,aniso", [
+    ("default", "none", False), ("default", "none", True), ("close", "none", False), ("rot", "none", True), ("back", "none", False),
+    ("near", "none", False), ("near_partial", "none", False), ("inside", "none", False),
+    ("default", "front", False), ("close", "back", False), ("rot", "two_nonunit", False), ("close", "two_nonunit", True),
+    ("back", "three", False), ("rot", "three", False), ("near", "front", False), ("inside", "two_nonunit", False)])
+def test_raycast_fragments_are_the_oracle_entry_points(oracle, tmp_path, cam, planes, aniso):
+    s = _scene(cam, aniso=aniso)
+    s.clip_planes = PLANES[planes]
+    draws = refhost.raycast_draws(_dat(tmp_path, s), s.camera, s.width, s.height, planes=s.clip_planes)
+    prog = [d for d in draws if d["program"] == 77]
+    # Renderer::raycastVolume: one GL_QUADS batch of 24 vertices with back-face culling on, then one fan per active plane
+    assert prog[0]["mode"] == softgl.GL_QUADS and len(prog[0]["verts"]) == 24 and prog[0]["cull"] == 1
+    assert len(prog) == 1 + len(s.clip_planes) and all(d["clip_mask"] == (1 << len(s.clip_planes)) - 1 for d in prog)
+    assert all(d["viewport"] == [0, 0, s.width, s.height] for d in prog)
+    tex, count, edge, _ = softgl.rasterize(draws, s.width, s.height, program=77)
+    e = _oracle_rays(oracle, s)
+    mism = tex[..., 3] != e[..., 3]
+    assert mism.sum() <= 0.005 * mism.size and (edge[mism] < EDGE_EPS).all(), (int(mism.sum()), edge[mism])
+    both = (tex[..., 3] == 1) & (e[..., 3] == 1)
+    if cam in ("near", "inside") and planes == "none":
+        assert not tex[..., 3].any() and not e[..., 3].any()          # the near plane / the culled back faces leave nothing
+    else:
+        assert both.sum() > 150
+        assert np.abs(tex[both][:, :3] - e[both][:, :3]).max() < TC_EPS
+    if cam == "near_partial":
+        assert 0.02 < both.mean() < 0.9                                # a hole, not an empty and not a full frame
+    # cube faces never overlap; a cap sits 1e-4 inside the kept half-space, so it can overlap a clipped face by a sliver
+    assert (count > 1).sum() <= (0 if not s.clip_planes else 0.005 * count.size)
+
+
+def test_clip_normal_is_normalised_by_the_first_cap_draw(oracle, tmp_path):
+    """VV/renderer.cpp:1301 hands ClipPlane::getNormal() (the object's own array) to ViewSlicing::setupSingleSlice, which
+    normalises its argument in place (VV/slicing.cpp:337-348): the plane the GL clips with is (n, d) in the first frame and
+    (n / |n|, d) from the second frame on"""
+    s = _scene("rot")
+    plane = (0.0, 0.6, 2.0, 0.2)
+    ln = float(np.linalg.norm(plane[:3]))
+    dat = _dat(tmp_path, s)
+    eq = []
+    for frames in (1, 2, 3):
+        d = [d for d in refhost.raycast_draws(dat, s.camera, s.width, s.height, planes=(plane,), frames=frames) if d["program"] == 77][0]
+        # back to the object space of the glClipPlane call (volume-centred): p_obj = p_eye M, M = frame model-view * T(center)
+        o = oracle.OracleScene(s)
+        T = np.eye(4); T[:3, 3] = list(o.c.center)
+        eq.append(d["clip_eye"][0] @ (d["modelview"] @ T))
+    assert np.abs(eq[0] - np.asarray(plane)).max() < 1e-9
+    assert np.abs(eq[1] - np.asarray([plane[0] / ln, plane[1] / ln, plane[2] / ln, plane[3]])).max() < 1e-9
+    assert np.abs(eq[2] - eq[1]).max() < 1e-12
+    # the oracle (and vv_set_clip_plane) evaluate the steady state
+    s.clip_planes = (plane,)
+    tex, _, edge, _ = softgl.rasterize(refhost.raycast_draws(dat, s.camera, s.width, s.height, planes=(plane,), frames=2), s.width, s.height, 77)
+    e = _oracle_rays(oracle, s)
+    mism = tex[..., 3] != e[..., 3]
+    assert (edge[mism] < EDGE_EPS).all()
+    first, _, _, _ = softgl.rasterize(refhost.raycast_draws(dat, s.camera, s.width, s.height, planes=(plane,), frames=1), s.width, s.height, 77)
+    assert (first[..., 3] != e[..., 3]).sum() > 20                      # the first frame really is different
+
+
+@pytest.mark.parametrize("cam,planes", [("default", "none"), ("rot", "none"), ("near_partial", "none"), ("inside", "none"),
+                                        ("close", "front"), ("rot", "three_unit")])
+def test_slicing_fragments_are_the_oracle_slice_fragments(oracle, tmp_path, cam, planes):
+    import vectorvisualization_b200 as vv
+    s = _scene(cam, size=40)
+    s.params.update(stepSizeVol=1 / 32)
+    s.technique = vv.VOLIC_SLICING
+    # unit normals: Renderer::sliceVolume never draws caps, so nothing normalises a non-unit normal in a slicing-only session
+    s.clip_planes = ((0.6, 0.0, -0.8, 0.05), (1.0, 0.0, 0.0, 0.12), (0.0, -0.8, 0.6, 0.2)) if planes == "three_unit" else PLANES[planes]
+    draws = refhost.raycast_draws(_dat(tmp_path, s), s.camera, s.width, s.height, planes=s.clip_planes, slicing=True,
+                                  step_size_vol=s.lic_params().stepSizeVol)
+    o = oracle.OracleScene(s)
+    _, _, nslices = o.slicing_setup()
+    prog = [d for d in draws if d["program"] == 79]
+    assert len(prog) == nslices and all(d["mode"] == softgl.GL_TRIANGLE_FAN and d["cull"] == 0 for d in prog)
+    starts, frags, edge = softgl.fragment_lists(draws, s.width, s.height, program=79)
+    buf = np.zeros((nslices, 4), np.float32)
+    total = differ = 0
+    worst = 0.0
+    for y in range(s.height):
+        for x in range(s.width):
+            n = oracle.lib().vvo_slice_fragments(ctypes.byref(o.c), x, y, oracle._p(buf), nslices)
+            g = frags[starts[y * s.width + x]:starts[y * s.width + x + 1]]
+            total += n
+            if len(g) != n:
+                differ += 1
+                assert edge[y, x] < EDGE_EPS, (x, y, len(g), n)
+            elif n:
+                worst = max(worst, float(np.abs(g - buf[:n, :3]).max()))       # same fragments in the same (front-to-back) order
+    assert total > 2000 and differ <= 4 and worst < TC_EPS
+
+
+def test_rasterised_fragments_through_the_reference_shaders(oracle, tmp_path):
+    """reference geometry (Renderer::render) -> GL-spec rasteriser -> reference shader code  ==  the oracle's frame"""
+    import vectorvisualization_b200 as vv
+    from util import psnr8
+    # ray-cast program, rotated view with two clip planes
+    s = _scene("rot", size=40)
+    s.clip_planes = ((0.6, 0.0, -0.8, 0.05), (1.0, 0.0, 0.0, 0.12))
+    draws = refhost.raycast_draws(_dat(tmp_path, s), s.camera, s.width, s.height, planes=s.clip_planes)
+    tex, _, edge, _ = softgl.rasterize(draws, s.width, s.height, program=77)
+    ref_img, _, ref_n = refshim.RefScene(s).raycast(texcoords=tex)
+    img, cnt, n = oracle.OracleScene(s).raycast()
+    interior = edge > EDGE_EPS
+    a, b = oracle.quantize_rgba8(ref_img)[interior], oracle.quantize_rgba8(img)[interior]
+    assert n > 20000 and abs(ref_n - n) <= 0.002 * n
+    assert np.abs(a.astype(np.int32) - b.astype(np.int32)).max() <= 1 and psnr8(a, b) >= 55.0
+    # slicing program
+    s = _scene("close", size=36)
+    s.params.update(stepSizeVol=1 / 32)
+    s.technique, s.tf_mode, s.gate_mode = vv.VOLIC_SLICING, vv.TF_A, vv.GATE_TF_ALPHA
+    draws = refhost.raycast_draws(_dat(tmp_path, s), s.camera, s.width, s.height, slicing=True, step_size_vol=1 / 32)
+    starts, frags, edge = softgl.fragment_lists(draws, s.width, s.height, program=79)
+    ref_img, _, ref_n = refshim.RefScene(s).slicing(fragments=(starts, frags))
+    img, cnt, n = oracle.OracleScene(s).slicing()
+    interior = edge > EDGE_EPS
+    a, b = oracle.quantize_rgba8(ref_img)[interior], oracle.quantize_rgba8(img)[interior]
+    assert n > 1000 and abs(ref_n - n) <= 0.002 * n
+    assert np.abs(a.astype(np.int32) - b.astype(np.int32)).max() <= 1 and psnr8(a, b) >= 55.0
+
+
+def test_lowres_preset_viewport(oracle, tmp_path):
+    """VV/renderer.cpp:111-119,159-160: the low-res preset rasterises into a (w/2, h/2) viewport while gluPerspective keeps the
+    window's aspect ratio (Camera::setWindow): the frame a caller gets from vv_enable_lowres + vv_resize(w/2, h/2)"""
+    s = _scene("close", size=64)
+    s.height = 48
+    s.lowres = 1
+    draws = refhost.raycast_draws(_dat(tmp_path, s), s.camera, s.width, s.height, lowres=1)
+    prog = [d for d in draws if d["program"] == 77]
+    assert prog[0]["viewport"] == [0, 0, 32, 24]
+    assert abs(prog[0]["projection"][1, 1] / prog[0]["projection"][0, 0] - 64 / 48) < 1e-6      # aspect is a float in Camera
+    tex, _, edge, _ = softgl.rasterize(draws, 32, 24, program=77)
+    s.width, s.height = 32, 24
+    e = _oracle_rays(oracle, s)
+    mism = tex[..., 3] != e[..., 3]
+    assert (edge[mism] < EDGE_EPS).all()
+    both = (tex[..., 3] == 1) & (e[..., 3] == 1)
+    assert both.sum() > 150 and np.abs(tex[both][:, :3] - e[both][:, :3]).max() < TC_EPS

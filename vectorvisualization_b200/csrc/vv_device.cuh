@@ -66,12 +66,14 @@ struct DevParams {
     float texMax[3], scaleVol[3], scaleVolInv[3], lightPos[3], camera[3];
     // ---- view (double: bit-identical ray set-up on host oracle and device) ----
     double camD[3], rot[9], tanHalf, aspect, extent[3];
+    double nearD, farD;           // gluPerspective near / far: GL clips the proxy geometry to the view volume, a fragment exists only
+                                  // where its eye-space depth (= the pixel-ray parameter t, d = R^T (ex, ey, -1)) lies in [near, far]
     int width, height;
     int tfMode, gateMode, quirkLumAlpha;
     // ---- Monte-Carlo ray-start offsets (USE_MC_OFFSET) and user clip planes ----
     const float *mcOffsets;          // [height][width], fp16-rounded values in [0,1]; null = off
     int nClip;                       // active clip planes
-    double clipEq[3][4];             // glClipPlane equations, n.q + d >= 0 kept, q = position - centerD
+    double clipEq[3][4];             // glClipPlane equations (n / |n|, d), n.q + d >= 0 kept, q = position - centerD
     double clipN[3][3], clipDist[3]; // unit normal and distance of the cap polygon, n^.q = -(d - 0.0001); clipDist NaN = no cap
     double centerD[3];
     // ---- partition / outputs ----

@@ -49,7 +49,7 @@ __device__ __forceinline__ bool pixel_ray(const DevParams &P, int px, int py, fl
         if (t0 > tn) { tn = t0; face = i; faceval = fv; }
         if (t1 < tf) tf = t1;
     }
-    bool have = (tn < tf) && tn > 0.0 && face >= 0;
+    bool have = (tn < tf) && tn >= P.nearD && tn <= P.farD && face >= 0;   // view-volume clipping of the front faces
     double p[3] = {0.0, 0.0, 0.0};
     if (have) {
 #pragma unroll
@@ -85,7 +85,7 @@ __device__ __forceinline__ bool pixel_ray(const DevParams &P, int px, int py, fl
             if (!(dn > 0.0)) continue;                                        // cap faces away from the viewer: culled
             const double on = __dadd_rn(__dadd_rn(__dmul_rn(n[0], oc[0]), __dmul_rn(n[1], oc[1])), __dmul_rn(n[2], oc[2]));
             const double t = __ddiv_rn(__dsub_rn(dist, on), dn);
-            if (!(t > 0.0)) continue;
+            if (!(t >= P.nearD && t <= P.farD)) continue;
             const double q[3] = {__dadd_rn(oc[0], __dmul_rn(t, d[0])), __dadd_rn(oc[1], __dmul_rn(t, d[1])), __dadd_rn(oc[2], __dmul_rn(t, d[2]))};
             bool inside = true;
 #pragma unroll
@@ -621,7 +621,7 @@ __device__ __forceinline__ bool slice_fragment(const DevParams &P, const PixelDi
     const double b = __dadd_rn(__dadd_rn(__dmul_rn(r.d[0], v0), __dmul_rn(r.d[1], v1)), __dmul_rn(r.d[2], v2));
     if (b == 0.0) return false;
     const double t = __ddiv_rn(__dsub_rn((double)slice_offset(P, slice), a), b);
-    if (!(t > 0.0)) return false;
+    if (!(t >= P.nearD && t <= P.farD)) return false;
     double pd[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {

@@ -409,6 +409,7 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycas
     }
     for (int i = 0; i < 9; ++i) P.rot[i] = (double)R[i];
     P.tanHalf = (double)(float)std::tan((double)r->fovy * M_PI / 360.0);
+    P.nearD = (double)r->near_clip; P.farD = (double)r->far_clip;
     P.aspect = (r->height > 0) ? (double)((float)r->width / (float)r->height) : 1.0;
     P.width = r->width; P.height = r->height;
     P.slicing = 0;
@@ -446,9 +447,13 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycas
         if (!r->clip_active[i]) continue;
         const double *e = r->clip_eq[i];
         const int j = P.nClip++;
-        for (int k = 0; k < 4; ++k) P.clipEq[j][k] = e[k];
+        // The reference normalises the plane's normal IN PLACE the first time its cap is drawn (drawClippedPolygon hands
+        // ClipPlane::getNormal() to ViewSlicing::setupSingleSlice, VV/renderer.cpp:1301, VV/slicing.cpp:337-348; |n| <= VS_EPS
+        // zeroes it), d untouched: from the second frame on the GL plane is (n / |n|, d).  That steady state is what runs here.
         const double len = std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
-        if (len > 1e-8) {                                   // ViewSlicing::setupSingleSlice normalises, VV/slicing.cpp:337-348
+        for (int k = 0; k < 3; ++k) P.clipEq[j][k] = (len > 1e-8) ? e[k] / len : 0.0;
+        P.clipEq[j][3] = e[3];
+        if (len > 1e-8) {
             for (int k = 0; k < 3; ++k) P.clipN[j][k] = e[k] / len;
             P.clipDist[j] = -(e[3] - 0.0001);               // ClipPlane::drawSlice, VV/transform.cpp:432-444
         } else {
