@@ -319,6 +319,7 @@ struct Mat4 { double m[16]; };
 struct DrawRec {
     unsigned program, mode;
     int cull, clip_mask, viewport[4];
+    int blend, blend_src, blend_dst;
     Mat4 mv, proj;
     double clip_eye[6][4];
     std::vector<double> v;          /* x y z s t r per vertex */
@@ -339,6 +340,8 @@ void glMultiTexCoord3fvARB(GLenum unit, const GLfloat *v)
     g_poly_tex.insert(g_poly_tex.end(), v, v + 3);
     if (unit == GL_TEXTURE0_ARB) for (int k = 0; k < 3; ++k) g_cur_tc[k] = v[k];
 }
+void glTexCoord3f(GLfloat x, GLfloat y, GLfloat z) { g_cur_tc[0] = x; g_cur_tc[1] = y; g_cur_tc[2] = z; }   /* VolumeBuffer::drawSlice */
+void glVertex2f(GLfloat x, GLfloat y) { const float v[3] = {x, y, 0.0f}; draw_vertex(v); }
 void glVertex3f(GLfloat x, GLfloat y, GLfloat z) { const float v[3] = {x, y, z}; g_poly_vert.insert(g_poly_vert.end(), v, v + 3); draw_vertex(v); }
 void glMultiTexCoord3fARB(GLenum unit, GLfloat x, GLfloat y, GLfloat z)
 {
@@ -493,7 +496,7 @@ static bool mat_inverse(const Mat4 &a, Mat4 &out)
     return true;
 }
 static double g_clip_eye[6][4];
-static int g_clip_mask = 0, g_cull = 0;
+static int g_clip_mask = 0, g_cull = 0, g_blend = 0, g_blend_src = GL_ONE, g_blend_dst = GL_ZERO;
 static GLhandleARB g_program = 0;
 /* GL 2.1 spec 2.12: the plane is stored in eye coordinates, (p1' p2' p3' p4') = (p1 p2 p3 p4) M^-1 with the model-view
  * of the time of the call */
@@ -510,20 +513,24 @@ void glClipPlane(GLenum plane, const GLdouble *eq)
 void glEnable(GLenum cap)
 {
     if (cap == GL_CULL_FACE) g_cull = 1;
+    else if (cap == GL_BLEND) g_blend = 1;
     else if (cap >= GL_CLIP_PLANE0 && cap < GL_CLIP_PLANE0 + 6) g_clip_mask |= 1 << (cap - GL_CLIP_PLANE0);
 }
 void glDisable(GLenum cap)
 {
     if (cap == GL_CULL_FACE) g_cull = 0;
+    else if (cap == GL_BLEND) g_blend = 0;
     else if (cap >= GL_CLIP_PLANE0 && cap < GL_CLIP_PLANE0 + 6) g_clip_mask &= ~(1 << (cap - GL_CLIP_PLANE0));
 }
 void glUseProgramObjectARB(GLhandleARB program) { g_program = program; }
+void glBlendFunc(GLenum src, GLenum dst) { g_blend_src = (int)src; g_blend_dst = (int)dst; }
 void glBegin(GLenum mode)
 {
     g_in_prim = true;
     if (!g_record_draws) return;
     DrawRec d;
     d.program = g_program; d.mode = mode; d.cull = g_cull; d.clip_mask = g_clip_mask;
+    d.blend = g_blend; d.blend_src = g_blend_src; d.blend_dst = g_blend_dst;
     for (int k = 0; k < 4; ++k) d.viewport[k] = g_viewport[k];
     d.mv = g_mv.back(); d.proj = g_proj.back();
     std::memcpy(d.clip_eye, g_clip_eye, sizeof(d.clip_eye));
@@ -611,13 +618,34 @@ int vvref_cube_faces(const char *dat, float *verts, float *tex, int cap)
     return copy_poly(verts, tex, cap);
 }
 
+static int serialize_draws(double *out, int cap)
+{
+    size_t need = 1;
+    for (const DrawRec &d : g_draws) need += 4 + 3 + 4 + 16 + 16 + 24 + 1 + d.v.size();
+    if ((size_t)cap < need) { g_draws.clear(); return -2; }
+    size_t k = 0;
+    out[k++] = (double)g_draws.size();
+    for (const DrawRec &d : g_draws) {
+        out[k++] = d.program; out[k++] = d.mode; out[k++] = d.cull; out[k++] = d.clip_mask;
+        out[k++] = d.blend; out[k++] = d.blend_src; out[k++] = d.blend_dst;
+        for (int i = 0; i < 4; ++i) out[k++] = d.viewport[i];
+        for (int i = 0; i < 16; ++i) out[k++] = d.mv.m[i];
+        for (int i = 0; i < 16; ++i) out[k++] = d.proj.m[i];
+        for (int i = 0; i < 6; ++i) for (int j = 0; j < 4; ++j) out[k++] = d.clip_eye[i][j];
+        out[k++] = (double)(d.v.size() / 6);
+        for (double x : d.v) out[k++] = x;
+    }
+    g_draws.clear();
+    return (int)k;
+}
+
 /* One frame of Renderer::render(true) in ray-cast mode (VV/renderer.cpp:126-312), run unmodified; every glBegin/glEnd primitive is
  * recorded with the program, matrices, viewport, cull / clip state it was issued under.  Serialised as doubles:
  *   out[0] = number of primitives, then per primitive
- *   program, mode, cull, clip_mask, viewport[4], modelview[16], projection[16], clip planes in eye space [6][4], nverts,
+ *   program, mode, cull, clip_mask, blend enabled, blend src, blend dst, viewport[4], modelview[16], projection[16], clip planes in eye space [6][4], nverts,
  *   nverts x (x y z s t r)
- * The ray-cast program has the handle 77, the slicing program 79 (set below; no GLSL is compiled in the shim); slicing != 0
- * renders with VOLIC_SLICING (after Renderer::updateSlices) instead of VOLIC_RAYCAST; step_size_vol > 0 overrides LICParams.  planes: up to 3 user clip planes
+ * The ray-cast program has the handle 77, the slicing program 79 (set below; no GLSL is compiled in the shim); slicing = 1
+ * renders with VOLIC_SLICING (after Renderer::updateSlices), 2 with VOLIC_LICVOLUME (program 81) instead of VOLIC_RAYCAST; step_size_vol > 0 overrides LICParams.  planes: up to 3 user clip planes
  * (n.xyz, d) as ClipPlane::setNormal takes them, active[i] != 0 to enable; frames >= 1: how many frames to render, the last one
  * is the one returned.  Returns the number of doubles written, < 0 on error. */
 int vvref_raycast_draws(const char *dat, const float cam_quat[4], const float cam_pos[3], float cam_dist, int width, int height,
@@ -664,18 +692,22 @@ int vvref_raycast_draws(const char *dat, const float cam_quat[4], const float ca
     r._paramSlice.imageFBOSampler = 20;                                 /* sliceVolume returns early without it (:1127) */
     r.enableLowRes(lowres != 0);
     r.resize(width, height);                                            /* VV/3DLIC.cpp:174-200 */
-    if (slicing) {
+    r._licRaycastShader._programObj = 81;
+    std::memset(&r._paramLicRaycast, 0xff, sizeof(r._paramLicRaycast));
+    if (slicing == 2) {
+        r.setTechnique(VOLIC_LICVOLUME);                                /* ray-cast of the LIC volume (F4) */
+    } else if (slicing) {
         r._useFBO = true;                                               /* the FBO ping-pong branch of sliceVolume (keys F3, VV/3DLIC.cpp:457-475) */
         r.setTechnique(VOLIC_SLICING);
     } else {
         r.setTechnique(VOLIC_RAYCAST);
     }
     g_mv.assign(1, mat_identity()); g_proj.assign(1, mat_identity()); g_mode = GL_MODELVIEW;
-    g_clip_mask = 0; g_cull = 0; g_program = 0;
+    g_clip_mask = 0; g_cull = 0; g_program = 0; g_blend = 0; g_blend_src = GL_ONE; g_blend_dst = GL_ZERO;
     glViewport(0, 0, width, height);                                    /* resize callback, VV/3DLIC.cpp:176 */
     /* `frames` calls of render(true); the LAST one is recorded.  (The first frame differs for non-unit plane normals:
      * drawClippedPolygon normalises ClipPlane::_normal in place, VV/renderer.cpp:1301 -> VV/slicing.cpp:337-348.) */
-    if (slicing) r.updateSlices();                                      /* VV/3DLIC.cpp:168, 469 */
+    if (slicing == 1) r.updateSlices();                                      /* VV/3DLIC.cpp:168, 469 */
     for (int f = 0; f < frames; ++f) {
         g_draws.clear();
         g_record_draws = true;
@@ -683,22 +715,40 @@ int vvref_raycast_draws(const char *dat, const float cam_quat[4], const float ca
         g_record_draws = false;
     }
     r._licFilter = NULL;
-    size_t need = 1;
-    for (const DrawRec &d : g_draws) need += 4 + 4 + 16 + 16 + 24 + 1 + d.v.size();
-    if ((size_t)cap < need) { g_draws.clear(); return -2; }
-    size_t k = 0;
-    out[k++] = (double)g_draws.size();
-    for (const DrawRec &d : g_draws) {
-        out[k++] = d.program; out[k++] = d.mode; out[k++] = d.cull; out[k++] = d.clip_mask;
-        for (int i = 0; i < 4; ++i) out[k++] = d.viewport[i];
-        for (int i = 0; i < 16; ++i) out[k++] = d.mv.m[i];
-        for (int i = 0; i < 16; ++i) out[k++] = d.proj.m[i];
-        for (int i = 0; i < 6; ++i) for (int j = 0; j < 4; ++j) out[k++] = d.clip_eye[i][j];
-        out[k++] = (double)(d.v.size() / 6);
-        for (double x : d.v) out[k++] = x;
-    }
+    return serialize_draws(out, cap);
+}
+
+/* Renderer::updateLICVolume -> renderLICVolume (VV/renderer.cpp:1311-1374) into a w x h x d VolumeBuffer (the reference
+ * allocates 512^3 in Renderer::init, :97): one screen-filling quad per layer, texcoord0 = (s, t, (z + 0.5) / d).  Same record
+ * format as vvref_raycast_draws; the LIC-volume program has the handle 80. */
+int vvref_licvolume_draws(int w, int h, int d, double *out, int cap)
+{
+    LICFilter filt;
+    filt.createBoxFilter();
+    LICParams lp;
+    Texture dummy[3];
+    VolumeData vol;
+    std::memset(&vol, 0, sizeof(vol));
+    for (int i = 0; i < 3; ++i) { vol.size[i] = 8; vol.extent[i] = 1.0f; vol.scale[i] = 1.0f; vol.scaleInv[i] = 1.0f; vol.center[i] = 0.5f; }
+    Renderer r;
+    r.setVolumeData(&vol);
+    r._licFilter = &filt;
+    r.setLICParams(&lp);
+    r._dataTex = &dummy[0]; r._tfRGBTex = &dummy[1]; r._tfAlphaOpacTex = &dummy[2];
+    r._licvolumebuffer = new VolumeBuffer(GL_RGBA16F_ARB, w, h, d, 2);
+    r._volumeRenderShader._programObj = 80;
+    std::memset(&r._paramLICVolume, 0xff, sizeof(r._paramLICVolume));
+    g_mv.assign(1, mat_identity()); g_proj.assign(1, mat_identity()); g_mode = GL_MODELVIEW;
+    g_clip_mask = 0; g_cull = 0; g_program = 0; g_blend = 0; g_blend_src = GL_ONE; g_blend_dst = GL_ZERO;
+    glViewport(0, 0, 640, 480);
     g_draws.clear();
-    return (int)k;
+    g_record_draws = true;
+    r.updateLICVolume();
+    g_record_draws = false;
+    delete r._licvolumebuffer;
+    r._licvolumebuffer = NULL;
+    r._licFilter = NULL;
+    return serialize_draws(out, cap);
 }
 
 int vvref_next_pow2(int v) { return nextPowerTwo(v); }

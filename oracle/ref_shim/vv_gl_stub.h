@@ -83,7 +83,7 @@ static inline void glScalef(GLfloat, GLfloat, GLfloat) {}
 void glBegin(GLenum mode);                              /* captured: draw list (oracle/softgl.py rasterises it) */
 void glEnd(void);
 static inline void glVertex2i(GLint, GLint) {}
-static inline void glVertex2f(GLfloat, GLfloat) {}
+void glVertex2f(GLfloat x, GLfloat y);                /* captured (z = 0): VolumeBuffer::drawSlice, screen-filling quads */
 void glVertex3f(GLfloat x, GLfloat y, GLfloat z);      /* captured: cube faces of Renderer::drawCubeFaces */
 /* captured (ref_host_driver.cpp): the slice / cap polygons of VV/slicing.cpp */
 void glVertex3fv(const GLfloat *v);
@@ -96,7 +96,7 @@ static inline void glColor4fv(const GLfloat *) {}
 static inline void glColor3fv(const GLfloat *) {}
 void glEnable(GLenum cap);                              /* captured: GL_CULL_FACE, GL_CLIP_PLANEi */
 void glDisable(GLenum cap);
-static inline void glBlendFunc(GLenum, GLenum) {}
+void glBlendFunc(GLenum src, GLenum dst);            /* captured */
 static inline void glPushAttrib(GLbitfield) {}
 static inline void glPopAttrib(void) {}
 static inline void glLineWidth(GLfloat) {}

@@ -51,9 +51,9 @@ void glUniform4fvARB(GLint loc, GLsizei n, const GLfloat *v);
 void glUniform4iARB(GLint loc, GLint a, GLint b, GLint c, GLint d);
 void glViewport(GLint x, GLint y, GLsizei w, GLsizei h);
 void glMultiTexCoord3fARB(GLenum unit, GLfloat x, GLfloat y, GLfloat z);
+void glTexCoord3f(GLfloat s, GLfloat t, GLfloat r);      /* captured: current texcoord0 */
 void glUseProgramObjectARB(GLhandleARB program);       /* the program bound when a primitive is drawn */
 /* ---- no-ops ---- */
-static inline void *wglGetProcAddress(const char *) { return (void *)0; }
 static inline void glNormal3f(GLfloat, GLfloat, GLfloat) {}
 static inline void glDepthMask(GLboolean) {}
 static inline void glBindFramebufferEXT(GLenum, GLuint) {}
@@ -66,10 +66,11 @@ static inline void glRenderbufferStorageEXT(GLenum, GLenum, GLsizei, GLsizei) {}
 /* GLEW exposes extension entry points as assignable function pointers (VV/renderer.cpp:545 re-loads this one) */
 static inline void vv_stub_gen_framebuffers(GLsizei n, GLuint *ids) { for (int i = 0; i < n; ++i) ids[i] = 1000 + i; }
 static PFNGLGENFRAMEBUFFERSEXTPROC glGenFramebuffersEXT = vv_stub_gen_framebuffers;
+/* the reference only ever asks for "glGenFramebuffersEXT" (VV/renderer.cpp:545, VV/VolumeBuffer.cpp:9) */
+static inline void *wglGetProcAddress(const char *) { return (void *)vv_stub_gen_framebuffers; }
 static inline void glGenRenderbuffersEXT(GLsizei n, GLuint *ids) { for (int i = 0; i < n; ++i) ids[i] = 2000 + i; }
 static inline void glDeleteFramebuffersEXT(GLsizei, const GLuint *) {}
 static inline void glDeleteRenderbuffersEXT(GLsizei, const GLuint *) {}
-static inline void glTexCoord3f(GLfloat, GLfloat, GLfloat) {}
 static inline void glCopyTexSubImage3D(GLenum, GLint, GLint, GLint, GLint, GLint, GLint, GLsizei, GLsizei) {}
 static inline void glCopyTexImage2D(GLenum, GLint, GLenum, GLint, GLint, GLsizei, GLsizei, GLint) {}
 static inline void glGetObjectParameterivARB(GLhandleARB, GLenum, GLint *v) { if (v) *v = 0; }

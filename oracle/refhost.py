@@ -209,8 +209,9 @@ def cube_faces(dat_path):
 
 def raycast_draws(dat_path, camera, width, height, lowres=0, planes=(), frames=2, slicing=False, step_size_vol=0.0):
     """Renderer::render(true) in ray-cast mode, run unmodified with the GL calls captured: the list of glBegin/glEnd primitives,
-    each a dict(program, mode, cull, clip_mask, viewport[4], modelview[4][4], projection[4][4], clip_eye[6][4],
+    each a dict(program, mode, cull, clip_mask, blend, blend_func, viewport[4], modelview[4][4], projection[4][4], clip_eye[6][4],
     verts[n][3], tex[n][3]).  program 77 = the LIC ray-cast program, 79 = the slicing program, 78 = the background program, 0 = fixed function.
+    slicing: 0 / False = VOLIC_RAYCAST, 1 / True = VOLIC_SLICING, 2 = VOLIC_LICVOLUME (program 81).
     frames: render(true) is called that many times and the last frame is returned (2 = the steady state, see the driver)."""
     f32 = lambda a: np.ascontiguousarray(a, np.float32)
     q, pos = f32(camera["quat"]), f32(camera["pos"])
@@ -227,15 +228,31 @@ def raycast_draws(dat_path, camera, width, height, lowres=0, planes=(), frames=2
                                       ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                       ctypes.c_void_p, ctypes.c_int]
     n = L.vvref_raycast_draws(dat_path.encode(), q.ctypes.data, pos.ctypes.data, float(camera["dist"]), int(width), int(height),
-                              int(lowres), pl.ctypes.data, act, int(frames), int(bool(slicing)), float(step_size_vol),
+                              int(lowres), pl.ctypes.data, act, int(frames), int(slicing), float(step_size_vol),
                               out.ctypes.data, cap)
     assert n > 0, n
+    return _parse_draws(out, n)
+
+
+def licvolume_draws(w, h, d):
+    """Renderer::updateLICVolume (VV/renderer.cpp:1311-1374) into a w x h x d VolumeBuffer: the captured primitives, same format
+    as raycast_draws; the LIC-volume program has the handle 80"""
+    cap = 1 << 20
+    out = np.zeros(cap, np.float64)
+    L = _L()
+    L.vvref_licvolume_draws.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    n = L.vvref_licvolume_draws(int(w), int(h), int(d), out.ctypes.data, cap)
+    assert n > 0, n
+    return _parse_draws(out, n)
+
+
+def _parse_draws(out, n):
     k = 1
     draws = []
     for _ in range(int(out[0])):
         d = dict(program=int(out[k]), mode=int(out[k + 1]), cull=int(out[k + 2]), clip_mask=int(out[k + 3]),
-                 viewport=[int(x) for x in out[k + 4:k + 8]])
-        k += 8
+                 blend=int(out[k + 4]), blend_func=(int(out[k + 5]), int(out[k + 6])), viewport=[int(x) for x in out[k + 7:k + 11]])
+        k += 11
         d["modelview"] = out[k:k + 16].reshape(4, 4).T.copy(); k += 16          # column-major -> [row][col]
         d["projection"] = out[k:k + 16].reshape(4, 4).T.copy(); k += 16
         d["clip_eye"] = out[k:k + 24].reshape(6, 4).copy(); k += 24

@@ -206,3 +206,41 @@ def test_lowres_preset_viewport(oracle, tmp_path):
     assert (edge[mism] < EDGE_EPS).all()
     both = (tex[..., 3] == 1) & (e[..., 3] == 1)
     assert both.sum() > 150 and np.abs(tex[both][:, :3] - e[both][:, :3]).max() < TC_EPS
+
+
+def test_lic_volume_layers_address_voxel_centres():
+    """Renderer::updateLICVolume (VV/renderer.cpp:1311-1374, VV/VolumeBuffer.cpp:100-108): one screen-filling quad per layer of
+    the w x h x d target; rasterised, fragment (x, y) of layer z carries texcoord0 = ((x + .5) / w, (y + .5) / h, (z + .5) / d)
+    -- the positions the oracle's vvo_lic_volume and the CUDA lic_volume_kernel evaluate"""
+    w, h, d = 7, 5, 3
+    draws = refhost.licvolume_draws(w, h, d)
+    prog = [x for x in draws if x["program"] == 80]
+    assert len(prog) == d and all(x["viewport"] == [0, 0, w, h] and x["mode"] == softgl.GL_QUADS for x in prog)
+    for z, x in enumerate(prog):
+        assert np.array_equal(x["modelview"], np.eye(4)) and np.array_equal(x["projection"], np.eye(4))
+        tex, count, _, _ = softgl.rasterize([x], w, h)
+        assert (count == 1).all()
+        gy, gx = np.mgrid[0:h, 0:w]
+        want = np.stack([(gx + 0.5) / w, (gy + 0.5) / h, np.full(gx.shape, (np.float32(z) + np.float32(0.5)) / np.float32(d), np.float64)], axis=-1)
+        assert np.abs(tex[..., :3] - want).max() < 1e-12
+
+
+def test_draw_state_of_the_three_techniques(tmp_path):
+    """What state the reference issues its proxy geometry under (Renderer::raycastVolume / sliceVolume / raycastLICVolume,
+    VV/renderer.cpp:1093-1120, 1123-1267, 1376-1405).  LIC ray-cast and FBO slicing draw with blending off: the frame is the
+    shader's gl_FragColor (the parity point).  The LIC-volume ray-cast leaves GL_BLEND ENABLED (:1389) with whatever blend function
+    was set last (renderLICVolume :1337, the HUD and the TF editor set SRC_ALPHA / ONE_MINUS_SRC_ALPHA): what reaches the frame
+    buffer there depends on that state and on the clear colour, so -- like Q19 -- the parity point of volume_raycast is
+    gl_FragColor itself."""
+    s = _scene("default", size=24)
+    dat = _dat(tmp_path, s)
+    ray = [d for d in refhost.raycast_draws(dat, s.camera, s.width, s.height, slicing=0) if d["program"] == 77]
+    sli = [d for d in refhost.raycast_draws(dat, s.camera, s.width, s.height, slicing=1) if d["program"] == 79]
+    vol = [d for d in refhost.raycast_draws(dat, s.camera, s.width, s.height, slicing=2) if d["program"] == 81 and d["mode"] == softgl.GL_QUADS]
+    assert ray and all(d["blend"] == 0 and d["cull"] == 1 for d in ray)
+    assert sli and all(d["blend"] == 0 and d["cull"] == 0 for d in sli)
+    assert len(vol) == 1 and vol[0]["blend"] == 1 and vol[0]["cull"] == 1
+    # same proxy cube, same matrices for the two ray-cast techniques: same fragments
+    a, _, _, _ = softgl.rasterize(ray, s.width, s.height)
+    b, _, _, _ = softgl.rasterize(vol, s.width, s.height)
+    assert np.array_equal(a, b) and a[..., 3].sum() > 50
