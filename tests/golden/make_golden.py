@@ -4,6 +4,9 @@ oracle/build_ref.py from /root/reference/VectorVisualization/shader/*.glsl).  Ru
 reference is mounted); the vectors are committed so the GPU box can check both the oracle and the CUDA path against
 outputs of the reference without the reference being present.
 
+A third family (y_chain_*) goes through the whole reference chain: the draw calls of Renderer::render(true) captured in the
+shim, rasterised per the GL specification (oracle/softgl.py), shaded by the reference's shader code (oracle/refchain.py).
+
     python tests/golden/make_golden.py
 """
 import os
@@ -18,7 +21,7 @@ sys.path.insert(0, HERE)
 
 from oracle import refshim  # noqa: E402
 from oracle import vvo  # noqa: E402
-from scenes import golden_scenes, golden_extra_scenes  # noqa: E402
+from scenes import golden_scenes, golden_extra_scenes, golden_chain_scenes  # noqa: E402
 
 
 def main():
@@ -46,6 +49,13 @@ def main():
         out = os.path.join(HERE, name + ".npz")
         np.savez_compressed(out, frame=img, samples=cnt.astype(np.uint16), total=np.int64(tot))
         print("%-32s %-8s samples %7d  -> %s (%d bytes)" % (name, kind, tot, os.path.basename(out), os.path.getsize(out)))
+    from oracle import refchain
+    for name, (mk, kind) in golden_chain_scenes().items():
+        s = mk()
+        img, cnt, tot, edge = refchain.reference_chain_frame(s)
+        out = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(out, frame=img, samples=cnt.astype(np.uint16), total=np.int64(tot), edge=edge)
+        print("%-36s %-8s samples %7d, %d edge pixels -> %s (%d bytes)" % (name, kind, tot, int(edge.sum()), os.path.basename(out), os.path.getsize(out)))
 
 
 if __name__ == "__main__":

@@ -120,3 +120,46 @@ def golden_extra_scenes():
         return s
     S["x_mc_slicing"] = (e6, "slicing")
     return S
+
+
+def golden_chain_scenes():
+    """third family: frames of the WHOLE reference chain -- the draw calls of Renderer::render(true) (VV/renderer.cpp compiled
+    unmodified, GL calls captured), rasterised per the OpenGL 2.1 specification (oracle/softgl.py), shaded by the reference's
+    shader code.  name -> (maker, kind); the fragments' texcoords are the rasteriser's, not the oracle's analytic entry points,
+    so consumers compare within the north-star tolerance instead of bit for bit."""
+    import vectorvisualization_b200 as vv
+    from vectorvisualization_b200 import configs, fields as F
+    S = {}
+
+    def c1():
+        s = configs.cfg3(n=20, size=40, camera=dict(quat=F.quat_from_axis_angle((0.3, -1.0, 0.2), 110.0), pos=(0.1, 0.0, 0.2), dist=3.0, fovy=35.0))
+        s.clip_planes = ((0.6, 0.0, -0.8, 0.05), (1.0, 0.0, 0.0, 0.12))
+        return s
+    S["y_chain_raycast_gradient_clip2"] = (c1, "raycast")
+
+    def c2():
+        # the near plane (0.1) cuts the front face: a hole where the entry point is nearer than it
+        s = configs.cfg1(n=20, size=48, camera=dict(quat=F.quat_from_axis_angle((0.2, 1.0, 0.1), 50.0), pos=(0.0, 0.0, 0.0), dist=0.75, fovy=35.0))
+        return s
+    S["y_chain_raycast_near_plane"] = (c2, "raycast")
+
+    def c3():
+        s = configs.cfg2(n=20, size=40, camera=F.CAMERA_CLOSE)
+        s.height = 30
+        s.field = np.ascontiguousarray(F.rankine_vortex(24)[::2, :16, :])     # 24 x 16 x 12, anisotropic spacing
+        s.slice_dist = (1.0, 1.5, 2.0)
+        s.clip_planes = ((0.3, 0.5, -0.8, 0.05),)                            # |n| = 0.99: the steady state (n / |n|, d)
+        return s
+    S["y_chain_raycast_aniso_nonunit_clip"] = (c3, "raycast")
+
+    def c4():
+        s = configs.cfg2(n=20, size=36, camera=F.CAMERA_CLOSE)
+        s.with_gradients = True
+        s.technique = vv.VOLIC_SLICING
+        s.tf_mode, s.gate_mode = vv.TF_A, vv.GATE_TF_ALPHA
+        s.tf = F.default_tf()
+        s.params.update(gradientScale=4.0, stepSizeVol=1 / 64)
+        s.clip_planes = ((0.0, 0.0, -1.0, 0.2),)
+        return s
+    S["y_chain_slicing_clip"] = (c4, "slicing")
+    return S

@@ -822,6 +822,31 @@ def test_noise_layouts_bit_identical(vv):
     assert np.array_equal(out[0], out[1])
 
 
+def _golden_chain_names():
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from scenes import golden_chain_scenes
+    return sorted(golden_chain_scenes().keys())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", _golden_chain_names())
+def test_cuda_matches_reference_chain(vv, oracle, name):
+    """CUDA path against frames of the whole reference chain (tests/golden/y_chain_*.npz: the draw calls of Renderer::render(true)
+    -> GL-spec rasteriser -> reference shader code, oracle/refchain.py), at the north-star tolerance; pixels whose coverage is
+    implementation-defined (fragment centre on a polygon edge) are masked"""
+    import os
+    from scenes import golden_chain_scenes
+    from util import psnr8, MIN_PSNR_DB
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    s = golden_chain_scenes()[name][0]()
+    r, img, _, cnt, tot = render_cuda(vv, s)
+    keep = ~g["edge"]
+    assert (cnt[keep] != g["samples"].astype(np.uint32)[keep]).mean() <= 0.005
+    a, b = oracle.quantize_rgba8(img)[keep], oracle.quantize_rgba8(g["frame"])[keep]
+    assert np.abs(a.astype(np.int32) - b.astype(np.int32)).max() <= MAX_DIFF_8BIT and psnr8(a, b) >= MIN_PSNR_DB
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("technique", ["raycast", "slicing"])
 def test_near_plane_clips_the_proxy_geometry(vv, oracle, technique):
