@@ -142,8 +142,11 @@ VV_API int vv_set_light(VVRenderer *r, const float quat[4], float dist);
 VV_API int vv_update_light_pos(VVRenderer *r);
 /* enableLowRes / enableFBO, VV/renderer.h:76-83.  Low-res = the interaction preset of VV/renderer.cpp:947-966 (step x2,
  * 15+15 LIC steps of 1/64, frequency x0.7, alpha correction for the doubled step).  The reference additionally renders
- * into half the window in that mode (VV/renderer.cpp:111-119): call vv_resize(w / 2, h / 2) for that. */
+ * into half the window in that mode (VV/renderer.cpp:111-119, 159-160) while gluPerspective keeps the WINDOW's aspect ratio
+ * (Camera::setWindow, VV/transform.h:79-80; VV/3DLIC.cpp:192): call vv_set_window(w, h) + vv_resize(max(w/2,1), max(h/2,1))
+ * for that.  vv_set_window(0, 0) returns to the default, aspect = frame width / frame height. */
 VV_API int vv_enable_lowres(VVRenderer *r, int enable);
+VV_API int vv_set_window(VVRenderer *r, int window_width, int window_height);
 VV_API int vv_enable_float_target(VVRenderer *r, int enable);
 VV_API int vv_set_option(VVRenderer *r, int option, int value);
 /* Screenshot / recording: Renderer::screenshot / switchRecording (VV/renderer.h:99-101, keys 'p' / 'P' VV/3DLIC.cpp:262-270)

@@ -324,7 +324,7 @@ void make_ctx(const VVOScene *s, Ctx &c, bool raycast_program = true)
         cam[i] = (double)s->center[i] + (double)c.rot[0 * 3 + i] * t[0] + (double)c.rot[1 * 3 + i] * t[1] + (double)c.rot[2 * 3 + i] * t[2];
     c.camera = {(float)cam[0], (float)cam[1], (float)cam[2]};
     c.tanHalf = (float)std::tan((double)s->fovy * M_PI / 360.0);
-    c.aspect = (float)s->width / (float)s->height;
+    c.aspect = (s->window_aspect > 0.0f) ? s->window_aspect : (float)s->width / (float)s->height;
     /* light: renderer.cpp:431-466: M = T(center) R(-angle, axis) T(cam_pos); lightPos = q_light (0,0,dist) */
     V3 lp = quat_rotate(s->light_quat, V3{0.0f, 0.0f, s->light_dist});
     float Rm[9];

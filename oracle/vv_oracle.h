@@ -80,6 +80,8 @@ typedef struct VVOScene {
                                   on the GL plane is n^.q + d >= 0.  The oracle evaluates that steady state. */
     float  near_clip, far_clip; /* gluPerspective near / far (camera.cpp:42-47: 0.1, 50): GL clips the proxy geometry to the view
                                   volume, so a fragment exists only where its eye-space depth lies in [near, far] */
+    float  window_aspect;      /* Camera::setWindow (transform.h:79-80): aspect of gluPerspective when the frame is not the window
+                                  (low-res preset: half-size viewport, renderer.cpp:111-119); 0 = width / height */
 } VVOScene;
 
 /* ---- hot path ------------------------------------------------------- */

@@ -41,7 +41,7 @@ class Scene(ctypes.Structure):
         ("lowres", ctypes.c_int), ("quirk_scalevolinv", ctypes.c_int), ("quirk_luminance_alpha", ctypes.c_int),
         ("speed_of_flow", ctypes.c_int), ("licvol_fp16", ctypes.c_int), ("weight_bits", ctypes.c_int),
         ("mc_offsets", ctypes.c_void_p), ("num_clip_planes", ctypes.c_int), ("clip_planes", (ctypes.c_double * 4) * 3),
-        ("near_clip", ctypes.c_float), ("far_clip", ctypes.c_float),
+        ("near_clip", ctypes.c_float), ("far_clip", ctypes.c_float), ("window_aspect", ctypes.c_float),
     ]
 
 
@@ -217,6 +217,8 @@ class OracleScene:
         c.cam_quat = (ctypes.c_float * 4)(*s.camera["quat"]); c.cam_pos = (ctypes.c_float * 3)(*s.camera["pos"])
         c.cam_dist = s.camera["dist"]; c.fovy = s.camera["fovy"]
         c.near_clip = s.camera.get("near", 0.1); c.far_clip = s.camera.get("far", 50.0)          # VV/camera.cpp:42-47
+        win = getattr(s, "window", None)
+        c.window_aspect = float(np.float32(win[0]) / np.float32(win[1])) if win else 0.0           # _aspect = (float)_w/_h
         c.light_quat = (ctypes.c_float * 4)(*s.light["quat"]); c.light_dist = s.light["dist"]; c.spec_exp = 40.0
         c.width = s.width; c.height = s.height
         c.illum_mode = illum_mode; c.tf_mode = s.tf_mode; c.gate_mode = s.gate_mode; c.noise_gate = s.noise_gate

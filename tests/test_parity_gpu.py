@@ -881,3 +881,20 @@ def test_near_plane_clips_the_proxy_geometry(vv, oracle, technique):
         full_tot = oracle.OracleScene(s).raycast()[2] if technique == "raycast" else oracle.OracleScene(s).slicing()[2]
         _, _, _, _, tot2 = render_cuda(vv, s)
         assert abs(tot2 - full_tot) <= (0 if technique == "raycast" else max(2, full_tot // 10000)) and full_tot > ref_tot
+
+
+def test_lowres_window_aspect(vv, oracle):
+    """low-res preset as the reference renders it: a (w/2, h/2) frame with the projection of the w x h window
+    (VV/renderer.cpp:111-119, VV/transform.h:79-80) -- vv_enable_lowres + vv_set_window + vv_resize"""
+    from vectorvisualization_b200 import configs, fields as F
+    s = configs.cfg3(n=32, size=25, camera=F.CAMERA_CLOSE)
+    s.height = 20
+    s.window = (51, 41)
+    s.lowres = 1
+    ref, ref_cnt, ref_tot = oracle.OracleScene(s).raycast()
+    _, img, _, cnt, tot = render_cuda(vv, s)
+    assert tot == ref_tot and tot > 0 and np.array_equal(cnt, ref_cnt)
+    assert_image_parity(oracle, img, ref, "lowres window aspect")
+    s.window = None
+    _, img2, _, _, _ = render_cuda(vv, s)
+    assert not np.array_equal(img, img2)

@@ -206,6 +206,22 @@ def test_lowres_preset_viewport(oracle, tmp_path):
     assert (edge[mism] < EDGE_EPS).all()
     both = (tex[..., 3] == 1) & (e[..., 3] == 1)
     assert both.sum() > 150 and np.abs(tex[both][:, :3] - e[both][:, :3]).max() < TC_EPS
+    # odd window: 51 x 41 -> a 25 x 20 frame whose projection keeps 51 / 41 (vv_set_window + vv_resize)
+    s = _scene("close", size=51)
+    s.height = 41
+    s.lowres = 1
+    draws = refhost.raycast_draws(_dat(tmp_path, s), s.camera, 51, 41, lowres=1)
+    assert [d for d in draws if d["program"] == 77][0]["viewport"] == [0, 0, 25, 20]
+    tex, _, edge, _ = softgl.rasterize(draws, 25, 20, program=77)
+    s.width, s.height, s.window = 25, 20, (51, 41)
+    e = _oracle_rays(oracle, s)
+    mism = tex[..., 3] != e[..., 3]
+    assert (edge[mism] < EDGE_EPS).all()
+    both = (tex[..., 3] == 1) & (e[..., 3] == 1)
+    assert both.sum() > 100 and np.abs(tex[both][:, :3] - e[both][:, :3]).max() < TC_EPS
+    s.window = None                                  # without the window's aspect the frame would be a different one
+    e2 = _oracle_rays(oracle, s)
+    assert np.abs(e2[both][:, :3] - e[both][:, :3]).max() > 1e-3
 
 
 def test_lic_volume_layers_address_voxel_centres():

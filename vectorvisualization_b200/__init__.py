@@ -83,7 +83,7 @@ def load_library():
         "vv_default_lic_params": ([ctypes.POINTER(LICParams)], None),
         "vv_set_camera": ([P, ctypes.POINTER(F), ctypes.POINTER(F), F, F, F, F], I),
         "vv_set_light": ([P, ctypes.POINTER(F), F], I), "vv_update_light_pos": ([P], I),
-        "vv_enable_lowres": ([P, I], I), "vv_enable_float_target": ([P, I], I), "vv_set_option": ([P, I, I], I),
+        "vv_enable_lowres": ([P, I], I), "vv_set_window": ([P, I, I], I), "vv_enable_float_target": ([P, I], I), "vv_set_option": ([P, I, I], I),
         "vv_set_mc_offsets": ([P, P, I, I], I), "vv_update_mc_offset_tex": ([P, I, I, ctypes.c_uint32], I),
         "vv_set_clip_plane": ([P, I, P, I], I),
         "vv_set_snapshot": ([P, CP, CP, I], I), "vv_screenshot": ([P], I), "vv_switch_recording": ([P], I),
@@ -222,6 +222,10 @@ class Renderer:
     def resize(self, w, h):
         _chk(self._lib.vv_resize(self._h, w, h))
         self.width, self.height = w, h
+
+    def setWindow(self, w, h):
+        """Camera::setWindow (VV/transform.h:79-80): the aspect ratio of the projection when it is not the frame's (low-res preset)"""
+        _chk(self._lib.vv_set_window(self._h, w, h))
 
     def setTechnique(self, t):
         _chk(self._lib.vv_set_technique(self._h, t))

@@ -40,6 +40,7 @@ class Scene:
     slice_dist: tuple = (1.0, 1.0, 1.0)
     mc_offsets: Optional[np.ndarray] = None   # [height][width] float32 in [0,1]; needs "#define USE_MC_OFFSET" in defines
     clip_planes: tuple = ()                # up to 3 active planes (nx, ny, nz, d): n.q + d >= 0 kept, q relative to the centre
+    window: Optional[tuple] = None         # (w, h) of the window when the frame is not the window (low-res preset: frame = half the window)
 
     def lic_params(self):
         return LICParams(**self.params)
@@ -107,6 +108,7 @@ def apply_scene(r: Renderer, s: Scene):
     r.updateLightPos()
     r.setTechnique(s.technique)
     r.resize(s.width, s.height)
+    r.setWindow(*(s.window or (0, 0)))
     if s.mc_offsets is not None:
         r.setMCOffsets(s.mc_offsets)
     for i in range(3):

@@ -97,6 +97,7 @@ struct VVRenderer {
     // ---- parameters ----
     VVLicParams lp;
     float cam_quat[4] = {0, 0, 0, 1}, cam_pos[3] = {0, 0, 0}, cam_dist = 4.0f, fovy = 35.0f, near_clip = 0.1f, far_clip = 50.0f;
+    float window_aspect = 0.0f;            // Camera::setWindow (VV/transform.h:79-80); 0 = frame width / frame height
     float light_quat[4] = {0, 0, 0, 1}, light_dist = 1.0f;   // VV/3DLIC.cpp:681
     float light_pos[3] = {0.5f, 0.5f, 1.5f};
     int technique = VV_VOLIC_RAYCAST;
@@ -410,7 +411,7 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycas
     for (int i = 0; i < 9; ++i) P.rot[i] = (double)R[i];
     P.tanHalf = (double)(float)std::tan((double)r->fovy * M_PI / 360.0);
     P.nearD = (double)r->near_clip; P.farD = (double)r->far_clip;
-    P.aspect = (r->height > 0) ? (double)((float)r->width / (float)r->height) : 1.0;
+    P.aspect = (r->window_aspect > 0.0f) ? (double)r->window_aspect : (r->height > 0) ? (double)((float)r->width / (float)r->height) : 1.0;
     P.width = r->width; P.height = r->height;
     P.slicing = 0;
     if (r->technique == VV_VOLIC_SLICING && need_frame) {
@@ -1067,6 +1068,15 @@ int vv_update_light_pos(VVRenderer *r)
 {
     if (!r) return fail(VV_ERR_INVALID, "null renderer");
     update_light(r);
+    r->frame_valid = false;
+    return VV_OK;
+}
+
+int vv_set_window(VVRenderer *r, int window_width, int window_height)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    if (window_width < 0 || window_height < 0 || (window_width == 0) != (window_height == 0)) return fail(VV_ERR_INVALID, "vv_set_window: bad size");
+    r->window_aspect = window_width > 0 ? (float)window_width / window_height : 0.0f;   // _aspect = (float)_w/_h
     r->frame_valid = false;
     return VV_OK;
 }
