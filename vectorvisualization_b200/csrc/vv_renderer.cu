@@ -702,6 +702,18 @@ void vv_default_lic_params(VVLicParams *p)
     p->numIterations = 255; p->stepsForward = 32; p->stepsBackward = 32; p->stepSizeLIC = 0.01f;
 }
 
+static int create_device_objects(VVRenderer *r)
+{
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, r->device));
+    r->num_sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&r->own_stream, cudaStreamNonBlocking));
+    r->stream = r->own_stream;
+    CU(cudaEventCreate(&r->ev0));
+    CU(cudaEventCreate(&r->ev1));
+    return VV_OK;
+}
+
 int vv_create(VVRenderer **out, int cuda_device)
 {
     if (!out) return fail(VV_ERR_INVALID, "vv_create: null out");
@@ -715,13 +727,8 @@ int vv_create(VVRenderer **out, int cuda_device)
     CU(cudaSetDevice(cuda_device));
     VVRenderer *r = new VVRenderer();
     r->device = cuda_device;
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, cuda_device));
-    r->num_sms = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&r->own_stream, cudaStreamNonBlocking));
-    r->stream = r->own_stream;
-    CU(cudaEventCreate(&r->ev0));
-    CU(cudaEventCreate(&r->ev1));
+    const int rc = create_device_objects(r);
+    if (rc != VV_OK) { vv_destroy(r); return rc; }       // (the error text set by fail() stays)
     vv_default_lic_params(&r->lp);
     // TransferEdit ctor, VV/transferEdit.cpp:76-82
     for (int i = 0; i < 256; ++i) {
