@@ -321,7 +321,11 @@ def run_cuda(args):
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = (json.load(open(prof)).get(scene.name) or {}).get("bytes_per_launch")
+            entry = json.load(open(prof)).get(scene.name) or {}
+            roofline["traffic"] = entry.get("bytes_per_launch")
+            if entry.get("ncu"):
+                # the kernel is not byte-bound: what it IS bound by, from the committed ncu capture of this kernel
+                roofline["ncu"] = entry["ncu"]
         except Exception:
             pass
 
