@@ -149,7 +149,7 @@ VV_API int vv_enable_lowres(VVRenderer *r, int enable);
 VV_API int vv_set_window(VVRenderer *r, int window_width, int window_height);
 VV_API int vv_enable_float_target(VVRenderer *r, int enable);
 VV_API int vv_set_option(VVRenderer *r, int option, int value);
-/* Screenshot / recording: Renderer::screenshot / switchRecording (VV/renderer.h:99-101, keys 'p' / 'P' VV/3DLIC.cpp:262-270)
+/* Screenshot / recording: Renderer::screenshot / switchRecording (VV/renderer.h:99-101, keys '0' / 'R', VV/3DLIC.cpp:259-270)
  * and the tail of Renderer::renderFBO (VV/renderer.cpp:1478-1513): after a screenshot request, and for every vv_render
  * while recording, the stored RGBA8 frame is written as PNG to "<dir>/<frames>_<file_name>" (recording or animation on;
  * frames counts the recorded frames) or "<dir>/<dd-mm-YYYY HH-MM-SS> <file_name>".  Defaults: dir "snapshotOut",
@@ -166,6 +166,31 @@ VV_API const char *vv_last_snapshot_path(VVRenderer *r);
  * mt19937(seed).  The size must equal the frame size at vv_render. */
 VV_API int vv_set_mc_offsets(VVRenderer *r, const float *offsets, int width, int height);
 VV_API int vv_update_mc_offset_tex(VVRenderer *r, int width, int height, uint32_t seed);
+/* ---- key map: keyboard / keyboardSpecial of VV/3DLIC.cpp:243-488 -------------------------------------------------------------
+ * VVAppState is the counterpart of the application's globals (licParams, renderTechnique, animationMode, updateSceneCont,
+ * clipPlanes[i]._active, currentClipPlane, VV/3DLIC.h:29-55) and is owned by the caller, as they are there.
+ * vv_key_apply is plain host logic (no device): it applies one key to the state with the reference's increments and clamps
+ * ('[' ']' sample distance /2 x2 in [0,1]; 's' 'x' 'S' 'X' LIC steps +-1 >= 1; 'a' 'z' LIC step x2 /2 >= 0.0005; 'h' 'n' noise
+ * frequency +-0.2 >= 0.5; 'j' 'm' illumination scale +-0.05 >= 0.05; 'g' 'b' gradient scale +-0.2 >= 0.2; 'L' low-res; 'F' float
+ * target; ' ' continuous; '1'-'4' clip planes; '6'-'9', '.', 'r' shader defines; 'u' LIC volume; '0' screenshot; 'R' recording;
+ * special keys 1..5 = F1..F5 technique / animation) and returns a mask of VVKeyAction saying what the reference does next.
+ * vv_keyboard applies the key and carries those actions out on the handle (returns the mask, or -1 with vv_last_error set).
+ * 'q' / Esc return VV_KEY_QUIT instead of calling exit(1). */
+typedef struct VVAppState {
+    VVLicParams lic;
+    int technique;                  /* VVTechnique; VV_VOLIC_VOLUME at start-up (VV/3DLIC.h:51) */
+    int lowres, float_target, continuous, recording, animation, screenshot;
+    int clip_active[3], selected_clip;   /* selected_clip: 0..2 or -1 */
+    char defines[64];               /* the string of the last loadGLSLShader(defines) request, "" = none */
+} VVAppState;
+typedef enum VVKeyAction {
+    VV_KEY_UPDATE_SCENE = 1, VV_KEY_RELOAD_SHADER = 2, VV_KEY_UPDATE_LICVOLUME = 4, VV_KEY_UPDATE_SLICES = 8, VV_KEY_QUIT = 16,
+    VV_KEY_SCREENSHOT = 32, VV_KEY_SWITCH_RECORDING = 64, VV_KEY_SET_TECHNIQUE = 128
+} VVKeyAction;
+VV_API void vv_app_state_init(VVAppState *s);
+VV_API int vv_key_apply(VVAppState *s, int key, int special);
+VV_API int vv_keyboard(VVRenderer *r, VVAppState *s, int key, int special);
+
 /* User clip planes: ClipPlane::setNormal(x, y, z, d) + activation (VV/transform.cpp:296-315, 446-483), index 0..2 =
  * GL_CLIP_PLANE0 + index (VV/3DLIC.cpp:763-781).  equation = (n.xyz, d) in volume-centred object coordinates, the
  * half-space n.q + d >= 0 is kept; NULL keeps the stored equation.  Semantics as drawn by Renderer::render

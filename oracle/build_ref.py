@@ -138,7 +138,8 @@ def build_host_objects(verbose=False):
     shim = os.path.join(HERE, "ref_shim")
     objs = []
     units = ["mmath.cpp", "reader.cpp", "parseArg.cpp", "gradient.cpp", "dataset.cpp", "transferEdit.cpp", "texture.cpp", "illumination.cpp", "slicing.cpp",
-             "transform.cpp", "trackball.cpp", "camera.cpp", "VolumeBuffer.cpp", "renderer.cpp", "GLSLShader.cpp"]
+             "transform.cpp", "trackball.cpp", "camera.cpp", "VolumeBuffer.cpp", "renderer.cpp", "GLSLShader.cpp",
+             "fpsCounter.cpp", "timer.cpp", "3DLIC.cpp"]
     flags = ["-O1", "-std=c++14", "-fPIC", "-w", "-fpermissive", "-ffp-contract=off", "-DGLEW_NO_GLU", "-D_USE_MATH_DEFINES",
              "-include", "climits", "-include", "cstring", "-include", "cstdlib", "-include", os.path.join(shim, "ref_prelude.h"),
              "-I", shim, "-I", REF]
@@ -154,9 +155,10 @@ def build_host_objects(verbose=False):
             print(" ".join(cmd))
         subprocess.check_call(cmd)
         objs.append(o)
-    o = os.path.join(GEN, "ref_host_driver.o")
-    subprocess.check_call(["g++"] + flags + ["-c", os.path.join(HERE, "ref_host_driver.cpp"), "-o", o])
-    objs.append(o)
+    for drv in ("ref_host_driver", "ref_app_driver"):
+        o = os.path.join(GEN, drv + ".o")
+        subprocess.check_call(["g++"] + flags + ["-c", os.path.join(HERE, drv + ".cpp"), "-o", o])
+        objs.append(o)
     return objs
 
 

@@ -1,0 +1,143 @@
+/* ref_app_driver.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * VV/3DLIC.cpp -- the reference's application file with its GLUT callbacks -- compiled UNMODIFIED against oracle/ref_shim/
+ * (Windows.h, GL\glew.h, GL\freeglut.h stand-ins).  Nothing opens a window or enters a main loop: this driver wires the
+ * application's own global objects the way its init() does (VV/3DLIC.cpp:677-799), then calls keyboard() / keyboardSpecial()
+ * directly and reads the globals back.  What is checked against it: the key map of the product's vv_keyboard /
+ * vv_keyboard_special (tests/test_host_vs_ref.py).
+ * The HUD (VV/hud.cpp, out of scope: VBO text rendering) is replaced by a recorder of the status line it is handed. */
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "GL/glew.h"
+#include <cmath>
+#include <ctime>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#define private public
+#define protected public
+#include "renderer.h"
+#include "transform.h"
+#undef private
+#undef protected
+#include "camera.h"
+#include "hud.h"
+#include "transferEdit.h"
+#include "imageUtils.h"
+
+/* ---- the application's globals (defined in VV/3DLIC.h, which only VV/3DLIC.cpp includes) ---- */
+extern Camera cam;
+extern Renderer renderer;
+extern ClipPlane clipPlanes[3];
+extern ClipPlane *currentClipPlane;
+extern Transform light;
+extern VectorDataSet vd;
+extern LICFilter licFilter;
+extern LICParams licParams;
+extern RenderTechnique renderTechnique;
+extern bool animationMode, updateSceneCont, updateScene, screenshot, lightVisible, wire, useIdle, requestHighRes;
+void keyboard(unsigned char key, int x, int y);
+void keyboardSpecial(int key, int x, int y);
+void resize(int width, int height);
+
+/* ---- HUD stand-in: keeps the status line of updateHUD (VV/3DLIC.cpp:203-240) ---- */
+static std::string g_hud_text;
+OpenGLHUD::OpenGLHUD(bool, bool) {}
+OpenGLHUD::~OpenGLHUD() {}
+bool OpenGLHUD::Init() { return true; }
+void OpenGLHUD::SetNumLines(int, bool) {}
+void OpenGLHUD::SetViewport(int *, bool) {}
+void OpenGLHUD::SetText(const char *text, bool) { g_hud_text = text ? text : ""; }
+void OpenGLHUD::DrawHUD(const char *, unsigned int, unsigned int) {}
+
+/* the shader sources a key hands to the GL: the defines string arrives as its own source string (VV/GLSLShader.cpp:120-180) */
+static std::string g_last_defines;
+static int g_shader_loads = 0;
+extern "C" void glShaderSourceARB(GLhandleARB, GLsizei n, const GLcharARB **src, const GLint *)
+{
+    g_last_defines.clear();                                   /* the defines of the LAST source hand-over ("" = none) */
+    for (int i = 0; i < n; ++i)
+        if (src && src[i] && !std::strncmp(src[i], "#define", 7)) g_last_defines = src[i];
+    ++g_shader_loads;
+}
+
+static bool g_wired = false;
+
+extern "C" {
+
+/* keys[i] is fed to keyboard() (special[i] == 0) or keyboardSpecial() (special[i] != 0; 1..5 = GLUT_KEY_F1..F5) after the
+ * application state has been reset to its start-up values.  out[0..7] = LICParams (stepSizeVol, gradientScale, illumScale,
+ * freqScale, numIterations, stepsForward, stepsBackward, stepSizeLIC); [8] technique; [9] low-res; [10] FBO; [11] recording;
+ * [12] animation flag; [13..15] clip plane active; [16] selected clip plane or -1; [17] screenshot requested;
+ * [18] shader (re)loads triggered; [19] continuous mode; [20] frame store.  defines_out / hud_out receive the last "#define ..."
+ * string handed to glShaderSourceARB (empty: none since reset) and the HUD status line. */
+int vvref_keyboard(const char *dat, const char *ref_dir, const unsigned char *keys, const int *special, int n, float *out,
+                   char *defines_out, int defines_cap, char *hud_out, int hud_cap)
+{
+    static Texture dummy[10];
+    if (!g_wired) {
+        if (!vd.loadData(dat)) return -10;
+        licFilter.createBoxFilter();
+        light.setDistance(1.0f);
+        renderer.setLight(&light);
+        renderer.setCamera(&cam);
+        VolumeData *v = vd.getVolumeData();
+        for (int i = 0; i < 3; ++i) {
+            clipPlanes[i].setPlaneId(GL_CLIP_PLANE0 + i);
+            clipPlanes[i].setBoundingBox(-v->extent[0] / 2.0f, -v->extent[1] / 2.0f, -v->extent[2] / 2.0f, v->extent[0] / 2.0f, v->extent[1] / 2.0f, v->extent[2] / 2.0f);
+        }
+        renderer.setClipPlanes(clipPlanes, 3);
+        renderer.setVolumeData(v);
+        renderer.setLICFilter(&licFilter);
+        renderer.setDataTex(&dummy[0]); renderer.setScalarTex(&dummy[1]); renderer.setNoiseTex(&dummy[2]);
+        renderer.setTFrgbTex(&dummy[3]); renderer.setTFalphaOpacTex(&dummy[4]);
+        renderer.setIllumZoecklerTex(&dummy[5]); renderer.setIllumMalloDiffTex(&dummy[6]); renderer.setIllumMalloSpecTex(&dummy[7]);
+        renderer._licKernelTex = &dummy[8];
+        renderer.setLICParams(&licParams);
+        renderer._licvolumebuffer = new VolumeBuffer(GL_RGBA16F_ARB, 4, 4, 4, 2);   /* Renderer::init allocates 512^3 (VV/renderer.cpp:97) */
+        resize(64, 48);
+        g_wired = true;
+    }
+    /* start-up state: LICParams ctor (VV/types.h:91-109), VV/3DLIC.h:29-55 */
+    licParams = LICParams();
+    renderTechnique = VOLIC_VOLUME;
+    renderer.setTechnique(renderTechnique);
+    renderer._lowRes = false; renderer._useFBO = false; renderer._recording = false; renderer._screenShot = false;
+    renderer._isAnimationOn = false; renderer._storeFrame = true; renderer._wireframe = false;
+    for (int i = 0; i < 3; ++i) { clipPlanes[i]._active = false; clipPlanes[i]._visible = false; }
+    currentClipPlane = NULL;
+    animationMode = false; updateSceneCont = false; updateScene = true; screenshot = false; lightVisible = false; wire = false;
+    requestHighRes = false;
+    g_last_defines.clear(); g_shader_loads = 0; g_hud_text.clear();
+    char cwd[4096];
+    if (!getcwd(cwd, sizeof(cwd))) return -11;
+    if (ref_dir && chdir(ref_dir) != 0) return -12;        /* "shader/..." is opened relative to the working directory */
+    for (int i = 0; i < n; ++i) {
+        if (special[i]) keyboardSpecial(keys[i], 0, 0);
+        else keyboard(keys[i], 0, 0);
+    }
+    if (chdir(cwd) != 0) return -13;
+    out[0] = licParams.stepSizeVol; out[1] = licParams.gradientScale; out[2] = licParams.illumScale; out[3] = licParams.freqScale;
+    out[4] = (float)licParams.numIterations; out[5] = (float)licParams.stepsForward; out[6] = (float)licParams.stepsBackward;
+    out[7] = licParams.stepSizeLIC;
+    out[8] = (float)(int)renderer._renderMode;
+    out[9] = renderer._lowRes; out[10] = renderer._useFBO; out[11] = renderer._recording; out[12] = renderer._isAnimationOn;
+    for (int i = 0; i < 3; ++i) out[13 + i] = clipPlanes[i]._active;
+    out[16] = currentClipPlane ? (float)(currentClipPlane - clipPlanes) : -1.0f;
+    out[17] = renderer._screenShot;
+    out[18] = (float)g_shader_loads;
+    out[19] = updateSceneCont;
+    out[20] = renderer._storeFrame;
+    if (defines_out && defines_cap > 0) { std::strncpy(defines_out, g_last_defines.c_str(), defines_cap - 1); defines_out[defines_cap - 1] = 0; }
+    if (hud_out && hud_cap > 0) { std::strncpy(hud_out, g_hud_text.c_str(), hud_cap - 1); hud_out[hud_cap - 1] = 0; }
+    return 0;
+}
+
+int vvref_has_app(void) { return 1; }
+
+} /* extern "C" */

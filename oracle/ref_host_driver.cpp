@@ -43,7 +43,8 @@
 #include <cmath>
 
 /* ------------------------------------------------------------------------------------------------ GL capture */
-static std::map<GLuint, VVStubTex> g_tex;
+/* never destroyed: the reference's global objects (VV/3DLIC.h) call glDeleteTextures from their static destructors */
+static std::map<GLuint, VVStubTex> &g_tex = *new std::map<GLuint, VVStubTex>();
 static GLuint g_next_id = 1, g_bound = 0, g_last = 0;
 
 static VVStubTex &cur()

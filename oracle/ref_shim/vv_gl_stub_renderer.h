@@ -73,8 +73,10 @@ static inline void glDeleteFramebuffersEXT(GLsizei, const GLuint *) {}
 static inline void glDeleteRenderbuffersEXT(GLsizei, const GLuint *) {}
 static inline void glCopyTexSubImage3D(GLenum, GLint, GLint, GLint, GLint, GLint, GLint, GLsizei, GLsizei) {}
 static inline void glCopyTexImage2D(GLenum, GLint, GLenum, GLint, GLint, GLsizei, GLsizei, GLint) {}
-static inline void glGetObjectParameterivARB(GLhandleARB, GLenum, GLint *v) { if (v) *v = 0; }
-static inline void glShaderSourceARB(GLhandleARB, GLsizei, const GLcharARB **, const GLint *) {}
+/* compile / link status: success; info-log lengths and active-uniform counts: 0 */
+static inline void glGetObjectParameterivARB(GLhandleARB, GLenum pname, GLint *v)
+{ if (v) *v = (pname == GL_OBJECT_COMPILE_STATUS_ARB || pname == GL_OBJECT_LINK_STATUS_ARB) ? 1 : 0; }
+void glShaderSourceARB(GLhandleARB, GLsizei n, const GLcharARB **src, const GLint *len);   /* captured: the defines string (ref_app_driver.cpp) */
 static inline void glGetInfoLogARB(GLhandleARB, GLsizei, GLsizei *len, GLcharARB *log) { if (len) *len = 0; if (log) log[0] = 0; }
 static inline void glGetActiveUniformARB(GLhandleARB, GLuint, GLsizei, GLsizei *len, GLint *size, GLenum *type, GLcharARB *name)
 { if (len) *len = 0; if (size) *size = 0; if (type) *type = 0; if (name) name[0] = 0; }
@@ -113,4 +115,5 @@ static inline void gluDisk(GLUquadricObj *, GLdouble, GLdouble, GLint, GLint) {}
 #ifdef __cplusplus
 }
 #endif
+#include "vv_glut_stub.h"
 #endif

@@ -262,3 +262,30 @@ def _parse_draws(out, n):
         draws.append(d)
     assert k == n
     return draws
+
+
+def has_app():
+    try:
+        return available() and bool(_L().vvref_has_app())
+    except AttributeError:
+        return False
+
+
+def app_keyboard(dat_path, keys, ref_dir="/root/reference/VectorVisualization"):
+    """keyboard() / keyboardSpecial() of VV/3DLIC.cpp (compiled unmodified, oracle/ref_app_driver.cpp) fed with `keys` -- a
+    list of (key, special) -- from the application's start-up state.  Returns dict(lic=(stepSizeVol, gradientScale, illumScale,
+    freqScale, numIterations, stepsForward, stepsBackward, stepSizeLIC), technique, lowres, fbo, recording, animation,
+    clip_active[3], selected_clip, screenshot, shader_loads, continuous, store_frame, defines, hud)"""
+    n = len(keys)
+    k = (ctypes.c_ubyte * max(n, 1))(*[(x if isinstance(x, int) else ord(x)) & 0xff for x, _ in keys])
+    sp = (ctypes.c_int * max(n, 1))(*[int(bool(f)) for _, f in keys])
+    out = (ctypes.c_float * 21)()
+    d = ctypes.create_string_buffer(256)
+    h = ctypes.create_string_buffer(1024)
+    rc = _L().vvref_keyboard(dat_path.encode(), ref_dir.encode() if ref_dir else None, k, sp, n, out, d, 256, h, 1024)
+    assert rc == 0, rc
+    o = list(out)
+    return dict(lic=(np.float32(o[0]), np.float32(o[1]), np.float32(o[2]), np.float32(o[3]), int(o[4]), int(o[5]), int(o[6]), np.float32(o[7])),
+                technique=int(o[8]), lowres=int(o[9]), fbo=int(o[10]), recording=int(o[11]), animation=int(o[12]),
+                clip_active=[int(x) for x in o[13:16]], selected_clip=int(o[16]), screenshot=int(o[17]), shader_loads=int(o[18]),
+                continuous=int(o[19]), store_frame=int(o[20]), defines=d.value.decode().strip(), hud=h.value.decode())

@@ -455,3 +455,63 @@ def test_proxy_cube_faces(oracle, tmp_path):
         # planar, on a face of the box
         axis = int(np.argmax(np.abs(outward)))
         assert len(set(P[:, axis])) == 1
+
+
+@pytest.mark.skipif(not refhost.has_app(), reason="oracle/_ref built without VV/3DLIC.cpp")
+def test_key_map_matches_the_application(vv, tmp_path):
+    """vv_key_apply against keyboard() / keyboardSpecial() of VV/3DLIC.cpp:243-488, compiled unmodified and called directly
+    (oracle/ref_app_driver.cpp): every key on its own, every key repeated until its clamp bites, and random key sequences;
+    LICParams compared bit for bit, technique / flags / clip-plane selection / shader defines exactly"""
+    from vectorvisualization_b200 import configs, fields as F
+    s = configs.cfg1(n=8, size=16)
+    dat = F.write_dat(str(tmp_path / "vol.dat"), s.field, slice_thickness=s.slice_dist)
+    with open(dat, "a") as f:
+        f.write("TimeDependent: 0 0\n")
+    if not os.path.isdir("/root/reference/VectorVisualization/shader"):
+        pytest.skip("the shader sources the reference's key handler re-loads are not on this box")
+
+    def ours(keys):
+        st = vv.AppState()
+        acts = [vv.keyApply(st, k, sp) for k, sp in keys]
+        return st, acts
+
+    def check(keys):
+        ref = refhost.app_keyboard(dat, keys)
+        st, acts = ours(keys)
+        lic = st.lic
+        got = (np.float32(lic.stepSizeVol), np.float32(lic.gradientScale), np.float32(lic.illumScale), np.float32(lic.freqScale),
+               lic.numIterations, lic.stepsForward, lic.stepsBackward, np.float32(lic.stepSizeLIC))
+        assert all(np.asarray(a).tobytes() == np.asarray(b).tobytes() for a, b in zip(got, ref["lic"])), (keys, got, ref["lic"])
+        assert st.technique == ref["technique"], keys
+        assert (st.lowres, st.float_target, st.recording, st.animation, st.screenshot, st.continuous) == \
+            (ref["lowres"], ref["fbo"], ref["recording"], ref["animation"], ref["screenshot"], ref["continuous"]), keys
+        assert ref["store_frame"] == 1 - st.continuous
+        assert list(st.clip_active) == ref["clip_active"] and st.selected_clip == ref["selected_clip"], keys
+        reloads = sum(1 for a in acts if a & vv.KEY_RELOAD_SHADER)
+        assert ref["shader_loads"] == 16 * reloads, keys          # 8 programs x (vertex + fragment) per Renderer::loadGLSLShader
+        if reloads:
+            assert st.defines.decode() == ref["defines"], keys
+        return st, acts, ref
+
+    plain = list("0RHrwtFpLI[]sxSXazhnjmgbu1234567899. ") + ["y", "Z"]
+    for k in plain:
+        check([(k, 0)])
+    for f in range(1, 7):
+        check([(f, 1)])
+    for k in "[]xXznmb":                                   # down (or up) to the clamp and beyond
+        check([(k, 0)] * 40)
+    for k in "sSahjg":
+        check([(k, 0)] * 12)
+    # what the application does next (VV/3DLIC.cpp:450-455, 457-488)
+    st, acts, ref = check([(4, 1), ("s", 0), (3, 1), ("h", 0), (2, 1), ("h", 0), ("H", 0)])
+    assert acts[0] == vv.KEY_SET_TECHNIQUE | vv.KEY_UPDATE_SCENE | vv.KEY_UPDATE_LICVOLUME
+    assert acts[1] == vv.KEY_UPDATE_SCENE | vv.KEY_UPDATE_LICVOLUME
+    assert acts[2] == vv.KEY_SET_TECHNIQUE | vv.KEY_UPDATE_SCENE | vv.KEY_UPDATE_SLICES
+    assert acts[3] == vv.KEY_UPDATE_SCENE | vv.KEY_UPDATE_SLICES
+    assert acts[5] == vv.KEY_UPDATE_SCENE and acts[6] == 0
+    assert vv.keyApply(st, "q") == vv.KEY_QUIT and vv.keyApply(st, 27) == vv.KEY_QUIT      # exit(1) there (not fed to the reference)
+    assert "Raycast" in ref["hud"] and "Freqency Scale: 1.4" in ref["hud"]
+    rng = np.random.RandomState(11)
+    alphabet = [(k, 0) for k in "0RrFpL[]sxSXazhnjmgbu12346789. "] + [(f, 1) for f in range(1, 6)]
+    for _ in range(25):
+        check([alphabet[i] for i in rng.randint(0, len(alphabet), size=30)])

@@ -898,3 +898,29 @@ def test_lowres_window_aspect(vv, oracle):
     s.window = None
     _, img2, _, _, _ = render_cuda(vv, s)
     assert not np.array_equal(img, img2)
+
+
+def test_keyboard_drives_the_renderer(vv):
+    """vv_keyboard = the key map of VV/3DLIC.cpp (pinned on the CPU in test_key_map_matches_the_application) carried out on a
+    handle: a frame after the keys equals the frame of a scene configured directly with the resulting parameters"""
+    from vectorvisualization_b200 import configs
+    from vectorvisualization_b200.configs import apply_scene
+    s = configs.cfg3(n=32, size=64)
+    r = vv.Renderer(0)
+    apply_scene(r, s)
+    st = vv.AppState()
+    st.lic = s.lic_params()
+    st.technique = vv.VOLIC_RAYCAST
+    for key in "[sXL1":                       # sample distance / 2, one more forward step, one fewer backward step, low-res, clip plane 1
+        act = r.keyboard(st, key)
+        assert act & vv.KEY_UPDATE_SCENE
+    r.render(True)
+    a, na = r.readRGBA32F(), r.lastRaySamples()
+    p = s.lic_params()
+    s2 = configs.cfg3(n=32, size=64)
+    s2.params.update(stepSizeVol=p.stepSizeVol / 2, stepsForward=p.stepsForward + 1, stepsBackward=p.stepsBackward - 1)
+    s2.lowres = 1
+    s2.clip_planes = ((0.0, 0.0, -1.0, 0.0),)      # ClipPlane ctor, VV/transform.cpp:240-254
+    _, b, _, _, nb = render_cuda(vv, s2)
+    assert na == nb and na > 0 and np.array_equal(a, b)
+    assert r.keyboard(st, "q") == vv.KEY_QUIT and r.keyboard(st, "H") == 0

@@ -41,6 +41,27 @@ class LICParams(ctypes.Structure):
             setattr(self, k, v)
 
 
+class AppState(ctypes.Structure):
+    """VVAppState: the application state the reference keeps in globals (VV/3DLIC.h:29-55), driven by keyApply / Renderer.keyboard"""
+    _fields_ = [("lic", LICParams), ("technique", ctypes.c_int), ("lowres", ctypes.c_int), ("float_target", ctypes.c_int),
+                ("continuous", ctypes.c_int), ("recording", ctypes.c_int), ("animation", ctypes.c_int), ("screenshot", ctypes.c_int),
+                ("clip_active", ctypes.c_int * 3), ("selected_clip", ctypes.c_int), ("defines", ctypes.c_char * 64)]
+
+    def __init__(self):
+        super().__init__()
+        load_library().vv_app_state_init(ctypes.byref(self))
+
+
+KEY_UPDATE_SCENE, KEY_RELOAD_SHADER, KEY_UPDATE_LICVOLUME, KEY_UPDATE_SLICES, KEY_QUIT, KEY_SCREENSHOT, KEY_SWITCH_RECORDING, \
+    KEY_SET_TECHNIQUE = 1, 2, 4, 8, 16, 32, 64, 128
+
+
+def keyApply(state, key, special=False):
+    """vv_key_apply: one key of VV/3DLIC.cpp's keyboard / keyboardSpecial applied to an AppState (host logic only)"""
+    k = key if isinstance(key, int) else ord(key)
+    return load_library().vv_key_apply(ctypes.byref(state), k, int(bool(special)))
+
+
 class DatInfo(ctypes.Structure):
     _fields_ = [("raw_file", ctypes.c_char * 512), ("resolution", ctypes.c_int * 3), ("slice_thickness", ctypes.c_float * 3),
                 ("data_type", ctypes.c_int), ("data_dim", ctypes.c_int), ("time_begin", ctypes.c_int), ("time_end", ctypes.c_int)]
@@ -83,7 +104,9 @@ def load_library():
         "vv_default_lic_params": ([ctypes.POINTER(LICParams)], None),
         "vv_set_camera": ([P, ctypes.POINTER(F), ctypes.POINTER(F), F, F, F, F], I),
         "vv_set_light": ([P, ctypes.POINTER(F), F], I), "vv_update_light_pos": ([P], I),
-        "vv_enable_lowres": ([P, I], I), "vv_set_window": ([P, I, I], I), "vv_enable_float_target": ([P, I], I), "vv_set_option": ([P, I, I], I),
+        "vv_enable_lowres": ([P, I], I), "vv_set_window": ([P, I, I], I),
+        "vv_app_state_init": ([P], None), "vv_key_apply": ([P, I, I], I), "vv_keyboard": ([P, P, I, I], I),
+        "vv_enable_float_target": ([P, I], I), "vv_set_option": ([P, I, I], I),
         "vv_set_mc_offsets": ([P, P, I, I], I), "vv_update_mc_offset_tex": ([P, I, I, ctypes.c_uint32], I),
         "vv_set_clip_plane": ([P, I, P, I], I),
         "vv_set_snapshot": ([P, CP, CP, I], I), "vv_screenshot": ([P], I), "vv_switch_recording": ([P], I),
@@ -222,6 +245,14 @@ class Renderer:
     def resize(self, w, h):
         _chk(self._lib.vv_resize(self._h, w, h))
         self.width, self.height = w, h
+
+    def keyboard(self, state, key, special=False):
+        """keyboard / keyboardSpecial of VV/3DLIC.cpp applied to `state` and carried out on this renderer; returns the action mask"""
+        k = key if isinstance(key, int) else ord(key)
+        act = self._lib.vv_keyboard(self._h, ctypes.byref(state), k, int(bool(special)))
+        if act < 0:
+            _chk(1)
+        return act
 
     def setWindow(self, w, h):
         """Camera::setWindow (VV/transform.h:79-80): the aspect ratio of the projection when it is not the frame's (low-res preset)"""
