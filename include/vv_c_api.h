@@ -116,6 +116,20 @@ VV_API int vv_set_vector_field(VVRenderer *r, const void *data, const void *next
                                const int dims[3], const float slice_dist[3]);
 /* interpIndex / InterpSize of VectorDataSet (VV/dataset.cpp:202-210, VV/3DLIC.cpp:705): re-packs on the GPU */
 VV_API int vv_set_time_interp(VVRenderer *r, int interp_index, int interp_size);
+/* Animation tick.  idle() (VV/3DLIC.cpp:129-172) calls, per tick, VectorDataSet::createTextureIterp -- pack with the fraction
+ * interpIndex / InterpSize, then interpIndex++ (VV/dataset.cpp:590-633) -- and checkInterpolateStage -- once interpIndex reaches
+ * InterpSize: data <- time step getNextTimeStep() (wrapping from the last to the first), newData <- the step after it,
+ * interpIndex <- 0 (VV/dataset.cpp:202-210, VV/reader.cpp:327-336).  VVTimeCursor is that bookkeeping as plain host logic;
+ * vv_time_cursor_tick returns the fraction index this tick's texture is packed with and sets *advanced when the pair of time
+ * steps moved on (data = step cursor->current, newData = step vv_time_cursor_next).
+ * vv_idle does the whole tick on a handle whose field came from vv_load_dat: re-pack on the GPU, advance, and re-read the two
+ * RAW files when the pair moves on.  Returns VV_OK, or VV_ERR_STATE when the field was not loaded from a DAT file. */
+typedef struct VVTimeCursor { int time_begin, time_end, current, interp_index, interp_size; } VVTimeCursor;
+VV_API void vv_time_cursor_init(VVTimeCursor *c, int time_begin, int time_end, int interp_size);
+VV_API int vv_time_cursor_next(const VVTimeCursor *c);
+VV_API int vv_time_cursor_tick(VVTimeCursor *c, int *advanced);
+VV_API int vv_idle(VVRenderer *r);
+VV_API int vv_get_time_cursor(VVRenderer *r, VVTimeCursor *out);
 /* setScalarTex (VolumeDataSet, VV/dataset.cpp:840-1050); UCHAR or FLOAT scalar */
 VV_API int vv_set_scalar(VVRenderer *r, const void *data, int dtype, const int dims[3]);
 /* setNoiseTex (NoiseDataSet, VV/dataset.cpp:1124-1344): u8 noise; with_gradients = the `-g` flag:

@@ -138,6 +138,34 @@ int vvref_keyboard(const char *dat, const char *ref_dir, const unsigned char *ke
     return 0;
 }
 
+/* The animation as init() + idle() drive it (VV/3DLIC.cpp:686-707, 129-142): after loadData the two first time steps are
+ * loaded, createTextureIterp + checkInterpolateStage run once, and then once per idle tick.  For tick i (0-based) out[3i] =
+ * the current time step and out[3i+1] = interpIndex when the tick starts (the fraction index its texture is packed with),
+ * out[3i+2] = 1 if checkInterpolateStage moved to the next pair of time steps during the tick.  The texture uploaded by tick
+ * `tex_tick` (RGBA float, as handed to glTexImage3D) is copied to tex_out. */
+int vvref_animation_ticks(const char *dat, int n, int *out, int tex_tick, float *tex_out, size_t tex_bytes)
+{
+    VectorDataSet v;
+    if (!v.loadData(dat)) return -10;
+    v.getVolumeData()->data = v.loadTimeStep(v.getCurTimeStep());
+    v.getVolumeData()->newData = v.loadTimeStep(v.NextTimeStep());
+    v.setInterpolateSize(10);
+    v.createTextureIterp("VectorData_Tex", GL_TEXTURE2_ARB, true);
+    v.checkInterpolateStage();
+    for (int i = 0; i < n; ++i) {
+        const int step = v.getCurTimeStep(), idx = v.interpIndex;
+        v.createTextureIterp("VectorData_Tex", GL_TEXTURE2_ARB, true);
+        if (i == tex_tick && tex_out) {
+            VVStubTex *t = vv_stub_texture(vv_stub_last_texture());
+            if (!t || t->bytes > tex_bytes) return -11;
+            std::memcpy(tex_out, t->data, t->bytes);
+        }
+        v.checkInterpolateStage();
+        out[3 * i] = step; out[3 * i + 1] = idx; out[3 * i + 2] = (v.getCurTimeStep() != step) ? 1 : 0;
+    }
+    return 0;
+}
+
 int vvref_has_app(void) { return 1; }
 
 } /* extern "C" */

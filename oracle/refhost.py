@@ -289,3 +289,15 @@ def app_keyboard(dat_path, keys, ref_dir="/root/reference/VectorVisualization"):
                 technique=int(o[8]), lowres=int(o[9]), fbo=int(o[10]), recording=int(o[11]), animation=int(o[12]),
                 clip_active=[int(x) for x in o[13:16]], selected_clip=int(o[16]), screenshot=int(o[17]), shader_loads=int(o[18]),
                 continuous=int(o[19]), store_frame=int(o[20]), defines=d.value.decode().strip(), hud=h.value.decode())
+
+
+def animation_ticks(dat_path, n, tex_tick=-1, tex_shape=None):
+    """init() + n idle() ticks of the reference's animation on a time-dependent DAT file (oracle/ref_app_driver.cpp): returns
+    ([(current time step, interpIndex the tick's texture is packed with, moved on), ...], texture of tick tex_tick or None)"""
+    out = (ctypes.c_int * (3 * n))()
+    tex = np.zeros(tuple(tex_shape) + (4,), np.float32) if tex_shape is not None else None
+    L = _L()
+    L.vvref_animation_ticks.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
+    rc = L.vvref_animation_ticks(dat_path.encode(), n, out, tex_tick, tex.ctypes.data if tex is not None else None, tex.nbytes if tex is not None else 0)
+    assert rc == 0, rc
+    return [(out[3 * i], out[3 * i + 1], out[3 * i + 2]) for i in range(n)], tex

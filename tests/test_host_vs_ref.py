@@ -515,3 +515,24 @@ def test_key_map_matches_the_application(vv, tmp_path):
     alphabet = [(k, 0) for k in "0RrFpL[]sxSXazhnjmgbu12346789. "] + [(f, 1) for f in range(1, 6)]
     for _ in range(25):
         check([alphabet[i] for i in rng.randint(0, len(alphabet), size=30)])
+
+
+@pytest.mark.skipif(not refhost.has_app(), reason="oracle/_ref built without VV/3DLIC.cpp")
+def test_animation_cursor_matches_the_application(vv, tmp_path):
+    """VVTimeCursor against the animation as VV/3DLIC.cpp drives it: init() (createTextureIterp + checkInterpolateStage once) and
+    then the same pair once per idle() tick, on a time-dependent DAT file -- current time step, fraction index of every tick's
+    texture, and the ticks at which the pair of time steps moves on (wrapping from the last step to the first)"""
+    from vectorvisualization_b200 import fields as F
+    steps = [F.abc_flow(6) * np.float32(1 + 0.3 * t) for t in range(3)]
+    dat = F.write_dat(str(tmp_path / "anim.dat"), None, time_steps=steps)
+    ref, _ = refhost.animation_ticks(dat, 47)
+    c = vv.TimeCursor(0, 2, 10)
+    c.tick()                                           # what init() has done before the first idle tick
+    ours = []
+    for _ in range(47):
+        cur = c.current
+        used, adv = c.tick()
+        ours.append((cur, used, int(adv)))
+    assert ours == ref
+    assert [t for t, (_, _, adv) in enumerate(ref) if adv] == [8, 18, 28, 38]
+    assert ref[0] == (0, 1, 0) and ref[9] == (1, 0, 0) and ref[29] == (0, 0, 0)        # first tick: 1/10; wraps 2 -> 0

@@ -924,3 +924,27 @@ def test_keyboard_drives_the_renderer(vv):
     _, b, _, _, nb = render_cuda(vv, s2)
     assert na == nb and na > 0 and np.array_equal(a, b)
     assert r.keyboard(st, "q") == vv.KEY_QUIT and r.keyboard(st, "H") == 0
+
+
+def test_idle_tick_animation(vv, tmp_path):
+    """vv_idle = one idle() tick of the reference's animation (VV/3DLIC.cpp:129-142): the RGBA16F vector texture after k ticks
+    equals, bit for bit, the texture VectorDataSet::createTextureIterp uploads at tick k (VV/dataset.cpp compiled unmodified,
+    oracle/ref_app_driver.cpp) -- across the point where the pair of time steps moves on"""
+    from oracle import refhost, vvo
+    from vectorvisualization_b200 import fields as F
+    if not refhost.has_app():
+        pytest.skip("oracle/_ref built without VV/3DLIC.cpp")
+    steps = [np.ascontiguousarray(F.abc_flow(10)[:, :8, :6] * np.float32(1 + 0.3 * t)) for t in range(3)]
+    dat = F.write_dat(str(tmp_path / "anim.dat"), None, time_steps=steps)
+    shape = steps[0].shape[:3]
+    r = vv.Renderer(0)
+    r.loadDat(dat)
+    seq, _ = refhost.animation_ticks(dat, 24)
+    for k in range(24):
+        c = r.timeCursor()
+        assert (c.current, c.interp_index) == seq[k][:2]
+        r.idle()
+        if k in (0, 5, 8, 9, 10, 19, 23):
+            _, tex = refhost.animation_ticks(dat, k + 1, tex_tick=k, tex_shape=shape)
+            got = r.readFieldTexture(shape)
+            assert np.array_equal(got.view(np.uint32), vvo.half_round(tex).view(np.uint32)), k

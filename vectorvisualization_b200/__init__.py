@@ -62,6 +62,25 @@ def keyApply(state, key, special=False):
     return load_library().vv_key_apply(ctypes.byref(state), k, int(bool(special)))
 
 
+class TimeCursor(ctypes.Structure):
+    """VVTimeCursor: interpIndex / InterpSize and the current time step of an animated VectorDataSet (VV/dataset.cpp:202-210)"""
+    _fields_ = [("time_begin", ctypes.c_int), ("time_end", ctypes.c_int), ("current", ctypes.c_int), ("interp_index", ctypes.c_int),
+                ("interp_size", ctypes.c_int)]
+
+    def __init__(self, time_begin=0, time_end=0, interp_size=10):
+        super().__init__()
+        load_library().vv_time_cursor_init(ctypes.byref(self), time_begin, time_end, interp_size)
+
+    def next(self):
+        return load_library().vv_time_cursor_next(ctypes.byref(self))
+
+    def tick(self):
+        """one createTextureIterp + checkInterpolateStage: (fraction index of this tick's texture, moved on to the next pair)"""
+        adv = ctypes.c_int(0)
+        used = load_library().vv_time_cursor_tick(ctypes.byref(self), ctypes.byref(adv))
+        return used, bool(adv.value)
+
+
 class DatInfo(ctypes.Structure):
     _fields_ = [("raw_file", ctypes.c_char * 512), ("resolution", ctypes.c_int * 3), ("slice_thickness", ctypes.c_float * 3),
                 ("data_type", ctypes.c_int), ("data_dim", ctypes.c_int), ("time_begin", ctypes.c_int), ("time_end", ctypes.c_int)]
@@ -105,6 +124,8 @@ def load_library():
         "vv_set_camera": ([P, ctypes.POINTER(F), ctypes.POINTER(F), F, F, F, F], I),
         "vv_set_light": ([P, ctypes.POINTER(F), F], I), "vv_update_light_pos": ([P], I),
         "vv_enable_lowres": ([P, I], I), "vv_set_window": ([P, I, I], I),
+        "vv_time_cursor_init": ([P, I, I, I], None), "vv_time_cursor_next": ([P], I), "vv_time_cursor_tick": ([P, P], I),
+        "vv_idle": ([P], I), "vv_get_time_cursor": ([P, P], I),
         "vv_app_state_init": ([P], None), "vv_key_apply": ([P, I, I], I), "vv_keyboard": ([P, P, I, I], I),
         "vv_enable_float_target": ([P, I], I), "vv_set_option": ([P, I, I], I),
         "vv_set_mc_offsets": ([P, P, I, I], I), "vv_update_mc_offset_tex": ([P, I, I, ctypes.c_uint32], I),
@@ -253,6 +274,15 @@ class Renderer:
         if act < 0:
             _chk(1)
         return act
+
+    def idle(self):
+        """one animation tick of idle() (VV/3DLIC.cpp:129-172) for a field loaded with loadDat"""
+        _chk(self._lib.vv_idle(self._h))
+
+    def timeCursor(self):
+        c = TimeCursor()
+        _chk(self._lib.vv_get_time_cursor(self._h, ctypes.byref(c)))
+        return c
 
     def setWindow(self, w, h):
         """Camera::setWindow (VV/transform.h:79-80): the aspect ratio of the projection when it is not the frame's (low-res preset)"""

@@ -104,6 +104,33 @@ int vv_key_apply(VVAppState *s, int key, int special)
     return act;
 }
 
+// ---- animation bookkeeping: VectorDataSet::interpIndex / checkInterpolateStage + DatFile::getNextTimeStep ----
+void vv_time_cursor_init(VVTimeCursor *c, int time_begin, int time_end, int interp_size)
+{
+    if (!c) return;
+    c->time_begin = time_begin; c->time_end = time_end; c->current = time_begin;   // DatFile: _timestep = _timeStepBeg
+    c->interp_index = 0; c->interp_size = interp_size;                              // VV/dataset.cpp:86, VV/3DLIC.cpp:705
+}
+
+int vv_time_cursor_next(const VVTimeCursor *c)
+{
+    return (c->current == c->time_end) ? c->time_begin : c->current + 1;            // DatFile::NextTimeStep, VV/reader.cpp:333-336
+}
+
+int vv_time_cursor_tick(VVTimeCursor *c, int *advanced)
+{
+    const int used = c->interp_index;          // createTextureIterp packs with interpIndex / InterpSize ...
+    ++c->interp_index;                         // ... and increments (VV/dataset.cpp:633)
+    int adv = 0;
+    if (c->interp_index >= c->interp_size) {   // checkInterpolateStage, VV/dataset.cpp:202-210
+        c->current = vv_time_cursor_next(c);   // getNextTimeStep() moves on; newData = NextTimeStep() of the new position
+        c->interp_index = 0;
+        adv = 1;
+    }
+    if (advanced) *advanced = adv;
+    return used;
+}
+
 int vv_keyboard(VVRenderer *r, VVAppState *s, int key, int special)
 {
     if (!r || !s) { fail(VV_ERR_INVALID, "vv_keyboard: null argument"); return -1; }

@@ -63,6 +63,9 @@ struct VVRenderer {
     DevBuf<uint8_t> raw0, raw1;        // raw time steps (FLOAT3 or UCHAR3)
     bool have_next = false, field_u8 = false, have_field = false;
     int interp_index = 0, interp_size = 10;   // VV/3DLIC.cpp:705 setInterpolateSize(10)
+    bool have_dat = false;                    // field loaded by vv_load_dat: vv_idle can step through its time steps
+    VVDatInfo dat;
+    VVTimeCursor cursor;
     DevBuf<float4> pack_tmp;
     DevBuf<unsigned int> maxbits;
     DevBuf<uint4> field_pair;
@@ -894,6 +897,7 @@ int vv_set_vector_field(VVRenderer *r, const void *data, const void *next, int d
     update_light(r);
     r->field_u8 = (dtype == VV_UCHAR);
     r->have_field = true;
+    r->have_dat = false;                       // (vv_load_dat sets it again)
     r->interp_index = 0;
     r->field_dirty = true;
     r->frame_valid = false;
@@ -1632,7 +1636,52 @@ int vv_load_dat(VVRenderer *r, const char *dat_path)
         if (rc) return rc;
         next = b.data();
     }
-    return vv_set_vector_field(r, a.data(), next, info.data_type, info.resolution, info.slice_thickness);
+    rc = vv_set_vector_field(r, a.data(), next, info.data_type, info.resolution, info.slice_thickness);
+    if (rc) return rc;
+    r->dat = info;
+    r->have_dat = true;
+    vv_time_cursor_init(&r->cursor, info.time_begin, info.time_end, r->interp_size);
+    // init() has run createTextureIterp + checkInterpolateStage once by the time the first idle tick comes (VV/3DLIC.cpp:706-707):
+    // the texture just packed used fraction 0, the first vv_idle uses 1 / InterpSize
+    vv_time_cursor_tick(&r->cursor, nullptr);
+    return VV_OK;
+}
+
+// One idle() tick of the reference's animation (VV/3DLIC.cpp:129-172): createTextureIterp + checkInterpolateStage
+int vv_idle(VVRenderer *r)
+{
+    if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    if (!r->have_dat || !r->have_field) return fail(VV_ERR_STATE, "vv_idle: the vector field was not loaded with vv_load_dat");
+    CU(cudaSetDevice(r->device));
+    r->cursor.interp_size = r->interp_size;
+    int advanced = 0;
+    r->interp_index = vv_time_cursor_tick(&r->cursor, &advanced);
+    r->field_dirty = true;
+    r->frame_valid = false;
+    r->licvol_valid = false;
+    int rc = pack_field(r);                    // this tick's texture: data + interpIndex / InterpSize (newData - data)
+    if (rc) return rc;
+    if (advanced && r->have_next) {
+        // data <- time step `current`, newData <- the one after it; the texture changes with the next tick
+        const size_t bytes = dat_bytes(&r->dat);
+        std::vector<uint8_t> a(bytes), b(bytes);
+        rc = read_raw(&r->dat, r->cursor.current, a.data(), bytes);
+        if (rc) return rc;
+        rc = read_raw(&r->dat, vv_time_cursor_next(&r->cursor), b.data(), bytes);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(r->raw0.p, a.data(), bytes, cudaMemcpyHostToDevice, r->stream));
+        CU(cudaMemcpyAsync(r->raw1.p, b.data(), bytes, cudaMemcpyHostToDevice, r->stream));
+        CU(cudaStreamSynchronize(r->stream));
+    }
+    return VV_OK;
+}
+
+int vv_get_time_cursor(VVRenderer *r, VVTimeCursor *out)
+{
+    if (!r || !out) return fail(VV_ERR_INVALID, "vv_get_time_cursor: null argument");
+    if (!r->have_dat) return fail(VV_ERR_STATE, "the vector field was not loaded with vv_load_dat");
+    *out = r->cursor;
+    return VV_OK;
 }
 
 int vv_load_scalar_dat(VVRenderer *r, const char *dat_path)
