@@ -227,6 +227,10 @@ VV_API int vv_read_rgba8(VVRenderer *r, uint8_t *out, size_t out_bytes);
 VV_API int vv_read_rgba32f(VVRenderer *r, float *out, size_t out_bytes);
 /* displayed frame: background_fragment.glsl:9-16 composited over white */
 VV_API int vv_read_display_rgba8(VVRenderer *r, uint8_t *out, size_t out_bytes);
+/* the same pass over a window that is larger than the stored frame (low-res preset: the frame is half the window): the shader
+ * reads texture2DRect(imageFBOSampler, gl_FragCoord.xy * viewport.xy), viewport = (frame / window) per axis (VV/renderer.cpp:
+ * 1436-1441), i.e. a NEAREST, edge-clamped up-scaling; out = window_width * window_height RGBA8, rows bottom-up like the frame */
+VV_API int vv_read_display_window_rgba8(VVRenderer *r, uint8_t *out, size_t out_bytes, int window_width, int window_height);
 /* LIC volume contents (fp32 scalar [d][h][w]) */
 VV_API int vv_read_lic_volume(VVRenderer *r, float *out, size_t out_bytes, int dims_out[3]);
 /* texture read-back (glGetTexImage equivalents, used by the parity tests):

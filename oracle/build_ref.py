@@ -108,6 +108,17 @@ def generate():
         with open(path, "w") as f:
             f.write("\n".join(text) + "\n")
         files.append(path)
+    # the display pass: background_fragment.glsl is a program of its own (VV/renderer.cpp:811, 851-857)
+    body = rewrite(open(os.path.join(REF, "shader", "background_fragment.glsl")).read())
+    text = ["// GENERATED by oracle/build_ref.py from VV/shader/background_fragment.glsl -- do not commit",
+            '#include "glsl_shim.h"', '#include "ref_api.h"', "namespace glsl { namespace background {", body,
+            '#include "ref_bg_driver.inc"', "} }",
+            'extern "C" void vvref_run_background(const float *img, int rw, int rh, int ww, int wh, float *out)',
+            "{ glsl::background::run_bg(img, rw, rh, ww, wh, out); }"]
+    path = os.path.join(GEN, "prog_background.cpp")
+    with open(path, "w") as f:
+        f.write("\n".join(text) + "\n")
+    files.append(path)
     return files
 
 

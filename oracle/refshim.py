@@ -249,3 +249,16 @@ class RefScene:
         self._set_scale(raycast=False)
         out, cnt = self._run("volraycast", self._rays((0, 0, s.width, s.height)))
         return out.reshape(s.height, s.width, 4), cnt.reshape(s.height, s.width), int(cnt.sum())
+
+
+def background(img, win_w=None, win_h=None):
+    """background_fragment.glsl (the display pass of Renderer::renderBackground, VV/renderer.cpp:1407-1476) over a window of
+    win_w x win_h pixels showing the stored frame img [rh][rw][4]; window = frame unless the low-res preset halves the frame"""
+    img = np.ascontiguousarray(img, np.float32)
+    rh, rw = img.shape[:2]
+    ww, wh = win_w or rw, win_h or rh
+    out = np.zeros((wh, ww, 4), np.float32)
+    L = lib()
+    L.vvref_run_background.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.vvref_run_background(img.ctypes.data, rw, rh, ww, wh, out.ctypes.data)
+    return out

@@ -956,6 +956,18 @@ void vvo_background(const float *rgba, int n_pixels, float *out)
     }
 }
 
+void vvo_display_window(const float *rgba, int rw, int rh, int ww, int wh, float *out)
+{
+    const float vx = static_cast<float>(rw) / ww, vy = static_cast<float>(rh) / wh;
+    for (int y = 0; y < wh; ++y)
+        for (int x = 0; x < ww; ++x) {
+            int sx = (int)std::floor(((float)x + 0.5f) * vx), sy = (int)std::floor(((float)y + 0.5f) * vy);
+            sx = sx < 0 ? 0 : (sx > rw - 1 ? rw - 1 : sx);
+            sy = sy < 0 ? 0 : (sy > rh - 1 ? rh - 1 : sy);
+            vvo_background(rgba + 4 * ((size_t)sy * rw + sx), 1, out + 4 * ((size_t)y * ww + x));
+        }
+}
+
 /* GL float -> UNORM8 conversion of the stored frame (renderer.cpp:216-226; GL 2.1 spec 2.14.9) */
 void vvo_quantize_rgba8(const float *rgba, int n, uint8_t *out)
 {

@@ -103,6 +103,10 @@ int vvo_slice_fragments(const VVOScene *s, int x, int y, float *out_xyzv, int ca
 void vvo_compute_lic(const VVOScene *s, const float pos[3], float out[4]);
 /* background_fragment.glsl:7-20 and the RGBA8 store (renderer.cpp:216-226) */
 void vvo_background(const float *rgba, int n_pixels, float *out);
+/* the same pass over a WINDOW of ww x wh pixels showing a stored frame of rw x rh (low-res preset: rw = ww/2, rh = wh/2):
+ * texture2DRect(imageFBOSampler, gl_FragCoord.xy * viewport.xy), viewport = (rw / ww, rh / wh) as floats (renderer.cpp:1438-1441),
+ * rectangle textures are NEAREST, coordinates clamp to the edge texel */
+void vvo_display_window(const float *rgba, int rw, int rh, int ww, int wh, float *out);
 void vvo_quantize_rgba8(const float *rgba, int n_values, uint8_t *out);
 
 /* ---- samplers, exposed for unit tests -------------------- */

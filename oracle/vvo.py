@@ -64,6 +64,7 @@ def lib():
         L.vvo_slicing_setup.argtypes = [S, P]
         L.vvo_slice_fragments.argtypes = [S, I, I, P, I]; L.vvo_slice_fragments.restype = I
         L.vvo_background.argtypes = [P, I, P]; L.vvo_quantize_rgba8.argtypes = [P, I, P]
+        L.vvo_display_window.argtypes = [P, I, I, I, I, P]
         for n in ("vvo_sample_vec", "vvo_sample_noise", "vvo_sample_scalar"):
             getattr(L, n).argtypes = [S, P, P]
         L.vvo_sample_kernel.argtypes = [S, F]; L.vvo_sample_kernel.restype = F
@@ -297,6 +298,14 @@ def quantize_rgba8(rgba):
     rgba = np.ascontiguousarray(rgba, dtype=np.float32)
     out = np.empty(rgba.shape, dtype=np.uint8)
     lib().vvo_quantize_rgba8(_p(rgba), rgba.size, _p(out))
+    return out
+
+
+def display_window(rgba, win_w, win_h):
+    """the display pass over a win_w x win_h window showing the stored frame rgba [rh][rw][4] (low-res preset: NEAREST up-scaling)"""
+    rgba = np.ascontiguousarray(rgba, dtype=np.float32)
+    out = np.empty((win_h, win_w, 4), dtype=np.float32)
+    lib().vvo_display_window(_p(rgba), rgba.shape[1], rgba.shape[0], win_w, win_h, _p(out))
     return out
 
 

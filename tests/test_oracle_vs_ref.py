@@ -128,3 +128,18 @@ def test_mc_offset_builds_bit_exact(oracle):
         assert ta == tb and ta > 0 and np.array_equal(ca, cb)
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "max abs diff %g" % np.abs(a - b).max()
         assert not np.array_equal(a, base[0])                      # the offsets do move the samples
+
+
+def test_display_pass_bit_exact(oracle):
+    """background_fragment.glsl (VV/shader, compiled as C++) against the oracle's display pass: frame-sized window, and the low-res
+    preset's window of twice (or 2n+1 times) the frame, where texture2DRect(.., gl_FragCoord.xy * viewport.xy) up-scales NEAREST"""
+    rng = np.random.RandomState(3)
+    for (rw, rh), (ww, wh) in (((13, 9), (13, 9)), ((32, 24), (64, 48)), ((25, 20), (51, 41)), ((1, 1), (3, 2)), ((40, 30), (81, 61))):
+        img = rng.rand(rh, rw, 4).astype(np.float32)
+        img[..., :3] *= img[..., 3:4]                       # premultiplied, as the ray-cast leaves it
+        img[0, 0] = (0, 0, 0, 0); img[-1, -1] = (1, 1, 1, 1)
+        ref = refshim.background(img, ww, wh)
+        got = oracle.display_window(img, ww, wh)
+        assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+        if (rw, rh) == (ww, wh):
+            assert np.array_equal(oracle.background(img).view(np.uint32), ref.view(np.uint32))

@@ -895,6 +895,12 @@ def test_lowres_window_aspect(vv, oracle):
     _, img, _, cnt, tot = render_cuda(vv, s)
     assert tot == ref_tot and tot > 0 and np.array_equal(cnt, ref_cnt)
     assert_image_parity(oracle, img, ref, "lowres window aspect")
+    # the displayed window: background pass with the NEAREST up-scaling of the half-size frame (VV/renderer.cpp:1436-1441)
+    r, img, _, _, _ = render_cuda(vv, s)
+    want = oracle.quantize_rgba8(oracle.display_window(img, 51, 41))
+    got = r.readDisplayWindowRGBA8(51, 41)
+    assert got.shape == (41, 51, 4) and np.array_equal(r.readDisplayWindowRGBA8(25, 20), r.readDisplayRGBA8())
+    assert np.array_equal(got, want)
     s.window = None
     _, img2, _, _, _ = render_cuda(vv, s)
     assert not np.array_equal(img, img2)

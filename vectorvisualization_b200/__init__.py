@@ -134,6 +134,7 @@ def load_library():
         "vv_last_snapshot_path": ([P], CP),
         "vv_render": ([P, I], I), "vv_read_rgba8": ([P, P, ctypes.c_size_t], I), "vv_read_rgba32f": ([P, P, ctypes.c_size_t], I),
         "vv_read_display_rgba8": ([P, P, ctypes.c_size_t], I),
+        "vv_read_display_window_rgba8": ([P, P, ctypes.c_size_t, I, I], I),
         "vv_read_lic_volume": ([P, P, ctypes.c_size_t, ctypes.POINTER(I)], I),
         "vv_read_field_texture": ([P, P, ctypes.c_size_t], I),
         "vv_read_noise_texture": ([P, P, ctypes.c_size_t, ctypes.POINTER(I)], I),
@@ -444,6 +445,12 @@ class Renderer:
     def readDisplayRGBA8(self):
         out = np.empty((self.height, self.width, 4), dtype=np.uint8)
         _chk(self._lib.vv_read_display_rgba8(self._h, _ptr(out), out.nbytes))
+        return out
+
+    def readDisplayWindowRGBA8(self, win_w, win_h):
+        """the displayed frame over a win_w x win_h window (low-res preset: NEAREST up-scaling of the half-size frame)"""
+        out = np.empty((win_h, win_w, 4), dtype=np.uint8)
+        _chk(self._lib.vv_read_display_window_rgba8(self._h, _ptr(out), out.nbytes, win_w, win_h))
         return out
 
     def readLICVolume(self):

@@ -1304,6 +1304,31 @@ int vv_read_display_rgba8(VVRenderer *r, uint8_t *out, size_t out_bytes)
     return VV_OK;
 }
 
+// The display pass over a WINDOW larger than the stored frame (low-res preset): background_fragment.glsl reads
+// texture2DRect(imageFBOSampler, gl_FragCoord.xy * viewport.xy) with viewport = (renderWidth / winWidth, renderHeight / winHeight)
+// as floats (VV/renderer.cpp:1438-1441) -- NEAREST, edge-clamped; the blend over white is per texel, so the displayed frame is
+// up-scaled as it is read back.
+int vv_read_display_window_rgba8(VVRenderer *r, uint8_t *out, size_t out_bytes, int window_width, int window_height)
+{
+    if (!r || !out) return fail(VV_ERR_INVALID, "vv_read_display_window_rgba8: null argument");
+    if (window_width <= 0 || window_height <= 0) return fail(VV_ERR_INVALID, "vv_read_display_window_rgba8: bad window size");
+    if (out_bytes < (size_t)window_width * window_height * 4) return fail(VV_ERR_INVALID, "output buffer too small");
+    std::vector<uint8_t> img((size_t)r->width * r->height * 4);
+    int rc = vv_read_display_rgba8(r, img.data(), img.size());
+    if (rc) return rc;
+    const float vx = static_cast<float>(r->width) / window_width, vy = static_cast<float>(r->height) / window_height;
+    for (int y = 0; y < window_height; ++y) {
+        int sy = (int)std::floor(((float)y + 0.5f) * vy);
+        sy = sy < 0 ? 0 : (sy > r->height - 1 ? r->height - 1 : sy);
+        for (int x = 0; x < window_width; ++x) {
+            int sx = (int)std::floor(((float)x + 0.5f) * vx);
+            sx = sx < 0 ? 0 : (sx > r->width - 1 ? r->width - 1 : sx);
+            std::memcpy(out + 4 * ((size_t)y * window_width + x), &img[4 * ((size_t)sy * r->width + sx)], 4);
+        }
+    }
+    return VV_OK;
+}
+
 int vv_read_lic_volume(VVRenderer *r, float *out, size_t out_bytes, int dims_out[3])
 {
     if (!r || !out) return fail(VV_ERR_INVALID, "vv_read_lic_volume: null argument");
