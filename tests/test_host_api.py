@@ -138,3 +138,40 @@ def test_synthetic_generators_are_deterministic():
         assert k.shape == (256,) and k.max() >= 254 and np.array_equal(k, k[::-1])
     tf = F.tf_preset("tf-length")
     assert tf.shape == (256, 5) and tf[:, 3].max() <= 26          # semi-transparent: no early ray termination
+
+
+def test_hot_kernel_resources_and_instruction_mix(vv):
+    """static guard on the shipped lic_sample_kernel<x-pair layout, gradient build> (what DESIGN.md section 5 measures): 64
+    registers (4 CTAs x 256 threads per SM), no spill traffic inside the walk loop, and the sm_100a instructions the design
+    relies on -- FHADD (f32 = f16 + f32) for the fp16 texels, packed FFMA2 / FADD2 lerps, 128-bit loads"""
+    name = "_ZN6vvb20017lic_sample_kernelILi1ELi1ELb0ELb0EEEvNS_9DevParamsE"
+    res = subprocess.run(["cuobjdump", "-res-usage", vv.LIB_PATH], capture_output=True, text=True).stdout
+    lines = res.splitlines()
+    i = next(k for k, l in enumerate(lines) if name in l)
+    usage = lines[i + 1]
+    assert "REG:64" in usage.replace(" ", ""), usage
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", name, vv.LIB_PATH], capture_output=True, text=True).stdout
+    ins = []
+    for l in sass.splitlines():
+        l = l.strip()
+        if l.startswith("/*") and ";" in l:
+            addr, rest = l[2:].split("*/", 1)
+            ins.append((int(addr, 16), rest.split(";")[0].strip()))
+    assert len(ins) > 2000
+    # the walk loop = the largest backward branch that is not the persistent work loop (second largest overall)
+    loops = []
+    for a, t in ins:
+        if "BRA" in t and "0x" in t:
+            tgt = int(t.split("0x")[-1].split()[0].rstrip(","), 16)
+            if tgt < a:
+                loops.append((a - tgt, tgt, a))
+    loops.sort(reverse=True)
+    _, lo, hi = loops[1]
+    body = [t for a, t in ins if lo <= a <= hi]
+    ops = [t.split()[1] if t.startswith("@") else t.split()[0] for t in body]
+    count = lambda p: sum(1 for o in ops if o.split(".")[0] == p)
+    assert 500 < len(body) < 900
+    assert count("FHADD") == 160                     # one per fp16 texel: 4 field fetches x 24 + 2 noise fetches x 32
+    assert count("FFMA2") >= 90 and count("FADD2") >= 60
+    assert count("STL") == 0 and count("LDL") == 0   # no spills in the loop
+    assert sum(1 for o in ops if o.startswith("LDG.E.128")) >= 24
