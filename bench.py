@@ -326,6 +326,20 @@ def run_cuda(args):
             if entry.get("ncu"):
                 # the kernel is not byte-bound: what it IS bound by, from the committed ncu capture of this kernel
                 roofline["ncu"] = entry["ncu"]
+                loop = entry["ncu"].get("sass_walk_loop")
+                if loop and local_samples > 0:
+                    # instruction roofline of the walk loop: every SM sub-partition issues at most one warp instruction per
+                    # clock, so a frame cannot take less than (warp double steps) x (instructions per double step) cycles
+                    steps = max(lp.stepsForward, lp.stepsBackward)
+                    sms, mhz = 148, 1965.0
+                    try:
+                        mhz = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("sm_max_mhz", mhz))
+                        sms = torch.cuda.get_device_properties(0).multi_processor_count
+                    except Exception:
+                        pass
+                    ideal_ms = (local_samples / 32.0) * steps * loop["executed_instructions_per_double_step"] / (sms * 4) / (mhz * 1e3)
+                    roofline["issue_roofline"] = {"ideal_kernel_ms": ideal_ms, "frac": ideal_ms / k_ms, "sm_mhz": mhz,
+                                                  "what": "walk-loop warp instructions / (4 issue slots per SM per clock)"}
         except Exception:
             pass
 
