@@ -143,3 +143,69 @@ def test_display_pass_bit_exact(oracle):
         assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
         if (rw, rh) == (ww, wh):
             assert np.array_equal(oracle.background(img).view(np.uint32), ref.view(np.uint32))
+
+
+def _random_scene(seed):
+    """a random small scene: everything the parameter block and the textures can vary in"""
+    import vectorvisualization_b200 as vv
+    from vectorvisualization_b200 import configs, fields as F
+    rng = np.random.RandomState(seed)
+    nx, ny, nz = (int(v) for v in rng.randint(6, 15, size=3))
+    field = rng.standard_normal((nz, ny, nx, 3)).astype(np.float32)
+    field[rng.rand(nz, ny, nx) < 0.05] = 0.0                                     # zero vectors (rgb = 0.5, a = 0)
+    nn = int(rng.randint(5, 12))
+    noise = (rng.rand(nn, nn, nn) < rng.choice([1 / 6, 0.5])).astype(np.uint8) * 255
+    if rng.rand() < 0.3:
+        noise = rng.randint(0, 256, size=(nn, nn, nn)).astype(np.uint8)
+    sn = int(rng.randint(3, 9))
+    scalar = rng.randint(20, 90, size=(sn, sn, sn)).astype(np.uint8)             # straddles the (0.1, 0.3) band
+    kw = int(rng.choice([7, 16, 100, 256]))
+    filt = None if rng.rand() < 0.2 else rng.randint(0, 256, size=kw).astype(np.uint8)
+    if filt is not None:
+        filt[rng.randint(0, kw)] = 255                                           # never an all-zero kernel
+    tf = rng.randint(0, 256, size=(256, 5)).astype(np.uint8)
+    tf[:, 3] = (tf[:, 3] * rng.choice([0.1, 0.4, 1.0])).astype(np.uint8)         # semi-transparent ... opaque (early termination)
+    size = int(rng.randint(14, 26))
+    illum = rng.choice(["", "ILLUM_GRADIENT", "SPEED_OF_FLOW", "ILLUM_MALLO", "ILLUM_ZOECKLER"], p=[0.3, 0.3, 0.2, 0.1, 0.1])
+    axis = rng.standard_normal(3)
+    cam = dict(quat=F.quat_from_axis_angle(tuple(axis), float(rng.uniform(0, 360))), pos=tuple(float(v) for v in rng.uniform(-0.2, 0.2, 3)),
+               dist=float(rng.uniform(1.2, 4.0)), fovy=35.0)
+    s = configs.Scene("random%d" % seed, field, noise, scalar, filt, tf, size, int(size * rng.choice([1.0, 0.75])),
+                      with_gradients=bool(illum == "ILLUM_GRADIENT" or rng.rand() < 0.5), defines=("#define " + illum) if illum else "",
+                      params=dict(stepSizeVol=float(rng.choice([1 / 16, 1 / 32, 1 / 64])), stepSizeLIC=float(rng.choice([0.005, 0.01, 0.04])),
+                                  stepsForward=int(rng.randint(1, 12)), stepsBackward=int(rng.randint(1, 12)),
+                                  freqScale=float(rng.choice([0.5, 1.0, 2.2, 4.0])), gradientScale=float(rng.uniform(1, 30)),
+                                  illumScale=float(rng.uniform(0.5, 1.5))),
+                      camera=cam, light=dict(quat=F.quat_from_axis_angle(tuple(rng.standard_normal(3)), float(rng.uniform(0, 360))), dist=float(rng.uniform(0.5, 2))))
+    s.slice_dist = tuple(float(v) for v in rng.choice([1.0, 1.5, 2.0], size=3))
+    s.lowres = int(rng.rand() < 0.15)
+    if illum in ("", "ILLUM_GRADIENT", "SPEED_OF_FLOW"):
+        s.tf_mode = int(rng.choice([vv.TF_B, vv.TF_A, vv.TF_R, vv.TF_LENGTH, vv.TF_SCALAR]))
+    else:
+        s.tf_mode = int(rng.choice([vv.TF_B, vv.TF_A, vv.TF_R, vv.TF_LENGTH, vv.TF_SCALAR]))
+    if illum == "" and s.tf_mode in (vv.TF_B, vv.TF_A) and rng.rand() < 0.3:
+        s.gate_mode = vv.GATE_TF_ALPHA                                           # built for raycast_none (.b / .a)
+    if rng.rand() < 0.3:
+        n = rng.standard_normal(3)
+        s.clip_planes = ((float(n[0]), float(n[1]), float(n[2]), float(rng.uniform(-0.1, 0.3))),)   # any length: the steady state applies
+    if rng.rand() < 0.2:
+        s.camera = dict(cam, dist=float(rng.uniform(0.55, 0.9)))                  # near the box: the near plane clips
+    return s
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_random_scenes_bit_exact(oracle, block):
+    """seeded random scenes -- random field (incl. zero vectors, anisotropic spacing, non-cubic), noise, scalar volume, filter
+    kernel, transfer function, LIC parameters, camera, light, build, TF index, gate, clip plane, near-plane positions: the oracle
+    against the reference's shader code, frames and ray-sample counts bit for bit"""
+    tables = oracle.illum_tables(40.0)
+    hits = 0
+    for seed in range(100 + 8 * block, 108 + 8 * block):
+        s = _random_scene(seed)
+        need = "MALLO" in s.defines or "ZOECKLER" in s.defines
+        a, ca, ta = oracle.OracleScene(s, illum_tables=tables if need else None).raycast()
+        b, cb, tb = refshim.RefScene(s, illum_tables=tables if need else None).raycast()
+        assert ta == tb and np.array_equal(ca, cb), seed
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "seed %d: max abs diff %g" % (seed, np.abs(a - b).max())
+        hits += int(ta > 0)
+    assert hits >= 5
