@@ -536,3 +536,44 @@ def test_animation_cursor_matches_the_application(vv, tmp_path):
     assert ours == ref
     assert [t for t, (_, _, adv) in enumerate(ref) if adv] == [8, 18, 28, 38]
     assert ref[0] == (0, 1, 0) and ref[9] == (1, 0, 0) and ref[29] == (0, 0, 0)        # first tick: 1/10; wraps 2 -> 0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_host_preprocessing(oracle, tmp_path, seed):
+    """seeded random inputs through the reference's host code (compiled unmodified) and the oracle: vector packing with time
+    interpolation on non-cubic, anisotropically spaced fields with huge / tiny / zero vectors; noise gradients (Sobel, 5^3
+    smoothing, quantisation) on non-cubic random noise; filter kernels of random width -- bit for bit"""
+    from vectorvisualization_b200 import fields as F
+    rng = np.random.RandomState(40 + seed)
+    nx, ny, nz = (int(v) for v in rng.randint(3, 14, size=3))
+    scale = np.float32(10.0 ** rng.uniform(-6, 6))
+    f0 = (rng.standard_normal((nz, ny, nx, 3)) * scale).astype(np.float32)
+    f1 = (rng.standard_normal((nz, ny, nx, 3)) * scale).astype(np.float32)
+    f0[rng.rand(nz, ny, nx) < 0.1] = 0.0
+    f1[rng.rand(nz, ny, nx) < 0.1] = 0.0
+    f0[0, 0, 0] = (1e-6 * scale, 0.0, 0.0)                                       # around the |v| < 1e-5 zero-vector test
+    sd = tuple(float(v) for v in rng.choice([0.5, 1.0, 1.5, 3.0], size=3))
+    dat = F.write_dat(str(tmp_path / "vec.dat"), None, time_steps=[f0, f1], slice_thickness=sd)
+    idx = int(rng.randint(0, 10))
+    ref, geom, _, _ = refhost.vector_texture(dat, (nz, ny, nx), interp=(idx, 10))
+    mine = oracle.pack_vector_field(f0, f1, (idx, 10), fp16=False)
+    assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32))
+    ext, sc, sci, cen = (np.zeros(3, np.float32) for _ in range(4))
+    oracle.lib().vvo_volume_geometry((ctypes.c_int * 3)(nx, ny, nz), (ctypes.c_float * 3)(*sd), oracle._p(ext), oracle._p(sc),
+                                     oracle._p(sci), oracle._p(cen))
+    assert np.array_equal(ext, geom["extent"]) and np.array_equal(cen, geom["center"])
+    assert np.array_equal(sc, geom["scale"][:3]) and np.array_equal(sci, geom["scale_inv"][:3])
+    # noise gradients
+    shape = tuple(int(v) for v in rng.randint(5, 13, size=3))
+    noise = rng.randint(0, 256, size=shape).astype(np.uint8) if seed % 2 else (rng.rand(*shape) < 0.2).astype(np.uint8) * 255
+    path = F.write_noise(str(tmp_path / "noise"), noise)
+    ref, _, _ = refhost.noise_texture(path, shape, True)
+    assert np.array_equal(oracle.pack_noise_rgba(noise, oracle.noise_gradients(noise)), ref)
+    # filter kernel of random width and content
+    width = int(rng.randint(2, 300))
+    row = rng.randint(0, 256, size=width).astype(np.uint8)
+    row[rng.randint(0, width)] = 200
+    png = F.write_png(str(tmp_path / "k.png"), row[None, :])
+    data, inv, _ = refhost.filter_texture(png)
+    mine, minv = oracle.filter_from_row(row)
+    assert np.array_equal(data, mine) and inv == minv
