@@ -209,3 +209,35 @@ def test_random_scenes_bit_exact(oracle, block):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "seed %d: max abs diff %g" % (seed, np.abs(a - b).max())
         hits += int(ta > 0)
     assert hits >= 5
+
+
+def test_random_scenes_slicing_and_lic_volume_bit_exact(oracle):
+    """the same random scenes through the slicing program (TF index .a, gate tfData.a > 0.05 as the shader hard-codes them) and
+    through the LIC-volume program + the ray-cast of the LIC volume"""
+    import vectorvisualization_b200 as vv
+    tables = oracle.illum_tables(40.0)
+    done = 0
+    for seed in range(200, 216):
+        s = _random_scene(seed)
+        if "SPEED_OF_FLOW" in s.defines:
+            s.defines = ""                                                        # no slicing build with that define in the shim
+        need = "MALLO" in s.defines or "ZOECKLER" in s.defines
+        s.technique, s.tf_mode, s.gate_mode = vv.VOLIC_SLICING, vv.TF_A, vv.GATE_TF_ALPHA
+        s.with_gradients = True
+        a, ca, ta = oracle.OracleScene(s, illum_tables=tables if need else None).slicing()
+        b, cb, tb = refshim.RefScene(s, illum_tables=tables if need else None).slicing()
+        assert ta == tb and np.array_equal(ca, cb), seed
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "seed %d: max abs diff %g" % (seed, np.abs(a - b).max())
+        done += int(ta > 0)
+        if need:
+            continue
+        s.technique = vv.VOLIC_RAYCAST
+        s.licvol_fp16 = 0
+        o, r = oracle.OracleScene(s), refshim.RefScene(s)
+        dims = (5 + seed % 4, 6, 4 + seed % 3)
+        lo, lr = o.lic_volume(dims), r.lic_volume(dims)
+        assert np.array_equal(lo.view(np.uint32), lr.view(np.uint32)), seed
+        a, ca, ta = o.raycast_licvolume(lo)
+        b, cb, tb = r.raycast_licvolume(lo)
+        assert ta == tb and np.array_equal(ca, cb) and np.array_equal(a.view(np.uint32), b.view(np.uint32)), seed
+    assert done >= 8
