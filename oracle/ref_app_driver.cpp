@@ -10,6 +10,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <string>
 
 #include "GL/glew.h"
@@ -67,8 +68,16 @@ extern "C" void glShaderSourceARB(GLhandleARB, GLsizei n, const GLcharARB **src,
 }
 
 static bool g_wired = false;
+static int g_modifiers = 0;
+extern "C" int glutGetModifiers(void) { return g_modifiers; }
+void mouseInteract(int button, int state, int x, int y);
+void mouseMotionInteract(int x, int y);
 
 extern "C" {
+
+static int wire_app(const char *dat);
+static int keyboard_impl(const char *ref_dir, const unsigned char *keys, const int *special, int n, float *out,
+                         char *defines_out, int defines_cap, char *hud_out, int hud_cap);
 
 /* keys[i] is fed to keyboard() (special[i] == 0) or keyboardSpecial() (special[i] != 0; 1..5 = GLUT_KEY_F1..F5) after the
  * application state has been reset to its start-up values.  out[0..7] = LICParams (stepSizeVol, gradientScale, illumScale,
@@ -78,6 +87,12 @@ extern "C" {
  * string handed to glShaderSourceARB (empty: none since reset) and the HUD status line. */
 int vvref_keyboard(const char *dat, const char *ref_dir, const unsigned char *keys, const int *special, int n, float *out,
                    char *defines_out, int defines_cap, char *hud_out, int hud_cap)
+{
+    if (wire_app(dat) != 0) return -10;
+    return keyboard_impl(ref_dir, keys, special, n, out, defines_out, defines_cap, hud_out, hud_cap);
+}
+
+static int wire_app(const char *dat)
 {
     static Texture dummy[10];
     if (!g_wired) {
@@ -103,6 +118,12 @@ int vvref_keyboard(const char *dat, const char *ref_dir, const unsigned char *ke
         resize(64, 48);
         g_wired = true;
     }
+    return 0;
+}
+
+static int keyboard_impl(const char *ref_dir, const unsigned char *keys, const int *special, int n, float *out,
+                         char *defines_out, int defines_cap, char *hud_out, int hud_cap)
+{
     /* start-up state: LICParams ctor (VV/types.h:91-109), VV/3DLIC.h:29-55 */
     licParams = LICParams();
     renderTechnique = VOLIC_VOLUME;
@@ -163,6 +184,49 @@ int vvref_animation_ticks(const char *dat, int n, int *out, int tex_tick, float 
         v.checkInterpolateStage();
         out[3 * i] = step; out[3 * i + 1] = idx; out[3 * i + 2] = (v.getCurTimeStep() != step) ? 1 : 0;
     }
+    return 0;
+}
+
+/* Mouse interaction: mouseInteract / mouseMotionInteract (VV/3DLIC.cpp:490-600) fed with events[i] = (type, button, x, y,
+ * modifiers): type 0 = button press (GLUT_DOWN), type 1 = motion, type 2 = select clip plane `button` (-1: none; what keys
+ * '1'-'4' do to currentClipPlane), on freshly constructed cam / light / clipPlanes set up as init() does (VV/3DLIC.cpp:681,
+ * 763-781) in a width x height window.  out: per object (camera, light, clip plane 0..2) 13 floats: _q_internal[4], _q[4],
+ * _dist, _pos[3] (camera only, else 0), locked; then the three plane equations as 12 doubles in out_normals. */
+int vvref_mouse(const char *dat, int width, int height, const int *events, int n, float *out, double *out_normals)
+{
+    if (wire_app(dat) != 0) return -10;
+    cam.~Camera(); new (&cam) Camera();
+    light.~Transform(); new (&light) Transform();
+    for (int i = 0; i < 3; ++i) { clipPlanes[i].~ClipPlane(); new (&clipPlanes[i]) ClipPlane(); }
+    cam.setPosition(Vector3_new(0.0f, 0.0f, 0.0f));         /* a global there: zero-initialised */
+    light.setDistance(1.0f);
+    clipPlanes[0].rotate(Quaternion_fromAngleAxis(static_cast<float>(M_PI / 2.0), Vector3_new(0.0f, 1.0f, 0.0f)));
+    clipPlanes[1].rotate(Quaternion_fromAngleAxis(static_cast<float>(M_PI / 2.0), Vector3_new(-1.0f, 0.0f, 0.0f)));
+    currentClipPlane = NULL;
+    for (int i = 0; i < 3; ++i) clipPlanes[i].setPlaneId(GL_CLIP_PLANE0 + i);
+    resize(width, height);
+    for (int i = 0; i < n; ++i) {
+        const int *e = events + 5 * i;
+        g_modifiers = e[4];
+        if (e[0] == 0) mouseInteract(e[1], GLUT_DOWN, e[2], e[3]);
+        else if (e[0] == 1) mouseMotionInteract(e[2], e[3]);
+        else currentClipPlane = (e[1] >= 0 && e[1] < 3) ? &clipPlanes[e[1]] : NULL;
+    }
+    g_modifiers = 0;
+    Transform *obj[5] = {&cam, &light, &clipPlanes[0], &clipPlanes[1], &clipPlanes[2]};
+    for (int k = 0; k < 5; ++k) {
+        float *o = out + 13 * k;
+        Transform *t = obj[k];
+        o[0] = t->_q_internal.x; o[1] = t->_q_internal.y; o[2] = t->_q_internal.z; o[3] = t->_q_internal.w;
+        o[4] = t->_q.x; o[5] = t->_q.y; o[6] = t->_q.z; o[7] = t->_q.w;
+        o[8] = t->_dist;
+        o[9] = o[10] = o[11] = 0.0f;
+        if (k == 0) { Vector3 p = cam.getPosition(); o[9] = p.x; o[10] = p.y; o[11] = p.z; }
+        o[12] = t->_locked ? 1.0f : 0.0f;
+    }
+    for (int i = 0; i < 3; ++i) for (int k = 0; k < 4; ++k) out_normals[4 * i + k] = clipPlanes[i].getNormal()[k];
+    currentClipPlane = NULL;
+    resize(64, 48);
     return 0;
 }
 

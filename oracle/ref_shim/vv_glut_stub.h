@@ -15,7 +15,7 @@ extern "C" {
 #endif
 static inline void glutSwapBuffers(void) {}
 static inline void glutIdleFunc(void (*)(void)) {}
-static inline int glutGetModifiers(void) { return 0; }
+int glutGetModifiers(void);                              /* set per event by oracle/ref_app_driver.cpp */
 static inline int glutCreateMenu(void (*)(int)) { return 1; }
 static inline void glutAddMenuEntry(const char *, int) {}
 static inline void glutAttachMenu(int) {}

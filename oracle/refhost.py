@@ -301,3 +301,17 @@ def animation_ticks(dat_path, n, tex_tick=-1, tex_shape=None):
     rc = L.vvref_animation_ticks(dat_path.encode(), n, out, tex_tick, tex.ctypes.data if tex is not None else None, tex.nbytes if tex is not None else 0)
     assert rc == 0, rc
     return [(out[3 * i], out[3 * i + 1], out[3 * i + 2]) for i in range(n)], tex
+
+
+def app_mouse(dat_path, width, height, events):
+    """mouseInteract / mouseMotionInteract of VV/3DLIC.cpp fed with events (type, button, x, y, modifiers) -- type 0 press, 1 motion,
+    2 select clip plane `button` -- on freshly constructed camera / light / clip planes.  Returns (objects float32 [5][13]: camera,
+    light, clip planes 0..2 as (_q_internal[4], _q[4], _dist, _pos[3], locked), plane equations float64 [3][4])"""
+    ev = np.ascontiguousarray(np.asarray(events, np.int32).reshape(-1, 5))
+    out = np.zeros((5, 13), np.float32)
+    normals = np.zeros((3, 4), np.float64)
+    L = _L()
+    L.vvref_mouse.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    rc = L.vvref_mouse(dat_path.encode(), int(width), int(height), ev.ctypes.data, len(ev), out.ctypes.data, normals.ctypes.data)
+    assert rc == 0, rc
+    return out, normals
