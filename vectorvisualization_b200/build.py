@@ -71,5 +71,33 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(tag, defines=(), extra_flags=()):
+    """A/B experiments: build libvv_b200_<tag>.so next to the shipped library from the same sources with extra -D defines /
+    nvcc flags (objects under build/<tag>/).  Select it at run time with VV_B200_LIB=<path> (scripts/profile_frame.py, tests):
+
+        python -m vectorvisualization_b200.build --variant regs80 -DLIC_MIN_CTAS=3
+        VV_B200_LIB=vectorvisualization_b200/libvv_b200_regs80.so python scripts/profile_frame.py cfg3 3 loop=20
+    """
+    nvcc = _nvcc()
+    objdir = os.path.join(HERE, "build", tag)
+    os.makedirs(objdir, exist_ok=True)
+    cpp = list(CPP_SOURCES) + [f for f in OPTIONAL_CPP if os.path.exists(os.path.join(CSRC, f))]
+    defs = (["-DVV_HAVE_ILLUM_TABLES"] if "vv_illum.cpp" in cpp else []) + list(defines) + list(extra_flags)
+    objs = []
+    for src in CU_SOURCES + cpp:
+        o = os.path.join(objdir, src + ".o")
+        objs.append(o)
+        cmd = [nvcc] + NVCC_FLAGS + defs + (["-x", "cu"] if src.endswith(".cpp") else []) + ["-c", os.path.join(CSRC, src), "-o", o]
+        subprocess.check_call(cmd)
+    lib = os.path.join(HERE, "libvv_b200_%s.so" % tag)
+    subprocess.check_call([nvcc, "-shared", "-o", lib] + objs + ["-lz", "-gencode", "arch=compute_100a,code=sm_100a"])
+    return lib
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if a.startswith("-D")],
+                            [a for a in sys.argv[i + 2:] if not a.startswith("-D")]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
