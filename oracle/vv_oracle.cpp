@@ -878,6 +878,7 @@ uint64_t vvo_slicing_lic(const VVOScene *s, float *out_rgba, uint32_t *out_sampl
                 if (!slice_fragment(c, sl, r, i, g)) continue;
                 bool shaded;
                 dest = grad ? frag_slicing<true>(c, g, dest, shaded, mc) : frag_slicing<false>(c, g, dest, shaded, mc);
+                if (s->fbo_fp16) dest = {half_round(dest.x), half_round(dest.y), half_round(dest.z), half_round(dest.w)};
                 if (shaded) ++n;
             }
             float *o = out_rgba + 4 * ((size_t)y * s->width + x);

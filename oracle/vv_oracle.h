@@ -82,6 +82,10 @@ typedef struct VVOScene {
                                   volume, so a fragment exists only where its eye-space depth lies in [near, far] */
     float  window_aspect;      /* Camera::setWindow (transform.h:79-80): aspect of gluPerspective when the frame is not the window
                                   (low-res preset: half-size viewport, renderer.cpp:111-119); 0 = width / height */
+    int    fbo_fp16;           /* slicing: the ping-pong targets of the FBO path are GL_RGBA16F_ARB (renderer.cpp:566-606), so what a
+                                  slice reads back is the previous slices' result rounded to fp16.  0 (default, and what the shim's
+                                  frame-buffer stand-in and the CUDA path do): keep fp32; 1: round after every slice -- used to bound
+                                  the effect (tests/test_oracle_closed_form.py) */
 } VVOScene;
 
 /* ---- hot path ------------------------------------------------------- */
