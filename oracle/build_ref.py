@@ -139,7 +139,9 @@ def build(verbose=False):
             print(" ".join(cmd))
         subprocess.check_call(cmd)
         objs.append(o)
-    cmd = ["g++", "-shared", "-fopenmp", "-o", LIB] + objs + extra
+    # -Bsymbolic: VV/3DLIC.cpp defines unmangled globals (w, h, aspect, light, noise, ...); bind the library's own references to
+    # them whatever else the process has loaded with RTLD_GLOBAL
+    cmd = ["g++", "-shared", "-fopenmp", "-Wl,-Bsymbolic", "-o", LIB] + objs + extra
     subprocess.check_call(cmd)
     return LIB
 
