@@ -212,6 +212,19 @@ int vvref_noise_texture_cached(const char *file, unsigned char *out, size_t cap,
     return copy_tex(nd.getTextureRef()->id, out, cap, dims, ifmt, wrap);
 }
 
+/* VolumeDataSet: loadData(.dat) + createTexture (VV/3DLIC.cpp:716-722; the scalar volume that gates the noise and feeds the
+ * scalar TF index).  out receives the bytes handed to glTexImage3D (UCHAR or FLOAT source), type_out its GL type. */
+int vvref_scalar_texture(const char *dat, unsigned char *out, size_t cap, int dims[3], int *ifmt, int *wrap, int *type_out, int *filter_out)
+{
+    VolumeDataSet sd;
+    if (!sd.loadData(dat)) return -10;
+    sd.createTexture("Scalar_Tex", GL_TEXTURE4_ARB);
+    VVStubTex *t = vv_stub_texture(sd.getTextureRef()->id);
+    if (t && type_out) *type_out = (int)t->type;
+    if (t && filter_out) *filter_out = (t->min_filter == GL_LINEAR && t->mag_filter == GL_LINEAR) ? 1 : 0;
+    return copy_tex(sd.getTextureRef()->id, out, cap, dims, ifmt, wrap);
+}
+
 /* LICFilter: loadData(png) or createBoxFilter + createTexture (VV/3DLIC.cpp:725-731) */
 int vvref_filter_texture(const char *png, unsigned char *out, size_t cap, int *width, float *inv_area, int *wrap)
 {

@@ -315,3 +315,15 @@ def app_mouse(dat_path, width, height, events):
     rc = L.vvref_mouse(dat_path.encode(), int(width), int(height), ev.ctypes.data, len(ev), out.ctypes.data, normals.ctypes.data)
     assert rc == 0, rc
     return out, normals
+
+
+def scalar_texture(dat_path, shape, dtype):
+    """VolumeDataSet::loadData + createTexture: (data as handed to glTexImage3D, internal format, wrap, GL source type, LINEAR?)"""
+    out = np.zeros(tuple(shape), dtype)
+    dims = (ctypes.c_int * 3)()
+    ifmt, wrap, typ, lin = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = _L().vvref_scalar_texture(dat_path.encode(), out.ctypes.data, out.nbytes, dims, ctypes.byref(ifmt), ctypes.byref(wrap),
+                                   ctypes.byref(typ), ctypes.byref(lin))
+    assert rc == out.nbytes, rc
+    assert tuple(dims) == tuple(shape[::-1])
+    return out, ifmt.value, wrap.value, typ.value, bool(lin.value)

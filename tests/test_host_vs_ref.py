@@ -642,3 +642,26 @@ def test_mouse_interaction_matches_the_application(vv, tmp_path):
     # light distance clamp (VV/3DLIC.cpp:574-576) and a long locked rotation
     check(800, 600, [(0, 2, 400, 300, vv.MOD_CTRL)] + [(1, 0, 400, 300 - 60 * k, vv.MOD_CTRL) for k in range(1, 12)])
     check(800, 600, [(0, 0, 100, 100, vv.MOD_SHIFT)] + [(1, 0, 100 + 17 * k, 100 + 9 * k, vv.MOD_SHIFT) for k in range(1, 30)])
+
+
+def test_scalar_volume_loader(vv, oracle, tmp_path):
+    """VolumeDataSet::loadData + createTexture (VV/dataset.cpp:840-1050): the scalar volume goes to the GL as it is on disk -- UCHAR
+    or FLOAT source, GL_LUMINANCE, LINEAR, CLAMP_TO_EDGE -- and the product's DAT / RAW reader hands over the same bytes; a FLOAT
+    source is clamped to [0, 1] and stored as UNORM8 by the GL (2.1 spec 3.6.4 / 2.14.9), which is what vv_set_scalar's conversion
+    kernel does on the GPU (test_preprocess_bit_exact)."""
+    from vectorvisualization_b200 import fields as F
+    rng = np.random.RandomState(9)
+    u8 = rng.randint(0, 256, size=(5, 7, 9)).astype(np.uint8)
+    f32 = rng.uniform(-0.2, 1.2, size=(6, 4, 8)).astype(np.float32)
+    for vol, gl_type in ((u8, 0x1401), (f32, 0x1406)):                # GL_UNSIGNED_BYTE, GL_FLOAT
+        dat = F.write_dat(str(tmp_path / ("s%d.dat" % vol.itemsize)), vol)
+        with open(dat, "a") as f:
+            f.write("TimeDependent: 0 0\n")
+        ref, ifmt, wrap, typ, linear = refhost.scalar_texture(dat, vol.shape, vol.dtype)
+        assert ifmt == 0x1909 and wrap == refhost.GL_CLAMP_TO_EDGE and typ == gl_type and linear      # GL_LUMINANCE
+        assert np.array_equal(ref.view(np.uint8), vol.view(np.uint8))
+        info = vv.parse_dat(dat)
+        assert info.data_dim == 1 and tuple(info.resolution) == vol.shape[::-1]
+        buf = np.zeros_like(vol)
+        assert vv.load_library().vv_read_raw(ctypes.byref(info), 0, buf.ctypes.data_as(ctypes.c_void_p), buf.nbytes) == 0
+        assert np.array_equal(buf.view(np.uint8), ref.view(np.uint8))
