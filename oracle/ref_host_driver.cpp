@@ -46,6 +46,8 @@
 /* never destroyed: the reference's global objects (VV/3DLIC.h) call glDeleteTextures from their static destructors */
 static std::map<GLuint, VVStubTex> &g_tex = *new std::map<GLuint, VVStubTex>();
 static GLuint g_next_id = 1, g_bound = 0, g_last = 0;
+static std::map<GLuint, VVStubTex> &g_dead = *new std::map<GLuint, VVStubTex>();   /* records of deleted textures (no data) */
+static std::vector<GLuint> &g_upload_log = *new std::vector<GLuint>();   /* texture ids in glTexImage* order */
 
 static VVStubTex &cur()
 {
@@ -65,7 +67,15 @@ void vv_stub_reset(void)
 void glGenTextures(GLsizei n, GLuint *ids) { for (int i = 0; i < n; ++i) { ids[i] = g_next_id++; g_tex[ids[i]] = VVStubTex(); } }
 void glDeleteTextures(GLsizei n, const GLuint *ids)
 {
-    for (int i = 0; i < n; ++i) { auto it = g_tex.find(ids[i]); if (it != g_tex.end()) { std::free(it->second.data); g_tex.erase(it); } }
+    for (int i = 0; i < n; ++i) {
+        auto it = g_tex.find(ids[i]);
+        if (it == g_tex.end()) continue;
+        VVStubTex dead = it->second;                /* keep format / sampler state of deleted textures for vvref_texture_state */
+        dead.data = nullptr; dead.bytes = 0;
+        g_dead[ids[i]] = dead;
+        std::free(it->second.data);
+        g_tex.erase(it);
+    }
 }
 void glBindTexture(GLenum target, GLuint id) { g_bound = id; g_tex[id].target = target; }
 void glTexParameteri(GLenum, GLenum pname, GLint v)
@@ -92,6 +102,7 @@ static void upload(GLint ifmt, int w, int h, int d, GLenum fmt, GLenum type, con
     t.data = std::malloc(t.bytes ? t.bytes : 1);
     if (data) std::memcpy(t.data, data, t.bytes);
     g_last = g_bound;
+    g_upload_log.push_back(g_bound);
 }
 void glTexImage1D(GLenum, GLint, GLint ifmt, GLsizei w, GLint, GLenum fmt, GLenum type, const void *data) { upload(ifmt, w, 1, 1, fmt, type, data); }
 void glTexImage2D(GLenum, GLint, GLint ifmt, GLsizei w, GLsizei h, GLint, GLenum fmt, GLenum type, const void *data) { upload(ifmt, w, h, 1, fmt, type, data); }
@@ -210,6 +221,37 @@ int vvref_noise_texture_cached(const char *file, unsigned char *out, size_t cap,
     nd.enableGradient(true);
     nd.createTexture("Noise_Tex", GL_TEXTURE3_ARB);
     return copy_tex(nd.getTextureRef()->id, out, cap, dims, ifmt, wrap);
+}
+
+/* Sampler state of what the reference uploads: the ids of all glTexImage* calls since the last reset, in call order, and per id
+ * (target, internal format, format, type, min filter, mag filter, wrap s, wrap t, wrap r, width, height, depth) as it stands now
+ * (the reference sets the parameters after the upload). */
+void vvref_upload_log_reset(void) { g_upload_log.clear(); g_dead.clear(); }
+int vvref_upload_log(unsigned int *ids, int cap)
+{
+    int n = (int)g_upload_log.size();
+    for (int i = 0; i < n && i < cap; ++i) ids[i] = g_upload_log[i];
+    return n;
+}
+int vvref_texture_state(unsigned int id, int out[12])
+{
+    VVStubTex *t = vv_stub_texture(id);
+    if (!t) { auto it = g_dead.find(id); if (it == g_dead.end()) return -1; t = &it->second; }
+    out[0] = (int)t->target; out[1] = t->internal_format; out[2] = (int)t->format; out[3] = (int)t->type;
+    out[4] = t->min_filter; out[5] = t->mag_filter; out[6] = t->wrap_s; out[7] = t->wrap_t; out[8] = t->wrap_r;
+    out[9] = t->dim[0]; out[10] = t->dim[1]; out[11] = t->dim[2];
+    return 0;
+}
+/* the textures Renderer itself creates: FBO colour targets (createFBO / updateFBO, VV/renderer.cpp:536-620), the MC-offset
+ * texture (updateMCOffsetTex, :636-679) and the two layers of the LIC volume buffer (VolumeBuffer ctor, VV/VolumeBuffer.cpp:5-57) */
+int vvref_renderer_textures(int width, int height, int lw, int lh, int ld)
+{
+    Renderer r;
+    r.createFBO();
+    r.resize(width, height);
+    r.updateMCOffsetTex(width, height);
+    VolumeBuffer vb(GL_RGBA16F_ARB, lw, lh, ld, 2);
+    return 0;
 }
 
 /* VolumeDataSet: loadData(.dat) + createTexture (VV/3DLIC.cpp:716-722; the scalar volume that gates the noise and feeds the

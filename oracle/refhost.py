@@ -327,3 +327,27 @@ def scalar_texture(dat_path, shape, dtype):
     assert rc == out.nbytes, rc
     assert tuple(dims) == tuple(shape[::-1])
     return out, ifmt.value, wrap.value, typ.value, bool(lin.value)
+
+
+def upload_log_reset():
+    _L().vvref_upload_log_reset()
+
+
+def uploaded_textures():
+    """state of every texture the reference uploaded since upload_log_reset(), in glTexImage* order: list of dicts(target,
+    internal_format, format, type, min_filter, mag_filter, wrap_s, wrap_t, wrap_r, dims)"""
+    ids = (ctypes.c_uint * 256)()
+    n = _L().vvref_upload_log(ids, 256)
+    out = []
+    for k in range(min(n, 256)):
+        st = (ctypes.c_int * 12)()
+        if _L().vvref_texture_state(ids[k], st) != 0:
+            continue                                   # deleted since
+        out.append(dict(id=int(ids[k]), target=st[0], internal_format=st[1], format=st[2], type=st[3], min_filter=st[4], mag_filter=st[5],
+                        wrap_s=st[6], wrap_t=st[7], wrap_r=st[8], dims=(st[9], st[10], st[11])))
+    return out
+
+
+def renderer_textures(width, height, lic_dims):
+    """the textures Renderer creates itself (FBO colour targets, MC-offset texture, LIC volume buffer layers)"""
+    assert _L().vvref_renderer_textures(int(width), int(height), *[int(v) for v in lic_dims]) == 0

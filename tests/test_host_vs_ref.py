@@ -665,3 +665,70 @@ def test_scalar_volume_loader(vv, oracle, tmp_path):
         buf = np.zeros_like(vol)
         assert vv.load_library().vv_read_raw(ctypes.byref(info), 0, buf.ctypes.data_as(ctypes.c_void_p), buf.nbytes) == 0
         assert np.array_equal(buf.view(np.uint8), ref.view(np.uint8))
+
+
+def test_sampler_state_of_every_texture(oracle, tmp_path):
+    """filter and wrap mode of every texture on the hot path, read back from the reference's own glTexParameteri calls
+    (loaders and Renderer compiled unmodified) and compared with what oracle, shim and CUDA samplers implement:
+      vector field      RGBA16F        LINEAR   CLAMP_TO_EDGE          (fetch_field: edge-replicated padding)
+      scalar volume     LUMINANCE      LINEAR   CLAMP_TO_EDGE          (fetch_scalar)
+      noise             LUMINANCE/RGBA LINEAR   REPEAT                 (fetch_noise_*: wrapped border)
+      filter kernel     LUMINANCE      LINEAR   GL_CLAMP (border 0)    (kernel_lookup, Q10)
+      TF rgba / alpha-opacity          LINEAR   CLAMP_TO_EDGE          (tf_lookup / opac_lookup)
+      Zoeckler / Mallo tables (2D)     LINEAR   CLAMP_TO_EDGE
+      LIC volume buffer RGBA16F        LINEAR   REPEAT                 (fetch_licvol, Q14)
+      FBO colour targets RGBA16F rect  NEAREST  CLAMP_TO_EDGE          (texture2DRect: imageFBOSampler)
+      MC offsets        LUMINANCE16F rect NEAREST CLAMP_TO_EDGE        (mc_offset)"""
+    from vectorvisualization_b200 import fields as F
+    GL = dict(NEAREST=0x2600, LINEAR=0x2601, CLAMP=0x2900, REPEAT=0x2901, CLAMP_TO_EDGE=0x812F, TEX1D=0x0DE0, TEX2D=0x0DE1, TEX3D=0x806F,
+              RECT=0x84F5, RGBA16F=0x881A, LUMINANCE=0x1909, RGBA=0x1908, LA=0x190A, L16F=0x881E)
+    f = F.abc_flow(6)
+    noise = np.random.RandomState(1).randint(0, 256, size=(5, 5, 5)).astype(np.uint8)
+    row = F.filter_kernel("cos2", 64)
+
+    def one(fn):
+        refhost.upload_log_reset()
+        fn()
+        return refhost.uploaded_textures()
+
+    dat = F.write_dat(str(tmp_path / "v.dat"), f)
+    with open(dat, "a") as fh:
+        fh.write("TimeDependent: 0 0\n")
+    t = one(lambda: refhost.vector_texture(dat, (6, 6, 6)))[-1]
+    assert (t["target"], t["internal_format"], t["min_filter"], t["mag_filter"]) == (GL["TEX3D"], GL["RGBA16F"], GL["LINEAR"], GL["LINEAR"])
+    assert (t["wrap_s"], t["wrap_t"], t["wrap_r"]) == (GL["CLAMP_TO_EDGE"],) * 3
+    sdat = F.write_dat(str(tmp_path / "s.dat"), noise)
+    with open(sdat, "a") as fh:
+        fh.write("TimeDependent: 0 0\n")
+    t = one(lambda: refhost.scalar_texture(sdat, noise.shape, np.uint8))[-1]
+    assert (t["target"], t["internal_format"], t["min_filter"], t["mag_filter"]) == (GL["TEX3D"], GL["LUMINANCE"], GL["LINEAR"], GL["LINEAR"])
+    assert (t["wrap_s"], t["wrap_t"], t["wrap_r"]) == (GL["CLAMP_TO_EDGE"],) * 3
+    npath = F.write_noise(str(tmp_path / "noise"), noise)
+    for grad, ifmt in ((False, GL["LUMINANCE"]), (True, GL["RGBA"])):
+        t = one(lambda: refhost.noise_texture(npath, noise.shape, grad))[-1]
+        assert (t["target"], t["internal_format"], t["min_filter"], t["mag_filter"]) == (GL["TEX3D"], ifmt, GL["LINEAR"], GL["LINEAR"])
+        assert (t["wrap_s"], t["wrap_t"], t["wrap_r"]) == (GL["REPEAT"],) * 3
+    png = F.write_png(str(tmp_path / "k.png"), row[None, :])
+    t = one(lambda: refhost.filter_texture(png))[-1]
+    assert (t["target"], t["min_filter"], t["mag_filter"], t["wrap_s"]) == (GL["TEX1D"], GL["LINEAR"], GL["LINEAR"], GL["CLAMP"])
+    ts = one(lambda: refhost.tf_textures(None))
+    assert len(ts) >= 2
+    for t, ifmt in zip(ts[-2:], (GL["RGBA"], GL["LA"])):
+        assert (t["target"], t["internal_format"], t["min_filter"], t["mag_filter"], t["wrap_s"]) == \
+            (GL["TEX1D"], ifmt, GL["LINEAR"], GL["LINEAR"], GL["CLAMP_TO_EDGE"]) and t["dims"][0] == 256
+    ts = one(lambda: refhost.illum_tables())
+    assert len(ts) == 3
+    for t in ts:
+        assert (t["target"], t["min_filter"], t["mag_filter"], t["wrap_s"], t["wrap_t"]) == \
+            (GL["TEX2D"], GL["LINEAR"], GL["LINEAR"], GL["CLAMP_TO_EDGE"], GL["CLAMP_TO_EDGE"]) and t["dims"][:2] == (256, 256)
+    ts = one(lambda: refhost.renderer_textures(40, 30, (8, 6, 4)))
+    fbo = [t for t in ts if t["target"] == GL["RECT"] and t["internal_format"] == GL["RGBA16F"]]
+    mc = [t for t in ts if t["target"] == GL["RECT"] and t["internal_format"] == GL["L16F"]]
+    lic = [t for t in ts if t["target"] == GL["TEX3D"]]
+    assert len(fbo) == 2 and len(mc) == 1 and len(lic) == 2
+    for t in fbo:
+        assert (t["min_filter"], t["mag_filter"], t["wrap_s"], t["wrap_t"], t["dims"][:2]) == (GL["NEAREST"], GL["NEAREST"], GL["CLAMP_TO_EDGE"], GL["CLAMP_TO_EDGE"], (40, 30))
+    assert (mc[0]["min_filter"], mc[0]["mag_filter"], mc[0]["wrap_s"], mc[0]["dims"][:2]) == (GL["NEAREST"], GL["NEAREST"], GL["CLAMP_TO_EDGE"], (40, 30))
+    for t in lic:
+        assert (t["internal_format"], t["min_filter"], t["mag_filter"], t["dims"]) == (GL["RGBA16F"], GL["LINEAR"], GL["LINEAR"], (8, 6, 4))
+        assert (t["wrap_s"], t["wrap_t"], t["wrap_r"]) == (GL["REPEAT"],) * 3
