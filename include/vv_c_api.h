@@ -161,6 +161,10 @@ VV_API int vv_update_light_pos(VVRenderer *r);
  * for that.  vv_set_window(0, 0) returns to the default, aspect = frame width / frame height. */
 VV_API int vv_enable_lowres(VVRenderer *r, int enable);
 VV_API int vv_set_window(VVRenderer *r, int window_width, int window_height);
+/* enableFBO (key 'F'): the stored frame lives in a GL_RGBA16F_ARB texture instead of the RGBA8 back buffer (VV/renderer.cpp:
+ * 562-606, Q18).  With it on, vv_read_rgba32f returns the frame rounded to fp16 and the stored-frame PNG (vv_save_png(.., 0),
+ * screenshots, recordings) is written the way saveTexture converts a float texture: (int)(255 * texel), truncated
+ * (VV/renderer.cpp:386-403).  vv_read_rgba8 is always the RGBA8 back-buffer frame. */
 VV_API int vv_enable_float_target(VVRenderer *r, int enable);
 VV_API int vv_set_option(VVRenderer *r, int option, int value);
 /* Screenshot / recording: Renderer::screenshot / switchRecording (VV/renderer.h:99-101, keys '0' / 'R', VV/3DLIC.cpp:259-270)

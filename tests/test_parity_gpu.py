@@ -978,3 +978,32 @@ def test_mouse_interaction_drives_the_renderer(vv):
     _, b, _, _, nb = render_cuda(vv, s2)
     assert tuple(it.cam.q) != (0.0, 0.0, 0.0, 1.0) and it.cam.pos[2] != 0.0
     assert na == nb and na > 0 and np.array_equal(a, b)
+
+
+def test_float_target_outputs(vv, oracle, tmp_path):
+    """enableFBO (key 'F'): the stored frame is an RGBA16F texture (VV/renderer.cpp:562-606) -- read back rounded to fp16 -- and
+    saveTexture writes a float texture as (int)(255 * texel), truncated (VV/renderer.cpp:386-403)"""
+    import os
+    from vectorvisualization_b200 import configs
+    s = configs.cfg1(n=16, size=40)
+    r = vv.Renderer(0)
+    configs.apply_scene(r, s)
+    out = str(tmp_path / "snapshotOut")
+    os.makedirs(out)
+    r.setSnapshot(out, "f.png")
+    r.render(True)
+    a = r.readRGBA32F()
+    a8 = r.readRGBA8()
+    r.enableFBO(True)
+    b = r.readRGBA32F()
+    want = oracle.half_round(a)
+    assert np.array_equal(b.view(np.uint32), want.view(np.uint32)) and not np.array_equal(a, b)
+    assert np.array_equal(r.readRGBA8(), a8)                       # the RGBA8 back-buffer frame is what it was
+    r.screenshot()
+    r.render(False)
+    png = vv.png_read(r.lastSnapshotPath())[::-1]
+    trunc = np.clip((np.float32(255.0) * want).astype(np.int32), 0, 255).astype(np.uint8)
+    assert np.array_equal(png, trunc)
+    assert int(np.abs(png.astype(np.int32) - a8.astype(np.int32)).max()) <= 1 and not np.array_equal(png, a8)
+    r.enableFBO(False)
+    assert np.array_equal(r.readRGBA32F(), a)

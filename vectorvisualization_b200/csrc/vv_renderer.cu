@@ -1291,6 +1291,12 @@ int vv_read_rgba32f(VVRenderer *r, float *out, size_t out_bytes)
     CU(cudaSetDevice(r->device));
     CU(cudaMemcpyAsync(out, r->frame.p, (size_t)r->width * r->height * 16, cudaMemcpyDeviceToHost, r->stream));
     CU(cudaStreamSynchronize(r->stream));
+    if (r->float_target) {
+        // enableFBO(true): the frame lives in a GL_RGBA16F_ARB texture (VV/renderer.cpp:562-606): what is read back is the
+        // shader's result rounded to fp16
+        const size_t n = (size_t)r->width * r->height * 4;
+        for (size_t i = 0; i < n; ++i) out[i] = __half2float(__float2half_rn(out[i]));
+    }
     return VV_OK;
 }
 
@@ -1425,8 +1431,21 @@ int vv_save_png(VVRenderer *r, const char *path, int displayed)
 {
     if (!r || !path) return fail(VV_ERR_INVALID, "vv_save_png: null argument");
     std::vector<uint8_t> img((size_t)r->width * r->height * 4), flip(img.size());
-    int rc = displayed ? vv_read_display_rgba8(r, img.data(), img.size()) : vv_read_rgba8(r, img.data(), img.size());
-    if (rc) return rc;
+    int rc;
+    if (!displayed && r->float_target) {
+        // saveTexture on a floating-point texture (VV/renderer.cpp:386-403): v = (int)(scale * texel) -- truncation, not the
+        // GL's round-to-nearest -- clamped to 0..255, all four channels (mask 15, scale 255)
+        std::vector<float> f((size_t)r->width * r->height * 4);
+        rc = vv_read_rgba32f(r, f.data(), f.size() * sizeof(float));      // fp16-rounded, see there
+        if (rc) return rc;
+        for (size_t i = 0; i < f.size(); ++i) {
+            int v = (int)(255.0f * f[i]);
+            img[i] = (uint8_t)(v > 255 ? 255 : (v < 0 ? 0 : v));
+        }
+    } else {
+        rc = displayed ? vv_read_display_rgba8(r, img.data(), img.size()) : vv_read_rgba8(r, img.data(), img.size());
+        if (rc) return rc;
+    }
     const size_t stride = (size_t)r->width * 4;
     for (int y = 0; y < r->height; ++y) std::memcpy(&flip[stride * y], &img[stride * (r->height - 1 - y)], stride);
     std::string err;
