@@ -35,6 +35,7 @@ RAYCAST = ["inc_header.glsl", "inc_lic.glsl", "inc_illum.glsl", "lic3d_fragment.
 LICVOL = ["inc_header.glsl", "inc_lic.glsl", "lic3d_volume_fragment.glsl"]
 VOLRAY = ["inc_header.glsl", "inc_illum.glsl", "raycast_lic3d_fragment.glsl"]
 SLICING = ["inc_header.glsl", "inc_lic.glsl", "inc_illum.glsl", "lic3d_slicing_fragment.glsl"]
+SLICINGBLEND = ["inc_header.glsl", "inc_lic.glsl", "inc_illum.glsl", "lic3d_slicingblend_fragment.glsl"]
 PROGRAMS = {
     "raycast_none": (RAYCAST, [], []),
     "raycast_gradient": (RAYCAST, ["ILLUM_GRADIENT"], []),
@@ -53,6 +54,10 @@ PROGRAMS = {
     "raycast_none_mc": (RAYCAST, ["USE_MC_OFFSET"], []),
     "raycast_gradient_mc": (RAYCAST, ["ILLUM_GRADIENT", "USE_MC_OFFSET"], []),
     "slicing_none_mc": (SLICING, ["USE_MC_OFFSET"], ["REF_SLICING"]),
+    # the variant sliceVolume runs without the FBO (the start-up state): the shader returns the premultiplied sample, the GL blends
+    "slicingblend_none": (SLICINGBLEND, [], []),
+    "slicingblend_gradient": (SLICINGBLEND, ["ILLUM_GRADIENT"], []),
+    "slicingblend_mallo": (SLICINGBLEND, ["ILLUM_MALLO"], []),
 }
 # Source-edit variants: the reference switches the TF index and the LIC gate by (un)commenting lines of
 # lic3d_fragment.glsl:53-61.  Each variant swaps the live expression for one of the alternatives the file itself lists.

@@ -232,6 +232,24 @@ class RefScene:
         fn(ctypes.byref(self.u), vvo._p(fr), vvo._p(st), npix, vvo._p(out), vvo._p(cnt))
         return out.reshape(s.height, s.width, 4), cnt.reshape(s.height, s.width), int(cnt.sum())
 
+    def slicing_blend_fragments(self, frags):
+        """lic3d_slicingblend_fragment.glsl (slicing without the FBO) on fragment positions frags [n][3]: the premultiplied sample
+        colour of every fragment, [n][4], as the shader leaves it in gl_FragColor (the GL clamps and blends it afterwards)"""
+        s = self.s
+        assert s.tf_mode == 1 and s.gate_mode == 1
+        d = s.defines or ""
+        prog = "slicingblend_none"
+        for k, v in (("ILLUM_GRADIENT", "gradient"), ("ILLUM_MALLO", "mallo")):
+            if k in d:
+                prog = "slicingblend_" + v
+        tc = np.zeros((len(frags), 4), np.float32)
+        tc[:, :3] = frags
+        tc[:, 3] = 1.0
+        self._set_scale(raycast=True)
+        self.u.frag_w = 0
+        out, _ = self._run(prog, np.ascontiguousarray(tc))
+        return out
+
     def lic_volume(self, dims=None):
         nz, ny, nx = self.s.field.shape[:3]
         w, h, d = dims or (nx, ny, nz)

@@ -889,6 +889,80 @@ uint64_t vvo_slicing_lic(const VVOScene *s, float *out_rgba, uint32_t *out_sampl
     return total;
 }
 
+} /* extern "C" */
+
+/* lic3d_slicingblend_fragment.glsl = lic3d_slicing_fragment.glsl without the frame-buffer read: with dest = 0 the FBO shader's
+ * skip never fires and its blend clamp((1 - 0) src + 0) is the clamp the GL applies to a fragment colour before blending */
+template <bool GRAD>
+static V4 frag_slicing_blend(const Ctx &c, V3 g, bool &shaded, float mc)
+{
+    V4 src = frag_slicing<GRAD>(c, g, V4{0, 0, 0, 0}, shaded, mc);
+    shaded = (src.x != 0.0f || src.y != 0.0f || src.z != 0.0f || src.w != 0.0f);
+    return src;
+}
+
+static inline uint8_t unorm8(float v) { return (uint8_t)std::floor(clampf(v, 0.0f, 1.0f) * 255.0f + 0.5f); }
+
+extern "C" {
+
+int vvo_slice_fragment_colors(const VVOScene *s, int x, int y, float *out_rgba, int cap)
+{
+    Ctx c;
+    make_ctx(s, c);
+    const Slicing sl = setup_slicing(c);
+    const bool grad = (s->illum_mode == VVO_ILLUM_GRADIENT);
+    PixelRay r = pixel_dir(c, x, y);
+    const float mc = s->mc_offsets ? s->mc_offsets[(size_t)y * s->width + x] : -1.0f;
+    int n = 0;
+    for (int i = 0; i < sl.numSlices; ++i) {
+        V3 g;
+        if (!slice_fragment(c, sl, r, i, g)) continue;
+        if (n >= cap) return -1;
+        bool shaded;
+        V4 v = grad ? frag_slicing_blend<true>(c, g, shaded, mc) : frag_slicing_blend<false>(c, g, shaded, mc);
+        out_rgba[4 * n] = v.x; out_rgba[4 * n + 1] = v.y; out_rgba[4 * n + 2] = v.z; out_rgba[4 * n + 3] = v.w;
+        ++n;
+    }
+    return n;
+}
+
+uint64_t vvo_slicing_blend8(const VVOScene *s, uint8_t *out_rgba8, uint32_t *out_samples)
+{
+    Ctx c;
+    make_ctx(s, c);
+    const Slicing sl = setup_slicing(c);
+    const bool grad = (s->illum_mode == VVO_ILLUM_GRADIENT);
+    uint64_t total = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
+    for (int y = 0; y < s->height; ++y)
+        for (int x = 0; x < s->width; ++x) {
+            PixelRay r = pixel_dir(c, x, y);
+            uint8_t dst[4] = {0, 0, 0, 0};                                          /* glClear with (0, 0, 0, 0), renderer.cpp:1164-1165 */
+            uint32_t n = 0;
+            const float mc = s->mc_offsets ? s->mc_offsets[(size_t)y * s->width + x] : -1.0f;
+            auto blend = [&](const float src[4]) {                                  /* glBlendFunc(ONE_MINUS_DST_ALPHA, ONE) */
+                const float da = (float)dst[3] / 255.0f;
+                for (int k = 0; k < 4; ++k) dst[k] = unorm8(src[k] * (1.0f - da) + (float)dst[k] / 255.0f);
+            };
+            for (int i = 0; i < sl.numSlices; ++i) {
+                V3 g;
+                if (!slice_fragment(c, sl, r, i, g)) continue;
+                bool shaded;
+                V4 v = grad ? frag_slicing_blend<true>(c, g, shaded, mc) : frag_slicing_blend<false>(c, g, shaded, mc);
+                const float src[4] = {v.x, v.y, v.z, v.w};
+                blend(src);
+                if (shaded) ++n;
+            }
+            const float white[4] = {1.0f, 1.0f, 1.0f, 1.0f};                        /* the screen-filling white plane, :1238-1255 */
+            blend(white);
+            uint8_t *o = out_rgba8 + 4 * ((size_t)y * s->width + x);
+            for (int k = 0; k < 4; ++k) o[k] = dst[k];
+            if (out_samples) out_samples[(size_t)y * s->width + x] = n;
+            total += n;
+        }
+    return total;
+}
+
 /* slicing set-up read-back for tests: out[5] = v.xyz, d, numSlices */
 void vvo_slicing_setup(const VVOScene *s, float *out)
 {

@@ -101,6 +101,14 @@ void vvo_lic_volume(const VVOScene *s, int w, int h, int d, int z0, int z1, floa
 uint64_t vvo_raycast_licvolume(const VVOScene *s, float *out_rgba, uint32_t *out_samples);
 /* lic3d_slicing_fragment.glsl:5-74 over the view-aligned slices of slicing.cpp:42-114 / renderer.cpp:1123-1267 */
 uint64_t vvo_slicing_lic(const VVOScene *s, float *out_rgba, uint32_t *out_samples);
+/* Slicing WITHOUT the FBO (Renderer::sliceVolume with _useFBO == false, the start-up state; renderer.cpp:1150-1160, 1238-1262):
+ * lic3d_slicingblend_fragment.glsl returns the premultiplied sample of every fragment (no dest.a < 0.95 skip), and the GL blends
+ * it into the RGBA8 back buffer with (ONE_MINUS_DST_ALPHA, ONE); at the end a white plane is blended in the same way.
+ * vvo_slice_fragment_colors: the fragment colours of pixel (x, y), slice order, clamped to [0, 1] as they enter the blend.
+ * vvo_slicing_blend8: the back buffer after all slices and the white plane, RGBA8 [h][w][4], each blend computed on the stored
+ * 8-bit values and rounded to nearest (GL 2.1 4.1.8, 2.14.9); out_samples counts fragments whose gate passed. */
+int vvo_slice_fragment_colors(const VVOScene *s, int x, int y, float *out_rgba, int cap);
+uint64_t vvo_slicing_blend8(const VVOScene *s, uint8_t *out_rgba8, uint32_t *out_samples);
 void vvo_slicing_setup(const VVOScene *s, float *out5);
 int vvo_slice_fragments(const VVOScene *s, int x, int y, float *out_xyzv, int cap);
 /* one computeLIC (inc_lic.glsl:152-202) at pos; out[4] */

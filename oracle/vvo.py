@@ -63,6 +63,8 @@ def lib():
         L.vvo_slicing_lic.argtypes = [S, P, P]; L.vvo_slicing_lic.restype = U64
         L.vvo_slicing_setup.argtypes = [S, P]
         L.vvo_slice_fragments.argtypes = [S, I, I, P, I]; L.vvo_slice_fragments.restype = I
+        L.vvo_slice_fragment_colors.argtypes = [S, I, I, P, I]; L.vvo_slice_fragment_colors.restype = I
+        L.vvo_slicing_blend8.argtypes = [S, P, P]; L.vvo_slicing_blend8.restype = U64
         L.vvo_background.argtypes = [P, I, P]; L.vvo_quantize_rgba8.argtypes = [P, I, P]
         L.vvo_display_window.argtypes = [P, I, I, I, I, P]
         for n in ("vvo_sample_vec", "vvo_sample_noise", "vvo_sample_scalar"):
@@ -242,6 +244,21 @@ class OracleScene:
                 c.illum_tex[i] = t.ctypes.data
             c.illum_dim = (ctypes.c_int * 2)(self.illum_tables[0].shape[1], self.illum_tables[0].shape[0])
         self.c = c
+
+    def slicing_blend8(self):
+        """slicing without the FBO (the start-up state of the reference): RGBA8 back buffer [h][w][4], samples, total"""
+        s = self.s
+        out = np.zeros((s.height, s.width, 4), dtype=np.uint8)
+        cnt = np.zeros((s.height, s.width), dtype=np.uint32)
+        tot = lib().vvo_slicing_blend8(ctypes.byref(self.c), _p(out), _p(cnt))
+        return out, cnt, int(tot)
+
+    def slice_fragment_colors(self, x, y):
+        _, _, n = self.slicing_setup()
+        buf = np.zeros((n, 4), np.float32)
+        k = lib().vvo_slice_fragment_colors(ctypes.byref(self.c), x, y, _p(buf), n)
+        assert k >= 0
+        return buf[:k].copy()
 
     def raycast(self, rect=None):
         """returns (rgba float [h][w][4], samples uint32 [h][w], total)"""

@@ -241,3 +241,52 @@ def test_random_scenes_slicing_and_lic_volume_bit_exact(oracle):
         b, cb, tb = r.raycast_licvolume(lo)
         assert ta == tb and np.array_equal(ca, cb) and np.array_equal(a.view(np.uint32), b.view(np.uint32)), seed
     assert done >= 8
+
+
+@pytest.mark.parametrize("define", ["", "ILLUM_GRADIENT", "ILLUM_MALLO"])
+def test_slicing_without_fbo_fragments_bit_exact(oracle, define):
+    """The slicing variant the reference runs until key 'F' switches the FBO on (Renderer::sliceVolume, VV/renderer.cpp:1150-1160):
+    lic3d_slicingblend_fragment.glsl returns every fragment's premultiplied sample and the GL blends it into the RGBA8 back
+    buffer.  The oracle's fragment colours against that shader's code, bit for bit (after the GL's clamp to [0, 1]); the 8-bit
+    blend of vvo_slicing_blend8 against the same arithmetic done here from the reference shader's outputs."""
+    import ctypes
+    import vectorvisualization_b200 as vv
+    from vectorvisualization_b200 import configs, fields as F
+    tables = oracle.illum_tables(40.0)
+    s = configs.cfg3(n=16, size=20, camera=F.CAMERA_CLOSE) if define else configs.cfg2(n=16, size=20)
+    s.defines = ("#define " + define) if define else ""
+    s.with_gradients = True
+    s.technique, s.tf_mode, s.gate_mode = vv.VOLIC_SLICING, vv.TF_A, vv.GATE_TF_ALPHA
+    s.tf = F.default_tf()
+    s.params.update(gradientScale=4.0, stepSizeVol=1 / 32)
+    need = "MALLO" in define
+    o = oracle.OracleScene(s, illum_tables=tables if need else None)
+    r = refshim.RefScene(s, illum_tables=tables if need else None)
+    _, _, nslices = o.slicing_setup()
+    frame = np.zeros((s.height, s.width, 4), np.uint8)
+    buf = np.zeros((nslices, 4), np.float32)
+    shaded = 0
+    for y in range(s.height):
+        for x in range(s.width):
+            n = oracle.lib().vvo_slice_fragments(ctypes.byref(o.c), x, y, oracle._p(buf), nslices)
+            mine = o.slice_fragment_colors(x, y)
+            assert len(mine) == n
+            dst = np.zeros(4, np.uint8)
+            if n:
+                ref = np.clip(r.slicing_blend_fragments(buf[:n, :3].copy()), 0.0, 1.0)
+                assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32)), (x, y)
+                shaded += int((ref != 0).any(axis=1).sum())
+                for src in ref:                                          # glBlendFunc(GL_ONE_MINUS_DST_ALPHA, GL_ONE) on RGBA8
+                    da = np.float32(dst[3]) / np.float32(255.0)
+                    v = src * (np.float32(1.0) - da) + dst.astype(np.float32) / np.float32(255.0)
+                    dst = np.floor(np.clip(v, 0, 1) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
+            da = np.float32(dst[3]) / np.float32(255.0)                  # the white plane, VV/renderer.cpp:1238-1255
+            v = np.float32(1.0) * (np.float32(1.0) - da) + dst.astype(np.float32) / np.float32(255.0)
+            frame[y, x] = np.floor(np.clip(v, 0, 1) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
+    got, cnt, tot = o.slicing_blend8()
+    assert np.array_equal(got, frame) and tot == shaded and tot > 200
+    assert (got[..., 3] == 255).all()                                    # the white plane completes the alpha
+    # against the FBO variant composited over white: same picture up to the 8-bit accumulation and the 0.95 skip
+    fbo, _, _ = o.slicing()
+    disp = oracle.quantize_rgba8(oracle.background(fbo))
+    assert np.abs(disp[..., :3].astype(np.int32) - got[..., :3].astype(np.int32)).max() <= 24
