@@ -123,7 +123,9 @@ VV_API int vv_set_time_interp(VVRenderer *r, int interp_index, int interp_size);
  * vv_time_cursor_tick returns the fraction index this tick's texture is packed with and sets *advanced when the pair of time
  * steps moved on (data = step cursor->current, newData = step vv_time_cursor_next).
  * vv_idle does the whole tick on a handle whose field came from vv_load_dat: re-pack on the GPU, advance, and re-read the two
- * RAW files when the pair moves on.  Returns VV_OK, or VV_ERR_STATE when the field was not loaded from a DAT file. */
+ * RAW files when the pair moves on.  Returns VV_OK, or VV_ERR_STATE when the field was not loaded from a DAT file.
+ * (FLOAT3 fields; a UCHAR3 field keeps its first time step: the reference's UCHAR interpolation path corrupts its own source
+ * array on every call, SURVEY Q20, and is not reproduced.) */
 typedef struct VVTimeCursor { int time_begin, time_end, current, interp_index, interp_size; } VVTimeCursor;
 VV_API void vv_time_cursor_init(VVTimeCursor *c, int time_begin, int time_end, int interp_size);
 VV_API int vv_time_cursor_next(const VVTimeCursor *c);
