@@ -71,13 +71,16 @@ def build(force=False, verbose=False):
     return LIB
 
 
-def build_variant(tag, defines=(), extra_flags=()):
+def build_variant(tag, defines=(), extra_flags=(), only=("vv_kernels.cu",)):
     """A/B experiments: build libvv_b200_<tag>.so next to the shipped library from the same sources with extra -D defines /
-    nvcc flags (objects under build/<tag>/).  Select it at run time with VV_B200_LIB=<path> (scripts/profile_frame.py, tests):
+    nvcc flags (objects under build/<tag>/).  Only the sources in `only` are recompiled with the extra flags (the kernel
+    variants live in vv_kernels.cu); the other objects are those of the shipped build.  Select the library at run time with
+    VV_B200_LIB=<path> (scripts/ab.py, scripts/profile_frame.py, tests):
 
         python -m vectorvisualization_b200.build --variant regs80 -DLIC_MIN_CTAS=3
-        VV_B200_LIB=vectorvisualization_b200/libvv_b200_regs80.so python scripts/profile_frame.py cfg3 3 loop=20
+        python scripts/ab.py cfg=cfg3 vectorvisualization_b200/libvv_b200.so vectorvisualization_b200/libvv_b200_regs80.so
     """
+    build()
     nvcc = _nvcc()
     objdir = os.path.join(HERE, "build", tag)
     os.makedirs(objdir, exist_ok=True)
@@ -85,6 +88,9 @@ def build_variant(tag, defines=(), extra_flags=()):
     defs = (["-DVV_HAVE_ILLUM_TABLES"] if "vv_illum.cpp" in cpp else []) + list(defines) + list(extra_flags)
     objs = []
     for src in CU_SOURCES + cpp:
+        if src not in only:
+            objs.append(os.path.join(HERE, "build", src + ".o"))
+            continue
         o = os.path.join(objdir, src + ".o")
         objs.append(o)
         cmd = [nvcc] + NVCC_FLAGS + defs + (["-x", "cu"] if src.endswith(".cpp") else []) + ["-c", os.path.join(CSRC, src), "-o", o]

@@ -288,6 +288,64 @@ __device__ __forceinline__ float4 fetch_field(const DevParams &P, float px, floa
     return r;
 }
 
+// ---- one trilinear cell of the x-pair field, widened once, evaluated at several positions -------------------------
+// Heun's predictor position Pos2 = p + d1 and corrector position p + (d1 + d2)/2 differ by (d2 - d1)/2, a small fraction
+// of a voxel wherever the field is smooth, so both almost always lie in the same trilinear cell: the 4 LDG.128, the address
+// arithmetic and the 24 fp16 -> fp32 widenings (FHADD) are done once per cell and only the lerps are evaluated twice.
+// The operations on the texel values are exactly those of fetch_field_pk<LAYOUT_PAIR, false> (same bits).
+struct CellCoord { unsigned int idx; float fx, fy, fz; };
+struct FieldCell {
+    pk2_t rg0[4], rgd[4];   // corner rows A = (y0,z0), B = (y1,z0), C = (y0,z1), D = (y1,z1): (r,g) of texel x0, and texel x0+1 minus it
+    pk2_t b0[2], bd[2];     // blue with the two z planes packed: [0] = rows (A, C), [1] = rows (B, D)
+};
+
+__device__ __forceinline__ CellCoord field_cell_coord(const DevParams &P, float px, float py, float pz)
+{
+    CellCoord c;
+    int x0, y0, z0;
+    axis_clamp_f(px, P.fnf[0], P.fnm1f[0], x0, c.fx);
+    axis_clamp_f(py, P.fnf[1], P.fnm1f[1], y0, c.fy);
+    axis_clamp_f(pz, P.fnf[2], P.fnm1f[2], z0, c.fz);
+    c.idx = (unsigned int)z0 * P.fPlane + (unsigned int)y0 * P.fRow + (unsigned int)x0;
+    return c;
+}
+
+__device__ __forceinline__ void widen_rg(unsigned int w0, unsigned int w1, pk2_t &t0, pk2_t &d)
+{
+    const float a0 = fh_cvt(h_lo(w0)), a1 = fh_cvt(h_hi(w0));
+    t0 = pk2(a0, a1);
+    d = pk2(fh_sub(h_lo(w1), a0), fh_sub(h_hi(w1), a1));
+}
+
+__device__ __forceinline__ FieldCell load_field_cell(const DevParams &P, unsigned int idx)
+{
+    const uint4 *F = P.field_pair + idx;
+    const uint4 A = ld_u4(F), B = ld_u4(F + P.fRow), C = ld_u4(F + P.fPlane), D = ld_u4(F + P.fPlane + P.fRow);
+    FieldCell c;
+    widen_rg(A.x, A.z, c.rg0[0], c.rgd[0]);
+    widen_rg(B.x, B.z, c.rg0[1], c.rgd[1]);
+    widen_rg(C.x, C.z, c.rg0[2], c.rgd[2]);
+    widen_rg(D.x, D.z, c.rg0[3], c.rgd[3]);
+    const float bA0 = fh_cvt(h_lo(A.y)), bC0 = fh_cvt(h_lo(C.y)), bB0 = fh_cvt(h_lo(B.y)), bD0 = fh_cvt(h_lo(D.y));
+    c.b0[0] = pk2(bA0, bC0); c.bd[0] = pk2(fh_sub(h_lo(A.w), bA0), fh_sub(h_lo(C.w), bC0));
+    c.b0[1] = pk2(bB0, bD0); c.bd[1] = pk2(fh_sub(h_lo(B.w), bB0), fh_sub(h_lo(D.w), bD0));
+    return c;
+}
+
+__device__ __forceinline__ FieldVal eval_field_cell(const FieldCell &c, float fx, float fy, float fz)
+{
+    const pk2_t fx2 = bc2(fx), fy2 = bc2(fy), fz2 = bc2(fz);
+    FieldVal r;
+    const pk2_t rgA = fma2(fx2, c.rgd[0], c.rg0[0]), rgB = fma2(fx2, c.rgd[1], c.rg0[1]);
+    const pk2_t rgC = fma2(fx2, c.rgd[2], c.rg0[2]), rgD = fma2(fx2, c.rgd[3], c.rg0[3]);
+    r.rg = lerp2(lerp2(rgA, rgB, fy2), lerp2(rgC, rgD, fy2), fz2);
+    const pk2_t bAC = fma2(fx2, c.bd[0], c.b0[0]), bBD = fma2(fx2, c.bd[1], c.b0[1]);
+    const pk2_t by = lerp2(bAC, bBD, fy2);
+    r.b = lerpf(lo2(by), hi2(by), fz);
+    r.a = 0.0f;
+    return r;
+}
+
 // byte k of w as the float 8388608 + byte (bits 0x4B0000bb): no I2F; the bias cancels in differences
 constexpr float kByteBias = 8388608.0f;
 __device__ __forceinline__ float byte_biased(unsigned int w, int k) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + k)); }
@@ -346,6 +404,8 @@ __device__ __forceinline__ Rgba2 quad_blend(uint4 q, pk2_t fx2, pk2_t fy2)
 }
 
 // noiseSampler, RGBA8 (gradient.xyz, noise), REPEAT -> raw texel (freqSamplingGrad, inc_lic.glsl:61-68)
+// NL: layout known at compile time (1 fp16 x-pair, 0 u8 xy-quad) or -1 = chosen at run time from P.noise_pair
+template <int NL = -1>
 __device__ __forceinline__ Rgba2 fetch_noise_rgba_pk(const DevParams &P, float px, float py, float pz)
 {
     int x0, y0, z0;
@@ -353,7 +413,7 @@ __device__ __forceinline__ Rgba2 fetch_noise_rgba_pk(const DevParams &P, float p
     axis_repeat_f(px, P.nnf[0], x0, fx);
     axis_repeat_f(py, P.nnf[1], y0, fy);
     axis_repeat_f(pz, P.nnf[2], z0, fz);
-    if (P.noise_pair) {
+    if (NL == 1 || (NL < 0 && P.noise_pair)) {
         // fp16 x-pair layout (byte values 0..255 are exact in fp16): the same FHADD lerp as the vector field, no byte
         // decode; wrapped border rows / planes, so the neighbours are +npRow / +npPlane for every cell index in [-1, n-1]
         const uint4 *N = P.noise_pair + (z0 * P.npPlane + y0 * P.npRow + x0);

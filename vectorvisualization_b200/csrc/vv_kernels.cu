@@ -153,6 +153,10 @@ __device__ __forceinline__ Walker make_walker(f3 pos, float4 centre)
     return w;
 }
 
+#ifndef VV_CELL_REUSE
+#define VV_CELL_REUSE 1   // one cell load per Heun step, evaluated at the predictor and the corrector position (see FieldCell)
+#endif
+
 // one Heun step of singleLICstep (inc_lic.glsl:104-128); sh = dir * h
 template <int LAYOUT, bool SOF>
 __device__ __forceinline__ void heun_step(const DevParams &P, Walker &w, float sh)
@@ -162,13 +166,28 @@ __device__ __forceinline__ void heun_step(const DevParams &P, Walker &w, float s
     const pk2_t d1 = mul2(fma2(two, w.vrg, mone), s2);                    // licdir = (2 v - 1) * dir * h
     const float d1z = fmaf(2.0f, w.vb, -1.0f) * s1;
     const pk2_t p2 = add2(w.qxy, d1);                                      // Pos2 = newPos + licdir
-    const FieldVal v2 = fetch_field_pk<LAYOUT, false>(P, lo2(p2), hi2(p2), w.qz + d1z);
-    const pk2_t d2 = mul2(fma2(two, v2.rg, mone), s2);
-    const float d2z = fmaf(2.0f, v2.b, -1.0f) * s1;
-    w.qxy = fma2(bc2(0.5f), add2(d1, d2), w.qxy);                          // newPos += 0.5 (licdir + licdir2)
-    w.qz = fmaf(0.5f, d1z + d2z, w.qz);
-    const FieldVal v = fetch_field_pk<LAYOUT, SOF>(P, lo2(w.qxy), hi2(w.qxy), w.qz);
-    w.vrg = v.rg; w.vb = v.b; w.va = v.a;
+    if constexpr (LAYOUT == LAYOUT_PAIR && !SOF && VV_CELL_REUSE) {
+        const CellCoord c2 = field_cell_coord(P, lo2(p2), hi2(p2), w.qz + d1z);
+        const FieldCell cell = load_field_cell(P, c2.idx);
+        const FieldVal v2 = eval_field_cell(cell, c2.fx, c2.fy, c2.fz);
+        const pk2_t d2 = mul2(fma2(two, v2.rg, mone), s2);
+        const float d2z = fmaf(2.0f, v2.b, -1.0f) * s1;
+        w.qxy = fma2(bc2(0.5f), add2(d1, d2), w.qxy);                      // newPos += 0.5 (licdir + licdir2)
+        w.qz = fmaf(0.5f, d1z + d2z, w.qz);
+        const CellCoord c = field_cell_coord(P, lo2(w.qxy), hi2(w.qxy), w.qz);
+        FieldVal v;
+        if (c.idx == c2.idx) v = eval_field_cell(cell, c.fx, c.fy, c.fz);
+        else v = eval_field_cell(load_field_cell(P, c.idx), c.fx, c.fy, c.fz);   // the corrector left the predictor's cell (rare)
+        w.vrg = v.rg; w.vb = v.b; w.va = v.a;
+    } else {
+        const FieldVal v2 = fetch_field_pk<LAYOUT, false>(P, lo2(p2), hi2(p2), w.qz + d1z);
+        const pk2_t d2 = mul2(fma2(two, v2.rg, mone), s2);
+        const float d2z = fmaf(2.0f, v2.b, -1.0f) * s1;
+        w.qxy = fma2(bc2(0.5f), add2(d1, d2), w.qxy);                      // newPos += 0.5 (licdir + licdir2)
+        w.qz = fmaf(0.5f, d1z + d2z, w.qz);
+        const FieldVal v = fetch_field_pk<LAYOUT, SOF>(P, lo2(w.qxy), hi2(w.qxy), w.qz);
+        w.vrg = v.rg; w.vb = v.b; w.va = v.a;
+    }
 }
 
 // computeLIC, inc_lic.glsl:152-202, scalar build.  The backward and forward walks are independent; they are
@@ -220,10 +239,10 @@ __device__ __forceinline__ float compute_lic_scalar(const DevParams &P, const fl
 }
 
 // computeLIC, USE_NOISE_GRADIENTS build: vec4 accumulation of raw RGBA noise texels (Q8)
-template <int LAYOUT, bool SOF, bool STRAIGHT = true>
+template <int LAYOUT, bool SOF, bool STRAIGHT = true, int NL = -1>
 __device__ __forceinline__ float4 compute_lic_grad(const DevParams &P, const float *s_kw, f3 pos, float4 centre)
 {
-    const Rgba2 c = fetch_noise_rgba_pk(P, pos.x, pos.y, pos.z);
+    const Rgba2 c = fetch_noise_rgba_pk<NL>(P, pos.x, pos.y, pos.z);
     const pk2_t w0 = bc2(s_kw[0]);
     pk2_t accBrg = pk2(0.f, 0.f), accBba = accBrg, accFrg = accBrg, accFba = accBrg;
     Walker wb = make_walker(pos, centre), wf = wb;
@@ -235,8 +254,8 @@ __device__ __forceinline__ float4 compute_lic_grad(const DevParams &P, const flo
         for (; k < nMin; ++k) {
             heun_step<LAYOUT, SOF>(P, wb, -P.h);
             heun_step<LAYOUT, SOF>(P, wf, P.h);
-            const Rgba2 tb = fetch_noise_rgba_pk(P, lo2(wb.qxy), hi2(wb.qxy), wb.qz);
-            const Rgba2 tf = fetch_noise_rgba_pk(P, lo2(wf.qxy), hi2(wf.qxy), wf.qz);
+            const Rgba2 tb = fetch_noise_rgba_pk<NL>(P, lo2(wb.qxy), hi2(wb.qxy), wb.qz);
+            const Rgba2 tf = fetch_noise_rgba_pk<NL>(P, lo2(wf.qxy), hi2(wf.qxy), wf.qz);
             const pk2_t wB = bc2(kwB[k]), wF = bc2(kwF[k]);
             accBrg = fma2(tb.rg, wB, accBrg);
             accBba = fma2(tb.ba, wB, accBba);
@@ -245,14 +264,14 @@ __device__ __forceinline__ float4 compute_lic_grad(const DevParams &P, const flo
         }
         for (; k < nB; ++k) {
             heun_step<LAYOUT, SOF>(P, wb, -P.h);
-            const Rgba2 t = fetch_noise_rgba_pk(P, lo2(wb.qxy), hi2(wb.qxy), wb.qz);
+            const Rgba2 t = fetch_noise_rgba_pk<NL>(P, lo2(wb.qxy), hi2(wb.qxy), wb.qz);
             const pk2_t w = bc2(kwB[k]);
             accBrg = fma2(t.rg, w, accBrg);
             accBba = fma2(t.ba, w, accBba);
         }
         for (; k < nF; ++k) {
             heun_step<LAYOUT, SOF>(P, wf, P.h);
-            const Rgba2 t = fetch_noise_rgba_pk(P, lo2(wf.qxy), hi2(wf.qxy), wf.qz);
+            const Rgba2 t = fetch_noise_rgba_pk<NL>(P, lo2(wf.qxy), hi2(wf.qxy), wf.qz);
             const pk2_t w = bc2(kwF[k]);
             accFrg = fma2(t.rg, w, accFrg);
             accFba = fma2(t.ba, w, accFba);
@@ -262,14 +281,14 @@ __device__ __forceinline__ float4 compute_lic_grad(const DevParams &P, const flo
         for (int k = 0; k < n; ++k) {
             if (k < nB) {
                 heun_step<LAYOUT, SOF>(P, wb, -P.h);
-                const Rgba2 t = fetch_noise_rgba_pk(P, lo2(wb.qxy), hi2(wb.qxy), wb.qz);
+                const Rgba2 t = fetch_noise_rgba_pk<NL>(P, lo2(wb.qxy), hi2(wb.qxy), wb.qz);
                 const pk2_t w = bc2(kwB[k]);
                 accBrg = fma2(t.rg, w, accBrg);
                 accBba = fma2(t.ba, w, accBba);
             }
             if (k < nF) {
                 heun_step<LAYOUT, SOF>(P, wf, P.h);
-                const Rgba2 t = fetch_noise_rgba_pk(P, lo2(wf.qxy), hi2(wf.qxy), wf.qz);
+                const Rgba2 t = fetch_noise_rgba_pk<NL>(P, lo2(wf.qxy), hi2(wf.qxy), wf.qz);
                 const pk2_t w = bc2(kwF[k]);
                 accFrg = fma2(t.rg, w, accFrg);
                 accFba = fma2(t.ba, w, accFba);
@@ -418,7 +437,7 @@ __device__ __forceinline__ void load_tables(const DevParams &P, SharedTables &S)
 
 // one ray sample of lic3d_fragment.glsl:44-81: vector fetch, TF, gate, computeLIC, illumination.
 // Returns false when the LIC gate skips the sample (src keeps its previous value in the shader).
-template <int LAYOUT, int ILLUM, bool NGATE, bool SOF>
+template <int LAYOUT, int ILLUM, bool NGATE, bool SOF, int NL = -1>
 __device__ __forceinline__ bool shade_sample(const DevParams &P, const SharedTables &S, f3 pos, f3 dir, float4 &src)
 {
     constexpr bool GRAD = (ILLUM == ILLUM_GRADIENT);   // ILLUM_GRADIENT => USE_NOISE_GRADIENTS, inc_header.glsl:17-19
@@ -429,7 +448,7 @@ __device__ __forceinline__ bool shade_sample(const DevParams &P, const SharedTab
     // gate :59-61 (scalarData.g > -0.0001 is always true for a LUMINANCE8 texture)
     if (P.gateMode == GATE_TF_ALPHA && !(tf.w > 0.05f)) return false;
     if (GRAD) {
-        float4 il = compute_lic_grad<LAYOUT, SOF>(P, S.kw, pos, vd);                // :64
+        float4 il = compute_lic_grad<LAYOUT, SOF, true, NL>(P, S.kw, pos, vd);                // :64
         il.w *= P.licScale;                                                         // :67
         src = illum_gradient(P, S.opac, il, tf, pos, dir);
     } else {
@@ -674,7 +693,8 @@ __global__ void __launch_bounds__(256) slice_setup_kernel(const __grid_constant_
     }
 }
 
-template <int LAYOUT, int ILLUM, bool NGATE, bool SOF>
+// NL: RGBA-noise layout of the gradient build as a compile-time parameter (the walk loop holds one sampler, not both)
+template <int LAYOUT, int ILLUM, bool NGATE, bool SOF, int NL>
 __global__ void __launch_bounds__(256, LIC_MIN_CTAS) lic_sample_kernel(const __grid_constant__ DevParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -724,7 +744,7 @@ __global__ void __launch_bounds__(256, LIC_MIN_CTAS) lic_sample_kernel(const __g
             }
         }
         if (!have) src = make_float4(0.f, 0.f, 0.f, -2.0f);                                                               // no fragment
-        else if (!shade_sample<LAYOUT, ILLUM, NGATE, SOF>(P, S, pos, dir, src)) src = make_float4(0.f, 0.f, 0.f, -1.0f);   // gated
+        else if (!shade_sample<LAYOUT, ILLUM, NGATE, SOF, NL>(P, S, pos, dir, src)) src = make_float4(0.f, 0.f, 0.f, -1.0f);   // gated
         const uint2 tr = P.tileRec[it.x];
         P.src[((size_t)tr.x + k) * 32 + lane] = src;
       }
@@ -974,17 +994,20 @@ __global__ void unblock_kernel(const float4 *__restrict__ tiles, int world, int 
 // ------------------------------------------------------------------------------------------------
 // launchers
 
+template <class K>
+static cudaError_t launch_with_tables(K kernel, const DevParams &P, int grid, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, 256, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
 template <int LAYOUT, int ILLUM, bool NGATE>
 static cudaError_t launch_raycast_sof(const DevParams &P, bool sof, int grid, size_t smem, cudaStream_t st)
 {
-    if (sof) {
-        cudaFuncSetAttribute(lic_raycast_kernel<LAYOUT, ILLUM, NGATE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        lic_raycast_kernel<LAYOUT, ILLUM, NGATE, true><<<grid, 256, smem, st>>>(P);
-    } else {
-        cudaFuncSetAttribute(lic_raycast_kernel<LAYOUT, ILLUM, NGATE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        lic_raycast_kernel<LAYOUT, ILLUM, NGATE, false><<<grid, 256, smem, st>>>(P);
-    }
-    return cudaGetLastError();
+    if (sof) return launch_with_tables(lic_raycast_kernel<LAYOUT, ILLUM, NGATE, true>, P, grid, smem, st);
+    return launch_with_tables(lic_raycast_kernel<LAYOUT, ILLUM, NGATE, false>, P, grid, smem, st);
 }
 
 template <int LAYOUT>
@@ -1027,48 +1050,48 @@ cudaError_t launch_composite(const DevParams &P, int grid, cudaStream_t st)
     return cudaGetLastError();
 }
 
-// persistent grid: (resident CTAs per SM of this instantiation) x (SM count), capped by ctas_per_sm
-template <class K>
-static int persistent_ctas(K kernel, size_t smem, int num_sms_times_cap)
-{
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem) != cudaSuccess || occ < 1) occ = 1;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int cap = num_sms_times_cap > 0 ? num_sms_times_cap / sms : occ;
-    return sms * (cap > 0 && cap < occ ? cap : occ);
-}
-
 // Ask for the smallest shared-memory carve-out that still holds the resident CTAs' tables, so the rest of the unified
 // 256 KB array serves as L1 (the driver's default picked 102 KB of shared memory for 3 x 14 KB; ncu
 // launch__shared_mem_config_size).  The gathers of this kernel live on L1 hits.
 template <class K>
-static int prefer_l1(K kernel, size_t smem)
+static cudaError_t prefer_l1(K kernel, size_t smem, int *occ_out = nullptr)
 {
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem) != cudaSuccess || occ < 1) occ = 1;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
     const size_t need = (size_t)occ * (smem + 1024);                 // + 1 KB per CTA reserved by the driver
     int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
     if (pct > 100) pct = 100;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    return occ;
+    if (occ_out) *occ_out = occ;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
+template <class K>
+static cudaError_t launch_sample_kernel(K kernel, const DevParams &P, int grid, size_t smem, cudaStream_t st)
+{
+    int dev = 0, sms = 148;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = prefer_l1(kernel, smem, &occ);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid > 0 ? grid : sms * occ, 256, smem, st>>>(P);
+    return cudaGetLastError();
 }
 
 template <int LAYOUT, int ILLUM, bool NGATE>
 static cudaError_t launch_sample_sof(const DevParams &P, bool sof, int grid, size_t smem, cudaStream_t st)
 {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sof) {
-        const int g = sms * prefer_l1(lic_sample_kernel<LAYOUT, ILLUM, NGATE, true>, smem);
-        lic_sample_kernel<LAYOUT, ILLUM, NGATE, true><<<grid > 0 ? grid : g, 256, smem, st>>>(P);
-    } else {
-        const int g = sms * prefer_l1(lic_sample_kernel<LAYOUT, ILLUM, NGATE, false>, smem);
-        lic_sample_kernel<LAYOUT, ILLUM, NGATE, false><<<grid > 0 ? grid : g, 256, smem, st>>>(P);
+    // only the gradient build samples the RGBA noise; its check layout (u8 quads) gets its own instantiation
+    if (ILLUM == ILLUM_GRADIENT && !P.noise_pair) {
+        constexpr int NL = (ILLUM == ILLUM_GRADIENT) ? 0 : 1;
+        if (sof) return launch_sample_kernel(lic_sample_kernel<LAYOUT, ILLUM, NGATE, true, NL>, P, grid, smem, st);
+        return launch_sample_kernel(lic_sample_kernel<LAYOUT, ILLUM, NGATE, false, NL>, P, grid, smem, st);
     }
-    return cudaGetLastError();
+    if (sof) return launch_sample_kernel(lic_sample_kernel<LAYOUT, ILLUM, NGATE, true, 1>, P, grid, smem, st);
+    return launch_sample_kernel(lic_sample_kernel<LAYOUT, ILLUM, NGATE, false, 1>, P, grid, smem, st);
 }
 
 template <int LAYOUT>
@@ -1105,27 +1128,24 @@ cudaError_t launch_lic_raycast(const DevParams &P, int layout, int illum, bool n
 cudaError_t launch_volume_raycast(const DevParams &P, int layout, int grid, cudaStream_t st)
 {
     const size_t smem = table_bytes(P);
-    if (layout == LAYOUT_PAIR) {
-        cudaFuncSetAttribute(volume_raycast_kernel<LAYOUT_PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        volume_raycast_kernel<LAYOUT_PAIR><<<grid, 256, smem, st>>>(P);
-    } else {
-        cudaFuncSetAttribute(volume_raycast_kernel<LAYOUT_F4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        volume_raycast_kernel<LAYOUT_F4><<<grid, 256, smem, st>>>(P);
-    }
+    if (layout == LAYOUT_PAIR) return launch_with_tables(volume_raycast_kernel<LAYOUT_PAIR>, P, grid, smem, st);
+    return launch_with_tables(volume_raycast_kernel<LAYOUT_F4>, P, grid, smem, st);
+}
+
+template <class K>
+static cudaError_t launch_licvol_kernel(K kernel, const DevParams &P, int grid, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = prefer_l1(kernel, smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, 256, smem, st>>>(P);
     return cudaGetLastError();
 }
 
 template <int LAYOUT, bool GRAD, bool NGATE>
 static cudaError_t launch_licvol_sof(const DevParams &P, bool sof, int grid, size_t smem, cudaStream_t st)
 {
-    if (sof) {
-        prefer_l1(lic_volume_kernel<LAYOUT, GRAD, NGATE, true>, smem);
-        lic_volume_kernel<LAYOUT, GRAD, NGATE, true><<<grid, 256, smem, st>>>(P);
-    } else {
-        prefer_l1(lic_volume_kernel<LAYOUT, GRAD, NGATE, false>, smem);
-        lic_volume_kernel<LAYOUT, GRAD, NGATE, false><<<grid, 256, smem, st>>>(P);
-    }
-    return cudaGetLastError();
+    if (sof) return launch_licvol_kernel(lic_volume_kernel<LAYOUT, GRAD, NGATE, true>, P, grid, smem, st);
+    return launch_licvol_kernel(lic_volume_kernel<LAYOUT, GRAD, NGATE, false>, P, grid, smem, st);
 }
 
 cudaError_t launch_lic_volume(const DevParams &P, int layout, bool grad, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st)
