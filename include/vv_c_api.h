@@ -86,10 +86,10 @@ typedef enum VVOption {
     VV_OPT_SAMPLE_MAP = 11,        /* 1: keep per-pixel ray-sample counts (vv_read_sample_map) */
     VV_OPT_RAYCAST_MODE = 12,      /* 1 (default): sample-parallel pipeline; 0: one thread per ray (cross-check) */
     VV_OPT_LIC_CTAS_PER_SM = 13,   /* persistent CTAs per SM of the lic_sample kernel (0 = default: all resident) */
-    VV_OPT_ITEM_CHUNK = 14,        /* experiment knob (unused) */
+    VV_OPT_WALK_FAST_PATHS = 14,   /* 1 (default): unclamped walk inside the field's guard band + shared field / noise cell coordinates where they apply; 0: the clamping samplers (check; same frames) */
     VV_OPT_DEPTH_MAJOR = 15,       /* 1 (default): work items ordered band-major / depth-major for L2 locality; 0: tile-major */
     VV_OPT_BAND_ROWS = 16,         /* 16-pixel block rows per band of the depth-major order (default 4) */
-    VV_OPT_NOISE_LAYOUT = 17       /* RGBA (-g) noise: 1 (default) fp16 x-pair, 0 u8 xy-quad; same values, same frames */
+    VV_OPT_NOISE_LAYOUT = 17       /* RGBA (-g) noise: 2 (default) bf16 {t0, t1 - t0}, 1 fp16 x-pair, 0 u8 xy-quad; same values, same frames */
 } VVOption;
 
 /* ---- lifecycle: Renderer() / init / resize / ~Renderer, VV/renderer.h:31-37 ------------------- */
@@ -295,6 +295,10 @@ VV_API int vv_get_tile_buffer(VVRenderer *r, void **dev_ptr, int *n_local_blocks
 /* assemble a row-major frame on this handle from `world` gathered tile buffers laid out [rank][block][256][4] */
 VV_API int vv_assemble_tiles(VVRenderer *r, const void *gathered_dev, int world);
 VV_API int vv_get_lic_volume_ptr(VVRenderer *r, void **dev_ptr, int dims_out[3]);
+/* Diagnostic: one direction (dir_sign < 0 backward, else forward) of computeLIC's streamline walk (inc_lic.glsl:104-145) from the
+ * texture-space position pos, with the device functions of the hot path; out[16 i ..] = (newPos.xyz, step.rgb, noise tap, kernel
+ * weight, Pos2.xyz, step2.rgb, 0, 0) of step i.  walk_variant: 0 clamping samplers, 1 guard band, 3 guard band + shared field / noise cell. */
+VV_API int vv_debug_walk(VVRenderer *r, const float pos[3], int dir_sign, int n_steps, int walk_variant, float *out, size_t out_bytes);
 /* Peer-to-peer frame exchange for one process per GPU on one NVLink / NVSwitch node (no reference counterpart: the
  * reference is single-GPU).  Instead of gathering tile buffers with a collective, vv_p2p_render stores this rank's
  * finished tiles straight into every rank's gather buffer over NVLink, signals arrival with system-scope atomics, waits

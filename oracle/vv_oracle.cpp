@@ -46,7 +46,7 @@ inline float half_round(float x) { return (float)(_Float16)x; }
 /* ---- GL samplers (GL 2.1 spec 3.8.8) ----------------------- */
 enum Wrap { CLAMP_TO_EDGE, REPEAT, CLAMP_BORDER /* GL_CLAMP, border colour 0 */ };
 
-struct Axis { int i0, i1; float f; bool b0, b1; /* b*: texel is border */ };
+struct Axis { int i0, i1; float f; bool b0, b1; /* b*: texel is border */ bool fused; /* weight_bits == -1, see lerp_axis */ };
 
 inline float quant_weight(float f, int bits)
 {
@@ -63,7 +63,11 @@ inline Axis axis_linear(float s, int n, Wrap wrap, int weight_bits)
         s = s - std::floor(s);           /* REPEAT ignores the integer part of s */
     else if (wrap == CLAMP_BORDER)
         s = clampf(s, 0.0f, 1.0f);       /* GL_CLAMP clamps s to [0,1] */
-    float u = s * (float)n - 0.5f;
+    a.fused = (weight_bits == -1);
+    /* weight_bits == -1: the same filtering rule with fused multiply-adds -- u = fma(s, n, -0.5) and a + f (b - a) as sub + fma (one
+     * rounding fewer each) -- which is the "fp32 software trilinear interpolation" the CUDA path implements.  GL leaves the rounding of
+     * the filter arithmetic to the implementation; the default (0) is the formula as the specification writes it. */
+    float u = a.fused ? std::fmaf(s, (float)n, -0.5f) : s * (float)n - 0.5f;
     float fl = std::floor(u);
     a.f = quant_weight(u - fl, weight_bits);
     int i0 = (int)fl, i1 = i0 + 1;
@@ -88,6 +92,7 @@ inline Axis axis_linear(float s, int n, Wrap wrap, int weight_bits)
 }
 
 inline float lerp_gl(float a, float b, float f) { return (1.0f - f) * a + f * b; }
+inline float lerp_axis(float a, float b, const Axis &ax) { return ax.fused ? std::fmaf(ax.f, b - a, a) : lerp_gl(a, b, ax.f); }
 
 /* generic trilinear fetch: C channels, texel decode by functor */
 template <int C, class Fetch>
@@ -103,13 +108,13 @@ inline void trilinear(const int dim[3], float sx, float sy, float sz, Wrap wrap,
             for (int i = 0; i < 2; ++i)
                 fetch(xs[i], ys[j], zs[k], t[k][j][i]);
     for (int c = 0; c < C; ++c) {
-        float x00 = lerp_gl(t[0][0][0][c], t[0][0][1][c], ax.f);
-        float x10 = lerp_gl(t[0][1][0][c], t[0][1][1][c], ax.f);
-        float x01 = lerp_gl(t[1][0][0][c], t[1][0][1][c], ax.f);
-        float x11 = lerp_gl(t[1][1][0][c], t[1][1][1][c], ax.f);
-        float y0 = lerp_gl(x00, x10, ay.f);
-        float y1 = lerp_gl(x01, x11, ay.f);
-        out[c] = lerp_gl(y0, y1, az.f);
+        float x00 = lerp_axis(t[0][0][0][c], t[0][0][1][c], ax);
+        float x10 = lerp_axis(t[0][1][0][c], t[0][1][1][c], ax);
+        float x01 = lerp_axis(t[1][0][0][c], t[1][0][1][c], ax);
+        float x11 = lerp_axis(t[1][1][0][c], t[1][1][1][c], ax);
+        float y0 = lerp_axis(x00, x10, ay);
+        float y1 = lerp_axis(x01, x11, ay);
+        out[c] = lerp_axis(y0, y1, az);
     }
 }
 
@@ -136,7 +141,7 @@ inline V4 texVolume(const Ctx &c, V3 p)
     const float *T = s->vec;
     const int *d = s->vdim;
     float o[4];
-    trilinear<4>(d, p.x, p.y, p.z, CLAMP_TO_EDGE, 0,
+    trilinear<4>(d, p.x, p.y, p.z, CLAMP_TO_EDGE, s->weight_bits < 0 ? -1 : 0,   /* (the 8-bit weight model is not applied to fp16 textures) */
                  [&](int x, int y, int z, float *t) {
                      const float *q = T + 4 * (((size_t)z * d[1] + y) * d[0] + x);
                      t[0] = q[0]; t[1] = q[1]; t[2] = q[2]; t[3] = q[3];
@@ -537,12 +542,13 @@ inline float freqSampling(const Ctx &c, V3 pos)
 
 /* singleLICstep, inc_lic.glsl:93-145.  GRAD selects the USE_NOISE_GRADIENTS build. */
 template <bool GRAD>
-inline V4 singleLICstep(const Ctx &c, V3 licdir, V3 &newPos, V4 &step, float kernelOffset, float logEyeDist, float dir)
+inline V4 singleLICstep(const Ctx &c, V3 licdir, V3 &newPos, V4 &step, float kernelOffset, float logEyeDist, float dir, float *dbg = nullptr)
 {
     if (c.s->speed_of_flow) licdir = licdir * step.w;                    /* :108-110 */
     licdir = licdir * (c.licParams[2] * (logEyeDist * 0.5f + 0.3f));      /* :114 */
     V3 Pos2 = newPos + licdir;                                            /* :115 */
     V4 step2 = texVolume(c, Pos2);                                        /* :116 */
+    if (dbg) { dbg[0] = Pos2.x; dbg[1] = Pos2.y; dbg[2] = Pos2.z; dbg[3] = step2.x; dbg[4] = step2.y; dbg[5] = step2.z; }   /* vvo_debug_walk */
     V3 licdir2 = 2.0f * rgb(step2) - V3{1.0f, 1.0f, 1.0f};               /* :117 */
     licdir2 = licdir2 * dir;                                              /* :118 */
     if (c.s->speed_of_flow) licdir2 = licdir2 * step.w;                   /* :120-122 */
@@ -1020,6 +1026,28 @@ void vvo_compute_lic(const VVOScene *s, const float pos[3], float out[4])
     V4 v = texVolume(c, p);
     V4 l = (s->illum_mode == VVO_ILLUM_GRADIENT) ? computeLIC<true>(c, p, v) : computeLIC<false>(c, p, v);
     out[0] = l.x; out[1] = l.y; out[2] = l.z; out[3] = l.w;
+}
+
+/* one direction of computeLIC's walk from pos, step by step: out[16 i ..] = (newPos.xyz, step.rgb, noise tap, kernel weight, Pos2.xyz, step2.rgb, 0, 0) */
+void vvo_debug_walk(const VVOScene *s, const float pos[3], int dir_sign, int nsteps, float *out)
+{
+    Ctx c;
+    make_ctx(s, c);
+    V3 p = {pos[0], pos[1], pos[2]}, newPos = p;
+    V4 step = texVolume(c, p);
+    const float dir = dir_sign < 0 ? -1.0f : 1.0f;
+    float kernelOffset = 0.5f;
+    for (int i = 0; i < nsteps; ++i) {
+        V3 licdir = dir < 0 ? -2.0f * rgb(step) + V3{1.0f, 1.0f, 1.0f} : 2.0f * rgb(step) - V3{1.0f, 1.0f, 1.0f};
+        kernelOffset += dir < 0 ? -c.licKernel[1] : c.licKernel[0];
+        V4 n = (s->illum_mode == VVO_ILLUM_GRADIENT) ? singleLICstep<true>(c, licdir, newPos, step, kernelOffset, 0.0f, dir, out + 16 * i + 8)
+                                                     : singleLICstep<false>(c, licdir, newPos, step, kernelOffset, 0.0f, dir, out + 16 * i + 8);
+        const float kw = texKernel(c, kernelOffset);
+        out[16 * i] = newPos.x; out[16 * i + 1] = newPos.y; out[16 * i + 2] = newPos.z;
+        out[16 * i + 3] = step.x; out[16 * i + 4] = step.y; out[16 * i + 5] = step.z;
+        out[16 * i + 6] = (kw != 0.0f) ? n.w / kw : 0.0f; out[16 * i + 7] = kw;
+        out[16 * i + 14] = out[16 * i + 15] = 0.0f;
+    }
 }
 
 /* background_fragment.glsl:9-16 */

@@ -69,7 +69,8 @@ typedef struct VVOScene {
     int quirk_luminance_alpha; /* Q7 */
     int speed_of_flow;         /* inc_lic.glsl:108-110,120-122 */
     int licvol_fp16;           /* Q14: LIC volume stored as RGBA16F */
-    int weight_bits;           /* 0: exact fp32 lerp weights; 8: quantise f to 8 fractional bits (B.6) */
+    int weight_bits;           /* 0: exact fp32 lerp weights, filter formula as GL 2.1 3.8.8 writes it; 8: quantise f to 8 fractional bits
+                                * (B.6); -1: exact weights, 3-D filtering with fused multiply-adds (u = fma(s,n,-.5), a + f (b - a) as sub + fma) */
     /* SURVEY 8(f) N4 */
     const float *mc_offsets;   /* USE_MC_OFFSET (lic3d_fragment.glsl:31-33, renderer.cpp:636-679): [height][width] ray-start
                                   offsets in [0,1], already fp16-rounded (GL_LUMINANCE16F rectangle texture); NULL = off */
@@ -113,6 +114,8 @@ void vvo_slicing_setup(const VVOScene *s, float *out5);
 int vvo_slice_fragments(const VVOScene *s, int x, int y, float *out_xyzv, int cap);
 /* one computeLIC (inc_lic.glsl:152-202) at pos; out[4] */
 void vvo_compute_lic(const VVOScene *s, const float pos[3], float out[4]);
+/* one direction of the walk, step by step: out[16 i ..] = (newPos.xyz, step.rgb, weighted tap / weight, kernel weight, Pos2.xyz, step2.rgb, 0, 0) */
+void vvo_debug_walk(const VVOScene *s, const float pos[3], int dir_sign, int nsteps, float *out);
 /* background_fragment.glsl:7-20 and the RGBA8 store (renderer.cpp:216-226) */
 void vvo_background(const float *rgba, int n_pixels, float *out);
 /* the same pass over a WINDOW of ww x wh pixels showing a stored frame of rw x rh (low-res preset: rw = ww/2, rh = wh/2):

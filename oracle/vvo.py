@@ -60,6 +60,7 @@ def lib():
         L.vvo_lic_volume.argtypes = [S, I, I, I, I, I, P]; L.vvo_lic_volume.restype = None
         L.vvo_raycast_licvolume.argtypes = [S, P, P]; L.vvo_raycast_licvolume.restype = U64
         L.vvo_compute_lic.argtypes = [S, P, P]; L.vvo_compute_lic.restype = None
+        L.vvo_debug_walk.argtypes = [S, P, ctypes.c_int, ctypes.c_int, P]; L.vvo_debug_walk.restype = None
         L.vvo_slicing_lic.argtypes = [S, P, P]; L.vvo_slicing_lic.restype = U64
         L.vvo_slicing_setup.argtypes = [S, P]
         L.vvo_slice_fragments.argtypes = [S, I, I, P, I]; L.vvo_slice_fragments.restype = I
@@ -303,6 +304,12 @@ class OracleScene:
     def compute_lic(self, pos):
         out = np.zeros(4, dtype=np.float32)
         lib().vvo_compute_lic(ctypes.byref(self.c), _p(np.asarray(pos, dtype=np.float32)), _p(out))
+        return out
+
+    def debug_walk(self, pos, dir_sign, nsteps):
+        """one direction of computeLIC's walk: rows (newPos.xyz, step.rgb, noise tap, kernel weight, Pos2.xyz, step2.rgb, 0, 0)"""
+        out = np.zeros((nsteps, 16), dtype=np.float32)
+        lib().vvo_debug_walk(ctypes.byref(self.c), _p(np.asarray(pos, dtype=np.float32)), int(dir_sign), int(nsteps), _p(out))
         return out
 
     def uniforms(self):

@@ -23,8 +23,8 @@ if "mode" in opts:
     r.setOption(vv.OPT_RAYCAST_MODE, int(opts["mode"]))
 if "layout" in opts:
     r.setOption(vv.OPT_FIELD_LAYOUT, int(opts["layout"]))
-if "chunk" in opts:
-    r.setOption(vv.OPT_ITEM_CHUNK, int(opts["chunk"]))
+if "xf" in opts:
+    r.setOption(vv.OPT_WALK_FAST_PATHS, int(opts["xf"]))
 if "depthmajor" in opts:
     r.setOption(vv.OPT_DEPTH_MAJOR, int(opts["depthmajor"]))
 if "band" in opts:

@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, 'vectorvisualization_b200', 'libvv_b200.so')
-pat = sys.argv[2] if len(sys.argv) > 2 else "lic_sample_kernelILi1ELi1ELb0ELb0ELi1E"
+pat = sys.argv[2] if len(sys.argv) > 2 else "lic_sample_kernelILi1ELi1ELb0ELb0ELi2E"
 
 
 def stats(lib, pat):

@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -141,37 +142,21 @@ def test_synthetic_generators_are_deterministic():
 
 
 def test_hot_kernel_resources_and_instruction_mix(vv):
-    """static guard on the shipped lic_sample_kernel<x-pair layout, gradient build> (what DESIGN.md section 5 measures): 64
-    registers (4 CTAs x 256 threads per SM), no spill traffic inside the walk loop, and the sm_100a instructions the design
-    relies on -- FHADD (f32 = f16 + f32) for the fp16 texels, packed FFMA2 / FADD2 lerps, 128-bit loads"""
-    name = "_ZN6vvb20017lic_sample_kernelILi1ELi1ELb0ELb0EEEvNS_9DevParamsE"
-    res = subprocess.run(["cuobjdump", "-res-usage", vv.LIB_PATH], capture_output=True, text=True).stdout
-    lines = res.splitlines()
-    i = next(k for k, l in enumerate(lines) if name in l)
-    usage = lines[i + 1]
-    assert "REG:64" in usage.replace(" ", ""), usage
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", name, vv.LIB_PATH], capture_output=True, text=True).stdout
-    ins = []
-    for l in sass.splitlines():
-        l = l.strip()
-        if l.startswith("/*") and ";" in l:
-            addr, rest = l[2:].split("*/", 1)
-            ins.append((int(addr, 16), rest.split(";")[0].strip()))
-    assert len(ins) > 2000
-    # the walk loop = the largest backward branch that is not the persistent work loop (second largest overall)
-    loops = []
-    for a, t in ins:
-        if "BRA" in t and "0x" in t:
-            tgt = int(t.split("0x")[-1].split()[0].rstrip(","), 16)
-            if tgt < a:
-                loops.append((a - tgt, tgt, a))
-    loops.sort(reverse=True)
-    _, lo, hi = loops[1]
-    body = [t for a, t in ins if lo <= a <= hi]
-    ops = [t.split()[1] if t.startswith("@") else t.split()[0] for t in body]
-    count = lambda p: sum(1 for o in ops if o.split(".")[0] == p)
-    assert 500 < len(body) < 900
-    assert count("FHADD") == 160                     # one per fp16 texel: 4 field fetches x 24 + 2 noise fetches x 32
-    assert count("FFMA2") >= 90 and count("FADD2") >= 60
-    assert count("STL") == 0 and count("LDL") == 0   # no spills in the loop
-    assert sum(1 for o in ops if o.startswith("LDG.E.128")) >= 24
+    """static guard on the shipped lic_sample_kernel<x-pair field, gradient build, bf16 noise, guard band + shared cell> (what DESIGN.md
+    section 5 measures): 64 registers (4 CTAs x 256 threads per SM) and the sm_100a instructions the design relies on -- FHADD
+    (f32 = f16 + f32) for the fp16 field texels, packed FFMA2 / FADD2 lerps, PRMT widening of the bf16 noise, 128-bit loads, no
+    index clamps (FMNMX) in the walk"""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from sass_loop_stats import stats
+    o = stats(vv.LIB_PATH, "lic_sample_kernelILi1ELi1ELb0ELb0ELi2ELi3E")
+    assert "REG:64" in o["usage"].replace(" ", ""), o["usage"]
+    assert o["total"] > 2000
+    loop = o["loops"][0]                              # the walk loop: one backward + one forward Heun step and their two noise taps
+    ops = loop["ops"]
+    assert 450 < loop["n"] < 620, loop["n"]
+    assert ops.get("FHADD", 0) == 96                  # 24 per field cell; 2 cells per Heun step in the code (the second only when the corrector leaves the predictor's cell)
+    assert ops.get("PRMT", 0) >= 64                   # 2 noise taps x 4 rows x 4 words x 2 halves
+    assert ops.get("FFMA2", 0) >= 90 and ops.get("FADD2", 0) >= 36
+    assert ops.get("FMNMX", 0) == 0                   # guard band: no coordinate clamp in the walk
+    assert ops.get("LDG", 0) >= 24
+    assert ops.get("STL", 0) <= 4 and ops.get("LDL", 0) <= 4   # at most the two walker positions parked across the rare reload path

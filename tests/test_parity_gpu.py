@@ -808,18 +808,19 @@ def test_item_order_does_not_change_the_frame(vv):
 
 
 def test_noise_layouts_bit_identical(vv):
-    """RGBA (-g) noise as fp16 x-pairs (FHADD lerps) vs u8 xy-quads (PRMT decode): same values, same frames"""
+    """RGBA (-g) noise as bf16 {t0, t1 - t0} (PRMT widening, the hot layout), as fp16 x-pairs (FHADD lerps) and as u8 xy-quads
+    (PRMT decode): same values, same operations on them, same frames"""
     from vectorvisualization_b200 import configs
     from vectorvisualization_b200.configs import apply_scene
     s = configs.cfg3(n=48, size=128)
     out = []
-    for layout in (1, 0):
+    for layout in (2, 1, 0):
         r = vv.Renderer(0)
         r.setOption(vv.OPT_NOISE_LAYOUT, layout)
         apply_scene(r, s)
         r.render(True)
         out.append(r.readRGBA32F())
-    assert np.array_equal(out[0], out[1])
+    assert np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[2])
 
 
 def _golden_chain_names():

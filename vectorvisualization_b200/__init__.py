@@ -24,7 +24,7 @@ TF_B, TF_A, TF_R, TF_LENGTH, TF_SCALAR = range(5)
 GATE_ALWAYS, GATE_TF_ALPHA = 0, 1
 (OPT_TF_MODE, OPT_GATE_MODE, OPT_NOISE_GATE, OPT_QUIRK_SCALEVOLINV, OPT_QUIRK_LUMINANCE_ALPHA, OPT_LICVOL_FP16,
  OPT_FIELD_LAYOUT, OPT_COUNT_SAMPLES, OPT_LICVOL_SIZE, OPT_SPEC_EXP, OPT_SAMPLE_MAP, OPT_RAYCAST_MODE,
- OPT_LIC_CTAS_PER_SM, OPT_ITEM_CHUNK, OPT_DEPTH_MAJOR, OPT_BAND_ROWS, OPT_NOISE_LAYOUT) = range(1, 18)
+ OPT_LIC_CTAS_PER_SM, OPT_WALK_FAST_PATHS, OPT_DEPTH_MAJOR, OPT_BAND_ROWS, OPT_NOISE_LAYOUT) = range(1, 18)
 LAYOUT_F4, LAYOUT_PAIR = 0, 1
 BLOCK = 16  # pixels per image-block edge (sort-first partition unit)
 
@@ -176,6 +176,7 @@ def load_library():
         "vv_get_tile_buffer": ([P, ctypes.POINTER(P), ctypes.POINTER(I), ctypes.POINTER(I)], I),
         "vv_assemble_tiles": ([P, P, I], I), "vv_get_lic_volume_ptr": ([P, ctypes.POINTER(P), ctypes.POINTER(I)], I),
         "vv_set_stream": ([P, P], I),
+        "vv_debug_walk": ([P, P, I, I, I, P, ctypes.c_size_t], I),
         "vv_p2p_export": ([P, P, ctypes.POINTER(P)], I), "vv_p2p_connect": ([P, P, ctypes.POINTER(P), I], I),
         "vv_p2p_render": ([P], I), "vv_p2p_status": ([P], I), "vv_p2p_disconnect": ([P], I),
         "vv_parse_dat": ([CP, ctypes.POINTER(DatInfo)], I), "vv_read_raw": ([ctypes.POINTER(DatInfo), I, P, ctypes.c_size_t], I),
@@ -493,6 +494,14 @@ class Renderer:
         _chk(self._lib.vv_get_lic_volume_ptr(self._h, ctypes.byref(ptr), dims))
         out = np.empty((dims[2], dims[1], dims[0]), dtype=np.float32)
         _chk(self._lib.vv_read_lic_volume(self._h, _ptr(out), out.nbytes, dims))
+        return out
+
+    def debugWalk(self, pos, dir_sign, n_steps, variant=0):
+        """one direction of the LIC walk from a texture-space position: rows (newPos.xyz, step.rgb, noise tap, kernel weight,
+        Pos2.xyz, step2.rgb, 0, 0)"""
+        out = np.zeros((n_steps, 16), dtype=np.float32)
+        p = np.asarray(pos, dtype=np.float32)
+        _chk(self._lib.vv_debug_walk(self._h, _ptr(p), int(dir_sign), int(n_steps), int(variant), _ptr(out), out.nbytes))
         return out
 
     def readFieldTexture(self, shape):

@@ -1,7 +1,7 @@
 // vv_device.cuh -- parameter block shared by host and device, and the software samplers.
 //
 // Data layout in HBM (see DESIGN.md "Layouts"):
-//   vector field   LAYOUT_PAIR : uint4 [z][y][x] = { half4 T[x], half4 T[min(x+1,nx-1)] }   16 B/voxel
+//   vector field   LAYOUT_PAIR : uint4 [z][y][x] = { half4 T[x], half4 T[min(x+1,nx-1)] }   16 B/voxel, G guard cells per side
 //                  LAYOUT_F4   : float4 [z][y][x]                                             16 B/voxel
 //                  T = the reference's RGBA16F texture contents (VV/dataset.cpp:290-366): rgb = 0.5 v/|v| + 0.5,
 //                  a = |v|/max|v|, rounded to fp16 -- so both layouts hold the same values.
@@ -33,11 +33,17 @@ constexpr int kMaxLicSteps = 1024;   // per direction (weights live in shared me
 
 struct DevParams {
     // ---- textures ----
-    const uint4  *field_pair;     // padded [nz+1][ny+1][nx] (edge replicated): neighbours are +fRow / +fPlane, no index clamp
+    const uint4  *field_pair;     // padded [nz+2G][ny+2G][nx+2G] (edge replicated, G = fGuard >= 1), pointing at cell (0,0,0): neighbours are
+                                  // +fRow / +fPlane, no index clamp; cells [-G, n-1+G] are addressable (signed element offsets)
     const float4 *field_f4;
     int fnx, fny, fnz;
     float fnf[3], fnm1f[3];       // (float)n and (float)(n-1) per axis: no I2FP of loop invariants in the walk
     unsigned int fRow, fPlane;    // element strides of field_pair
+    int fGuard;                   // guard cells around the field; the unclamped samplers (XF_GUARD) need every walk position inside it
+    int guardOk;                  // the host checked that fGuard covers this frame's longest walk (else the clamped samplers run)
+    int noiseSameDims;            // RGBA noise has the field's dimensions: its cell coordinates inside [0,1)^3 are the field's (XF_NSHARE)
+    int noiseShared;              // ... and noise_bf is stored with the field's guard geometry: the field's cell index addresses it
+    float walkReach;              // (S + 2) h: a walk started at least this far inside [0,1)^3 never leaves it
     const uint2  *scalar_cell;
     int snx, sny, snz;
     float snf[3], snm1f[3];
@@ -46,9 +52,11 @@ struct DevParams {
     const uint2  *noise_cell;     // scalar noise (LUMINANCE / .a channel), cell8, padded [nz+1][ny+1][nx+1]
     const uint4  *noise_quad;     // RGBA noise (gradient build), u8 xy-quad layout (unpadded check layout)
     const uint4  *noise_pair;     // RGBA noise as fp16 x-pairs {half4 T[x], half4 T[x+1]} padded [nz+2][ny+2][nx+1] (used when non-null)
+    const uint4  *noise_bf;       // RGBA noise as bf16 {T[x], T[x+1] - T[x]} (bytes and their differences are exact in bf16), same padding
     int nnx, nny, nnz;
     float nnf[3];
     int ncRow, ncPlane, npRow, npPlane;   // element strides of noise_cell / noise_pair
+    int nbRow, nbPlane;                   // element strides of noise_bf
     const float  *licvol;         // fp32 scalar LIC volume, sampled REPEAT
     int lnx, lny, lnz;
     const float4 *tf_rgba;        // [256]
@@ -90,7 +98,6 @@ struct DevParams {
     uint2  *items, *itemsNext;       // work items (tile, k) of the current / next depth window
     unsigned int *itemCount, *itemCountNext, *itemHead, *slotAlloc, *nMaxGlobal;
     int win0, win1, win2;            // current window [win0, win1), next window ends at win2
-    int itemChunk;                   // (experiment knob, unused by the shipped kernel)
     // depth-major item order: buckets = (band of block rows) x (chunk of 8 depths)
     unsigned int *bucketCount, *bucketBase, *bucketFill;
     int bandRows, nDepthChunks;
@@ -188,6 +195,9 @@ __device__ __forceinline__ pk2_t add2(pk2_t a, pk2_t b) { pk2_t d; asm("add.rn.f
 __device__ __forceinline__ pk2_t sub2(pk2_t a, pk2_t b) { pk2_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ pk2_t mul2(pk2_t a, pk2_t b) { pk2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ pk2_t bc2(float f) { return pk2(f, f); }
+// a * b that ptxas cannot contract into a following add: it fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (unlike the scalar .rn
+// forms, which it treats conservatively), which moves a rounding.  x * y + (+0) rounds exactly like x * y.
+__device__ __forceinline__ pk2_t mul2_keep(pk2_t a, pk2_t b) { return fma2(a, b, pk2(0.0f, 0.0f)); }
 // a + f (b - a) in both lanes: the same sub + fma as lerpf()
 __device__ __forceinline__ pk2_t lerp2(pk2_t a, pk2_t b, pk2_t f) { return fma2(f, sub2(b, a), a); }
 __device__ __forceinline__ pk2_t h2pk(unsigned int w) { float2 t = h2f(w); return pk2(t.x, t.y); }
@@ -293,20 +303,41 @@ __device__ __forceinline__ float4 fetch_field(const DevParams &P, float px, floa
 // of a voxel wherever the field is smooth, so both almost always lie in the same trilinear cell: the 4 LDG.128, the address
 // arithmetic and the 24 fp16 -> fp32 widenings (FHADD) are done once per cell and only the lerps are evaluated twice.
 // The operations on the texel values are exactly those of fetch_field_pk<LAYOUT_PAIR, false> (same bits).
-struct CellCoord { unsigned int idx; float fx, fy, fz; };
+struct CellCoord { int idx; float fx, fy, fz; };
 struct FieldCell {
     pk2_t rg0[4], rgd[4];   // corner rows A = (y0,z0), B = (y1,z0), C = (y0,z1), D = (y1,z1): (r,g) of texel x0, and texel x0+1 minus it
     pk2_t b0[2], bd[2];     // blue with the two z planes packed: [0] = rows (A, C), [1] = rows (B, D)
 };
 
+// compile-time options of the walk's coordinate arithmetic (template parameter XF of the sample kernel)
+enum { XF_GUARD = 1,     // field coordinates without the CLAMP_TO_EDGE clamp: the layout's guard band replicates the edge texels, so
+                         // t0 + f (t1 - t0) with t1 == t0 returns the edge value exactly as the clamped f = 0 does (host guarantees the
+                         // band covers every position a walk can reach)
+       XF_NSHARE = 2,    // gradient build, noise dimensions == field dimensions and noise_bf stored with the field's guard geometry:
+                         // for a position inside [0,1)^3 REPEAT leaves the coordinate untouched, so the noise cell index and weights
+                         // ARE the field's (same expression u = s n - 0.5, floor, fraction: same bits).  Used for ray samples whose
+                         // whole walk stays inside [0,1)^3 (warp-uniform interior test, DevParams::walkReach); other warps take the
+                         // REPEAT rule
+       XF_SSHARE = 4 };  // scalar builds, scalar-volume dimensions == field dimensions: the band gate's cell index / weights are the field's
+
+template <bool GUARD>
 __device__ __forceinline__ CellCoord field_cell_coord(const DevParams &P, float px, float py, float pz)
 {
     CellCoord c;
     int x0, y0, z0;
-    axis_clamp_f(px, P.fnf[0], P.fnm1f[0], x0, c.fx);
-    axis_clamp_f(py, P.fnf[1], P.fnm1f[1], y0, c.fy);
-    axis_clamp_f(pz, P.fnf[2], P.fnm1f[2], z0, c.fz);
-    c.idx = (unsigned int)z0 * P.fPlane + (unsigned int)y0 * P.fRow + (unsigned int)x0;
+    if (GUARD) {
+        float u = fmaf(px, P.fnf[0], -0.5f);
+        x0 = __float2int_rd(u); c.fx = u - __int2float_rn(x0);
+        u = fmaf(py, P.fnf[1], -0.5f);
+        y0 = __float2int_rd(u); c.fy = u - __int2float_rn(y0);
+        u = fmaf(pz, P.fnf[2], -0.5f);
+        z0 = __float2int_rd(u); c.fz = u - __int2float_rn(z0);
+    } else {
+        axis_clamp_f(px, P.fnf[0], P.fnm1f[0], x0, c.fx);
+        axis_clamp_f(py, P.fnf[1], P.fnm1f[1], y0, c.fy);
+        axis_clamp_f(pz, P.fnf[2], P.fnm1f[2], z0, c.fz);
+    }
+    c.idx = z0 * (int)P.fPlane + y0 * (int)P.fRow + x0;
     return c;
 }
 
@@ -317,7 +348,7 @@ __device__ __forceinline__ void widen_rg(unsigned int w0, unsigned int w1, pk2_t
     d = pk2(fh_sub(h_lo(w1), a0), fh_sub(h_hi(w1), a1));
 }
 
-__device__ __forceinline__ FieldCell load_field_cell(const DevParams &P, unsigned int idx)
+__device__ __forceinline__ FieldCell load_field_cell(const DevParams &P, int idx)
 {
     const uint4 *F = P.field_pair + idx;
     const uint4 A = ld_u4(F), B = ld_u4(F + P.fRow), C = ld_u4(F + P.fPlane), D = ld_u4(F + P.fPlane + P.fRow);
@@ -404,15 +435,38 @@ __device__ __forceinline__ Rgba2 quad_blend(uint4 q, pk2_t fx2, pk2_t fy2)
 }
 
 // noiseSampler, RGBA8 (gradient.xyz, noise), REPEAT -> raw texel (freqSamplingGrad, inc_lic.glsl:61-68)
-// NL: layout known at compile time (1 fp16 x-pair, 0 u8 xy-quad) or -1 = chosen at run time from P.noise_pair
-template <int NL = -1>
-__device__ __forceinline__ Rgba2 fetch_noise_rgba_pk(const DevParams &P, float px, float py, float pz)
+// two bf16 values of one word as an fp32 register pair: a bf16 is the upper half of the fp32 with the same value, so the
+// widening is a byte permute / mask on the ALU pipe instead of an FHADD on the (binding) FMA pipe
+__device__ __forceinline__ pk2_t bf2pk(unsigned int w)
 {
-    int x0, y0, z0;
-    float fx, fy, fz;
-    axis_repeat_f(px, P.nnf[0], x0, fx);
-    axis_repeat_f(py, P.nnf[1], y0, fy);
-    axis_repeat_f(pz, P.nnf[2], z0, fz);
+    unsigned int lo, hi;
+    asm("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(lo) : "r"(w));
+    asm("prmt.b32 %0, %1, 0, 0x3244;" : "=r"(hi) : "r"(w));
+    return pk2(__uint_as_float(lo), __uint_as_float(hi));
+}
+
+// pre-differenced bf16 layout, cell index idx: x-lerp = t0 + fx * d with d = t1 - t0 stored (exact: |d| <= 255 has 8 significant
+// bits); the same fp32 values and operations as the fp16 x-pair path (FHADD forms t1 - t0 exactly as well)
+__device__ __forceinline__ Rgba2 blend_noise_bf(const DevParams &P, int idx, float fx, float fy, float fz)
+{
+    const uint4 *N = P.noise_bf + idx;
+    const uint4 A = ld_u4(N), B = ld_u4(N + P.nbRow);
+    const uint4 C = ld_u4(N + P.nbPlane), D = ld_u4(N + P.nbPlane + P.nbRow);
+    const pk2_t fx2 = bc2(fx), fy2 = bc2(fy), fz2 = bc2(fz), k2 = bc2(1.0f / 255.0f);
+    Rgba2 r;
+    r.rg = mul2(lerp2(lerp2(fma2(fx2, bf2pk(A.z), bf2pk(A.x)), fma2(fx2, bf2pk(B.z), bf2pk(B.x)), fy2),
+                      lerp2(fma2(fx2, bf2pk(C.z), bf2pk(C.x)), fma2(fx2, bf2pk(D.z), bf2pk(D.x)), fy2), fz2), k2);
+    r.ba = mul2(lerp2(lerp2(fma2(fx2, bf2pk(A.w), bf2pk(A.y)), fma2(fx2, bf2pk(B.w), bf2pk(B.y)), fy2),
+                      lerp2(fma2(fx2, bf2pk(C.w), bf2pk(C.y)), fma2(fx2, bf2pk(D.w), bf2pk(D.y)), fy2), fz2), k2);
+    return r;
+}
+
+// NL: layout known at compile time (2 bf16 {t0, t1 - t0}, 1 fp16 x-pair, 0 u8 xy-quad) or -1 = chosen at run time
+// load + trilinear blend of the RGBA noise cell (x0, y0, z0) (cell index in [-1, n-1] per axis) with the weights (fx, fy, fz)
+template <int NL = -1>
+__device__ __forceinline__ Rgba2 blend_noise_rgba(const DevParams &P, int x0, int y0, int z0, float fx, float fy, float fz)
+{
+    if (NL == 2 || (NL < 0 && P.noise_bf)) return blend_noise_bf(P, z0 * P.nbPlane + y0 * P.nbRow + x0, fx, fy, fz);
     if (NL == 1 || (NL < 0 && P.noise_pair)) {
         // fp16 x-pair layout (byte values 0..255 are exact in fp16): the same FHADD lerp as the vector field, no byte
         // decode; wrapped border rows / planes, so the neighbours are +npRow / +npPlane for every cell index in [-1, n-1]
@@ -442,6 +496,18 @@ __device__ __forceinline__ Rgba2 fetch_noise_rgba_pk(const DevParams &P, float p
     r.rg = mul2(lerp2(p0.rg, p1.rg, fz2), k2);
     r.ba = mul2(lerp2(p0.ba, p1.ba, fz2), k2);
     return r;
+}
+
+// noiseSampler, RGBA8 (gradient.xyz, noise), REPEAT -> raw texel (freqSamplingGrad, inc_lic.glsl:61-68)
+template <int NL = -1>
+__device__ __forceinline__ Rgba2 fetch_noise_rgba_pk(const DevParams &P, float px, float py, float pz)
+{
+    int x0, y0, z0;
+    float fx, fy, fz;
+    axis_repeat_f(px, P.nnf[0], x0, fx);
+    axis_repeat_f(py, P.nnf[1], y0, fy);
+    axis_repeat_f(pz, P.nnf[2], z0, fz);
+    return blend_noise_rgba<NL>(P, x0, y0, z0, fx, fy, fz);
 }
 
 __device__ __forceinline__ float4 fetch_noise_rgba(const DevParams &P, float px, float py, float pz)

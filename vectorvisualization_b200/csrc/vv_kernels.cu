@@ -12,6 +12,9 @@
 #include "vv_device.cuh"
 #include "vv_kernels.h"
 
+#ifndef LIC_CTA_THREADS
+#define LIC_CTA_THREADS 256   // threads per CTA of lic_sample_kernel (warps pull work items independently; the CTA only shares the tables)
+#endif
 #ifndef LIC_MIN_CTAS
 #define LIC_MIN_CTAS 4   // resident CTAs per SM the sample kernel is compiled for (64 registers per thread; measured 2.5 %
                          // faster than 3 CTAs / 80 registers on cfg2 / cfg3 despite 24-64 B of spills)
@@ -143,7 +146,7 @@ __device__ __forceinline__ float noise_tap(const DevParams &P, f3 q)
 }
 
 // streamline walker: position (x,y packed, z) and the field sample at it (r,g packed, b, a)
-struct Walker { pk2_t qxy; float qz; pk2_t vrg; float vb, va; };
+struct Walker { pk2_t qxy; float qz; pk2_t vrg; float vb, va; CellCoord c; };   // c: field cell of the position (heun_step, XF sharing)
 
 __device__ __forceinline__ Walker make_walker(f3 pos, float4 centre)
 {
@@ -153,38 +156,48 @@ __device__ __forceinline__ Walker make_walker(f3 pos, float4 centre)
     return w;
 }
 
+#ifndef VV_SEQ_WALKS
+#define VV_SEQ_WALKS 0    // experiment: 1 = backward walk, then forward walk (one fetch chain per thread, fewer live registers)
+#endif
 #ifndef VV_CELL_REUSE
 #define VV_CELL_REUSE 1   // one cell load per Heun step, evaluated at the predictor and the corrector position (see FieldCell)
 #endif
 
 // one Heun step of singleLICstep (inc_lic.glsl:104-128); sh = dir * h
-template <int LAYOUT, bool SOF>
-__device__ __forceinline__ void heun_step(const DevParams &P, Walker &w, float sh)
+template <int LAYOUT, bool SOF, int XF = 0>
+__device__ __forceinline__ void heun_step(const DevParams &P, Walker &w, float sh, float *dbg = nullptr)
 {
     const float s1 = SOF ? w.va * sh : sh;    // licdir *= step.a (SPEED_OF_FLOW) then *= h
     const pk2_t s2 = bc2(s1), two = bc2(2.0f), mone = bc2(-1.0f);
-    const pk2_t d1 = mul2(fma2(two, w.vrg, mone), s2);                    // licdir = (2 v - 1) * dir * h
-    const float d1z = fmaf(2.0f, w.vb, -1.0f) * s1;
+    const pk2_t d1 = mul2_keep(fma2(two, w.vrg, mone), s2);               // licdir = (2 v - 1) * dir * h
+    // (scalar z lane with explicit round-to-nearest intrinsics: nvcc must not contract the product into the position sums, the
+    // packed x / y lanes are not contracted either -- every lane rounds exactly where the shader's statement sequence does)
+    const float d1z = __fmul_rn(fmaf(2.0f, w.vb, -1.0f), s1);
+    const float p2z = __fadd_rn(w.qz, d1z);
     const pk2_t p2 = add2(w.qxy, d1);                                      // Pos2 = newPos + licdir
     if constexpr (LAYOUT == LAYOUT_PAIR && !SOF && VV_CELL_REUSE) {
-        const CellCoord c2 = field_cell_coord(P, lo2(p2), hi2(p2), w.qz + d1z);
+        constexpr bool GUARD = (XF & XF_GUARD) != 0;
+        const CellCoord c2 = field_cell_coord<GUARD>(P, lo2(p2), hi2(p2), p2z);
         const FieldCell cell = load_field_cell(P, c2.idx);
         const FieldVal v2 = eval_field_cell(cell, c2.fx, c2.fy, c2.fz);
-        const pk2_t d2 = mul2(fma2(two, v2.rg, mone), s2);
-        const float d2z = fmaf(2.0f, v2.b, -1.0f) * s1;
+        if (dbg) { dbg[0] = lo2(p2); dbg[1] = hi2(p2); dbg[2] = p2z; dbg[3] = lo2(v2.rg); dbg[4] = hi2(v2.rg); dbg[5] = v2.b; }   // diagnostic only
+        const pk2_t d2 = mul2_keep(fma2(two, v2.rg, mone), s2);
+        const float d2z = __fmul_rn(fmaf(2.0f, v2.b, -1.0f), s1);
         w.qxy = fma2(bc2(0.5f), add2(d1, d2), w.qxy);                      // newPos += 0.5 (licdir + licdir2)
-        w.qz = fmaf(0.5f, d1z + d2z, w.qz);
-        const CellCoord c = field_cell_coord(P, lo2(w.qxy), hi2(w.qxy), w.qz);
+        w.qz = fmaf(0.5f, __fadd_rn(d1z, d2z), w.qz);
+        const CellCoord c = field_cell_coord<GUARD>(P, lo2(w.qxy), hi2(w.qxy), w.qz);
         FieldVal v;
         if (c.idx == c2.idx) v = eval_field_cell(cell, c.fx, c.fy, c.fz);
         else v = eval_field_cell(load_field_cell(P, c.idx), c.fx, c.fy, c.fz);   // the corrector left the predictor's cell (rare)
         w.vrg = v.rg; w.vb = v.b; w.va = v.a;
+        w.c = c;
     } else {
-        const FieldVal v2 = fetch_field_pk<LAYOUT, false>(P, lo2(p2), hi2(p2), w.qz + d1z);
-        const pk2_t d2 = mul2(fma2(two, v2.rg, mone), s2);
-        const float d2z = fmaf(2.0f, v2.b, -1.0f) * s1;
+        static_assert(XF == 0 || (LAYOUT == LAYOUT_PAIR && !SOF && VV_CELL_REUSE), "the coordinate fast paths live in the cell-reuse step");
+        const FieldVal v2 = fetch_field_pk<LAYOUT, false>(P, lo2(p2), hi2(p2), p2z);
+        const pk2_t d2 = mul2_keep(fma2(two, v2.rg, mone), s2);
+        const float d2z = __fmul_rn(fmaf(2.0f, v2.b, -1.0f), s1);
         w.qxy = fma2(bc2(0.5f), add2(d1, d2), w.qxy);                      // newPos += 0.5 (licdir + licdir2)
-        w.qz = fmaf(0.5f, d1z + d2z, w.qz);
+        w.qz = fmaf(0.5f, __fadd_rn(d1z, d2z), w.qz);
         const FieldVal v = fetch_field_pk<LAYOUT, SOF>(P, lo2(w.qxy), hi2(w.qxy), w.qz);
         w.vrg = v.rg; w.vb = v.b; w.va = v.a;
     }
@@ -196,7 +209,7 @@ __device__ __forceinline__ void heun_step(const DevParams &P, Walker &w, float s
 // weights contribute exactly 0 to the sum).
 // STRAIGHT: the common part of the two walks as straight-line code (measured: 3 % faster in lic_sample_kernel on the
 // scalar builds, neutral on the gradient build, 8 % slower in lic_volume_kernel, which therefore keeps the guarded loop)
-template <int LAYOUT, bool NGATE, bool SOF, bool STRAIGHT = true>
+template <int LAYOUT, bool NGATE, bool SOF, bool STRAIGHT = true, int XF = 0>
 __device__ __forceinline__ float compute_lic_scalar(const DevParams &P, const float *s_kw, f3 pos, float4 centre)
 {
     float acc0 = noise_tap<NGATE>(P, pos) * s_kw[0];
@@ -206,31 +219,31 @@ __device__ __forceinline__ float compute_lic_scalar(const DevParams &P, const fl
     const int nB = P.nBwdEff, nF = P.nFwdEff;
     if (STRAIGHT) {
         // common part of the two walks without per-direction guards, then the tail of the longer walk
-        const int nMin = min(nB, nF);
+        const int nMin = VV_SEQ_WALKS ? 0 : min(nB, nF);
         int k = 0;
         for (; k < nMin; ++k) {
-            heun_step<LAYOUT, SOF>(P, wb, -P.h);
-            heun_step<LAYOUT, SOF>(P, wf, P.h);
+            heun_step<LAYOUT, SOF, XF>(P, wb, -P.h);
+            heun_step<LAYOUT, SOF, XF>(P, wf, P.h);
             accB = fmaf(noise_tap<NGATE>(P, mk3(lo2(wb.qxy), hi2(wb.qxy), wb.qz)), kwB[k], accB);
             accF = fmaf(noise_tap<NGATE>(P, mk3(lo2(wf.qxy), hi2(wf.qxy), wf.qz)), kwF[k], accF);
         }
         for (; k < nB; ++k) {
-            heun_step<LAYOUT, SOF>(P, wb, -P.h);
+            heun_step<LAYOUT, SOF, XF>(P, wb, -P.h);
             accB = fmaf(noise_tap<NGATE>(P, mk3(lo2(wb.qxy), hi2(wb.qxy), wb.qz)), kwB[k], accB);
         }
-        for (; k < nF; ++k) {
-            heun_step<LAYOUT, SOF>(P, wf, P.h);
+        for (k = nMin; k < nF; ++k) {
+            heun_step<LAYOUT, SOF, XF>(P, wf, P.h);
             accF = fmaf(noise_tap<NGATE>(P, mk3(lo2(wf.qxy), hi2(wf.qxy), wf.qz)), kwF[k], accF);
         }
     } else {
         const int n = max(nB, nF);
         for (int k = 0; k < n; ++k) {
             if (k < nB) {
-                heun_step<LAYOUT, SOF>(P, wb, -P.h);
+                heun_step<LAYOUT, SOF, XF>(P, wb, -P.h);
                 accB = fmaf(noise_tap<NGATE>(P, mk3(lo2(wb.qxy), hi2(wb.qxy), wb.qz)), kwB[k], accB);
             }
             if (k < nF) {
-                heun_step<LAYOUT, SOF>(P, wf, P.h);
+                heun_step<LAYOUT, SOF, XF>(P, wf, P.h);
                 accF = fmaf(noise_tap<NGATE>(P, mk3(lo2(wf.qxy), hi2(wf.qxy), wf.qz)), kwF[k], accF);
             }
         }
@@ -238,10 +251,38 @@ __device__ __forceinline__ float compute_lic_scalar(const DevParams &P, const fl
     return (acc0 + accB) + accF;
 }
 
+// the RGBA-noise tap at a walker's position; fast: the walk stays inside [0,1)^3 and the noise shares the field's cell (XF_NSHARE)
+template <int NL, int XF>
+__device__ __forceinline__ Rgba2 noise_tap_rgba(const DevParams &P, const Walker &w, bool fast)
+{
+    if constexpr ((XF & XF_NSHARE) != 0) {
+        static_assert(NL == 2, "the shared cell index addresses the bf16 layout");
+        // only the coordinates differ between the two cases; one copy of the loads and the blend
+        int idx = w.c.idx;
+        float fx = w.c.fx, fy = w.c.fy, fz = w.c.fz;
+        if (!fast) {
+            int x0, y0, z0;
+            axis_repeat_f(lo2(w.qxy), P.nnf[0], x0, fx);
+            axis_repeat_f(hi2(w.qxy), P.nnf[1], y0, fy);
+            axis_repeat_f(w.qz, P.nnf[2], z0, fz);
+            idx = z0 * P.nbPlane + y0 * P.nbRow + x0;
+        }
+        return blend_noise_bf(P, idx, fx, fy, fz);
+    } else {
+        return fetch_noise_rgba_pk<NL>(P, lo2(w.qxy), hi2(w.qxy), w.qz);
+    }
+}
+
 // computeLIC, USE_NOISE_GRADIENTS build: vec4 accumulation of raw RGBA noise texels (Q8)
-template <int LAYOUT, bool SOF, bool STRAIGHT = true, int NL = -1>
+template <int LAYOUT, bool SOF, bool STRAIGHT = true, int NL = -1, int XF = 0>
 __device__ __forceinline__ float4 compute_lic_grad(const DevParams &P, const float *s_kw, f3 pos, float4 centre)
 {
+    bool fast = false;
+    if constexpr ((XF & XF_NSHARE) != 0) {
+        // warp-uniform: every active lane's walk stays inside [0,1)^3 (it starts at least (S + 2) h away from the faces)
+        const float lo = fminf(fminf(pos.x, pos.y), pos.z), hi = fmaxf(fmaxf(pos.x, pos.y), pos.z);
+        fast = __all_sync(__activemask(), lo >= P.walkReach && hi < 1.0f - P.walkReach) != 0;
+    }
     const Rgba2 c = fetch_noise_rgba_pk<NL>(P, pos.x, pos.y, pos.z);
     const pk2_t w0 = bc2(s_kw[0]);
     pk2_t accBrg = pk2(0.f, 0.f), accBba = accBrg, accFrg = accBrg, accFba = accBrg;
@@ -249,13 +290,13 @@ __device__ __forceinline__ float4 compute_lic_grad(const DevParams &P, const flo
     const float *kwB = s_kw + 1, *kwF = s_kw + 1 + P.nBwd;
     const int nB = P.nBwdEff, nF = P.nFwdEff;
     if (STRAIGHT) {
-        const int nMin = min(nB, nF);
+        const int nMin = VV_SEQ_WALKS ? 0 : min(nB, nF);
         int k = 0;
         for (; k < nMin; ++k) {
-            heun_step<LAYOUT, SOF>(P, wb, -P.h);
-            heun_step<LAYOUT, SOF>(P, wf, P.h);
-            const Rgba2 tb = fetch_noise_rgba_pk<NL>(P, lo2(wb.qxy), hi2(wb.qxy), wb.qz);
-            const Rgba2 tf = fetch_noise_rgba_pk<NL>(P, lo2(wf.qxy), hi2(wf.qxy), wf.qz);
+            heun_step<LAYOUT, SOF, XF>(P, wb, -P.h);
+            heun_step<LAYOUT, SOF, XF>(P, wf, P.h);
+            const Rgba2 tb = noise_tap_rgba<NL, XF>(P, wb, fast);
+            const Rgba2 tf = noise_tap_rgba<NL, XF>(P, wf, fast);
             const pk2_t wB = bc2(kwB[k]), wF = bc2(kwF[k]);
             accBrg = fma2(tb.rg, wB, accBrg);
             accBba = fma2(tb.ba, wB, accBba);
@@ -263,15 +304,15 @@ __device__ __forceinline__ float4 compute_lic_grad(const DevParams &P, const flo
             accFba = fma2(tf.ba, wF, accFba);
         }
         for (; k < nB; ++k) {
-            heun_step<LAYOUT, SOF>(P, wb, -P.h);
-            const Rgba2 t = fetch_noise_rgba_pk<NL>(P, lo2(wb.qxy), hi2(wb.qxy), wb.qz);
+            heun_step<LAYOUT, SOF, XF>(P, wb, -P.h);
+            const Rgba2 t = noise_tap_rgba<NL, XF>(P, wb, fast);
             const pk2_t w = bc2(kwB[k]);
             accBrg = fma2(t.rg, w, accBrg);
             accBba = fma2(t.ba, w, accBba);
         }
-        for (; k < nF; ++k) {
-            heun_step<LAYOUT, SOF>(P, wf, P.h);
-            const Rgba2 t = fetch_noise_rgba_pk<NL>(P, lo2(wf.qxy), hi2(wf.qxy), wf.qz);
+        for (k = nMin; k < nF; ++k) {
+            heun_step<LAYOUT, SOF, XF>(P, wf, P.h);
+            const Rgba2 t = noise_tap_rgba<NL, XF>(P, wf, fast);
             const pk2_t w = bc2(kwF[k]);
             accFrg = fma2(t.rg, w, accFrg);
             accFba = fma2(t.ba, w, accFba);
@@ -280,15 +321,15 @@ __device__ __forceinline__ float4 compute_lic_grad(const DevParams &P, const flo
         const int n = max(nB, nF);
         for (int k = 0; k < n; ++k) {
             if (k < nB) {
-                heun_step<LAYOUT, SOF>(P, wb, -P.h);
-                const Rgba2 t = fetch_noise_rgba_pk<NL>(P, lo2(wb.qxy), hi2(wb.qxy), wb.qz);
+                heun_step<LAYOUT, SOF, XF>(P, wb, -P.h);
+                const Rgba2 t = noise_tap_rgba<NL, XF>(P, wb, fast);
                 const pk2_t w = bc2(kwB[k]);
                 accBrg = fma2(t.rg, w, accBrg);
                 accBba = fma2(t.ba, w, accBba);
             }
             if (k < nF) {
-                heun_step<LAYOUT, SOF>(P, wf, P.h);
-                const Rgba2 t = fetch_noise_rgba_pk<NL>(P, lo2(wf.qxy), hi2(wf.qxy), wf.qz);
+                heun_step<LAYOUT, SOF, XF>(P, wf, P.h);
+                const Rgba2 t = noise_tap_rgba<NL, XF>(P, wf, fast);
                 const pk2_t w = bc2(kwF[k]);
                 accFrg = fma2(t.rg, w, accFrg);
                 accFba = fma2(t.ba, w, accFba);
@@ -437,7 +478,7 @@ __device__ __forceinline__ void load_tables(const DevParams &P, SharedTables &S)
 
 // one ray sample of lic3d_fragment.glsl:44-81: vector fetch, TF, gate, computeLIC, illumination.
 // Returns false when the LIC gate skips the sample (src keeps its previous value in the shader).
-template <int LAYOUT, int ILLUM, bool NGATE, bool SOF, int NL = -1>
+template <int LAYOUT, int ILLUM, bool NGATE, bool SOF, int NL = -1, int XF = 0>
 __device__ __forceinline__ bool shade_sample(const DevParams &P, const SharedTables &S, f3 pos, f3 dir, float4 &src)
 {
     constexpr bool GRAD = (ILLUM == ILLUM_GRADIENT);   // ILLUM_GRADIENT => USE_NOISE_GRADIENTS, inc_header.glsl:17-19
@@ -448,11 +489,11 @@ __device__ __forceinline__ bool shade_sample(const DevParams &P, const SharedTab
     // gate :59-61 (scalarData.g > -0.0001 is always true for a LUMINANCE8 texture)
     if (P.gateMode == GATE_TF_ALPHA && !(tf.w > 0.05f)) return false;
     if (GRAD) {
-        float4 il = compute_lic_grad<LAYOUT, SOF, true, NL>(P, S.kw, pos, vd);                // :64
+        float4 il = compute_lic_grad<LAYOUT, SOF, true, NL, XF>(P, S.kw, pos, vd);                // :64
         il.w *= P.licScale;                                                         // :67
         src = illum_gradient(P, S.opac, il, tf, pos, dir);
     } else {
-        float il = compute_lic_scalar<LAYOUT, NGATE, SOF>(P, S.kw, pos, vd) * P.licScale;
+        float il = compute_lic_scalar<LAYOUT, NGATE, SOF, true, XF>(P, S.kw, pos, vd) * P.licScale;
         if (ILLUM == ILLUM_MALLO) src = illum_mallo(P, S.opac, il, tf, pos, dir, mk3(vd.x, vd.y, vd.z));
         else if (ILLUM == ILLUM_ZOECKLER) src = illum_zoeckler(P, S.opac, il, tf, pos, dir, mk3(vd.x, vd.y, vd.z));
         else src = illum_lic(P, S.opac, il, tf);
@@ -694,8 +735,9 @@ __global__ void __launch_bounds__(256) slice_setup_kernel(const __grid_constant_
 }
 
 // NL: RGBA-noise layout of the gradient build as a compile-time parameter (the walk loop holds one sampler, not both)
-template <int LAYOUT, int ILLUM, bool NGATE, bool SOF, int NL>
-__global__ void __launch_bounds__(256, LIC_MIN_CTAS) lic_sample_kernel(const __grid_constant__ DevParams P)
+// XF: coordinate fast paths (XF_GUARD | XF_NSHARE | XF_SSHARE) the host found applicable to this frame
+template <int LAYOUT, int ILLUM, bool NGATE, bool SOF, int NL, int XF>
+__global__ void __launch_bounds__(LIC_CTA_THREADS, LIC_MIN_CTAS) lic_sample_kernel(const __grid_constant__ DevParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SharedTables &S = *reinterpret_cast<SharedTables *>(smem_raw);
@@ -744,7 +786,7 @@ __global__ void __launch_bounds__(256, LIC_MIN_CTAS) lic_sample_kernel(const __g
             }
         }
         if (!have) src = make_float4(0.f, 0.f, 0.f, -2.0f);                                                               // no fragment
-        else if (!shade_sample<LAYOUT, ILLUM, NGATE, SOF, NL>(P, S, pos, dir, src)) src = make_float4(0.f, 0.f, 0.f, -1.0f);   // gated
+        else if (!shade_sample<LAYOUT, ILLUM, NGATE, SOF, NL, XF>(P, S, pos, dir, src)) src = make_float4(0.f, 0.f, 0.f, -1.0f);   // gated
         const uint2 tr = P.tileRec[it.x];
         P.src[((size_t)tr.x + k) * 32 + lane] = src;
       }
@@ -964,6 +1006,43 @@ __global__ void __launch_bounds__(256) lic_volume_kernel(const __grid_constant__
     }
 }
 
+// diagnostic: one direction of the walk of compute_lic_scalar / compute_lic_grad from one position, step by step, with the device
+// functions of the hot path: out[16 i ..] = (position.xyz, field sample rgb, noise tap (.a of the RGBA tap), kernel weight,
+// predictor position Pos2.xyz, field sample at it rgb, 0, 0)
+template <int LAYOUT, bool GRAD, int XF>
+__global__ void debug_walk_kernel(const __grid_constant__ DevParams P, float px, float py, float pz, int dirSign, int nSteps, float *out)
+{
+    const f3 pos = mk3(px, py, pz);
+    const float4 centre = fetch_field<LAYOUT, true>(P, pos.x, pos.y, pos.z);
+    Walker w = make_walker(pos, centre);
+    const float *kw = P.kw + 1 + (dirSign < 0 ? 0 : P.nBwd);
+    for (int k = 0; k < nSteps; ++k) {
+        float *o = out + 16 * k;
+        heun_step<LAYOUT, false, XF>(P, w, dirSign < 0 ? -P.h : P.h, threadIdx.x == 0 ? o + 8 : nullptr);
+        float tap;
+        if (GRAD) tap = hi2(noise_tap_rgba<2, XF>(P, w, (XF & XF_NSHARE) != 0).ba);
+        else tap = noise_tap<true>(P, mk3(lo2(w.qxy), hi2(w.qxy), w.qz));
+        if (threadIdx.x == 0) {
+            o[0] = lo2(w.qxy); o[1] = hi2(w.qxy); o[2] = w.qz;
+            o[3] = lo2(w.vrg); o[4] = hi2(w.vrg); o[5] = w.vb;
+            o[6] = tap; o[7] = kw[k];
+        }
+    }
+}
+
+cudaError_t launch_debug_walk(const DevParams &P, bool grad, int xf, const float pos[3], int dirSign, int nSteps, float *out, cudaStream_t st)
+{
+    if (grad) {
+        if (xf == 3) debug_walk_kernel<LAYOUT_PAIR, true, 3><<<1, 32, 0, st>>>(P, pos[0], pos[1], pos[2], dirSign, nSteps, out);
+        else if (xf == 1) debug_walk_kernel<LAYOUT_PAIR, true, 1><<<1, 32, 0, st>>>(P, pos[0], pos[1], pos[2], dirSign, nSteps, out);
+        else debug_walk_kernel<LAYOUT_PAIR, true, 0><<<1, 32, 0, st>>>(P, pos[0], pos[1], pos[2], dirSign, nSteps, out);
+    } else {
+        if (xf == 1) debug_walk_kernel<LAYOUT_PAIR, false, 1><<<1, 32, 0, st>>>(P, pos[0], pos[1], pos[2], dirSign, nSteps, out);
+        else debug_walk_kernel<LAYOUT_PAIR, false, 0><<<1, 32, 0, st>>>(P, pos[0], pos[1], pos[2], dirSign, nSteps, out);
+    }
+    return cudaGetLastError();
+}
+
 // K5 ------------------------------------------------------------------------------------------------
 // tiles laid out [world][nLocalBlocksMax][256] -> row-major float frame, RGBA8 frame, and displayed RGBA8
 __global__ void unblock_kernel(const float4 *__restrict__ tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY, int skew,
@@ -1054,10 +1133,10 @@ cudaError_t launch_composite(const DevParams &P, int grid, cudaStream_t st)
 // 256 KB array serves as L1 (the driver's default picked 102 KB of shared memory for 3 x 14 KB; ncu
 // launch__shared_mem_config_size).  The gathers of this kernel live on L1 hits.
 template <class K>
-static cudaError_t prefer_l1(K kernel, size_t smem, int *occ_out = nullptr)
+static cudaError_t prefer_l1(K kernel, size_t smem, int *occ_out = nullptr, int threads = 256)
 {
     int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     const size_t need = (size_t)occ * (smem + 1024);                 // + 1 KB per CTA reserved by the driver
@@ -1075,23 +1154,43 @@ static cudaError_t launch_sample_kernel(K kernel, const DevParams &P, int grid, 
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = prefer_l1(kernel, smem, &occ);
+    e = prefer_l1(kernel, smem, &occ, LIC_CTA_THREADS);
     if (e != cudaSuccess) return e;
-    kernel<<<grid > 0 ? grid : sms * occ, 256, smem, st>>>(P);
+    kernel<<<grid > 0 ? grid : sms * occ, LIC_CTA_THREADS, smem, st>>>(P);
     return cudaGetLastError();
+}
+
+// which coordinate fast paths apply (decided per frame on the host, see fill_params): only the hot layouts get them
+template <int LAYOUT, int ILLUM, bool NGATE, bool SOF, int NL>
+static cudaError_t launch_sample_xf(const DevParams &P, int grid, size_t smem, cudaStream_t st)
+{
+    if constexpr (LAYOUT == LAYOUT_PAIR && !SOF && VV_CELL_REUSE && (NL == 2 || ILLUM != ILLUM_GRADIENT)) {
+        if (P.fGuard > 1 && P.guardOk) {
+            if constexpr (ILLUM == ILLUM_GRADIENT) {
+                if (P.noiseShared) return launch_sample_kernel(lic_sample_kernel<LAYOUT, ILLUM, NGATE, SOF, NL, XF_GUARD | XF_NSHARE>, P, grid, smem, st);
+            }
+            return launch_sample_kernel(lic_sample_kernel<LAYOUT, ILLUM, NGATE, SOF, NL, XF_GUARD>, P, grid, smem, st);
+        }
+    }
+    return launch_sample_kernel(lic_sample_kernel<LAYOUT, ILLUM, NGATE, SOF, NL, 0>, P, grid, smem, st);
 }
 
 template <int LAYOUT, int ILLUM, bool NGATE>
 static cudaError_t launch_sample_sof(const DevParams &P, bool sof, int grid, size_t smem, cudaStream_t st)
 {
-    // only the gradient build samples the RGBA noise; its check layout (u8 quads) gets its own instantiation
-    if (ILLUM == ILLUM_GRADIENT && !P.noise_pair) {
-        constexpr int NL = (ILLUM == ILLUM_GRADIENT) ? 0 : 1;
-        if (sof) return launch_sample_kernel(lic_sample_kernel<LAYOUT, ILLUM, NGATE, true, NL>, P, grid, smem, st);
-        return launch_sample_kernel(lic_sample_kernel<LAYOUT, ILLUM, NGATE, false, NL>, P, grid, smem, st);
+    // only the gradient build samples the RGBA noise; each of its layouts (2 bf16 diff, 1 fp16 pair, 0 u8 quads) is an instantiation
+    if (ILLUM == ILLUM_GRADIENT && !P.noise_bf) {
+        if (P.noise_pair) {
+            constexpr int NL = (ILLUM == ILLUM_GRADIENT) ? 1 : 2;
+            if (sof) return launch_sample_xf<LAYOUT, ILLUM, NGATE, true, NL>(P, grid, smem, st);
+            return launch_sample_xf<LAYOUT, ILLUM, NGATE, false, NL>(P, grid, smem, st);
+        }
+        constexpr int NL = (ILLUM == ILLUM_GRADIENT) ? 0 : 2;
+        if (sof) return launch_sample_xf<LAYOUT, ILLUM, NGATE, true, NL>(P, grid, smem, st);
+        return launch_sample_xf<LAYOUT, ILLUM, NGATE, false, NL>(P, grid, smem, st);
     }
-    if (sof) return launch_sample_kernel(lic_sample_kernel<LAYOUT, ILLUM, NGATE, true, 1>, P, grid, smem, st);
-    return launch_sample_kernel(lic_sample_kernel<LAYOUT, ILLUM, NGATE, false, 1>, P, grid, smem, st);
+    if (sof) return launch_sample_xf<LAYOUT, ILLUM, NGATE, true, 2>(P, grid, smem, st);
+    return launch_sample_xf<LAYOUT, ILLUM, NGATE, false, 2>(P, grid, smem, st);
 }
 
 template <int LAYOUT>

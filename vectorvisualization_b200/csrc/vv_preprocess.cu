@@ -65,10 +65,12 @@ __device__ __forceinline__ uint2 to_half4(float4 v, float maxLen)
 }
 
 // pass 2: scale |v| by 1/max, round to fp16, write the x-pair layout and/or float4
-// The x-pair layout is padded to [nz+1][ny+1][nx] with the last row / plane replicated (CLAMP_TO_EDGE), so the
-// sampler's y / z neighbours are always one row / plane further.
+// The x-pair layout carries CLAMP_TO_EDGE as replicated guard cells: the array is [nz+2G][ny+2G][fRow] with cell (x,y,z) at
+// ((z+G) (ny+2G) + (y+G)) fRow + (x+gx); every cell holds texels (clamp(x), clamp(x+1)) of row clamp(y), plane clamp(z).
+// G = 1 / gx = 0 is the minimum (the sampler's y / z neighbours are always one row / plane further, x is baked into the pair);
+// larger guards let the walk drop the coordinate clamp altogether (XF_GUARD).
 __global__ void pack_field_pass2(const float4 *__restrict__ tmp, const unsigned int *__restrict__ maxbits, int nx, int ny, int nz,
-                                 uint4 *__restrict__ out_pair, float4 *__restrict__ out_f4)
+                                 int guard, int gx, int frow, uint4 *__restrict__ out_pair, float4 *__restrict__ out_f4)
 {
     const float maxLen = __uint_as_float(*maxbits);
     const size_t n = (size_t)nx * ny * nz;
@@ -80,19 +82,21 @@ __global__ void pack_field_pass2(const float4 *__restrict__ tmp, const unsigned 
         }
     }
     if (out_pair) {
-        const size_t np = (size_t)nx * (ny + 1) * (nz + 1);
+        const int py = ny + 2 * guard, pz = nz + 2 * guard;
+        const size_t np = (size_t)frow * py * pz;
         for (size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x; a < np; a += (size_t)gridDim.x * blockDim.x) {
-            const int x = (int)(a % nx), y = (int)((a / nx) % (ny + 1)), z = (int)(a / ((size_t)nx * (ny + 1)));
-            const size_t s = ((size_t)min(z, nz - 1) * ny + min(y, ny - 1)) * nx + x;
-            uint2 t0 = to_half4(tmp[s], maxLen);
-            uint2 t1 = (x + 1 < nx) ? to_half4(tmp[s + 1], maxLen) : t0;
+            const int x = (int)(a % frow) - gx, y = (int)((a / frow) % py) - guard, z = (int)(a / ((size_t)frow * py)) - guard;
+            const int x0 = min(max(x, 0), nx - 1), x1 = min(max(x + 1, 0), nx - 1);
+            const size_t s = ((size_t)min(max(z, 0), nz - 1) * ny + min(max(y, 0), ny - 1)) * nx;
+            uint2 t0 = to_half4(tmp[s + x0], maxLen);
+            uint2 t1 = to_half4(tmp[s + x1], maxLen);
             out_pair[a] = make_uint4(t0.x, t0.y, t1.x, t1.y);
         }
     }
 }
 
 cudaError_t launch_pack_field(const void *v0, const void *v1, int is_u8, int nx, int ny, int nz, float interp_frac,
-                              float4 *tmp, unsigned int *maxbits, uint4 *out_pair, float4 *out_f4, cudaStream_t st)
+                              float4 *tmp, unsigned int *maxbits, uint4 *out_pair, int guard, int gx, int frow, float4 *out_f4, cudaStream_t st)
 {
     const size_t n = (size_t)nx * ny * nz;
     cudaError_t e = cudaMemsetAsync(maxbits, 0, sizeof(unsigned int), st);
@@ -100,7 +104,7 @@ cudaError_t launch_pack_field(const void *v0, const void *v1, int is_u8, int nx,
     const int grid = 148 * 8;
     if (is_u8) pack_field_pass1<true><<<grid, 256, 0, st>>>(v0, v1, n, interp_frac, tmp, maxbits);
     else pack_field_pass1<false><<<grid, 256, 0, st>>>(v0, v1, n, interp_frac, tmp, maxbits);
-    pack_field_pass2<<<grid, 256, 0, st>>>(tmp, maxbits, nx, ny, nz, out_pair, out_f4);
+    pack_field_pass2<<<grid, 256, 0, st>>>(tmp, maxbits, nx, ny, nz, guard, gx, frow, out_pair, out_f4);
     return cudaGetLastError();
 }
 
@@ -155,18 +159,27 @@ cudaError_t launch_build_quad(const uchar4 *src, int nx, int ny, int nz, uint4 *
     return cudaGetLastError();
 }
 
-// RGBA8 volume -> fp16 x-pair layout {half4 T[x], half4 T[(x+1) mod nx]}; byte values are exact in fp16
-__global__ void build_noise_pair_kernel(const uchar4 *__restrict__ src, int nx, int ny, int nz, uint4 *__restrict__ out)
+// RGBA8 volume -> x-pair layout {T[x mod nx], T[(x+1) mod nx]} with REPEAT baked in as wrapped guard cells:
+// the array is [nz+2G][ny+2G][frow], cell (x,y,z) at ((z+G)(ny+2G) + (y+G)) frow + x + gx  (default G = 1, gx = 1, frow = nx+1;
+// or the vector field's geometry, so that both arrays share one cell index, XF_NSHARE).
+// bf16diff = 0: fp16 {half4 T0, half4 T1} (byte values are exact in fp16);  1: {bf16x4 T0, bf16x4 (T1 - T0)} (integers up to 255
+// and their differences are exact in bf16)
+__global__ void build_noise_pair_kernel(const uchar4 *__restrict__ src, int nx, int ny, int nz, int guard, int gx, int frow,
+                                        uint4 *__restrict__ out, int bf16diff)
 {
-    // padded [nz+2][ny+2][nx+1]: entry (jx,jy,jz) = texels ((jx-1) mod nx, jx mod nx) of row (jy-1) mod ny, plane (jz-1) mod nz
-    const int px = nx + 1, py = ny + 2;
-    const size_t n = (size_t)px * py * (nz + 2);
+    const int py = ny + 2 * guard;
+    const size_t n = (size_t)frow * py * (nz + 2 * guard);
+    auto wrap = [](int v, int m) { v %= m; return v < 0 ? v + m : v; };
     for (size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += (size_t)gridDim.x * blockDim.x) {
-        const int jx = (int)(a % px), jy = (int)((a / px) % py), jz = (int)(a / ((size_t)px * py));
-        const int x0 = (jx == 0) ? nx - 1 : jx - 1, x1 = (jx == nx) ? 0 : jx;
-        const int y = (jy == 0) ? ny - 1 : (jy == ny + 1 ? 0 : jy - 1), z = (jz == 0) ? nz - 1 : (jz == nz + 1 ? 0 : jz - 1);
-        const size_t r = ((size_t)z * ny + y) * nx;
+        const int x = (int)(a % frow) - gx, y = (int)((a / frow) % py) - guard, z = (int)(a / ((size_t)frow * py)) - guard;
+        const int x0 = wrap(x, nx), x1 = wrap(x + 1, nx);
+        const size_t r = ((size_t)wrap(z, nz) * ny + wrap(y, ny)) * nx;
         const uchar4 t0 = src[r + x0], t1 = src[r + x1];
+        if (bf16diff) {
+            auto bf = [](int lo, int hi) { return (__float_as_uint((float)lo) >> 16) | (__float_as_uint((float)hi) & 0xffff0000u); };
+            out[a] = make_uint4(bf(t0.x, t0.y), bf(t0.z, t0.w), bf((int)t1.x - t0.x, (int)t1.y - t0.y), bf((int)t1.z - t0.z, (int)t1.w - t0.w));
+            continue;
+        }
         __half2 p0 = __floats2half2_rn((float)t0.x, (float)t0.y), p1 = __floats2half2_rn((float)t0.z, (float)t0.w);
         __half2 q0 = __floats2half2_rn((float)t1.x, (float)t1.y), q1 = __floats2half2_rn((float)t1.z, (float)t1.w);
         out[a] = make_uint4(*reinterpret_cast<unsigned int *>(&p0), *reinterpret_cast<unsigned int *>(&p1),
@@ -174,9 +187,9 @@ __global__ void build_noise_pair_kernel(const uchar4 *__restrict__ src, int nx, 
     }
 }
 
-cudaError_t launch_build_noise_pair(const uchar4 *src, int nx, int ny, int nz, uint4 *out, cudaStream_t st)
+cudaError_t launch_build_noise_pair(const uchar4 *src, int nx, int ny, int nz, int guard, int gx, int frow, uint4 *out, int bf16diff, cudaStream_t st)
 {
-    build_noise_pair_kernel<<<148 * 8, 256, 0, st>>>(src, nx, ny, nz, out);
+    build_noise_pair_kernel<<<148 * 8, 256, 0, st>>>(src, nx, ny, nz, guard, gx, frow, out, bf16diff);
     return cudaGetLastError();
 }
 

@@ -69,6 +69,9 @@ struct VVRenderer {
     DevBuf<float4> pack_tmp;
     DevBuf<unsigned int> maxbits;
     DevBuf<uint4> field_pair;
+    int field_guard = 1, field_gx = 0, field_row = 0;   // guard cells of the x-pair layout (see pack_field_pass2), x offset, row stride
+    float walk_reach = 0.0f;                            // (S + 2) h: how far a walk can get from its ray sample, texture coordinates
+    int guard_wanted = 1;                               // guard the current LIC parameters need for the unclamped walk (XF_GUARD)
     DevBuf<float4> field_f4;
     int field_layout = LAYOUT_PAIR;
     bool field_dirty = false;
@@ -82,8 +85,9 @@ struct VVRenderer {
     DevBuf<uint8_t> noise_raw;
     DevBuf<uint2> noise_cell;
     DevBuf<uchar4> noise_rgba;
-    DevBuf<uint4> noise_quad, noise_pair;
-    int noise_layout = 1;                  // RGBA noise: 1 = fp16 x-pair (default), 0 = u8 xy-quad
+    DevBuf<uint4> noise_quad, noise_pair, noise_bf;
+    int nbf_guard = 1, nbf_gx = 1, nbf_row = 0;   // geometry of noise_bf: its own wrapped border, or the vector field's guard geometry
+    int noise_layout = 2;                  // RGBA noise: 2 = bf16 {t0, t1 - t0} (default), 1 = fp16 x-pair, 0 = u8 xy-quad (check layouts)
     DevBuf<float> grad_tmp, grad_filter;
     int ndim[3] = {0, 0, 0};
     bool have_noise = false, noise_has_grad = false;
@@ -146,7 +150,7 @@ struct VVRenderer {
     DevBuf<uint2> tileRec, items[2];
     int raycast_mode = 1;                  // 1: sample-parallel pipeline (default), 0: one thread per ray
     int lic_ctas_per_sm = 0;               // 0: as many as are resident (occupancy query)
-    int item_chunk = 8;                    // (experiment knob)
+    int xf_enable = 1;                     // coordinate fast paths of the walk (XF_GUARD / XF_NSHARE): 0 = the clamping samplers (check)
     int depth_major = 1;                   // 1: bucket work items by (band, depth chunk) for L2 locality; 0: tile-major
     int band_rows = 4;                     // block rows per band (4 x 16 = 64 pixel rows)
     DevBuf<unsigned int> buckets;
@@ -331,14 +335,26 @@ static int pack_field(VVRenderer *r)
     CU(r->maxbits.ensure(1));
     uint4 *pair = nullptr;
     float4 *f4 = nullptr;
-    if (r->field_layout == LAYOUT_PAIR) {   // padded [nz+1][ny+1][nx]
-        CU(r->field_pair.ensure((size_t)r->size[0] * (r->size[1] + 1) * (r->size[2] + 1)));
+    if (r->field_layout == LAYOUT_PAIR) {
+        // guard cells: what the unclamped walk needs (guard_wanted, from the LIC parameters), as long as the padded array stays
+        // addressable with signed 32-bit element offsets; else the minimum and the clamping samplers
+        int g = std::max(1, r->guard_wanted);
+        auto padded = [&](int gg) {
+            const size_t gx = gg > 1 ? (size_t)((gg + 7) & ~7) : 0;
+            return (((size_t)r->size[0] + 2 * gx + 7) & ~(size_t)7) * ((size_t)r->size[1] + 2 * gg) * ((size_t)r->size[2] + 2 * gg);
+        };
+        if (padded(g) >= ((size_t)1 << 31)) g = 1;
+        if (padded(g) >= ((size_t)1 << 31)) return fail(VV_ERR_INVALID, "vector field too large for 32-bit element offsets");
+        r->field_guard = g;
+        r->field_gx = g > 1 ? ((g + 7) & ~7) : 0;               // x guard in whole 128-byte lines: cell x = 0 stays line-aligned
+        r->field_row = (r->size[0] + 2 * r->field_gx + 7) & ~7;
+        CU(r->field_pair.ensure(padded(g)));
         pair = r->field_pair.p;
     }
     else { CU(r->field_f4.ensure(n)); f4 = r->field_f4.p; }
     const float frac = (float)r->interp_index / r->interp_size;   // VV/dataset.cpp:590
     CU(launch_pack_field(r->raw0.p, r->have_next ? r->raw1.p : nullptr, r->field_u8 ? 1 : 0, r->size[0], r->size[1], r->size[2],
-                         frac, r->pack_tmp.p, r->maxbits.p, pair, f4, r->stream));
+                         frac, r->pack_tmp.p, r->maxbits.p, pair, r->field_guard, r->field_gx, r->field_row, f4, r->stream));
     r->field_dirty = false;
     return VV_OK;
 }
@@ -347,6 +363,25 @@ static int pack_field(VVRenderer *r)
 static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycast_program = true)
 {
     if (!r->have_field) return fail(VV_ERR_STATE, "no vector field set (vv_set_vector_field / vv_load_dat)");
+    const Uniforms u = derive_uniforms(r);
+    // Guard band of the unclamped walk (XF_GUARD): a Heun step moves a position by at most h per axis in texture coordinates
+    // (|2 v - 1| <= 1 per component for texels in [0,1]) and its predictor looks one more step ahead, so a walk of S steps stays
+    // within (S + 1) h of its ray sample.  Ray samples lie in [0, max(texMax, extent * scaleVol)] per axis -- inside [0,1] for a
+    // cubic volume, beyond it for anisotropic ones (texMax = maxTexSize / maxVolSize, and Q1 puts scaleInv into scaleVol).
+    // + 3 cells of slack (rounding, the +1 neighbour).
+    {
+        double reach = 0.0;
+        for (int i = 0; i < 3; ++i) {
+            const double pos_max = std::max((double)(r->extent[i] * r->scale[i]), (double)(r->extent[i] * r->scale_inv[i]));
+            const double walk = (double)(std::max(u.nFwd, u.nBwd) + 1) * (double)(u.licParams[2] * 0.3f);
+            reach = std::max(reach, (walk + std::max(0.0, pos_max - 1.0)) * (double)r->size[i]);
+        }
+        const int need = (reach < 60.0) ? (((int)std::ceil(reach) + 3 + 3) & ~3) : 1;      // capped: beyond 64 cells the clamping samplers run
+        r->guard_wanted = std::max(need, 1);
+        r->walk_reach = (float)((double)(std::max(u.nFwd, u.nBwd) + 2) * (double)(u.licParams[2] * 0.3f));
+        if (r->field_layout == LAYOUT_PAIR && r->field_pair.p && !r->field_dirty && r->field_guard < r->guard_wanted && need > 1)
+            r->field_dirty = true;      // the LIC parameters outgrew the packed guard band: pack again with the larger one
+    }
     if (r->field_dirty || (r->field_layout == LAYOUT_PAIR ? !r->field_pair.p : !r->field_f4.p)) {
         int rc = pack_field(r);
         if (rc) return rc;
@@ -359,16 +394,20 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycas
     if (r->tf_modes[prog] == TF_SCALAR && !r->have_scalar) return fail(VV_ERR_STATE, "tf_mode scalar needs a scalar volume");
     if (need_frame && (r->width <= 0 || r->height <= 0)) return fail(VV_ERR_STATE, "vv_resize not called");
 
-    const Uniforms u = derive_uniforms(r);
     if (r->tables_dirty) {
         int rc = upload_tables(r, u);
         if (rc) return rc;
         r->tables_dirty = false;
     }
     std::memset(&P, 0, sizeof(P));
-    P.field_pair = r->field_pair.p; P.field_f4 = r->field_f4.p;
+    P.field_f4 = r->field_f4.p;
     P.fnx = r->size[0]; P.fny = r->size[1]; P.fnz = r->size[2];
-    P.fRow = (unsigned int)r->size[0]; P.fPlane = (unsigned int)r->size[0] * (unsigned int)(r->size[1] + 1);
+    P.fRow = (unsigned int)r->field_row; P.fPlane = (unsigned int)r->field_row * (unsigned int)(r->size[1] + 2 * r->field_guard);
+    P.field_pair = r->field_pair.p ? r->field_pair.p + ((size_t)r->field_guard * P.fPlane + (size_t)r->field_guard * P.fRow + r->field_gx) : nullptr;
+    P.fGuard = r->field_guard;
+    P.walkReach = r->walk_reach;
+    P.guardOk = (r->field_guard > 1 && r->field_guard >= r->guard_wanted && r->xf_enable) ? 1 : 0;
+    P.noiseSameDims = (r->ndim[0] == r->size[0] && r->ndim[1] == r->size[1] && r->ndim[2] == r->size[2]) ? 1 : 0;
     P.scalar_cell = r->scalar_cell.p; P.snx = r->sdim[0]; P.sny = r->sdim[1]; P.snz = r->sdim[2];
     P.nnx = r->ndim[0]; P.nny = r->ndim[1]; P.nnz = r->ndim[2];
     for (int k = 0; k < 3; ++k) {
@@ -382,6 +421,22 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycas
     P.noise_cell = r->noise_cell.p ? r->noise_cell.p + (P.ncPlane + P.ncRow + 1) : nullptr;
     P.noise_quad = r->noise_quad.p;
     P.noise_pair = (r->noise_layout == 1 && r->noise_pair.p) ? r->noise_pair.p + (P.npPlane + P.npRow + 1) : nullptr;
+    P.noise_bf = nullptr;
+    P.noiseShared = 0;
+    if (r->noise_layout == 2 && r->noise_bf.p && r->noise_has_grad) {
+        // The hot RGBA-noise layout takes the vector field's guard geometry when both volumes have the same dimensions: one cell
+        // index then addresses both arrays (XF_NSHARE).  Rebuilt from the RGBA texels whenever the field's geometry moved.
+        const bool share = P.guardOk && r->field_layout == LAYOUT_PAIR && P.noiseSameDims && grad;
+        const int g = share ? r->field_guard : 1, gx = share ? r->field_gx : 1, row = share ? r->field_row : r->ndim[0] + 1;
+        if (g != r->nbf_guard || gx != r->nbf_gx || row != r->nbf_row) {
+            CU(r->noise_bf.ensure((size_t)row * (r->ndim[1] + 2 * g) * (r->ndim[2] + 2 * g)));
+            CU(launch_build_noise_pair(r->noise_rgba.p, r->ndim[0], r->ndim[1], r->ndim[2], g, gx, row, r->noise_bf.p, 1, r->stream));
+            r->nbf_guard = g; r->nbf_gx = gx; r->nbf_row = row;
+        }
+        P.nbRow = row; P.nbPlane = row * (r->ndim[1] + 2 * g);
+        P.noise_bf = r->noise_bf.p + ((size_t)g * P.nbPlane + (size_t)g * P.nbRow + gx);
+        P.noiseShared = share ? 1 : 0;
+    }
     P.licvol = r->licvol.p; P.lnx = r->ldim[0]; P.lny = r->ldim[1]; P.lnz = r->ldim[2];
     P.tf_rgba = r->tf_rgba.p; P.tf_opac = r->tf_opac.p; P.kw = r->kw.p;
     for (int i = 0; i < 3; ++i) P.illum2d[i] = r->illum_tab[i].p;
@@ -596,7 +651,10 @@ static int upload_noise(VVRenderer *r, const uint8_t *data, const int dims[3], i
     if (with_gradients) {
         CU(launch_build_quad(r->noise_rgba.p, dims[0], dims[1], dims[2], r->noise_quad.p, r->stream));
         CU(r->noise_pair.ensure((size_t)(dims[0] + 1) * (dims[1] + 2) * (dims[2] + 2)));
-        CU(launch_build_noise_pair(r->noise_rgba.p, dims[0], dims[1], dims[2], r->noise_pair.p, r->stream));
+        CU(launch_build_noise_pair(r->noise_rgba.p, dims[0], dims[1], dims[2], 1, 1, dims[0] + 1, r->noise_pair.p, 0, r->stream));
+        r->nbf_guard = 1; r->nbf_gx = 1; r->nbf_row = dims[0] + 1;
+        CU(r->noise_bf.ensure((size_t)(dims[0] + 1) * (dims[1] + 2) * (dims[2] + 2)));
+        CU(launch_build_noise_pair(r->noise_rgba.p, dims[0], dims[1], dims[2], 1, 1, dims[0] + 1, r->noise_bf.p, 1, r->stream));
         r->noise_has_grad = true;
     }
     CU(cudaStreamSynchronize(r->stream));
@@ -643,7 +701,6 @@ static int render_sample_parallel(VVRenderer *r, DevParams &P)
     CU(r->items[0].ensure(rows));
     CU(r->items[1].ensure(rows));
     P.src = r->src.p;
-    P.itemChunk = r->item_chunk;
     // depth windows: whole ray at once when no sample can trigger the early termination, else 4, 8, 16, ... samples
     std::vector<int> w;
     w.push_back(0);
@@ -1141,15 +1198,15 @@ int vv_set_option(VVRenderer *r, int option, int value)
         if (value != 0 && value != 1) return fail(VV_ERR_INVALID, "bad raycast mode");
         r->raycast_mode = value; break;
     case VV_OPT_NOISE_LAYOUT:
-        if (value != 0 && value != 1) return fail(VV_ERR_INVALID, "bad noise layout");
+        if (value < 0 || value > 2) return fail(VV_ERR_INVALID, "bad noise layout");
         r->noise_layout = value; break;
     case VV_OPT_DEPTH_MAJOR: r->depth_major = value != 0; break;
     case VV_OPT_BAND_ROWS:
         if (value < 1 || value > 1024) return fail(VV_ERR_INVALID, "bad band rows");
         r->band_rows = value; break;
-    case VV_OPT_ITEM_CHUNK:
-        if (value < 8 || value > 256 || (value % 8)) return fail(VV_ERR_INVALID, "item chunk must be a multiple of 8 in 8..256");
-        r->item_chunk = value; break;
+    case VV_OPT_WALK_FAST_PATHS:
+        if (value != 0 && value != 1) return fail(VV_ERR_INVALID, "bad walk fast-path switch");
+        r->xf_enable = value; break;
     case VV_OPT_LIC_CTAS_PER_SM:
         if (value < 0 || value > 8) return fail(VV_ERR_INVALID, "bad CTAs per SM");
         r->lic_ctas_per_sm = value; break;
@@ -1379,17 +1436,19 @@ int vv_read_field_texture(VVRenderer *r, float *out, size_t out_bytes)
         CU(cudaStreamSynchronize(r->stream));
         return VV_OK;
     }
-    // gather the unpadded [nz][ny][nx] texels out of the padded x-pair layout
-    const size_t nx = r->size[0], ny = r->size[1], nz = r->size[2], np = nx * (ny + 1) * (nz + 1);
-    std::vector<uint16_t> tmp(np * 8);
-    CU(cudaMemcpyAsync(tmp.data(), r->field_pair.p, np * 16, cudaMemcpyDeviceToHost, r->stream));
-    CU(cudaStreamSynchronize(r->stream));
-    for (size_t z = 0; z < nz; ++z)
+    // gather the unpadded [nz][ny][nx] texels out of the padded x-pair layout, one row at a time
+    const size_t nx = r->size[0], ny = r->size[1], nz = r->size[2], G = r->field_guard, row = r->field_row, py = ny + 2 * G;
+    std::vector<uint16_t> tmp(nx * ny * 8);
+    for (size_t z = 0; z < nz; ++z) {
+        CU(cudaMemcpy2DAsync(tmp.data(), nx * 16, r->field_pair.p + ((z + G) * py + G) * row + r->field_gx, row * 16, nx * 16, ny,
+                             cudaMemcpyDeviceToHost, r->stream));
+        CU(cudaStreamSynchronize(r->stream));
         for (size_t y = 0; y < ny; ++y)
             for (size_t x = 0; x < nx; ++x) {
-                const size_t i = (z * ny + y) * nx + x, j = (z * (ny + 1) + y) * nx + x;
+                const size_t i = (z * ny + y) * nx + x, j = y * nx + x;
                 for (int k = 0; k < 4; ++k) out[4 * i + k] = half_bits_to_float(tmp[8 * j + k]);
             }
+    }
     return VV_OK;
 }
 
@@ -1638,6 +1697,30 @@ int vv_p2p_disconnect(VVRenderer *r)
     p2p_close(r);
     if (r->p2p_base) { CU(cudaFree(r->p2p_base)); r->p2p_base = nullptr; }
     r->p2p_world = 0;
+    return VV_OK;
+}
+
+int vv_debug_walk(VVRenderer *r, const float pos[3], int dir_sign, int n_steps, int walk_variant, float *out, size_t out_bytes)
+{
+    if (!r || !pos || !out) return fail(VV_ERR_INVALID, "vv_debug_walk: null argument");
+    if (n_steps < 1 || out_bytes < (size_t)n_steps * 16 * sizeof(float)) return fail(VV_ERR_INVALID, "vv_debug_walk: output buffer too small");
+    CU(cudaSetDevice(r->device));
+    DevParams P;
+    int rc = fill_params(r, P, false, true);
+    if (rc) return rc;
+    if (r->field_layout != LAYOUT_PAIR) return fail(VV_ERR_STATE, "vv_debug_walk: x-pair field layout only");
+    const bool grad = (r->illum_mode == ILLUM_GRADIENT);
+    if (n_steps > (dir_sign < 0 ? P.nBwd : P.nFwd)) return fail(VV_ERR_INVALID, "vv_debug_walk: more steps than the LIC parameters have");
+    if (walk_variant != 0 && !P.guardOk) return fail(VV_ERR_STATE, "vv_debug_walk: no guard band for this field / these LIC parameters");
+    if (walk_variant == 3 && !(grad && P.noiseShared)) return fail(VV_ERR_STATE, "vv_debug_walk: the noise does not share the field's cells");
+    if (walk_variant != 0 && walk_variant != 1 && walk_variant != 3) return fail(VV_ERR_INVALID, "vv_debug_walk: bad variant");
+    if (grad && !P.noise_bf) return fail(VV_ERR_STATE, "vv_debug_walk: bf16 noise layout only");
+    DevBuf<float> d;
+    CU(d.ensure((size_t)n_steps * 16));
+    CU(cudaMemsetAsync(d.p, 0, (size_t)n_steps * 16 * sizeof(float), r->stream));
+    CU(launch_debug_walk(P, grad, walk_variant, pos, dir_sign, n_steps, d.p, r->stream));
+    CU(cudaMemcpyAsync(out, d.p, (size_t)n_steps * 16 * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+    CU(cudaStreamSynchronize(r->stream));
     return VV_OK;
 }
 
