@@ -111,7 +111,10 @@ VV_API int vv_update_slices(VVRenderer *r);
 
 /* ---- inputs: setVolumeData/setDataTex (VectorDataSet), VV/renderer.h:48-60, VV/dataset.cpp:97-366 --- */
 /* FLOAT3 / UCHAR3 vector field; `next` may be NULL (single time step).  Packs to the RGBA16F texture
- * contents of VectorDataSet::createTextureIterp (VV/dataset.cpp:290-366, 533-635) on the GPU. */
+ * contents of VectorDataSet::createTextureIterp (VV/dataset.cpp:290-366, 533-635) on the GPU: bit-identical for FLOAT3.
+ * UCHAR3 is a stated DEVIATION: the path the reference runs subtracts 128 in `unsigned char` IN PLACE on every call
+ * (VV/dataset.cpp:563-571: u = 100 -> 228, never negative, and the source is mutated again by the next frame); here a
+ * UCHAR3 component is the signed (float)u - 128 of the reference's non-mutating fillTexDataFloat (VV/dataset.cpp:474-490). */
 VV_API int vv_set_vector_field(VVRenderer *r, const void *data, const void *next, int dtype,
                                const int dims[3], const float slice_dist[3]);
 /* interpIndex / InterpSize of VectorDataSet (VV/dataset.cpp:202-210, VV/3DLIC.cpp:705): re-packs on the GPU */
@@ -211,34 +214,8 @@ VV_API void vv_app_state_init(VVAppState *s);
 VV_API int vv_key_apply(VVAppState *s, int key, int special);
 VV_API int vv_keyboard(VVRenderer *r, VVAppState *s, int key, int special);
 
-/* ---- mouse interaction: mouseInteract / mouseMotionInteract of VV/3DLIC.cpp:490-600 --------------------------------------------
- * VVInteractState is the counterpart of the application's cam, light, clipPlanes[3], mouseMode and mousePosOld globals
- * (VV/3DLIC.h:12-52).  vv_mouse = a button press (which object the drag addresses: camera, or with Ctrl the selected clip plane
- * or else the light; Shift locks rotations to the nearest axis / diagonal, Transform::update), vv_motion = one mouse-move event
- * (trackball rotation VV/trackball.cpp:47-74, camera translate / dolly VV/camera.cpp:71-81, light / plane distance).  Plain host
- * logic with the reference's float / double expressions: the quaternions, positions and plane equations are the same bits.
- * vv_apply_interaction hands camera, light and clip planes (activation from VVAppState, may be NULL) to a renderer. */
-typedef struct VVTransformState {       /* Transform / Camera, VV/transform.h:44-118, VV/camera.h */
-    float q_internal[4], q[4];          /* x, y, z, w: orientation before / after the lock */
-    int   locked;
-    float dist;
-    float pos[3];                       /* Camera::_pos */
-} VVTransformState;
-typedef enum VVMouseMode {              /* MouseMode, VV/types.h:73-82 */
-    VV_MOUSE_ROTATE = 0, VV_MOUSE_TRANSLATE, VV_MOUSE_DOLLY, VV_MOUSE_ROTATE_LIGHT, VV_MOUSE_TRANSLATE_LIGHT, VV_MOUSE_ROTATE_CLIP,
-    VV_MOUSE_TRANSLATE_CLIP
-} VVMouseMode;
-enum { VV_BUTTON_LEFT = 0, VV_BUTTON_MIDDLE = 1, VV_BUTTON_RIGHT = 2, VV_MOD_SHIFT = 1, VV_MOD_CTRL = 2 };   /* GLUT values */
-typedef struct VVInteractState {
-    VVTransformState cam, light, clip[3];
-    double clip_normal[3][4];           /* ClipPlane::_normal: q * (0, 0, -1) and the distance */
-    int w, h, mouse_mode, old_x, old_y;
-} VVInteractState;
-VV_API void vv_interact_init(VVInteractState *s, int width, int height);
-VV_API void vv_interact_resize(VVInteractState *s, int width, int height);
-VV_API void vv_mouse(VVInteractState *s, int selected_clip, int button, int x, int y, int modifiers);
-VV_API void vv_motion(VVInteractState *s, int selected_clip, int x, int y);
-VV_API int  vv_apply_interaction(VVRenderer *r, const VVInteractState *s, const VVAppState *app);
+/* (Mouse interaction -- trackball, translate, dolly of VV/3DLIC.cpp:490-600 -- is caller-side state handling and not part of this
+ * library: a caller hands its camera, light and clip planes to vv_set_camera / vv_set_light / vv_set_clip_plane.) */
 
 /* User clip planes: ClipPlane::setNormal(x, y, z, d) + activation (VV/transform.cpp:296-315, 446-483), index 0..2 =
  * GL_CLIP_PLANE0 + index (VV/3DLIC.cpp:763-781).  equation = (n.xyz, d) in volume-centred object coordinates, the

@@ -579,71 +579,6 @@ def test_random_host_preprocessing(oracle, tmp_path, seed):
     assert np.array_equal(data, mine) and inv == minv
 
 
-@pytest.mark.skipif(not refhost.has_app(), reason="oracle/_ref built without VV/3DLIC.cpp")
-def test_mouse_interaction_matches_the_application(vv, tmp_path):
-    """vv_mouse / vv_motion against mouseInteract / mouseMotionInteract of VV/3DLIC.cpp:490-600 (with VV/transform.cpp, trackball.cpp,
-    camera.cpp, mmath.cpp behind them), compiled unmodified and called directly: random drags with every button / modifier
-    combination -- trackball rotation of the camera, of the light and (in camera space) of the selected clip plane, axis locking
-    with Shift, camera translate / dolly, light and plane distance.  Quaternions, positions, distances and plane equations are
-    compared bit for bit."""
-    from vectorvisualization_b200 import configs, fields as F
-    s = configs.cfg1(n=8, size=16)
-    dat = F.write_dat(str(tmp_path / "vol.dat"), s.field, slice_thickness=s.slice_dist)
-    with open(dat, "a") as f:
-        f.write("TimeDependent: 0 0\n")
-
-    def ours(width, height, events):
-        st = vv.InteractState(width, height)
-        sel = -1
-        for typ, button, x, y, mod in events:
-            if typ == 0:
-                st.mouse(button, x, y, mod, sel)
-            elif typ == 1:
-                st.motion(x, y, sel)
-            else:
-                sel = button
-        objs = [st.cam, st.light, st.clip[0], st.clip[1], st.clip[2]]
-        out = np.zeros((5, 13), np.float32)
-        for k, t in enumerate(objs):
-            out[k, 0:4] = list(t.q_internal); out[k, 4:8] = list(t.q); out[k, 8] = t.dist
-            out[k, 9:12] = list(t.pos) if k == 0 else 0.0
-            out[k, 12] = t.locked
-        normals = np.array([[st.clip_normal[i][k] for k in range(4)] for i in range(3)], np.float64)
-        return out, normals
-
-    def check(width, height, events):
-        a, an = ours(width, height, events)
-        b, bn = refhost.app_mouse(dat, width, height, events)
-        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (events, a, b)
-        assert np.array_equal(an.view(np.uint64), bn.view(np.uint64)), (events, an, bn)
-        return a, an
-
-    a, an = check(640, 480, [])
-    assert np.array_equal(a[0, :9], [0, 0, 0, 1, 0, 0, 0, 1, 4]) and a[1, 8] == 1.0               # Camera / light defaults
-    assert np.allclose(an, [[-1, 0, 0, 0], [0, -1, 0, 0], [0, 0, -1, 0]], atol=1e-6)              # VV/3DLIC.cpp:763-764
-    rng = np.random.RandomState(21)
-    for trial in range(40):
-        width, height = int(rng.randint(200, 1400)), int(rng.randint(150, 1000))
-        events = []
-        for drag in range(int(rng.randint(1, 6))):
-            if rng.rand() < 0.4:
-                events.append((2, int(rng.randint(-1, 3)), 0, 0, 0))                               # keys '1'-'4'
-            button = int(rng.randint(0, 3))
-            mod = int(rng.choice([0, 0, vv.MOD_SHIFT, vv.MOD_CTRL, vv.MOD_CTRL | vv.MOD_SHIFT]))
-            x, y = int(rng.randint(0, width)), int(rng.randint(0, height))
-            events.append((0, button, x, y, mod))
-            for _ in range(int(rng.randint(1, 12))):
-                if rng.rand() < 0.1:
-                    events.append((1, 0, x, y, mod))                                               # a motion event without movement
-                x = int(np.clip(x + rng.randint(-40, 41), -20, width + 20))
-                y = int(np.clip(y + rng.randint(-40, 41), -20, height + 20))
-                events.append((1, 0, x, y, mod))
-        check(width, height, events)
-    # light distance clamp (VV/3DLIC.cpp:574-576) and a long locked rotation
-    check(800, 600, [(0, 2, 400, 300, vv.MOD_CTRL)] + [(1, 0, 400, 300 - 60 * k, vv.MOD_CTRL) for k in range(1, 12)])
-    check(800, 600, [(0, 0, 100, 100, vv.MOD_SHIFT)] + [(1, 0, 100 + 17 * k, 100 + 9 * k, vv.MOD_SHIFT) for k in range(1, 30)])
-
-
 def test_scalar_volume_loader(vv, oracle, tmp_path):
     """VolumeDataSet::loadData + createTexture (VV/dataset.cpp:840-1050): the scalar volume goes to the GL as it is on disk -- UCHAR
     or FLOAT source, GL_LUMINANCE, LINEAR, CLAMP_TO_EDGE -- and the product's DAT / RAW reader hands over the same bytes; a FLOAT

@@ -957,30 +957,6 @@ def test_idle_tick_animation(vv, tmp_path):
             assert np.array_equal(got.view(np.uint32), vvo.half_round(tex).view(np.uint32)), k
 
 
-def test_mouse_interaction_drives_the_renderer(vv):
-    """vv_apply_interaction: the camera a trackball drag produces (vv_mouse / vv_motion, pinned against VV/3DLIC.cpp on the CPU)
-    renders the same frame as a scene configured directly with that quaternion"""
-    from vectorvisualization_b200 import configs
-    from vectorvisualization_b200.configs import apply_scene
-    s = configs.cfg1(n=32, size=64)
-    r = vv.Renderer(0)
-    apply_scene(r, s)
-    it = vv.InteractState(64, 64)
-    it.mouse(vv.BUTTON_LEFT, 20, 20)
-    for x, y in ((30, 26), (41, 30), (47, 44)):
-        it.motion(x, y)
-    it.mouse(vv.BUTTON_RIGHT, 10, 10)
-    it.motion(10, 22)                         # dolly
-    r.applyInteraction(it)
-    r.render(True)
-    a, na = r.readRGBA32F(), r.lastRaySamples()
-    s2 = configs.cfg1(n=32, size=64)
-    s2.camera = dict(quat=tuple(it.cam.q), pos=tuple(it.cam.pos), dist=it.cam.dist, fovy=35.0)
-    _, b, _, _, nb = render_cuda(vv, s2)
-    assert tuple(it.cam.q) != (0.0, 0.0, 0.0, 1.0) and it.cam.pos[2] != 0.0
-    assert na == nb and na > 0 and np.array_equal(a, b)
-
-
 def test_float_target_outputs(vv, oracle, tmp_path):
     """enableFBO (key 'F'): the stored frame is an RGBA16F texture (VV/renderer.cpp:562-606) -- read back rounded to fp16 -- and
     saveTexture writes a float texture as (int)(255 * texel), truncated (VV/renderer.cpp:386-403)"""

@@ -81,34 +81,6 @@ class TimeCursor(ctypes.Structure):
         return used, bool(adv.value)
 
 
-class TransformState(ctypes.Structure):
-    _fields_ = [("q_internal", ctypes.c_float * 4), ("q", ctypes.c_float * 4), ("locked", ctypes.c_int), ("dist", ctypes.c_float),
-                ("pos", ctypes.c_float * 3)]
-
-
-MOUSE_ROTATE, MOUSE_TRANSLATE, MOUSE_DOLLY, MOUSE_ROTATE_LIGHT, MOUSE_TRANSLATE_LIGHT, MOUSE_ROTATE_CLIP, MOUSE_TRANSLATE_CLIP = range(7)
-BUTTON_LEFT, BUTTON_MIDDLE, BUTTON_RIGHT, MOD_SHIFT, MOD_CTRL = 0, 1, 2, 1, 2
-
-
-class InteractState(ctypes.Structure):
-    """VVInteractState: camera, light and clip planes as the reference's mouse handlers move them (VV/3DLIC.cpp:490-600)"""
-    _fields_ = [("cam", TransformState), ("light", TransformState), ("clip", TransformState * 3), ("clip_normal", (ctypes.c_double * 4) * 3),
-                ("w", ctypes.c_int), ("h", ctypes.c_int), ("mouse_mode", ctypes.c_int), ("old_x", ctypes.c_int), ("old_y", ctypes.c_int)]
-
-    def __init__(self, width=1280, height=960):
-        super().__init__()
-        load_library().vv_interact_init(ctypes.byref(self), width, height)
-
-    def resize(self, width, height):
-        load_library().vv_interact_resize(ctypes.byref(self), width, height)
-
-    def mouse(self, button, x, y, modifiers=0, selected_clip=-1):
-        load_library().vv_mouse(ctypes.byref(self), selected_clip, button, x, y, modifiers)
-
-    def motion(self, x, y, selected_clip=-1):
-        load_library().vv_motion(ctypes.byref(self), selected_clip, x, y)
-
-
 class DatInfo(ctypes.Structure):
     _fields_ = [("raw_file", ctypes.c_char * 512), ("resolution", ctypes.c_int * 3), ("slice_thickness", ctypes.c_float * 3),
                 ("data_type", ctypes.c_int), ("data_dim", ctypes.c_int), ("time_begin", ctypes.c_int), ("time_end", ctypes.c_int)]
@@ -154,8 +126,6 @@ def load_library():
         "vv_enable_lowres": ([P, I], I), "vv_set_window": ([P, I, I], I),
         "vv_time_cursor_init": ([P, I, I, I], None), "vv_time_cursor_next": ([P], I), "vv_time_cursor_tick": ([P, P], I),
         "vv_idle": ([P], I), "vv_get_time_cursor": ([P, P], I),
-        "vv_interact_init": ([P, I, I], None), "vv_interact_resize": ([P, I, I], None), "vv_mouse": ([P, I, I, I, I, I], None),
-        "vv_motion": ([P, I, I, I], None), "vv_apply_interaction": ([P, P, P], I),
         "vv_app_state_init": ([P], None), "vv_key_apply": ([P, I, I], I), "vv_keyboard": ([P, P, I, I], I),
         "vv_enable_float_target": ([P, I], I), "vv_set_option": ([P, I, I], I),
         "vv_set_mc_offsets": ([P, P, I, I], I), "vv_update_mc_offset_tex": ([P, I, I, ctypes.c_uint32], I),
@@ -306,10 +276,6 @@ class Renderer:
         if act < 0:
             _chk(1)
         return act
-
-    def applyInteraction(self, interact, app=None):
-        """camera, light and clip planes of an InteractState (activation from an AppState) -> this renderer"""
-        _chk(self._lib.vv_apply_interaction(self._h, ctypes.byref(interact), ctypes.byref(app) if app is not None else None))
 
     def idle(self):
         """one animation tick of idle() (VV/3DLIC.cpp:129-172) for a field loaded with loadDat"""

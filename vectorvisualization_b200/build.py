@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libvv_b200.so")
 VOLIC = os.path.join(HERE, "volic")
 
 CU_SOURCES = ["vv_kernels.cu", "vv_preprocess.cu", "vv_renderer.cu"]
-CPP_SOURCES = ["vv_io.cpp", "vv_keys.cpp", "vv_interact.cpp"]
+CPP_SOURCES = ["vv_io.cpp", "vv_keys.cpp"]
 OPTIONAL_CPP = ["vv_illum.cpp"]
 
 NVCC_FLAGS = [

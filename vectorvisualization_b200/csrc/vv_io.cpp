@@ -33,7 +33,21 @@ static int paeth(int a, int b, int c)
     return (pb <= pc) ? b : c;
 }
 
+static bool png_read_impl(const char *path, std::vector<uint8_t> &out, int &w, int &h, int &channels, std::string &err);
+
+// no exception leaves this function: its callers are extern "C" entry points (a hostile header could otherwise size a vector
+// the allocator refuses)
 bool png_read_file(const char *path, std::vector<uint8_t> &out, int &w, int &h, int &channels, std::string &err)
+{
+    try {
+        return png_read_impl(path, out, w, h, channels, err);
+    } catch (const std::exception &e) {
+        err = std::string("PNG read failed: ") + e.what();
+        return false;
+    }
+}
+
+static bool png_read_impl(const char *path, std::vector<uint8_t> &out, int &w, int &h, int &channels, std::string &err)
 {
     FILE *fp = std::fopen(path, "rb");
     if (!fp) { err = std::string("Could not open PNG file ") + path; return false; }
@@ -54,7 +68,10 @@ bool png_read_file(const char *path, std::vector<uint8_t> &out, int &w, int &h, 
         if (pos + 12 + len > buf.size()) { err = "truncated PNG chunk"; return false; }
         const uint8_t *d = &buf[pos + 8];
         if (!std::memcmp(type, "IHDR", 4)) {
-            w = (int)be32(d); h = (int)be32(d + 4); bitDepth = d[8]; colorType = d[9]; interlace = d[12];
+            if (len != 13) { err = "bad PNG header"; return false; }
+            const uint32_t uw = be32(d), uh = be32(d + 4);
+            if (uw == 0 || uh == 0 || uw > 65536u || uh > 65536u) { err = "PNG dimensions out of range"; return false; }
+            w = (int)uw; h = (int)uh; bitDepth = d[8]; colorType = d[9]; interlace = d[12];
         } else if (!std::memcmp(type, "PLTE", 4)) {
             plte.assign(d, d + len);
         } else if (!std::memcmp(type, "IDAT", 4)) {
@@ -64,6 +81,8 @@ bool png_read_file(const char *path, std::vector<uint8_t> &out, int &w, int &h, 
         }
         pos += 12 + len;
     }
+    if (w <= 0 || h <= 0) { err = "PNG without header"; return false; }
+    if (idat.empty()) { err = "PNG without image data"; return false; }
     if (bitDepth != 8) { err = "pngRead: currently only 8 Bit per channel are supported."; return false; }   // imageUtils.cpp:71-77
     if (interlace) { err = "pngRead: interlaced PNG not supported"; return false; }
     int srcCh;
@@ -356,6 +375,7 @@ int vv_png_read(const char *path, uint8_t **data, int *w, int *h, int *channels)
     std::string err;
     if (!png_read_file(path, img, *w, *h, *channels, err)) return fail(VV_ERR_IO, err);
     *data = (uint8_t *)std::malloc(img.size());
+    if (!*data) return fail(VV_ERR_IO, "vv_png_read: out of memory");
     std::memcpy(*data, img.data(), img.size());
     return VV_OK;
 }

@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(256) ray_setup_kernel(const __grid_constant__ 
         if (px < P.width && py < P.height && pixel_ray(P, px, py, e)) {
             ray_setup(P, e, pos, dir, dstep);
             mc_offset(P, px, py, pos, dstep);
-            const int maxSamples = P.numIter * P.numIter;
+            const int maxSamples = (int)min((unsigned int)P.numIter * (unsigned int)P.numIter, 0x7fffffffu);   // numIter <= 32768
             f3 q = pos;
             for (;;) {                                  // the march of lic3d_fragment.glsl:38-95 without the shading
                 ++n;

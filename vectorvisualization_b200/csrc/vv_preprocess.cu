@@ -1,6 +1,8 @@
 // vv_preprocess.cu -- bandwidth-bound pre-processing kernels: the GPU versions of the host loops the
 // reference runs before it uploads its textures.  All arithmetic uses explicit round-to-nearest intrinsics in the
-// reference's evaluation order, so the results are bit-identical to the CPU loops they replace.
+// reference's evaluation order, so the results are bit-identical to the CPU loops they replace (one stated exception: UCHAR3
+// vector components are the signed (float)u - 128 of fillTexDataFloat, VV/dataset.cpp:474-490, not the in-place unsigned
+// wrap-around of the interpolating path, VV/dataset.cpp:563-571).
 //
 //   pack_field_*        VectorDataSet::fillTexDataFloatInterp      VV/dataset.cpp:533-635
 //   build_cell8/quad    sampler state baked into the layout         VV/dataset.cpp:1033-1038,1328-1335

@@ -1105,7 +1105,9 @@ int vv_set_lic_params(VVRenderer *r, const VVLicParams *p)
     if (p->stepsForward < 0 || p->stepsBackward < 0 || p->stepsForward > kMaxLicSteps || p->stepsBackward > kMaxLicSteps)
         return fail(VV_ERR_INVALID, "LIC steps out of range (0..1024 per direction)");
     if (!(p->stepSizeVol > 0.0f)) return fail(VV_ERR_INVALID, "stepSizeVol must be > 0");
-    if (p->numIterations <= 0) return fail(VV_ERR_INVALID, "numIterations must be > 0");
+    // the shader's two nested loops give numIterations^2 samples per ray at most (lic3d_fragment.glsl:38-40); bounded so that the
+    // product fits 32 bits in every kernel and the sample buffer stays finite
+    if (p->numIterations <= 0 || p->numIterations > 32768) return fail(VV_ERR_INVALID, "numIterations must be in 1..32768");
     const bool steps_changed = p->stepsForward != r->lp.stepsForward || p->stepsBackward != r->lp.stepsBackward;
     r->lp = *p;
     if (steps_changed) r->tables_dirty = true;
@@ -1655,6 +1657,10 @@ int vv_p2p_render(VVRenderer *r)
     if (rc) return rc;
     if (r->world == 1) return VV_OK;
     if (!r->p2p_base || !r->p2p_peer[r->world - 1] || !r->p2p_peer[0]) return fail(VV_ERR_STATE, "vv_p2p_render: not connected (vv_p2p_export / vv_p2p_connect)");
+    // the gather buffers (here and in every peer) were sized by vv_p2p_export for the frame size and partition of that moment: a
+    // vv_resize / vv_set_partition since then would make the stores below land outside the peers' buffers
+    if (r->world != r->p2p_world || (size_t)r->world * r->blocks_per_rank * kBlockPixels * sizeof(float4) != r->p2p_tile_bytes)
+        return fail(VV_ERR_STATE, "vv_p2p_render: frame size or partition changed since vv_p2p_export (export and connect again on every rank)");
     const unsigned int parity = r->p2p_epoch & 1u;
     P2PArgs a;
     std::memset(&a, 0, sizeof(a));
