@@ -28,6 +28,11 @@ typedef struct RefUniforms {
     float spot_exponent;
     RefTex mc_offset;             /* mcOffsetSampler: F_L32F [frame height][frame width] (USE_MC_OFFSET programs) */
     int frag_x0, frag_y0, frag_w; /* fragment i of a run is pixel (frag_x0 + i % frag_w, frag_y0 + i / frag_w); frag_w = 0: unset */
+    /* the frame-buffer side of the FBO slicing pass (Renderer::sliceVolume, VV/renderer.cpp:1176-1225), which the reference leaves
+     * to the GL: slice_count > 0 = two ping-pong targets per pixel, a fragment's .w is its slice index (slice i samples the target
+     * of slice i - 1 and is written to the other one; the frame is the target of slice slice_count - 1); 0 = one accumulator.
+     * fbo_fp16: the targets are GL_RGBA16F_ARB (VV/renderer.cpp:566-606), every write rounds to fp16. */
+    int slice_count, fbo_fp16;
 } RefUniforms;
 
 /* sets the gl_* state shared by all programs */

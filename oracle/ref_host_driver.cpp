@@ -376,6 +376,7 @@ struct DrawRec {
     unsigned program, mode;
     int cull, clip_mask, viewport[4];
     int blend, blend_src, blend_dst;
+    unsigned fbo_tex, bound_tex;    /* texture attached as colour target / texture bound last (the slicing pass binds its source, VV/renderer.cpp:1213) */
     Mat4 mv, proj;
     double clip_eye[6][4];
     std::vector<double> v;          /* x y z s t r per vertex */
@@ -580,6 +581,8 @@ void glDisable(GLenum cap)
 }
 void glUseProgramObjectARB(GLhandleARB program) { g_program = program; }
 void glBlendFunc(GLenum src, GLenum dst) { g_blend_src = (int)src; g_blend_dst = (int)dst; }
+static unsigned g_fbo_tex = 0;
+void glFramebufferTexture2DEXT(GLenum, GLenum attachment, GLenum, GLuint texture, GLint) { if (attachment == GL_COLOR_ATTACHMENT0_EXT) g_fbo_tex = texture; }
 void glBegin(GLenum mode)
 {
     g_in_prim = true;
@@ -587,6 +590,7 @@ void glBegin(GLenum mode)
     DrawRec d;
     d.program = g_program; d.mode = mode; d.cull = g_cull; d.clip_mask = g_clip_mask;
     d.blend = g_blend; d.blend_src = g_blend_src; d.blend_dst = g_blend_dst;
+    d.fbo_tex = g_fbo_tex; d.bound_tex = g_bound;
     for (int k = 0; k < 4; ++k) d.viewport[k] = g_viewport[k];
     d.mv = g_mv.back(); d.proj = g_proj.back();
     std::memcpy(d.clip_eye, g_clip_eye, sizeof(d.clip_eye));
@@ -677,13 +681,14 @@ int vvref_cube_faces(const char *dat, float *verts, float *tex, int cap)
 static int serialize_draws(double *out, int cap)
 {
     size_t need = 1;
-    for (const DrawRec &d : g_draws) need += 4 + 3 + 4 + 16 + 16 + 24 + 1 + d.v.size();
+    for (const DrawRec &d : g_draws) need += 4 + 3 + 2 + 4 + 16 + 16 + 24 + 1 + d.v.size();
     if ((size_t)cap < need) { g_draws.clear(); return -2; }
     size_t k = 0;
     out[k++] = (double)g_draws.size();
     for (const DrawRec &d : g_draws) {
         out[k++] = d.program; out[k++] = d.mode; out[k++] = d.cull; out[k++] = d.clip_mask;
         out[k++] = d.blend; out[k++] = d.blend_src; out[k++] = d.blend_dst;
+        out[k++] = d.fbo_tex; out[k++] = d.bound_tex;
         for (int i = 0; i < 4; ++i) out[k++] = d.viewport[i];
         for (int i = 0; i < 16; ++i) out[k++] = d.mv.m[i];
         for (int i = 0; i < 16; ++i) out[k++] = d.proj.m[i];
@@ -701,7 +706,9 @@ static int serialize_draws(double *out, int cap)
  *   program, mode, cull, clip_mask, blend enabled, blend src, blend dst, viewport[4], modelview[16], projection[16], clip planes in eye space [6][4], nverts,
  *   nverts x (x y z s t r)
  * The ray-cast program has the handle 77, the slicing program 79 (set below; no GLSL is compiled in the shim); slicing = 1
- * renders with VOLIC_SLICING (after Renderer::updateSlices), 2 with VOLIC_LICVOLUME (program 81) instead of VOLIC_RAYCAST; step_size_vol > 0 overrides LICParams.  planes: up to 3 user clip planes
+ * renders with VOLIC_SLICING through the FBO ping-pong (after Renderer::updateSlices), 3 with VOLIC_SLICING without the FBO (program 82 +
+ * fixed-function blending), 2 with VOLIC_LICVOLUME (program 81) instead of VOLIC_RAYCAST; per primitive also the texture attached as
+ * colour target and the texture bound last (after blend dst); step_size_vol > 0 overrides LICParams.  planes: up to 3 user clip planes
  * (n.xyz, d) as ClipPlane::setNormal takes them, active[i] != 0 to enable; frames >= 1: how many frames to render, the last one
  * is the one returned.  Returns the number of doubles written, < 0 on error. */
 int vvref_raycast_draws(const char *dat, const float cam_quat[4], const float cam_pos[3], float cam_dist, int width, int height,
@@ -746,12 +753,23 @@ int vvref_raycast_draws(const char *dat, const float cam_quat[4], const float ca
     r._sliceShader._programObj = 79;
     std::memset(&r._paramSlice, 0xff, sizeof(r._paramSlice));
     r._paramSlice.imageFBOSampler = 20;                                 /* sliceVolume returns early without it (:1127) */
+    /* the two image textures get their names in Renderer::initFBO (VV/renderer.cpp:547-555), which needs a GL; any two distinct
+     * names do -- what is recorded is which of them is the colour target / the bound source of every primitive */
+    r._imgBufferTex0->setTex(GL_TEXTURE_RECTANGLE_ARB, 501, "FBO-Tex0");
+    r._imgBufferTex0->texUnit = GL_TEXTURE1_ARB;
+    r._imgBufferTex1->setTex(GL_TEXTURE_RECTANGLE_ARB, 502, "FBO-Tex1");
+    r._imgBufferTex1->texUnit = GL_TEXTURE1_ARB;
     r.enableLowRes(lowres != 0);
     r.resize(width, height);                                            /* VV/3DLIC.cpp:174-200 */
     r._licRaycastShader._programObj = 81;
     std::memset(&r._paramLicRaycast, 0xff, sizeof(r._paramLicRaycast));
     if (slicing == 2) {
         r.setTechnique(VOLIC_LICVOLUME);                                /* ray-cast of the LIC volume (F4) */
+    } else if (slicing == 3) {
+        r._useFBO = false;                                              /* the start-up state of F3: lic3d_slicingblend + fixed-function blending */
+        r._sliceBlendShader._programObj = 82;
+        std::memset(&r._paramSliceBlend, 0xff, sizeof(r._paramSliceBlend));
+        r.setTechnique(VOLIC_SLICING);
     } else if (slicing) {
         r._useFBO = true;                                               /* the FBO ping-pong branch of sliceVolume (keys F3, VV/3DLIC.cpp:457-475) */
         r.setTechnique(VOLIC_SLICING);
@@ -763,7 +781,7 @@ int vvref_raycast_draws(const char *dat, const float cam_quat[4], const float ca
     glViewport(0, 0, width, height);                                    /* resize callback, VV/3DLIC.cpp:176 */
     /* `frames` calls of render(true); the LAST one is recorded.  (The first frame differs for non-unit plane normals:
      * drawClippedPolygon normalises ClipPlane::_normal in place, VV/renderer.cpp:1301 -> VV/slicing.cpp:337-348.) */
-    if (slicing == 1) r.updateSlices();                                      /* VV/3DLIC.cpp:168, 469 */
+    if (slicing == 1 || slicing == 3) r.updateSlices();                      /* VV/3DLIC.cpp:168, 469 */
     for (int f = 0; f < frames; ++f) {
         g_draws.clear();
         g_record_draws = true;

@@ -53,13 +53,14 @@ void glViewport(GLint x, GLint y, GLsizei w, GLsizei h);
 void glMultiTexCoord3fARB(GLenum unit, GLfloat x, GLfloat y, GLfloat z);
 void glTexCoord3f(GLfloat s, GLfloat t, GLfloat r);      /* captured: current texcoord0 */
 void glUseProgramObjectARB(GLhandleARB program);       /* the program bound when a primitive is drawn */
+void glFramebufferTexture2DEXT(GLenum target, GLenum attachment, GLenum textarget, GLuint texture, GLint level);   /* captured: the
+                                                        colour target a primitive is drawn into (the slicing pass's ping-pong) */
 /* ---- no-ops ---- */
 static inline void glNormal3f(GLfloat, GLfloat, GLfloat) {}
 static inline void glDepthMask(GLboolean) {}
 static inline void glBindFramebufferEXT(GLenum, GLuint) {}
 static inline void glBindRenderbufferEXT(GLenum, GLuint) {}
 static inline void glFramebufferTexture1DEXT(GLenum, GLenum, GLenum, GLuint, GLint) {}
-static inline void glFramebufferTexture2DEXT(GLenum, GLenum, GLenum, GLuint, GLint) {}
 static inline void glFramebufferTexture3DEXT(GLenum, GLenum, GLenum, GLuint, GLint, GLint) {}
 static inline void glFramebufferRenderbufferEXT(GLenum, GLenum, GLenum, GLuint) {}
 static inline void glRenderbufferStorageEXT(GLenum, GLenum, GLsizei, GLsizei) {}

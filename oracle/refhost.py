@@ -251,8 +251,9 @@ def _parse_draws(out, n):
     draws = []
     for _ in range(int(out[0])):
         d = dict(program=int(out[k]), mode=int(out[k + 1]), cull=int(out[k + 2]), clip_mask=int(out[k + 3]),
-                 blend=int(out[k + 4]), blend_func=(int(out[k + 5]), int(out[k + 6])), viewport=[int(x) for x in out[k + 7:k + 11]])
-        k += 11
+                 blend=int(out[k + 4]), blend_func=(int(out[k + 5]), int(out[k + 6])), fbo_tex=int(out[k + 7]), bound_tex=int(out[k + 8]),
+                 viewport=[int(x) for x in out[k + 9:k + 13]])
+        k += 13
         d["modelview"] = out[k:k + 16].reshape(4, 4).T.copy(); k += 16          # column-major -> [row][col]
         d["projection"] = out[k:k + 16].reshape(4, 4).T.copy(); k += 16
         d["clip_eye"] = out[k:k + 24].reshape(6, 4).copy(); k += 24

@@ -30,7 +30,8 @@ class RefUniforms(ctypes.Structure):
         ("alphaCorrection", ctypes.c_float), ("licParams", ctypes.c_float * 3), ("licKernel", ctypes.c_float * 3),
         ("camera", ctypes.c_float * 4), ("light_position", ctypes.c_float * 4), ("light_ambient", ctypes.c_float * 4),
         ("light_diffuse", ctypes.c_float * 4), ("light_specular", ctypes.c_float * 4), ("spot_exponent", ctypes.c_float),
-        ("mc_offset", RefTex), ("frag_x0", ctypes.c_int), ("frag_y0", ctypes.c_int), ("frag_w", ctypes.c_int)]
+        ("mc_offset", RefTex), ("frag_x0", ctypes.c_int), ("frag_y0", ctypes.c_int), ("frag_w", ctypes.c_int),
+        ("slice_count", ctypes.c_int), ("fbo_fp16", ctypes.c_int)]
 
 
 _lib = None
@@ -189,11 +190,12 @@ class RefScene:
         cm[y0:y1, x0:x1] = cnt.reshape(y1 - y0, x1 - x0)
         return img, cm, int(cnt.sum())
 
-    def slicing(self, fragments=None):
+    def slicing(self, fragments=None, fbo_fp16=1, fbo_pingpong=1):
         """lic3d_slicing_fragment.glsl over the oracle's slice geometry; the shader hard-codes TF index .a and the
         tfData.a > 0.05 gate, so the scene must use tf_mode A / gate TF_ALPHA.
-        fragments: optional (starts int32 [h*w + 1], frags [n][3]) per-pixel fragment lists in draw order to shade instead
-        (oracle/softgl.py fragment_lists of the reference's own slice polygons)"""
+        fragments: optional (starts int32 [h*w + 1], frags [n][4] = texcoord.xyz + slice index) per-pixel fragment lists in draw
+        order to shade instead (oracle/softgl.py fragment_lists of the reference's own slice polygons).
+        fbo_fp16 / fbo_pingpong: the frame-buffer side as Renderer::sliceVolume runs it (see ref_api.h); 0 / 0 = one fp32 accumulator"""
         s = self.s
         assert s.tf_mode == 1 and s.gate_mode == 1
         d = s.defines or ""
@@ -209,11 +211,12 @@ class RefScene:
         L = lib()
         if fragments is not None:
             st = np.ascontiguousarray(fragments[0], np.int32)
-            fr = np.zeros((len(fragments[1]), 4), np.float32)
-            fr[:, :3] = fragments[1]
-            fr[:, 3] = 1.0
-        else:
-            _, _, nslices = self.o.slicing_setup()
+            fr = np.ascontiguousarray(fragments[1], np.float32)
+            assert fr.shape[1] == 4
+        _, _, nslices = self.o.slicing_setup()
+        self.u.slice_count = int(nslices) if fbo_pingpong else 0
+        self.u.fbo_fp16 = int(fbo_fp16)
+        if fragments is None:
             frags, starts = [], [0]
             buf = np.zeros((nslices, 4), np.float32)
             for y in range(s.height):

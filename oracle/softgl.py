@@ -121,11 +121,17 @@ def _raster_triangle(tri, width, height, emit, edge_dist=None):
     emit(gy[inside], gx[inside], attrs[inside])
 
 
-def _run(draws, width, height, program, emit, edge_dist):
+def _run(draws, width, height, program, emit, edge_dist, ordinal=None):
+    """ordinal: optional one-element list that is kept at the number of selected primitives before the current one (the slice
+    index of the slicing pass, which issues one glBegin / glEnd per slice whether or not the polygon is empty)"""
     facing = []
+    nth = -1
     for di, d in enumerate(draws):
         if program is not None and d["program"] != program:
             continue
+        nth += 1
+        if ordinal is not None:
+            ordinal[0] = nth
         for poly in _polygons(d):
             win = _to_window(d, poly)
             if win is None:
@@ -165,19 +171,21 @@ def rasterize(draws, width, height, program=None):
 
 def fragment_lists(draws, width, height, program=None):
     """Every fragment of every pixel in draw order (the slicing pass, VV/renderer.cpp:1176-1225: slice i reads what slices
-    0..i-1 left in the frame buffer).  Returns (starts int32 [H*W + 1], frags float64 [n][3], edge_dist [H][W]): the fragments
-    of pixel p = y * W + x are frags[starts[p]:starts[p + 1]]."""
+    0..i-1 left in the frame buffer).  Returns (starts int32 [H*W + 1], frags float64 [n][4], edge_dist [H][W]): the fragments
+    of pixel p = y * W + x are frags[starts[p]:starts[p + 1]], columns = texcoord0.xyz and the index of the primitive among those
+    drawn with `program` (= the slice index: which of the two ping-pong targets the fragment is written to)."""
     pix, att = [], []
     edge_dist = np.full((height, width), np.inf)
+    ordinal = [0]
 
     def emit(ys, xs, attrs):
         pix.append(ys.astype(np.int64) * width + xs)
-        att.append(attrs)
+        att.append(np.concatenate([attrs, np.full((len(attrs), 1), float(ordinal[0]))], axis=1))
 
-    _run(draws, width, height, program, emit, edge_dist)
+    _run(draws, width, height, program, emit, edge_dist, ordinal)
     starts = np.zeros(height * width + 1, np.int32)
     if not pix:
-        return starts, np.zeros((0, 3)), edge_dist
+        return starts, np.zeros((0, 4)), edge_dist
     pix = np.concatenate(pix)
     att = np.concatenate(att, axis=0)
     order = np.argsort(pix, kind="stable")                  # emission order is kept inside a pixel

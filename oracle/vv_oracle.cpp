@@ -877,16 +877,22 @@ uint64_t vvo_slicing_lic(const VVOScene *s, float *out_rgba, uint32_t *out_sampl
         for (int x = 0; x < s->width; ++x) {
             PixelRay r = pixel_dir(c, x, y);
             V4 dest = {0, 0, 0, 0};
+            /* the two ping-pong targets, both cleared (renderer.cpp:1164-1165 clears the one attached before the loop, :1210-1211
+             * the other one at i = 0); slice i is drawn into buf[(i + 1) & 1] and samples buf[i & 1] */
+            V4 buf[2] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
             uint32_t n = 0;
             const float mc = s->mc_offsets ? s->mc_offsets[(size_t)y * s->width + x] : -1.0f;
             for (int i = 0; i < sl.numSlices; ++i) {
                 V3 g;
                 if (!slice_fragment(c, sl, r, i, g)) continue;
                 bool shaded;
+                if (s->fbo_pingpong) dest = buf[i & 1];
                 dest = grad ? frag_slicing<true>(c, g, dest, shaded, mc) : frag_slicing<false>(c, g, dest, shaded, mc);
                 if (s->fbo_fp16) dest = {half_round(dest.x), half_round(dest.y), half_round(dest.z), half_round(dest.w)};
+                if (s->fbo_pingpong) buf[(i + 1) & 1] = dest;
                 if (shaded) ++n;
             }
+            if (s->fbo_pingpong) dest = buf[sl.numSlices & 1];      /* what is displayed / stored: the target of slice N - 1 */
             float *o = out_rgba + 4 * ((size_t)y * s->width + x);
             o[0] = dest.x; o[1] = dest.y; o[2] = dest.z; o[3] = dest.w;
             if (out_samples) out_samples[(size_t)y * s->width + x] = n;
@@ -989,7 +995,7 @@ int vvo_slice_fragments(const VVOScene *s, int x, int y, float *out, int cap)
     for (int i = 0; i < sl.numSlices && n < cap; ++i) {
         V3 g;
         if (!slice_fragment(c, sl, r, i, g)) continue;
-        out[4 * n] = g.x; out[4 * n + 1] = g.y; out[4 * n + 2] = g.z; out[4 * n + 3] = 1.0f;
+        out[4 * n] = g.x; out[4 * n + 1] = g.y; out[4 * n + 2] = g.z; out[4 * n + 3] = (float)i;   /* .w: the slice index */
         ++n;
     }
     return n;

@@ -84,9 +84,13 @@ typedef struct VVOScene {
     float  window_aspect;      /* Camera::setWindow (transform.h:79-80): aspect of gluPerspective when the frame is not the window
                                   (low-res preset: half-size viewport, renderer.cpp:111-119); 0 = width / height */
     int    fbo_fp16;           /* slicing: the ping-pong targets of the FBO path are GL_RGBA16F_ARB (renderer.cpp:566-606), so what a
-                                  slice reads back is the previous slices' result rounded to fp16.  0 (default, and what the shim's
-                                  frame-buffer stand-in and the CUDA path do): keep fp32; 1: round after every slice -- used to bound
-                                  the effect (tests/test_oracle_closed_form.py) */
+                                  slice reads back is the previous slices' result rounded to fp16.  1: round after every slice (what
+                                  the reference's targets do); 0: keep fp32 (the idealised model, used to bound the effect) */
+    int    fbo_pingpong;       /* slicing: Renderer::sliceVolume swaps _imgBufferTex0 / _imgBufferTex1 before EVERY slice and a slice
+                                  writes only the pixels its polygon covers (renderer.cpp:1201-1225): slice i reads the target of
+                                  slice i-1 and writes the other texture, whose uncovered pixels keep what slice i-2 left there.
+                                  The display pass and saveTexture read the target of the LAST slice (N-1).  1: two buffers per
+                                  pixel, exactly that; 0: one accumulator carried from fragment to fragment (idealised) */
 } VVOScene;
 
 /* ---- hot path ------------------------------------------------------- */

@@ -42,6 +42,7 @@ class Scene(ctypes.Structure):
         ("speed_of_flow", ctypes.c_int), ("licvol_fp16", ctypes.c_int), ("weight_bits", ctypes.c_int),
         ("mc_offsets", ctypes.c_void_p), ("num_clip_planes", ctypes.c_int), ("clip_planes", (ctypes.c_double * 4) * 3),
         ("near_clip", ctypes.c_float), ("far_clip", ctypes.c_float), ("window_aspect", ctypes.c_float), ("fbo_fp16", ctypes.c_int),
+        ("fbo_pingpong", ctypes.c_int),
     ]
 
 
@@ -177,7 +178,9 @@ class OracleScene:
     """Builds the VVOScene for a vectorvisualization_b200.configs.Scene using the ORACLE's own pre-processing
     (pack / gradients / filter), and keeps the numpy arrays alive."""
 
-    def __init__(self, s, weight_bits=0, illum_tables=None, fbo_fp16=0):
+    def __init__(self, s, weight_bits=0, illum_tables=None, fbo_fp16=1, fbo_pingpong=1):
+        """fbo_fp16 / fbo_pingpong: the FBO slicing path as Renderer::sliceVolume runs it (RGBA16F targets, two textures swapped per
+        slice); 0 / 0 = one fp32 accumulator per pixel (the idealised model)"""
         L = lib()
         self.s = s
         self.keep = []
@@ -229,7 +232,7 @@ class OracleScene:
         c.lowres = s.lowres; c.quirk_scalevolinv = s.quirk_scalevolinv
         c.quirk_luminance_alpha = 0 if s.with_gradients else s.quirk_luminance_alpha   # Q7 only bites GL_LUMINANCE noise
         c.speed_of_flow = 1 if "SPEED_OF_FLOW" in (s.defines or "") else 0
-        c.licvol_fp16 = s.licvol_fp16; c.weight_bits = weight_bits; c.fbo_fp16 = fbo_fp16
+        c.licvol_fp16 = s.licvol_fp16; c.weight_bits = weight_bits; c.fbo_fp16 = fbo_fp16; c.fbo_pingpong = fbo_pingpong
         if getattr(s, "mc_offsets", None) is not None:
             assert "USE_MC_OFFSET" in (s.defines or ""), "mc_offsets need #define USE_MC_OFFSET"
             self.mc = half_round(np.ascontiguousarray(s.mc_offsets, dtype=np.float32).reshape(s.height, s.width))

@@ -16,6 +16,7 @@ for name, mk in (("cfg1 ray-cast", lambda: configs.cfg1(n=n, size=size)),
         s.clip_planes = ((0.0, 0.0, -1.0, 0.1),)
     if "slicing" in name:
         s.technique, s.tf_mode, s.gate_mode = vv.VOLIC_SLICING, vv.TF_A, vv.GATE_TF_ALPHA
+        s.fbo = 1
     r = vv.Renderer(0)
     configs.apply_scene(r, s)
     r.render(True)

@@ -72,6 +72,7 @@ def golden_extra_scenes():
 
     def slicing(s):
         s.technique = vv.VOLIC_SLICING
+        s.fbo = 1
         s.tf_mode, s.gate_mode = vv.TF_A, vv.GATE_TF_ALPHA          # what lic3d_slicing_fragment.glsl hard-codes
         s.tf = F.default_tf()
         s.params.update(gradientScale=4.0)
@@ -156,6 +157,7 @@ def golden_chain_scenes():
         s = configs.cfg2(n=20, size=36, camera=F.CAMERA_CLOSE)
         s.with_gradients = True
         s.technique = vv.VOLIC_SLICING
+        s.fbo = 1
         s.tf_mode, s.gate_mode = vv.TF_A, vv.GATE_TF_ALPHA
         s.tf = F.default_tf()
         s.params.update(gradientScale=4.0, stepSizeVol=1 / 64)

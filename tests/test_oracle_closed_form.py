@@ -295,23 +295,54 @@ def test_eight_bit_filter_weights_stay_inside_the_tolerance(oracle):
 
 
 def test_fp16_ping_pong_of_the_slicing_fbo_is_bounded(oracle):
-    """The FBO slicing path accumulates in GL_RGBA16F_ARB targets (VV/renderer.cpp:566-606): every slice reads back the previous
-    slices' result rounded to fp16.  Oracle, shim and CUDA path keep the accumulator in fp32; this bounds what
-    that leaves out: PSNR > 60 dB, the few pixels that differ by more than 2/255 are those where the rounding flips the
-    dest.a < 0.95 skip of lic3d_slicing_fragment.glsl:14 for one slice."""
+    """The FBO slicing path accumulates in two GL_RGBA16F_ARB targets that are swapped before every slice (VV/renderer.cpp:566-606,
+    1201-1225).  The oracle (and the CUDA path) model both: fbo_fp16 rounds what every slice writes, fbo_pingpong keeps the two
+    targets per pixel.  This bounds each effect against the idealised model (one fp32 accumulator carried from fragment to
+    fragment): fp16 rounding -- PSNR > 60 dB, the few pixels that differ by more than 2/255 are those where the rounding flips the
+    dest.a < 0.95 skip of lic3d_slicing_fragment.glsl:14 for one slice; ping-pong -- a pixel whose last fragment belongs to a slice
+    of the same parity as the last slice N - 1 shows exactly the carried result, any other pixel shows the result WITHOUT its last
+    fragment (that fragment went into the texture that is not displayed)."""
+    import ctypes
     import vectorvisualization_b200 as vv
     from util import psnr8
     from vectorvisualization_b200 import configs, fields as F
+    missing = 0
     for mk in (lambda: configs.cfg3(n=32, size=64, camera=F.CAMERA_CLOSE), lambda: configs.cfg2(n=32, size=64)):
         s = mk()
         s.with_gradients = True
         s.technique, s.tf_mode, s.gate_mode = vv.VOLIC_SLICING, vv.TF_A, vv.GATE_TF_ALPHA
         s.tf = F.default_tf()
         s.params.update(gradientScale=4.0)
-        a, ca, ta = oracle.OracleScene(s).slicing()
-        b, cb, tb = oracle.OracleScene(s, fbo_fp16=1).slicing()
+        a, ca, ta = oracle.OracleScene(s, fbo_fp16=0, fbo_pingpong=0).slicing()
+        b, cb, tb = oracle.OracleScene(s, fbo_fp16=1, fbo_pingpong=0).slicing()
         qa, qb = oracle.quantize_rgba8(a), oracle.quantize_rgba8(b)
         d = np.abs(qa.astype(np.int32) - qb.astype(np.int32)).max(axis=-1)
         assert psnr8(qa, qb) > 60.0 and ta > 1000
         assert (d > 2).mean() < 0.01 and not np.array_equal(a, b)
         assert ((d > 2) & (ca == cb)).sum() <= (d > 2).sum() // 2 + 1          # large differences come with a flipped skip
+        # the two targets
+        o = oracle.OracleScene(s)                                               # the defaults: fp16 targets, ping-pong
+        c, cc, tc = o.slicing()
+        _, _, nslices = o.slicing_setup()
+        buf = np.zeros((nslices, 4), np.float32)
+        same = np.zeros((s.height, s.width), bool)
+        covered = np.zeros((s.height, s.width), bool)
+        single = np.zeros((s.height, s.width), bool)
+        for y in range(s.height):
+            for x in range(s.width):
+                n = oracle.lib().vvo_slice_fragments(ctypes.byref(o.c), x, y, oracle._p(buf), nslices)
+                if n:
+                    covered[y, x] = True
+                    idx = buf[:n, 3].astype(np.int64)
+                    assert np.array_equal(idx, np.arange(idx[0], idx[0] + n))   # a pixel's fragments are consecutive slices
+                    same[y, x] = (idx[-1] & 1) == ((nslices - 1) & 1)
+                    single[y, x] = n == 1
+        assert tc == tb and np.array_equal(cc, cb)                               # the same fragments did the same work
+        assert np.array_equal(c[same], b[same])                                  # last fragment in the displayed target: the carried result
+        other = covered & ~same
+        assert other.sum() > 100
+        missing += int((c[other] != b[other]).any(axis=-1).sum())                # ... else it is missing from the frame (which shows
+                                                                                 # unless the pixel was already opaque: dest.a >= 0.95)
+        assert (c[other & single] == 0).all()                                    # a pixel with one fragment comes out empty there
+        assert psnr8(oracle.quantize_rgba8(c), qb) > 35.0
+    assert missing > 100

@@ -286,7 +286,7 @@ def test_slicing_without_fbo_fragments_bit_exact(oracle, define):
     got, cnt, tot = o.slicing_blend8()
     assert np.array_equal(got, frame) and tot == shaded and tot > 200
     assert (got[..., 3] == 255).all()                                    # the white plane completes the alpha
-    # against the FBO variant composited over white: same picture up to the 8-bit accumulation and the 0.95 skip
-    fbo, _, _ = o.slicing()
+    # against the FBO variant (one fp32 accumulator) composited over white: same picture up to the 8-bit accumulation and the 0.95 skip
+    fbo, _, _ = oracle.OracleScene(s, illum_tables=tables if need else None, fbo_fp16=0, fbo_pingpong=0).slicing()
     disp = oracle.quantize_rgba8(oracle.background(fbo))
     assert np.abs(disp[..., :3].astype(np.int32) - got[..., :3].astype(np.int32)).max() <= 24

@@ -6,7 +6,7 @@ ray-sample counts exactly equal, LIC volume <= 1e-4 relative, pre-processing bit
 import numpy as np
 import pytest
 
-from util import MAX_DIFF_8BIT, assert_image_parity, render_cuda, LICVOL_REL
+from util import MAX_DIFF_8BIT, MIN_PSNR_DB, assert_image_parity, render_cuda, LICVOL_REL
 
 pytestmark = pytest.mark.gpu
 
@@ -186,6 +186,7 @@ def test_slicing_parity(vv, oracle, define):
         s.defines = ("#define " + define) if define else ""
         s.with_gradients = True
         s.technique = vv.VOLIC_SLICING
+        s.fbo = 1
         s.tf_mode, s.gate_mode = vv.TF_A, vv.GATE_TF_ALPHA
         s.tf = F.default_tf()
         s.params.update(gradientScale=4.0)
@@ -194,6 +195,36 @@ def test_slicing_parity(vv, oracle, define):
         assert ref_tot > 0
         assert int((cnt != ref_cnt).sum()) <= max(1, cnt.size // 20000), "%d pixels differ in fragment count" % int((cnt != ref_cnt).sum())
         assert_image_parity(oracle, img, ref, "slicing " + define)
+
+
+@pytest.mark.parametrize("define", ["", "ILLUM_GRADIENT"])
+def test_slicing_without_fbo_parity(vv, oracle, define):
+    """VOLIC_SLICING as the reference starts up (no FBO until key 'F'): lic3d_slicingblend_fragment.glsl, every fragment blended with
+    (ONE_MINUS_DST_ALPHA, ONE) into the RGBA8 back buffer -- rounded to 8 bits per slice, no dest.a skip -- and the white plane
+    at the end (VV/renderer.cpp:1151-1160, 1236-1262).  The oracle's fragment colours are bit-identical to that shader."""
+    from util import psnr8
+    from vectorvisualization_b200 import configs, fields as F
+    for mk in (lambda: configs.cfg3(n=48, size=112, camera=F.CAMERA_CLOSE), lambda: configs.cfg2(n=40, size=96),
+               lambda: configs.cfg1(n=32, size=75, camera=dict(quat=F.quat_from_axis_angle((0.3, -1.0, 0.2), 110.0), pos=(0.1, 0, 0.2), dist=3.0, fovy=35.0))):
+        s = mk()
+        s.defines = ("#define " + define) if define else ""
+        s.with_gradients = True
+        s.technique = vv.VOLIC_SLICING
+        s.fbo = 0
+        s.tf_mode, s.gate_mode = vv.TF_A, vv.GATE_TF_ALPHA
+        s.tf = F.default_tf()
+        s.params.update(gradientScale=4.0)
+        ref8, ref_cnt, ref_tot = oracle.OracleScene(s).slicing_blend8()
+        r, img, img8, cnt, tot = render_cuda(vv, s)
+        assert ref_tot > 0 and (img8[..., 3] == 255).all()                      # the white plane completes the alpha
+        assert np.array_equal(img8, oracle.quantize_rgba8(img))                  # the float read-back is the byte frame / 255
+        d = np.abs(img8.astype(np.int32) - ref8.astype(np.int32))
+        print("slicing without FBO %s %s: %d fragments (oracle %d), max 8-bit diff %d, %d bytes differ, PSNR %.1f"
+              % (s.name, define or "plain", tot, ref_tot, d.max(), int((d > 0).sum()), psnr8(img8, ref8)))
+        assert d.max() <= MAX_DIFF_8BIT and psnr8(img8, ref8) >= MIN_PSNR_DB
+        assert int((cnt != ref_cnt).sum()) <= max(1, cnt.size // 20000) and abs(tot - ref_tot) <= max(1, ref_tot // 20000)
+        # the displayed frame: background_fragment.glsl over a frame whose alpha is 1 changes nothing
+        assert np.array_equal(r.readDisplayRGBA8(), img8)
 
 
 def test_mc_offset_parity(vv, oracle):
@@ -206,6 +237,7 @@ def test_mc_offset_parity(vv, oracle):
     def slicing():
         s = configs.cfg2(n=40, size=75)
         s.technique = vv.VOLIC_SLICING
+        s.fbo = 1
         s.tf_mode, s.gate_mode = vv.TF_A, vv.GATE_TF_ALPHA
         s.tf = F.default_tf()
         return s
@@ -274,6 +306,7 @@ def test_clip_planes_parity(vv, oracle, planes):
     # slicing: the slice polygons are clipped
     s = configs.cfg2(n=40, size=75)
     s.technique = vv.VOLIC_SLICING
+    s.fbo = 1
     s.tf_mode, s.gate_mode = vv.TF_A, vv.GATE_TF_ALPHA
     s.tf = F.default_tf()
     s.clip_planes = planes
@@ -861,6 +894,7 @@ def test_near_plane_clips_the_proxy_geometry(vv, oracle, technique):
         s = configs.cfg1(n=32, size=96, camera=cam)
         if technique == "slicing":
             s.technique = vv.VOLIC_SLICING
+            s.fbo = 1
             s.tf_mode, s.gate_mode = vv.TF_A, vv.GATE_TF_ALPHA
             ref, ref_cnt, ref_tot = oracle.OracleScene(s).slicing()
         else:

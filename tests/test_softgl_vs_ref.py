@@ -156,7 +156,8 @@ def test_slicing_fragments_are_the_oracle_slice_fragments(oracle, tmp_path, cam,
                 differ += 1
                 assert edge[y, x] < EDGE_EPS, (x, y, len(g), n)
             elif n:
-                worst = max(worst, float(np.abs(g - buf[:n, :3]).max()))       # same fragments in the same (front-to-back) order
+                worst = max(worst, float(np.abs(g[:, :3] - buf[:n, :3]).max()))       # same fragments in the same (front-to-back) order
+                assert np.array_equal(g[:, 3], buf[:n, 3])                            # ... of the same slices (-> the same ping-pong target)
     assert total > 2000 and differ <= 4 and worst < TC_EPS
 
 
@@ -260,3 +261,43 @@ def test_draw_state_of_the_three_techniques(tmp_path):
     a, _, _, _ = softgl.rasterize(ray, s.width, s.height)
     b, _, _, _ = softgl.rasterize(vol, s.width, s.height)
     assert np.array_equal(a, b) and a[..., 3].sum() > 50
+
+
+def test_fbo_slicing_ping_pong_targets(tmp_path):
+    """Renderer::sliceVolume with the FBO (VV/renderer.cpp:1201-1225), read from the reference's own GL calls: the two image textures
+    are swapped before EVERY slice -- slice i is drawn into one of them with the other (the target of slice i - 1) bound as
+    imageFBOSampler -- so a pixel that slice i does not cover keeps, in slice i's target, what slice i - 2 left there; the frame that
+    is displayed / stored is the target of the last slice.  (What the oracle's fbo_pingpong switch and the CUDA path implement.)"""
+    s = _scene("default", size=24)
+    dat = _dat(tmp_path, s)
+    draws = refhost.raycast_draws(dat, s.camera, s.width, s.height, slicing=1)
+    sli = [d for d in draws if d["program"] == 79]
+    assert len(sli) > 8
+    tex = sorted(set(d["fbo_tex"] for d in sli))
+    assert len(tex) == 2 and 0 not in tex                               # exactly two colour targets
+    for i, d in enumerate(sli):
+        assert d["fbo_tex"] == (sli[0]["fbo_tex"] if i % 2 == 0 else sli[1]["fbo_tex"])    # alternate, starting at slice 0
+        assert d["bound_tex"] == (set(tex) - {d["fbo_tex"]}).pop()       # the source is the OTHER texture = the previous slice's target
+        assert d["blend"] == 0
+    # the display pass (background program) samples the target of the last slice
+    bg = [d for d in draws if d["program"] == 78]
+    assert bg and bg[-1]["bound_tex"] == sli[-1]["fbo_tex"]
+
+
+def test_slicing_without_fbo_draw_state(tmp_path):
+    """Renderer::sliceVolume without the FBO (the reference's start-up state for F3, VV/renderer.cpp:1151-1160, 1236-1262): every slice
+    is drawn with lic3d_slicingblend and fixed-function blending (ONE_MINUS_DST_ALPHA, ONE) into the back buffer, then a
+    screen-filling white quad is blended in with the same function and no program."""
+    s = _scene("default", size=24)
+    dat = _dat(tmp_path, s)
+    draws = refhost.raycast_draws(dat, s.camera, s.width, s.height, slicing=3)
+    sli = [d for d in draws if d["program"] == 82]
+    fbo = [d for d in refhost.raycast_draws(dat, s.camera, s.width, s.height, slicing=1) if d["program"] == 79]
+    assert len(sli) == len(fbo) > 8
+    GL_ONE_MINUS_DST_ALPHA, GL_ONE = 0x0305, 1
+    assert all(d["blend"] == 1 and d["blend_func"] == (GL_ONE_MINUS_DST_ALPHA, GL_ONE) and d["fbo_tex"] == 0 for d in sli)
+    assert all(np.array_equal(a["verts"], b["verts"]) and np.array_equal(a["tex"], b["tex"]) for a, b in zip(sli, fbo))   # same polygons
+    k = next(i for i, d in enumerate(draws) if d is sli[-1])
+    white = draws[k + 1]
+    assert white["program"] == 0 and white["mode"] == softgl.GL_QUADS and white["blend"] == 1
+    assert white["blend_func"] == (GL_ONE_MINUS_DST_ALPHA, GL_ONE) and len(white["verts"]) == 4

@@ -41,6 +41,8 @@ class Scene:
     mc_offsets: Optional[np.ndarray] = None   # [height][width] float32 in [0,1]; needs "#define USE_MC_OFFSET" in defines
     clip_planes: tuple = ()                # up to 3 active planes (nx, ny, nz, d): n.q + d >= 0 kept, q relative to the centre
     window: Optional[tuple] = None         # (w, h) of the window when the frame is not the window (low-res preset: frame = half the window)
+    fbo: int = 0                           # Renderer::enableFBO (key 'F'; off at start-up, VV/renderer.cpp:33): float RGBA16F targets;
+                                           # for VOLIC_SLICING it selects the FBO ping-pong program over the blending one
 
     def lic_params(self):
         return LICParams(**self.params)
@@ -107,6 +109,7 @@ def apply_scene(r: Renderer, s: Scene):
     r.setLight(**s.light)
     r.updateLightPos()
     r.setTechnique(s.technique)
+    r.enableFBO(s.fbo)
     r.resize(s.width, s.height)
     r.setWindow(*(s.window or (0, 0)))
     if s.mc_offsets is not None:

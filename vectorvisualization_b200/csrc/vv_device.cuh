@@ -102,7 +102,8 @@ struct DevParams {
     unsigned int *bucketCount, *bucketBase, *bucketFill;
     int bandRows, nDepthChunks;
     // ---- view-aligned slicing (VV/slicing.cpp:42-114): unit view vector, covered depth, slice count ----
-    int slicing;
+    int slicing;                     // 0 off; 1 FBO path (lic3d_slicing_fragment.glsl, two RGBA16F ping-pong targets); 2 without the FBO
+                                     // (lic3d_slicingblend_fragment.glsl + (ONE_MINUS_DST_ALPHA, ONE) blending in the RGBA8 back buffer)
     float slV[3], slD;
     int slNum;
     double slCenter[3];

@@ -501,6 +501,19 @@ __device__ __forceinline__ bool shade_sample(const DevParams &P, const SharedTab
     return true;
 }
 
+// GL float -> UNORM8 -> float of the RGBA8 back buffer (GL 2.1 spec 2.14.9), uncontracted like the oracle's
+__device__ __forceinline__ float unorm8_rn(float v) { return floorf(__fadd_rn(__fmul_rn(clamp01(v), 255.0f), 0.5f)); }
+// glBlendFunc(GL_ONE_MINUS_DST_ALPHA, GL_ONE) in an RGBA8 frame buffer: dst holds the byte values 0..255 as floats
+__device__ __forceinline__ void blend8(float4 &dst, float4 src)
+{
+    const float k = __fsub_rn(1.0f, __fdiv_rn(dst.w, 255.0f));
+    dst.x = unorm8_rn(__fadd_rn(__fmul_rn(src.x, k), __fdiv_rn(dst.x, 255.0f)));
+    dst.y = unorm8_rn(__fadd_rn(__fmul_rn(src.y, k), __fdiv_rn(dst.y, 255.0f)));
+    dst.z = unorm8_rn(__fadd_rn(__fmul_rn(src.z, k), __fdiv_rn(dst.z, 255.0f)));
+    dst.w = unorm8_rn(__fadd_rn(__fmul_rn(src.w, k), __fdiv_rn(dst.w, 255.0f)));
+}
+__device__ __forceinline__ float half_round(float v) { return __half2float(__float2half_rn(v)); }
+
 // lic3d_fragment.glsl:83-84: src.rgb *= src.a; dest = clamp((1 - dest.a) src + dest, 0, 1)
 __device__ __forceinline__ void composite(float4 &dest, float4 src)
 {
@@ -714,23 +727,39 @@ __global__ void __launch_bounds__(256) slice_setup_kernel(const __grid_constant_
             for (int i = 0; i < P.slNum; ++i)
                 if (slice_fragment(P, r, i, g)) { if (first < 0) first = i; last = i; }
         }
+        // FBO path: Renderer::sliceVolume swaps its two image textures before EVERY slice and a slice writes only the pixels its polygon
+        // covers (VV/renderer.cpp:1201-1225); the frame is the target of the last slice N - 1.  A pixel's fragments are consecutive
+        // slices (ray / convex region), so along them the value read back is the value just written -- except that the LAST fragment
+        // lands in the texture that is not displayed when its slice has the other parity than N - 1: it is dropped from the frame
+        // (and still counted as a ray sample if the frame buffer it read was not opaque, like every fragment that did work).
+        int dropped = 0;
+        if (P.slicing == 1 && last >= 0 && ((last ^ (P.slNum - 1)) & 1)) { dropped = 1; --last; }
         // a tile's items address slices first_tile + k, so that the 32 lanes of an item shade the same slice
         const int tfirst = __reduce_min_sync(0xffffffffu, first < 0 ? 0x7fffffff : first);
-        const int tlast = __reduce_max_sync(0xffffffffu, last);
-        const int nmax = (tlast >= 0) ? tlast - tfirst + 1 : 0;
-        const int n = (last >= 0) ? last - tfirst + 1 : 0;       // per ray: samples up to its last fragment
+        const int tlast = __reduce_max_sync(0xffffffffu, (last >= first) ? last : -1);
+        const int nmax = (tlast >= 0 && tfirst != 0x7fffffff) ? tlast - tfirst + 1 : 0;
+        const int n = (first >= 0 && last >= first) ? last - tfirst + 1 : 0;       // per ray: samples up to its last displayed fragment
         unsigned int base = 0;
         if (lane == 0 && nmax > 0) base = atomicAdd(P.slotAlloc, (unsigned int)nmax);
         base = __shfl_sync(0xffffffffu, base, 0);
         const int ray = lt * 32 + lane;
-        P.rayA[ray] = make_float4(__int_as_float(tfirst), 0.f, 0.f, __int_as_float(n));
+        P.rayA[ray] = make_float4(__int_as_float(tfirst), __int_as_float(dropped), 0.f, __int_as_float(n));
         P.rayB[ray] = make_float4(0.f, 0.f, 0.f, __int_as_float(n > 0 ? 0 : -1));
         if (lane == 0) {
             P.tileRec[lt] = make_uint2(base, (unsigned int)nmax);
             if (nmax > 0) atomicMax(P.nMaxGlobal, (unsigned int)nmax);
         }
-        P.tiles[o] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (P.samplesPerPixel) P.samplesPerPixel[o] = 0;
+        // a pixel without (displayed) fragments: the cleared target; without the FBO the white plane that is blended over everything
+        // at the end (VV/renderer.cpp:1236-1255) gives (1,1,1,1).  A dropped single fragment still counts as a ray sample: it read
+        // the cleared (transparent) target and did its work.
+        const float bg = (P.slicing == 2 && n == 0) ? 1.0f : 0.0f;
+        P.tiles[o] = make_float4(bg, bg, bg, bg);
+        const unsigned int lone = (n == 0 && dropped) ? 1u : 0u;
+        if (P.samplesPerPixel) P.samplesPerPixel[o] = lone;
+        if (P.sampleCounter) {
+            const unsigned int tot = __reduce_add_sync(0xffffffffu, lone);
+            if (lane == 0 && tot) atomicAdd(P.sampleCounter, (unsigned long long)tot);
+        }
     }
 }
 
@@ -811,6 +840,7 @@ __global__ void __launch_bounds__(256) composite_kernel(const __grid_constant__ 
         unsigned int consumed = 0;
         if (state >= 0) {
             float4 dest = P.tiles[o];
+            if (P.slicing == 2) { dest.x = unorm8_rn(dest.x); dest.y = unorm8_rn(dest.y); dest.z = unorm8_rn(dest.z); dest.w = unorm8_rn(dest.w); }   // bytes
             const int kend = min(n, P.win1);
             bool done = false;
             // The blend is a serial chain but the loads are not: fetch 8 samples ahead so that one ray keeps 8 requests in
@@ -824,12 +854,26 @@ __global__ void __launch_bounds__(256) composite_kernel(const __grid_constant__ 
                 for (int j = 0; j < kAhead; ++j) {
                     if (done || k0 + j >= kend) continue;
                     const float4 s = buf[j];
+                    if (P.slicing == 2) {
+                        // without the FBO (lic3d_slicingblend_fragment.glsl:5-67): every fragment's colour -- src.rgb * src.a, src.a,
+                        // clamped by the GL -- is blended into the RGBA8 back buffer, no skip
+                        if (s.w < 0.0f) continue;                         // no fragment, or gated off: colour 0 leaves the buffer as it is
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        composite(v, s);                                  // clamp((1 - 0) (src.rgb * src.a, src.a) + 0)
+                        if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f) ++consumed;
+                        blend8(dest, v);
+                        continue;
+                    }
                     if (P.slicing) {
                         // lic3d_slicing_fragment.glsl:14: a fragment only works while the frame buffer has dest.a < 0.95
                         if (s.w == -2.0f) continue;                       // no fragment of this slice under the pixel
                         if (!(dest.w < 0.95f)) { done = true; continue; }
                         ++consumed;
-                        if (s.w >= 0.0f) composite(dest, s);
+                        if (s.w >= 0.0f) {
+                            composite(dest, s);
+                            // the target is GL_RGBA16F_ARB (VV/renderer.cpp:566-606): the next slice reads this rounded to fp16
+                            dest.x = half_round(dest.x); dest.y = half_round(dest.y); dest.z = half_round(dest.z); dest.w = half_round(dest.w);
+                        }
                         continue;
                     }
                     ++consumed;
@@ -839,7 +883,15 @@ __global__ void __launch_bounds__(256) composite_kernel(const __grid_constant__ 
                     }
                 }
             }
-            if (kend >= n) done = true;
+            if (kend >= n) {
+                // the fragment that went into the other ping-pong target (slice_setup_kernel): it did its work if what it read was not opaque
+                if (P.slicing == 1 && !done && __float_as_int(A.y) && dest.w < 0.95f) ++consumed;
+                done = true;
+            }
+            if (P.slicing == 2) {
+                if (done) blend8(dest, make_float4(1.f, 1.f, 1.f, 1.f));       // the screen-filling white plane, VV/renderer.cpp:1236-1255
+                dest.x = __fdiv_rn(dest.x, 255.0f); dest.y = __fdiv_rn(dest.y, 255.0f); dest.z = __fdiv_rn(dest.z, 255.0f); dest.w = __fdiv_rn(dest.w, 255.0f);
+            }
             state += (int)consumed;
             P.tiles[o] = dest;
             if (P.samplesPerPixel) P.samplesPerPixel[o] = (unsigned int)state;

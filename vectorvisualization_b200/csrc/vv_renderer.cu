@@ -489,7 +489,9 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycas
         float d = dv[6];
         for (int i = 0; i < 6; ++i) if (d < dv[i]) d = dv[i];
         d *= 2.0;
-        P.slicing = 1;
+        // key 'F' (enableFBO): with the FBO the two RGBA16F ping-pong targets and lic3d_slicing_fragment.glsl; without it -- the
+        // reference's start-up state -- lic3d_slicingblend_fragment.glsl blended into the RGBA8 back buffer (VV/renderer.cpp:1138-1160)
+        P.slicing = r->float_target ? 1 : 2;
         P.slV[0] = v[0]; P.slV[1] = v[1]; P.slV[2] = v[2];
         P.slD = d;
         P.slNum = (int)(d / u.stepSize) + 1;
@@ -705,7 +707,8 @@ static int render_sample_parallel(VVRenderer *r, DevParams &P)
     std::vector<int> w;
     w.push_back(0);
     // (slicing stops on the accumulated dest.a, which any TF can drive past 0.95: always windowed)
-    if (!P.slicing && !termination_possible(r, derive_uniforms(r))) w.push_back(nmax);
+    // (without the FBO nothing stops a slice from being blended: one window)
+    if (P.slicing == 2 || (!P.slicing && !termination_possible(r, derive_uniforms(r)))) w.push_back(nmax);
     else for (int len = 4; w.back() < nmax; len *= 2) w.push_back(std::min(nmax, w.back() + len));
     w.push_back(w.back());   // sentinel: nothing after the last window
     const int comp_grid = setup_grid;
@@ -1163,6 +1166,7 @@ int vv_enable_lowres(VVRenderer *r, int enable)
 int vv_enable_float_target(VVRenderer *r, int enable)
 {
     if (!r) return fail(VV_ERR_INVALID, "null renderer");
+    if (r->technique == VV_VOLIC_SLICING && r->float_target != (enable != 0)) r->frame_valid = false;   // another slicing program runs
     r->float_target = enable != 0;
     return VV_OK;
 }
