@@ -44,13 +44,7 @@ B_VOLRAY = 8 * 8 + 8 * 4 + 12                                   # volume ray-cas
 def make_scene(name, args=None):
     from vectorvisualization_b200 import configs
     if name == "cfg3o":
-        # cfg3 with the reference's default transfer function (alpha = opacity = max(0, i - 20), VV/transferEdit.cpp:76-82):
-        # samples reach src.a > 0.95, rays terminate early (lic3d_fragment.glsl:91) and the frame is computed in depth windows
-        from vectorvisualization_b200 import fields as F
-        s = configs.cfg3()
-        s.tf = F.default_tf()
-        s.name = "cfg3o"
-        return s
+        return configs.cfg3o()
     if name == "cfg5":
         return configs.cfg5(n=args.cfg5_n, size=args.cfg5_size)
     mk = {"cfg1": configs.cfg1, "cfg2": configs.cfg2, "cfg3": configs.cfg3, "cfg4": configs.cfg4}[name]

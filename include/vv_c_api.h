@@ -89,6 +89,8 @@ typedef enum VVOption {
     VV_OPT_WALK_FAST_PATHS = 14,   /* 1 (default): unclamped walk inside the field's guard band + shared field / noise cell coordinates where they apply; 0: the clamping samplers (check; same frames) */
     VV_OPT_DEPTH_MAJOR = 15,       /* 1 (default): work items ordered band-major / depth-major for L2 locality; 0: tile-major */
     VV_OPT_BAND_ROWS = 16,         /* 16-pixel block rows per band of the depth-major order (default 4) */
+    VV_OPT_FIRST_WINDOW = 18,      /* early-termination frames: ray samples in the first depth window (multiple of 8, default 8) */
+    VV_OPT_WINDOW_GROWTH = 19,     /* ... and the length of every further window in percent of the previous one (100..400, default 200) */
     VV_OPT_NOISE_LAYOUT = 17       /* RGBA (-g) noise: 2 (default) bf16 {t0, t1 - t0}, 1 fp16 x-pair, 0 u8 xy-quad; same values, same frames */
 } VVOption;
 

@@ -195,7 +195,7 @@ inline float texLicVol(const Ctx &c, V3 p)
     const float *T = s->licvol;
     const int *d = s->ldim;
     float o[1];
-    trilinear<1>(d, p.x, p.y, p.z, REPEAT, 0,
+    trilinear<1>(d, p.x, p.y, p.z, REPEAT, s->weight_bits < 0 ? -1 : 0,
                  [&](int x, int y, int z, float *t) { t[0] = T[((size_t)z * d[1] + y) * d[0] + x]; }, o);
     return o[0];
 }

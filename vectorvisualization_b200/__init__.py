@@ -24,7 +24,7 @@ TF_B, TF_A, TF_R, TF_LENGTH, TF_SCALAR = range(5)
 GATE_ALWAYS, GATE_TF_ALPHA = 0, 1
 (OPT_TF_MODE, OPT_GATE_MODE, OPT_NOISE_GATE, OPT_QUIRK_SCALEVOLINV, OPT_QUIRK_LUMINANCE_ALPHA, OPT_LICVOL_FP16,
  OPT_FIELD_LAYOUT, OPT_COUNT_SAMPLES, OPT_LICVOL_SIZE, OPT_SPEC_EXP, OPT_SAMPLE_MAP, OPT_RAYCAST_MODE,
- OPT_LIC_CTAS_PER_SM, OPT_WALK_FAST_PATHS, OPT_DEPTH_MAJOR, OPT_BAND_ROWS, OPT_NOISE_LAYOUT) = range(1, 18)
+ OPT_LIC_CTAS_PER_SM, OPT_WALK_FAST_PATHS, OPT_DEPTH_MAJOR, OPT_BAND_ROWS, OPT_NOISE_LAYOUT, OPT_FIRST_WINDOW, OPT_WINDOW_GROWTH) = range(1, 20)
 LAYOUT_F4, LAYOUT_PAIR = 0, 1
 BLOCK = 16  # pixels per image-block edge (sort-first partition unit)
 
@@ -159,6 +159,8 @@ def load_library():
         "vv_free": ([P], None), "vv_png_write": ([CP, P, I, I, I], I),
     }
     for name, (args, res) in sig.items():
+        if name == "vv_debug_walk" and os.environ.get("VV_B200_LIB") and not hasattr(lib, name):
+            continue              # an older A/B build selected with VV_B200_LIB (scripts/ab.py): the diagnostic entry point may be missing
         fn = getattr(lib, name)   # AttributeError here == header/library mismatch
         fn.argtypes = args
         fn.restype = res

@@ -70,6 +70,28 @@ def cfg3(n=256, size=1024, camera=None, noise_n=None):
                  camera=dict(camera or F.CAMERA_DEFAULT))
 
 
+def cfg3o(n=256, size=1024, camera=None, noise_n=None):
+    """cfg3 with an opaque transfer function -- the reference's default ramp (alpha = opacity = max(0, i - 20), VV/transferEdit.cpp:76-82)
+    twice as steep, saturating at 255: samples reach src.a > 0.95, rays terminate early (lic3d_fragment.glsl:91) and the frame is
+    computed in depth windows.  (With the default ramp itself and alphaCorrection = 1 no sample of this scene can exceed 0.85.)"""
+    s = cfg3(n, size, camera, noise_n)
+    s.tf = F.default_tf().copy()
+    ramp = np.clip(2 * (np.arange(256) - 20), 0, 255).astype(np.uint8)
+    s.tf[:, 3] = ramp
+    s.tf[:, 4] = ramp
+    s.name = "cfg3o"
+    return s
+
+
+def cfg1t(n=64, size=512, camera=None):
+    """cfg1 with a semi-transparent transfer function (no early ray termination): the single-window reference point of cfg1"""
+    s = cfg1(n, size, camera)
+    s.tf = s.tf.copy()
+    s.tf[:, 3] = (s.tf[:, 3].astype(np.int32) * 3 // 10).astype(np.uint8)
+    s.name = "cfg1t"
+    return s
+
+
 def cfg4(n=512, size=2048, camera=None, noise_n=256):
     """512^3 curl-noise turbulence, 256^3 sparse noise (REPEAT-tiled), triangle filter, step 1/256, 2048^2"""
     return Scene("cfg4", F.curl_noise(n, 4), F.white_noise(noise_n, 4, F.SPARSE_P), F.constant_scalar(), F.filter_kernel("triangle"),

@@ -97,7 +97,9 @@ struct DevParams {
     float4 *src;                     // [(row + k) * 32 + lane]: shaded ray samples, w < 0 = gated off
     uint2  *items, *itemsNext;       // work items (tile, k) of the current / next depth window
     unsigned int *itemCount, *itemCountNext, *itemHead, *slotAlloc, *nMaxGlobal;
-    int win0, win1, win2;            // current window [win0, win1), next window ends at win2
+    unsigned int *tileLive;          // [tile]: longest ray of the tile that is still alive (0: every ray of the tile has finished)
+    int win0, win1, win2;            // current window [win0, win1), next window [win1, win2) (the one whose items are being built)
+    int emitItems;                   // composite_kernel emits the next window's items itself, tile-major (VV_OPT_DEPTH_MAJOR = 0)
     // depth-major item order: buckets = (band of block rows) x (chunk of 8 depths)
     unsigned int *bucketCount, *bucketBase, *bucketFill;
     int bandRows, nDepthChunks;

@@ -652,12 +652,38 @@ __global__ void __launch_bounds__(256) ray_setup_kernel(const __grid_constant__ 
         P.rayB[ray] = make_float4(dir.x, dir.y, dir.z, __int_as_float(n > 0 ? 0 : -1));   // state: consumed samples, < 0 = finished
         if (lane == 0) {
             P.tileRec[lt] = make_uint2(base, (unsigned int)nmax);
+            P.tileLive[lt] = (unsigned int)nmax;
             if (nmax > 0) atomicMax(P.nMaxGlobal, (unsigned int)nmax);
         }
         P.tiles[o] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (P.samplesPerPixel) P.samplesPerPixel[o] = 0;
-        // the first window's work items are emitted by composite_kernel run on the empty window [0,0), after the
-        // host has sized the src / item buffers from slotAlloc
+        // the work items of the first window are built afterwards (item_bucket_kernel, or composite_kernel run on the empty
+        // window [0,0)), once the host has sized the src / item buffers from slotAlloc
+    }
+}
+
+// The same view as the previous frame (camera, frame size, sample spacing, partition ... unchanged): the ray records, the src
+// rows and the first window's item list of that frame are still valid -- only what a frame consumes is put back: ray state,
+// tile accumulators, per-frame counters.  (ray_setup_kernel would recompute exactly the same records.)
+__global__ void __launch_bounds__(256) ray_reset_kernel(const __grid_constant__ DevParams P, unsigned int *counters)
+{
+    if (blockIdx.x == 0 && threadIdx.x < 8) {
+        // [0,1] ray samples, [2] block queue, [4],[5] item counts of the later windows, [6] item queue head; [3] src rows,
+        // [7] longest ray and [8] the first window's item count are kept
+        const int t = threadIdx.x;
+        if (t != 3 && t != 7) counters[t] = 0u;
+    }
+    const int lane = threadIdx.x & 31;
+    const int nTiles = P.nLocalBlocks * 8;
+    for (int lt = blockIdx.x * 8 + (threadIdx.x >> 5); lt < nTiles; lt += gridDim.x * 8) {
+        int px, py;
+        const int o = tile_pixel(P, lt, lane, px, py);
+        const int ray = lt * 32 + lane;
+        const int n = __float_as_int(P.rayA[ray].w);
+        P.rayB[ray].w = __int_as_float(n > 0 ? 0 : -1);
+        if (lane == 0) P.tileLive[lt] = P.tileRec[lt].y;
+        P.tiles[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (P.samplesPerPixel) P.samplesPerPixel[o] = 0;
     }
 }
 
@@ -747,6 +773,7 @@ __global__ void __launch_bounds__(256) slice_setup_kernel(const __grid_constant_
         P.rayB[ray] = make_float4(0.f, 0.f, 0.f, __int_as_float(n > 0 ? 0 : -1));
         if (lane == 0) {
             P.tileRec[lt] = make_uint2(base, (unsigned int)nmax);
+            P.tileLive[lt] = (unsigned int)nmax;
             if (nmax > 0) atomicMax(P.nMaxGlobal, (unsigned int)nmax);
         }
         // a pixel without (displayed) fragments: the cleared target; without the FBO the white plane that is blended over everything
@@ -903,9 +930,10 @@ __global__ void __launch_bounds__(256) composite_kernel(const __grid_constant__ 
             unsigned int tot = __reduce_add_sync(0xffffffffu, consumed);
             if (lane == 0 && tot) atomicAdd(P.sampleCounter, (unsigned long long)tot);
         }
-        // items of the next window for rays still alive
+        // what is left of the tile for the next window: the longest ray still alive
         const int live = __reduce_max_sync(0xffffffffu, state >= 0 ? n : 0);
-        const int cnt = min(live, P.win2) - P.win1;
+        if (lane == 0) P.tileLive[lt] = (unsigned int)live;
+        const int cnt = P.emitItems ? min(live, P.win2) - P.win1 : 0;
         if (cnt > 0) {
             unsigned int ib = 0;
             if (lane == 0) ib = atomicAdd(P.itemCountNext, (unsigned int)cnt);
@@ -926,21 +954,23 @@ __global__ void __launch_bounds__(256) item_bucket_kernel(const __grid_constant_
 {
     const int lane = threadIdx.x & 31;
     const int nTiles = P.nLocalBlocks * 8;
+    // items of the window [win1, win2) (win1 a multiple of 8) for the tiles that still have live rays reaching into it
+    const int c0 = P.win1 >> 3;
     for (int lt = blockIdx.x * 8 + (threadIdx.x >> 5); lt < nTiles; lt += gridDim.x * 8) {
-        const uint2 tr = P.tileRec[lt];
-        const int nmax = min((int)tr.y, P.win2);
-        if (nmax <= 0) continue;
+        const int nmax = min((int)P.tileLive[lt], P.win2);
+        if (nmax <= P.win1) continue;
         const int b = P.rank + (lt >> 3) * P.world;
         const int band = (b / P.nBlocksX) / P.bandRows;
-        const int nchunks = (nmax + 7) >> 3;
+        const int nchunks = ((nmax + 7) >> 3) - c0;
         for (int c = lane; c < nchunks; c += 32) {
-            const int cnt = min(8, nmax - 8 * c);
+            const int k0 = 8 * (c0 + c);
+            const int cnt = min(8, nmax - k0);
             const int bucket = band * P.nDepthChunks + c;
             if (pass == 0) {
                 atomicAdd(P.bucketCount + bucket, (unsigned int)cnt);
             } else {
                 const unsigned int at = P.bucketBase[bucket] + atomicAdd(P.bucketFill + bucket, (unsigned int)cnt);
-                for (int j = 0; j < cnt; ++j) P.itemsNext[at + j] = make_uint2((unsigned int)lt, (unsigned int)(8 * c + j));
+                for (int j = 0; j < cnt; ++j) P.itemsNext[at + j] = make_uint2((unsigned int)lt, (unsigned int)(k0 + j));
             }
         }
     }
@@ -1164,6 +1194,12 @@ cudaError_t launch_ray_setup(const DevParams &P, int grid, cudaStream_t st)
 {
     if (P.slicing) slice_setup_kernel<<<grid, 256, 0, st>>>(P);
     else ray_setup_kernel<<<grid, 256, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ray_reset(const DevParams &P, unsigned int *counters, int grid, cudaStream_t st)
+{
+    ray_reset_kernel<<<grid, 256, 0, st>>>(P, counters);
     return cudaGetLastError();
 }
 

@@ -11,6 +11,8 @@ size_t shared_table_bytes();
 cudaError_t launch_lic_raycast(const DevParams &P, int layout, int illum, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st);
 // sample-parallel pipeline (ray_setup -> [lic_sample -> composite] per depth window)
 cudaError_t launch_ray_setup(const DevParams &P, int grid, cudaStream_t st);
+// same view as the previous frame: put back what a frame consumes (ray state, tile accumulators, per-frame counters)
+cudaError_t launch_ray_reset(const DevParams &P, unsigned int *counters, int grid, cudaStream_t st);
 cudaError_t launch_lic_sample(const DevParams &P, int layout, int illum, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st);
 cudaError_t launch_composite(const DevParams &P, int grid, cudaStream_t st);
 cudaError_t launch_item_buckets(const DevParams &P, int nBuckets, int grid, cudaStream_t st);

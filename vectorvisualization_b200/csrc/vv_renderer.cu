@@ -31,6 +31,16 @@ using namespace vvb200;
 
 static const int kNumCounters = 16;
 
+// What the ray records, the src rows and the first window's item list of a frame depend on: compared frame to frame (memcmp of
+// a zero-initialised struct) so that an unchanged view neither recomputes them nor reads their sizes back to the host.
+struct GeomKey {
+    double camD[3], rot[9], tanHalf, aspect, extent[3], nearD, farD, clipEq[3][4], clipN[3][3], clipDist[3], centerD[3], slCenter[3];
+    float stepSize, scaleVol[3], texMax[3], camera[3], slV[3], slD;
+    int width, height, numIter, nClip, rank, world, nLocalBlocks, blockSkew, slicing, slNum, depthMajor, bandRows, firstWindow, windowGrowth, sampleMap;
+    unsigned long long mcVersion;
+    const void *mcOffsets;
+};
+
 template <class T>
 struct DevBuf {
     T *p = nullptr;
@@ -147,10 +157,21 @@ struct VVRenderer {
     unsigned int *host_counters = nullptr; // pinned
     // sample-parallel pipeline state
     DevBuf<float4> rayA, rayB, src;
-    DevBuf<uint2> tileRec, items[2];
+    DevBuf<uint2> tileRec, items[3];       // items[0]: first depth window (kept while the view is unchanged), [1], [2]: later windows
+    DevBuf<unsigned int> tileLive;
+    // the view the ray records / src rows / first-window items on the device were computed for (GeomKey), and their sizes
+    GeomKey geom_key = {};
+    bool geom_valid = false;
+    size_t geom_rows = 0;
+    int geom_nmax = 0;
+    const void *geom_rayA = nullptr;
+    unsigned long long mc_version = 0;
     int raycast_mode = 1;                  // 1: sample-parallel pipeline (default), 0: one thread per ray
     int lic_ctas_per_sm = 0;               // 0: as many as are resident (occupancy query)
     int xf_enable = 1;                     // coordinate fast paths of the walk (XF_GUARD / XF_NSHARE): 0 = the clamping samplers (check)
+    int first_window = 8, window_growth = 200;    // depth windows of early-termination frames: first length, growth in percent
+                                                  // (measured, profiles/r02/ab10_window_schedules.log: cfg1 is flat between 8 and 32,
+                                                  // a surface-like frame such as cfg3o pays for every speculative sample: 1.17 ms at 8, 2.06 at 16)
     int depth_major = 1;                   // 1: bucket work items by (band, depth chunk) for L2 locality; 0: tile-major
     int band_rows = 4;                     // block rows per band (4 x 16 = 64 pixel rows)
     DevBuf<unsigned int> buckets;
@@ -678,7 +699,24 @@ static bool termination_possible(const VVRenderer *r, const Uniforms &u)
     return corrected > 0.94;   // margin for fp32 rounding
 }
 
-// K1 as three kernels: ray_setup -> [lic_sample -> composite] per depth window (see vv_kernels.cu)
+static void make_geom_key(const VVRenderer *r, const DevParams &P, int first_window, GeomKey &k)
+{
+    std::memset(&k, 0, sizeof(k));
+    std::memcpy(k.camD, P.camD, sizeof(k.camD)); std::memcpy(k.rot, P.rot, sizeof(k.rot));
+    k.tanHalf = P.tanHalf; k.aspect = P.aspect; std::memcpy(k.extent, P.extent, sizeof(k.extent)); k.nearD = P.nearD; k.farD = P.farD;
+    std::memcpy(k.clipEq, P.clipEq, sizeof(k.clipEq)); std::memcpy(k.clipN, P.clipN, sizeof(k.clipN));
+    for (int i = 0; i < 3; ++i) k.clipDist[i] = (i < P.nClip && P.clipDist[i] == P.clipDist[i]) ? P.clipDist[i] : -1e300;   // NaN-free
+    std::memcpy(k.centerD, P.centerD, sizeof(k.centerD)); std::memcpy(k.slCenter, P.slCenter, sizeof(k.slCenter));
+    k.stepSize = P.stepSize;
+    for (int i = 0; i < 3; ++i) { k.scaleVol[i] = P.scaleVol[i]; k.texMax[i] = P.texMax[i]; k.camera[i] = P.camera[i]; k.slV[i] = P.slV[i]; }
+    k.slD = P.slD;
+    k.width = P.width; k.height = P.height; k.numIter = P.numIter; k.nClip = P.nClip; k.rank = P.rank; k.world = P.world;
+    k.nLocalBlocks = P.nLocalBlocks; k.blockSkew = P.blockSkew; k.slicing = P.slicing; k.slNum = P.slNum;
+    k.depthMajor = r->depth_major; k.bandRows = r->band_rows; k.firstWindow = first_window; k.windowGrowth = r->window_growth; k.sampleMap = P.samplesPerPixel ? 1 : 0;
+    k.mcVersion = r->mc_version; k.mcOffsets = P.mcOffsets;
+}
+
+// K1 as three kernels: ray_setup -> [work items -> lic_sample -> composite] per depth window (see vv_kernels.cu)
 static int render_sample_parallel(VVRenderer *r, DevParams &P)
 {
     const int nTiles = r->n_local_blocks * 8;
@@ -686,69 +724,109 @@ static int render_sample_parallel(VVRenderer *r, DevParams &P)
     CU(r->rayA.ensure((size_t)nTiles * 32));
     CU(r->rayB.ensure((size_t)nTiles * 32));
     CU(r->tileRec.ensure((size_t)nTiles));
+    CU(r->tileLive.ensure((size_t)nTiles));
     unsigned int *cnt = reinterpret_cast<unsigned int *>(r->counters.p);
-    P.rayA = r->rayA.p; P.rayB = r->rayB.p; P.tileRec = r->tileRec.p;
+    P.rayA = r->rayA.p; P.rayB = r->rayB.p; P.tileRec = r->tileRec.p; P.tileLive = r->tileLive.p;
     P.slotAlloc = cnt + 3; P.nMaxGlobal = cnt + 7; P.itemHead = cnt + 6;
     const int setup_grid = std::max(1, std::min((nTiles + 7) / 8, r->num_sms * 8));
-    CU(launch_ray_setup(P, setup_grid, r->stream));
-    ++r->launches;
-    // size the src / item buffers from the allocation the set-up made (one small read-back per frame)
-    if (!r->host_counters) CU(cudaMallocHost((void **)&r->host_counters, kNumCounters * sizeof(unsigned int)));
-    CU(cudaMemcpyAsync(r->host_counters, cnt, kNumCounters * sizeof(unsigned int), cudaMemcpyDeviceToHost, r->stream));
-    CU(cudaStreamSynchronize(r->stream));
-    const size_t rows = r->host_counters[3];
-    const int nmax = (int)r->host_counters[7];
-    if (rows == 0 || nmax == 0) return VV_OK;
+    // depth windows: whole ray at once when no sample can trigger the early termination (and without the FBO nothing stops a slice
+    // from being blended), else 8, 16, 32, ... samples (VV_OPT_FIRST_WINDOW / VV_OPT_WINDOW_GROWTH): a window bounds the work done
+    // speculatively past a termination
+    const bool windowed = P.slicing == 1 || (!P.slicing && termination_possible(r, derive_uniforms(r)));
+    const int first_window = windowed ? r->first_window : 0x7fffffff;
+    GeomKey key;
+    make_geom_key(r, P, first_window, key);
+    const bool same_view = r->geom_valid && std::memcmp(&key, &r->geom_key, sizeof(key)) == 0 && r->rayA.p == r->geom_rayA;
+    if (!same_view) {
+        r->geom_valid = false;
+        CU(cudaMemsetAsync(cnt, 0, kNumCounters * sizeof(unsigned int), r->stream));
+        CU(launch_ray_setup(P, setup_grid, r->stream));
+        ++r->launches;
+        // size the src / item buffers from the allocation the set-up made (one small read-back, only when the view changed)
+        if (!r->host_counters) CU(cudaMallocHost((void **)&r->host_counters, kNumCounters * sizeof(unsigned int)));
+        CU(cudaMemcpyAsync(r->host_counters, cnt, kNumCounters * sizeof(unsigned int), cudaMemcpyDeviceToHost, r->stream));
+        CU(cudaStreamSynchronize(r->stream));
+        r->geom_rows = r->host_counters[3];
+        r->geom_nmax = (int)r->host_counters[7];
+    } else if (P.slicing) {
+        // (the slicing set-up also counts ray samples and paints the white background: it runs again, and so does the item
+        // construction below; only the sizes are known already)
+        CU(cudaMemsetAsync(cnt, 0, kNumCounters * sizeof(unsigned int), r->stream));
+        CU(launch_ray_setup(P, setup_grid, r->stream));
+        ++r->launches;
+    } else {
+        CU(launch_ray_reset(P, cnt, setup_grid, r->stream));
+        ++r->launches;
+    }
+    const size_t rows = r->geom_rows;
+    const int nmax = r->geom_nmax;
+    if (rows == 0 || nmax == 0) { r->geom_key = key; r->geom_rayA = r->rayA.p; r->geom_valid = true; return VV_OK; }
+    if (rows * 512 > ((size_t)64 << 30)) return fail(VV_ERR_INVALID, "frame needs more than 64 GiB of ray-sample buffer (stepSizeVol too small for this frame size)");
     CU(r->src.ensure(rows * 32));
     CU(r->items[0].ensure(rows));
-    CU(r->items[1].ensure(rows));
     P.src = r->src.p;
-    // depth windows: whole ray at once when no sample can trigger the early termination, else 4, 8, 16, ... samples
     std::vector<int> w;
     w.push_back(0);
-    // (slicing stops on the accumulated dest.a, which any TF can drive past 0.95: always windowed)
-    // (without the FBO nothing stops a slice from being blended: one window)
-    if (P.slicing == 2 || (!P.slicing && !termination_possible(r, derive_uniforms(r)))) w.push_back(nmax);
-    else for (int len = 4; w.back() < nmax; len *= 2) w.push_back(std::min(nmax, w.back() + len));
+    if (!windowed) w.push_back(nmax);
+    else for (int len = first_window; w.back() < nmax; len = std::max(8, (len * r->window_growth / 100 + 7) & ~7)) w.push_back(std::min(nmax, w.back() + len));
     w.push_back(w.back());   // sentinel: nothing after the last window
+    if (w.size() > 3) { CU(r->items[1].ensure(rows)); CU(r->items[2].ensure(rows)); }
     const int comp_grid = setup_grid;
     const int lic_grid = r->num_sms * r->lic_ctas_per_sm;   // 0: launcher uses the occupancy of the instantiation
     const bool ngate = r->illum_mode != ILLUM_GRADIENT && r->noise_gate;
-    int cur = 0;
-    P.win0 = 0; P.win1 = 0; P.win2 = w[1];
-    P.itemsNext = r->items[cur].p; P.itemCountNext = cnt + 4 + cur;
-    if (r->depth_major) {
-        // work items of the first window in (band, depth chunk)-major order (see item_bucket_kernel)
-        P.bandRows = r->band_rows;
-        P.nDepthChunks = (std::min(nmax, w[1]) + 7) / 8;
-        const int nBands = (r->nby + r->band_rows - 1) / r->band_rows;
+    const int nBands = (r->nby + r->band_rows - 1) / r->band_rows;
+    P.bandRows = r->band_rows;
+    P.emitItems = r->depth_major ? 0 : 1;
+    // work items of window p = [w[p], w[p+1]) into `items` / `count`, in (band, depth chunk)-major order (item_bucket_kernel)
+    auto build_items = [&](size_t p, uint2 *items, unsigned int *count) -> int {
+        P.win1 = w[p]; P.win2 = w[p + 1];
+        P.nDepthChunks = (w[p + 1] - w[p] + 7) / 8;
         const int nBuckets = nBands * P.nDepthChunks;
         CU(r->buckets.ensure((size_t)3 * nBuckets));
         CU(cudaMemsetAsync(r->buckets.p, 0, (size_t)3 * nBuckets * sizeof(unsigned int), r->stream));
         P.bucketCount = r->buckets.p; P.bucketBase = r->buckets.p + nBuckets; P.bucketFill = r->buckets.p + 2 * nBuckets;
+        P.itemsNext = items; P.itemCountNext = count;
         CU(launch_item_buckets(P, nBuckets, comp_grid, r->stream));
         r->launches += 3;
-    } else {
-        // empty window [0,0): composite_kernel emits the work items of the first real window, tile-major
-        P.sampleCounter = nullptr;
-        CU(launch_composite(P, comp_grid, r->stream));
-        ++r->launches;
+        return VV_OK;
+    };
+    if (!same_view || P.slicing) {
+        // the first window's items live in their own buffer and counter ([8]): an unchanged view reuses them
+        if (r->depth_major) {
+            int rc = build_items(0, r->items[0].p, cnt + 8);
+            if (rc) return rc;
+        } else {
+            // empty window [0,0): composite_kernel emits the work items of the first real window, tile-major
+            P.win0 = 0; P.win1 = 0; P.win2 = w[1];
+            P.itemsNext = r->items[0].p; P.itemCountNext = cnt + 8;
+            P.sampleCounter = nullptr;
+            CU(launch_composite(P, comp_grid, r->stream));
+            ++r->launches;
+        }
+        r->geom_key = key; r->geom_rayA = r->rayA.p; r->geom_valid = true;
     }
     P.sampleCounter = r->count_samples ? r->counters.p : nullptr;
     CU(cudaEventRecord(r->ev0, r->stream));
     for (size_t p = 0; p + 2 < w.size(); ++p) {
-        P.win0 = w[p]; P.win1 = w[p + 1]; P.win2 = w[p + 2];
-        P.items = r->items[cur].p; P.itemCount = cnt + 4 + cur;
-        P.itemsNext = r->items[cur ^ 1].p; P.itemCountNext = cnt + 4 + (cur ^ 1);
+        uint2 *items = (p == 0) ? r->items[0].p : r->items[1 + (p & 1)].p;
+        unsigned int *count = (p == 0) ? cnt + 8 : cnt + 4 + (p & 1);
+        uint2 *items_next = r->items[1 + ((p + 1) & 1)].p;
+        unsigned int *count_next = cnt + 4 + ((p + 1) & 1);
         if (p > 0) {
             CU(cudaMemsetAsync(cnt + 6, 0, sizeof(unsigned int), r->stream));          // queue head
+            if (r->depth_major) {
+                int rc = build_items(p, items, count);
+                if (rc) return rc;
+            }
         }
-        CU(cudaMemsetAsync(cnt + 4 + (cur ^ 1), 0, sizeof(unsigned int), r->stream));  // next window's item count
+        P.win0 = w[p]; P.win1 = w[p + 1]; P.win2 = w[p + 2];
+        P.items = items; P.itemCount = count;
+        P.itemsNext = items_next; P.itemCountNext = count_next;
+        if (P.emitItems && p + 3 < w.size()) CU(cudaMemsetAsync(count_next, 0, sizeof(unsigned int), r->stream));   // next window's item count
         CU(launch_lic_sample(P, r->field_layout, r->illum_mode, ngate, r->speed_of_flow, lic_grid, r->stream));
         if (p == 0) CU(cudaEventRecord(r->ev1, r->stream));   // first window = the bulk of the work (all of it in single-window mode)
         CU(launch_composite(P, comp_grid, r->stream));
         r->launches += 2;
-        cur ^= 1;
     }
     return VV_OK;
 }
@@ -859,6 +937,7 @@ int vv_set_mc_offsets(VVRenderer *r, const float *offsets, int width, int height
     if (!r) return fail(VV_ERR_INVALID, "null renderer");
     CU(cudaSetDevice(r->device));
     r->frame_valid = false;
+    ++r->mc_version;                       // the ray records of the previous frame started from the old offsets
     if (!offsets) { r->mc_offsets.release(); r->mc_w = r->mc_h = 0; return VV_OK; }
     if (width < 1 || height < 1) return fail(VV_ERR_INVALID, "vv_set_mc_offsets: bad size");
     const size_t n = (size_t)width * height;
@@ -1210,6 +1289,12 @@ int vv_set_option(VVRenderer *r, int option, int value)
     case VV_OPT_BAND_ROWS:
         if (value < 1 || value > 1024) return fail(VV_ERR_INVALID, "bad band rows");
         r->band_rows = value; break;
+    case VV_OPT_FIRST_WINDOW:
+        if (value < 8 || value > 4096 || (value % 8)) return fail(VV_ERR_INVALID, "first window must be a multiple of 8 in 8..4096");
+        r->first_window = value; break;
+    case VV_OPT_WINDOW_GROWTH:
+        if (value < 100 || value > 400) return fail(VV_ERR_INVALID, "window growth must be 100..400 percent");
+        r->window_growth = value; break;
     case VV_OPT_WALK_FAST_PATHS:
         if (value != 0 && value != 1) return fail(VV_ERR_INVALID, "bad walk fast-path switch");
         r->xf_enable = value; break;
@@ -1296,7 +1381,12 @@ static int render_frame(VVRenderer *r, int update)
     DevParams P;
     int rc = fill_params(r, P, true, r->technique == VV_VOLIC_RAYCAST || r->technique == VV_VOLIC_SLICING);
     if (rc) return rc;
-    CU(cudaMemsetAsync(r->counters.p, 0, kNumCounters * sizeof(unsigned int), r->stream));
+    // (the sample-parallel pipeline manages its counters itself: some of them outlive the frame, see render_sample_parallel)
+    const bool pipeline = r->technique == VV_VOLIC_SLICING || (r->technique == VV_VOLIC_RAYCAST && r->raycast_mode != 0);
+    if (!pipeline) {
+        CU(cudaMemsetAsync(r->counters.p, 0, kNumCounters * sizeof(unsigned int), r->stream));
+        r->geom_valid = false;             // the other techniques use the same counters and tile buffers
+    }
     const int grid = persistent_grid(r, r->n_local_blocks);
     switch (r->technique) {
     case VV_VOLIC_SLICING:
