@@ -604,6 +604,21 @@ def run_cfg5(args):
     r.setLICVolumeSlab(*__import__("vectorvisualization_b200.dist", fromlist=["slab_range"]).slab_range(depth, rank, world))
     r.updateLICVolume(); torch.cuda.synchronize()
     k_vol_ms = amax(r.lastKernelMs())
+    # the volume the ranks assembled from their z-slabs against the whole volume computed on one GPU, at full size: rank 0 keeps
+    # a copy of the gathered volume, computes all slabs itself into the same buffer and compares on the device
+    identical = None
+    if world > 1:
+        volume(); torch.cuda.synchronize()
+        if rank == 0:
+            ptr, dims = r.licVolumePtr()
+            from vectorvisualization_b200.dist import device_tensor
+            vol = device_tensor(ptr, (dims[2] * dims[1] * dims[0],), torch.float32)
+            gathered = vol.clone()
+            r.setLICVolumeSlab(0, depth)
+            r.updateLICVolume(); torch.cuda.synchronize()
+            identical = bool(torch.equal(vol, gathered))
+            del gathered
+        dist.barrier()
     if rank != 0:
         return 0
     peak, peak_src, _ = measured_peaks()
@@ -617,6 +632,7 @@ def run_cfg5(args):
             depth, depth, world, scene.width, scene.height)},
         "lic_volume": {"ms_per_volume": vol_ms, "voxels_per_s": nvox / (vol_ms * 1e-3), "lic_taps_per_s": nvox * 65 / (vol_ms * 1e-3),
                        "slab_kernel_ms_max_over_ranks": k_vol_ms, "voxels": nvox,
+                       "gathered_slabs_bit_identical_to_one_gpu": identical,
                        "includes": "slab kernel on every rank + NCCL all-gather of the fp32 slabs" if world > 1 else "kernel only (one GPU)"},
         "volume_raycast": {"ms_per_frame": ray_ms, "ray_samples_per_frame": samples, "ray_samples_per_s": samples / (ray_ms * 1e-3)},
         "roofline": {"bound": "hbm", "kernel": "lic_volume_kernel", "achieved": B * (nvox / world) / (k_vol_ms * 1e-3) / 1e9, "peak": peak,

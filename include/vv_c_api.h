@@ -79,7 +79,7 @@ typedef enum VVOption {
     VV_OPT_QUIRK_SCALEVOLINV = 4,  /* 1 (default): reproduce VV/renderer.cpp:941-944 */
     VV_OPT_QUIRK_LUMINANCE_ALPHA = 5, /* 0 (default): noise .a is the noise value; 1: GL_LUMINANCE .a == 1 (Q7) */
     VV_OPT_LICVOL_FP16 = 6,        /* 1 (default): LIC volume rounded to fp16 like the RGBA16F target (Q14) */
-    VV_OPT_FIELD_LAYOUT = 7,       /* 0: float4 [z][y][x]; 1 (default): x-pair-packed fp16 (16 B/voxel) */
+    VV_OPT_FIELD_LAYOUT = 7,       /* 0: float4 [z][y][x]; 1 (default): x-pair-packed fp16 (16 B/voxel); 2: xy-quad-packed fp16 (32 B/voxel, one 256-bit load per cell face: for incoherent walks) */
     VV_OPT_COUNT_SAMPLES = 8,      /* 1 (default): count ray samples per frame */
     VV_OPT_LICVOL_SIZE = 9,        /* LIC-volume edge length; 0 (default) = field resolution (reference: 512) */
     VV_OPT_SPEC_EXP = 10,          /* gl_LightSource[0].spotExponent as int (default 40, VV/illumination.h:52) */

@@ -1,4 +1,5 @@
-"""LIC-volume mode timing: python scripts/run_licvol.py <n> <image size> [cfg name]  (precompute + volume ray-cast)"""
+"""LIC-volume mode timing: python scripts/run_licvol.py <n> <image size> [cfg name] [field layout]  (precompute + volume ray-cast)"""
+import hashlib
 import os
 import sys
 import time
@@ -13,6 +14,8 @@ s = getattr(configs, name)(n=n, size=size) if name in ("cfg5", "cfg4") else geta
 s.technique = vv.VOLIC_LICVOLUME
 print("generated %s n=%d in %.1f s" % (name, n, time.perf_counter() - t), flush=True)
 r = vv.Renderer(0)
+if len(sys.argv) > 4:
+    r.setOption(vv.OPT_FIELD_LAYOUT, int(sys.argv[4]))      # 1 x-pair (default), 2 xy-quad
 t = time.perf_counter()
 configs.apply_scene(r, s)
 r.synchronize()
@@ -24,6 +27,7 @@ for i in range(3):
     ms = r.lastKernelMs()
     vox = n ** 3
     print("lic_volume %d^3: %.2f ms (kernel %.2f ms) = %.3f G voxels/s = %.3f G LIC taps/s" % (n, dt * 1e3, ms, vox / ms / 1e6, vox * 65 / ms / 1e6), flush=True)
+print("volume sha1 %s" % hashlib.sha1(r.readLICVolume().tobytes()).hexdigest()[:16], flush=True)
 for i in range(3):
     t = time.perf_counter()
     r.render(True); r.synchronize()

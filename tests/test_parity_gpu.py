@@ -348,13 +348,18 @@ def test_slicing_default_modes(vv):
 
 
 def test_layouts_bit_identical(vv):
-    """float4 and x-pair fp16 layouts hold the same RGBA16F values -> identical frames"""
+    """float4, x-pair fp16 and xy-quad fp16 layouts hold the same RGBA16F values -> identical frames, field read-backs and LIC volumes"""
     from vectorvisualization_b200 import configs
-    s = configs.cfg3(n=48, size=96)
-    _, a, _, ca, ta = render_cuda(vv, s, layout=vv.LAYOUT_PAIR)
-    _, b, _, cb, tb = render_cuda(vv, s, layout=vv.LAYOUT_F4)
-    assert ta == tb and np.array_equal(ca, cb)
-    assert np.array_equal(a, b)
+    for s in (configs.cfg3(n=48, size=96), configs.cfg1(n=40, size=80), configs.cfg4(n=48, size=96, noise_n=32)):
+        ra, a, _, ca, ta = render_cuda(vv, s, layout=vv.LAYOUT_PAIR)
+        _, b, _, cb, tb = render_cuda(vv, s, layout=vv.LAYOUT_F4)
+        rc, c, _, cc, tc = render_cuda(vv, s, layout=vv.LAYOUT_QUAD)
+        assert ta == tb == tc and np.array_equal(ca, cb) and np.array_equal(ca, cc)
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+        assert np.array_equal(ra.readFieldTexture(s.field.shape[:3]), rc.readFieldTexture(s.field.shape[:3]))
+        ra.setOption(vv.OPT_LICVOL_FP16, 0); rc.setOption(vv.OPT_LICVOL_FP16, 0)
+        ra.updateLICVolume(); rc.updateLICVolume()
+        assert np.array_equal(ra.readLICVolume(), rc.readLICVolume())
 
 
 @pytest.mark.parametrize("name", ["cfg1_small", "cfg3_small", "gate_tf_alpha_tf_a", "odd_image_size"])

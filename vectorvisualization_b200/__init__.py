@@ -25,7 +25,7 @@ GATE_ALWAYS, GATE_TF_ALPHA = 0, 1
 (OPT_TF_MODE, OPT_GATE_MODE, OPT_NOISE_GATE, OPT_QUIRK_SCALEVOLINV, OPT_QUIRK_LUMINANCE_ALPHA, OPT_LICVOL_FP16,
  OPT_FIELD_LAYOUT, OPT_COUNT_SAMPLES, OPT_LICVOL_SIZE, OPT_SPEC_EXP, OPT_SAMPLE_MAP, OPT_RAYCAST_MODE,
  OPT_LIC_CTAS_PER_SM, OPT_WALK_FAST_PATHS, OPT_DEPTH_MAJOR, OPT_BAND_ROWS, OPT_NOISE_LAYOUT, OPT_FIRST_WINDOW, OPT_WINDOW_GROWTH) = range(1, 20)
-LAYOUT_F4, LAYOUT_PAIR = 0, 1
+LAYOUT_F4, LAYOUT_PAIR, LAYOUT_QUAD = 0, 1, 2
 BLOCK = 16  # pixels per image-block edge (sort-first partition unit)
 
 

@@ -2,6 +2,8 @@
 //
 // Data layout in HBM (see DESIGN.md "Layouts"):
 //   vector field   LAYOUT_PAIR : uint4 [z][y][x] = { half4 T[x], half4 T[min(x+1,nx-1)] }   16 B/voxel, G guard cells per side
+//                  LAYOUT_QUAD : 2 x uint4 [z][y][x] = the pairs of rows y and y+1 (the xy face of the trilinear cell in one
+//                                32-byte sector, read with one 256-bit load)                  32 B/voxel, same guard geometry
 //                  LAYOUT_F4   : float4 [z][y][x]                                             16 B/voxel
 //                  T = the reference's RGBA16F texture contents (VV/dataset.cpp:290-366): rgb = 0.5 v/|v| + 0.5,
 //                  a = |v|/max|v|, rounded to fp16 -- so both layouts hold the same values.
@@ -22,7 +24,7 @@
 
 namespace vvb200 {
 
-enum { LAYOUT_F4 = 0, LAYOUT_PAIR = 1 };
+enum { LAYOUT_F4 = 0, LAYOUT_PAIR = 1, LAYOUT_QUAD = 2 };
 enum { ILLUM_NONE = 0, ILLUM_GRADIENT = 1, ILLUM_MALLO = 2, ILLUM_ZOECKLER = 3 };
 enum { TF_B = 0, TF_A = 1, TF_R = 2, TF_LENGTH = 3, TF_SCALAR = 4 };
 enum { GATE_ALWAYS = 0, GATE_TF_ALPHA = 1 };
@@ -176,6 +178,12 @@ __device__ __forceinline__ void axis_repeat_f(float s, float nf, int &i0, float 
 }
 
 __device__ __forceinline__ float4 ld_f4(const float4 *p) { return __ldg(p); }
+// one 256-bit load (LDG.E.256 on sm_100): two consecutive uint4, 32-byte aligned
+__device__ __forceinline__ void ld_u4x2(const uint4 *p, uint4 &a, uint4 &b)
+{
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
 __device__ __forceinline__ uint4 ld_u4(const uint4 *p) { return __ldg(p); }
 __device__ __forceinline__ uint2 ld_u2(const uint2 *p) { return __ldg(p); }
 
@@ -224,25 +232,42 @@ __device__ __forceinline__ pk2_t xlerp_h2(unsigned int w0, unsigned int w1, pk2_
 
 struct FieldVal { pk2_t rg; float b, a; };
 
+// the four x-pairs of a trilinear cell: rows A = (y0,z0), B = (y1,z0), C = (y0,z1), D = (y1,z1), each { T[x0].rg, T[x0].ba,
+// T[x0+1].rg, T[x0+1].ba } as fp16 words; idx = cell index in the padded array (DevParams::fRow / fPlane strides)
+struct CellRaw { uint4 A, B, C, D; };
+template <int LAYOUT>
+__device__ __forceinline__ CellRaw load_cell_raw(const uint4 *field, unsigned int fRow, unsigned int fPlane, int idx)
+{
+    CellRaw c;
+    if (LAYOUT == LAYOUT_QUAD) {
+        struct alignas(32) Face { uint4 y0, y1; };
+        const Face *F = reinterpret_cast<const Face *>(field) + idx;
+        ld_u4x2(reinterpret_cast<const uint4 *>(F), c.A, c.B);
+        ld_u4x2(reinterpret_cast<const uint4 *>(F + fPlane), c.C, c.D);
+    } else {
+        const uint4 *F = field + idx;
+        c.A = __ldg(F); c.B = __ldg(F + fRow); c.C = __ldg(F + fPlane); c.D = __ldg(F + fPlane + fRow);
+    }
+    return c;
+}
+
 // ---- vector field: trilinear RGBA16F fetch, CLAMP_TO_EDGE (volumeSampler, VV/dataset.cpp:350-357) ----
 template <int LAYOUT, bool ALPHA>
 __device__ __forceinline__ FieldVal fetch_field_pk(const DevParams &P, float px, float py, float pz)
 {
     FieldVal r;
-    if (LAYOUT == LAYOUT_PAIR) {
+    if (LAYOUT == LAYOUT_PAIR || LAYOUT == LAYOUT_QUAD) {
         int x0, y0, z0;
         float fx, fy, fz;
         axis_clamp_f(px, P.fnf[0], P.fnm1f[0], x0, fx);
         axis_clamp_f(py, P.fnf[1], P.fnm1f[1], y0, fy);
         axis_clamp_f(pz, P.fnf[2], P.fnm1f[2], z0, fz);
-        // 32-bit element indices (volumes up to 2^31 voxels), one zero-extended pointer add per load; the y / z
-        // neighbours are one padded row / plane further (at the clamped edge the replicated texel, weight 0)
-        const unsigned int b00 = (unsigned int)z0 * P.fPlane + (unsigned int)y0 * P.fRow + (unsigned int)x0;
-        const unsigned int b10 = b00 + P.fRow, b01 = b00 + P.fPlane, b11 = b01 + P.fRow;
+        // 32-bit cell indices (volumes up to 2^31 cells); the y / z neighbours are one padded row / plane further (at the
+        // clamped edge the replicated texel, weight 0)
         const pk2_t fx2 = bc2(fx), fy2 = bc2(fy), fz2 = bc2(fz);
-        const uint4 *F = P.field_pair;
         // corner loads A = (y0,z0), B = (y1,z0), C = (y0,z1), D = (y1,z1); each holds texels x0 (.x,.y) and x0+1 (.z,.w)
-        const uint4 A = ld_u4(F + b00), B = ld_u4(F + b10), C = ld_u4(F + b01), D = ld_u4(F + b11);
+        const CellRaw cr = load_cell_raw<LAYOUT>(P.field_pair, P.fRow, P.fPlane, z0 * (int)P.fPlane + y0 * (int)P.fRow + x0);
+        const uint4 A = cr.A, B = cr.B, C = cr.C, D = cr.D;
         // x-lerp straight from the fp16 pair: t0 + fx (t1 - t0) with t0 = FHADD(h0, 0), t1 - t0 = FHADD(h1, -t0)
         const pk2_t rgA = xlerp_h2(A.x, A.z, fx2), rgB = xlerp_h2(B.x, B.z, fx2);
         const pk2_t rgC = xlerp_h2(C.x, C.z, fx2), rgD = xlerp_h2(D.x, D.z, fx2);
@@ -351,10 +376,11 @@ __device__ __forceinline__ void widen_rg(unsigned int w0, unsigned int w1, pk2_t
     d = pk2(fh_sub(h_lo(w1), a0), fh_sub(h_hi(w1), a1));
 }
 
+template <int LAYOUT>
 __device__ __forceinline__ FieldCell load_field_cell(const DevParams &P, int idx)
 {
-    const uint4 *F = P.field_pair + idx;
-    const uint4 A = ld_u4(F), B = ld_u4(F + P.fRow), C = ld_u4(F + P.fPlane), D = ld_u4(F + P.fPlane + P.fRow);
+    const CellRaw cr = load_cell_raw<LAYOUT>(P.field_pair, P.fRow, P.fPlane, idx);
+    const uint4 A = cr.A, B = cr.B, C = cr.C, D = cr.D;
     FieldCell c;
     widen_rg(A.x, A.z, c.rg0[0], c.rgd[0]);
     widen_rg(B.x, B.z, c.rg0[1], c.rgd[1]);

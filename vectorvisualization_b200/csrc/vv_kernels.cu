@@ -175,10 +175,10 @@ __device__ __forceinline__ void heun_step(const DevParams &P, Walker &w, float s
     const float d1z = __fmul_rn(fmaf(2.0f, w.vb, -1.0f), s1);
     const float p2z = __fadd_rn(w.qz, d1z);
     const pk2_t p2 = add2(w.qxy, d1);                                      // Pos2 = newPos + licdir
-    if constexpr (LAYOUT == LAYOUT_PAIR && !SOF && VV_CELL_REUSE) {
+    if constexpr (LAYOUT != LAYOUT_F4 && !SOF && VV_CELL_REUSE) {
         constexpr bool GUARD = (XF & XF_GUARD) != 0;
         const CellCoord c2 = field_cell_coord<GUARD>(P, lo2(p2), hi2(p2), p2z);
-        const FieldCell cell = load_field_cell(P, c2.idx);
+        const FieldCell cell = load_field_cell<LAYOUT>(P, c2.idx);
         const FieldVal v2 = eval_field_cell(cell, c2.fx, c2.fy, c2.fz);
         if (dbg) { dbg[0] = lo2(p2); dbg[1] = hi2(p2); dbg[2] = p2z; dbg[3] = lo2(v2.rg); dbg[4] = hi2(v2.rg); dbg[5] = v2.b; }   // diagnostic only
         const pk2_t d2 = mul2_keep(fma2(two, v2.rg, mone), s2);
@@ -188,11 +188,11 @@ __device__ __forceinline__ void heun_step(const DevParams &P, Walker &w, float s
         const CellCoord c = field_cell_coord<GUARD>(P, lo2(w.qxy), hi2(w.qxy), w.qz);
         FieldVal v;
         if (c.idx == c2.idx) v = eval_field_cell(cell, c.fx, c.fy, c.fz);
-        else v = eval_field_cell(load_field_cell(P, c.idx), c.fx, c.fy, c.fz);   // the corrector left the predictor's cell (rare)
+        else v = eval_field_cell(load_field_cell<LAYOUT>(P, c.idx), c.fx, c.fy, c.fz);   // the corrector left the predictor's cell (rare)
         w.vrg = v.rg; w.vb = v.b; w.va = v.a;
         w.c = c;
     } else {
-        static_assert(XF == 0 || (LAYOUT == LAYOUT_PAIR && !SOF && VV_CELL_REUSE), "the coordinate fast paths live in the cell-reuse step");
+        static_assert(XF == 0 || (LAYOUT != LAYOUT_F4 && !SOF && VV_CELL_REUSE), "the coordinate fast paths live in the cell-reuse step");
         const FieldVal v2 = fetch_field_pk<LAYOUT, false>(P, lo2(p2), hi2(p2), p2z);
         const pk2_t d2 = mul2_keep(fma2(two, v2.rg, mone), s2);
         const float d2z = __fmul_rn(fmaf(2.0f, v2.b, -1.0f), s1);
@@ -1061,8 +1061,13 @@ __global__ void __launch_bounds__(256) volume_raycast_kernel(const __grid_consta
 
 // K2 ------------------------------------------------------------------------------------------------
 // one thread per voxel of the target; CTA = 8x8x4 voxels (warp = 8x4 voxels of one z-layer)
+#ifndef LICVOL_MIN_CTAS
+#define LICVOL_MIN_CTAS 4   // resident CTAs per SM lic_volume_kernel is compiled for (64 registers; the kernel is latency-bound on large chaotic
+                           // fields: 512^3 curl noise 170.5 -> 156.4 ms against 3 CTAs / 80 registers, 256^3 tornado 9.76 -> 10.0 ms; 5 CTAs / 48
+                           // registers spill: 264 ms)
+#endif
 template <int LAYOUT, bool GRAD, bool NGATE, bool SOF>
-__global__ void __launch_bounds__(256) lic_volume_kernel(const __grid_constant__ DevParams P)
+__global__ void __launch_bounds__(256, LICVOL_MIN_CTAS) lic_volume_kernel(const __grid_constant__ DevParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SharedTables &S = *reinterpret_cast<SharedTables *>(smem_raw);
@@ -1252,7 +1257,7 @@ static cudaError_t launch_sample_kernel(K kernel, const DevParams &P, int grid, 
 template <int LAYOUT, int ILLUM, bool NGATE, bool SOF, int NL>
 static cudaError_t launch_sample_xf(const DevParams &P, int grid, size_t smem, cudaStream_t st)
 {
-    if constexpr (LAYOUT == LAYOUT_PAIR && !SOF && VV_CELL_REUSE && (NL == 2 || ILLUM != ILLUM_GRADIENT)) {
+    if constexpr (LAYOUT != LAYOUT_F4 && !SOF && VV_CELL_REUSE && (NL == 2 || ILLUM != ILLUM_GRADIENT)) {
         if (P.fGuard > 1 && P.guardOk) {
             if constexpr (ILLUM == ILLUM_GRADIENT) {
                 if (P.noiseShared) return launch_sample_kernel(lic_sample_kernel<LAYOUT, ILLUM, NGATE, SOF, NL, XF_GUARD | XF_NSHARE>, P, grid, smem, st);
@@ -1302,6 +1307,7 @@ cudaError_t launch_lic_sample(const DevParams &P, int layout, int illum, bool no
 {
     const size_t smem = table_bytes(P);
     if (layout == LAYOUT_PAIR) return launch_sample_layout<LAYOUT_PAIR>(P, illum, noise_gate, speed_of_flow, grid, smem, st);
+    if (layout == LAYOUT_QUAD) return launch_sample_layout<LAYOUT_QUAD>(P, illum, noise_gate, speed_of_flow, grid, smem, st);
     return launch_sample_layout<LAYOUT_F4>(P, illum, noise_gate, speed_of_flow, grid, smem, st);
 }
 
@@ -1309,6 +1315,7 @@ cudaError_t launch_lic_raycast(const DevParams &P, int layout, int illum, bool n
 {
     const size_t smem = table_bytes(P);
     if (layout == LAYOUT_PAIR) return launch_raycast_layout<LAYOUT_PAIR>(P, illum, noise_gate, speed_of_flow, grid, smem, st);
+    if (layout == LAYOUT_QUAD) return cudaErrorNotSupported;     // the one-thread-per-ray cross-check kernel is built for the pair and float4 layouts
     return launch_raycast_layout<LAYOUT_F4>(P, illum, noise_gate, speed_of_flow, grid, smem, st);
 }
 
@@ -1316,6 +1323,7 @@ cudaError_t launch_volume_raycast(const DevParams &P, int layout, int grid, cuda
 {
     const size_t smem = table_bytes(P);
     if (layout == LAYOUT_PAIR) return launch_with_tables(volume_raycast_kernel<LAYOUT_PAIR>, P, grid, smem, st);
+    if (layout == LAYOUT_QUAD) return launch_with_tables(volume_raycast_kernel<LAYOUT_QUAD>, P, grid, smem, st);
     return launch_with_tables(volume_raycast_kernel<LAYOUT_F4>, P, grid, smem, st);
 }
 
@@ -1342,6 +1350,11 @@ cudaError_t launch_lic_volume(const DevParams &P, int layout, bool grad, bool no
         if (grad) return launch_licvol_sof<LAYOUT_PAIR, true, false>(P, speed_of_flow, grid, smem, st);
         return noise_gate ? launch_licvol_sof<LAYOUT_PAIR, false, true>(P, speed_of_flow, grid, smem, st)
                           : launch_licvol_sof<LAYOUT_PAIR, false, false>(P, speed_of_flow, grid, smem, st);
+    }
+    if (layout == LAYOUT_QUAD) {
+        if (grad) return launch_licvol_sof<LAYOUT_QUAD, true, false>(P, speed_of_flow, grid, smem, st);
+        return noise_gate ? launch_licvol_sof<LAYOUT_QUAD, false, true>(P, speed_of_flow, grid, smem, st)
+                          : launch_licvol_sof<LAYOUT_QUAD, false, false>(P, speed_of_flow, grid, smem, st);
     }
     if (grad) return launch_licvol_sof<LAYOUT_F4, true, false>(P, speed_of_flow, grid, smem, st);
     return noise_gate ? launch_licvol_sof<LAYOUT_F4, false, true>(P, speed_of_flow, grid, smem, st)

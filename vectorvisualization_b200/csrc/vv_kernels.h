@@ -41,7 +41,7 @@ cudaError_t launch_wait_arrivals(unsigned int *flag, unsigned int target, unsign
 // tmp: float4 [n] scratch; maxbits: 1 uint scratch.  Writes the pair-packed fp16 layout (padded [nz+2G][ny+2G][frow], cell
 // (x,y,z) at ((z+G)(ny+2G) + (y+G)) frow + x + gx, edge replicated) and/or the float4 layout.
 cudaError_t launch_pack_field(const void *v0, const void *v1, int is_u8, int nx, int ny, int nz, float interp_frac,
-                              float4 *tmp, unsigned int *maxbits, uint4 *out_pair, int guard, int gx, int frow, float4 *out_f4, cudaStream_t st);
+                              float4 *tmp, unsigned int *maxbits, uint4 *out_pair, int guard, int gx, int frow, int quad, float4 *out_f4, cudaStream_t st);
 // u8 volume -> cell8 layout (wrap: 0 = CLAMP_TO_EDGE, 1 = REPEAT); src_stride = bytes per voxel, src_offset = channel;
 // pad = 1 adds the wrapped cell -1 on every axis: out is [nz+1][ny+1][nx+1]
 cudaError_t launch_build_cell8(const uint8_t *src, int src_stride, int src_offset, int nx, int ny, int nz, int repeat, int pad,

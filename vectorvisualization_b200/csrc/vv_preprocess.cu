@@ -71,8 +71,9 @@ __device__ __forceinline__ uint2 to_half4(float4 v, float maxLen)
 // ((z+G) (ny+2G) + (y+G)) fRow + (x+gx); every cell holds texels (clamp(x), clamp(x+1)) of row clamp(y), plane clamp(z).
 // G = 1 / gx = 0 is the minimum (the sampler's y / z neighbours are always one row / plane further, x is baked into the pair);
 // larger guards let the walk drop the coordinate clamp altogether (XF_GUARD).
+// quad != 0: every cell holds the pairs of rows y and y + 1 (2 x uint4, LAYOUT_QUAD)
 __global__ void pack_field_pass2(const float4 *__restrict__ tmp, const unsigned int *__restrict__ maxbits, int nx, int ny, int nz,
-                                 int guard, int gx, int frow, uint4 *__restrict__ out_pair, float4 *__restrict__ out_f4)
+                                 int guard, int gx, int frow, int quad, uint4 *__restrict__ out_pair, float4 *__restrict__ out_f4)
 {
     const float maxLen = __uint_as_float(*maxbits);
     const size_t n = (size_t)nx * ny * nz;
@@ -92,13 +93,21 @@ __global__ void pack_field_pass2(const float4 *__restrict__ tmp, const unsigned 
             const size_t s = ((size_t)min(max(z, 0), nz - 1) * ny + min(max(y, 0), ny - 1)) * nx;
             uint2 t0 = to_half4(tmp[s + x0], maxLen);
             uint2 t1 = to_half4(tmp[s + x1], maxLen);
+            if (quad) {
+                const size_t s1 = ((size_t)min(max(z, 0), nz - 1) * ny + min(max(y + 1, 0), ny - 1)) * nx;
+                uint2 u0 = to_half4(tmp[s1 + x0], maxLen);
+                uint2 u1 = to_half4(tmp[s1 + x1], maxLen);
+                out_pair[2 * a] = make_uint4(t0.x, t0.y, t1.x, t1.y);
+                out_pair[2 * a + 1] = make_uint4(u0.x, u0.y, u1.x, u1.y);
+                continue;
+            }
             out_pair[a] = make_uint4(t0.x, t0.y, t1.x, t1.y);
         }
     }
 }
 
 cudaError_t launch_pack_field(const void *v0, const void *v1, int is_u8, int nx, int ny, int nz, float interp_frac,
-                              float4 *tmp, unsigned int *maxbits, uint4 *out_pair, int guard, int gx, int frow, float4 *out_f4, cudaStream_t st)
+                              float4 *tmp, unsigned int *maxbits, uint4 *out_pair, int guard, int gx, int frow, int quad, float4 *out_f4, cudaStream_t st)
 {
     const size_t n = (size_t)nx * ny * nz;
     cudaError_t e = cudaMemsetAsync(maxbits, 0, sizeof(unsigned int), st);
@@ -106,7 +115,7 @@ cudaError_t launch_pack_field(const void *v0, const void *v1, int is_u8, int nx,
     const int grid = 148 * 8;
     if (is_u8) pack_field_pass1<true><<<grid, 256, 0, st>>>(v0, v1, n, interp_frac, tmp, maxbits);
     else pack_field_pass1<false><<<grid, 256, 0, st>>>(v0, v1, n, interp_frac, tmp, maxbits);
-    pack_field_pass2<<<grid, 256, 0, st>>>(tmp, maxbits, nx, ny, nz, guard, gx, frow, out_pair, out_f4);
+    pack_field_pass2<<<grid, 256, 0, st>>>(tmp, maxbits, nx, ny, nz, guard, gx, frow, quad, out_pair, out_f4);
     return cudaGetLastError();
 }
 

@@ -356,7 +356,9 @@ static int pack_field(VVRenderer *r)
     CU(r->maxbits.ensure(1));
     uint4 *pair = nullptr;
     float4 *f4 = nullptr;
-    if (r->field_layout == LAYOUT_PAIR) {
+    const bool cells = r->field_layout == LAYOUT_PAIR || r->field_layout == LAYOUT_QUAD;
+    const size_t per_cell = r->field_layout == LAYOUT_QUAD ? 2 : 1;     // uint4 per cell
+    if (cells) {
         // guard cells: what the unclamped walk needs (guard_wanted, from the LIC parameters), as long as the padded array stays
         // addressable with signed 32-bit element offsets; else the minimum and the clamping samplers
         int g = std::max(1, r->guard_wanted);
@@ -369,13 +371,13 @@ static int pack_field(VVRenderer *r)
         r->field_guard = g;
         r->field_gx = g > 1 ? ((g + 7) & ~7) : 0;               // x guard in whole 128-byte lines: cell x = 0 stays line-aligned
         r->field_row = (r->size[0] + 2 * r->field_gx + 7) & ~7;
-        CU(r->field_pair.ensure(padded(g)));
+        CU(r->field_pair.ensure(padded(g) * per_cell));
         pair = r->field_pair.p;
     }
     else { CU(r->field_f4.ensure(n)); f4 = r->field_f4.p; }
     const float frac = (float)r->interp_index / r->interp_size;   // VV/dataset.cpp:590
     CU(launch_pack_field(r->raw0.p, r->have_next ? r->raw1.p : nullptr, r->field_u8 ? 1 : 0, r->size[0], r->size[1], r->size[2],
-                         frac, r->pack_tmp.p, r->maxbits.p, pair, r->field_guard, r->field_gx, r->field_row, f4, r->stream));
+                         frac, r->pack_tmp.p, r->maxbits.p, pair, r->field_guard, r->field_gx, r->field_row, r->field_layout == LAYOUT_QUAD ? 1 : 0, f4, r->stream));
     r->field_dirty = false;
     return VV_OK;
 }
@@ -400,10 +402,10 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycas
         const int need = (reach < 60.0) ? (((int)std::ceil(reach) + 3 + 3) & ~3) : 1;      // capped: beyond 64 cells the clamping samplers run
         r->guard_wanted = std::max(need, 1);
         r->walk_reach = (float)((double)(std::max(u.nFwd, u.nBwd) + 2) * (double)(u.licParams[2] * 0.3f));
-        if (r->field_layout == LAYOUT_PAIR && r->field_pair.p && !r->field_dirty && r->field_guard < r->guard_wanted && need > 1)
+        if (r->field_layout != LAYOUT_F4 && r->field_pair.p && !r->field_dirty && r->field_guard < r->guard_wanted && need > 1)
             r->field_dirty = true;      // the LIC parameters outgrew the packed guard band: pack again with the larger one
     }
-    if (r->field_dirty || (r->field_layout == LAYOUT_PAIR ? !r->field_pair.p : !r->field_f4.p)) {
+    if (r->field_dirty || (r->field_layout != LAYOUT_F4 ? !r->field_pair.p : !r->field_f4.p)) {
         int rc = pack_field(r);
         if (rc) return rc;
     }
@@ -424,7 +426,8 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycas
     P.field_f4 = r->field_f4.p;
     P.fnx = r->size[0]; P.fny = r->size[1]; P.fnz = r->size[2];
     P.fRow = (unsigned int)r->field_row; P.fPlane = (unsigned int)r->field_row * (unsigned int)(r->size[1] + 2 * r->field_guard);
-    P.field_pair = r->field_pair.p ? r->field_pair.p + ((size_t)r->field_guard * P.fPlane + (size_t)r->field_guard * P.fRow + r->field_gx) : nullptr;
+    P.field_pair = r->field_pair.p ? r->field_pair.p + ((size_t)r->field_guard * P.fPlane + (size_t)r->field_guard * P.fRow + r->field_gx) *
+                                                           (r->field_layout == LAYOUT_QUAD ? 2 : 1) : nullptr;
     P.fGuard = r->field_guard;
     P.walkReach = r->walk_reach;
     P.guardOk = (r->field_guard > 1 && r->field_guard >= r->guard_wanted && r->xf_enable) ? 1 : 0;
@@ -447,7 +450,7 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycas
     if (r->noise_layout == 2 && r->noise_bf.p && r->noise_has_grad) {
         // The hot RGBA-noise layout takes the vector field's guard geometry when both volumes have the same dimensions: one cell
         // index then addresses both arrays (XF_NSHARE).  Rebuilt from the RGBA texels whenever the field's geometry moved.
-        const bool share = P.guardOk && r->field_layout == LAYOUT_PAIR && P.noiseSameDims && grad;
+        const bool share = P.guardOk && r->field_layout != LAYOUT_F4 && P.noiseSameDims && grad;
         const int g = share ? r->field_guard : 1, gx = share ? r->field_gx : 1, row = share ? r->field_row : r->ndim[0] + 1;
         if (g != r->nbf_guard || gx != r->nbf_gx || row != r->nbf_row) {
             CU(r->noise_bf.ensure((size_t)row * (r->ndim[1] + 2 * g) * (r->ndim[2] + 2 * g)));
@@ -1265,7 +1268,7 @@ int vv_set_option(VVRenderer *r, int option, int value)
     case VV_OPT_QUIRK_LUMINANCE_ALPHA: r->quirk_lum_alpha = value != 0; break;
     case VV_OPT_LICVOL_FP16: r->licvol_fp16 = value != 0; break;
     case VV_OPT_FIELD_LAYOUT:
-        if (value != LAYOUT_F4 && value != LAYOUT_PAIR) return fail(VV_ERR_INVALID, "bad field layout");
+        if (value != LAYOUT_F4 && value != LAYOUT_PAIR && value != LAYOUT_QUAD) return fail(VV_ERR_INVALID, "bad field layout");
         if (value != r->field_layout) {
             r->field_layout = value;
             r->field_pair.release();
@@ -1534,14 +1537,15 @@ int vv_read_field_texture(VVRenderer *r, float *out, size_t out_bytes)
     }
     // gather the unpadded [nz][ny][nx] texels out of the padded x-pair layout, one row at a time
     const size_t nx = r->size[0], ny = r->size[1], nz = r->size[2], G = r->field_guard, row = r->field_row, py = ny + 2 * G;
-    std::vector<uint16_t> tmp(nx * ny * 8);
+    const size_t pc = r->field_layout == LAYOUT_QUAD ? 2 : 1;             // uint4 per cell; the cell's own texel comes first in both
+    std::vector<uint16_t> tmp(nx * ny * 8 * pc);
     for (size_t z = 0; z < nz; ++z) {
-        CU(cudaMemcpy2DAsync(tmp.data(), nx * 16, r->field_pair.p + ((z + G) * py + G) * row + r->field_gx, row * 16, nx * 16, ny,
+        CU(cudaMemcpy2DAsync(tmp.data(), nx * 16 * pc, r->field_pair.p + (((z + G) * py + G) * row + r->field_gx) * pc, row * 16 * pc, nx * 16 * pc, ny,
                              cudaMemcpyDeviceToHost, r->stream));
         CU(cudaStreamSynchronize(r->stream));
         for (size_t y = 0; y < ny; ++y)
             for (size_t x = 0; x < nx; ++x) {
-                const size_t i = (z * ny + y) * nx + x, j = y * nx + x;
+                const size_t i = (z * ny + y) * nx + x, j = (y * nx + x) * pc;
                 for (int k = 0; k < 4; ++k) out[4 * i + k] = half_bits_to_float(tmp[8 * j + k]);
             }
     }
