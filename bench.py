@@ -379,6 +379,7 @@ def run_cuda(args):
     job.warm(warm)
     local_samples = r.lastRaySamples()
     launches_per_frame = r.lastLaunchCount()
+    field_layout = {0: "float4 (16 B/voxel)", 1: "x-pair fp16 (16 B/voxel)", 2: "xy-quad fp16 (32 B/voxel, one 256-bit load per cell face)"}.get(r.fieldLayout())
     samples_per_frame = job.all_sum(local_samples)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -509,7 +510,7 @@ def run_cuda(args):
                 "parallelism": "sort-first 16x16 blocks over %d GPU(s), volume replicated" % world,
                 "exchange": {"none": "single GPU", "p2p": "peer-to-peer tile stores over NVLink + arrival counters (vv_p2p_render)",
                              "nccl": "NCCL all_gather_into_tensor of the tile buffers"}[exchange],
-                "field_layout": "x-pair fp16 (16 B/voxel)", "launches_per_frame": launches_per_frame},
+                "field_layout": field_layout, "launches_per_frame": launches_per_frame},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "fps": args.steps / e2e_s, "what": "vv_set_camera + vv_set_lic_params + vv_render + vv_read_rgba8 into pinned host memory, per frame"},
         "gpu_launches": launches_per_frame * args.steps,

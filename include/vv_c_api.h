@@ -79,7 +79,8 @@ typedef enum VVOption {
     VV_OPT_QUIRK_SCALEVOLINV = 4,  /* 1 (default): reproduce VV/renderer.cpp:941-944 */
     VV_OPT_QUIRK_LUMINANCE_ALPHA = 5, /* 0 (default): noise .a is the noise value; 1: GL_LUMINANCE .a == 1 (Q7) */
     VV_OPT_LICVOL_FP16 = 6,        /* 1 (default): LIC volume rounded to fp16 like the RGBA16F target (Q14) */
-    VV_OPT_FIELD_LAYOUT = 7,       /* 0: float4 [z][y][x]; 1 (default): x-pair-packed fp16 (16 B/voxel); 2: xy-quad-packed fp16 (32 B/voxel, one 256-bit load per cell face: for incoherent walks) */
+    VV_OPT_FIELD_LAYOUT = 7,       /* 0: float4 [z][y][x]; 1: x-pair-packed fp16 (16 B/voxel); 2: xy-quad-packed fp16 (32 B/voxel, one 256-bit load per
+                                      cell face); 3 (default): 2 up to 48 GiB of packed field, else 1.  Same frames and LIC volumes bit for bit. */
     VV_OPT_COUNT_SAMPLES = 8,      /* 1 (default): count ray samples per frame */
     VV_OPT_LICVOL_SIZE = 9,        /* LIC-volume edge length; 0 (default) = field resolution (reference: 512) */
     VV_OPT_SPEC_EXP = 10,          /* gl_LightSource[0].spotExponent as int (default 40, VV/illumination.h:52) */
@@ -91,6 +92,7 @@ typedef enum VVOption {
     VV_OPT_BAND_ROWS = 16,         /* 16-pixel block rows per band of the depth-major order (default 4) */
     VV_OPT_FIRST_WINDOW = 18,      /* early-termination frames: ray samples in the first depth window (multiple of 8, default 8) */
     VV_OPT_WINDOW_GROWTH = 19,     /* ... and the length of every further window in percent of the previous one (100..400, default 200) */
+    VV_OPT_ITEM_AFFINITY = 20,     /* lic_sample work items handed out CTA-affine in chunks of this many consecutive items (0: one global queue) */
     VV_OPT_NOISE_LAYOUT = 17       /* RGBA (-g) noise: 2 (default) bf16 {t0, t1 - t0}, 1 fp16 x-pair, 0 u8 xy-quad; same values, same frames */
 } VVOption;
 
@@ -261,6 +263,7 @@ VV_API int vv_save_raw(VVRenderer *r, const char *path);
 VV_API uint64_t vv_last_ray_samples(VVRenderer *r);   /* ray samples of the last vv_render */
 VV_API float    vv_last_kernel_ms(VVRenderer *r);     /* CUDA-event time of the dominant kernel, last frame */
 VV_API int      vv_last_launch_count(VVRenderer *r);  /* kernels launched by the last vv_render */
+VV_API int      vv_field_layout(VVRenderer *r);       /* layout the vector field is packed in (VV_OPT_FIELD_LAYOUT resolved: 0, 1 or 2) */
 VV_API int      vv_synchronize(VVRenderer *r);
 
 /* ---- device-side / multi-GPU hooks (pointers are CUDA device pointers on the handle's device) --- */

@@ -27,3 +27,29 @@ for name, mk in (("cfg1 ray-cast", lambda: configs.cfg1(n=n, size=size)),
         r.render(True)
         print("  LIC volume + volume ray-cast: %d ray samples" % r.lastRaySamples(), flush=True)
     r.close()
+
+# three partitioned handles in one process exchanging tiles through peer stores + system-scope arrival counters (vv_p2p_*):
+# the atomic work queue and the exchange are where racecheck / synccheck matter
+s = configs.cfg3(n=n, size=size)
+s.width, s.height = 40, 28
+hs = []
+for rank in range(3):
+    r = vv.Renderer(0)
+    configs.apply_scene(r, s)
+    r.setPartition(rank, 3)
+    r.render(True)
+    r.synchronize()
+    hs.append(r)
+bases = [r.p2pExport()[1] for r in hs]
+for r in hs:
+    r.p2pConnect(local_bases=bases)
+for frame in range(2):
+    for r in hs:
+        r.p2pRender()
+    for r in hs:
+        r.p2pStatus()
+        r.readRGBA8()
+print("p2p exchange, 3 handles x 2 frames: %d ray samples on rank 0" % hs[0].lastRaySamples(), flush=True)
+for r in hs:
+    r.p2pDisconnect()
+    r.close()

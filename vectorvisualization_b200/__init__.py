@@ -24,8 +24,8 @@ TF_B, TF_A, TF_R, TF_LENGTH, TF_SCALAR = range(5)
 GATE_ALWAYS, GATE_TF_ALPHA = 0, 1
 (OPT_TF_MODE, OPT_GATE_MODE, OPT_NOISE_GATE, OPT_QUIRK_SCALEVOLINV, OPT_QUIRK_LUMINANCE_ALPHA, OPT_LICVOL_FP16,
  OPT_FIELD_LAYOUT, OPT_COUNT_SAMPLES, OPT_LICVOL_SIZE, OPT_SPEC_EXP, OPT_SAMPLE_MAP, OPT_RAYCAST_MODE,
- OPT_LIC_CTAS_PER_SM, OPT_WALK_FAST_PATHS, OPT_DEPTH_MAJOR, OPT_BAND_ROWS, OPT_NOISE_LAYOUT, OPT_FIRST_WINDOW, OPT_WINDOW_GROWTH) = range(1, 20)
-LAYOUT_F4, LAYOUT_PAIR, LAYOUT_QUAD = 0, 1, 2
+ OPT_LIC_CTAS_PER_SM, OPT_WALK_FAST_PATHS, OPT_DEPTH_MAJOR, OPT_BAND_ROWS, OPT_NOISE_LAYOUT, OPT_FIRST_WINDOW, OPT_WINDOW_GROWTH, OPT_ITEM_AFFINITY) = range(1, 21)
+LAYOUT_F4, LAYOUT_PAIR, LAYOUT_QUAD, LAYOUT_AUTO = 0, 1, 2, 3   # AUTO (default): QUAD up to 48 GiB of packed field, else PAIR
 BLOCK = 16  # pixels per image-block edge (sort-first partition unit)
 
 
@@ -141,7 +141,7 @@ def load_library():
         "vv_read_sample_map": ([P, P, ctypes.c_size_t], I),
         "vv_make_illum_tables": ([F, I, I, P, P, P], I),
         "vv_save_png": ([P, CP, I], I), "vv_save_raw": ([P, CP], I),
-        "vv_last_ray_samples": ([P], U64), "vv_last_kernel_ms": ([P], F), "vv_last_launch_count": ([P], I),
+        "vv_last_ray_samples": ([P], U64), "vv_last_kernel_ms": ([P], F), "vv_last_launch_count": ([P], I), "vv_field_layout": ([P], I),
         "vv_synchronize": ([P], I), "vv_set_partition": ([P, I, I], I), "vv_set_licvol_slab": ([P, I, I], I),
         "vv_get_tile_buffer": ([P, ctypes.POINTER(P), ctypes.POINTER(I), ctypes.POINTER(I)], I),
         "vv_assemble_tiles": ([P, P, I], I), "vv_get_lic_volume_ptr": ([P, ctypes.POINTER(P), ctypes.POINTER(I)], I),
@@ -505,6 +505,10 @@ class Renderer:
 
     def lastLaunchCount(self):
         return int(self._lib.vv_last_launch_count(self._h))
+
+    def fieldLayout(self):
+        """the layout the vector field is packed in (OPT_FIELD_LAYOUT resolved): LAYOUT_F4 / LAYOUT_PAIR / LAYOUT_QUAD"""
+        return int(self._lib.vv_field_layout(self._h))
 
     def synchronize(self):
         _chk(self._lib.vv_synchronize(self._h))

@@ -32,6 +32,10 @@ enum { GATE_ALWAYS = 0, GATE_TF_ALPHA = 1 };
 constexpr int kBlockDim = 16;        // 16x16-pixel image blocks, one per CTA iteration
 constexpr int kBlockPixels = 256;
 constexpr int kMaxLicSteps = 1024;   // per direction (weights live in shared memory)
+#ifndef VV_CK_STRIDE
+#define VV_CK_STRIDE 16
+#endif
+constexpr int kCkStride = VV_CK_STRIDE;   // ray-march positions kept every kCkStride steps (ray_checkpoint_kernel)
 
 struct DevParams {
     // ---- textures ----
@@ -96,11 +100,15 @@ struct DevParams {
     // ---- sample-parallel pipeline ----
     float4 *rayA, *rayB;             // [tile*32 + lane]: (pos0.xyz, n) and (dir.xyz, state)
     uint2  *tileRec;                 // [tile]: (first src row, max samples of the tile)
+    float4 *rayCk;                   // march checkpoints: [(tileCk[tile] + j - 1) * 32 + lane] = the ray's position after 16 j steps (j >= 1)
+    unsigned int *tileCk;            // [tile]: first checkpoint row of the tile
+    unsigned int *ckAlloc;           // checkpoint rows allocated by the ray set-up
     float4 *src;                     // [(row + k) * 32 + lane]: shaded ray samples, w < 0 = gated off
     uint2  *items, *itemsNext;       // work items (tile, k) of the current / next depth window
     unsigned int *itemCount, *itemCountNext, *itemHead, *slotAlloc, *nMaxGlobal;
     unsigned int *tileLive;          // [tile]: longest ray of the tile that is still alive (0: every ray of the tile has finished)
     int win0, win1, win2;            // current window [win0, win1), next window [win1, win2) (the one whose items are being built)
+    int itemChunk;                   // > 0: items are handed out CTA-affine in chunks of this many consecutive items (lic_sample_kernel)
     int emitItems;                   // composite_kernel emits the next window's items itself, tile-major (VV_OPT_DEPTH_MAJOR = 0)
     // depth-major item order: buckets = (band of block rows) x (chunk of 8 depths)
     unsigned int *bucketCount, *bucketBase, *bucketFill;
@@ -475,7 +483,10 @@ __device__ __forceinline__ pk2_t bf2pk(unsigned int w)
 }
 
 // pre-differenced bf16 layout, cell index idx: x-lerp = t0 + fx * d with d = t1 - t0 stored (exact: |d| <= 255 has 8 significant
-// bits); the same fp32 values and operations as the fp16 x-pair path (FHADD forms t1 - t0 exactly as well)
+// bits); the same fp32 values and operations as the fp16 x-pair path (FHADD forms t1 - t0 exactly as well).
+// (An xy-quad form of this layout -- rows y and y+1 in one 32-byte sector, 2 x LDG.256 per tap, like the vector field's -- was
+// measured and dropped: cfg3 11.71 -> 12.02 ms, the doubled noise footprint costs more L1 hits than the two loads save;
+// profiles/r02/ab16_quad_noise_reload_then_eval.log.)
 __device__ __forceinline__ Rgba2 blend_noise_bf(const DevParams &P, int idx, float fx, float fy, float fz)
 {
     const uint4 *N = P.noise_bf + idx;

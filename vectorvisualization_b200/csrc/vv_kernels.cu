@@ -12,12 +12,17 @@
 #include "vv_device.cuh"
 #include "vv_kernels.h"
 
-#ifndef LIC_CTA_THREADS
-#define LIC_CTA_THREADS 256   // threads per CTA of lic_sample_kernel (warps pull work items independently; the CTA only shares the tables)
-#endif
-#ifndef LIC_MIN_CTAS
-#define LIC_MIN_CTAS 4   // resident CTAs per SM the sample kernel is compiled for (64 registers per thread; measured 2.5 %
-                         // faster than 3 CTAs / 80 registers on cfg2 / cfg3 despite 24-64 B of spills)
+// CTA shape of lic_sample_kernel (warps pull work items independently; the CTA only shares the tables).  The register file
+// allows 64 registers per thread at 4 x 256 threads per SM and 72 at 7 x 128 (7 instead of 8 warps per scheduler).  The walk
+// loop of the gradient build wants ~130: at 64 it spills its four accumulators in every iteration, at 72 it does not --
+// measured (profiles/r02/ab14_checkpoints_cta_shapes.log) 2.8 % faster on cfg3; the scalar builds (cfg2, cfg4) are 1.5 % / 3 %
+// SLOWER at 7 x 128 and keep 4 x 256 (3 x 256 / 80 registers: cfg2 +5 %, cfg4 +8 %; 5 x 128 / 96 and 4 x 128 / 106
+// registers: slower everywhere).  LIC_CTA_THREADS / LIC_MIN_CTAS force one shape for every build (A/B variants).
+#if defined(LIC_CTA_THREADS) && defined(LIC_MIN_CTAS)
+template <int ILLUM> struct LicShape { static constexpr int kThreads = LIC_CTA_THREADS, kMinCtas = LIC_MIN_CTAS; };
+#else
+template <int ILLUM> struct LicShape { static constexpr int kThreads = 256, kMinCtas = 4; };
+template <> struct LicShape<1 /* ILLUM_GRADIENT */> { static constexpr int kThreads = 128, kMinCtas = 7; };
 #endif
 
 namespace vvb200 {
@@ -186,6 +191,8 @@ __device__ __forceinline__ void heun_step(const DevParams &P, Walker &w, float s
         w.qxy = fma2(bc2(0.5f), add2(d1, d2), w.qxy);                      // newPos += 0.5 (licdir + licdir2)
         w.qz = fmaf(0.5f, __fadd_rn(d1z, d2z), w.qz);
         const CellCoord c = field_cell_coord<GUARD>(P, lo2(w.qxy), hi2(w.qxy), w.qz);
+        // (measured alternative: the reload as a conditional region in front of ONE copy of the evaluation -- cfg3 +2 %, cfg2 +2.5 %,
+        // cfg4 -1.7 %; profiles/r02/ab16_quad_noise_reload_then_eval.log)
         FieldVal v;
         if (c.idx == c2.idx) v = eval_field_cell(cell, c.fx, c.fy, c.fz);
         else v = eval_field_cell(load_field_cell<LAYOUT>(P, c.idx), c.fx, c.fy, c.fz);   // the corrector left the predictor's cell (rare)
@@ -274,18 +281,12 @@ __device__ __forceinline__ Rgba2 noise_tap_rgba(const DevParams &P, const Walker
 }
 
 // computeLIC, USE_NOISE_GRADIENTS build: vec4 accumulation of raw RGBA noise texels (Q8)
-template <int LAYOUT, bool SOF, bool STRAIGHT = true, int NL = -1, int XF = 0>
-__device__ __forceinline__ float4 compute_lic_grad(const DevParams &P, const float *s_kw, f3 pos, float4 centre)
+// the two walks of compute_lic_grad; FAST (XF_NSHARE only): every tap takes the field's cell -- a separate instantiation of the
+// loops, so that the hot one carries neither the REPEAT arithmetic nor the branch around it
+template <int LAYOUT, bool SOF, bool STRAIGHT, int NL, int XF, bool FAST>
+__device__ __forceinline__ void lic_grad_walks(const DevParams &P, const float *s_kw, f3 pos, float4 centre,
+                                               pk2_t &accBrg, pk2_t &accBba, pk2_t &accFrg, pk2_t &accFba)
 {
-    bool fast = false;
-    if constexpr ((XF & XF_NSHARE) != 0) {
-        // warp-uniform: every active lane's walk stays inside [0,1)^3 (it starts at least (S + 2) h away from the faces)
-        const float lo = fminf(fminf(pos.x, pos.y), pos.z), hi = fmaxf(fmaxf(pos.x, pos.y), pos.z);
-        fast = __all_sync(__activemask(), lo >= P.walkReach && hi < 1.0f - P.walkReach) != 0;
-    }
-    const Rgba2 c = fetch_noise_rgba_pk<NL>(P, pos.x, pos.y, pos.z);
-    const pk2_t w0 = bc2(s_kw[0]);
-    pk2_t accBrg = pk2(0.f, 0.f), accBba = accBrg, accFrg = accBrg, accFba = accBrg;
     Walker wb = make_walker(pos, centre), wf = wb;
     const float *kwB = s_kw + 1, *kwF = s_kw + 1 + P.nBwd;
     const int nB = P.nBwdEff, nF = P.nFwdEff;
@@ -295,8 +296,8 @@ __device__ __forceinline__ float4 compute_lic_grad(const DevParams &P, const flo
         for (; k < nMin; ++k) {
             heun_step<LAYOUT, SOF, XF>(P, wb, -P.h);
             heun_step<LAYOUT, SOF, XF>(P, wf, P.h);
-            const Rgba2 tb = noise_tap_rgba<NL, XF>(P, wb, fast);
-            const Rgba2 tf = noise_tap_rgba<NL, XF>(P, wf, fast);
+            const Rgba2 tb = noise_tap_rgba<NL, XF>(P, wb, FAST);
+            const Rgba2 tf = noise_tap_rgba<NL, XF>(P, wf, FAST);
             const pk2_t wB = bc2(kwB[k]), wF = bc2(kwF[k]);
             accBrg = fma2(tb.rg, wB, accBrg);
             accBba = fma2(tb.ba, wB, accBba);
@@ -305,14 +306,14 @@ __device__ __forceinline__ float4 compute_lic_grad(const DevParams &P, const flo
         }
         for (; k < nB; ++k) {
             heun_step<LAYOUT, SOF, XF>(P, wb, -P.h);
-            const Rgba2 t = noise_tap_rgba<NL, XF>(P, wb, fast);
+            const Rgba2 t = noise_tap_rgba<NL, XF>(P, wb, FAST);
             const pk2_t w = bc2(kwB[k]);
             accBrg = fma2(t.rg, w, accBrg);
             accBba = fma2(t.ba, w, accBba);
         }
         for (k = nMin; k < nF; ++k) {
             heun_step<LAYOUT, SOF, XF>(P, wf, P.h);
-            const Rgba2 t = noise_tap_rgba<NL, XF>(P, wf, fast);
+            const Rgba2 t = noise_tap_rgba<NL, XF>(P, wf, FAST);
             const pk2_t w = bc2(kwF[k]);
             accFrg = fma2(t.rg, w, accFrg);
             accFba = fma2(t.ba, w, accFba);
@@ -322,19 +323,36 @@ __device__ __forceinline__ float4 compute_lic_grad(const DevParams &P, const flo
         for (int k = 0; k < n; ++k) {
             if (k < nB) {
                 heun_step<LAYOUT, SOF, XF>(P, wb, -P.h);
-                const Rgba2 t = noise_tap_rgba<NL, XF>(P, wb, fast);
+                const Rgba2 t = noise_tap_rgba<NL, XF>(P, wb, FAST);
                 const pk2_t w = bc2(kwB[k]);
                 accBrg = fma2(t.rg, w, accBrg);
                 accBba = fma2(t.ba, w, accBba);
             }
             if (k < nF) {
                 heun_step<LAYOUT, SOF, XF>(P, wf, P.h);
-                const Rgba2 t = noise_tap_rgba<NL, XF>(P, wf, fast);
+                const Rgba2 t = noise_tap_rgba<NL, XF>(P, wf, FAST);
                 const pk2_t w = bc2(kwF[k]);
                 accFrg = fma2(t.rg, w, accFrg);
                 accFba = fma2(t.ba, w, accFba);
             }
         }
+    }
+}
+
+template <int LAYOUT, bool SOF, bool STRAIGHT = true, int NL = -1, int XF = 0>
+__device__ __forceinline__ float4 compute_lic_grad(const DevParams &P, const float *s_kw, f3 pos, float4 centre)
+{
+    const Rgba2 c = fetch_noise_rgba_pk<NL>(P, pos.x, pos.y, pos.z);
+    const pk2_t w0 = bc2(s_kw[0]);
+    pk2_t accBrg = pk2(0.f, 0.f), accBba = accBrg, accFrg = accBrg, accFba = accBrg;
+    if constexpr ((XF & XF_NSHARE) != 0) {
+        // warp-uniform: every active lane's walk stays inside [0,1)^3 (it starts at least (S + 2) h away from the faces)
+        const float lo = fminf(fminf(pos.x, pos.y), pos.z), hi = fmaxf(fmaxf(pos.x, pos.y), pos.z);
+        const bool fast = __all_sync(__activemask(), lo >= P.walkReach && hi < 1.0f - P.walkReach) != 0;
+        if (fast) lic_grad_walks<LAYOUT, SOF, STRAIGHT, NL, XF, true>(P, s_kw, pos, centre, accBrg, accBba, accFrg, accFba);
+        else lic_grad_walks<LAYOUT, SOF, STRAIGHT, NL, XF, false>(P, s_kw, pos, centre, accBrg, accBba, accFrg, accFba);
+    } else {
+        lic_grad_walks<LAYOUT, SOF, STRAIGHT, NL, XF, false>(P, s_kw, pos, centre, accBrg, accBba, accFrg, accFba);
     }
     const pk2_t rg = add2(fma2(c.rg, w0, accBrg), accFrg);
     const pk2_t ba = add2(fma2(c.ba, w0, accBba), accFba);
@@ -651,6 +669,8 @@ __global__ void __launch_bounds__(256) ray_setup_kernel(const __grid_constant__ 
         P.rayA[ray] = make_float4(pos.x, pos.y, pos.z, __int_as_float(n));
         P.rayB[ray] = make_float4(dir.x, dir.y, dir.z, __int_as_float(n > 0 ? 0 : -1));   // state: consumed samples, < 0 = finished
         if (lane == 0) {
+            // rows of march checkpoints (ray_checkpoint_kernel): samples kCkStride, 2 kCkStride, ... < nmax
+            P.tileCk[lt] = nmax > kCkStride ? atomicAdd(P.ckAlloc, (unsigned int)((nmax - 1) / kCkStride)) : 0u;
             P.tileRec[lt] = make_uint2(base, (unsigned int)nmax);
             P.tileLive[lt] = (unsigned int)nmax;
             if (nmax > 0) atomicMax(P.nMaxGlobal, (unsigned int)nmax);
@@ -659,6 +679,34 @@ __global__ void __launch_bounds__(256) ray_setup_kernel(const __grid_constant__ 
         if (P.samplesPerPixel) P.samplesPerPixel[o] = 0;
         // the work items of the first window are built afterwards (item_bucket_kernel, or composite_kernel run on the empty
         // window [0,0)), once the host has sized the src / item buffers from slotAlloc
+    }
+}
+
+// Position checkpoints of the march.  The shader accumulates pos += dir * stepSize with one rounding per step, so sample k's
+// position is only reachable by k dependent additions from the entry point; a warp that shades sample k of its tile would spend
+// k x 3 FADD on it (cfg3: ~60 on average, cfg4 ~120).  After the set-up has sized the buffers this kernel repeats the march once
+// per ray and keeps every kCkStride-th position, so the sample kernel adds at most kCkStride - 1 steps.  Same additions in the
+// same order: same bits.  (1 byte per ray sample; runs only when the view changed.)
+__global__ void __launch_bounds__(256) ray_checkpoint_kernel(const __grid_constant__ DevParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const int nTiles = P.nLocalBlocks * 8;
+    for (int lt = blockIdx.x * 8 + (threadIdx.x >> 5); lt < nTiles; lt += gridDim.x * 8) {
+        const int nmax = (int)P.tileRec[lt].y;
+        if (nmax <= kCkStride) continue;
+        const int ray = lt * 32 + lane;
+        const float4 A = P.rayA[ray], B = P.rayB[ray];
+        const f3 dstep = mk3(__fmul_rn(B.x, P.stepSize), __fmul_rn(B.y, P.stepSize), __fmul_rn(B.z, P.stepSize));
+        f3 q = mk3(A.x, A.y, A.z);
+        float4 *ck = P.rayCk + (size_t)P.tileCk[lt] * 32 + lane;
+        const int rows = (nmax - 1) / kCkStride;
+        for (int j = 0; j < rows; ++j) {
+#pragma unroll
+            for (int i = 0; i < kCkStride; ++i) {
+                q.x = __fadd_rn(q.x, dstep.x); q.y = __fadd_rn(q.y, dstep.y); q.z = __fadd_rn(q.z, dstep.z);
+            }
+            ck[(size_t)j * 32] = make_float4(q.x, q.y, q.z, 0.0f);     // rays shorter than the tile's longest keep marching: never read
+        }
     }
 }
 
@@ -793,7 +841,7 @@ __global__ void __launch_bounds__(256) slice_setup_kernel(const __grid_constant_
 // NL: RGBA-noise layout of the gradient build as a compile-time parameter (the walk loop holds one sampler, not both)
 // XF: coordinate fast paths (XF_GUARD | XF_NSHARE | XF_SSHARE) the host found applicable to this frame
 template <int LAYOUT, int ILLUM, bool NGATE, bool SOF, int NL, int XF>
-__global__ void __launch_bounds__(LIC_CTA_THREADS, LIC_MIN_CTAS) lic_sample_kernel(const __grid_constant__ DevParams P)
+__global__ void __launch_bounds__(LicShape<ILLUM>::kThreads, LicShape<ILLUM>::kMinCtas) lic_sample_kernel(const __grid_constant__ DevParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SharedTables &S = *reinterpret_cast<SharedTables *>(smem_raw);
@@ -801,15 +849,38 @@ __global__ void __launch_bounds__(LIC_CTA_THREADS, LIC_MIN_CTAS) lic_sample_kern
     if (nItems == 0) return;
     load_tables(P, S);
     const int lane = threadIdx.x & 31;
-    // Items are ordered tile-major, depth-minor; every warp pops single items.  (Measured alternative: a CTA pops a chunk
-    // of 8..64 consecutive items and its warps walk it together behind a barrier -- L1 hit rate unchanged at 89 %, issue
-    // utilisation 72 % -> 64 % from the barrier; profiles/README.md.)
+    // Every warp pops single items and works on its own (no barrier in the loop).  WHICH item a pop returns decides what the
+    // warps of one SM share in L1.  The list is bucket-major (band, chunk of 8 depths) and inside a bucket 8 consecutive items are
+    // the 8 depths of one ray tile: ray samples whose streamlines start 1 - 2 voxels apart and run side by side.
+    //   itemChunk == 0: one global queue -- consecutive items go to whichever warps pop next, on any SM.
+    //   itemChunk == C: CTA-affine hand-out.  The list is cut into chunks of C consecutive items, dealt round-robin to the CTAs
+    //     (CTA b owns chunks b, b + G, b + 2G, ...); the warps of a CTA pop from the CTA's own cursor in shared memory, so they
+    //     shade neighbouring samples at the same time.  All CTAs advance through the list at the same pace, which keeps the
+    //     depth-major sweep (L2).  The last ~10 % of the list go through the global queue to even out the finish.
+    const unsigned int C = (unsigned int)P.itemChunk, G = gridDim.x;
+    unsigned int nAffine = 0;
+    if (C > 0) {
+        const unsigned long long round = (unsigned long long)C * G;
+        nAffine = (unsigned int)(((unsigned long long)nItems * 9 / 10) / round * round);
+        if (threadIdx.x == 0) S.block = 0;
+        __syncthreads();
+    }
+    bool affine = nAffine > 0;
     for (;;) {
       {
         unsigned int i = 0;
-        if (lane == 0) i = atomicAdd(P.itemHead, 1u);
-        i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= nItems) break;
+        if (affine) {
+            if (lane == 0) i = (unsigned int)atomicAdd(&S.block, 1);
+            i = __shfl_sync(0xffffffffu, i, 0);
+            const unsigned long long g = ((unsigned long long)(i / C) * G + blockIdx.x) * C + i % C;
+            if (g < nAffine) i = (unsigned int)g;
+            else affine = false;                         // this CTA's share is done: on to the common tail
+        }
+        if (!affine) {
+            if (lane == 0) i = atomicAdd(P.itemHead, 1u);
+            i = __shfl_sync(0xffffffffu, i, 0) + nAffine;
+            if (i >= nItems) break;
+        }
         const uint2 it = P.items[i];
         const int ray = (int)it.x * 32 + lane;
         const int k = (int)it.y;
@@ -836,10 +907,17 @@ __global__ void __launch_bounds__(LIC_CTA_THREADS, LIC_MIN_CTAS) lic_sample_kern
         } else {
             dir = mk3(B.x, B.y, B.z);
             const f3 dstep = mk3(__fmul_rn(dir.x, P.stepSize), __fmul_rn(dir.y, P.stepSize), __fmul_rn(dir.z, P.stepSize));
-            pos = mk3(A.x, A.y, A.z);
-            for (int j = 0; j < k; ++j) {                  // pos += dir * stepSize, k times, as the shader accumulates it
-                pos.x = __fadd_rn(pos.x, dstep.x); pos.y = __fadd_rn(pos.y, dstep.y); pos.z = __fadd_rn(pos.z, dstep.z);
+            // pos += dir * stepSize, k times, as the shader accumulates it: from the last checkpoint of the march at or before k
+            f3 q = mk3(A.x, A.y, A.z);
+            const int ckRow = k / kCkStride;               // warp-uniform
+            if (ckRow > 0) {
+                const float4 c = P.rayCk[((size_t)P.tileCk[it.x] + ckRow - 1) * 32 + lane];
+                q = mk3(c.x, c.y, c.z);
             }
+            for (int j = ckRow * kCkStride; j < k; ++j) {
+                q.x = __fadd_rn(q.x, dstep.x); q.y = __fadd_rn(q.y, dstep.y); q.z = __fadd_rn(q.z, dstep.z);
+            }
+            pos = q;
         }
         if (!have) src = make_float4(0.f, 0.f, 0.f, -2.0f);                                                               // no fragment
         else if (!shade_sample<LAYOUT, ILLUM, NGATE, SOF, NL, XF>(P, S, pos, dir, src)) src = make_float4(0.f, 0.f, 0.f, -1.0f);   // gated
@@ -1117,17 +1195,25 @@ __global__ void debug_walk_kernel(const __grid_constant__ DevParams P, float px,
     }
 }
 
-cudaError_t launch_debug_walk(const DevParams &P, bool grad, int xf, const float pos[3], int dirSign, int nSteps, float *out, cudaStream_t st)
+template <int LAYOUT>
+static cudaError_t launch_debug_walk_layout(const DevParams &P, bool grad, int xf, const float pos[3], int dirSign, int nSteps, float *out, cudaStream_t st)
 {
     if (grad) {
-        if (xf == 3) debug_walk_kernel<LAYOUT_PAIR, true, 3><<<1, 32, 0, st>>>(P, pos[0], pos[1], pos[2], dirSign, nSteps, out);
-        else if (xf == 1) debug_walk_kernel<LAYOUT_PAIR, true, 1><<<1, 32, 0, st>>>(P, pos[0], pos[1], pos[2], dirSign, nSteps, out);
-        else debug_walk_kernel<LAYOUT_PAIR, true, 0><<<1, 32, 0, st>>>(P, pos[0], pos[1], pos[2], dirSign, nSteps, out);
+        if (xf == 3) debug_walk_kernel<LAYOUT, true, 3><<<1, 32, 0, st>>>(P, pos[0], pos[1], pos[2], dirSign, nSteps, out);
+        else if (xf == 1) debug_walk_kernel<LAYOUT, true, 1><<<1, 32, 0, st>>>(P, pos[0], pos[1], pos[2], dirSign, nSteps, out);
+        else debug_walk_kernel<LAYOUT, true, 0><<<1, 32, 0, st>>>(P, pos[0], pos[1], pos[2], dirSign, nSteps, out);
     } else {
-        if (xf == 1) debug_walk_kernel<LAYOUT_PAIR, false, 1><<<1, 32, 0, st>>>(P, pos[0], pos[1], pos[2], dirSign, nSteps, out);
-        else debug_walk_kernel<LAYOUT_PAIR, false, 0><<<1, 32, 0, st>>>(P, pos[0], pos[1], pos[2], dirSign, nSteps, out);
+        if (xf == 1) debug_walk_kernel<LAYOUT, false, 1><<<1, 32, 0, st>>>(P, pos[0], pos[1], pos[2], dirSign, nSteps, out);
+        else debug_walk_kernel<LAYOUT, false, 0><<<1, 32, 0, st>>>(P, pos[0], pos[1], pos[2], dirSign, nSteps, out);
     }
     return cudaGetLastError();
+}
+
+cudaError_t launch_debug_walk(const DevParams &P, int layout, bool grad, int xf, const float pos[3], int dirSign, int nSteps, float *out, cudaStream_t st)
+{
+    if (layout == LAYOUT_QUAD) return launch_debug_walk_layout<LAYOUT_QUAD>(P, grad, xf, pos, dirSign, nSteps, out, st);
+    if (layout == LAYOUT_PAIR) return launch_debug_walk_layout<LAYOUT_PAIR>(P, grad, xf, pos, dirSign, nSteps, out, st);
+    return cudaErrorNotSupported;
 }
 
 // K5 ------------------------------------------------------------------------------------------------
@@ -1202,6 +1288,12 @@ cudaError_t launch_ray_setup(const DevParams &P, int grid, cudaStream_t st)
     return cudaGetLastError();
 }
 
+cudaError_t launch_ray_checkpoints(const DevParams &P, int grid, cudaStream_t st)
+{
+    ray_checkpoint_kernel<<<grid, 256, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_ray_reset(const DevParams &P, unsigned int *counters, int grid, cudaStream_t st)
 {
     ray_reset_kernel<<<grid, 256, 0, st>>>(P, counters);
@@ -1239,7 +1331,7 @@ static cudaError_t prefer_l1(K kernel, size_t smem, int *occ_out = nullptr, int 
     return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 
-template <class K>
+template <int THREADS, class K>
 static cudaError_t launch_sample_kernel(K kernel, const DevParams &P, int grid, size_t smem, cudaStream_t st)
 {
     int dev = 0, sms = 148;
@@ -1247,9 +1339,9 @@ static cudaError_t launch_sample_kernel(K kernel, const DevParams &P, int grid, 
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = prefer_l1(kernel, smem, &occ, LIC_CTA_THREADS);
+    e = prefer_l1(kernel, smem, &occ, THREADS);
     if (e != cudaSuccess) return e;
-    kernel<<<grid > 0 ? grid : sms * occ, LIC_CTA_THREADS, smem, st>>>(P);
+    kernel<<<grid > 0 ? grid : sms * occ, THREADS, smem, st>>>(P);
     return cudaGetLastError();
 }
 
@@ -1260,12 +1352,12 @@ static cudaError_t launch_sample_xf(const DevParams &P, int grid, size_t smem, c
     if constexpr (LAYOUT != LAYOUT_F4 && !SOF && VV_CELL_REUSE && (NL == 2 || ILLUM != ILLUM_GRADIENT)) {
         if (P.fGuard > 1 && P.guardOk) {
             if constexpr (ILLUM == ILLUM_GRADIENT) {
-                if (P.noiseShared) return launch_sample_kernel(lic_sample_kernel<LAYOUT, ILLUM, NGATE, SOF, NL, XF_GUARD | XF_NSHARE>, P, grid, smem, st);
+                if (P.noiseShared) return launch_sample_kernel<LicShape<ILLUM>::kThreads>(lic_sample_kernel<LAYOUT, ILLUM, NGATE, SOF, NL, XF_GUARD | XF_NSHARE>, P, grid, smem, st);
             }
-            return launch_sample_kernel(lic_sample_kernel<LAYOUT, ILLUM, NGATE, SOF, NL, XF_GUARD>, P, grid, smem, st);
+            return launch_sample_kernel<LicShape<ILLUM>::kThreads>(lic_sample_kernel<LAYOUT, ILLUM, NGATE, SOF, NL, XF_GUARD>, P, grid, smem, st);
         }
     }
-    return launch_sample_kernel(lic_sample_kernel<LAYOUT, ILLUM, NGATE, SOF, NL, 0>, P, grid, smem, st);
+    return launch_sample_kernel<LicShape<ILLUM>::kThreads>(lic_sample_kernel<LAYOUT, ILLUM, NGATE, SOF, NL, 0>, P, grid, smem, st);
 }
 
 template <int LAYOUT, int ILLUM, bool NGATE>
@@ -1315,7 +1407,7 @@ cudaError_t launch_lic_raycast(const DevParams &P, int layout, int illum, bool n
 {
     const size_t smem = table_bytes(P);
     if (layout == LAYOUT_PAIR) return launch_raycast_layout<LAYOUT_PAIR>(P, illum, noise_gate, speed_of_flow, grid, smem, st);
-    if (layout == LAYOUT_QUAD) return cudaErrorNotSupported;     // the one-thread-per-ray cross-check kernel is built for the pair and float4 layouts
+    if (layout == LAYOUT_QUAD) return launch_raycast_layout<LAYOUT_QUAD>(P, illum, noise_gate, speed_of_flow, grid, smem, st);
     return launch_raycast_layout<LAYOUT_F4>(P, illum, noise_gate, speed_of_flow, grid, smem, st);
 }
 

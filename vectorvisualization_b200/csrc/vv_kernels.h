@@ -11,13 +11,15 @@ size_t shared_table_bytes();
 cudaError_t launch_lic_raycast(const DevParams &P, int layout, int illum, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st);
 // sample-parallel pipeline (ray_setup -> [lic_sample -> composite] per depth window)
 cudaError_t launch_ray_setup(const DevParams &P, int grid, cudaStream_t st);
+// march checkpoints (every kCkStride-th position of every ray), once the set-up's allocation has sized DevParams::rayCk
+cudaError_t launch_ray_checkpoints(const DevParams &P, int grid, cudaStream_t st);
 // same view as the previous frame: put back what a frame consumes (ray state, tile accumulators, per-frame counters)
 cudaError_t launch_ray_reset(const DevParams &P, unsigned int *counters, int grid, cudaStream_t st);
 cudaError_t launch_lic_sample(const DevParams &P, int layout, int illum, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st);
 cudaError_t launch_composite(const DevParams &P, int grid, cudaStream_t st);
 cudaError_t launch_item_buckets(const DevParams &P, int nBuckets, int grid, cudaStream_t st);
 // diagnostic (vv_debug_walk): one direction of the LIC walk from one position, 8 floats per step
-cudaError_t launch_debug_walk(const DevParams &P, bool grad, int xf, const float pos[3], int dirSign, int nSteps, float *out, cudaStream_t st);
+cudaError_t launch_debug_walk(const DevParams &P, int layout, bool grad, int xf, const float pos[3], int dirSign, int nSteps, float *out, cudaStream_t st);
 cudaError_t launch_volume_raycast(const DevParams &P, int layout, int grid, cudaStream_t st);
 cudaError_t launch_lic_volume(const DevParams &P, int layout, bool grad, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st);
 cudaError_t launch_unblock(const float4 *tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY, int skew, int width, int height,

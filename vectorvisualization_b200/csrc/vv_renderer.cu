@@ -83,7 +83,8 @@ struct VVRenderer {
     float walk_reach = 0.0f;                            // (S + 2) h: how far a walk can get from its ray sample, texture coordinates
     int guard_wanted = 1;                               // guard the current LIC parameters need for the unclamped walk (XF_GUARD)
     DevBuf<float4> field_f4;
-    int field_layout = LAYOUT_PAIR;
+    int field_layout = LAYOUT_PAIR;        // layout of the packed field (resolved from field_layout_req by resolve_field_layout)
+    int field_layout_req = 3;              // VV_OPT_FIELD_LAYOUT: 0 float4, 1 x-pair, 2 xy-quad, 3 (default) = by size / technique
     bool field_dirty = false;
 
     // ---- scalar volume ----
@@ -153,12 +154,14 @@ struct VVRenderer {
     DevBuf<float4> tiles, frame;
     DevBuf<uchar4> frame8, display8;
     DevBuf<unsigned long long> counters;   // as unsigned int[16]: [0,1] ray samples (u64), [2] block queue, [3] src rows,
-                                           // [4],[5] item counts (ping-pong), [6] item queue head, [7] max samples per ray
+                                           // [4],[5] item counts (ping-pong), [6] item queue head, [7] max samples per ray,
+                                           // [8] first window's item count, [9] march-checkpoint rows
     unsigned int *host_counters = nullptr; // pinned
     // sample-parallel pipeline state
     DevBuf<float4> rayA, rayB, src;
     DevBuf<uint2> tileRec, items[3];       // items[0]: first depth window (kept while the view is unchanged), [1], [2]: later windows
-    DevBuf<unsigned int> tileLive;
+    DevBuf<unsigned int> tileLive, tileCk;
+    DevBuf<float4> rayCk;                  // march checkpoints (ray_checkpoint_kernel), sized from counter [9]
     // the view the ray records / src rows / first-window items on the device were computed for (GeomKey), and their sizes
     GeomKey geom_key = {};
     bool geom_valid = false;
@@ -172,6 +175,7 @@ struct VVRenderer {
     int first_window = 8, window_growth = 200;    // depth windows of early-termination frames: first length, growth in percent
                                                   // (measured, profiles/r02/ab10_window_schedules.log: cfg1 is flat between 8 and 32,
                                                   // a surface-like frame such as cfg3o pays for every speculative sample: 1.17 ms at 8, 2.06 at 16)
+    int item_chunk = 0;                    // VV_OPT_ITEM_AFFINITY
     int depth_major = 1;                   // 1: bucket work items by (band, depth chunk) for L2 locality; 0: tile-major
     int band_rows = 4;                     // block rows per band (4 x 16 = 64 pixel rows)
     DevBuf<unsigned int> buckets;
@@ -382,11 +386,32 @@ static int pack_field(VVRenderer *r)
     return VV_OK;
 }
 
+// VV_OPT_FIELD_LAYOUT = 3: the xy-quad layout (32 B/voxel, one 256-bit load per cell face) wherever it fits comfortably: measured
+// against the x-pair layout (16 B/voxel), frames and volumes bit-identical -- lic_sample_kernel 2.5 % faster on cfg3 and cfg2, 2 % on
+// cfg4 (512^3) (profiles/r02/ab13_quad_layout.log, ab15_split_loops_per_build_shape.log); lic_volume_kernel equal at 512^3 and 9 %
+// faster at 1024^3, where the kernel is DRAM-bound and a cell face is one fully used 32-byte sector instead of two half-used ones
+// (profiles/r02/licvol16_layouts.log, licvol17_layouts_1024.log).  Above 48 GiB of packed field (~1150^3) the x-pair layout.
+static void resolve_field_layout(VVRenderer *r)
+{
+    int want = r->field_layout_req;
+    if (want == 3) {
+        const size_t n = (size_t)r->size[0] * r->size[1] * r->size[2];
+        want = (n * 32 <= ((size_t)48 << 30)) ? LAYOUT_QUAD : LAYOUT_PAIR;
+    }
+    if (want != r->field_layout) {
+        r->field_layout = want;
+        r->field_pair.release();
+        r->field_f4.release();
+        r->field_dirty = true;
+    }
+}
+
 // raycast_program: the LIC ray-cast program, the only one where scaleVolInv can be an active uniform (Q1)
 static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycast_program = true)
 {
     if (!r->have_field) return fail(VV_ERR_STATE, "no vector field set (vv_set_vector_field / vv_load_dat)");
     const Uniforms u = derive_uniforms(r);
+    resolve_field_layout(r);
     // Guard band of the unclamped walk (XF_GUARD): a Heun step moves a position by at most h per axis in texture coordinates
     // (|2 v - 1| <= 1 per component for texels in [0,1]) and its predictor looks one more step ahead, so a walk of S steps stays
     // within (S + 1) h of its ray sample.  Ray samples lie in [0, max(texMax, extent * scaleVol)] per axis -- inside [0,1] for a
@@ -447,12 +472,12 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycas
     P.noise_pair = (r->noise_layout == 1 && r->noise_pair.p) ? r->noise_pair.p + (P.npPlane + P.npRow + 1) : nullptr;
     P.noise_bf = nullptr;
     P.noiseShared = 0;
-    if (r->noise_layout == 2 && r->noise_bf.p && r->noise_has_grad) {
+    if (r->noise_layout == 2 && r->noise_has_grad && grad) {
         // The hot RGBA-noise layout takes the vector field's guard geometry when both volumes have the same dimensions: one cell
-        // index then addresses both arrays (XF_NSHARE).  Rebuilt from the RGBA texels whenever the field's geometry moved.
+        // index then addresses both arrays (XF_NSHARE).  Built from the RGBA texels on first use and whenever that geometry moved.
         const bool share = P.guardOk && r->field_layout != LAYOUT_F4 && P.noiseSameDims && grad;
         const int g = share ? r->field_guard : 1, gx = share ? r->field_gx : 1, row = share ? r->field_row : r->ndim[0] + 1;
-        if (g != r->nbf_guard || gx != r->nbf_gx || row != r->nbf_row) {
+        if (g != r->nbf_guard || gx != r->nbf_gx || row != r->nbf_row || !r->noise_bf.p) {
             CU(r->noise_bf.ensure((size_t)row * (r->ndim[1] + 2 * g) * (r->ndim[2] + 2 * g)));
             CU(launch_build_noise_pair(r->noise_rgba.p, r->ndim[0], r->ndim[1], r->ndim[2], g, gx, row, r->noise_bf.p, 1, r->stream));
             r->nbf_guard = g; r->nbf_gx = gx; r->nbf_row = row;
@@ -678,9 +703,7 @@ static int upload_noise(VVRenderer *r, const uint8_t *data, const int dims[3], i
         CU(launch_build_quad(r->noise_rgba.p, dims[0], dims[1], dims[2], r->noise_quad.p, r->stream));
         CU(r->noise_pair.ensure((size_t)(dims[0] + 1) * (dims[1] + 2) * (dims[2] + 2)));
         CU(launch_build_noise_pair(r->noise_rgba.p, dims[0], dims[1], dims[2], 1, 1, dims[0] + 1, r->noise_pair.p, 0, r->stream));
-        r->nbf_guard = 1; r->nbf_gx = 1; r->nbf_row = dims[0] + 1;
-        CU(r->noise_bf.ensure((size_t)(dims[0] + 1) * (dims[1] + 2) * (dims[2] + 2)));
-        CU(launch_build_noise_pair(r->noise_rgba.p, dims[0], dims[1], dims[2], 1, 1, dims[0] + 1, r->noise_bf.p, 1, r->stream));
+        r->nbf_row = 0;                   // the hot bf16 layout is built by fill_params in the geometry the frame's field layout asks for
         r->noise_has_grad = true;
     }
     CU(cudaStreamSynchronize(r->stream));
@@ -728,9 +751,11 @@ static int render_sample_parallel(VVRenderer *r, DevParams &P)
     CU(r->rayB.ensure((size_t)nTiles * 32));
     CU(r->tileRec.ensure((size_t)nTiles));
     CU(r->tileLive.ensure((size_t)nTiles));
+    CU(r->tileCk.ensure((size_t)nTiles));
     unsigned int *cnt = reinterpret_cast<unsigned int *>(r->counters.p);
-    P.rayA = r->rayA.p; P.rayB = r->rayB.p; P.tileRec = r->tileRec.p; P.tileLive = r->tileLive.p;
-    P.slotAlloc = cnt + 3; P.nMaxGlobal = cnt + 7; P.itemHead = cnt + 6;
+    P.rayA = r->rayA.p; P.rayB = r->rayB.p; P.tileRec = r->tileRec.p; P.tileLive = r->tileLive.p; P.tileCk = r->tileCk.p;
+    P.slotAlloc = cnt + 3; P.nMaxGlobal = cnt + 7; P.itemHead = cnt + 6; P.ckAlloc = cnt + 9;
+    P.rayCk = r->rayCk.p;
     const int setup_grid = std::max(1, std::min((nTiles + 7) / 8, r->num_sms * 8));
     // depth windows: whole ray at once when no sample can trigger the early termination (and without the FBO nothing stops a slice
     // from being blended), else 8, 16, 32, ... samples (VV_OPT_FIRST_WINDOW / VV_OPT_WINDOW_GROWTH): a window bounds the work done
@@ -751,6 +776,13 @@ static int render_sample_parallel(VVRenderer *r, DevParams &P)
         CU(cudaStreamSynchronize(r->stream));
         r->geom_rows = r->host_counters[3];
         r->geom_nmax = (int)r->host_counters[7];
+        if (!P.slicing && r->host_counters[9] > 0) {
+            // every kCkStride-th position of every ray's march (kept with the ray records while the view stays the same)
+            CU(r->rayCk.ensure((size_t)r->host_counters[9] * 32));
+            P.rayCk = r->rayCk.p;
+            CU(launch_ray_checkpoints(P, setup_grid, r->stream));
+            ++r->launches;
+        }
     } else if (P.slicing) {
         // (the slicing set-up also counts ray samples and paints the white background: it runs again, and so does the item
         // construction below; only the sizes are known already)
@@ -779,6 +811,7 @@ static int render_sample_parallel(VVRenderer *r, DevParams &P)
     const bool ngate = r->illum_mode != ILLUM_GRADIENT && r->noise_gate;
     const int nBands = (r->nby + r->band_rows - 1) / r->band_rows;
     P.bandRows = r->band_rows;
+    P.itemChunk = r->item_chunk;
     P.emitItems = r->depth_major ? 0 : 1;
     // work items of window p = [w[p], w[p+1]) into `items` / `count`, in (band, depth chunk)-major order (item_bucket_kernel)
     auto build_items = [&](size_t p, uint2 *items, unsigned int *count) -> int {
@@ -1268,13 +1301,9 @@ int vv_set_option(VVRenderer *r, int option, int value)
     case VV_OPT_QUIRK_LUMINANCE_ALPHA: r->quirk_lum_alpha = value != 0; break;
     case VV_OPT_LICVOL_FP16: r->licvol_fp16 = value != 0; break;
     case VV_OPT_FIELD_LAYOUT:
-        if (value != LAYOUT_F4 && value != LAYOUT_PAIR && value != LAYOUT_QUAD) return fail(VV_ERR_INVALID, "bad field layout");
-        if (value != r->field_layout) {
-            r->field_layout = value;
-            r->field_pair.release();
-            r->field_f4.release();
-            r->field_dirty = true;
-        }
+        if (value != LAYOUT_F4 && value != LAYOUT_PAIR && value != LAYOUT_QUAD && value != 3) return fail(VV_ERR_INVALID, "bad field layout");
+        r->field_layout_req = value;
+        resolve_field_layout(r);
         break;
     case VV_OPT_COUNT_SAMPLES: r->count_samples = value != 0; break;
     case VV_OPT_LICVOL_SIZE:
@@ -1289,6 +1318,9 @@ int vv_set_option(VVRenderer *r, int option, int value)
         if (value < 0 || value > 2) return fail(VV_ERR_INVALID, "bad noise layout");
         r->noise_layout = value; break;
     case VV_OPT_DEPTH_MAJOR: r->depth_major = value != 0; break;
+    case VV_OPT_ITEM_AFFINITY:
+        if (value < 0 || value > 4096) return fail(VV_ERR_INVALID, "bad item affinity chunk");
+        r->item_chunk = value; break;
     case VV_OPT_BAND_ROWS:
         if (value < 1 || value > 1024) return fail(VV_ERR_INVALID, "bad band rows");
         r->band_rows = value; break;
@@ -1648,6 +1680,7 @@ float vv_last_kernel_ms(VVRenderer *r)
 }
 
 int vv_last_launch_count(VVRenderer *r) { return r ? r->launches : 0; }
+int vv_field_layout(VVRenderer *r) { if (!r) return -1; resolve_field_layout(r); return r->field_layout; }
 
 int vv_synchronize(VVRenderer *r)
 {
@@ -1812,7 +1845,7 @@ int vv_debug_walk(VVRenderer *r, const float pos[3], int dir_sign, int n_steps, 
     DevParams P;
     int rc = fill_params(r, P, false, true);
     if (rc) return rc;
-    if (r->field_layout != LAYOUT_PAIR) return fail(VV_ERR_STATE, "vv_debug_walk: x-pair field layout only");
+    if (r->field_layout == LAYOUT_F4) return fail(VV_ERR_STATE, "vv_debug_walk: fp16 cell layouts only (x-pair / xy-quad)");
     const bool grad = (r->illum_mode == ILLUM_GRADIENT);
     if (n_steps > (dir_sign < 0 ? P.nBwd : P.nFwd)) return fail(VV_ERR_INVALID, "vv_debug_walk: more steps than the LIC parameters have");
     if (walk_variant != 0 && !P.guardOk) return fail(VV_ERR_STATE, "vv_debug_walk: no guard band for this field / these LIC parameters");
@@ -1822,7 +1855,7 @@ int vv_debug_walk(VVRenderer *r, const float pos[3], int dir_sign, int n_steps, 
     DevBuf<float> d;
     CU(d.ensure((size_t)n_steps * 16));
     CU(cudaMemsetAsync(d.p, 0, (size_t)n_steps * 16 * sizeof(float), r->stream));
-    CU(launch_debug_walk(P, grad, walk_variant, pos, dir_sign, n_steps, d.p, r->stream));
+    CU(launch_debug_walk(P, r->field_layout, grad, walk_variant, pos, dir_sign, n_steps, d.p, r->stream));
     CU(cudaMemcpyAsync(out, d.p, (size_t)n_steps * 16 * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
     CU(cudaStreamSynchronize(r->stream));
     return VV_OK;
