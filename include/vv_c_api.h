@@ -92,7 +92,6 @@ typedef enum VVOption {
     VV_OPT_BAND_ROWS = 16,         /* 16-pixel block rows per band of the depth-major order (default 4) */
     VV_OPT_FIRST_WINDOW = 18,      /* early-termination frames: ray samples in the first depth window (multiple of 8, default 8) */
     VV_OPT_WINDOW_GROWTH = 19,     /* ... and the length of every further window in percent of the previous one (100..400, default 200) */
-    VV_OPT_ITEM_AFFINITY = 20,     /* lic_sample work items handed out CTA-affine in chunks of this many consecutive items (0: one global queue) */
     VV_OPT_NOISE_LAYOUT = 17       /* RGBA (-g) noise: 2 (default) bf16 {t0, t1 - t0}, 1 fp16 x-pair, 0 u8 xy-quad; same values, same frames */
 } VVOption;
 

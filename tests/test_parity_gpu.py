@@ -357,6 +357,13 @@ def test_layouts_bit_identical(vv):
         assert ta == tb == tc and np.array_equal(ca, cb) and np.array_equal(ca, cc)
         assert np.array_equal(a, b) and np.array_equal(a, c)
         assert np.array_equal(ra.readFieldTexture(s.field.shape[:3]), rc.readFieldTexture(s.field.shape[:3]))
+        assert (ra.fieldLayout(), rc.fieldLayout()) == (vv.LAYOUT_PAIR, vv.LAYOUT_QUAD)
+        # the default (VV_OPT_FIELD_LAYOUT = 3) resolves to the xy-quad layout at these sizes; one-thread-per-ray kernel on it too
+        rd, d, _, cd, td = render_cuda(vv, s)
+        assert rd.fieldLayout() == vv.LAYOUT_QUAD and td == ta and np.array_equal(d, a) and np.array_equal(cd, ca)
+        rd.setOption(vv.OPT_RAYCAST_MODE, 0)
+        rd.render(True)
+        assert np.array_equal(rd.readRGBA32F(), a)
         ra.setOption(vv.OPT_LICVOL_FP16, 0); rc.setOption(vv.OPT_LICVOL_FP16, 0)
         ra.updateLICVolume(); rc.updateLICVolume()
         assert np.array_equal(ra.readLICVolume(), rc.readLICVolume())

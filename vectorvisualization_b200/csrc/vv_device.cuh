@@ -108,7 +108,6 @@ struct DevParams {
     unsigned int *itemCount, *itemCountNext, *itemHead, *slotAlloc, *nMaxGlobal;
     unsigned int *tileLive;          // [tile]: longest ray of the tile that is still alive (0: every ray of the tile has finished)
     int win0, win1, win2;            // current window [win0, win1), next window [win1, win2) (the one whose items are being built)
-    int itemChunk;                   // > 0: items are handed out CTA-affine in chunks of this many consecutive items (lic_sample_kernel)
     int emitItems;                   // composite_kernel emits the next window's items itself, tile-major (VV_OPT_DEPTH_MAJOR = 0)
     // depth-major item order: buckets = (band of block rows) x (chunk of 8 depths)
     unsigned int *bucketCount, *bucketBase, *bucketFill;

@@ -849,38 +849,20 @@ __global__ void __launch_bounds__(LicShape<ILLUM>::kThreads, LicShape<ILLUM>::kM
     if (nItems == 0) return;
     load_tables(P, S);
     const int lane = threadIdx.x & 31;
-    // Every warp pops single items and works on its own (no barrier in the loop).  WHICH item a pop returns decides what the
-    // warps of one SM share in L1.  The list is bucket-major (band, chunk of 8 depths) and inside a bucket 8 consecutive items are
-    // the 8 depths of one ray tile: ray samples whose streamlines start 1 - 2 voxels apart and run side by side.
-    //   itemChunk == 0: one global queue -- consecutive items go to whichever warps pop next, on any SM.
-    //   itemChunk == C: CTA-affine hand-out.  The list is cut into chunks of C consecutive items, dealt round-robin to the CTAs
-    //     (CTA b owns chunks b, b + G, b + 2G, ...); the warps of a CTA pop from the CTA's own cursor in shared memory, so they
-    //     shade neighbouring samples at the same time.  All CTAs advance through the list at the same pace, which keeps the
-    //     depth-major sweep (L2).  The last ~10 % of the list go through the global queue to even out the finish.
-    const unsigned int C = (unsigned int)P.itemChunk, G = gridDim.x;
-    unsigned int nAffine = 0;
-    if (C > 0) {
-        const unsigned long long round = (unsigned long long)C * G;
-        nAffine = (unsigned int)(((unsigned long long)nItems * 9 / 10) / round * round);
-        if (threadIdx.x == 0) S.block = 0;
-        __syncthreads();
-    }
-    bool affine = nAffine > 0;
+    // Every warp pops single items from ONE global queue and works on its own (no barrier in the loop).  The list is bucket-major
+    // (band, chunk of 8 depths), so the items in flight at any moment -- the last ~4700 pops -- are one thin slab of the volume: that
+    // tight window is what keeps the gathers in L2.  Measured alternatives: a CTA pops a chunk of 8..64 consecutive items and its
+    // warps walk it together behind a barrier (round 1: L1 hit rate unchanged, issue utilisation 72 % -> 64 % from the barrier);
+    // CTA-affine hand-out without a barrier (chunks of 4..32 consecutive items dealt round-robin to the CTAs, each CTA popping from
+    // its own cursor in shared memory so that its warps shade neighbouring depths of one ray tile, last 10 % through the global
+    // queue): cfg3 +12 %, cfg2 +10 %, cfg4 +18 % SLOWER -- the CTAs drift apart and the window in L2 widens
+    // (profiles/r02/ab18_cta_affine_items.log).
     for (;;) {
       {
         unsigned int i = 0;
-        if (affine) {
-            if (lane == 0) i = (unsigned int)atomicAdd(&S.block, 1);
-            i = __shfl_sync(0xffffffffu, i, 0);
-            const unsigned long long g = ((unsigned long long)(i / C) * G + blockIdx.x) * C + i % C;
-            if (g < nAffine) i = (unsigned int)g;
-            else affine = false;                         // this CTA's share is done: on to the common tail
-        }
-        if (!affine) {
-            if (lane == 0) i = atomicAdd(P.itemHead, 1u);
-            i = __shfl_sync(0xffffffffu, i, 0) + nAffine;
-            if (i >= nItems) break;
-        }
+        if (lane == 0) i = atomicAdd(P.itemHead, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= nItems) break;
         const uint2 it = P.items[i];
         const int ray = (int)it.x * 32 + lane;
         const int k = (int)it.y;
@@ -1144,6 +1126,10 @@ __global__ void __launch_bounds__(256) volume_raycast_kernel(const __grid_consta
                            // fields: 512^3 curl noise 170.5 -> 156.4 ms against 3 CTAs / 80 registers, 256^3 tornado 9.76 -> 10.0 ms; 5 CTAs / 48
                            // registers spill: 264 ms)
 #endif
+// (Measured and dropped: an L2 prefetch of the cell the next Heun step's predictor is expected in -- position + 2 x the current
+// displacement, no destination registers -- made this kernel 36 % (512^3) to 41 % (1024^3) SLOWER on the curl-noise fields and 6 %
+// slower on the 256^3 tornado: it is bound by DRAM gather bandwidth, not by the number of loads in flight, and every mispredicted
+// line is paid for; profiles/r02/licvol22_l2_prefetch.log.)
 template <int LAYOUT, bool GRAD, bool NGATE, bool SOF>
 __global__ void __launch_bounds__(256, LICVOL_MIN_CTAS) lic_volume_kernel(const __grid_constant__ DevParams P)
 {

@@ -175,7 +175,6 @@ struct VVRenderer {
     int first_window = 8, window_growth = 200;    // depth windows of early-termination frames: first length, growth in percent
                                                   // (measured, profiles/r02/ab10_window_schedules.log: cfg1 is flat between 8 and 32,
                                                   // a surface-like frame such as cfg3o pays for every speculative sample: 1.17 ms at 8, 2.06 at 16)
-    int item_chunk = 0;                    // VV_OPT_ITEM_AFFINITY
     int depth_major = 1;                   // 1: bucket work items by (band, depth chunk) for L2 locality; 0: tile-major
     int band_rows = 4;                     // block rows per band (4 x 16 = 64 pixel rows)
     DevBuf<unsigned int> buckets;
@@ -811,7 +810,6 @@ static int render_sample_parallel(VVRenderer *r, DevParams &P)
     const bool ngate = r->illum_mode != ILLUM_GRADIENT && r->noise_gate;
     const int nBands = (r->nby + r->band_rows - 1) / r->band_rows;
     P.bandRows = r->band_rows;
-    P.itemChunk = r->item_chunk;
     P.emitItems = r->depth_major ? 0 : 1;
     // work items of window p = [w[p], w[p+1]) into `items` / `count`, in (band, depth chunk)-major order (item_bucket_kernel)
     auto build_items = [&](size_t p, uint2 *items, unsigned int *count) -> int {
@@ -1318,9 +1316,6 @@ int vv_set_option(VVRenderer *r, int option, int value)
         if (value < 0 || value > 2) return fail(VV_ERR_INVALID, "bad noise layout");
         r->noise_layout = value; break;
     case VV_OPT_DEPTH_MAJOR: r->depth_major = value != 0; break;
-    case VV_OPT_ITEM_AFFINITY:
-        if (value < 0 || value > 4096) return fail(VV_ERR_INVALID, "bad item affinity chunk");
-        r->item_chunk = value; break;
     case VV_OPT_BAND_ROWS:
         if (value < 1 || value > 1024) return fail(VV_ERR_INVALID, "bad band rows");
         r->band_rows = value; break;
