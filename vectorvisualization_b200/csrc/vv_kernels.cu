@@ -210,6 +210,12 @@ __device__ __forceinline__ void heun_step(const DevParams &P, Walker &w, float s
     }
 }
 
+// (Measured and dropped: one Heun step of BOTH walkers with their predictor cells requested together -- pinned loads in front of
+// the first walker's divergent reload region, which ptxas does not hoist the second walker's loads across, so that the two walks'
+// memory round trips overlap instead of running one after the other.  Same arithmetic, same frames; the 32 registers of raw cells in
+// flight push the loop into spills (gradient build 5 + 5, scalar builds 11 + 11 local accesses per double step) and the kernel is
+// throughput-, not latency-limited: cfg3 +2.6 %, cfg2 +2.1 %, cfg4 +7.5 % slower; profiles/r02/ab23_paired_walker_loads.log.)
+
 // computeLIC, inc_lic.glsl:152-202, scalar build.  The backward and forward walks are independent; they are
 // advanced in the same loop iteration so that each thread keeps two dependent fetch chains in flight.
 // nBwdEff / nFwdEff: the walk stops after the last step whose filter-kernel weight is non-zero (trailing zero
