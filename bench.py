@@ -62,7 +62,7 @@ def config_dict(s):
     """the workload definition -- identical in the CUDA arm and the reference arm"""
     n = s.field.shape
     return {"workload": workload_string(s),
-            "l2": "inputs larger than L2 (field %.0f MB + noise %.0f MB vs 126 MB)" % (
+            "l2": "inputs larger than L2 (field %.0f MB at 16 B/voxel, twice that in the default xy-quad layout, + noise %.0f MB vs 126 MB)" % (
                 n[0] * n[1] * n[2] * 16 / 1e6, s.noise.size * (16 if s.with_gradients else 8) / 1e6)}
 
 
@@ -454,7 +454,8 @@ def run_cuda(args):
     k_ms = float(np.median(kernel_ms)) if kernel_ms else ms_per_step
     requested = B * local_samples / (k_ms * 1e-3) / 1e9            # GB/s asked for by the lanes of THIS rank's launch
     n = scene.field.shape
-    compulsory = n[0] * n[1] * n[2] * 16 + scene.noise.size * (16 if scene.with_gradients else 8) + scene.width * scene.height * 16
+    field_bytes_per_voxel = 32 if field_layout and field_layout.startswith("xy-quad") else 16
+    compulsory = n[0] * n[1] * n[2] * field_bytes_per_voxel + scene.noise.size * (16 if scene.with_gradients else 8) + scene.width * scene.height * 16
     prof = profile_record(scene.name)
     ncu = prof.get("ncu") or {}
     sms = torch.cuda.get_device_properties(0).multi_processor_count
