@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2 multi-GPU record on one box: gpurun --gpus N -- 'bash scripts/gpu_scaling2.sh N'
+# round 2 multi-GPU record on one box: gpurun --gpus N -- 'bash scripts/gpu_calls/gpu_scaling2.sh N'
 N=${1:-8}
 mkdir -p gpurun_out
 O=gpurun_out

@@ -915,6 +915,11 @@ __global__ void __launch_bounds__(LicShape<ILLUM>::kThreads, LicShape<ILLUM>::kM
     }
 }
 
+// (Measured and dropped: compositing fused into lic_sample_kernel for single-window frames -- a per-tile counter of shaded items, the
+// warp that shades a tile's last item blends the tile's rays right there (fence + atomic per item, samples read past L1, the blend
+// as a called function so that the walk loops' register allocation does not see it).  Frames identical, racecheck clean, one launch
+// less -- and no faster: cfg3 11.87 -> 11.92 ms, cfg2 +0.8 %, cfg4 +2.2 %, a rank's 1/8 share 1.580 -> 1.583 ms: the per-item
+// synchronisation added to the hot kernel costs what the 72 us launch saves.  profiles/r02/ab25_fused_compositing.log.)
 __global__ void __launch_bounds__(256) composite_kernel(const __grid_constant__ DevParams P)
 {
     const int lane = threadIdx.x & 31;
