@@ -31,6 +31,8 @@ if "band" in opts:
     r.setOption(vv.OPT_BAND_ROWS, int(opts["band"]))
 if "noiselayout" in opts:
     r.setOption(vv.OPT_NOISE_LAYOUT, int(opts["noiselayout"]))
+if "unit" in opts:
+    r.setOption(vv.OPT_PARTITION_UNIT, int(opts["unit"]))
 if "ctas" in opts:
     r.setOption(vv.OPT_LIC_CTAS_PER_SM, int(opts["ctas"]))
 configs.apply_scene(r, s)

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, w, h, q):
+def _worker(rank, world, port, w, h, q, unit=1):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -31,18 +31,19 @@ def _worker(rank, world, port, w, h, q):
     rng = np.random.RandomState(7)
     full = rng.rand(h, w, 4).astype(np.float32)                      # the frame every rank would agree on
     nbx, nby = vd.block_grid(w, h)
-    bpr = vd.blocks_per_rank(w, h, world)
+    bpr = vd.blocks_per_rank(w, h, world, unit=unit)
     mine = np.zeros((bpr, 256, 4), np.float32)
-    for lb, b in enumerate(vd.local_blocks(w, h, rank, world)):      # this rank "renders" only its own blocks
-        bx, by = vd.block_xy(nbx, vd.block_skew(world), b)
+    for lb, b in enumerate(vd.local_blocks(w, h, rank, world, unit=unit)):      # this rank "renders" only its own blocks
+        bx, by = vd.block_xy(nbx, vd.block_skew(world), b, world, unit)
         tile = np.zeros((16, 16, 4), np.float32)
         y0, x0 = by * 16, bx * 16
-        hh, ww = min(16, h - y0), min(16, w - x0)
-        tile[:hh, :ww] = full[y0:y0 + hh, x0:x0 + ww]
+        hh, ww = max(0, min(16, h - y0)), max(0, min(16, w - x0))    # blocks of a border unit may lie outside the image
+        if hh and ww:
+            tile[:hh, :ww] = full[y0:y0 + hh, x0:x0 + ww]
         mine[lb] = tile.reshape(256, 4)
     gathered = torch.empty((world * bpr * 256 * 4,), dtype=torch.float32)
     dist.all_gather_into_tensor(gathered, torch.from_numpy(mine).reshape(-1))
-    img = vd.assemble_host(gathered.numpy().reshape(world, bpr, 256, 4), w, h, world)
+    img = vd.assemble_host(gathered.numpy().reshape(world, bpr, 256, 4), w, h, world, unit=unit)
     ok = bool(np.array_equal(img, full))
     # LIC-volume slabs: every rank fills its z range, slabs are exchanged, result is complete
     depth = 13
@@ -57,13 +58,13 @@ def _worker(rank, world, port, w, h, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("size", [(90, 70), (64, 64), (33, 17)])
-def test_partition_gather_assemble_gloo(size):
+@pytest.mark.parametrize("size,unit", [((90, 70), 1), ((64, 64), 1), ((33, 17), 1), ((90, 70), 2), ((200, 120), 4)])
+def test_partition_gather_assemble_gloo(size, unit):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, size[0], size[1], q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, size[0], size[1], q, unit)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=120) for _ in procs)
@@ -88,6 +89,29 @@ def test_partition_bookkeeping():
             pos = [vd.block_xy(nbx, sk, b) for b in range(nbx * nby)]
             assert sorted(pos) == sorted((x, y) for y in range(nby) for x in range(nbx))
             assert all(vd.block_id(nbx, sk, x, y) == b for b, (x, y) in enumerate(pos))
+    # units of U x U blocks (VV_OPT_PARTITION_UNIT): ids stay a bijection onto the padded block grid, id % world owns whole units
+    for (w, h) in ((1024, 1024), (90, 70), (200, 120), (16, 16)):
+        nbx, nby = vd.block_grid(w, h)
+        for unit in (2, 4):
+            for world in (2, 3, 8):
+                sk = vd.block_skew(world)
+                nids = vd.num_block_ids(w, h, unit)
+                seen = []
+                for r in range(world):
+                    lb = vd.local_blocks(w, h, r, world, unit=unit)
+                    assert len(lb) <= vd.blocks_per_rank(w, h, world, unit=unit) and len(lb) % (unit * unit) == 0
+                    seen += lb
+                pos = {}
+                for b in seen:
+                    x, y = vd.block_xy(nbx, sk, b, world, unit)
+                    assert (x, y) not in pos
+                    pos[(x, y)] = b
+                    assert vd.block_id(nbx, sk, x, y, world, unit) == b
+                assert len(seen) == nids and all((x, y) in pos for y in range(nby) for x in range(nbx))
+                # the blocks of a unit share their owner and are consecutive local blocks
+                for (x, y), b in pos.items():
+                    b0 = pos[(x // unit * unit, y // unit * unit)]
+                    assert b % world == b0 % world and b // world - b0 // world == (y % unit) * unit + x % unit
     # the rotation scatters a rank's blocks over columns as well as rows even when nbx % world == 0
     nbx, nby = vd.block_grid(1024, 1024)
     for world in (2, 4, 8):

@@ -531,8 +531,10 @@ def test_volume_raycast_parity(vv, oracle):
         assert_image_parity(oracle, img, ref2, "volume_raycast_e2e")
 
 
-def test_partition_invariance_single_gpu(vv):
-    """sort-first block partition: 1 handle == 3 partitioned handles assembled (bit-identical)"""
+@pytest.mark.parametrize("unit", [1, 2, 4])
+def test_partition_invariance_single_gpu(vv, unit):
+    """sort-first block partition: 1 handle == 3 partitioned handles assembled (bit-identical), for single blocks and for units of
+    2 x 2 / 4 x 4 blocks (VV_OPT_PARTITION_UNIT; the 90 x 70 frame has 6 x 5 blocks, so border units stick out of the image)"""
     import torch
     from vectorvisualization_b200 import configs
     from vectorvisualization_b200.configs import apply_scene
@@ -545,6 +547,7 @@ def test_partition_invariance_single_gpu(vv):
     total = 0
     for rank in range(world):
         r = vv.Renderer(0)
+        r.setOption(vv.OPT_PARTITION_UNIT, unit)
         apply_scene(r, s)
         r.setPartition(rank, world)
         r.render(True)
@@ -563,7 +566,8 @@ def test_partition_invariance_single_gpu(vv):
     assert np.array_equal(img, full)
 
 
-def test_p2p_exchange_single_process(vv):
+@pytest.mark.parametrize("unit", [1, 2])
+def test_p2p_exchange_single_process(vv, unit):
     """vv_p2p_*: three partitioned handles in one process exchange their tiles through peer stores + arrival counters
     (the multi-GPU path without IPC): every handle ends up with the unpartitioned frame, over several frames (buffer
     parity / arrival targets) and a camera change"""
@@ -575,6 +579,7 @@ def test_p2p_exchange_single_process(vv):
     hs = []
     for rank in range(world):
         r = vv.Renderer(0)
+        r.setOption(vv.OPT_PARTITION_UNIT, unit)
         apply_scene(r, s)
         r.setPartition(rank, world)
         # warm-up with both views: every buffer reaches its final size.  (Ranks normally live in separate processes; here

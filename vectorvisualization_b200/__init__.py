@@ -24,7 +24,7 @@ TF_B, TF_A, TF_R, TF_LENGTH, TF_SCALAR = range(5)
 GATE_ALWAYS, GATE_TF_ALPHA = 0, 1
 (OPT_TF_MODE, OPT_GATE_MODE, OPT_NOISE_GATE, OPT_QUIRK_SCALEVOLINV, OPT_QUIRK_LUMINANCE_ALPHA, OPT_LICVOL_FP16,
  OPT_FIELD_LAYOUT, OPT_COUNT_SAMPLES, OPT_LICVOL_SIZE, OPT_SPEC_EXP, OPT_SAMPLE_MAP, OPT_RAYCAST_MODE,
- OPT_LIC_CTAS_PER_SM, OPT_WALK_FAST_PATHS, OPT_DEPTH_MAJOR, OPT_BAND_ROWS, OPT_NOISE_LAYOUT, OPT_FIRST_WINDOW, OPT_WINDOW_GROWTH) = range(1, 20)
+ OPT_LIC_CTAS_PER_SM, OPT_WALK_FAST_PATHS, OPT_DEPTH_MAJOR, OPT_BAND_ROWS, OPT_NOISE_LAYOUT, OPT_FIRST_WINDOW, OPT_WINDOW_GROWTH, OPT_PARTITION_UNIT) = range(1, 21)
 LAYOUT_F4, LAYOUT_PAIR, LAYOUT_QUAD, LAYOUT_AUTO = 0, 1, 2, 3   # AUTO (default): QUAD up to 48 GiB of packed field, else PAIR
 BLOCK = 16  # pixels per image-block edge (sort-first partition unit)
 

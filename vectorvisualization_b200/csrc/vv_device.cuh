@@ -93,6 +93,7 @@ struct DevParams {
     // ---- partition / outputs ----
     int rank, world, nBlocksX, nBlocksY, nLocalBlocks;
     int blockSkew;                   // per-row rotation of the block ids, see block_id()
+    int partUnit;                    // the partition deals units of partUnit x partUnit blocks to the ranks, see block_id_u()
     float4 *tiles;
     unsigned long long *sampleCounter;
     unsigned int *blockCounter;
@@ -137,9 +138,31 @@ __host__ __device__ __forceinline__ void block_xy_of(int nbx, int skew, int b, i
     if (bx < 0) bx += nbx;
 }
 
+// The same deal with UNITS of U x U blocks: the unit (ux, uy) = (bx / U, by / U) has the unit id block_id(ceil(nbx / U), skew, ux, uy) and
+// belongs to rank (unit id mod world); a block's id is ((unit id / world) U^2 + sub) world + rank with sub = (by mod U) U + bx mod U, so
+// that, as before, id mod world is the owner and id / world the local block index (units of a rank back to back, blocks of a unit
+// consecutive).  Blocks of a unit that lie outside the image (nbx or nby not a multiple of U) exist as ids and hold no pixel.
+// Why units: a rank's block needs the volume its rays cross plus a margin of one streamline length on every side (cfg3: 6 voxels
+// + 2 x 12); isolated 16-pixel blocks make every rank fetch ~25 x the volume it owns through L2, 2 x 2 units ~9 x, 4 x 4 units ~4 x.
+__host__ __device__ __forceinline__ int block_id_u(int nbx, int skew, int world, int U, int bx, int by)
+{
+    if (U <= 1) return block_id(nbx, skew, bx, by);
+    const int uid = block_id((nbx + U - 1) / U, skew, bx / U, by / U);
+    return ((uid / world) * U * U + (by % U) * U + bx % U) * world + uid % world;
+}
+__host__ __device__ __forceinline__ void block_xy_of_u(int nbx, int skew, int world, int U, int b, int &bx, int &by)
+{
+    if (U <= 1) { block_xy_of(nbx, skew, b, bx, by); return; }
+    const int lb = b / world, sub = lb % (U * U);
+    int ux, uy;
+    block_xy_of((nbx + U - 1) / U, skew, (lb / (U * U)) * world + b % world, ux, uy);
+    bx = ux * U + sub % U;
+    by = uy * U + sub / U;
+}
+
 __device__ __forceinline__ float lerpf(float a, float b, float f) { return fmaf(f, b - a, a); }
 
-__device__ __forceinline__ void block_xy(const DevParams &P, int b, int &bx, int &by) { block_xy_of(P.nBlocksX, P.blockSkew, b, bx, by); }
+__device__ __forceinline__ void block_xy(const DevParams &P, int b, int &bx, int &by) { block_xy_of_u(P.nBlocksX, P.blockSkew, P.world, P.partUnit, b, bx, by); }
 
 struct f3 { float x, y, z; };
 __device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }

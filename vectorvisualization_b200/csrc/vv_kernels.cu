@@ -1030,8 +1030,9 @@ __global__ void __launch_bounds__(256) item_bucket_kernel(const __grid_constant_
     for (int lt = blockIdx.x * 8 + (threadIdx.x >> 5); lt < nTiles; lt += gridDim.x * 8) {
         const int nmax = min((int)P.tileLive[lt], P.win2);
         if (nmax <= P.win1) continue;
-        const int b = P.rank + (lt >> 3) * P.world;
-        const int band = (b / P.nBlocksX) / P.bandRows;
+        int bbx, bby;
+        block_xy(P, P.rank + (lt >> 3) * P.world, bbx, bby);
+        const int band = bby / P.bandRows;
         const int nchunks = ((nmax + 7) >> 3) - c0;
         for (int c = lane; c < nchunks; c += 32) {
             const int k0 = 8 * (c0 + c);
@@ -1215,14 +1216,14 @@ cudaError_t launch_debug_walk(const DevParams &P, int layout, bool grad, int xf,
 
 // K5 ------------------------------------------------------------------------------------------------
 // tiles laid out [world][nLocalBlocksMax][256] -> row-major float frame, RGBA8 frame, and displayed RGBA8
-__global__ void unblock_kernel(const float4 *__restrict__ tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY, int skew,
+__global__ void unblock_kernel(const float4 *__restrict__ tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY, int skew, int unit,
                                int width, int height, float4 *__restrict__ frame, uchar4 *__restrict__ frame8,
                                uchar4 *__restrict__ display8)
 {
     const int px = blockIdx.x * blockDim.x + threadIdx.x;
     const int py = blockIdx.y * blockDim.y + threadIdx.y;
     if (px >= width || py >= height) return;
-    const int b = block_id(nBlocksX, skew, px / kBlockDim, py / kBlockDim);
+    const int b = block_id_u(nBlocksX, skew, world, unit, px / kBlockDim, py / kBlockDim);
     const int r = b % world, lb = b / world;
     float4 c = tiles[((size_t)r * blocksPerRank + lb) * kBlockPixels + (py % kBlockDim) * kBlockDim + (px % kBlockDim)];
     const size_t o = (size_t)py * width + px;
@@ -1505,11 +1506,11 @@ cudaError_t launch_wait_arrivals(unsigned int *flag, unsigned int target, unsign
     return cudaGetLastError();
 }
 
-cudaError_t launch_unblock(const float4 *tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY, int skew, int width, int height,
+cudaError_t launch_unblock(const float4 *tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY, int skew, int unit, int width, int height,
                            float4 *frame, uchar4 *frame8, uchar4 *display8, cudaStream_t st)
 {
     dim3 blk(16, 16), grd((width + 15) / 16, (height + 15) / 16);
-    unblock_kernel<<<grd, blk, 0, st>>>(tiles, world, blocksPerRank, nBlocksX, nBlocksY, skew, width, height, frame, frame8, display8);
+    unblock_kernel<<<grd, blk, 0, st>>>(tiles, world, blocksPerRank, nBlocksX, nBlocksY, skew, unit, width, height, frame, frame8, display8);
     return cudaGetLastError();
 }
 

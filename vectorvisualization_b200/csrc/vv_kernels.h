@@ -22,7 +22,7 @@ cudaError_t launch_item_buckets(const DevParams &P, int nBuckets, int grid, cuda
 cudaError_t launch_debug_walk(const DevParams &P, int layout, bool grad, int xf, const float pos[3], int dirSign, int nSteps, float *out, cudaStream_t st);
 cudaError_t launch_volume_raycast(const DevParams &P, int layout, int grid, cudaStream_t st);
 cudaError_t launch_lic_volume(const DevParams &P, int layout, bool grad, bool noise_gate, bool speed_of_flow, int grid, cudaStream_t st);
-cudaError_t launch_unblock(const float4 *tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY, int skew, int width, int height,
+cudaError_t launch_unblock(const float4 *tiles, int world, int blocksPerRank, int nBlocksX, int nBlocksY, int skew, int unit, int width, int height,
                            float4 *frame, uchar4 *frame8, uchar4 *display8, cudaStream_t st);
 
 // ---- peer-to-peer tile exchange (multi-GPU) ----

@@ -36,7 +36,7 @@ static const int kNumCounters = 16;
 struct GeomKey {
     double camD[3], rot[9], tanHalf, aspect, extent[3], nearD, farD, clipEq[3][4], clipN[3][3], clipDist[3], centerD[3], slCenter[3];
     float stepSize, scaleVol[3], texMax[3], camera[3], slV[3], slD;
-    int width, height, numIter, nClip, rank, world, nLocalBlocks, blockSkew, slicing, slNum, depthMajor, bandRows, firstWindow, windowGrowth, sampleMap;
+    int width, height, numIter, nClip, rank, world, nLocalBlocks, blockSkew, partUnit, slicing, slNum, depthMajor, bandRows, firstWindow, windowGrowth, sampleMap;
     unsigned long long mcVersion;
     const void *mcOffsets;
 };
@@ -175,6 +175,7 @@ struct VVRenderer {
     int first_window = 8, window_growth = 200;    // depth windows of early-termination frames: first length, growth in percent
                                                   // (measured, profiles/r02/ab10_window_schedules.log: cfg1 is flat between 8 and 32,
                                                   // a surface-like frame such as cfg3o pays for every speculative sample: 1.17 ms at 8, 2.06 at 16)
+    int part_unit = 1;                     // VV_OPT_PARTITION_UNIT: the sort-first partition deals units of this many x this many blocks
     int depth_major = 1;                   // 1: bucket work items by (band, depth chunk) for L2 locality; 0: tile-major
     int band_rows = 4;                     // block rows per band (4 x 16 = 64 pixel rows)
     DevBuf<unsigned int> buckets;
@@ -258,14 +259,17 @@ static void update_light(VVRenderer *r)
         r->light_pos[i] = (float)(Rm[3 * i] * l[0] + Rm[3 * i + 1] * l[1] + Rm[3 * i + 2] * l[2] + r->center[i]);
 }
 
+static int part_unit(const VVRenderer *r) { return r->world > 1 ? r->part_unit : 1; }
+
 static int ensure_frame(VVRenderer *r)
 {
     r->nbx = (r->width + kBlockDim - 1) / kBlockDim;
     r->nby = (r->height + kBlockDim - 1) / kBlockDim;
-    const int nb = r->nbx * r->nby;
-    r->blocks_per_rank = (nb + r->world - 1) / r->world;
-    r->n_local_blocks = (nb - r->rank + r->world - 1) / r->world;
-    if (r->n_local_blocks < 0) r->n_local_blocks = 0;
+    // units of U x U blocks are dealt to the ranks (block_id_u); a single GPU keeps plain blocks
+    const int U = part_unit(r);
+    const int nunits = ((r->nbx + U - 1) / U) * ((r->nby + U - 1) / U);
+    r->blocks_per_rank = (nunits + r->world - 1) / r->world * U * U;
+    r->n_local_blocks = std::max(0, (nunits - r->rank + r->world - 1) / r->world) * U * U;
     CU(r->tiles.ensure((size_t)r->blocks_per_rank * kBlockPixels));
     const size_t npx = (size_t)r->width * r->height;
     CU(r->frame.ensure(npx));
@@ -571,6 +575,7 @@ static int fill_params(VVRenderer *r, DevParams &P, bool need_frame, bool raycas
     }
     P.rank = r->rank; P.world = r->world; P.nBlocksX = r->nbx; P.nBlocksY = r->nby; P.nLocalBlocks = r->n_local_blocks;
     P.blockSkew = block_skew_for(r->world);
+    P.partUnit = part_unit(r);
     P.tiles = r->tiles.p;
     P.sampleCounter = r->count_samples ? r->counters.p : nullptr;
     P.blockCounter = r->counters.p ? reinterpret_cast<unsigned int *>(r->counters.p + 1) : nullptr;
@@ -592,7 +597,7 @@ static int persistent_grid(const VVRenderer *r, int work_items)
 
 static int run_unblock(VVRenderer *r, const float4 *tiles, int world, int blocks_per_rank)
 {
-    CU(launch_unblock(tiles, world, blocks_per_rank, r->nbx, r->nby, block_skew_for(world), r->width, r->height, r->frame.p, r->frame8.p, r->display8.p, r->stream));
+    CU(launch_unblock(tiles, world, blocks_per_rank, r->nbx, r->nby, block_skew_for(world), world > 1 ? r->part_unit : 1, r->width, r->height, r->frame.p, r->frame8.p, r->display8.p, r->stream));
     ++r->launches;
     r->frame_valid = true;
     return VV_OK;
@@ -736,7 +741,7 @@ static void make_geom_key(const VVRenderer *r, const DevParams &P, int first_win
     for (int i = 0; i < 3; ++i) { k.scaleVol[i] = P.scaleVol[i]; k.texMax[i] = P.texMax[i]; k.camera[i] = P.camera[i]; k.slV[i] = P.slV[i]; }
     k.slD = P.slD;
     k.width = P.width; k.height = P.height; k.numIter = P.numIter; k.nClip = P.nClip; k.rank = P.rank; k.world = P.world;
-    k.nLocalBlocks = P.nLocalBlocks; k.blockSkew = P.blockSkew; k.slicing = P.slicing; k.slNum = P.slNum;
+    k.nLocalBlocks = P.nLocalBlocks; k.blockSkew = P.blockSkew; k.partUnit = P.partUnit; k.slicing = P.slicing; k.slNum = P.slNum;
     k.depthMajor = r->depth_major; k.bandRows = r->band_rows; k.firstWindow = first_window; k.windowGrowth = r->window_growth; k.sampleMap = P.samplesPerPixel ? 1 : 0;
     k.mcVersion = r->mc_version; k.mcOffsets = P.mcOffsets;
 }
@@ -1316,6 +1321,14 @@ int vv_set_option(VVRenderer *r, int option, int value)
         if (value < 0 || value > 2) return fail(VV_ERR_INVALID, "bad noise layout");
         r->noise_layout = value; break;
     case VV_OPT_DEPTH_MAJOR: r->depth_major = value != 0; break;
+    case VV_OPT_PARTITION_UNIT:
+        if (value != 1 && value != 2 && value != 4 && value != 8) return fail(VV_ERR_INVALID, "partition unit must be 1, 2, 4 or 8 blocks");
+        if (value != r->part_unit) {
+            r->part_unit = value;
+            r->frame_valid = false;
+            if (r->width > 0) { int rc = ensure_frame(r); if (rc) return rc; }
+        }
+        break;
     case VV_OPT_BAND_ROWS:
         if (value < 1 || value > 1024) return fail(VV_ERR_INVALID, "bad band rows");
         r->band_rows = value; break;

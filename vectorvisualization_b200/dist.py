@@ -37,37 +37,59 @@ def block_skew(world):
     return 0 if world <= 1 else 2 * ((382 * world // 1000) // 2) + 1
 
 
-def block_id(nbx, skew, bx, by):
-    return by * nbx + (bx + skew * by) % nbx
+def block_id(nbx, skew, bx, by, world=1, unit=1):
+    """id of block (bx, by): owner = id % world, local block index = id // world (vv_device.cuh: block_id / block_id_u).
+    unit > 1: units of unit x unit blocks are dealt to the ranks instead of single blocks"""
+    if unit <= 1:
+        return by * nbx + (bx + skew * by) % nbx
+    nux = (nbx + unit - 1) // unit
+    uid = (by // unit) * nux + (bx // unit + skew * (by // unit)) % nux
+    return ((uid // world) * unit * unit + (by % unit) * unit + bx % unit) * world + uid % world
 
 
-def block_xy(nbx, skew, b):
-    by = b // nbx
-    return (b % nbx - skew * by) % nbx, by
+def block_xy(nbx, skew, b, world=1, unit=1):
+    if unit <= 1:
+        by = b // nbx
+        return (b % nbx - skew * by) % nbx, by
+    nux = (nbx + unit - 1) // unit
+    lb, sub = b // world, (b // world) % (unit * unit)
+    uid = (lb // (unit * unit)) * world + b % world
+    uy = uid // nux
+    ux = (uid % nux - skew * uy) % nux
+    return ux * unit + sub % unit, uy * unit + sub // unit
 
 
-def blocks_per_rank(width, height, world, block=16):
+def num_block_ids(width, height, unit=1, block=16):
+    """ids in use: whole units, so blocks of a border unit that lie outside the image are counted (they hold no pixel)"""
     nbx, nby = block_grid(width, height, block)
-    return (nbx * nby + world - 1) // world
+    return ((nbx + unit - 1) // unit) * ((nby + unit - 1) // unit) * unit * unit
 
 
-def local_blocks(width, height, rank, world, block=16):
+def blocks_per_rank(width, height, world, block=16, unit=1):
+    nunits = num_block_ids(width, height, unit, block) // (unit * unit)
+    return (nunits + world - 1) // world * unit * unit
+
+
+def local_blocks(width, height, rank, world, block=16, unit=1):
     """block ids owned by `rank`, in local order; block_xy() gives their position"""
-    nbx, nby = block_grid(width, height, block)
-    return list(range(rank, nbx * nby, world))
+    nunits = num_block_ids(width, height, unit, block) // (unit * unit)
+    n_local = max(0, (nunits - rank + world - 1) // world) * unit * unit
+    return [rank + lb * world for lb in range(n_local)]
 
 
-def assemble_host(gathered, width, height, world, block=16):
+def assemble_host(gathered, width, height, world, block=16, unit=1):
     """numpy reference of unblock_kernel: gathered [world][blocks_per_rank][block*block][C] -> [h][w][C]"""
     nbx, nby = block_grid(width, height, block)
     out = np.zeros((height, width, gathered.shape[-1]), dtype=gathered.dtype)
-    for b in range(nbx * nby):
-        r, lb = b % world, b // world
-        bx, by = block_xy(nbx, block_skew(world), b)
-        tile = gathered[r, lb].reshape(block, block, -1)
-        y0, x0 = by * block, bx * block
-        h, w = min(block, height - y0), min(block, width - x0)
-        out[y0:y0 + h, x0:x0 + w] = tile[:h, :w]
+    sk = block_skew(world)
+    for by in range(nby):
+        for bx in range(nbx):
+            b = block_id(nbx, sk, bx, by, world, unit)
+            r, lb = b % world, b // world
+            tile = gathered[r, lb].reshape(block, block, -1)
+            y0, x0 = by * block, bx * block
+            h, w = min(block, height - y0), min(block, width - x0)
+            out[y0:y0 + h, x0:x0 + w] = tile[:h, :w]
     return out
 
 
