@@ -90,8 +90,8 @@ typedef enum VVOption {
     VV_OPT_WALK_FAST_PATHS = 14,   /* 1 (default): unclamped walk inside the field's guard band + shared field / noise cell coordinates where they apply; 0: the clamping samplers (check; same frames) */
     VV_OPT_DEPTH_MAJOR = 15,       /* 1 (default): work items ordered band-major / depth-major for L2 locality; 0: tile-major */
     VV_OPT_BAND_ROWS = 16,         /* 16-pixel block rows per band of the depth-major order (default 4) */
-    VV_OPT_FIRST_WINDOW = 18,      /* early-termination frames: ray samples in the first depth window (multiple of 8, default 8) */
-    VV_OPT_WINDOW_GROWTH = 19,     /* ... and the length of every further window in percent of the previous one (100..400, default 200) */
+    VV_OPT_FIRST_WINDOW = 18,      /* early-termination frames: ray samples in the first depth window (1..4096, default 2) */
+    VV_OPT_WINDOW_GROWTH = 19,     /* ... and the length of every further window in percent of the previous one (100..400, default 300) */
     VV_OPT_PARTITION_UNIT = 20,    /* multi-GPU: the sort-first partition deals units of n x n 16-pixel blocks to the ranks (1, 2, 4 or 8; every rank the same
                                       value, before vv_p2p_export); larger units keep a rank's rays together (L2 locality), smaller ones balance better */
     VV_OPT_NOISE_LAYOUT = 17       /* RGBA (-g) noise: 2 (default) bf16 {t0, t1 - t0}, 1 fp16 x-pair, 0 u8 xy-quad; same values, same frames */

@@ -1025,17 +1025,16 @@ __global__ void __launch_bounds__(256) item_bucket_kernel(const __grid_constant_
 {
     const int lane = threadIdx.x & 31;
     const int nTiles = P.nLocalBlocks * 8;
-    // items of the window [win1, win2) (win1 a multiple of 8) for the tiles that still have live rays reaching into it
-    const int c0 = P.win1 >> 3;
+    // items of the window [win1, win2) for the tiles that still have live rays reaching into it, in chunks of 8 depths from win1
     for (int lt = blockIdx.x * 8 + (threadIdx.x >> 5); lt < nTiles; lt += gridDim.x * 8) {
         const int nmax = min((int)P.tileLive[lt], P.win2);
         if (nmax <= P.win1) continue;
         int bbx, bby;
         block_xy(P, P.rank + (lt >> 3) * P.world, bbx, bby);
         const int band = bby / P.bandRows;
-        const int nchunks = ((nmax + 7) >> 3) - c0;
+        const int nchunks = (nmax - P.win1 + 7) >> 3;
         for (int c = lane; c < nchunks; c += 32) {
-            const int k0 = 8 * (c0 + c);
+            const int k0 = P.win1 + 8 * c;
             const int cnt = min(8, nmax - k0);
             const int bucket = band * P.nDepthChunks + c;
             if (pass == 0) {

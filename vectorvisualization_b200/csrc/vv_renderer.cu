@@ -172,9 +172,10 @@ struct VVRenderer {
     int raycast_mode = 1;                  // 1: sample-parallel pipeline (default), 0: one thread per ray
     int lic_ctas_per_sm = 0;               // 0: as many as are resident (occupancy query)
     int xf_enable = 1;                     // coordinate fast paths of the walk (XF_GUARD / XF_NSHARE): 0 = the clamping samplers (check)
-    int first_window = 8, window_growth = 200;    // depth windows of early-termination frames: first length, growth in percent
-                                                  // (measured, profiles/r02/ab10_window_schedules.log: cfg1 is flat between 8 and 32,
-                                                  // a surface-like frame such as cfg3o pays for every speculative sample: 1.17 ms at 8, 2.06 at 16)
+    int first_window = 2, window_growth = 300;    // depth windows of early-termination frames: first length, growth in percent: 2, 6, 18, 54 ...
+                                                  // (measured, profiles/r02/ab27_window_schedules_any_length.log: a surface-like frame such as
+                                                  // cfg3o pays for every speculative sample -- 1.12 ms with windows 8, 16, 32 ..., 0.40 ms with
+                                                  // 2, 6, 18 ...; cfg1, whose rays live ~17 samples, is flat: 1.63 vs 1.65 ms)
     int part_unit = 1;                     // VV_OPT_PARTITION_UNIT: the sort-first partition deals units of this many x this many blocks
     int depth_major = 1;                   // 1: bucket work items by (band, depth chunk) for L2 locality; 0: tile-major
     int band_rows = 4;                     // block rows per band (4 x 16 = 64 pixel rows)
@@ -762,7 +763,7 @@ static int render_sample_parallel(VVRenderer *r, DevParams &P)
     P.rayCk = r->rayCk.p;
     const int setup_grid = std::max(1, std::min((nTiles + 7) / 8, r->num_sms * 8));
     // depth windows: whole ray at once when no sample can trigger the early termination (and without the FBO nothing stops a slice
-    // from being blended), else 8, 16, 32, ... samples (VV_OPT_FIRST_WINDOW / VV_OPT_WINDOW_GROWTH): a window bounds the work done
+    // from being blended), else 2, 6, 18, ... samples (VV_OPT_FIRST_WINDOW / VV_OPT_WINDOW_GROWTH): a window bounds the work done
     // speculatively past a termination
     const bool windowed = P.slicing == 1 || (!P.slicing && termination_possible(r, derive_uniforms(r)));
     const int first_window = windowed ? r->first_window : 0x7fffffff;
@@ -807,7 +808,7 @@ static int render_sample_parallel(VVRenderer *r, DevParams &P)
     std::vector<int> w;
     w.push_back(0);
     if (!windowed) w.push_back(nmax);
-    else for (int len = first_window; w.back() < nmax; len = std::max(8, (len * r->window_growth / 100 + 7) & ~7)) w.push_back(std::min(nmax, w.back() + len));
+    else for (int len = first_window; w.back() < nmax; len = std::max(len + 1, len * r->window_growth / 100)) w.push_back(std::min(nmax, w.back() + len));
     w.push_back(w.back());   // sentinel: nothing after the last window
     if (w.size() > 3) { CU(r->items[1].ensure(rows)); CU(r->items[2].ensure(rows)); }
     const int comp_grid = setup_grid;
@@ -1333,7 +1334,7 @@ int vv_set_option(VVRenderer *r, int option, int value)
         if (value < 1 || value > 1024) return fail(VV_ERR_INVALID, "bad band rows");
         r->band_rows = value; break;
     case VV_OPT_FIRST_WINDOW:
-        if (value < 8 || value > 4096 || (value % 8)) return fail(VV_ERR_INVALID, "first window must be a multiple of 8 in 8..4096");
+        if (value < 1 || value > 4096) return fail(VV_ERR_INVALID, "first window must be 1..4096 samples");
         r->first_window = value; break;
     case VV_OPT_WINDOW_GROWTH:
         if (value < 100 || value > 400) return fail(VV_ERR_INVALID, "window growth must be 100..400 percent");
