@@ -928,6 +928,7 @@ __global__ void __launch_bounds__(256) composite_kernel(const __grid_constant__ 
         const uint2 tr = P.tileRec[lt];
         const int nmax = (int)tr.y;
         if (nmax <= P.win0) continue;                      // warp-uniform: nothing of this tile in the window
+        if (P.win0 > 0 && P.tileLive[lt] == 0u) continue;  // ... or every ray of the tile finished in an earlier window (no ray record is read)
         const int ray = lt * 32 + lane;
         const float4 A = P.rayA[ray];
         float4 B = P.rayB[ray];
