@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
     headers.append(os.path.join(HERE, "..", "include", "vv_c_api.h"))
     cpp = list(CPP_SOURCES) + [f for f in OPTIONAL_CPP if os.path.exists(os.path.join(CSRC, f))]
     defs = ["-DVV_HAVE_ILLUM_TABLES"] if "vv_illum.cpp" in cpp else []
-    objs = []
+    objs, jobs = [], []
     for src in CU_SOURCES + cpp:
         s = os.path.join(CSRC, src)
         o = os.path.join(objdir, src + ".o")
@@ -56,9 +56,17 @@ def build(force=False, verbose=False):
             cmd = [nvcc] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             if src.endswith(".cpp"):
                 cmd = [nvcc] + NVCC_FLAGS + defs + ["-x", "cu", "-c", s, "-o", o]
+            jobs.append(cmd)
+    if jobs:
+        # the translation units are independent: compile them side by side (vv_kernels.cu alone takes ~3 minutes)
+        from concurrent.futures import ThreadPoolExecutor
+
+        def run(cmd):
             if verbose:
                 print(" ".join(cmd))
             subprocess.check_call(cmd)
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            list(ex.map(run, jobs))
     if force or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lz", "-gencode", "arch=compute_100a,code=sm_100a"]
         if verbose:
